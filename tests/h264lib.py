@@ -1,0 +1,160 @@
+"""Test helpers: ctypes bindings for the CPU oracle (oracle/liboracle.so), the compiled reference
+behind its plain-C shim (oracle/_ref/librefshim.so, present only where the reference was built) and
+the product library (openh264_b200/libopenh264_b200.so).
+
+The oracle and the reference shim export the same signatures under the prefixes ``orc_`` / ``ref_``
+so a test can run both on identical buffers.
+"""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+REFSHIM_SO = os.path.join(ROOT, "oracle", "_ref", "librefshim.so")
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+BLK_DIMS = [(16, 16), (16, 8), (8, 16), (8, 8), (4, 4), (8, 4), (4, 8)]
+
+u8p = C.POINTER(C.c_uint8)
+i8p = C.POINTER(C.c_int8)
+i16p = C.POINTER(C.c_int16)
+u16p = C.POINTER(C.c_uint16)
+i32p = C.POINTER(C.c_int32)
+
+
+class MeJob(C.Structure):
+    _fields_ = [("blk", C.c_int32), ("cur_off", C.c_int32), ("ref_off", C.c_int32),
+                ("mvp_x", C.c_int16), ("mvp_y", C.c_int16),
+                ("mv_min_x", C.c_int16), ("mv_min_y", C.c_int16), ("mv_max_x", C.c_int16), ("mv_max_y", C.c_int16),
+                ("n_mvc", C.c_int32), ("mvc", (C.c_int16 * 2) * 5),
+                ("sad_pred", C.c_uint32), ("qp", C.c_int32), ("calc_satd", C.c_int32)]
+
+
+class MeResult(C.Structure):
+    _fields_ = [("mv_x", C.c_int16), ("mv_y", C.c_int16), ("sad_cost", C.c_uint32), ("satd_cost", C.c_uint32),
+                ("ref_off", C.c_int32)]
+
+
+# name -> (restype, argtypes) shared by orc_* and ref_*
+SIGS = {
+    "sad": (C.c_int32, [C.c_int, u8p, C.c_int, u8p, C.c_int]),
+    "sad_four": (None, [C.c_int, u8p, C.c_int, u8p, C.c_int, i32p]),
+    "satd": (C.c_int32, [C.c_int, u8p, C.c_int, u8p, C.c_int]),
+    "mc_luma": (None, [u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mc_chroma": (None, [u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "pixel_avg": (None, [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int]),
+    "dct4x4": (None, [i16p, u8p, C.c_int, u8p, C.c_int]),
+    "dct_four4x4": (None, [i16p, u8p, C.c_int, u8p, C.c_int]),
+    "quant4x4": (None, [i16p, i16p, i16p]),
+    "quant4x4_dc": (None, [i16p, C.c_int16, C.c_int16]),
+    "quant_four4x4": (None, [i16p, i16p, i16p]),
+    "quant_four4x4_max": (None, [i16p, i16p, i16p, i16p]),
+    "hadamard_quant2x2_skip": (C.c_int32, [i16p, C.c_int16, C.c_int16]),
+    "hadamard_quant2x2": (C.c_int32, [i16p, C.c_int16, C.c_int16, i16p, i16p]),
+    "hadamard_t4_dc": (None, [i16p, i16p]),
+    "scan4x4_dcac": (None, [i16p, i16p]),
+    "scan4x4_ac": (None, [i16p, i16p]),
+    "single_ctr4x4": (C.c_int32, [i16p]),
+    "nonzero_count": (C.c_int32, [i16p]),
+    "ihadamard4x4_dc": (None, [i16p]),
+    "dequant_luma_dc4x4": (None, [i16p, C.c_int]),
+    "dequant_ihadamard4x4": (None, [i16p, C.c_uint16]),
+    "dequant_ihadamard2x2_dc": (None, [i16p, C.c_uint16]),
+    "dequant4x4": (None, [i16p, u16p]),
+    "dequant_four4x4": (None, [i16p, u16p]),
+    "idct4x4_rec": (None, [u8p, C.c_int, u8p, C.c_int, i16p]),
+    "idct_four4x4_rec": (None, [u8p, C.c_int, u8p, C.c_int, i16p]),
+    "idct_rec_i16x16_dc": (None, [u8p, C.c_int, u8p, C.c_int, i16p]),
+    "idct_res_add_pred": (None, [u8p, C.c_int, i16p]),
+    "idct_res_add_pred8x8": (None, [u8p, C.c_int, i16p]),
+    "deblock_luma_lt4": (None, [u8p, C.c_int, C.c_int, C.c_int, C.c_int, i8p]),
+    "deblock_luma_eq4": (None, [u8p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "deblock_chroma_lt4": (None, [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, i8p]),
+    "deblock_chroma_eq4": (None, [u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "expand_plane": (None, [u8p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "me_search": (None, [u8p, C.c_int, u8p, C.c_int, C.POINTER(MeJob), C.POINTER(MeResult)]),
+    "quant_ff": (i16p, [C.c_int]),
+    "quant_mf": (i16p, [C.c_int]),
+    "dequant_coeff": (u16p, [C.c_int]),
+    "qp_lambda": (C.c_int, [C.c_int]),
+    "chroma_qp": (C.c_int, [C.c_int]),
+}
+
+
+class _Lib:
+    def __init__(self, path, prefix):
+        self.lib = C.CDLL(path)
+        self.prefix = prefix
+        for name, (res, args) in SIGS.items():
+            fn = getattr(self.lib, prefix + name)
+            fn.restype = res
+            fn.argtypes = args
+            setattr(self, name, fn)
+
+
+def build_oracle():
+    """(Re)build oracle/liboracle.so from the C restatement (seconds, gcc only)."""
+    subprocess.check_call(["make", "-s", "-f", "oracle/Makefile"], cwd=ROOT)
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        build_oracle()
+        _oracle = _Lib(ORACLE_SO, "orc_")
+        _oracle.lib.orc_mvd_cost_init.argtypes = [u16p, C.c_int, C.c_int]
+        _oracle.lib.orc_mvd_cost_init.restype = None
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(REFSHIM_SO)
+
+
+def ref():
+    global _ref
+    if _ref is None:
+        _ref = _Lib(REFSHIM_SO, "ref_")
+        _ref.lib.ref_mvd_cost_init_all.argtypes = [u16p, C.c_int]
+        _ref.lib.ref_halfpel.argtypes = [C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int]
+    return _ref
+
+
+def ptr(a, ct=None, off=0):
+    """ctypes pointer into a numpy array at element offset `off`."""
+    if ct is None:
+        ct = {np.dtype(np.uint8): C.c_uint8, np.dtype(np.int8): C.c_int8, np.dtype(np.int16): C.c_int16,
+              np.dtype(np.uint16): C.c_uint16, np.dtype(np.int32): C.c_int32}[a.dtype]
+    return C.cast(a.ctypes.data + off * a.itemsize, C.POINTER(ct))
+
+
+def sha1(*arrays):
+    h = hashlib.sha1()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def synth_frame(w, h, t=0, seed=264):
+    """Deterministic natural-ish luma frame: smooth multi-octave pattern + moving rectangles +
+    small per-frame noise, global pan (+3,+1)/frame (SURVEY §8(d) generator, numpy form)."""
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.int64)
+    px, py = xx + 3 * t, yy + 1 * t
+    v = (128 + 40 * np.sin(px / 37.0) + 30 * np.cos(py / 23.0) + 20 * np.sin((px + py) / 11.0)
+         + 12 * np.sin(px / 5.0) * np.cos(py / 7.0))
+    for k in range(8):
+        rx = (k * 211 + 5 * t * (k % 3 + 1)) % max(1, w - 64)
+        ry = (k * 97 + 3 * t * (k % 2 + 1)) % max(1, h - 48)
+        blk = ((xx[ry:ry + 48, rx:rx + 64] * (k + 3) + yy[ry:ry + 48, rx:rx + 64] * (k + 1)) % 64) + 60 + 10 * k
+        v[ry:ry + 48, rx:rx + 64] = blk
+    rng = np.random.RandomState(seed + t)
+    v = v + rng.randint(-3, 4, size=(h, w))
+    return np.clip(v, 16, 235).astype(np.uint8)

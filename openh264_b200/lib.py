@@ -1,0 +1,156 @@
+"""ctypes binding of libopenh264_b200.so (include/b2h264.h).  No CPU fallback: `load()` raises if the
+library has not been built, and every call raises B2H264Error on a non-zero CUDA status."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libopenh264_b200.so")
+
+u8p, i8p = C.POINTER(C.c_uint8), C.POINTER(C.c_int8)
+i16p, u16p, i32p = C.POINTER(C.c_int16), C.POINTER(C.c_uint16), C.POINTER(C.c_int32)
+vp = C.c_void_p
+
+
+class B2H264Error(RuntimeError):
+    pass
+
+
+class EdgeJob(C.Structure):
+    _fields_ = [("off", C.c_int32), ("sx", C.c_int32), ("sy", C.c_int32), ("alpha", C.c_int16), ("beta", C.c_int16),
+                ("tc", C.c_int8 * 4), ("strong", C.c_int32)]
+
+
+class MeJob(C.Structure):
+    _fields_ = [("blk", C.c_int32), ("cur_off", C.c_int32), ("ref_off", C.c_int32),
+                ("mvp_x", C.c_int16), ("mvp_y", C.c_int16),
+                ("mv_min_x", C.c_int16), ("mv_min_y", C.c_int16), ("mv_max_x", C.c_int16), ("mv_max_y", C.c_int16),
+                ("n_mvc", C.c_int32), ("mvc", (C.c_int16 * 2) * 5),
+                ("sad_pred", C.c_uint32), ("qp", C.c_int32), ("calc_satd", C.c_int32)]
+
+
+class MeResult(C.Structure):
+    _fields_ = [("mv_x", C.c_int16), ("mv_y", C.c_int16), ("sad_cost", C.c_uint32), ("satd_cost", C.c_uint32),
+                ("ref_off", C.c_int32)]
+
+
+# every symbol include/b2h264.h declares: name -> argtypes (restype int unless noted)
+API = {
+    "b2h264_init": [C.c_int],
+    "b2h264_abi_version": [],
+    "b2h264_dev_malloc": [C.POINTER(vp), C.c_size_t],
+    "b2h264_dev_free": [vp],
+    "b2h264_h2d": [vp, vp, C.c_size_t, vp],
+    "b2h264_d2h": [vp, vp, C.c_size_t, vp],
+    "b2h264_sync": [vp],
+    "b2h264_error_string": [C.c_int],
+    "b2h264_launch_count": [],
+    "b2h264_k_sad": [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, C.c_int, vp, vp, vp, vp],
+    "b2h264_k_mc_luma": [vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp],
+    "b2h264_k_mc_chroma": [vp, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, vp, vp],
+    "b2h264_k_halfpel": [C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp],
+    "b2h264_k_pixel_avg": [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, vp],
+    "b2h264_k_dct_four4x4": [vp, C.c_int, vp, vp, C.c_int, vp, C.c_int, vp, vp],
+    "b2h264_k_quant_four4x4": [vp, C.c_int, C.c_int, C.c_int, vp, vp],
+    "b2h264_k_quant4x4_dc": [vp, C.c_int, C.c_int, C.c_int, vp],
+    "b2h264_k_hadamard_quant2x2": [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp],
+    "b2h264_k_hadamard_t4_dc": [vp, C.c_int, vp, vp],
+    "b2h264_k_scan4x4": [vp, C.c_int, vp, vp, vp, vp],
+    "b2h264_k_dequant_four4x4": [vp, C.c_int, C.c_int, vp],
+    "b2h264_k_dequant_ihadamard4x4": [vp, C.c_int, C.c_int, vp],
+    "b2h264_k_dequant_luma_dc": [vp, C.c_int, C.c_int, vp],
+    "b2h264_k_dequant_ihadamard2x2": [vp, C.c_int, C.c_int, vp],
+    "b2h264_k_idct_four4x4_rec": [vp, C.c_int, vp, vp, C.c_int, vp, vp],
+    "b2h264_k_idct_rec_i16x16_dc": [vp, C.c_int, vp, vp, C.c_int, vp, vp],
+    "b2h264_k_idct_res_add_pred": [vp, C.c_int, vp, vp, C.c_int, C.c_int, vp],
+    "b2h264_k_deblock_luma": [vp, vp, C.c_int, vp],
+    "b2h264_k_deblock_chroma": [vp, vp, vp, C.c_int, vp],
+    "b2h264_k_expand_plane": [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
+    "b2h264_k_me_search": [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp],
+    "b2h264_k_mc_sad": [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp],
+    "b2h264_table_quant_ff": [C.c_int],
+    "b2h264_table_quant_mf": [C.c_int],
+    "b2h264_table_dequant": [C.c_int],
+    "b2h264_table_lambda": [C.c_int],
+    "b2h264_table_chroma_qp": [C.c_int],
+}
+_RESTYPES = {"b2h264_error_string": C.c_char_p, "b2h264_launch_count": C.c_ulonglong,
+             "b2h264_table_quant_ff": i16p, "b2h264_table_quant_mf": i16p, "b2h264_table_dequant": u16p}
+
+_lib = None
+_inited = False
+
+
+def build(verbose=False):
+    """Compile libopenh264_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-C", os.path.join(HERE, "csrc"), "-j", "8"] + ([] if verbose else ["-s"]))
+
+
+def load():
+    """dlopen the product library; raises if it is not built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise B2H264Error(f"{SO_PATH} is missing: run openh264_b200.build() / make -C openh264_b200/csrc")
+        L = C.CDLL(SO_PATH)
+        for name, args in API.items():
+            fn = getattr(L, name)           # AttributeError here = header/library mismatch
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, C.c_int)
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise B2H264Error(f"CUDA error {rc}: {load().b2h264_error_string(rc).decode()}")
+
+
+def lib(device=0):
+    """Loaded library with the device selected and the constant tables uploaded."""
+    global _inited
+    L = load()
+    if not _inited:
+        check(L.b2h264_init(device))
+        _inited = True
+    return L
+
+
+class DeviceArray:
+    """A numpy-shaped buffer in HBM (cudaMalloc through the C-ABI; + slack so word loads stay in bounds)."""
+
+    def __init__(self, arr=None, shape=None, dtype=None):
+        L = lib()
+        if arr is not None:
+            arr = np.ascontiguousarray(arr)
+            shape, dtype = arr.shape, arr.dtype
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = vp()
+        check(L.b2h264_dev_malloc(C.byref(p), self.nbytes + 64))
+        self.ptr = p.value
+        if arr is not None:
+            check(L.b2h264_h2d(self.ptr, arr.ctypes.data, self.nbytes, None))
+            check(L.b2h264_sync(None))
+
+    def at(self, byte_off):
+        return self.ptr + byte_off
+
+    def get(self):
+        out = np.empty(self.shape, self.dtype)
+        check(load().b2h264_d2h(out.ctypes.data, self.ptr, self.nbytes, None))
+        check(load().b2h264_sync(None))
+        return out
+
+    def free(self):
+        if self.ptr:
+            load().b2h264_dev_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -5,4 +5,4 @@ code, sources under ``openh264_b200/csrc``, headers under ``include/``).  This P
 thin ctypes mirror used by the tests and the benchmark; it never computes anything itself and it
 fails loudly when the CUDA library is missing (there is no CPU fallback).
 """
-from .lib import B2H264Error, DeviceArray, build, lib, load  # noqa: F401
+from .binding import B2H264Error, DeviceArray, build, lib, load  # noqa: F401

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 import openh264_b200 as m
-from openh264_b200.lib import check
+from openh264_b200.binding import check
 import h264lib
 
 L = m.lib(0)

@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported(L):
 
 
 def test_python_binding_covers_header():
-    from openh264_b200.lib import API
+    from openh264_b200.binding import API
     assert set(n for n in declared_symbols() if n.startswith("b2h264_")) <= set(API)
 
 

@@ -19,7 +19,7 @@ H, STRIDE = 96, 128
 @pytest.fixture(scope="module")
 def env():
     import openh264_b200 as m
-    from openh264_b200 import lib as libmod
+    from openh264_b200 import binding as libmod
     L = m.lib(0)
     return m, libmod, L, h264lib.oracle()
 
@@ -274,7 +274,7 @@ def test_idct_res_add_pred(env, size):
 
 
 def test_deblock_filters(env):
-    from openh264_b200.lib import EdgeJob
+    from openh264_b200.binding import EdgeJob
     m, lm, L, orc = env
     rng = np.random.RandomState(77)
     base = rng.randint(40, 200, size=(H // 16, STRIDE // 16)).repeat(16, 0).repeat(16, 1)
@@ -344,7 +344,7 @@ def _padded_pair(w, h, pad=32):
 
 @pytest.mark.parametrize("calc_satd", [0, 1])
 def test_me_search(env, calc_satd):
-    from openh264_b200.lib import MeJob as GJob, MeResult as GRes
+    from openh264_b200.binding import MeJob as GJob, MeResult as GRes
     m, lm, L, orc = env
     w, h = 320, 192
     cur, ref, stride, pad = _padded_pair(w, h)

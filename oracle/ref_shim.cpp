@@ -189,3 +189,157 @@ void ref_me_search (const uint8_t* cur, int cs, const uint8_t* ref, int rs, cons
 }
 
 } // extern "C"
+
+/* ------------------------------------------------------------------------------------------------
+ * Frame-level drivers through the reference's own PUBLIC API (codec_api.h): used as the end-to-end
+ * oracle (bitstream / YUV parity) and as the CPU baseline ("kind": "reference").
+ * ---------------------------------------------------------------------------------------------- */
+#include "codec_api.h"
+#include <time.h>
+
+static double now_s() { struct timespec t; clock_gettime (CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
+extern "C" {
+
+/* Encode n I420 frames (tightly packed w*h*3/2 each) at constant QP, camera mode, single layer, CAVLC,
+ * deblock on, no denoise/BGD/AQ/scene-change/LTR, IDR only at frame 0 — the configuration of
+ * BASELINE.md configs 2/3.  complexity: 0 low, 1 medium, 2 high.  threads = iMultipleThreadIdc
+ * (1 = single thread, single slice; >1 = that many fixed slices + threads: a speed reference only,
+ * it changes the bitstream).  Returns total bytes written to out (or <0 on error); seconds spent in
+ * EncodeFrame in *enc_seconds; per-frame byte counts in frame_bytes[n]. */
+long ref_encode (const uint8_t* yuv, int w, int h, int n, int qp, int complexity, int threads, float fps,
+                 uint8_t* out, long out_cap, int32_t* frame_bytes, double* enc_seconds) {
+  ISVCEncoder* enc = NULL;
+  if (WelsCreateSVCEncoder (&enc) || !enc) return -1;
+  SEncParamExt p;
+  enc->GetDefaultParams (&p);
+  p.iUsageType = CAMERA_VIDEO_REAL_TIME;
+  p.iPicWidth = w; p.iPicHeight = h;
+  p.iTargetBitrate = 5000000;
+  p.iRCMode = RC_OFF_MODE;
+  p.fMaxFrameRate = fps;
+  p.iTemporalLayerNum = 1;
+  p.iSpatialLayerNum = 1;
+  p.iComplexityMode = (ECOMPLEXITY_MODE) complexity;
+  p.uiIntraPeriod = 0;
+  p.iNumRefFrame = 1;
+  p.iEntropyCodingModeFlag = 0;
+  p.bEnableFrameSkip = false;
+  p.bEnableLongTermReference = false;
+  p.iMultipleThreadIdc = (unsigned short) threads;
+  p.iLoopFilterDisableIdc = 0;
+  p.bEnableDenoise = false;
+  p.bEnableBackgroundDetection = false;
+  p.bEnableAdaptiveQuant = false;
+  p.bEnableFrameCroppingFlag = true;
+  p.bEnableSceneChangeDetect = false;
+  p.sSpatialLayers[0].iVideoWidth = w;
+  p.sSpatialLayers[0].iVideoHeight = h;
+  p.sSpatialLayers[0].fFrameRate = fps;
+  p.sSpatialLayers[0].iSpatialBitrate = 5000000;
+  p.sSpatialLayers[0].iDLayerQp = qp;
+  p.sSpatialLayers[0].uiProfileIdc = PRO_BASELINE;
+  if (threads > 1) {
+    p.sSpatialLayers[0].sSliceArgument.uiSliceMode = SM_FIXEDSLCNUM_SLICE;
+    p.sSpatialLayers[0].sSliceArgument.uiSliceNum = threads;
+  } else {
+    p.sSpatialLayers[0].sSliceArgument.uiSliceMode = SM_SINGLE_SLICE;
+  }
+  if (enc->InitializeExt (&p)) { WelsDestroySVCEncoder (enc); return -2; }
+  int lvl = WELS_LOG_QUIET;
+  enc->SetOption (ENCODER_OPTION_TRACE_LEVEL, &lvl);
+  long total = 0;
+  double secs = 0;
+  const size_t fsz = (size_t) w * h * 3 / 2;
+  for (int i = 0; i < n; i++) {
+    SSourcePicture pic;
+    memset (&pic, 0, sizeof (pic));
+    pic.iColorFormat = videoFormatI420;
+    pic.iPicWidth = w; pic.iPicHeight = h;
+    pic.iStride[0] = w; pic.iStride[1] = pic.iStride[2] = w / 2;
+    pic.pData[0] = (uint8_t*) yuv + i * fsz;
+    pic.pData[1] = pic.pData[0] + (size_t) w * h;
+    pic.pData[2] = pic.pData[1] + (size_t) w * h / 4;
+    pic.uiTimeStamp = (long long) (i * 1000.0 / fps);
+    SFrameBSInfo info;
+    memset (&info, 0, sizeof (info));
+    const double t0 = now_s();
+    const int rc = enc->EncodeFrame (&pic, &info);
+    secs += now_s() - t0;
+    if (rc) { WelsDestroySVCEncoder (enc); return -3; }
+    int fb = 0;
+    if (info.eFrameType != videoFrameTypeSkip) {
+      for (int l = 0; l < info.iLayerNum; l++) {
+        int sz = 0;
+        for (int k = 0; k < info.sLayerInfo[l].iNalCount; k++) sz += info.sLayerInfo[l].pNalLengthInByte[k];
+        if (total + sz > out_cap) { WelsDestroySVCEncoder (enc); return -4; }
+        memcpy (out + total, info.sLayerInfo[l].pBsBuf, sz);
+        total += sz; fb += sz;
+      }
+    }
+    if (frame_bytes) frame_bytes[i] = fb;
+  }
+  if (enc_seconds) *enc_seconds = secs;
+  enc->Uninitialize();
+  WelsDestroySVCEncoder (enc);
+  return total;
+}
+
+/* Decode an Annex-B stream; writes cropped I420 frames back to back into out. Returns frame count
+ * (or <0); *w,*h = picture size; seconds in the decode calls in *dec_seconds. */
+int ref_decode (const uint8_t* bs, long len, uint8_t* out, long out_cap, int* w, int* h, double* dec_seconds) {
+  ISVCDecoder* dec = NULL;
+  if (WelsCreateDecoder (&dec) || !dec) return -1;
+  SDecodingParam dp;
+  memset (&dp, 0, sizeof (dp));
+  dp.sVideoProperty.eVideoBsType = VIDEO_BITSTREAM_AVC;
+  dp.eEcActiveIdc = ERROR_CON_DISABLE;
+  if (dec->Initialize (&dp)) { WelsDestroyDecoder (dec); return -2; }
+  int lvl = WELS_LOG_QUIET;
+  dec->SetOption (DECODER_OPTION_TRACE_LEVEL, &lvl);
+  long pos = 0, outpos = 0;
+  int frames = 0;
+  double secs = 0;
+  auto emit = [&] (uint8_t** d, SBufferInfo& bi) {
+    if (bi.iBufferStatus != 1) return;
+    const int W = bi.UsrData.sSystemBuffer.iWidth, H = bi.UsrData.sSystemBuffer.iHeight;
+    *w = W; *h = H;
+    if (outpos + (long) W * H * 3 / 2 > out_cap) return;
+    for (int pl = 0; pl < 3; pl++) {
+      const int pw = pl ? W / 2 : W, ph = pl ? H / 2 : H, st = bi.UsrData.sSystemBuffer.iStride[pl ? 1 : 0];
+      for (int y = 0; y < ph; y++) { memcpy (out + outpos, d[pl] + (size_t) y * st, pw); outpos += pw; }
+    }
+    frames++;
+  };
+  while (pos < len) {
+    /* next access-unit chunk: up to the next start code that follows at least one slice NAL */
+    long end = pos + 4;
+    while (end + 4 <= len && ! (bs[end] == 0 && bs[end + 1] == 0 && bs[end + 2] == 0 && bs[end + 3] == 1)) end++;
+    if (end + 4 > len) end = len;
+    uint8_t* d[3] = {0, 0, 0};
+    SBufferInfo bi;
+    memset (&bi, 0, sizeof (bi));
+    const double t0 = now_s();
+    dec->DecodeFrameNoDelay (bs + pos, (int) (end - pos), d, &bi);
+    secs += now_s() - t0;
+    emit (d, bi);
+    pos = end;
+  }
+  for (;;) {
+    int32_t remain = 0;
+    dec->GetOption (DECODER_OPTION_NUM_OF_FRAMES_REMAINING_IN_BUFFER, &remain);
+    if (remain <= 0) break;
+    uint8_t* d[3] = {0, 0, 0};
+    SBufferInfo bi;
+    memset (&bi, 0, sizeof (bi));
+    dec->FlushFrame (d, &bi);
+    if (bi.iBufferStatus != 1) break;
+    emit (d, bi);
+  }
+  if (dec_seconds) *dec_seconds = secs;
+  dec->Uninitialize();
+  WelsDestroyDecoder (dec);
+  return frames;
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// enc_host.cpp — see enc_host.h.
+#include "enc_host.h"
+
+#include <string.h>
+
+namespace b2h264 {
+
+void StreamCtl::init(int width, int height, int qp, float fps_, int target_bitrate) {
+  memset(&sp, 0, sizeof(sp));
+  sp.width = width; sp.height = height;
+  sp.mb_w = (width + 15) >> 4; sp.mb_h = (height + 15) >> 4;
+  sp.num_ref_frames = 1;
+  sp.qp = qp;
+  fps = fps_;
+  select_level(&sp, fps_, target_bitrate);
+  // WelsGetPaddingOffset (au_set.cpp:476): crop offsets in units of 2 luma samples, right/bottom only
+  sp.crop = (sp.mb_w * 16 != width) || (sp.mb_h * 16 != height);
+  sp.crop_right = (sp.mb_w * 16 - width) / 2;
+  sp.crop_bottom = (sp.mb_h * 16 - height) / 2;
+  frame_num = 0; idr_pic_id = 0; frames_coded = 0; force_idr = true;
+}
+
+EncFrameParams StreamCtl::frame_params(bool idr, bool ref_is_p) const {
+  EncFrameParams p;
+  memset(&p, 0, sizeof(p));
+  p.mb_w = sp.mb_w; p.mb_h = sp.mb_h;
+  p.cur_stride_y = sp.mb_w * 16; p.cur_stride_c = sp.mb_w * 8;
+  p.rec_stride_y = rec_stride_y(); p.rec_stride_c = rec_stride_c();
+  p.qp = sp.qp;
+  p.is_idr = idr;
+  // GetMvMvdRange (encoder_ext.cpp:1508): min(level vertical MV limit / 4, CAMERA_STARTMV_RANGE = 64)
+  p.mv_range = sp.level_idc <= 10 ? 63 : 64;
+  p.ref_is_p = ref_is_p;
+  return p;
+}
+
+void StreamCtl::write_access_unit(bool idr, const MbOut* mbs, std::vector<uint8_t>* au) {
+  std::vector<uint8_t> rbsp;
+  if (idr) {
+    idr_pic_id = idr_pic_id < 65535 ? idr_pic_id + 1 : 0;
+    frame_num = 0;
+    write_sps(sp, &rbsp); append_nal(au, 3, 7, rbsp); rbsp.clear();
+    write_pps(sp, &rbsp); append_nal(au, 3, 8, rbsp); rbsp.clear();
+  }
+  SliceState ss;
+  ss.idr = idr; ss.frame_num = frame_num; ss.idr_pic_id = idr_pic_id; ss.qp = sp.qp;
+  write_slice(sp, ss, mbs, &rbsp);
+  append_nal(au, 3, idr ? 5 : 1, rbsp);
+  frame_num = (frame_num + 1) & 0x7fff;
+  frames_coded++;
+  force_idr = false;
+}
+
+void pad_source(const uint8_t* yuv, int w, int h, int mb_w, int mb_h, uint8_t* y, uint8_t* u, uint8_t* v) {
+  const int W = mb_w * 16, H = mb_h * 16, cw = w / 2, ch = h / 2, CW = W / 2, CH = H / 2;
+  const uint8_t* sy = yuv;
+  const uint8_t* su = yuv + (size_t)w * h;
+  const uint8_t* sv = su + (size_t)cw * ch;
+  for (int r = 0; r < H; r++) {
+    if (r < h) { memcpy(y + (size_t)r * W, sy + (size_t)r * w, w); memset(y + (size_t)r * W + w, 0, W - w); }
+    else memset(y + (size_t)r * W, 0, W);
+  }
+  for (int r = 0; r < CH; r++) {
+    if (r < ch) {
+      memcpy(u + (size_t)r * CW, su + (size_t)r * cw, cw); memset(u + (size_t)r * CW + cw, 0x80, CW - cw);
+      memcpy(v + (size_t)r * CW, sv + (size_t)r * cw, cw); memset(v + (size_t)r * CW + cw, 0x80, CW - cw);
+    } else { memset(u + (size_t)r * CW, 0x80, CW); memset(v + (size_t)r * CW, 0x80, CW); }
+  }
+}
+
+}  // namespace b2h264

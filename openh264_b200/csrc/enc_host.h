@@ -1,0 +1,39 @@
+// enc_host.h — host-side stream control for one encoder instance: parameter sets, frame numbering,
+// slice serialisation from the device's MbOut records.  Mirrors the small part of
+// codec/encoder/core/src/encoder_ext.cpp (WelsEncoderEncodeExt :3441, frame_num / idr_pic_id handling
+// :3131,:3253) that the supported configuration exercises: CAMERA_VIDEO_REAL_TIME, 1 spatial + 1
+// temporal layer, RC_OFF_MODE, SM_SINGLE_SLICE, CAVLC, 1 reference frame, IDR only at the start
+// (uiIntraPeriod = 0) or on ForceIntraFrame.
+#pragma once
+#include <vector>
+
+#include "enc_types.h"
+#include "h264_bitstream.h"
+
+namespace b2h264 {
+
+struct StreamCtl {
+  StreamParams sp;
+  float fps;
+  int frame_num = 0;
+  int idr_pic_id = 0;
+  long frames_coded = 0;
+  bool force_idr = true;
+
+  void init(int width, int height, int qp, float fps_, int target_bitrate);
+  bool next_is_idr() const { return force_idr; }
+  // geometry of the padded pictures (picture_handle.cpp:60-85: 32-pixel luma padding)
+  int rec_stride_y() const { return sp.mb_w * 16 + 64; }
+  int rec_stride_c() const { return sp.mb_w * 8 + 32; }
+  int rec_rows_y() const { return sp.mb_h * 16 + 64; }
+  int rec_rows_c() const { return sp.mb_h * 8 + 32; }
+  EncFrameParams frame_params(bool idr, bool ref_is_p) const;
+  // serialises the access unit of the frame just coded (SPS+PPS+IDR slice, or P slice)
+  void write_access_unit(bool idr, const MbOut* mbs, std::vector<uint8_t>* au);
+};
+
+// copies a w x h I420 picture into MB-aligned planes; rows/cols beyond the picture are 0 (luma) / 0x80
+// (chroma) like CWelsPreProcess::Padding (wels_preprocess.cpp:1250)
+void pad_source(const uint8_t* yuv, int w, int h, int mb_w, int mb_h, uint8_t* y, uint8_t* u, uint8_t* v);
+
+}  // namespace b2h264

@@ -1,0 +1,413 @@
+// enc_mb.cuh — one macroblock, one warp: scratch layout, neighbour plumbing, intra mode decision and
+// intra residual coding.  (Inter: enc_inter.cuh.)  See enc_intra.cuh for the reference map.
+#pragma once
+#include "enc_intra.cuh"
+#include "enc_types.h"
+
+namespace mbk {
+
+// Per-warp working set (shared memory on the device, a plain struct in the host emulation build).
+struct MbScratch {
+  RecTile tile;                 // reconstruction tile incl. neighbour samples
+  uint8_t cur_y[256];           // current MB, stride 16
+  uint8_t cur_c[128];           // Cb 0..63, Cr 64..127, stride 8
+  uint8_t pred_y[2][256];       // luma prediction ping-pong (pMemPredMb)
+  uint8_t pred_c[2][128];       // chroma prediction ping-pong (Cb, Cr)
+  uint8_t skip_pred[384];       // P-skip prediction (pSkipMb): Y 256, Cb 64, Cr 64
+  uint8_t me_buf[4][17 * 32];   // fractional-refinement candidates (pBufferInterPredMe)
+  int16_t coef[384];            // pCoeffLevel: transform coefficients (coding order, 16 per 4x4)
+  int16_t dc16[16];
+  int8_t  i4m[25];              // intra4x4 mode cache: (by+1)*5+(bx+1), -1 = unavailable
+  int16_t mvc[30][2];           // motion vector cache (6 wide: col 0 = left MB, row 0 = top MBs)
+  int8_t  refc[30];             // reference index cache (REF_NOT_AVAIL -2 / REF_NOT_IN_LIST -1)
+  int32_t sadc[4];              // neighbour SAD costs (topleft, top, topright, left)
+  int32_t sad_skip[4];
+  int8_t  skip_flag[4];
+  MbOut   out;                  // staged output record
+  MbInfo  info;                 // staged MbInfo
+  int32_t red[32];              // small scratch
+};
+
+struct MbCtx {
+  EncFrameParams p;
+  EncFramePtrs f;
+  int mbx, mby, nb;             // position, neighbour availability (NB_*)
+  int qp, qp_c, lambda;
+};
+
+// position of 4x4 block k (coding / z order) in units of 4 pixels
+MBK_HD int blk_x(int k) { return (k & 1) | ((k >> 1) & 2); }
+MBK_HD int blk_y(int k) { return ((k >> 1) & 1) | ((k >> 2) & 2); }
+MBK_HD int blk_raster(int k) { return blk_y(k) * 4 + blk_x(k); }
+
+// loads from memory written by OTHER warps (previous MB row): bypass L1 on the device
+MBK_HD uint8_t ld_cg_u8(const uint8_t* p) {
+#ifdef __CUDA_ARCH__
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
+
+// ---- MB setup ------------------------------------------------------------------------------------
+MBK_HD void mb_load_cur(const MbCtx& c, MbScratch& s) {
+  const uint8_t* y = c.f.cur[0] + (size_t)(c.mby * 16) * c.p.cur_stride_y + c.mbx * 16;
+  for (int i = lane_id(); i < 64; i += MBK_WS) {
+    const int r = i >> 2, c4 = (i & 3) << 2;
+    *reinterpret_cast<uint32_t*>(s.cur_y + r * 16 + c4) = *reinterpret_cast<const uint32_t*>(y + (size_t)r * c.p.cur_stride_y + c4);
+  }
+  for (int i = lane_id(); i < 32; i += MBK_WS) {
+    const int pl = i >> 4, r = (i >> 1) & 7, c4 = (i & 1) << 2;
+    const uint8_t* src = c.f.cur[1 + pl] + (size_t)(c.mby * 8 + r) * c.p.cur_stride_c + c.mbx * 8 + c4;
+    *reinterpret_cast<uint32_t*>(s.cur_c + pl * 64 + r * 8 + c4) = *reinterpret_cast<const uint32_t*>(src);
+  }
+  warp_sync();
+}
+
+// neighbour samples into the tile borders.  Left column / top-left come from the tile of the previous
+// MB of this row (same warp); the top row comes from the picture (row above, other warp).
+MBK_HD void mb_load_borders(const MbCtx& c, MbScratch& s) {
+  RecTile& t = s.tile;
+  // left: column 15 of the previous tile -> column -1 (before the tile is overwritten)
+  for (int i = lane_id(); i < 32; i += MBK_WS) {
+    if (i < 16) *tile_y(t, -1, i) = (c.nb & NB_LEFT) ? *tile_y(t, 15, i) : 0;
+    else if (i < 24) *tile_c(t.u, -1, i - 16) = (c.nb & NB_LEFT) ? *tile_c(t.u, 7, i - 16) : 0;
+    else *tile_c(t.v, -1, i - 24) = (c.nb & NB_LEFT) ? *tile_c(t.v, 7, i - 24) : 0;
+  }
+  warp_sync();
+  if (c.nb & (NB_TOP | NB_TOPLEFT | NB_TOPRIGHT)) {
+    const uint8_t* ry = c.f.rec[0] + (ptrdiff_t)(c.mby * 16 - 1) * c.p.rec_stride_y + c.mbx * 16;
+    const uint8_t* ru = c.f.rec[1] + (ptrdiff_t)(c.mby * 8 - 1) * c.p.rec_stride_c + c.mbx * 8;
+    const uint8_t* rv = c.f.rec[2] + (ptrdiff_t)(c.mby * 8 - 1) * c.p.rec_stride_c + c.mbx * 8;
+    for (int i = lane_id(); i < 25 + 9 + 9; i += MBK_WS) {
+      if (i < 25) {             // x = -1 .. 23
+        const int x = i - 1;
+        const bool ok = x < 0 ? (c.nb & NB_TOPLEFT) : x < 16 ? (c.nb & NB_TOP) : (c.nb & NB_TOPRIGHT);
+        *tile_y(t, x, -1) = ok ? ld_cg_u8(ry + x) : 0;
+      } else if (i < 34) {
+        const int x = i - 26;
+        const bool ok = x < 0 ? (c.nb & NB_TOPLEFT) : (c.nb & NB_TOP);
+        *tile_c(t.u, x, -1) = ok ? ld_cg_u8(ru + x) : 0;
+      } else {
+        const int x = i - 35;
+        const bool ok = x < 0 ? (c.nb & NB_TOPLEFT) : (c.nb & NB_TOP);
+        *tile_c(t.v, x, -1) = ok ? ld_cg_u8(rv + x) : 0;
+      }
+    }
+  }
+  warp_sync();
+}
+
+// reconstructed tile -> picture
+MBK_HD void mb_store_recon(const MbCtx& c, MbScratch& s) {
+  uint8_t* ry = c.f.rec[0] + (size_t)(c.mby * 16) * c.p.rec_stride_y + c.mbx * 16;
+  for (int i = lane_id(); i < 64; i += MBK_WS) {
+    const int r = i >> 2, c4 = (i & 3) << 2;
+    const uint8_t* src = tile_y(s.tile, c4, r);
+    *reinterpret_cast<uint32_t*>(ry + (size_t)r * c.p.rec_stride_y + c4) =
+        (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24);
+  }
+  for (int i = lane_id(); i < 32; i += MBK_WS) {
+    const int pl = i >> 4, r = (i >> 1) & 7, c4 = (i & 1) << 2;
+    const uint8_t* src = tile_c(pl ? s.tile.v : s.tile.u, c4, r);
+    uint8_t* dst = c.f.rec[1 + pl] + (size_t)(c.mby * 8 + r) * c.p.rec_stride_c + c.mbx * 8 + c4;
+    *reinterpret_cast<uint32_t*>(dst) = (uint32_t)src[0] | ((uint32_t)src[1] << 8) | ((uint32_t)src[2] << 16) | ((uint32_t)src[3] << 24);
+  }
+  warp_sync();
+}
+
+// ---- I16x16 mode decision (WelsMdI16x16, svc_base_layer_md.cpp:365; pfMdCost = SATD) -------------
+// returns the cost; s.out.i16_mode = raw mode id; the winning prediction is in s.pred_y[*best_buf]
+MBK_HD int md_i16x16(const MbCtx& c, MbScratch& s, int* best_buf) {
+  int modes[4];
+  const int n = i16_modes(c.nb & 7, modes);
+  int best = 0x7fffffff, best_mode = modes[0], bb = 1;
+  const uint8_t* org = tile_y(s.tile, 0, 0);
+  for (int i = 0; i < n; i++) {
+    uint8_t* dst = s.pred_y[1 - bb];
+    pred_i16(dst, org, TY_PITCH, modes[i]);
+    const int cost = warp_satd(dst, 16, s.cur_y, 16, 4, 4) + c.lambda * ue_bits(map_i16(modes[i]));
+    if (cost < best) { best = cost; best_mode = modes[i]; bb = 1 - bb; }
+    warp_sync();
+  }
+  s.out.i16_mode = (uint8_t)map_i16(best_mode);
+  *best_buf = bb;
+  return best;
+}
+
+// ---- intra chroma mode decision (WelsMdIntraChroma, :867) ---------------------------------------
+MBK_HD int md_chroma(const MbCtx& c, MbScratch& s, int* best_buf) {
+  int modes[4];
+  const int n = chroma_modes(c.nb & 7, modes);
+  int best = 0x7fffffff, best_mode = modes[0], bb = 1;
+  for (int i = 0; i < n; i++) {
+    uint8_t* dst = s.pred_c[1 - bb];
+    pred_chroma(dst, tile_c(s.tile.u, 0, 0), TC_PITCH, modes[i]);
+    pred_chroma(dst + 64, tile_c(s.tile.v, 0, 0), TC_PITCH, modes[i]);
+    const int cost = warp_satd(dst, 8, s.cur_c, 8, 3, 3) + warp_satd(dst + 64, 8, s.cur_c + 64, 8, 3, 3) +
+                     c.lambda * ue_bits(map_chroma(modes[i]));
+    if (cost < best) { best = cost; best_mode = modes[i]; bb = 1 - bb; }
+    warp_sync();
+  }
+  s.out.chroma_mode = (uint8_t)map_chroma(best_mode);
+  *best_buf = bb;
+  return best;
+}
+
+// ---- I16x16 residual coding + reconstruction (WelsEncRecI16x16Y, svc_encode_mb.cpp:54) ----------
+MBK_HD void enc_rec_i16x16(const MbCtx& c, MbScratch& s, const uint8_t* pred) {
+  const int qp = c.qp;
+  const int16_t* ff = tbl_quant_ff(qp + 6);
+  const int16_t* mf = tbl_quant_mf(qp);
+  // forward transform of the 16 blocks
+  for (int k = lane_id(); k < 16; k += MBK_WS) {
+    int16_t d[16];
+    const int o = blk_y(k) * 4 * 16 + blk_x(k) * 4;
+    dct4x4(d, s.cur_y + o, 16, pred + o, 16);
+    for (int i = 0; i < 16; i++) s.coef[16 * k + i] = d[i];
+  }
+  warp_sync();
+  // DC path: one lane (serial in the reference too)
+  int16_t dcq[16];
+  {
+    int16_t in[16];
+    for (int k = 0; k < 16; k++) in[k] = s.coef[16 * k];
+    hadamard_t4_dc(dcq, in);
+    quant4x4_dc(dcq, ff[0] << 1, mf[0] >> 1);
+  }
+  int16_t lv[16];
+  scan4x4_dcac(lv, dcq);
+  const int n_dc = nonzero_count(lv);
+  for (int i = lane_id(); i < 16; i += MBK_WS) s.out.luma_dc[i] = lv[i];
+  // AC quantisation + scan + counts
+  int nz_ac = 0;
+  for (int k = lane_id(); k < 16; k += MBK_WS) {
+    int16_t d[16], l[16];
+    for (int i = 0; i < 16; i++) d[i] = s.coef[16 * k + i];
+    quant4x4(d, ff, mf);
+    scan4x4_ac(l, d);
+    const int nz = nonzero_count(l);
+    for (int i = 0; i < 16; i++) { s.coef[16 * k + i] = d[i]; s.out.luma[k][i] = l[i]; }
+    s.info.nnz[blk_raster(k)] = (int8_t)nz;
+    nz_ac += nz;
+  }
+  nz_ac = warp_sum(nz_ac);
+  if (n_dc > 0) {
+    if (qp < 12) { ihadamard4x4(dcq); dequant_luma_dc4x4(dcq, qp); }
+    else dequant_ihadamard4x4(dcq, (uint16_t)(tbl_dequant(qp)[0] >> 2));
+  }
+  warp_sync();
+  uint8_t* rec = tile_y(s.tile, 0, 0);
+  if (nz_ac > 0) {
+    s.info.cbp = 15;
+    for (int k = lane_id(); k < 16; k += MBK_WS) {
+      int16_t d[16];
+      for (int i = 0; i < 16; i++) d[i] = s.coef[16 * k + i];
+      dequant4x4(d, tbl_dequant(qp));
+      d[0] = dcq[blk_raster(k)];
+      const int o = blk_y(k) * 4, ox = blk_x(k) * 4;
+      idct4x4_rec(rec + o * TY_PITCH + ox, TY_PITCH, pred + o * 16 + ox, 16, d);
+    }
+  } else if (n_dc > 0) {
+    for (int i = lane_id(); i < 256; i += MBK_WS) {
+      const int y = i >> 4, x = i & 15;
+      rec[y * TY_PITCH + x] = (uint8_t)clip255(pred[i] + ((dcq[(y & 12) + (x >> 2)] + 32) >> 6));
+    }
+  } else {
+    for (int i = lane_id(); i < 256; i += MBK_WS) rec[(i >> 4) * TY_PITCH + (i & 15)] = pred[i];
+  }
+  warp_sync();
+}
+
+// ---- I4x4 mode decision with in-loop coding (WelsMdI4x4 :418 + WelsEncRecI4x4Y svc_encode_mb.cpp:139)
+// returns the I4x4 cost; reconstructs into the tile as it goes; stops early once the running cost
+// reaches `cost_limit` (the I16x16 / inter cost), exactly like the reference.
+MBK_HD int md_enc_i4x4(const MbCtx& c, MbScratch& s, int cost_limit) {
+  const int qp = c.qp;
+  const int16_t* ff = tbl_quant_ff(qp + 6);
+  const int16_t* mf = tbl_quant_mf(qp);
+  const int lam4 = c.lambda << 2, lam1 = c.lambda;
+  int total = 0;
+  for (int k = 0; k < 16; k++) {
+    const int bx = blk_x(k), by = blk_y(k);
+    uint8_t* org = tile_y(s.tile, bx * 4, by * 4);
+    const uint8_t* cur = s.cur_y + by * 4 * 16 + bx * 4;
+    // predicted mode (PredIntra4x4Mode :246)
+    const int lm = s.i4m[(by + 1) * 5 + bx], tm = s.i4m[by * 5 + bx + 1];
+    const int pm = (lm == -1 || tm == -1) ? 2 : (lm < tm ? lm : tm);
+    int modes[9];
+    const int n = i4_modes(i4_avail(c.nb, k), modes);
+    // all candidates in parallel (one lane each); ties resolve to the earliest list entry like the serial '<'
+    int key = 0x7fffffff;
+    for (int j = lane_id(); j < n; j += MBK_WS) {
+      uint8_t p[16];
+      pred_i4(p, org, TY_PITCH, modes[j]);
+      const int cost = satd4x4_pred(p, cur, 16) + (pm == map_i4(modes[j]) ? lam1 : lam4);
+      const int kj = (cost << 4) | j;
+      if (kj < key) key = kj;
+    }
+    key = warp_min(key);
+    const int best_cost = key >> 4, best_mode = modes[key & 15];
+    total += best_cost;
+    if (total >= cost_limit) break;
+    const int fm = map_i4(best_mode);
+    s.out.prev_i4_flag[k] = (int8_t)(pm == fm);
+    s.out.rem_i4_mode[k] = (int8_t)(fm < pm ? fm : fm - 1);
+    s.i4m[(by + 1) * 5 + bx + 1] = (int8_t)fm;
+    s.info.i4_mode[by * 4 + bx] = (int8_t)fm;
+    // encode + reconstruct this block (single lane: 16 samples)
+    if (lane_id() == 0) {
+      uint8_t p[16];
+      int16_t d[16], l[16];
+      pred_i4(p, org, TY_PITCH, best_mode);
+      dct4x4(d, cur, 16, p, 4);
+      quant4x4(d, ff, mf);
+      scan4x4_dcac(l, d);
+      const int nz = nonzero_count(l);
+      for (int i = 0; i < 16; i++) s.out.luma[k][i] = l[i];
+      s.info.nnz[by * 4 + bx] = (int8_t)nz;
+      if (nz > 0) {
+        s.info.cbp |= (uint8_t)(1 << (k >> 2));
+        dequant4x4(d, tbl_dequant(qp));
+        idct4x4_rec(org, TY_PITCH, p, 4, d);
+      } else {
+        for (int i = 0; i < 16; i++) org[(i >> 2) * TY_PITCH + (i & 3)] = p[i];
+      }
+    }
+    warp_sync();
+  }
+  return total + 24 * c.lambda;       // 4*6*lambda (JVT SATD0)
+}
+
+// ---- chroma residual of one plane (WelsEncRecUV, svc_encode_mb.cpp:244); res = s.coef + 256 + 64*uv
+MBK_HD void enc_rec_uv(const MbCtx& c, MbScratch& s, int uv, bool inter) {
+  int16_t* res = s.coef + 256 + 64 * uv;
+  const int qpc = c.qp_c;
+  const int16_t* ff = tbl_quant_ff(qpc + (inter ? 0 : 6));
+  const int16_t* mf = tbl_quant_mf(qpc);
+  // the whole plane is 4 blocks: done by lane 0 (cheap), mirrors the serial reference exactly
+  if (lane_id() == 0) {
+    int16_t dcin[4] = {res[0], res[16], res[32], res[48]}, dc[4];
+    const int nz_dc = hadamard_quant2x2(dcin, (int16_t)(ff[0] << 1), (int16_t)(mf[0] >> 1), dc);
+    res[0] = res[16] = res[32] = res[48] = 0;
+    for (int i = 0; i < 4; i++) s.out.chroma_dc[uv][i] = dc[i];
+    int ctr = 0;
+    for (int j = 0; j < 4; j++) {
+      int16_t d[16], l[16];
+      for (int i = 0; i < 16; i++) d[i] = res[16 * j + i];
+      const int16_t mx = quant4x4_max(d, ff, mf);
+      for (int i = 0; i < 16; i++) res[16 * j + i] = d[i];
+      if (mx == 0) {
+        for (int i = 0; i < 16; i++) s.out.chroma_ac[4 * uv + j][i] = 0;
+      } else {
+        scan4x4_ac(l, d);
+        for (int i = 0; i < 16; i++) s.out.chroma_ac[4 * uv + j][i] = l[i];
+        if (inter) {
+          if (mx > 1) ctr += 9;
+          else if (ctr < 7) ctr += single_ctr4x4(l);
+        } else ctr = 0x7fffffff;
+      }
+    }
+    if (ctr < 7) {
+      for (int i = 0; i < 64; i++) res[i] = 0;
+      for (int j = 0; j < 4; j++) s.info.nnz[16 + 4 * uv + j] = 0;
+    } else {
+      for (int j = 0; j < 4; j++) {
+        s.info.nnz[16 + 4 * uv + j] = (int8_t)nonzero_count(s.out.chroma_ac[4 * uv + j]);
+        int16_t d[16];
+        for (int i = 0; i < 16; i++) d[i] = res[16 * j + i];
+        dequant4x4(d, tbl_dequant(qpc));
+        for (int i = 0; i < 16; i++) res[16 * j + i] = d[i];
+      }
+      s.info.cbp = (uint8_t)((s.info.cbp & 0x0F) | 0x20);
+    }
+    if (nz_dc > 0) {
+      dequant_ihadamard2x2_dc(dc, tbl_dequant(qpc)[0]);
+      if (2 != (s.info.cbp >> 4)) s.info.cbp |= 0x10;
+      res[0] = dc[0]; res[16] = dc[1]; res[32] = dc[2]; res[48] = dc[3];
+    }
+  }
+  warp_sync();
+}
+
+// chroma transform of both planes against prediction `pred` (Cb 0..63, Cr 64..127)
+MBK_HD void dct_chroma(MbScratch& s, const uint8_t* pred) {
+  for (int t = lane_id(); t < 8; t += MBK_WS) {
+    const int uv = t >> 2, j = t & 3, ox = (j & 1) * 4, oy = (j >> 1) * 4;
+    int16_t d[16];
+    dct4x4(d, s.cur_c + 64 * uv + oy * 8 + ox, 8, pred + 64 * uv + oy * 8 + ox, 8);
+    for (int i = 0; i < 16; i++) s.coef[256 + 64 * uv + 16 * j + i] = d[i];
+  }
+  warp_sync();
+}
+// chroma reconstruction of both planes into the tile: pred + IDCT(coef)
+MBK_HD void rec_chroma(MbScratch& s, const uint8_t* pred) {
+  for (int t = lane_id(); t < 8; t += MBK_WS) {
+    const int uv = t >> 2, j = t & 3, ox = (j & 1) * 4, oy = (j >> 1) * 4;
+    int16_t d[16];
+    for (int i = 0; i < 16; i++) d[i] = s.coef[256 + 64 * uv + 16 * j + i];
+    idct4x4_rec(tile_c(uv ? s.tile.v : s.tile.u, ox, oy), TC_PITCH, pred + 64 * uv + oy * 8 + ox, 8, d);
+  }
+  warp_sync();
+}
+
+// ---- intra4x4 mode cache from the neighbours (FillNeighborCacheIntra, md.cpp:51) -----------------
+MBK_HD void fill_i4_cache(const MbCtx& c, MbScratch& s) {
+  if (lane_id() == 0) {
+    for (int i = 0; i < 25; i++) s.i4m[i] = -1;
+    if (c.nb & NB_LEFT) {
+      const MbInfo* l = c.f.mbi + (c.mby * c.p.mb_w + c.mbx - 1);
+      for (int y = 0; y < 4; y++) s.i4m[(y + 1) * 5] = l->mb_type == MBT_I4x4 ? l->i4_mode[y * 4 + 3] : 2;
+    }
+    if (c.nb & NB_TOP) {
+      const MbInfo* t = c.f.mbi + ((c.mby - 1) * c.p.mb_w + c.mbx);
+      for (int x = 0; x < 4; x++) s.i4m[x + 1] = t->mb_type == MBT_I4x4 ? t->i4_mode[12 + x] : 2;
+    }
+  }
+  warp_sync();
+}
+
+// ---- a macroblock of an I slice (WelsMdIntraMb :956 + WelsMdIntraSecondaryModesEnc :2023) ---------
+// returns the luma cost (iCostLuma)
+MBK_HD int intra_mb_md_enc(const MbCtx& c, MbScratch& s, int cost_limit_for_i16 /*INT_MAX in I slices*/) {
+  (void)cost_limit_for_i16;
+  int bb;
+  int cost = md_i16x16(c, s, &bb);
+  s.info.mb_type = MBT_I16x16;
+  s.info.cbp = 0;
+  fill_i4_cache(c, s);
+  const int cost4 = md_enc_i4x4(c, s, cost);           // pfIntraFineMd = WelsMdIntraFinePartition (:932)
+  if (cost4 < cost) { s.info.mb_type = MBT_I4x4; cost = cost4; }
+  if (s.info.mb_type == MBT_I16x16) {
+    s.info.cbp = 0;
+    enc_rec_i16x16(c, s, s.pred_y[bb]);
+  }
+  int cb;
+  md_chroma(c, s, &cb);
+  dct_chroma(s, s.pred_c[cb]);
+  enc_rec_uv(c, s, 0, false);
+  enc_rec_uv(c, s, 1, false);
+  rec_chroma(s, s.pred_c[cb]);
+  return cost;
+}
+
+// publishes MbInfo / RefMbInfo / MbOut of a finished macroblock
+MBK_HD void mb_publish(const MbCtx& c, MbScratch& s) {
+  const int idx = c.mby * c.p.mb_w + c.mbx;
+  if (lane_id() == 0) {
+    s.info.qp = (uint8_t)c.qp; s.info.qp_c = (uint8_t)c.qp_c;
+    s.out.mb_type = s.info.mb_type; s.out.cbp = s.info.cbp; s.out.qp = (uint8_t)c.qp;
+    for (int i = 0; i < 24; i++) s.out.nnz[i] = s.info.nnz[i];
+  }
+  warp_sync();
+  // word copies
+  const uint32_t* si = reinterpret_cast<const uint32_t*>(&s.info);
+  uint32_t* di = reinterpret_cast<uint32_t*>(c.f.mbi + idx);
+  for (int i = lane_id(); i < (int)(sizeof(MbInfo) / 4); i += MBK_WS) di[i] = si[i];
+  const uint32_t* so = reinterpret_cast<const uint32_t*>(&s.out);
+  uint32_t* dout = reinterpret_cast<uint32_t*>(c.f.out + idx);
+  for (int i = lane_id(); i < (int)(sizeof(MbOut) / 4); i += MBK_WS) dout[i] = so[i];
+  warp_sync();
+}
+
+}  // namespace mbk

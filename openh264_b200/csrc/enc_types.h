@@ -1,0 +1,74 @@
+// enc_types.h — plain-data structures shared by the device macroblock pipeline, the host entropy
+// coder and the frame-level C-ABI (include/b2h264_codec.h).  No CUDA or C++ types in here.
+#pragma once
+#include <stdint.h>
+
+// macroblock types (own numbering)
+enum {
+  MBT_I4x4 = 0, MBT_I16x16 = 1, MBT_P16x16 = 2, MBT_P16x8 = 3, MBT_P8x16 = 4, MBT_P8x8 = 5, MBT_PSKIP = 6
+};
+#define MBT_IS_INTRA(t) ((t) <= MBT_I16x16)
+#define MBT_IS_INTER(t) ((t) >= MBT_P16x16)
+
+// Per-macroblock state kept in HBM for the frame being coded: read by the neighbours' mode decision,
+// by the deblocking pass and (through MbOut) by the host entropy coder.
+// Mirrors the parts of the reference's SMB (codec/encoder/core/inc/svc_enc_macroblock.h:49-77)
+// this path needs.
+typedef struct {
+  int16_t mv[16][2];        // per 4x4 block, RASTER order (row*4+col), quarter-pel
+  int8_t  nnz[24];          // non-zero counts: luma raster 0..15, Cb 16..19, Cr 20..23 (raster 2x2)
+  int8_t  i4_mode[16];      // intra4x4 pred modes (0..8), raster order; valid when mb_type == MBT_I4x4
+  int16_t p16x16_mv[2];     // sP16x16Mv: 16x16 search result, candidate for the neighbours' search
+  int32_t sad_cost;         // pSadCost[0] (0 for intra) -> neighbours' SAD predictor
+  uint8_t mb_type;
+  uint8_t cbp;
+  uint8_t qp, qp_c;
+  int8_t  ref_idx;          // 0 for inter, -2 for intra (REF_NOT_IN_LIST)
+  uint8_t pad[3];
+} MbInfo;                   // 64+24+16+4+4+8 = 120 bytes
+
+// Per-macroblock info a coded picture carries for the NEXT frame's decisions
+// (SPicture::uiRefMbType / pMbSkipSad / sMvList, codec/encoder/core/inc/picture.h).
+typedef struct {
+  int16_t mv16[2];          // sMvList
+  int32_t skip_sad;         // pMbSkipSad
+  uint8_t mb_type;          // uiRefMbType
+  uint8_t pad[3];
+} RefMbInfo;                // 12 bytes
+
+// What the device hands to the host entropy coder for one macroblock (pinned-async copy-back).
+// Levels are already zig-zag scanned (SDCTCoeff, codec/encoder/core/inc/mb_cache.h:63-72).
+typedef struct {
+  uint8_t mb_type, cbp, qp, i16_mode;     // i16_mode: 0..3 as coded
+  uint8_t chroma_mode;                    // 0..3 as coded
+  uint8_t pad0[3];
+  int8_t  prev_i4_flag[16];               // prev_intra4x4_pred_mode_flag, coding (z) order
+  int8_t  rem_i4_mode[16];                // rem_intra4x4_pred_mode
+  int16_t mvd[4][2];                      // mv - mvp per partition in coding order
+  int8_t  nnz[24];                        // same layout as MbInfo::nnz
+  int16_t luma_dc[16];                    // I16x16 DC levels (scan order)
+  int16_t luma[16][16];                   // per 4x4 block in CODING (z) order; I16x16: AC in [0..14]
+  int16_t chroma_dc[2][4];
+  int16_t chroma_ac[8][16];               // Cb 0..3, Cr 4..7
+} MbOut;                                  // 8+32+16+24+32+512+16+256 = 896 bytes
+
+typedef struct {
+  int32_t mb_w, mb_h;
+  int32_t cur_stride_y, cur_stride_c;     // source picture (MB-aligned, unpadded)
+  int32_t rec_stride_y, rec_stride_c;     // reconstructed / reference pictures (padded 32 / 16)
+  int32_t qp;                             // constant luma QP (RC_OFF_MODE)
+  int32_t is_idr;                         // 1: I slice, 0: P slice
+  int32_t mv_range;                       // iMvRange (integer pel)
+  int32_t ref_is_p;                       // reference picture was coded as P (temporal candidates valid)
+} EncFrameParams;
+
+typedef struct {
+  const uint8_t* cur[3];                  // source Y,U,V (pixel (0,0))
+  uint8_t* rec[3];                        // picture being reconstructed (pixel (0,0) inside padding)
+  const uint8_t* ref[3];                  // reference picture (padded, expanded)
+  MbInfo* mbi;                            // mb_w*mb_h, frame being coded
+  RefMbInfo* rec_info;                    // written for the next frame
+  const RefMbInfo* ref_info;              // of the reference picture
+  MbOut* out;                             // mb_w*mb_h
+  int32_t* row_progress;                  // wavefront: number of finished MBs per MB row (device only)
+} EncFramePtrs;

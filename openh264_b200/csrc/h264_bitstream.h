@@ -1,0 +1,70 @@
+// h264_bitstream.h — host-side bitstream serialisation (stays on the CPU by design, north_star):
+// parameter sets, slice headers, CAVLC macroblock syntax, NAL encapsulation.  It consumes the MbOut
+// records the device pipeline copies back.  Syntax follows Rec. H.264 7.3 / 9.2; the field values
+// follow what the reference emits for the supported configuration
+// (codec/encoder/core/src/au_set.cpp:197-470, svc_encode_slice.cpp:275-346,
+//  svc_set_mb_syn_cavlc.cpp:60-420, set_mb_syn_cavlc.cpp:84-250, nal_encap.cpp).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include <vector>
+
+#include "enc_types.h"
+
+namespace b2h264 {
+
+class BitWriter {
+ public:
+  explicit BitWriter(std::vector<uint8_t>* out) : out_(out) {}
+  void put(int n, uint32_t v) {                 // n <= 32 bits, MSB first
+    for (int i = n - 1; i >= 0; i--) {
+      cur_ = (uint8_t)((cur_ << 1) | ((v >> i) & 1));
+      if (++nbits_ == 8) { out_->push_back(cur_); cur_ = 0; nbits_ = 0; }
+    }
+  }
+  void bit(int b) { put(1, (uint32_t)(b != 0)); }
+  void ue(uint32_t v) {
+    int len = 0;
+    for (uint32_t t = v + 1; t > 1; t >>= 1) len++;
+    put(len, 0);
+    put(len + 1, v + 1);
+  }
+  void se(int32_t v) { ue(v > 0 ? (uint32_t)(2 * v - 1) : (uint32_t)(-2 * v)); }
+  void trailing() { bit(1); while (nbits_) bit(0); }
+  size_t bit_pos() const { return out_->size() * 8 + nbits_; }
+ private:
+  std::vector<uint8_t>* out_;
+  uint8_t cur_ = 0;
+  int nbits_ = 0;
+};
+
+struct StreamParams {
+  int width, height;            // picture size in luma samples (coded size = MB aligned)
+  int mb_w, mb_h;
+  int num_ref_frames;
+  int level_idc;
+  bool constraint_set3;
+  int qp;
+  bool crop;
+  int crop_right, crop_bottom;  // in units of 2 luma samples
+};
+
+// level selection (WelsGetLevelIdc, au_set.cpp:51-195; limits = H.264 Table A-1)
+void select_level(StreamParams* sp, float fps, int target_bitrate);
+
+// appends one NAL unit (4-byte start code + header + emulation-prevented payload)
+void append_nal(std::vector<uint8_t>* dst, int nal_ref_idc, int nal_type, const std::vector<uint8_t>& rbsp);
+
+void write_sps(const StreamParams& sp, std::vector<uint8_t>* rbsp);
+void write_pps(const StreamParams& sp, std::vector<uint8_t>* rbsp);
+
+struct SliceState {
+  bool idr;
+  int frame_num;
+  int idr_pic_id;
+  int qp;
+};
+// slice header + all macroblocks + trailing bits of a single-slice picture
+void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* mbs, std::vector<uint8_t>* rbsp);
+
+}  // namespace b2h264

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) k_mc_sad(const uint8_t* __restrict__ cur,
       const int y = i >> 4, x = i & 15;
       s += iabs((int)cm[i] - luma_qpel_sample(p + y * MCS_WSTRIDE + x, MCS_WSTRIDE, fx, fy));
     }
-    s = __reduce_add_sync(MBK_FULL, s);
+    s = warp_sum(s);
     if (l == 0) cost[(size_t)m * k + c] = s;
   }
 }

@@ -9,45 +9,121 @@
 
 #define MBK_FULL 0xffffffffu
 
+// ---- host/device portability ------------------------------------------------------------------
+// The macroblock code is written once.  Compiled for the device, a routine is executed by the 32
+// lanes of one warp (lane-strided loops + REDUX).  Compiled for the host (tests/emu only: a
+// debugging build that is NOT part of the product library) the same source runs as a "1-lane warp":
+// MBK_WS == 1, so every lane-strided loop visits all indices and warp reductions are the identity.
+#define MBK_HD __host__ __device__ __forceinline__
+#ifdef __CUDA_ARCH__
+#define MBK_WS 32
+#else
+#define MBK_WS 1
+#endif
+
 namespace mbk {
 
+MBK_HD int lane_id() {
+#ifdef __CUDA_ARCH__
+  return threadIdx.x & 31;
+#else
+  return 0;
+#endif
+}
+MBK_HD int warp_sum(int v) {
+#ifdef __CUDA_ARCH__
+  return __reduce_add_sync(MBK_FULL, v);
+#else
+  return v;
+#endif
+}
+MBK_HD int warp_min(int v) {
+#ifdef __CUDA_ARCH__
+  return __reduce_min_sync(MBK_FULL, v);
+#else
+  return v;
+#endif
+}
+MBK_HD void warp_sync() {
+#ifdef __CUDA_ARCH__
+  __syncwarp();
+#endif
+}
+MBK_HD uint32_t vsadu4(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __vsadu4(a, b);
+#else
+  uint32_t s = 0;
+  for (int i = 0; i < 4; i++) { const int d = (int)((a >> (8 * i)) & 0xff) - (int)((b >> (8 * i)) & 0xff); s += d < 0 ? -d : d; }
+  return s;
+#endif
+}
+MBK_HD int clz32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+  return __clz((int)v);
+#else
+  return v ? __builtin_clz(v) : 32;
+#endif
+}
+
 // quantiser tables live in constant memory, filled once by b2h264 init (closed forms, see tables.cu)
+// host copies of the same tables (tables.cu); the device reads constant memory, the host build reads these
+extern int16_t h_quant_ff[58][8];
+extern int16_t h_quant_mf[52][8];
+extern uint16_t h_dequant[52][8];
+extern uint8_t h_lambda[52];
+extern uint8_t h_chroma_qp[52];
+#ifdef __CUDACC__
 extern __constant__ int16_t c_quant_ff[58][8];   // g_kiQuantInterFF (intra = row qp+6)
 extern __constant__ int16_t c_quant_mf[52][8];   // g_kiQuantMF
 extern __constant__ uint16_t c_dequant[52][8];   // g_kuiDequantCoeff
 extern __constant__ uint8_t c_lambda[52];        // g_kiQpCostTable
 extern __constant__ uint8_t c_chroma_qp[52];     // g_kuiChromaQpTable
+#endif
+#ifdef __CUDA_ARCH__
+#define MBK_TBL(dev, host) dev
+#else
+#define MBK_TBL(dev, host) host
+#endif
+MBK_HD const int16_t* tbl_quant_ff(int q) { return MBK_TBL(c_quant_ff, h_quant_ff)[q]; }
+MBK_HD const int16_t* tbl_quant_mf(int q) { return MBK_TBL(c_quant_mf, h_quant_mf)[q]; }
+MBK_HD const uint16_t* tbl_dequant(int q) { return MBK_TBL(c_dequant, h_dequant)[q]; }
+MBK_HD int tbl_lambda(int q) { return MBK_TBL(c_lambda, h_lambda)[q]; }
+MBK_HD int tbl_chroma_qp(int q) { return MBK_TBL(c_chroma_qp, h_chroma_qp)[q]; }
 
-__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
-__device__ __forceinline__ int iabs(int v) { return v < 0 ? -v : v; }
-__device__ __forceinline__ int clip3(int v, int lo, int hi) { return min(max(v, lo), hi); }
-__device__ __forceinline__ int clip255(int v) { return min(max(v, 0), 255); }
+MBK_HD int iabs(int v) { return v < 0 ? -v : v; }
+MBK_HD int clip3(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+MBK_HD int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 
 // block-size ids follow the reference (encoder/core/inc/wels_const.h:139-148)
 enum { BLK_16x16 = 0, BLK_16x8, BLK_8x16, BLK_8x8, BLK_4x4, BLK_8x4, BLK_4x8 };
-__device__ __forceinline__ int blk_lw(int blk) { return (0x2323344 >> (blk * 4)) & 0xf; }  // log2(width)
-__device__ __forceinline__ int blk_lh(int blk) { return (0x3223434 >> (blk * 4)) & 0xf; }  // log2(height)
-__device__ __forceinline__ int blk_w(int blk) { return 1 << blk_lw(blk); }
-__device__ __forceinline__ int blk_h(int blk) { return 1 << blk_lh(blk); }
+MBK_HD int blk_lw(int blk) { return (0x2323344 >> (blk * 4)) & 0xf; }  // log2(width)
+MBK_HD int blk_lh(int blk) { return (0x3223434 >> (blk * 4)) & 0xf; }  // log2(height)
+MBK_HD int blk_w(int blk) { return 1 << blk_lw(blk); }
+MBK_HD int blk_h(int blk) { return 1 << blk_lh(blk); }
 
 // 4 consecutive bytes at an arbitrary byte address as a little-endian word: two aligned 32-bit
 // loads + funnel shift (never reads past the aligned word that holds byte p+3).
-__device__ __forceinline__ uint32_t ld4u(const uint8_t* p) {
+MBK_HD uint32_t ld4u(const uint8_t* p) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(p);
   const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
   const uint32_t sh = (uint32_t)(a & 3) * 8;
   const uint32_t lo = w[0];
   const uint32_t hi = sh ? w[1] : 0u;
+#ifdef __CUDA_ARCH__
   return __funnelshift_r(lo, hi, sh);
+#else
+  return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
 }
 
 // bits of the signed Exp-Golomb code of v (encoder/core/inc/svc_enc_golomb.h:84-95)
-__device__ __forceinline__ int se_bits(int v) {
+MBK_HD int se_bits(int v) {
   const uint32_t code = v > 0 ? (uint32_t)(2 * v - 1) : (uint32_t)(-2 * v);
-  return 2 * (31 - __clz(code + 1)) + 1;
+  return 2 * (31 - clz32(code + 1)) + 1;
 }
 // COST_MVD(table, dx, dy) with table[d] = (uint16)(lambda * bits(se(d)))  (md.cpp:797-824)
-__device__ __forceinline__ int mvd_cost(int lambda, int dx, int dy) {
+MBK_HD int mvd_cost(int lambda, int dx, int dy) {
   return ((lambda * se_bits(dx)) & 0xffff) + ((lambda * se_bits(dy)) & 0xffff);
 }
 

@@ -7,7 +7,7 @@
 namespace mbk {
 
 // bS < 4 luma, one line; tc0 < 0 means "not filtered"
-__device__ __forceinline__ void deblock_luma_lt4_line(uint8_t* pix, int sx, int alpha, int beta, int tc0) {
+MBK_HD void deblock_luma_lt4_line(uint8_t* pix, int sx, int alpha, int beta, int tc0) {
   if (tc0 < 0) return;
   const int p0 = pix[-sx], p1 = pix[-2 * sx], p2 = pix[-3 * sx], q0 = pix[0], q1 = pix[sx], q2 = pix[2 * sx];
   if (!(iabs(p0 - q0) < alpha && iabs(p1 - p0) < beta && iabs(q1 - q0) < beta)) return;
@@ -19,7 +19,7 @@ __device__ __forceinline__ void deblock_luma_lt4_line(uint8_t* pix, int sx, int 
   pix[0] = (uint8_t)clip255(q0 - delta);
 }
 // bS == 4 luma, one line
-__device__ __forceinline__ void deblock_luma_eq4_line(uint8_t* pix, int sx, int alpha, int beta) {
+MBK_HD void deblock_luma_eq4_line(uint8_t* pix, int sx, int alpha, int beta) {
   const int p0 = pix[-sx], p1 = pix[-2 * sx], p2 = pix[-3 * sx], q0 = pix[0], q1 = pix[sx], q2 = pix[2 * sx];
   const int d = iabs(p0 - q0);
   if (!(d < alpha && iabs(p1 - p0) < beta && iabs(q1 - q0) < beta)) return;
@@ -46,7 +46,7 @@ __device__ __forceinline__ void deblock_luma_eq4_line(uint8_t* pix, int sx, int 
   }
 }
 // bS < 4 chroma, one line of one plane; filtered only when tc > 0
-__device__ __forceinline__ void deblock_chroma_lt4_line(uint8_t* pix, int sx, int alpha, int beta, int tc) {
+MBK_HD void deblock_chroma_lt4_line(uint8_t* pix, int sx, int alpha, int beta, int tc) {
   if (tc <= 0) return;
   const int p0 = pix[-sx], p1 = pix[-2 * sx], q0 = pix[0], q1 = pix[sx];
   if (iabs(p0 - q0) < alpha && iabs(p1 - p0) < beta && iabs(q1 - q0) < beta) {
@@ -55,7 +55,7 @@ __device__ __forceinline__ void deblock_chroma_lt4_line(uint8_t* pix, int sx, in
     pix[0] = (uint8_t)clip255(q0 - delta);
   }
 }
-__device__ __forceinline__ void deblock_chroma_eq4_line(uint8_t* pix, int sx, int alpha, int beta) {
+MBK_HD void deblock_chroma_eq4_line(uint8_t* pix, int sx, int alpha, int beta) {
   const int p0 = pix[-sx], p1 = pix[-2 * sx], q0 = pix[0], q1 = pix[sx];
   if (iabs(p0 - q0) < alpha && iabs(p1 - p0) < beta && iabs(q1 - q0) < beta) {
     pix[-sx] = (uint8_t)((2 * p1 + p0 + q1 + 2) >> 2);

@@ -7,20 +7,20 @@
 namespace mbk {
 
 // 6-tap (1,-5,20,20,-5,1) centred between p[0] and p[step]
-__device__ __forceinline__ int tap6(const uint8_t* p, int step) {
+MBK_HD int tap6(const uint8_t* p, int step) {
   return (int)(p[-2 * step] + p[3 * step]) - 5 * (int)(p[-step] + p[2 * step]) + 20 * (int)(p[0] + p[step]);
 }
-__device__ __forceinline__ int half_h(const uint8_t* p) { return clip255((tap6(p, 1) + 16) >> 5); }
-__device__ __forceinline__ int half_v(const uint8_t* p, int s) { return clip255((tap6(p, s) + 16) >> 5); }
+MBK_HD int half_h(const uint8_t* p) { return clip255((tap6(p, 1) + 16) >> 5); }
+MBK_HD int half_v(const uint8_t* p, int s) { return clip255((tap6(p, s) + 16) >> 5); }
 // centre sample: vertical pass unrounded (fits int16, as mc.cpp:218), then horizontal pass, (x+512)>>10
-__device__ __forceinline__ int half_c(const uint8_t* p, int s) {
+MBK_HD int half_c(const uint8_t* p, int s) {
   const int c0 = tap6(p - 2, s), c1 = tap6(p - 1, s), c2 = tap6(p, s), c3 = tap6(p + 1, s), c4 = tap6(p + 2, s),
             c5 = tap6(p + 3, s);
   return clip255(((c0 + c5) - 5 * (c1 + c4) + 20 * (c2 + c3) + 512) >> 10);
 }
 
 // one luma sample at quarter-sample phase (fx, fy); p points at the integer sample
-__device__ __forceinline__ int luma_qpel_sample(const uint8_t* p, int s, int fx, int fy) {
+MBK_HD int luma_qpel_sample(const uint8_t* p, int s, int fx, int fy) {
   if ((fx | fy) == 0) return p[0];
   if (fy == 0) {
     const int b = half_h(p);
@@ -37,18 +37,18 @@ __device__ __forceinline__ int luma_qpel_sample(const uint8_t* p, int s, int fx,
 }
 
 // w x h luma prediction; src already offset by the integer part of the MV (as McLuma_c expects)
-__device__ __forceinline__ void warp_mc_luma(const uint8_t* src, int ss, uint8_t* dst, int ds, int mvx, int mvy, int w,
+MBK_HD void warp_mc_luma(const uint8_t* src, int ss, uint8_t* dst, int ds, int mvx, int mvy, int w,
                                              int h) {
   const int fx = mvx & 3, fy = mvy & 3;
-  for (int i = lane_id(); i < w * h; i += 32) {
+  for (int i = lane_id(); i < w * h; i += MBK_WS) {
     const int y = i / w, x = i - y * w;
     dst[y * ds + x] = (uint8_t)luma_qpel_sample(src + y * ss + x, ss, fx, fy);
   }
 }
 
 // half-sample planes used by the fractional refinement (pfLumaHalfpelHor/Ver/Cen, mc.h:46-49)
-__device__ __forceinline__ void warp_halfpel(int which, const uint8_t* src, int ss, uint8_t* dst, int ds, int w, int h) {
-  for (int i = lane_id(); i < w * h; i += 32) {
+MBK_HD void warp_halfpel(int which, const uint8_t* src, int ss, uint8_t* dst, int ds, int w, int h) {
+  for (int i = lane_id(); i < w * h; i += MBK_WS) {
     const int y = i / w, x = i - y * w;
     const uint8_t* p = src + y * ss + x;
     dst[y * ds + x] = (uint8_t)(which == 0 ? half_h(p) : which == 1 ? half_v(p, ss) : half_c(p, ss));
@@ -56,11 +56,11 @@ __device__ __forceinline__ void warp_halfpel(int which, const uint8_t* src, int 
 }
 
 // bilinear eighth-sample chroma (mc.cpp:349-380)
-__device__ __forceinline__ void warp_mc_chroma(const uint8_t* src, int ss, uint8_t* dst, int ds, int mvx, int mvy, int w,
+MBK_HD void warp_mc_chroma(const uint8_t* src, int ss, uint8_t* dst, int ds, int mvx, int mvy, int w,
                                                int h) {
   const int dx = mvx & 7, dy = mvy & 7;
   const int A = (8 - dx) * (8 - dy), B = dx * (8 - dy), Cc = (8 - dx) * dy, D = dx * dy;
-  for (int i = lane_id(); i < w * h; i += 32) {
+  for (int i = lane_id(); i < w * h; i += MBK_WS) {
     const int y = i / w, x = i - y * w;
     const uint8_t* p = src + y * ss + x;
     int v;
@@ -70,9 +70,9 @@ __device__ __forceinline__ void warp_mc_chroma(const uint8_t* src, int ss, uint8
   }
 }
 
-__device__ __forceinline__ void warp_pixel_avg(uint8_t* dst, int ds, const uint8_t* a, int sa, const uint8_t* b, int sb,
+MBK_HD void warp_pixel_avg(uint8_t* dst, int ds, const uint8_t* a, int sa, const uint8_t* b, int sb,
                                                int w, int h) {
-  for (int i = lane_id(); i < w * h; i += 32) {
+  for (int i = lane_id(); i < w * h; i += MBK_WS) {
     const int y = i / w, x = i - y * w;
     dst[y * ds + x] = (uint8_t)((a[y * sa + x] + b[y * sb + x] + 1) >> 1);
   }

@@ -8,40 +8,40 @@ namespace mbk {
 
 // SAD of a (1<<lw) x (1<<lh) block: the block is cut into 4-pixel groups, lane g takes groups
 // g, g+32, ...; each group is one __vsadu4 on packed bytes; warp total by REDUX.
-__device__ __forceinline__ int warp_sad(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh) {
+MBK_HD int warp_sad(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh) {
   const int lg = lw - 2;                    // log2(groups per row)
   const int ngroups = 1 << (lg + lh);
   int s = 0;
-  for (int g = lane_id(); g < ngroups; g += 32) {
+  for (int g = lane_id(); g < ngroups; g += MBK_WS) {
     const int row = g >> lg, col = (g & ((1 << lg) - 1)) << 2;
-    s += __vsadu4(ld4u(a + row * sa + col), ld4u(b + row * sb + col));
+    s += vsadu4(ld4u(a + row * sa + col), ld4u(b + row * sb + col));
   }
-  return __reduce_add_sync(MBK_FULL, s);
+  return warp_sum(s);
 }
 
 // SADs against b shifted up, down, left, right by one pixel (pfSample4Sad order), cur read once.
-__device__ __forceinline__ void warp_sad_four(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh,
+MBK_HD void warp_sad_four(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh,
                                               int out[4]) {
   const int lg = lw - 2;
   const int ngroups = 1 << (lg + lh);
   int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-  for (int g = lane_id(); g < ngroups; g += 32) {
+  for (int g = lane_id(); g < ngroups; g += MBK_WS) {
     const int row = g >> lg, col = (g & ((1 << lg) - 1)) << 2;
     const uint32_t c = ld4u(a + row * sa + col);
     const uint8_t* r = b + row * sb + col;
-    s0 += __vsadu4(c, ld4u(r - sb));
-    s1 += __vsadu4(c, ld4u(r + sb));
-    s2 += __vsadu4(c, ld4u(r - 1));
-    s3 += __vsadu4(c, ld4u(r + 1));
+    s0 += vsadu4(c, ld4u(r - sb));
+    s1 += vsadu4(c, ld4u(r + sb));
+    s2 += vsadu4(c, ld4u(r - 1));
+    s3 += vsadu4(c, ld4u(r + 1));
   }
-  out[0] = __reduce_add_sync(MBK_FULL, s0);
-  out[1] = __reduce_add_sync(MBK_FULL, s1);
-  out[2] = __reduce_add_sync(MBK_FULL, s2);
-  out[3] = __reduce_add_sync(MBK_FULL, s3);
+  out[0] = warp_sum(s0);
+  out[1] = warp_sum(s1);
+  out[2] = warp_sum(s2);
+  out[3] = warp_sum(s3);
 }
 
 // |Hadamard4x4(a - b)| summed, (sum+1)>>1, for ONE 4x4 block, by one thread (sample.cpp:48-96).
-__device__ __forceinline__ int satd4x4_thread(const uint8_t* a, int sa, const uint8_t* b, int sb) {
+MBK_HD int satd4x4_thread(const uint8_t* a, int sa, const uint8_t* b, int sb) {
   int t[4][4];
 #pragma unroll
   for (int y = 0; y < 4; y++) {
@@ -61,16 +61,15 @@ __device__ __forceinline__ int satd4x4_thread(const uint8_t* a, int sa, const ui
 }
 
 // SATD of a block: one lane per 4x4 sub-block (16 lanes busy for 16x16), warp total by REDUX.
-__device__ __forceinline__ int warp_satd(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh) {
+MBK_HD int warp_satd(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh) {
   const int lbx = lw - 2;                    // log2(4x4 blocks per row)
   const int nblk = 1 << (lbx + lh - 2);
   int s = 0;
-  const int l = lane_id();
-  if (l < nblk) {
+  for (int l = lane_id(); l < nblk; l += MBK_WS) {
     const int by = l >> lbx, bx = l & ((1 << lbx) - 1);
-    s = satd4x4_thread(a + 4 * by * sa + 4 * bx, sa, b + 4 * by * sb + 4 * bx, sb);
+    s += satd4x4_thread(a + 4 * by * sa + 4 * bx, sa, b + 4 * by * sb + 4 * bx, sb);
   }
-  return __reduce_add_sync(MBK_FULL, s);
+  return warp_sum(s);
 }
 
 }  // namespace mbk

@@ -8,10 +8,10 @@
 
 namespace mbk {
 
-__device__ __forceinline__ int16_t s16(int v) { return (int16_t)v; }
+MBK_HD int16_t s16(int v) { return (int16_t)v; }
 
 // residual + forward core transform (WelsDctT4_c, encode_mb_aux.cpp:313)
-__device__ __forceinline__ void dct4x4(int16_t d[16], const uint8_t* p1, int s1, const uint8_t* p2, int s2) {
+MBK_HD void dct4x4(int16_t d[16], const uint8_t* p1, int s1, const uint8_t* p2, int s2) {
   int16_t m[16];
 #pragma unroll
   for (int y = 0; y < 4; y++) {
@@ -30,13 +30,13 @@ __device__ __forceinline__ void dct4x4(int16_t d[16], const uint8_t* p1, int s1,
 }
 
 // sign * (((ff + |x|) * mf) >> 16)   (encode_mb_aux.cpp:161-163)
-__device__ __forceinline__ int16_t quant1(int16_t x, int ff, int mf) {
+MBK_HD int16_t quant1(int16_t x, int ff, int mf) {
   const int sign = x < 0 ? -1 : 0;
   const int mag = ((ff + ((sign ^ (int)x) - sign)) * mf) >> 16;
   return s16((sign ^ mag) - sign);
 }
 // quantise one 4x4 block in place; returns the block's largest magnitude as WelsQuantFour4x4Max_c does
-__device__ __forceinline__ int16_t quant4x4_max(int16_t d[16], const int16_t* ff, const int16_t* mf) {
+MBK_HD int16_t quant4x4_max(int16_t d[16], const int16_t* ff, const int16_t* mf) {
   int16_t mx = 0;
 #pragma unroll
   for (int i = 0; i < 16; i++) {
@@ -48,27 +48,27 @@ __device__ __forceinline__ int16_t quant4x4_max(int16_t d[16], const int16_t* ff
   }
   return mx;
 }
-__device__ __forceinline__ void quant4x4(int16_t d[16], const int16_t* ff, const int16_t* mf) {
+MBK_HD void quant4x4(int16_t d[16], const int16_t* ff, const int16_t* mf) {
 #pragma unroll
   for (int i = 0; i < 16; i++) d[i] = quant1(d[i], ff[i & 7], mf[i & 7]);
 }
-__device__ __forceinline__ void quant4x4_dc(int16_t d[16], int ff, int mf) {
+MBK_HD void quant4x4_dc(int16_t d[16], int ff, int mf) {
 #pragma unroll
   for (int i = 0; i < 16; i++) d[i] = quant1(d[i], ff, mf);
 }
 
 // chroma DC 2x2 Hadamard (+quant). in[4] = DC of blocks 0..3 (raster). (encode_mb_aux.cpp:226-277)
-__device__ __forceinline__ void hadamard2x2(const int16_t in[4], int16_t out[4]) {
+MBK_HD void hadamard2x2(const int16_t in[4], int16_t out[4]) {
   const int16_t s0 = s16(in[0] + in[2]), s1 = s16(in[0] - in[2]), s2 = s16(in[1] + in[3]), s3 = s16(in[1] - in[3]);
   out[0] = s16(s0 + s2); out[1] = s16(s0 - s2); out[2] = s16(s1 + s3); out[3] = s16(s1 - s3);
 }
-__device__ __forceinline__ int hadamard_quant2x2_skip(const int16_t in[4], int16_t ff, int16_t mf) {
+MBK_HD int hadamard_quant2x2_skip(const int16_t in[4], int16_t ff, int16_t mf) {
   const int16_t thr = s16(65535 / mf - ff);
   int16_t d[4];
   hadamard2x2(in, d);
   return iabs(d[0]) > thr || iabs(d[1]) > thr || iabs(d[2]) > thr || iabs(d[3]) > thr;
 }
-__device__ __forceinline__ int hadamard_quant2x2(const int16_t in[4], int16_t ff, int16_t mf, int16_t out[4]) {
+MBK_HD int hadamard_quant2x2(const int16_t in[4], int16_t ff, int16_t mf, int16_t out[4]) {
   int16_t d[4];
   hadamard2x2(in, d);
   int nz = 0;
@@ -79,7 +79,7 @@ __device__ __forceinline__ int hadamard_quant2x2(const int16_t in[4], int16_t ff
 
 // I16x16 luma DC 4x4 Hadamard, (x+1)>>1, saturate (WelsHadamardT4Dc_c, encode_mb_aux.cpp:280).
 // dc_in[k] = DC of 4x4 block k in the reference's coefficient storage order (4 groups of 4 = 8x8 z-order).
-__device__ __forceinline__ void hadamard_t4_dc(int16_t out[16], const int16_t dc_in[16]) {
+MBK_HD void hadamard_t4_dc(int16_t out[16], const int16_t dc_in[16]) {
   int p[16];
 #pragma unroll
   for (int i = 0; i < 16; i += 4) {
@@ -100,18 +100,18 @@ __device__ __forceinline__ void hadamard_t4_dc(int16_t out[16], const int16_t dc
 }
 
 // frame zig-zag (WelsScan4x4DcAc_c / WelsScan4x4Ac_c, encode_mb_aux.cpp:371-401)
-__device__ __forceinline__ int zigzag_pos(int i) { return (int)((0xFEB7ADC963258410ull >> (4 * i)) & 0xf); }
-__device__ __forceinline__ void scan4x4_dcac(int16_t lv[16], const int16_t d[16]) {
+MBK_HD int zigzag_pos(int i) { return (int)((0xFEB7ADC963258410ull >> (4 * i)) & 0xf); }
+MBK_HD void scan4x4_dcac(int16_t lv[16], const int16_t d[16]) {
 #pragma unroll
   for (int i = 0; i < 16; i++) lv[i] = d[zigzag_pos(i)];
 }
-__device__ __forceinline__ void scan4x4_ac(int16_t lv[16], const int16_t d[16]) {
+MBK_HD void scan4x4_ac(int16_t lv[16], const int16_t d[16]) {
 #pragma unroll
   for (int i = 1; i < 16; i++) lv[i - 1] = d[zigzag_pos(i)];
   lv[15] = 0;
 }
 // JVT-O079 single-coefficient cost (WelsCalculateSingleCtr4x4_c, encode_mb_aux.cpp:418)
-__device__ __forceinline__ int single_ctr4x4(const int16_t lv[16]) {
+MBK_HD int single_ctr4x4(const int16_t lv[16]) {
   // every non-zero level costs T[number of zero levels directly below it], T = {3,2,2,1,1,1,0,...} (2 bits each)
   int total = 0, run = 0;
 #pragma unroll
@@ -121,7 +121,7 @@ __device__ __forceinline__ int single_ctr4x4(const int16_t lv[16]) {
   }
   return total;
 }
-__device__ __forceinline__ int nonzero_count(const int16_t lv[16]) {
+MBK_HD int nonzero_count(const int16_t lv[16]) {
   int n = 0;
 #pragma unroll
   for (int i = 0; i < 16; i++) n += lv[i] != 0;
@@ -129,11 +129,11 @@ __device__ __forceinline__ int nonzero_count(const int16_t lv[16]) {
 }
 
 // ---- dequant / inverse transforms (encoder/core/src/decode_mb_aux.cpp) ----
-__device__ __forceinline__ void dequant4x4(int16_t r[16], const uint16_t* mf) {
+MBK_HD void dequant4x4(int16_t r[16], const uint16_t* mf) {
 #pragma unroll
   for (int i = 0; i < 16; i++) r[i] = s16((int)r[i] * (int)mf[i & 7]);
 }
-__device__ __forceinline__ void ihadamard4x4(int16_t r[16]) {   // butterflies only, int16 storage
+MBK_HD void ihadamard4x4(int16_t r[16]) {   // butterflies only, int16 storage
 #pragma unroll
   for (int i = 0; i < 16; i += 4) {
     const int16_t a = s16(r[i] + r[i + 2]), b = s16(r[i] - r[i + 2]), c = s16(r[i + 1] - r[i + 3]), e = s16(r[i + 1] + r[i + 3]);
@@ -146,7 +146,7 @@ __device__ __forceinline__ void ihadamard4x4(int16_t r[16]) {   // butterflies o
   }
 }
 // WelsDequantIHadamard4x4_c (:98): inverse Hadamard then * mf (qp >= 12 path)
-__device__ __forceinline__ void dequant_ihadamard4x4(int16_t r[16], uint16_t mf) {
+MBK_HD void dequant_ihadamard4x4(int16_t r[16], uint16_t mf) {
 #pragma unroll
   for (int i = 0; i < 16; i += 4) {
     const int16_t a = s16(r[i] + r[i + 2]), b = s16(r[i] - r[i + 2]), c = s16(r[i + 1] - r[i + 3]), e = s16(r[i + 1] + r[i + 3]);
@@ -160,20 +160,20 @@ __device__ __forceinline__ void dequant_ihadamard4x4(int16_t r[16], uint16_t mf)
   }
 }
 // WelsDequantLumaDc4x4 (:80): qp < 12 luma DC scaling after WelsIHadamard4x4Dc
-__device__ __forceinline__ void dequant_luma_dc4x4(int16_t r[16], int qp) {
-  const int v = c_dequant[qp % 6][0];
+MBK_HD void dequant_luma_dc4x4(int16_t r[16], int qp) {
+  const int v = tbl_dequant(qp % 6)[0];
   const int qf0 = qp / 6, sh = 2 - qf0, rnd = 1 << (1 - qf0);
 #pragma unroll
   for (int i = 0; i < 16; i++) r[i] = s16(((int)r[i] * v + rnd) >> sh);
 }
 // WelsDequantIHadamard2x2Dc (:127)
-__device__ __forceinline__ void dequant_ihadamard2x2_dc(int16_t d[4], uint16_t mf) {
+MBK_HD void dequant_ihadamard2x2_dc(int16_t d[4], uint16_t mf) {
   const int16_t su = s16(d[0] + d[2]), du = s16(d[0] - d[2]), sd = s16(d[1] + d[3]), dd = s16(d[1] - d[3]);
   d[0] = s16(((su + sd) * (int)mf) >> 1); d[1] = s16(((su - sd) * (int)mf) >> 1);
   d[2] = s16(((du + dd) * (int)mf) >> 1); d[3] = s16(((du - dd) * (int)mf) >> 1);
 }
 // WelsIDctT4Rec_c (:164): inverse core transform + prediction + clip; row pass stored as int16
-__device__ __forceinline__ void idct4x4_rec(uint8_t* rec, int rs, const uint8_t* pred, int ps, const int16_t c[16]) {
+MBK_HD void idct4x4_rec(uint8_t* rec, int rs, const uint8_t* pred, int ps, const int16_t c[16]) {
   int16_t t[16];
 #pragma unroll
   for (int y = 0; y < 4; y++) {
@@ -192,7 +192,7 @@ __device__ __forceinline__ void idct4x4_rec(uint8_t* rec, int rs, const uint8_t*
 }
 
 // ---- decoder: IdctResAddPred_c / IdctResAddPred8x8_c (decoder/core/src/decode_mb_aux.cpp:42,79) ----
-__device__ __forceinline__ void idct_res_add_pred(uint8_t* pred, int stride, const int16_t rs[16]) {
+MBK_HD void idct_res_add_pred(uint8_t* pred, int stride, const int16_t rs[16]) {
   int16_t t[16];
 #pragma unroll
   for (int y = 0; y < 4; y++) {
@@ -209,7 +209,7 @@ __device__ __forceinline__ void idct_res_add_pred(uint8_t* pred, int stride, con
     pred[2 * stride + x] = (uint8_t)clip255(((32 + c - d) >> 6) + pred[2 * stride + x]);
   }
 }
-__device__ __forceinline__ void idct8_1d(const int16_t p[8], int16_t o[8]) {   // all int16, as the reference
+MBK_HD void idct8_1d(const int16_t p[8], int16_t o[8]) {   // all int16, as the reference
   int16_t a0 = s16(p[0] + p[4]), a1 = s16(p[0] - p[4]), a2 = s16(p[6] - (p[2] >> 1)), a3 = s16(p[2] + (p[6] >> 1));
   const int16_t b0 = s16(a0 + a3), b2 = s16(a1 - a2), b4 = s16(a1 + a2), b6 = s16(a0 - a3);
   a0 = s16(-p[3] + p[5] - p[7] - (p[7] >> 1));

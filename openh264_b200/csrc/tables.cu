@@ -22,11 +22,14 @@ int b2h264_launched() {
 }
 
 // host copies (also used by the host-side encoder)
+namespace mbk {
 int16_t h_quant_ff[58][8];
 int16_t h_quant_mf[52][8];
 uint16_t h_dequant[52][8];
 uint8_t h_lambda[52];
 uint8_t h_chroma_qp[52];
+}  // namespace mbk
+using namespace mbk;
 
 static void build_host_tables() {
   // 2x the standard's multiplication factors for qp%6 at position classes (0,0) / (0,1) / (1,1)

@@ -1,0 +1,134 @@
+// tests/emu/emu.cu — HOST EMULATION BUILD of the device macroblock pipeline (debugging aid).
+//
+// TEST INFRASTRUCTURE ONLY.  The macroblock code in openh264_b200/csrc/enc_*.cuh is written once as
+// __host__ __device__; this file compiles its HOST instantiation ("1-lane warp", see mbk_common.cuh)
+// and drives it in plain raster order, so that bit-exactness against the reference can be debugged in a
+// container without a GPU.  It is built into tests/emu/libb2h264_emu.so, which the product library
+// never links or loads; the shipped path is the CUDA one (enc_kernels.cu) and fails without a device.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../openh264_b200/csrc/enc_frame.cuh"
+#include "../../openh264_b200/csrc/h264_bitstream.h"
+
+#include "../../openh264_b200/csrc/enc_host.h"
+
+using namespace mbk;
+
+extern "C" void b2h264_build_host_tables();
+
+namespace {
+
+// host-memory twin of the product's device-side frame buffers
+struct HostFrameEncoder {
+  b2h264::StreamCtl ctl;
+  EncFrameParams p;
+  std::vector<uint8_t> cur[3], pic[2][3];
+  std::vector<MbInfo> mbi;
+  std::vector<RefMbInfo> rinfo[2];
+  std::vector<MbOut> out;
+  MbScratch scratch;
+  int cur_rec = 0;
+  bool idr = true, have_ref_p = false;
+
+  HostFrameEncoder(int w, int h, int qp, float fps) {
+    ctl.init(w, h, qp, fps, 5000000);
+    const int n = ctl.sp.mb_w * ctl.sp.mb_h;
+    cur[0].resize((size_t)n * 256 + 64); cur[1].resize((size_t)n * 64 + 64); cur[2].resize((size_t)n * 64 + 64);
+    for (int b = 0; b < 2; b++) {
+      pic[b][0].assign((size_t)ctl.rec_stride_y() * ctl.rec_rows_y() + 64, 0);
+      pic[b][1].assign((size_t)ctl.rec_stride_c() * ctl.rec_rows_c() + 64, 0);
+      pic[b][2].assign((size_t)ctl.rec_stride_c() * ctl.rec_rows_c() + 64, 0);
+      rinfo[b].resize(n);
+    }
+    mbi.resize(n); out.resize(n);
+    memset(&scratch, 0, sizeof(scratch));
+  }
+  void load_source(const uint8_t* yuv) {
+    b2h264::pad_source(yuv, ctl.sp.width, ctl.sp.height, ctl.sp.mb_w, ctl.sp.mb_h, cur[0].data(), cur[1].data(), cur[2].data());
+  }
+  void begin_frame() {
+    idr = ctl.next_is_idr();
+    p = ctl.frame_params(idr, have_ref_p);
+  }
+  uint8_t* plane0(int b, int pl) {   // pixel (0,0) inside the padding
+    const int pad = pl ? 16 : 32, st = pl ? ctl.rec_stride_c() : ctl.rec_stride_y();
+    return pic[b][pl].data() + (size_t)pad * st + pad;
+  }
+  EncFramePtrs ptrs() {
+    EncFramePtrs f;
+    memset(&f, 0, sizeof(f));
+    for (int pl = 0; pl < 3; pl++) { f.cur[pl] = cur[pl].data(); f.rec[pl] = plane0(cur_rec, pl); f.ref[pl] = plane0(1 - cur_rec, pl); }
+    f.mbi = mbi.data(); f.rec_info = rinfo[cur_rec].data(); f.ref_info = rinfo[1 - cur_rec].data(); f.out = out.data();
+    return f;
+  }
+  void finish_frame(std::vector<uint8_t>* bs) {
+    ctl.write_access_unit(idr, out.data(), bs);
+    have_ref_p = !idr;
+    cur_rec = 1 - cur_rec;            // the picture just reconstructed becomes the reference
+  }
+  void copy_recon(uint8_t* dst) {     // cropped I420 of the picture just finished (now the reference)
+    const int b = 1 - cur_rec;
+    for (int pl = 0; pl < 3; pl++) {
+      const int w = pl ? ctl.sp.width / 2 : ctl.sp.width, h = pl ? ctl.sp.height / 2 : ctl.sp.height;
+      const int st = pl ? ctl.rec_stride_c() : ctl.rec_stride_y();
+      for (int y = 0; y < h; y++) { memcpy(dst, plane0(b, pl) + (size_t)y * st, w); dst += w; }
+    }
+  }
+};
+
+void deblock_frame_host(const EncFrameParams& p, const EncFramePtrs& f);
+void expand_frame_host(const EncFrameParams& p, const EncFramePtrs& f) {
+  for (int pl = 0; pl < 3; pl++) {
+    const int pad = pl ? 16 : 32, st = pl ? p.rec_stride_c : p.rec_stride_y;
+    const int w = (pl ? 8 : 16) * p.mb_w, h = (pl ? 8 : 16) * p.mb_h;
+    uint8_t* pic = f.rec[pl];
+    for (int y = 0; y < h; y++) { memset(pic + (size_t)y * st - pad, pic[(size_t)y * st], pad); memset(pic + (size_t)y * st + w, pic[(size_t)y * st + w - 1], pad); }
+    for (int y = 1; y <= pad; y++) {
+      memcpy(pic - (ptrdiff_t)y * st - pad, pic - pad, w + 2 * pad);
+      memcpy(pic + (size_t)(h - 1 + y) * st - pad, pic + (size_t)(h - 1) * st - pad, w + 2 * pad);
+    }
+  }
+}
+#ifndef B2H264_WITH_INTER
+void deblock_frame_host(const EncFrameParams&, const EncFramePtrs&) {}
+#endif
+
+}  // namespace
+
+static std::vector<MbOut> g_last_out;
+static std::vector<MbInfo> g_last_info;
+extern "C" int emu_last(MbOut* out, MbInfo* info, int n) {
+  if ((int)g_last_out.size() < n) return -1;
+  if (out) memcpy(out, g_last_out.data(), sizeof(MbOut) * n);
+  if (info) memcpy(info, g_last_info.data(), sizeof(MbInfo) * n);
+  return 0;
+}
+extern "C" long emu_encode(const uint8_t* yuv, int w, int h, int nframes, int qp, float fps, uint8_t* out, long cap,
+                           int32_t* frame_bytes, uint8_t* recon_out /* nframes * w*h*3/2 or NULL */) {
+  b2h264_build_host_tables();
+  HostFrameEncoder enc(w, h, qp, fps);
+  long total = 0;
+  const size_t fsz = (size_t)w * h * 3 / 2;
+  for (int i = 0; i < nframes; i++) {
+    std::vector<uint8_t> bs;
+    enc.load_source(yuv + i * fsz);
+    enc.begin_frame();
+    // --- the part the GPU does in the product: macroblocks (raster order here), deblocking, expansion
+    for (int mby = 0; mby < enc.p.mb_h; mby++)
+      for (int mbx = 0; mbx < enc.p.mb_w; mbx++) encode_one_mb(enc.p, enc.ptrs(), enc.scratch, mbx, mby);
+    deblock_frame_host(enc.p, enc.ptrs());
+    expand_frame_host(enc.p, enc.ptrs());
+    // --- host entropy coding
+    g_last_out = enc.out; g_last_info = enc.mbi;
+    enc.finish_frame(&bs);
+    if (total + (long)bs.size() > cap) return -1;
+    memcpy(out + total, bs.data(), bs.size());
+    total += bs.size();
+    if (frame_bytes) frame_bytes[i] = (int32_t)bs.size();
+    if (recon_out) enc.copy_recon(recon_out + i * fsz);
+  }
+  return total;
+}

@@ -28,7 +28,7 @@ MBK_HD void encode_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScra
   mb_load_borders(c, s);
   if (p.is_idr) {
     intra_mb_md_enc(c, s, 0x7fffffff);
-    if (lane_id() == 0) { s.info.ref_idx = -2; s.info.sad_cost = 0; }
+    if (lane_id() == 0) { s.info.ref_idx = -1; c.f.sad_cost[mby * p.mb_w + mbx] = 0; }   // pSadCost[0] = 0 (:2038)
   }
 #ifdef B2H264_WITH_INTER
   else {

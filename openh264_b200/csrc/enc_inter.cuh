@@ -1,0 +1,618 @@
+// enc_inter.cuh — P-slice macroblock mode decision and coding for one macroblock owned by one warp.
+// Restates the decision order of
+//   WelsMdInterMb / WelsMdInterJudgePskip / WelsMdPSkipEnc / WelsMdP16x16 / WelsMdP16x8 / WelsMdP8x16 /
+//   WelsMdP8x8 / WelsMdInterFinePartition / WelsMdInterMbRefinement / WelsMdFirstIntraMode /
+//   WelsMdInterEncode / WelsMdInterDoubleCheckPskip      codec/encoder/core/src/svc_base_layer_md.cpp:978-2021
+//   MeRefineFracPixel, PredictSad, PredictSadSkip, FillNeighborCacheInterWithoutBGD  .../src/md.cpp:132-250,575-790,826-910
+//   PredMv, PredInter16x8Mv, PredInter8x16Mv, PredSkipMv and the cache updates        .../src/mv_pred.cpp
+//   WelsEncInterY, WelsTryPYskip, WelsTryPUVskip                                      .../src/svc_encode_mb.cpp:180-383
+// for CAMERA_VIDEO_REAL_TIME, complexity MEDIUM/HIGH (SATD costs, all partitions), no BGD/AQ/scene detect.
+#pragma once
+#include "enc_mb.cuh"
+#include "mbk_mc.cuh"
+#include "mbk_me.cuh"
+
+namespace mbk {
+
+#define REF_NOT_AVAIL (-2)
+#define REF_NOT_IN_LIST (-1)
+
+// motion cache: 6 columns x 5 rows, index = row*6 + col; the MB's 4x4 blocks sit at rows 1..4, cols 1..4
+// (g_kuiCache30ScanIdx, common_tables.cpp): cache index of 4x4 block k (coding order)
+MBK_HD int cache30(int k) { return 7 + blk_y(k) * 6 + blk_x(k); }
+
+struct MeState {            // the parts of SWelsME the later stages need
+  int mv_x, mv_y;           // quarter-pel
+  int mvp_x, mvp_y;
+  uint32_t sad_cost, satd_cost;
+  int satd;                 // raw SATD at the integer position (uSadPredISatd.uiSatd)
+  const uint8_t* ref;       // integer-position block in the reference plane
+};
+
+MBK_HD int median3(int a, int b, int c) {
+  const int mn = a < b ? a : b, mx = a < b ? b : a;
+  return c < mn ? mn : (c > mx ? mx : c);
+}
+
+// ---- neighbour caches (FillNeighborCacheInterWithoutBGD, md.cpp:132) ----------------------------------
+MBK_HD void fill_inter_cache(const MbCtx& c, MbScratch& s) {
+  if (lane_id() == 0) {
+    const int mbw = c.p.mb_w, idx = c.mby * mbw + c.mbx;
+    const MbInfo* cur = c.f.mbi + idx;
+    for (int i = 0; i < 30; i++) { s.mvc[i][0] = s.mvc[i][1] = 0; s.refc[i] = 0; }
+    // slot: 0 top-left, 1 top, 2 top-right, 3 left
+    const int offs[4] = {-mbw - 1, -mbw, -mbw + 1, -1};
+    const int bits[4] = {NB_TOPLEFT, NB_TOP, NB_TOPRIGHT, NB_LEFT};
+    for (int k = 0; k < 4; k++) {
+      const bool avail = (c.nb & bits[k]) != 0;
+      const MbInfo* n = cur + offs[k];
+      const bool inter = avail && MBT_IS_INTER(n->mb_type);
+      const int8_t na = avail ? REF_NOT_IN_LIST : REF_NOT_AVAIL;
+      s.sadc[k] = inter ? c.f.sad_cost[idx + offs[k]] : 0;
+      const bool skip = inter && n->mb_type == MBT_PSKIP;
+      s.skip_flag[k] = skip;
+      s.sad_skip[k] = skip ? c.f.rec_info[idx + offs[k]].skip_sad : 0;
+      if (k == 3) {          // left column: cache 6,12,18,24 <- right column of the left MB
+        for (int r = 0; r < 4; r++) {
+          const int ci = 6 + 6 * r;
+          if (inter) { s.mvc[ci][0] = n->mv[4 * r + 3][0]; s.mvc[ci][1] = n->mv[4 * r + 3][1]; s.refc[ci] = 0; }
+          else s.refc[ci] = na;
+        }
+      } else if (k == 1) {   // top row: cache 1..4 <- bottom row of the top MB
+        for (int x = 0; x < 4; x++) {
+          if (inter) { s.mvc[1 + x][0] = n->mv[12 + x][0]; s.mvc[1 + x][1] = n->mv[12 + x][1]; s.refc[1 + x] = 0; }
+          else s.refc[1 + x] = na;
+        }
+      } else if (k == 0) {
+        if (inter) { s.mvc[0][0] = n->mv[15][0]; s.mvc[0][1] = n->mv[15][1]; s.refc[0] = 0; }
+        else s.refc[0] = na;
+      } else {
+        if (inter) { s.mvc[5][0] = n->mv[12][0]; s.mvc[5][1] = n->mv[12][1]; s.refc[5] = 0; }
+        else s.refc[5] = na;
+      }
+    }
+    // blocks whose top-right neighbour is never available
+    s.refc[9] = s.refc[11] = s.refc[17] = s.refc[21] = s.refc[23] = REF_NOT_AVAIL;
+  }
+  warp_sync();
+}
+
+// ---- motion vector prediction (mv_pred.cpp:45-150) ----------------------------------------------------
+MBK_HD void pred_mv(const MbScratch& s, int blk /*coding idx*/, int part_w, int ref, int* px, int* py) {
+  const int left = cache30(blk) - 1, top = cache30(blk) - 6;
+  const int lr = s.refc[left], tr = s.refc[top], rtr = s.refc[top + part_w];
+  int dr, dmx, dmy;
+  if (rtr == REF_NOT_AVAIL) { dr = s.refc[top - 1]; dmx = s.mvc[top - 1][0]; dmy = s.mvc[top - 1][1]; }
+  else { dr = rtr; dmx = s.mvc[top + part_w][0]; dmy = s.mvc[top + part_w][1]; }
+  if (tr == REF_NOT_AVAIL && dr == REF_NOT_AVAIL && lr != REF_NOT_AVAIL) { *px = s.mvc[left][0]; *py = s.mvc[left][1]; return; }
+  const int match = (ref == lr ? 1 : 0) | (ref == tr ? 2 : 0) | (ref == dr ? 4 : 0);
+  if (match == 1) { *px = s.mvc[left][0]; *py = s.mvc[left][1]; }
+  else if (match == 2) { *px = s.mvc[top][0]; *py = s.mvc[top][1]; }
+  else if (match == 4) { *px = dmx; *py = dmy; }
+  else { *px = median3(s.mvc[left][0], s.mvc[top][0], dmx); *py = median3(s.mvc[left][1], s.mvc[top][1], dmy); }
+}
+MBK_HD void pred_16x8_mv(const MbScratch& s, int blk, int ref, int* px, int* py) {
+  if (blk == 0) { if (ref == s.refc[1]) { *px = s.mvc[1][0]; *py = s.mvc[1][1]; return; } }
+  else { if (ref == s.refc[18]) { *px = s.mvc[18][0]; *py = s.mvc[18][1]; return; } }
+  pred_mv(s, blk, 4, ref, px, py);
+}
+MBK_HD void pred_8x16_mv(const MbScratch& s, int blk, int ref, int* px, int* py) {
+  if (blk == 0) { if (ref == s.refc[6]) { *px = s.mvc[6][0]; *py = s.mvc[6][1]; return; } }
+  else {
+    int di = 5;
+    if (s.refc[5] == REF_NOT_AVAIL) di = 2;
+    if (ref == s.refc[di]) { *px = s.mvc[di][0]; *py = s.mvc[di][1]; return; }
+  }
+  pred_mv(s, blk, 2, ref, px, py);
+}
+MBK_HD void pred_skip_mv(const MbScratch& s, int* px, int* py) {
+  const int lr = s.refc[6], tr = s.refc[1];
+  if (lr == REF_NOT_AVAIL || tr == REF_NOT_AVAIL || (lr == 0 && s.mvc[6][0] == 0 && s.mvc[6][1] == 0) ||
+      (tr == 0 && s.mvc[1][0] == 0 && s.mvc[1][1] == 0)) { *px = 0; *py = 0; return; }
+  pred_mv(s, 0, 4, 0, px, py);
+}
+// writes (ref 0, mv) into a w4 x h4 rectangle of cache cells starting at block `blk`
+MBK_HD void cache_set(MbScratch& s, int blk, int w4, int h4, int mvx, int mvy) {
+  if (lane_id() == 0) {
+    const int c0 = cache30(blk);
+    for (int y = 0; y < h4; y++)
+      for (int x = 0; x < w4; x++) { s.mvc[c0 + 6 * y + x][0] = (int16_t)mvx; s.mvc[c0 + 6 * y + x][1] = (int16_t)mvy; s.refc[c0 + 6 * y + x] = 0; }
+  }
+  warp_sync();
+}
+MBK_HD void mb_mv_set(MbScratch& s, int blk, int w4, int h4, int mvx, int mvy) {
+  if (lane_id() == 0) {
+    const int x0 = blk_x(blk), y0 = blk_y(blk);
+    for (int y = 0; y < h4; y++)
+      for (int x = 0; x < w4; x++) { s.info.mv[(y0 + y) * 4 + x0 + x][0] = (int16_t)mvx; s.info.mv[(y0 + y) * 4 + x0 + x][1] = (int16_t)mvy; }
+  }
+  warp_sync();
+}
+
+// ---- SAD predictors (md.cpp:826-910) ---------------------------------------------------------------------
+MBK_HD int predict_sad(const MbScratch& s) {
+  const int rb = s.refc[1], ra = s.refc[6];
+  int rc = s.refc[5], sc = s.sadc[2];
+  const int sb = s.sadc[1], sa = s.sadc[3];
+  if (rc == REF_NOT_AVAIL) { rc = s.refc[0]; sc = s.sadc[0]; }
+  int pred;
+  if (rb == REF_NOT_AVAIL && rc == REF_NOT_AVAIL && ra != REF_NOT_AVAIL) pred = sa;
+  else {
+    const int m = (0 == ra ? 1 : 0) | (0 == rb ? 2 : 0) | (0 == rc ? 4 : 0);
+    pred = m == 1 ? sa : m == 2 ? sb : m == 4 ? sc : median3(sa, sb, sc);
+  }
+  const int t = pred << 6;
+  return ((t - (t >> 3) + (t >> 5)) + 32) >> 6;
+}
+MBK_HD int predict_sad_skip(const MbScratch& s) {
+  const int rb = s.refc[1], ra = s.refc[6];
+  int rc = s.refc[5];
+  const int sb = s.skip_flag[1] ? s.sad_skip[1] : 0, sa = s.skip_flag[3] ? s.sad_skip[3] : 0;
+  int sc = s.skip_flag[2] ? s.sad_skip[2] : 0, rskip = s.skip_flag[2];
+  if (rc == REF_NOT_AVAIL) { rc = s.refc[0]; sc = s.skip_flag[0] ? s.sad_skip[0] : 0; rskip = s.skip_flag[0]; }
+  if (rb == REF_NOT_AVAIL && rc == REF_NOT_AVAIL && ra != REF_NOT_AVAIL) return sa;
+  const int m = ((0 == ra && s.skip_flag[3]) ? 1 : 0) | ((0 == rb && s.skip_flag[1]) ? 2 : 0) | ((0 == rc && rskip) ? 4 : 0);
+  return m == 1 ? sa : m == 2 ? sb : m == 4 ? sc : median3(sa, sb, sc);
+}
+
+// ---- reference plane access ------------------------------------------------------------------------------
+MBK_HD const uint8_t* ref_luma(const MbCtx& c, int px, int py) {
+  return c.f.ref[0] + (ptrdiff_t)(c.mby * 16 + py) * c.p.rec_stride_y + c.mbx * 16 + px;
+}
+MBK_HD const uint8_t* ref_chroma(const MbCtx& c, int pl, int px, int py) {
+  return c.f.ref[pl] + (ptrdiff_t)(c.mby * 8 + py) * c.p.rec_stride_c + c.mbx * 8 + px;
+}
+
+// chroma prediction of a (w x h luma) partition at luma offset (ox, oy) with quarter-pel luma mv
+MBK_HD void mc_chroma_part(const MbCtx& c, uint8_t* dst /*Cb, Cr at +64, stride 8*/, int ox, int oy, int w, int h, int mvx, int mvy) {
+  const int cx = ox >> 1, cy = oy >> 1;
+  for (int pl = 0; pl < 2; pl++) {
+    const uint8_t* src = ref_chroma(c, 1 + pl, cx + (mvx >> 3), cy + (mvy >> 3));
+    warp_mc_chroma(src, c.p.rec_stride_c, dst + 64 * pl + cy * 8 + cx, 8, mvx, mvy, w >> 1, h >> 1);
+  }
+  warp_sync();
+}
+
+// ---- P-skip test (WelsMdPSkipEnc :1423, WelsTryPYskip / WelsTryPUVskip svc_encode_mb.cpp:325,352) -----------
+struct SkipResult { bool ok; int cost_luma; int cost_skip; int mvx, mvy; };
+
+MBK_HD bool try_py_skip(const MbCtx& c, MbScratch& s) {      // lane-0 logic replicated by every lane (uniform)
+  const int16_t* ff = tbl_quant_ff(c.qp);
+  const int16_t* mf = tbl_quant_mf(c.qp);
+  int ctr = 0;
+  for (int k = 0; k < 16; k++) {
+    int16_t d[16], l[16];
+    for (int i = 0; i < 16; i++) d[i] = s.coef[16 * k + i];
+    const uint16_t mx = (uint16_t)quant4x4_max(d, ff, mf);
+    if (mx > 1) return false;
+    if (mx == 1) { scan4x4_dcac(l, d); ctr += single_ctr4x4(l); }
+    if (ctr >= 6) return false;
+  }
+  return true;
+}
+MBK_HD bool try_puv_skip(const MbCtx& c, MbScratch& s, int uv) {
+  const int16_t* res = s.coef + 256 + 64 * uv;
+  const int16_t* ff = tbl_quant_ff(c.qp_c);
+  const int16_t* mf = tbl_quant_mf(c.qp_c);
+  const int16_t dcin[4] = {res[0], res[16], res[32], res[48]};
+  if (hadamard_quant2x2_skip(dcin, (int16_t)(ff[0] << 1), (int16_t)(mf[0] >> 1))) return false;
+  int ctr = 0;
+  for (int j = 0; j < 4; j++) {
+    int16_t d[16], l[16];
+    for (int i = 0; i < 16; i++) d[i] = res[16 * j + i];
+    const uint16_t mx = (uint16_t)quant4x4_max(d, ff, mf);
+    if (mx > 1) return false;
+    if (mx == 1) { scan4x4_ac(l, d); ctr += single_ctr4x4(l); }
+    if (ctr >= 7) return false;
+  }
+  return true;
+}
+MBK_HD void dct_luma_mb(MbScratch& s, const uint8_t* pred /*stride 16*/) {
+  for (int k = lane_id(); k < 16; k += MBK_WS) {
+    int16_t d[16];
+    const int o = blk_y(k) * 4 * 16 + blk_x(k) * 4;
+    dct4x4(d, s.cur_y + o, 16, pred + o, 16);
+    for (int i = 0; i < 16; i++) s.coef[16 * k + i] = d[i];
+  }
+  warp_sync();
+}
+
+MBK_HD SkipResult pskip_enc(const MbCtx& c, MbScratch& s, int sad_pred_skip, int ref_mb_type) {
+  SkipResult r;
+  r.ok = false; r.cost_luma = 0; r.cost_skip = 0;
+  int mvx, mvy;
+  pred_skip_mv(s, &mvx, &mvy);
+  r.mvx = mvx; r.mvy = mvy;
+  const int ix = mvx >> 2, iy = mvy >> 2;
+  int n = c.mbx * 16 + ix;
+  if (n < -29 || n > c.p.mb_w * 16 + 12) return r;
+  n = c.mby * 16 + iy;
+  if (n < -29 || n > c.p.mb_h * 16 + 12) return r;
+  uint8_t* py = s.skip_pred;
+  warp_mc_luma(ref_luma(c, ix, iy), c.p.rec_stride_y, py, 16, mvx, mvy, 16, 16);
+  warp_sync();
+  const int sad_y = warp_sad(s.cur_y, 16, py, 16, 4, 4);
+  // NB the reference derives the chroma offset from the INTEGER luma vector: (ix >> 1, iy >> 1)
+  for (int pl = 0; pl < 2; pl++)
+    warp_mc_chroma(ref_chroma(c, 1 + pl, ix >> 1, iy >> 1), c.p.rec_stride_c, s.skip_pred + 256 + 64 * pl, 8, mvx, mvy, 8, 8);
+  warp_sync();
+  const int sad_c = warp_sad(s.cur_c, 8, s.skip_pred + 256, 8, 3, 3) + warp_sad(s.cur_c + 64, 8, s.skip_pred + 320, 8, 3, 3);
+  const int sad_mb = sad_y + sad_c;
+  bool ok = sad_mb == 0 || sad_mb < sad_pred_skip ||
+            (c.p.ref_is_p && ref_mb_type == MBT_PSKIP && sad_mb < c.f.ref_info[c.mby * c.p.mb_w + c.mbx].skip_sad);
+  if (!ok) {
+    dct_luma_mb(s, py);
+    if (try_py_skip(c, s)) {
+      for (int t = lane_id(); t < 4; t += MBK_WS) {
+        int16_t d[16];
+        const int ox = (t & 1) * 4, oy = (t >> 1) * 4;
+        dct4x4(d, s.cur_c + oy * 8 + ox, 8, s.skip_pred + 256 + oy * 8 + ox, 8);
+        for (int i = 0; i < 16; i++) s.coef[256 + 16 * t + i] = d[i];
+      }
+      warp_sync();
+      if (try_puv_skip(c, s, 0)) {
+        for (int t = lane_id(); t < 4; t += MBK_WS) {
+          int16_t d[16];
+          const int ox = (t & 1) * 4, oy = (t >> 1) * 4;
+          dct4x4(d, s.cur_c + 64 + oy * 8 + ox, 8, s.skip_pred + 320 + oy * 8 + ox, 8);
+          for (int i = 0; i < 16; i++) s.coef[320 + 16 * t + i] = d[i];
+        }
+        warp_sync();
+        ok = try_puv_skip(c, s, 1);
+      }
+    }
+  }
+  if (ok) {
+    r.ok = true;
+    r.cost_luma = warp_satd(s.cur_y, 16, py, 16, 4, 4);
+    r.cost_skip = sad_mb;
+  }
+  return r;
+}
+
+// ---- integer search of one partition ------------------------------------------------------------------------
+MBK_HD void me_partition(const MbCtx& c, MbScratch& s, int blk_size, int ox, int oy, int mvp_x, int mvp_y, uint32_t sad_pred,
+                         int n_mvc, const int16_t* mvc, MeState* st) {
+  MeIn in;
+  in.enc = s.cur_y + oy * 16 + ox; in.enc_stride = 16;
+  in.ref = ref_luma(c, ox, oy); in.ref_stride = c.p.rec_stride_y;
+  in.blk = blk_size;
+  in.mvp_x = mvp_x; in.mvp_y = mvp_y;
+  // SetMvWithinIntegerMvRange (svc_motion_estimate.h:345): one window per MB, shared by its partitions
+  const int r = c.p.mv_range;
+  const int lo_x = -((c.mbx + 1) << 4) + 3, lo_y = -((c.mby + 1) << 4) + 3;
+  const int hi_x = ((c.p.mb_w - c.mbx) << 4) - 3, hi_y = ((c.p.mb_h - c.mby) << 4) - 3;
+  in.min_x = lo_x > -r ? lo_x : -r; in.min_y = lo_y > -r ? lo_y : -r;
+  in.max_x = hi_x < r ? hi_x : r; in.max_y = hi_y < r ? hi_y : r;
+  in.n_mvc = n_mvc; in.mvc = mvc;
+  in.sad_pred = sad_pred;
+  in.lambda = c.lambda;
+  in.calc_satd = true;
+  MeOut o;
+  warp_me_search(in, o);
+  st->mv_x = o.mv_x; st->mv_y = o.mv_y; st->mvp_x = mvp_x; st->mvp_y = mvp_y;
+  st->sad_cost = o.sad_cost; st->satd_cost = o.satd_cost;
+  st->satd = (int)o.satd_cost - mvd_cost(c.lambda, o.mv_x - mvp_x, o.mv_y - mvp_y);
+  st->ref = o.ref_best;
+}
+
+// ---- fractional refinement (MeRefineFracPixel, md.cpp:575) ------------------------------------------------------
+// candidate cost = SATD(enc, McLuma(ref, mv)) + mvd cost, visited in the reference's order with strict '<';
+// the winning prediction is left in dst (stride 16).
+MBK_HD void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy, int w, int h, uint8_t* dst) {
+  const int lw = w == 16 ? 4 : 3, lh = h == 16 ? 4 : 3;
+  const uint8_t* enc = s.cur_y + oy * 16 + ox;
+  const int rs = c.p.rec_stride_y;
+  const int px = st->mvp_x, py = st->mvp_y;
+  int best = st->satd + mvd_cost(c.lambda, st->mv_x - px, st->mv_y - py);
+  uint8_t* tmp = s.me_buf[0];
+  auto eval = [&](int mvx, int mvy) {
+    // st->ref sits at the integer MV; candidate integer part relative to it
+    const int dx = (mvx >> 2) - (st->mv_x >> 2), dy = (mvy >> 2) - (st->mv_y >> 2);
+    warp_mc_luma(st->ref + dy * rs + dx, rs, tmp, 32, mvx, mvy, w, h);
+    warp_sync();
+    const int cost = warp_satd(enc, 16, tmp, 32, lw, lh) + mvd_cost(c.lambda, mvx - px, mvy - py);
+    warp_sync();
+    return cost;
+  };
+  int hx = st->mv_x, hy = st->mv_y;
+  {
+    const int ddx[4] = {0, 0, -2, 2}, ddy[4] = {-2, 2, 0, 0};
+    int bi = -1;
+    for (int i = 0; i < 4; i++) {
+      const int cst = eval(st->mv_x + ddx[i], st->mv_y + ddy[i]);
+      if (cst < best) { best = cst; bi = i; }
+    }
+    if (bi >= 0) { hx += ddx[bi]; hy += ddy[bi]; }
+  }
+  int fx = hx, fy = hy;
+  {
+    const int ddx[4] = {0, 0, -1, 1}, ddy[4] = {-1, 1, 0, 0};
+    int bi = -1;
+    for (int i = 0; i < 4; i++) {
+      const int cst = eval(hx + ddx[i], hy + ddy[i]);
+      if (cst < best) { best = cst; bi = i; }
+    }
+    if (bi >= 0) { fx += ddx[bi]; fy += ddy[bi]; }
+  }
+  // final prediction
+  {
+    const int dx = (fx >> 2) - (st->mv_x >> 2), dy = (fy >> 2) - (st->mv_y >> 2);
+    warp_mc_luma(st->ref + dy * rs + dx, rs, dst, 16, fx, fy, w, h);
+    warp_sync();
+  }
+  st->mv_x = fx; st->mv_y = fy;
+  st->satd_cost = (uint32_t)best;
+}
+
+// ---- luma residual of an inter MB (WelsEncInterY, svc_encode_mb.cpp:180) -------------------------------------------
+MBK_HD void enc_inter_y(const MbCtx& c, MbScratch& s) {
+  const int16_t* ff = tbl_quant_ff(c.qp);
+  const int16_t* mf = tbl_quant_mf(c.qp);
+  // per-block quantisation / scan in parallel; the JVT-O079 accumulation is order dependent -> serial scalar part
+  for (int k = lane_id(); k < 16; k += MBK_WS) {
+    int16_t d[16], l[16];
+    for (int i = 0; i < 16; i++) d[i] = s.coef[16 * k + i];
+    const int16_t mx = quant4x4_max(d, ff, mf);
+    if (mx == 0) { for (int i = 0; i < 16; i++) l[i] = 0; }
+    else scan4x4_dcac(l, d);
+    for (int i = 0; i < 16; i++) { s.coef[16 * k + i] = d[i]; s.out.luma[k][i] = l[i]; }
+    s.red[k] = mx;
+    s.red[16 + k] = mx == 0 ? 0 : single_ctr4x4(l);
+  }
+  warp_sync();
+  int ctr8[4], ctr_mb = 0;
+  for (int i = 0; i < 4; i++) {
+    ctr8[i] = 0;
+    for (int j = 0; j < 4; j++) {
+      const int mx = s.red[4 * i + j];
+      if (mx == 0) continue;
+      if (mx > 1) ctr8[i] += 9;
+      else if (ctr8[i] < 6) ctr8[i] += s.red[16 + 4 * i + j];
+    }
+    ctr_mb += ctr8[i];
+  }
+  for (int i = lane_id(); i < 16; i += MBK_WS) s.info.nnz[i] = 0;
+  warp_sync();
+  if (ctr_mb < 6) {
+    for (int i = lane_id(); i < 256; i += MBK_WS) s.coef[i] = 0;
+  } else {
+    for (int k = lane_id(); k < 16; k += MBK_WS) {
+      if (ctr8[k >> 2] >= 4) {
+        s.info.nnz[blk_raster(k)] = (int8_t)nonzero_count(s.out.luma[k]);
+        int16_t d[16];
+        for (int i = 0; i < 16; i++) d[i] = s.coef[16 * k + i];
+        dequant4x4(d, tbl_dequant(c.qp));
+        for (int i = 0; i < 16; i++) s.coef[16 * k + i] = d[i];
+      } else {
+        for (int i = 0; i < 16; i++) s.coef[16 * k + i] = 0;
+      }
+    }
+    if (lane_id() == 0)
+      for (int i = 0; i < 4; i++) if (ctr8[i] >= 4) s.info.cbp |= (uint8_t)(1 << i);
+  }
+  warp_sync();
+}
+
+// luma reconstruction of an inter MB: pred + IDCT(coef) for all 16 blocks (OutputPMbWithoutConstructCsRsNoCopy)
+MBK_HD void rec_luma_inter(MbScratch& s, const uint8_t* pred) {
+  for (int k = lane_id(); k < 16; k += MBK_WS) {
+    int16_t d[16];
+    for (int i = 0; i < 16; i++) d[i] = s.coef[16 * k + i];
+    const int oy = blk_y(k) * 4, ox = blk_x(k) * 4;
+    idct4x4_rec(tile_y(s.tile, ox, oy), TY_PITCH, pred + oy * 16 + ox, 16, d);
+  }
+  warp_sync();
+}
+
+// ---- decided skip (WelsMdInterDecidedPskip :1954 + WelsRecPskip svc_encode_mb.cpp:315) ------------------------------
+MBK_HD void decided_pskip(const MbCtx& c, MbScratch& s) {
+  for (int i = lane_id(); i < 256; i += MBK_WS) *tile_y(s.tile, i & 15, i >> 4) = s.skip_pred[i];
+  for (int i = lane_id(); i < 64; i += MBK_WS) {
+    *tile_c(s.tile.u, i & 7, i >> 3) = s.skip_pred[256 + i];
+    *tile_c(s.tile.v, i & 7, i >> 3) = s.skip_pred[320 + i];
+  }
+  if (lane_id() == 0) {
+    s.info.mb_type = MBT_PSKIP;
+    s.info.cbp = 0;
+    for (int i = 0; i < 24; i++) s.info.nnz[i] = 0;
+  }
+  warp_sync();
+}
+
+// ---- the P-slice macroblock (WelsMdInterMb :1858 + WelsMdInterSecondaryModesEnc :1997) --------------------------------
+MBK_HD void inter_mb_md_enc(const MbCtx& c, MbScratch& s) {
+  const int mbw = c.p.mb_w, idx = c.mby * mbw + c.mbx;
+  fill_inter_cache(c, s);
+  const int ref_mb_type = c.p.ref_is_p ? c.f.ref_info[idx].mb_type : 0xff;
+  int p16_mvx = 0, p16_mvy = 0;                       // sP16x16Mv / sMvList (WelsMdInterInit :352-353)
+  const MbInfo* cur = c.f.mbi + idx;
+  const bool sk_l = (c.nb & NB_LEFT) && cur[-1].mb_type == MBT_PSKIP;
+  const bool sk_t = (c.nb & NB_TOP) && cur[-mbw].mb_type == MBT_PSKIP;
+  const bool sk_tl = (c.nb & NB_TOPLEFT) && cur[-mbw - 1].mb_type == MBT_PSKIP;
+  const bool sk_tr = (c.nb & NB_TOPRIGHT) && cur[-mbw + 1].mb_type == MBT_PSKIP;
+  const bool try_skip = sk_l || sk_t || sk_tl || sk_tr;
+  const bool keep_skip = sk_l && sk_t && sk_tr;
+  int cost_luma = 0, cost_skip_mb = 0;
+  bool is_skip = false;
+  // step 1: SKIP (WelsMdInterJudgePskip :1906)
+  if ((c.p.ref_is_p && ref_mb_type == MBT_PSKIP) || try_skip) {
+    const SkipResult r = pskip_enc(c, s, predict_sad_skip(s), ref_mb_type);
+    if (r.ok) {
+      is_skip = true;
+      cost_luma = r.cost_luma; cost_skip_mb = r.cost_skip;
+      p16_mvx = r.mvx; p16_mvy = r.mvy;
+      mb_mv_set(s, 0, 4, 4, r.mvx, r.mvy);
+    }
+  }
+  MeState me16, me16x8[2], me8x16[2], me8x8[4];
+  int final_type = MBT_P16x16;
+  bool done = false;
+  if (is_skip && keep_skip) {
+    decided_pskip(c, s);
+    final_type = MBT_PSKIP;
+    done = true;
+  }
+  int sad_pred_mb = 0;
+  if (!done && !is_skip) {
+    sad_pred_mb = predict_sad(s);
+    // step 2: P16x16 (WelsMdP16x16 :978)
+    int16_t mvc[5][2];
+    int n = 0;
+    mvc[n][0] = 0; mvc[n][1] = 0; n++;                                    // sMvBase
+    if (c.nb & NB_LEFT) { mvc[n][0] = cur[-1].p16x16_mv[0]; mvc[n][1] = cur[-1].p16x16_mv[1]; n++; }
+    if (c.nb & NB_TOP) { mvc[n][0] = cur[-mbw].p16x16_mv[0]; mvc[n][1] = cur[-mbw].p16x16_mv[1]; n++; }
+    if (c.p.ref_is_p) {
+      if (c.mbx < mbw - 1) { mvc[n][0] = c.f.ref_info[idx + 1].mv16[0]; mvc[n][1] = c.f.ref_info[idx + 1].mv16[1]; n++; }
+      if (c.mby < c.p.mb_h - 1) { mvc[n][0] = c.f.ref_info[idx + mbw].mv16[0]; mvc[n][1] = c.f.ref_info[idx + mbw].mv16[1]; n++; }
+    }
+    int px, py;
+    pred_mv(s, 0, 4, 0, &px, &py);
+    me_partition(c, s, BLK_16x16, 0, 0, px, py, (uint32_t)sad_pred_mb, n, &mvc[0][0], &me16);
+    p16_mvx = me16.mv_x; p16_mvy = me16.mv_y;
+    cost_luma = (int)me16.satd_cost;
+  }
+  if (!done) {
+    // intra check (WelsMdFirstIntraMode :1829)
+    int bb;
+    const int cost16 = md_i16x16(c, s, &bb);
+    if (cost16 < cost_luma) {
+      int cost = cost16;
+      s.info.mb_type = MBT_I16x16;
+      s.info.cbp = 0;
+      fill_i4_cache(c, s);
+      const int cost4 = md_enc_i4x4(c, s, cost);
+      if (cost4 < cost) { s.info.mb_type = MBT_I4x4; cost = cost4; }
+      if (s.info.mb_type == MBT_I16x16) { s.info.cbp = 0; enc_rec_i16x16(c, s, s.pred_y[bb]); }
+      int cb;
+      md_chroma(c, s, &cb);
+      dct_chroma(s, s.pred_c[cb]);
+      enc_rec_uv(c, s, 0, false);
+      enc_rec_uv(c, s, 1, false);
+      rec_chroma(s, s.pred_c[cb]);
+      if (lane_id() == 0) { c.f.sad_cost[idx] = 0; s.info.ref_idx = REF_NOT_IN_LIST; }
+      final_type = s.info.mb_type;
+      done = true;
+    }
+  }
+  if (!done && is_skip) {
+    decided_pskip(c, s);
+    final_type = MBT_PSKIP;
+    done = true;
+  }
+  if (!done) {
+    // step 3: sub-16x16 partitions (WelsMdInterFinePartition :1238)
+    const int16_t mvc0[2] = {0, 0};
+    int cost8 = 0;
+    for (int i = 0; i < 4; i++) {
+      int px, py;
+      pred_mv(s, 4 * i, 2, 0, &px, &py);
+      me_partition(c, s, BLK_8x8, (i & 1) * 8, (i >> 1) * 8, px, py, (uint32_t)(sad_pred_mb >> 2), 1, mvc0, &me8x8[i]);
+      cache_set(s, 4 * i, 2, 2, me8x8[i].mv_x, me8x8[i].mv_y);
+      cost8 += (int)me8x8[i].satd_cost;
+    }
+    if (cost8 < cost_luma) {
+      int cost = cost8;
+      final_type = MBT_P8x8;
+      int cst = 0;
+      for (int i = 0; i < 2; i++) {
+        int px, py;
+        pred_16x8_mv(s, 8 * i, 0, &px, &py);
+        me_partition(c, s, BLK_16x8, 0, 8 * i, px, py, (uint32_t)(sad_pred_mb >> 1), 1, mvc0, &me16x8[i]);
+        cache_set(s, 8 * i, 4, 2, me16x8[i].mv_x, me16x8[i].mv_y);
+        cst += (int)me16x8[i].satd_cost;
+      }
+      if (cst <= cost) { cost = cst; final_type = MBT_P16x8; }
+      cst = 0;
+      for (int i = 0; i < 2; i++) {
+        int px, py;
+        pred_8x16_mv(s, 4 * i, 0, &px, &py);
+        me_partition(c, s, BLK_8x16, 8 * i, 0, px, py, (uint32_t)(sad_pred_mb >> 1), 1, mvc0, &me8x16[i]);
+        cache_set(s, 4 * i, 2, 4, me8x16[i].mv_x, me8x16[i].mv_y);
+        cst += (int)me8x16[i].satd_cost;
+      }
+      if (cst <= cost) { cost = cst; final_type = MBT_P8x16; }
+    }
+    // refinement (WelsMdInterMbRefinement :1573)
+    uint8_t* pl = s.pred_y[0];
+    uint8_t* pc = s.pred_c[0];
+    int best_sad = 0;
+    if (final_type == MBT_P16x16) {
+      me_refine(c, s, &me16, 0, 0, 16, 16, pl);
+      cache_set(s, 0, 4, 4, me16.mv_x, me16.mv_y);
+      mb_mv_set(s, 0, 4, 4, me16.mv_x, me16.mv_y);
+      if (lane_id() == 0) { s.out.mvd[0][0] = (int16_t)(me16.mv_x - me16.mvp_x); s.out.mvd[0][1] = (int16_t)(me16.mv_y - me16.mvp_y); }
+      best_sad = (int)me16.sad_cost;
+      mc_chroma_part(c, pc, 0, 0, 16, 16, me16.mv_x, me16.mv_y);
+      cost_skip_mb = warp_sad(s.cur_y, 16, pl, 16, 4, 4) + warp_sad(s.cur_c, 8, pc, 8, 3, 3) + warp_sad(s.cur_c + 64, 8, pc + 64, 8, 3, 3);
+    } else if (final_type == MBT_P16x8) {
+      for (int i = 0; i < 2; i++) {
+        pred_16x8_mv(s, 8 * i, 0, &me16x8[i].mvp_x, &me16x8[i].mvp_y);
+        me_refine(c, s, &me16x8[i], 0, 8 * i, 16, 8, pl + 128 * i);
+        cache_set(s, 8 * i, 4, 2, me16x8[i].mv_x, me16x8[i].mv_y);
+        mb_mv_set(s, 8 * i, 4, 2, me16x8[i].mv_x, me16x8[i].mv_y);
+        if (lane_id() == 0) { s.out.mvd[i][0] = (int16_t)(me16x8[i].mv_x - me16x8[i].mvp_x); s.out.mvd[i][1] = (int16_t)(me16x8[i].mv_y - me16x8[i].mvp_y); }
+        best_sad += (int)me16x8[i].sad_cost;
+        mc_chroma_part(c, pc, 0, 8 * i, 16, 8, me16x8[i].mv_x, me16x8[i].mv_y);
+      }
+    } else if (final_type == MBT_P8x16) {
+      for (int i = 0; i < 2; i++) {
+        pred_8x16_mv(s, 4 * i, 0, &me8x16[i].mvp_x, &me8x16[i].mvp_y);
+        me_refine(c, s, &me8x16[i], 8 * i, 0, 8, 16, pl + 8 * i);
+        cache_set(s, 4 * i, 2, 4, me8x16[i].mv_x, me8x16[i].mv_y);
+        mb_mv_set(s, 4 * i, 2, 4, me8x16[i].mv_x, me8x16[i].mv_y);
+        if (lane_id() == 0) { s.out.mvd[i][0] = (int16_t)(me8x16[i].mv_x - me8x16[i].mvp_x); s.out.mvd[i][1] = (int16_t)(me8x16[i].mv_y - me8x16[i].mvp_y); }
+        best_sad += (int)me8x16[i].sad_cost;
+        mc_chroma_part(c, pc, 8 * i, 0, 8, 16, me8x16[i].mv_x, me8x16[i].mv_y);
+      }
+    } else {
+      if (lane_id() == 0) { s.refc[9] = s.refc[21] = REF_NOT_AVAIL; }
+      warp_sync();
+      for (int i = 0; i < 4; i++) {
+        const int ox = (i & 1) * 8, oy = (i >> 1) * 8;
+        pred_mv(s, 4 * i, 2, 0, &me8x8[i].mvp_x, &me8x8[i].mvp_y);
+        me_refine(c, s, &me8x8[i], ox, oy, 8, 8, pl + oy * 16 + ox);
+        cache_set(s, 4 * i, 2, 2, me8x8[i].mv_x, me8x8[i].mv_y);
+        mb_mv_set(s, 4 * i, 2, 2, me8x8[i].mv_x, me8x8[i].mv_y);
+        if (lane_id() == 0) { s.out.mvd[i][0] = (int16_t)(me8x8[i].mv_x - me8x8[i].mvp_x); s.out.mvd[i][1] = (int16_t)(me8x8[i].mv_y - me8x8[i].mvp_y); }
+        best_sad += (int)me8x8[i].sad_cost;
+        mc_chroma_part(c, pc, ox, oy, 8, 8, me8x8[i].mv_x, me8x8[i].mv_y);
+      }
+    }
+    if (lane_id() == 0) c.f.sad_cost[idx] = best_sad;          // pCurMb->pSadCost[0]
+    // step 7: residual coding (WelsMdInterEncode :1964)
+    if (lane_id() == 0) s.info.cbp = 0;
+    warp_sync();
+    dct_luma_mb(s, pl);
+    enc_inter_y(c, s);
+    dct_chroma(s, pc);
+    enc_rec_uv(c, s, 0, true);
+    enc_rec_uv(c, s, 1, true);
+    rec_luma_inter(s, pl);
+    rec_chroma(s, pc);
+    // step 8: a 16x16 MB without residual whose vector equals the skip predictor becomes P_SKIP (:1937)
+    if (final_type == MBT_P16x16 && s.info.cbp == 0) {
+      // PredSkipMv reads the cache, whose in-MB cells now hold this MB's vector; it only looks at cells 6, 1, 5/0
+      int sx, sy;
+      pred_skip_mv(s, &sx, &sy);
+      if (sx == me16.mv_x && sy == me16.mv_y) final_type = MBT_PSKIP;
+    }
+    if (lane_id() == 0) s.info.mb_type = (uint8_t)final_type;
+    warp_sync();
+  }
+  // bookkeeping for the neighbours and the next frame
+  if (lane_id() == 0) {
+    s.info.mb_type = (uint8_t)final_type;
+    s.info.p16x16_mv[0] = (int16_t)p16_mvx; s.info.p16x16_mv[1] = (int16_t)p16_mvy;
+    if (MBT_IS_INTER(final_type)) s.info.ref_idx = 0;
+    RefMbInfo ri;
+    ri.mv16[0] = (int16_t)p16_mvx; ri.mv16[1] = (int16_t)p16_mvy;
+    ri.skip_sad = final_type == MBT_PSKIP ? cost_skip_mb : 0;      // WelsMdInterSaveSadAndRefMbType (:1987)
+    ri.mb_type = (uint8_t)final_type;
+    ri.pad[0] = ri.pad[1] = ri.pad[2] = 0;
+    c.f.rec_info[idx] = ri;
+  }
+  warp_sync();
+}
+
+}  // namespace mbk

@@ -70,5 +70,7 @@ typedef struct {
   RefMbInfo* rec_info;                    // written for the next frame
   const RefMbInfo* ref_info;              // of the reference picture
   MbOut* out;                             // mb_w*mb_h
+  int32_t* sad_cost;                      // mb_w*mb_h, PERSISTS across frames like the reference's pSadCostMb
+                                          // (encoder_ext.cpp:1675): a decided-skip MB keeps its older value
   int32_t* row_progress;                  // wavefront: number of finished MBs per MB row (device only)
 } EncFramePtrs;

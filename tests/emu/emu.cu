@@ -10,7 +10,9 @@
 #include <string.h>
 #include <vector>
 
+#define B2H264_WITH_INTER 1
 #include "../../openh264_b200/csrc/enc_frame.cuh"
+#include "../../openh264_b200/csrc/enc_deblock.cuh"
 #include "../../openh264_b200/csrc/h264_bitstream.h"
 
 #include "../../openh264_b200/csrc/enc_host.h"
@@ -29,6 +31,7 @@ struct HostFrameEncoder {
   std::vector<MbInfo> mbi;
   std::vector<RefMbInfo> rinfo[2];
   std::vector<MbOut> out;
+  std::vector<int32_t> sad_cost;
   MbScratch scratch;
   int cur_rec = 0;
   bool idr = true, have_ref_p = false;
@@ -43,7 +46,7 @@ struct HostFrameEncoder {
       pic[b][2].assign((size_t)ctl.rec_stride_c() * ctl.rec_rows_c() + 64, 0);
       rinfo[b].resize(n);
     }
-    mbi.resize(n); out.resize(n);
+    mbi.resize(n); out.resize(n); sad_cost.assign(n, 0);
     memset(&scratch, 0, sizeof(scratch));
   }
   void load_source(const uint8_t* yuv) {
@@ -62,6 +65,7 @@ struct HostFrameEncoder {
     memset(&f, 0, sizeof(f));
     for (int pl = 0; pl < 3; pl++) { f.cur[pl] = cur[pl].data(); f.rec[pl] = plane0(cur_rec, pl); f.ref[pl] = plane0(1 - cur_rec, pl); }
     f.mbi = mbi.data(); f.rec_info = rinfo[cur_rec].data(); f.ref_info = rinfo[1 - cur_rec].data(); f.out = out.data();
+    f.sad_cost = sad_cost.data();
     return f;
   }
   void finish_frame(std::vector<uint8_t>* bs) {
@@ -92,9 +96,10 @@ void expand_frame_host(const EncFrameParams& p, const EncFramePtrs& f) {
     }
   }
 }
-#ifndef B2H264_WITH_INTER
-void deblock_frame_host(const EncFrameParams&, const EncFramePtrs&) {}
-#endif
+void deblock_frame_host(const EncFrameParams& p, const EncFramePtrs& f) {
+  for (int mby = 0; mby < p.mb_h; mby++)
+    for (int mbx = 0; mbx < p.mb_w; mbx++) deblock_one_mb(p, f, mbx, mby);
+}
 
 }  // namespace
 

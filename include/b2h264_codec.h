@@ -1,0 +1,73 @@
+/*
+ * include/b2h264_codec.h — C-ABI of libopenh264_b200.so, layers 2 and 3: frame-level encoding.
+ *
+ * Layer 2 — batched frame encoder (b2h264_enc_*): N independent streams of identical geometry are coded
+ * together, one picture per stream per call.  This is the B200-shaped entry point: the macroblock loop
+ * of the reference (WelsCodeOneSlice -> WelsISliceMdEnc / WelsMdInterMbLoop,
+ * codec/encoder/core/src/svc_encode_slice.cpp:534,1642,1807) plus PerformDeblockingFilter
+ * (deblocking.cpp:744) and ExpandReferencingPicture (expand_pic.cpp:388) run on the GPU as a wavefront
+ * over macroblock rows x streams; CAVLC / NAL serialisation (svc_set_mb_syn_cavlc.cpp, nal_encap.cpp)
+ * runs on host threads from the pinned copy-back of the per-macroblock records.
+ *
+ * Layer 3 — the reference's own public API (codec/api/wels/codec_api.h:272-339,545-586):
+ * WelsCreateSVCEncoder() returns an object whose vtable layout is that of ISVCEncoder, so a caller
+ * built against the reference's header can link this library instead.  It wraps a
+ * 1-stream layer-2 encoder.
+ *
+ * Supported configuration (everything else is rejected with an error, never silently approximated):
+ * CAMERA_VIDEO_REAL_TIME, 1 spatial / 1 temporal layer, RC_OFF_MODE (constant QP), SM_SINGLE_SLICE,
+ * CAVLC, complexity MEDIUM/HIGH, 1 reference frame, deblocking idc 0, IDR at the first frame (and on
+ * ForceIntraFrame), no denoise / background detection / adaptive quant / scene-change / LTR.
+ * For that configuration the bitstream is bit-identical to the reference's.
+ */
+#ifndef B2H264_CODEC_H
+#define B2H264_CODEC_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2h264_enc b2h264_enc;
+
+typedef struct {
+  int32_t width, height;        /* luma samples, multiples of 2 (width % 4 == 0) */
+  int32_t qp;                   /* constant QP 0..51 (SSpatialLayerConfig::iDLayerQp) */
+  float   fps;                  /* fMaxFrameRate: only used for level selection */
+  int32_t target_bitrate;       /* iTargetBitrate in bps: only used for level selection (0 = unspecified) */
+  int32_t n_streams;            /* independent streams coded per call */
+  int32_t entropy_threads;      /* host threads for CAVLC (0 = min(n_streams, hardware threads)) */
+  int32_t device;               /* CUDA device ordinal */
+} b2h264_enc_config;
+
+/* returns 0 or a negative b2h264 error / positive cudaError_t */
+int  b2h264_enc_create (const b2h264_enc_config* cfg, b2h264_enc** out);
+void b2h264_enc_destroy (b2h264_enc* e);
+
+/* Submits one picture per stream.  src[i] = I420 picture of stream i (w*h*3/2 bytes, tightly packed).
+ * src_on_device = 0: host pointers; the pictures are staged through pinned memory and copied H2D
+ * inside this call's asynchronous pipeline.  src_on_device = 1: device pointers (already in HBM).
+ * At most 2 submissions may be in flight before b2h264_enc_collect is called. */
+int  b2h264_enc_submit (b2h264_enc* e, const uint8_t* const* src, int src_on_device);
+
+/* Waits for the oldest submitted batch, entropy-codes it, and returns per-stream Annex-B access units.
+ * bs[i] / bs_bytes[i]: encoder-owned buffer of stream i, valid until the next collect on this encoder
+ * (like SFrameBSInfo::pBsBuf, codec_app_def.h:647-654).  frame_type[i]: 1 = IDR, 2 = P (may be NULL). */
+int  b2h264_enc_collect (b2h264_enc* e, const uint8_t** bs, int32_t* bs_bytes, int32_t* frame_type);
+
+/* next picture of stream i (or all streams when i < 0) is coded as IDR (ISVCEncoder::ForceIntraFrame) */
+int  b2h264_enc_force_idr (b2h264_enc* e, int stream);
+
+/* copies the reconstructed (deblocked) picture of stream i that is currently the reference into dst
+ * (cropped I420, w*h*3/2 bytes, host memory): for parity tests */
+int  b2h264_enc_get_recon (b2h264_enc* e, int stream, uint8_t* h_dst);
+
+/* timing of the last collected batch, microseconds: [0] GPU kernels (CUDA events), [1] host entropy coding */
+int  b2h264_enc_last_timing (b2h264_enc* e, float* us2);
+
+/* layer 3 (WelsCreateSVCEncoder / ISVCEncoder, codec_api.h:272-339,545-586) is declared in b2h264_wels_api.h */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -70,13 +70,26 @@ API = {
     "b2h264_k_expand_plane": [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "b2h264_k_me_search": [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp],
     "b2h264_k_mc_sad": [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp],
+    "b2h264_enc_create": [vp, C.POINTER(vp)],
+    "b2h264_enc_destroy": [vp],
+    "b2h264_enc_submit": [vp, C.POINTER(vp), C.c_int],
+    "b2h264_enc_collect": [vp, C.POINTER(vp), i32p, i32p],
+    "b2h264_enc_force_idr": [vp, C.c_int],
+    "b2h264_enc_get_recon": [vp, C.c_int, vp],
+    "b2h264_enc_last_timing": [vp, C.POINTER(C.c_float)],
     "b2h264_table_quant_ff": [C.c_int],
     "b2h264_table_quant_mf": [C.c_int],
     "b2h264_table_dequant": [C.c_int],
     "b2h264_table_lambda": [C.c_int],
     "b2h264_table_chroma_qp": [C.c_int],
 }
-_RESTYPES = {"b2h264_error_string": C.c_char_p, "b2h264_launch_count": C.c_ulonglong,
+class EncConfig(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("qp", C.c_int32), ("fps", C.c_float),
+                ("target_bitrate", C.c_int32), ("n_streams", C.c_int32), ("entropy_threads", C.c_int32),
+                ("device", C.c_int32)]
+
+
+_RESTYPES = {"b2h264_enc_destroy": None, "b2h264_error_string": C.c_char_p, "b2h264_launch_count": C.c_ulonglong,
              "b2h264_table_quant_ff": i16p, "b2h264_table_quant_mf": i16p, "b2h264_table_dequant": u16p}
 
 _lib = None
@@ -152,5 +165,59 @@ class DeviceArray:
     def __del__(self):
         try:
             self.free()
+        except Exception:
+            pass
+
+
+class BatchEncoder:
+    """Host-side mirror of the layer-2 C-ABI (include/b2h264_codec.h): N independent streams, one picture per
+    stream per call; returns the Annex-B access units.  No computation happens in Python."""
+
+    def __init__(self, width, height, qp=26, fps=30.0, n_streams=1, target_bitrate=5000000, entropy_threads=0, device=0):
+        self.L = lib(device)
+        self.cfg = EncConfig(width, height, qp, fps, target_bitrate, n_streams, entropy_threads, device)
+        self.h = vp()
+        check(self.L.b2h264_enc_create(C.byref(self.cfg), C.byref(self.h)))
+        self.n = n_streams
+        self.frame_bytes = width * height * 3 // 2
+
+    def submit(self, frames, on_device=False):
+        """frames: list of n_streams numpy uint8 arrays (host) or raw device pointers (on_device=True)."""
+        ptrs = (vp * self.n)(*[(f if on_device else f.ctypes.data) for f in frames])
+        self._keep = frames
+        check(self.L.b2h264_enc_submit(self.h, ptrs, 1 if on_device else 0))
+
+    def collect(self):
+        bs = (vp * self.n)()
+        nb = (C.c_int32 * self.n)()
+        ft = (C.c_int32 * self.n)()
+        check(self.L.b2h264_enc_collect(self.h, bs, nb, ft))
+        return [C.string_at(bs[i], nb[i]) for i in range(self.n)], list(ft)
+
+    def encode(self, frames):
+        self.submit(frames)
+        return self.collect()
+
+    def force_idr(self, stream=-1):
+        check(self.L.b2h264_enc_force_idr(self.h, stream))
+
+    def recon(self, stream=0):
+        out = np.empty(self.frame_bytes, np.uint8)
+        check(self.L.b2h264_enc_get_recon(self.h, stream, out.ctypes.data))
+        return out
+
+    def timing_us(self):
+        t = (C.c_float * 2)()
+        check(self.L.b2h264_enc_last_timing(self.h, t))
+        return t[0], t[1]
+
+    def close(self):
+        if self.h:
+            self.L.b2h264_enc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass

@@ -1,0 +1,292 @@
+// enc_batch.cu — layer-2 batched frame encoder (include/b2h264_codec.h): device buffers, the asynchronous
+// H2D -> kernels -> D2H pipeline on one CUDA stream, and host entropy coding on a small thread pool.
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <string.h>
+#include <thread>
+#include <vector>
+
+#include "../../include/b2h264_codec.h"
+#include "b2h264_internal.h"
+#include "enc_host.h"
+#include "enc_launch.h"
+
+using b2h264::StreamCtl;
+
+namespace {
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+// minimal fork-join pool for the per-stream CAVLC jobs
+class Pool {
+ public:
+  explicit Pool(int n) {
+    for (int i = 0; i < n; i++) th_.emplace_back([this] { loop(); });
+  }
+  ~Pool() {
+    { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  void run(int n, const std::function<void(int)>& fn) {
+    { std::lock_guard<std::mutex> l(m_); fn_ = &fn; next_ = 0; total_ = n; done_ = 0; }
+    cv_.notify_all();
+    std::unique_lock<std::mutex> l(m_);
+    done_cv_.wait(l, [&] { return done_ == total_; });
+    fn_ = nullptr;
+  }
+ private:
+  void loop() {
+    for (;;) {
+      int job;
+      const std::function<void(int)>* fn;
+      {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return stop_ || (fn_ && next_ < total_); });
+        if (stop_) return;
+        job = next_++; fn = fn_;
+      }
+      (*fn)(job);
+      { std::lock_guard<std::mutex> l(m_); if (++done_ == total_) done_cv_.notify_all(); }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int next_ = 0, total_ = 0, done_ = 0;
+  bool stop_ = false;
+};
+
+}  // namespace
+
+struct b2h264_enc {
+  b2h264_enc_config cfg;
+  int S = 0, n_mb = 0;
+  std::vector<StreamCtl> ctl;
+  std::vector<uint8_t> idr_next;          // per stream: code next picture as IDR
+  std::vector<uint8_t> have_ref_p;        // reference picture of the stream was a P picture
+  int cur_rec = 0;                        // which of the two picture sets is being written
+  cudaStream_t st = nullptr;
+  // device memory
+  uint8_t* d_cur = nullptr;               // S x (Y,U,V) MB-aligned current pictures
+  uint8_t* d_pic[2] = {nullptr, nullptr}; // S x padded (Y,U,V), ping-pong
+  uint8_t* d_src = nullptr;               // S x raw I420 staging (2 slots)
+  MbInfo* d_mbi = nullptr;
+  RefMbInfo* d_rinfo[2] = {nullptr, nullptr};
+  MbOut* d_out[2] = {nullptr, nullptr};
+  int32_t* d_sad = nullptr;
+  int32_t* d_prog = nullptr;              // S x 2 x mb_h
+  int* d_tickets = nullptr;
+  StreamFrame* d_sf[2] = {nullptr, nullptr};
+  const uint8_t** d_srcptr[2] = {nullptr, nullptr};
+  // pinned host memory
+  uint8_t* h_src = nullptr;               // 2 slots x S x frame
+  MbOut* h_out[2] = {nullptr, nullptr};
+  StreamFrame* h_sf[2] = {nullptr, nullptr};
+  const uint8_t** h_srcptr[2] = {nullptr, nullptr};
+  // in-flight bookkeeping
+  struct Slot { bool busy = false; std::vector<uint8_t> idr; cudaEvent_t ev0, ev1, done; };
+  Slot slot[2];
+  int submit_idx = 0, collect_idx = 0;
+  std::vector<std::vector<uint8_t>> bs;   // per stream output of the last collect
+  Pool* pool = nullptr;
+  float last_us[2] = {0, 0};
+  size_t frame_bytes = 0, cur_bytes = 0, pic_bytes = 0, pic_y_bytes = 0, pic_c_bytes = 0;
+
+  uint8_t* pic_plane0(int set, int s, int pl) const {   // pixel (0,0) of plane pl of stream s
+    const int sty = ctl[0].rec_stride_y(), stc = ctl[0].rec_stride_c();
+    uint8_t* base = d_pic[set] + (size_t)s * pic_bytes;
+    if (pl == 0) return base + (size_t)32 * sty + 32;
+    return base + pic_y_bytes + (size_t)(pl - 1) * pic_c_bytes + (size_t)16 * stc + 16;
+  }
+};
+
+extern "C" {
+
+int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
+  if (!cfg || !out) return -1;
+  if (cfg->width < 16 || cfg->height < 16 || (cfg->width & 3) || (cfg->height & 1) || cfg->qp < 0 || cfg->qp > 51 ||
+      cfg->n_streams < 1)
+    return -2;
+  int rc = b2h264_init(cfg->device);
+  if (rc) return rc;
+  if ((rc = enc_upload_deblock_tables())) return rc;
+  b2h264_enc* e = new b2h264_enc();
+  e->cfg = *cfg;
+  e->S = cfg->n_streams;
+  e->ctl.resize(e->S);
+  for (auto& c : e->ctl) c.init(cfg->width, cfg->height, cfg->qp, cfg->fps, cfg->target_bitrate);
+  e->idr_next.assign(e->S, 1);
+  e->have_ref_p.assign(e->S, 0);
+  const StreamCtl& c0 = e->ctl[0];
+  const int mbw = c0.sp.mb_w, mbh = c0.sp.mb_h;
+  e->n_mb = mbw * mbh;
+  e->frame_bytes = (size_t)cfg->width * cfg->height * 3 / 2;
+  e->cur_bytes = (size_t)e->n_mb * 384;
+  e->pic_y_bytes = (size_t)c0.rec_stride_y() * c0.rec_rows_y();
+  e->pic_c_bytes = (size_t)c0.rec_stride_c() * c0.rec_rows_c();
+  e->pic_bytes = (e->pic_y_bytes + 2 * e->pic_c_bytes + 255) & ~(size_t)255;
+  const size_t S = e->S;
+  CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+  CK(cudaMalloc(&e->d_cur, S * e->cur_bytes + 256));
+  for (int i = 0; i < 2; i++) {
+    CK(cudaMalloc(&e->d_pic[i], S * e->pic_bytes + 256));
+    CK(cudaMemset(e->d_pic[i], 0, S * e->pic_bytes + 256));
+    CK(cudaMalloc(&e->d_rinfo[i], S * e->n_mb * sizeof(RefMbInfo)));
+    CK(cudaMemset(e->d_rinfo[i], 0, S * e->n_mb * sizeof(RefMbInfo)));
+    CK(cudaMalloc(&e->d_out[i], S * e->n_mb * sizeof(MbOut)));
+    CK(cudaMalloc(&e->d_sf[i], S * sizeof(StreamFrame)));
+    CK(cudaMalloc(&e->d_srcptr[i], S * sizeof(uint8_t*)));
+    CK(cudaMallocHost(&e->h_out[i], S * e->n_mb * sizeof(MbOut)));
+    CK(cudaMallocHost(&e->h_sf[i], S * sizeof(StreamFrame)));
+    CK(cudaMallocHost(&e->h_srcptr[i], S * sizeof(uint8_t*)));
+    CK(cudaEventCreate(&e->slot[i].ev0));
+    CK(cudaEventCreate(&e->slot[i].ev1));
+    CK(cudaEventCreateWithFlags(&e->slot[i].done, cudaEventDisableTiming));
+  }
+  CK(cudaMalloc(&e->d_src, 2 * S * e->frame_bytes + 256));
+  CK(cudaMallocHost(&e->h_src, 2 * S * e->frame_bytes));
+  CK(cudaMalloc(&e->d_mbi, S * e->n_mb * sizeof(MbInfo)));
+  CK(cudaMemset(e->d_mbi, 0, S * e->n_mb * sizeof(MbInfo)));
+  CK(cudaMalloc(&e->d_sad, S * e->n_mb * sizeof(int32_t)));
+  CK(cudaMemset(e->d_sad, 0, S * e->n_mb * sizeof(int32_t)));
+  CK(cudaMalloc(&e->d_prog, S * 2 * mbh * sizeof(int32_t)));
+  CK(cudaMalloc(&e->d_tickets, 2 * sizeof(int)));
+  e->bs.resize(S);
+  int nt = cfg->entropy_threads;
+  if (nt <= 0) { nt = (int)std::thread::hardware_concurrency(); if (nt > (int)S) nt = (int)S; if (nt < 1) nt = 1; }
+  e->pool = new Pool(nt);
+  *out = e;
+  return 0;
+}
+
+void b2h264_enc_destroy(b2h264_enc* e) {
+  if (!e) return;
+  cudaStreamSynchronize(e->st);
+  delete e->pool;
+  cudaFree(e->d_cur); cudaFree(e->d_src); cudaFree(e->d_mbi); cudaFree(e->d_sad); cudaFree(e->d_prog); cudaFree(e->d_tickets);
+  cudaFreeHost(e->h_src);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(e->d_pic[i]); cudaFree(e->d_rinfo[i]); cudaFree(e->d_out[i]); cudaFree(e->d_sf[i]); cudaFree(e->d_srcptr[i]);
+    cudaFreeHost(e->h_out[i]); cudaFreeHost(e->h_sf[i]); cudaFreeHost(e->h_srcptr[i]);
+    cudaEventDestroy(e->slot[i].ev0); cudaEventDestroy(e->slot[i].ev1); cudaEventDestroy(e->slot[i].done);
+  }
+  cudaStreamDestroy(e->st);
+  delete e;
+}
+
+int b2h264_enc_force_idr(b2h264_enc* e, int stream) {
+  if (!e || stream >= e->S) return -1;
+  for (int s = 0; s < e->S; s++) if (stream < 0 || stream == s) e->idr_next[s] = 1;
+  return 0;
+}
+
+int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_device) {
+  if (!e || !src) return -1;
+  const int k = e->submit_idx & 1;
+  b2h264_enc::Slot& sl = e->slot[k];
+  if (sl.busy) return -3;                       // two batches already in flight
+  const int S = e->S, mbw = e->ctl[0].sp.mb_w, mbh = e->ctl[0].sp.mb_h;
+  // stage sources
+  for (int s = 0; s < S; s++) {
+    if (src_on_device) e->h_srcptr[k][s] = src[s];
+    else {
+      uint8_t* hs = e->h_src + ((size_t)k * S + s) * e->frame_bytes;
+      memcpy(hs, src[s], e->frame_bytes);
+      e->h_srcptr[k][s] = e->d_src + ((size_t)k * S + s) * e->frame_bytes;
+    }
+  }
+  if (!src_on_device)
+    CK(cudaMemcpyAsync(e->d_src + (size_t)k * S * e->frame_bytes, e->h_src + (size_t)k * S * e->frame_bytes,
+                       (size_t)S * e->frame_bytes, cudaMemcpyHostToDevice, e->st));
+  // per-stream frame descriptors
+  sl.idr.assign(S, 0);
+  const int rec = e->cur_rec;
+  for (int s = 0; s < S; s++) {
+    const bool idr = e->idr_next[s] != 0;
+    sl.idr[s] = idr;
+    StreamFrame& F = e->h_sf[k][s];
+    F.p = e->ctl[s].frame_params(idr, e->have_ref_p[s] != 0);
+    uint8_t* cur = e->d_cur + (size_t)s * e->cur_bytes;
+    F.f.cur[0] = cur; F.f.cur[1] = cur + (size_t)e->n_mb * 256; F.f.cur[2] = cur + (size_t)e->n_mb * 320;
+    for (int pl = 0; pl < 3; pl++) { F.f.rec[pl] = e->pic_plane0(rec, s, pl); F.f.ref[pl] = e->pic_plane0(1 - rec, s, pl); }
+    F.f.mbi = e->d_mbi + (size_t)s * e->n_mb;
+    F.f.rec_info = e->d_rinfo[rec] + (size_t)s * e->n_mb;
+    F.f.ref_info = e->d_rinfo[1 - rec] + (size_t)s * e->n_mb;
+    F.f.out = e->d_out[k] + (size_t)s * e->n_mb;
+    F.f.sad_cost = e->d_sad + (size_t)s * e->n_mb;
+    F.f.row_progress = e->d_prog + (size_t)s * 2 * mbh;
+    F.f.row_progress_dbk = F.f.row_progress + mbh;
+    e->idr_next[s] = 0;
+    e->have_ref_p[s] = !idr;
+  }
+  e->cur_rec = 1 - rec;
+  CK(cudaMemcpyAsync(e->d_sf[k], e->h_sf[k], S * sizeof(StreamFrame), cudaMemcpyHostToDevice, e->st));
+  CK(cudaMemcpyAsync(e->d_srcptr[k], e->h_srcptr[k], S * sizeof(uint8_t*), cudaMemcpyHostToDevice, e->st));
+  CK(cudaMemsetAsync(e->d_prog, 0, (size_t)S * 2 * mbh * sizeof(int32_t), e->st));
+  CK(cudaEventRecord(sl.ev0, e->st));
+  int rc = enc_launch_frame(e->d_sf[k], e->d_srcptr[k], S, e->cfg.width, e->cfg.height, mbw, mbh, e->d_tickets, e->st);
+  if (rc) return rc;
+  // the entropy coder only needs the macroblock records: copy them back while deblocking runs
+  rc = enc_launch_deblock_expand(e->d_sf[k], S, mbw, mbh, e->d_tickets, e->st);
+  if (rc) return rc;
+  CK(cudaEventRecord(sl.ev1, e->st));
+  CK(cudaMemcpyAsync(e->h_out[k], e->d_out[k], (size_t)S * e->n_mb * sizeof(MbOut), cudaMemcpyDeviceToHost, e->st));
+  CK(cudaEventRecord(sl.done, e->st));
+  sl.busy = true;
+  e->submit_idx++;
+  return 0;
+}
+
+int b2h264_enc_collect(b2h264_enc* e, const uint8_t** bs, int32_t* bs_bytes, int32_t* frame_type) {
+  if (!e) return -1;
+  const int k = e->collect_idx & 1;
+  b2h264_enc::Slot& sl = e->slot[k];
+  if (!sl.busy) return -4;
+  CK(cudaEventSynchronize(sl.done));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, sl.ev0, sl.ev1);
+  e->last_us[0] = ms * 1000.f;
+  const auto t0 = std::chrono::steady_clock::now();
+  const int n_mb = e->n_mb;
+  std::function<void(int)> job = [&](int s) {
+    e->bs[s].clear();
+    e->ctl[s].write_access_unit(sl.idr[s] != 0, e->h_out[k] + (size_t)s * n_mb, &e->bs[s]);
+  };
+  e->pool->run(e->S, job);
+  e->last_us[1] = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - t0).count();
+  for (int s = 0; s < e->S; s++) {
+    if (bs) bs[s] = e->bs[s].data();
+    if (bs_bytes) bs_bytes[s] = (int32_t)e->bs[s].size();
+    if (frame_type) frame_type[s] = sl.idr[s] ? 1 : 2;
+  }
+  sl.busy = false;
+  e->collect_idx++;
+  return 0;
+}
+
+int b2h264_enc_get_recon(b2h264_enc* e, int stream, uint8_t* dst) {
+  if (!e || stream < 0 || stream >= e->S || !dst) return -1;
+  CK(cudaStreamSynchronize(e->st));
+  const int set = 1 - e->cur_rec;               // the picture reconstructed last is now the reference
+  const int w = e->cfg.width, h = e->cfg.height;
+  for (int pl = 0; pl < 3; pl++) {
+    const int pw = pl ? w / 2 : w, ph = pl ? h / 2 : h;
+    const int st = pl ? e->ctl[0].rec_stride_c() : e->ctl[0].rec_stride_y();
+    CK(cudaMemcpy2D(dst, pw, e->pic_plane0(set, stream, pl), st, pw, ph, cudaMemcpyDeviceToHost));
+    dst += (size_t)pw * ph;
+  }
+  return 0;
+}
+
+int b2h264_enc_last_timing(b2h264_enc* e, float* us2) {
+  if (!e || !us2) return -1;
+  us2[0] = e->last_us[0]; us2[1] = e->last_us[1];
+  return 0;
+}
+
+}  // extern "C"

@@ -16,6 +16,7 @@ MBK_HD void encode_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScra
   c.qp = p.qp;
   c.qp_c = tbl_chroma_qp(p.qp);          // chroma_qp_index_offset = 0
   c.lambda = tbl_lambda(p.qp);
+  mb_load_neighbors(c, s);               // (uses the previous MB's staged record as the left neighbour)
   // clear the staged records
   {
     uint32_t* a = reinterpret_cast<uint32_t*>(&s.info);

@@ -37,21 +37,18 @@ MBK_HD int median3(int a, int b, int c) {
 // ---- neighbour caches (FillNeighborCacheInterWithoutBGD, md.cpp:132) ----------------------------------
 MBK_HD void fill_inter_cache(const MbCtx& c, MbScratch& s) {
   if (lane_id() == 0) {
-    const int mbw = c.p.mb_w, idx = c.mby * mbw + c.mbx;
-    const MbInfo* cur = c.f.mbi + idx;
     for (int i = 0; i < 30; i++) { s.mvc[i][0] = s.mvc[i][1] = 0; s.refc[i] = 0; }
     // slot: 0 top-left, 1 top, 2 top-right, 3 left
-    const int offs[4] = {-mbw - 1, -mbw, -mbw + 1, -1};
     const int bits[4] = {NB_TOPLEFT, NB_TOP, NB_TOPRIGHT, NB_LEFT};
     for (int k = 0; k < 4; k++) {
       const bool avail = (c.nb & bits[k]) != 0;
-      const MbInfo* n = cur + offs[k];
+      const MbInfo* n = &s.nbi[k];
       const bool inter = avail && MBT_IS_INTER(n->mb_type);
       const int8_t na = avail ? REF_NOT_IN_LIST : REF_NOT_AVAIL;
-      s.sadc[k] = inter ? c.f.sad_cost[idx + offs[k]] : 0;
+      s.sadc[k] = inter ? s.nb_sad[k] : 0;
       const bool skip = inter && n->mb_type == MBT_PSKIP;
       s.skip_flag[k] = skip;
-      s.sad_skip[k] = skip ? c.f.rec_info[idx + offs[k]].skip_sad : 0;
+      s.sad_skip[k] = skip ? s.nb_skip_sad[k] : 0;
       if (k == 3) {          // left column: cache 6,12,18,24 <- right column of the left MB
         for (int r = 0; r < 4; r++) {
           const int ci = 6 + 6 * r;
@@ -426,11 +423,10 @@ MBK_HD void inter_mb_md_enc(const MbCtx& c, MbScratch& s) {
   fill_inter_cache(c, s);
   const int ref_mb_type = c.p.ref_is_p ? c.f.ref_info[idx].mb_type : 0xff;
   int p16_mvx = 0, p16_mvy = 0;                       // sP16x16Mv / sMvList (WelsMdInterInit :352-353)
-  const MbInfo* cur = c.f.mbi + idx;
-  const bool sk_l = (c.nb & NB_LEFT) && cur[-1].mb_type == MBT_PSKIP;
-  const bool sk_t = (c.nb & NB_TOP) && cur[-mbw].mb_type == MBT_PSKIP;
-  const bool sk_tl = (c.nb & NB_TOPLEFT) && cur[-mbw - 1].mb_type == MBT_PSKIP;
-  const bool sk_tr = (c.nb & NB_TOPRIGHT) && cur[-mbw + 1].mb_type == MBT_PSKIP;
+  const bool sk_l = (c.nb & NB_LEFT) && s.nbi[3].mb_type == MBT_PSKIP;
+  const bool sk_t = (c.nb & NB_TOP) && s.nbi[1].mb_type == MBT_PSKIP;
+  const bool sk_tl = (c.nb & NB_TOPLEFT) && s.nbi[0].mb_type == MBT_PSKIP;
+  const bool sk_tr = (c.nb & NB_TOPRIGHT) && s.nbi[2].mb_type == MBT_PSKIP;
   const bool try_skip = sk_l || sk_t || sk_tl || sk_tr;
   const bool keep_skip = sk_l && sk_t && sk_tr;
   int cost_luma = 0, cost_skip_mb = 0;
@@ -460,8 +456,8 @@ MBK_HD void inter_mb_md_enc(const MbCtx& c, MbScratch& s) {
     int16_t mvc[5][2];
     int n = 0;
     mvc[n][0] = 0; mvc[n][1] = 0; n++;                                    // sMvBase
-    if (c.nb & NB_LEFT) { mvc[n][0] = cur[-1].p16x16_mv[0]; mvc[n][1] = cur[-1].p16x16_mv[1]; n++; }
-    if (c.nb & NB_TOP) { mvc[n][0] = cur[-mbw].p16x16_mv[0]; mvc[n][1] = cur[-mbw].p16x16_mv[1]; n++; }
+    if (c.nb & NB_LEFT) { mvc[n][0] = s.nbi[3].p16x16_mv[0]; mvc[n][1] = s.nbi[3].p16x16_mv[1]; n++; }
+    if (c.nb & NB_TOP) { mvc[n][0] = s.nbi[1].p16x16_mv[0]; mvc[n][1] = s.nbi[1].p16x16_mv[1]; n++; }
     if (c.p.ref_is_p) {
       if (c.mbx < mbw - 1) { mvc[n][0] = c.f.ref_info[idx + 1].mv16[0]; mvc[n][1] = c.f.ref_info[idx + 1].mv16[1]; n++; }
       if (c.mby < c.p.mb_h - 1) { mvc[n][0] = c.f.ref_info[idx + mbw].mv16[0]; mvc[n][1] = c.f.ref_info[idx + mbw].mv16[1]; n++; }

@@ -1,0 +1,199 @@
+// enc_kernels.cu — frame-level CUDA kernels of the encoder path (sm_100a):
+//   k_pad_source     source I420 -> MB-aligned current picture
+//   k_encode_rows    macroblock mode decision + coding + reconstruction, ONE WARP PER MACROBLOCK ROW,
+//                    rows of all streams of the batch scheduled as a wavefront (persistent warps + ticket)
+//   k_deblock_rows   in-loop deblocking, same wavefront
+//   k_expand_*       border replication of the new reference picture (ExpandReferencingPicture)
+// Why a wavefront: MB(x,y) needs the FINAL state of (x-1,y), (x,y-1), (x+1,y-1) — motion-vector / SAD
+// predictors, intra neighbours, skip context (SURVEY.md §7 hard part 1); bit-exactness forbids breaking
+// that chain, so parallelism comes from rows (2-MB lag) x independent streams of the batch.
+#include <cooperative_groups.h>
+
+#include "b2h264_internal.h"
+#define B2H264_WITH_INTER 1
+#include "enc_deblock.cuh"
+#include "enc_frame.cuh"
+#include "enc_launch.h"
+
+using namespace mbk;
+
+namespace mbk {
+__constant__ uint8_t c_alpha[52];
+__constant__ uint8_t c_beta[52];
+__constant__ uint8_t c_tc0[52][3];
+}  // namespace mbk
+
+#define ENC_WPC 4          // warps per CTA in the row kernels
+
+__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+// ---- source padding (CWelsPreProcess::Padding, wels_preprocess.cpp:1250) --------------------------------
+__global__ void k_pad_source(const StreamFrame* __restrict__ sf, const uint8_t* const* __restrict__ src, int w, int h) {
+  const StreamFrame& F = sf[blockIdx.z];
+  const uint8_t* yuv = src[blockIdx.z];
+  const int W = F.p.mb_w * 16, H = F.p.mb_h * 16;
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= W || y >= H) return;
+  uchar4 v = make_uchar4(0, 0, 0, 0);
+  if (y < h) {
+    const uint8_t* r = yuv + (size_t)y * w;
+    if (x + 3 < w) v = *reinterpret_cast<const uchar4*>(r + x);          // w % 4 == 0 is required at create time
+  }
+  *reinterpret_cast<uchar4*>(const_cast<uint8_t*>(F.f.cur[0]) + (size_t)y * F.p.cur_stride_y + x) = v;
+  if (y < H / 2 && x < W / 2) {
+    const int cw = w / 2, ch = h / 2;
+    for (int pl = 0; pl < 2; pl++) {
+      uchar4 c = make_uchar4(0x80, 0x80, 0x80, 0x80);
+      const uint8_t* p = yuv + (size_t)w * h + (size_t)pl * cw * ch + (size_t)y * cw;
+      if (y < ch) {
+        uint8_t t[4];
+        for (int i = 0; i < 4; i++) t[i] = (x + i < cw) ? p[x + i] : 0x80;
+        c = make_uchar4(t[0], t[1], t[2], t[3]);
+      }
+      *reinterpret_cast<uchar4*>(const_cast<uint8_t*>(F.f.cur[1 + pl]) + (size_t)y * F.p.cur_stride_c + x) = c;
+    }
+  }
+}
+
+// ---- wavefront row scheduling ----------------------------------------------------------------------------
+// ticket t -> (row = t / n_streams, stream = t % n_streams): every stream's row r is handed out before any
+// row r+1, so the row a warp waits on has always been claimed by a warp that is already running.
+template <bool kDeblock, class Body>
+__device__ __forceinline__ void run_rows(const StreamFrame* sf, int n_streams, int* ticket, Body body) {
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(ticket, 1);
+    t = __shfl_sync(MBK_FULL, t, 0);
+    const int mb_h = sf[0].p.mb_h;
+    if (t >= n_streams * mb_h) break;
+    const int row = t / n_streams, si = t - row * n_streams;
+    const StreamFrame& F = sf[si];
+    const int mb_w = F.p.mb_w;
+    int* prog = kDeblock ? F.f.row_progress_dbk : F.f.row_progress;
+    int seen = 0;
+    for (int x = 0; x < mb_w; x++) {
+      if (row > 0) {
+        const int need = x + 2 < mb_w ? x + 2 : mb_w;
+        if (seen < need) {
+          if (lane == 0) {
+            while ((seen = ld_volatile(prog + row - 1)) < need) __nanosleep(64);
+          }
+          seen = __shfl_sync(MBK_FULL, seen, 0);
+          __threadfence();
+        }
+      }
+      body(F, x, row);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) *reinterpret_cast<volatile int*>(prog + row) = x + 1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32 * ENC_WPC) k_encode_rows(const StreamFrame* __restrict__ sf, int n_streams, int* ticket) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  MbScratch& s = reinterpret_cast<MbScratch*>(smem)[threadIdx.x >> 5];
+  run_rows<false>(sf, n_streams, ticket, [&](const StreamFrame& F, int x, int row) { encode_one_mb(F.p, F.f, s, x, row); });
+}
+
+__global__ void __launch_bounds__(32 * ENC_WPC) k_deblock_rows(const StreamFrame* __restrict__ sf, int n_streams, int* ticket) {
+  run_rows<true>(sf, n_streams, ticket, [&](const StreamFrame& F, int x, int row) { deblock_one_mb(F.p, F.f, x, row); });
+}
+
+// ---- border replication, all planes of all streams in two launches -------------------------------------------
+__global__ void k_expand_lr_batch(const StreamFrame* __restrict__ sf) {
+  const StreamFrame& F = sf[blockIdx.z / 3];
+  const int pl = blockIdx.z % 3;
+  const int pad = pl ? 16 : 32, st = pl ? F.p.rec_stride_c : F.p.rec_stride_y;
+  const int w = (pl ? 8 : 16) * F.p.mb_w, h = (pl ? 8 : 16) * F.p.mb_h;
+  const int y = blockIdx.x * blockDim.y + threadIdx.y;
+  if (y >= h) return;
+  uint8_t* row = F.f.rec[pl] + (size_t)y * st;
+  const uint8_t l = row[0], r = row[w - 1];
+  for (int x = threadIdx.x; x < pad; x += blockDim.x) { row[x - pad] = l; row[w + x] = r; }
+}
+__global__ void k_expand_tb_batch(const StreamFrame* __restrict__ sf) {
+  const StreamFrame& F = sf[blockIdx.z / 3];
+  const int pl = blockIdx.z % 3;
+  const int pad = pl ? 16 : 32, st = pl ? F.p.rec_stride_c : F.p.rec_stride_y;
+  const int w = (pl ? 8 : 16) * F.p.mb_w, h = (pl ? 8 : 16) * F.p.mb_h;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x - pad;
+  if (x >= w + pad) return;
+  uint8_t* pic = F.f.rec[pl];
+  const uint8_t t = pic[x], b = pic[(size_t)(h - 1) * st + x];
+  for (int y = 1 + blockIdx.y; y <= pad; y += gridDim.y) {
+    pic[x - (ptrdiff_t)y * st] = t;
+    pic[(size_t)(h - 1 + y) * st + x] = b;
+  }
+}
+
+// ================================================================================================
+// H.264 Tables 8-16 / 8-17 (host copies; the device reads the constant-memory twins)
+namespace mbk {
+uint8_t h_alpha[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 4, 5, 6, 7, 8, 9, 10, 12, 13, 15, 17, 20, 22, 25, 28,
+                       32, 36, 40, 45, 50, 56, 63, 71, 80, 90, 101, 113, 127, 144, 162, 182, 203, 226, 255, 255};
+uint8_t h_beta[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 6, 6, 7, 7, 8, 8,
+                      9, 9, 10, 10, 11, 11, 12, 12, 13, 13, 14, 14, 15, 15, 16, 16, 17, 17, 18, 18};
+uint8_t h_tc0[52][3] = {
+    {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0},
+    {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 0, 1}, {0, 1, 1},
+    {0, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 1}, {1, 1, 2}, {1, 1, 2}, {1, 1, 2}, {1, 1, 2}, {1, 2, 3}, {1, 2, 3},
+    {2, 2, 3}, {2, 2, 4}, {2, 3, 4}, {2, 3, 4}, {3, 3, 5}, {3, 4, 6}, {3, 4, 6}, {4, 5, 7}, {4, 5, 8}, {4, 6, 9}, {5, 7, 10},
+    {6, 8, 11}, {6, 8, 13}, {7, 10, 14}, {8, 11, 16}, {9, 12, 18}, {10, 13, 20}, {11, 15, 23}, {13, 17, 25}};
+}  // namespace mbk
+
+int enc_upload_deblock_tables() {
+  cudaError_t e;
+  if ((e = cudaMemcpyToSymbol(mbk::c_alpha, mbk::h_alpha, sizeof(mbk::h_alpha))) != cudaSuccess) return (int)e;
+  if ((e = cudaMemcpyToSymbol(mbk::c_beta, mbk::h_beta, sizeof(mbk::h_beta))) != cudaSuccess) return (int)e;
+  if ((e = cudaMemcpyToSymbol(mbk::c_tc0, mbk::h_tc0, sizeof(mbk::h_tc0))) != cudaSuccess) return (int)e;
+  return 0;
+}
+
+static int g_enc_blocks = 0;
+static int enc_grid_blocks() {
+  if (g_enc_blocks) return g_enc_blocks;
+  cudaFuncSetAttribute(k_encode_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MbScratch) * ENC_WPC));
+  int dev = 0, sms = 0, per_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_rows, 32 * ENC_WPC, sizeof(MbScratch) * ENC_WPC);
+  if (per_sm < 1) per_sm = 1;
+  g_enc_blocks = sms * per_sm;          // persistent: exactly what the chip can hold
+  return g_enc_blocks;
+}
+
+int enc_launch_frame(const StreamFrame* d_sf, const uint8_t* const* d_src, int n_streams, int w, int h, int mb_w, int mb_h,
+                     int* d_tickets /* 2 ints */, cudaStream_t st) {
+  int rc;
+  if (d_src) {
+    dim3 b(32, 8), g((mb_w * 4 + 31) / 32, (mb_h * 16 + 7) / 8, n_streams);
+    k_pad_source<<<g, b, 0, st>>>(d_sf, d_src, w, h);
+    if ((rc = b2h264_launched())) return rc;
+  }
+  cudaMemsetAsync(d_tickets, 0, 2 * sizeof(int), st);
+  const int rows = n_streams * mb_h;
+  int blocks = enc_grid_blocks();
+  const int need = (rows + ENC_WPC - 1) / ENC_WPC;
+  if (blocks > need) blocks = need;
+  k_encode_rows<<<blocks, 32 * ENC_WPC, sizeof(MbScratch) * ENC_WPC, st>>>(d_sf, n_streams, d_tickets);
+  if ((rc = b2h264_launched())) return rc;
+  return 0;
+}
+
+int enc_launch_deblock_expand(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h, int* d_tickets, cudaStream_t st) {
+  int rc;
+  const int rows = n_streams * mb_h;
+  int blocks = enc_grid_blocks() * 2;
+  const int need = (rows + ENC_WPC - 1) / ENC_WPC;
+  if (blocks > need) blocks = need;
+  k_deblock_rows<<<blocks, 32 * ENC_WPC, 0, st>>>(d_sf, n_streams, d_tickets + 1);
+  if ((rc = b2h264_launched())) return rc;
+  k_expand_lr_batch<<<dim3((mb_h * 16 + 7) / 8, 1, 3 * n_streams), dim3(32, 8), 0, st>>>(d_sf);
+  if ((rc = b2h264_launched())) return rc;
+  k_expand_tb_batch<<<dim3((mb_w * 16 + 64 + 127) / 128, 4, 3 * n_streams), dim3(128), 0, st>>>(d_sf);
+  return b2h264_launched();
+}
+
+size_t enc_scratch_bytes() { return sizeof(MbScratch); }

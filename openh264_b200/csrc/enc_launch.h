@@ -1,0 +1,19 @@
+// enc_launch.h — host-callable launchers of the encoder kernels (enc_kernels.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "enc_types.h"
+
+struct StreamFrame {            // one stream's frame job, array in device memory
+  EncFrameParams p;
+  EncFramePtrs f;
+};
+
+int enc_upload_deblock_tables();
+// pad (if d_src != NULL) + wavefront macroblock kernel for n_streams pictures of identical geometry
+int enc_launch_frame(const StreamFrame* d_sf, const uint8_t* const* d_src, int n_streams, int w, int h, int mb_w, int mb_h,
+                     int* d_tickets, cudaStream_t st);
+// wavefront deblocking + border expansion of the pictures just reconstructed
+int enc_launch_deblock_expand(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h, int* d_tickets, cudaStream_t st);
+size_t enc_scratch_bytes();

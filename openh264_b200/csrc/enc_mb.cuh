@@ -25,6 +25,9 @@ struct MbScratch {
   int8_t  skip_flag[4];
   MbOut   out;                  // staged output record
   MbInfo  info;                 // staged MbInfo
+  MbInfo  nbi[4];               // neighbours' MbInfo: 0 top-left, 1 top, 2 top-right, 3 left (valid per c.nb)
+  int32_t nb_sad[4];            // neighbours' persistent SAD cost (pSadCost[0])
+  int32_t nb_skip_sad[4];       // neighbours' skip SAD of THIS picture (pMbSkipSad)
   int32_t red[32];              // small scratch
 };
 
@@ -47,6 +50,44 @@ MBK_HD uint8_t ld_cg_u8(const uint8_t* p) {
 #else
   return *p;
 #endif
+}
+
+MBK_HD uint32_t ld_cg_u32(const uint32_t* p) {
+#ifdef __CUDA_ARCH__
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
+
+// Neighbour records into the scratch.  The left MB was coded by this warp (its staged record is still in
+// s.info when this is called); the three top neighbours were written by the warp of the previous MB row,
+// possibly on another SM, so they are fetched with L1-bypassing loads.
+MBK_HD void mb_load_neighbors(const MbCtx& c, MbScratch& s) {
+  const int mbw = c.p.mb_w, idx = c.mby * mbw + c.mbx;
+  {
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(&s.info);
+    uint32_t* b = reinterpret_cast<uint32_t*>(&s.nbi[3]);
+    for (int i = lane_id(); i < (int)(sizeof(MbInfo) / 4); i += MBK_WS) b[i] = a[i];
+  }
+  const int offs[3] = {-mbw - 1, -mbw, -mbw + 1};
+  const int bits[3] = {NB_TOPLEFT, NB_TOP, NB_TOPRIGHT};
+  for (int k = 0; k < 3; k++) {
+    if (!(c.nb & bits[k])) continue;
+    const uint32_t* a = reinterpret_cast<const uint32_t*>(c.f.mbi + idx + offs[k]);
+    uint32_t* b = reinterpret_cast<uint32_t*>(&s.nbi[k]);
+    for (int i = lane_id(); i < (int)(sizeof(MbInfo) / 4); i += MBK_WS) b[i] = ld_cg_u32(a + i);
+  }
+  if (lane_id() == 0) {
+    const int o4[4] = {-mbw - 1, -mbw, -mbw + 1, -1};
+    const int b4[4] = {NB_TOPLEFT, NB_TOP, NB_TOPRIGHT, NB_LEFT};
+    for (int k = 0; k < 4; k++) {
+      const bool av = (c.nb & b4[k]) != 0;
+      s.nb_sad[k] = av ? (int32_t)ld_cg_u32(reinterpret_cast<const uint32_t*>(c.f.sad_cost + idx + o4[k])) : 0;
+      s.nb_skip_sad[k] = av ? (int32_t)ld_cg_u32(reinterpret_cast<const uint32_t*>(&c.f.rec_info[idx + o4[k]].skip_sad)) : 0;
+    }
+  }
+  warp_sync();
 }
 
 // ---- MB setup ------------------------------------------------------------------------------------
@@ -356,11 +397,11 @@ MBK_HD void fill_i4_cache(const MbCtx& c, MbScratch& s) {
   if (lane_id() == 0) {
     for (int i = 0; i < 25; i++) s.i4m[i] = -1;
     if (c.nb & NB_LEFT) {
-      const MbInfo* l = c.f.mbi + (c.mby * c.p.mb_w + c.mbx - 1);
+      const MbInfo* l = &s.nbi[3];
       for (int y = 0; y < 4; y++) s.i4m[(y + 1) * 5] = l->mb_type == MBT_I4x4 ? l->i4_mode[y * 4 + 3] : 2;
     }
     if (c.nb & NB_TOP) {
-      const MbInfo* t = c.f.mbi + ((c.mby - 1) * c.p.mb_w + c.mbx);
+      const MbInfo* t = &s.nbi[1];
       for (int x = 0; x < 4; x++) s.i4m[x + 1] = t->mb_type == MBT_I4x4 ? t->i4_mode[12 + x] : 2;
     }
   }

@@ -158,3 +158,47 @@ def synth_frame(w, h, t=0, seed=264):
     rng = np.random.RandomState(seed + t)
     v = v + rng.randint(-3, 4, size=(h, w))
     return np.clip(v, 16, 235).astype(np.uint8)
+
+
+def synth_clip(w, h, n, seed=264):
+    """Deterministic INTEGER-ONLY I420 clip (bit-identical on every machine): multi-octave value noise from a
+    32-bit LCG, bilinearly upsampled with integer weights, global pan (+3,+1)/frame, 6 moving textured
+    rectangles, +-3 per-frame noise; chroma = low-amplitude functions of the half-resolution luma.
+    Returns a uint8 array of n*w*h*3/2 bytes."""
+    def lcg_field(gh, gw, s):
+        idx = (np.arange(gh * gw, dtype=np.uint64).reshape(gh, gw) + np.uint64(s) * np.uint64(7919)) & np.uint64(0xffffffff)
+        x = (idx * np.uint64(1664525) + np.uint64(1013904223)) & np.uint64(0xffffffff)
+        x = (x * np.uint64(1664525) + np.uint64(1013904223)) & np.uint64(0xffffffff)
+        x = (x ^ (x >> np.uint64(15))) * np.uint64(2246822519) & np.uint64(0xffffffff)
+        return ((x >> np.uint64(13)) & np.uint64(255)).astype(np.int64)
+
+    def upsample(f, cell, H, W):       # integer bilinear, weights in 1/cell units
+        yy = np.arange(H, dtype=np.int64); xx = np.arange(W, dtype=np.int64)
+        y0, fy = yy // cell, yy % cell
+        x0, fx = xx // cell, xx % cell
+        a = f[y0][:, x0]; b = f[y0][:, x0 + 1]; c = f[y0 + 1][:, x0]; d = f[y0 + 1][:, x0 + 1]
+        fy = fy[:, None]; fx = fx[None, :]
+        return (a * (cell - fy) * (cell - fx) + b * (cell - fy) * fx + c * fy * (cell - fx) + d * fy * fx) // (cell * cell)
+
+    PW, PH = w + 3 * n + 64, h + n + 64            # panned canvas
+    base = np.zeros((PH, PW), np.int64)
+    for k, (cell, amp) in enumerate([(64, 6), (16, 3), (4, 1)]):
+        f = lcg_field(PH // cell + 3, PW // cell + 3, seed + k)
+        base += upsample(f, cell, PH, PW) * amp
+    base = 40 + base * 150 // (255 * 10)
+    frames = []
+    for t in range(n):
+        y = base[t:t + h, 3 * t:3 * t + w].copy()
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.int64)
+        for k in range(6):
+            rw, rh = 48 + 8 * k, 32 + 8 * (k % 3)
+            rx = (k * 211 + (2 * (k % 3) + 1) * t * 2) % max(1, w - rw)
+            ry = (k * 97 + ((k % 2) + 1) * t) % max(1, h - rh)
+            y[ry:ry + rh, rx:rx + rw] = ((xx[ry:ry + rh, rx:rx + rw] * (k + 3) + yy[ry:ry + rh, rx:rx + rw] * (k + 1)) % 64) + 60 + 12 * k
+        nz = lcg_field(h, w, seed + 1000 + t) % 7 - 3
+        y = np.clip(y + nz, 16, 235).astype(np.uint8)
+        sub = y[::2, ::2].astype(np.int64)
+        u = np.clip(128 + (sub - 128) // 4, 16, 240).astype(np.uint8)
+        v = np.clip(128 - (sub - 128) // 6, 16, 240).astype(np.uint8)
+        frames.append(np.concatenate([y.ravel(), u[:h // 2, :w // 2].ravel(), v[:h // 2, :w // 2].ravel()]))
+    return np.concatenate(frames)

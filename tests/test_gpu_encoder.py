@@ -1,0 +1,115 @@
+"""GPU parity tests, layer 2: the batched frame encoder through the C-ABI (include/b2h264_codec.h).
+Bit-exact bitstreams against (i) golden SHA-1s generated from the unmodified reference
+(tests/golden/encoder.json), (ii) the reference itself where oracle/_ref travelled with the repo;
+plus size-independent properties at BASELINE.json's full 1080p size: the reference decoder
+(oracle/_ref) decodes our stream to exactly our own reconstruction; identical streams in a batch give
+identical bitstreams; pipelined (2 in flight) == synchronous."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import h264lib
+
+pytestmark = pytest.mark.gpu
+ROOT = h264lib.ROOT
+GOLD = json.load(open(os.path.join(ROOT, "tests", "golden", "encoder.json")))
+
+
+def parse_key(key):
+    w, h = map(int, key.split("_")[0].split("x"))
+    return w, h, int(key.split("_n")[1].split("_")[0]), int(key.split("_qp")[1].split("_")[0]), float(key.split("_fps")[1])
+
+
+def gpu_encode(yuv, w, h, n, qp, fps, n_streams=1, pipelined=False):
+    from openh264_b200.binding import BatchEncoder
+    enc = BatchEncoder(w, h, qp=qp, fps=fps, n_streams=n_streams)
+    fsz = w * h * 3 // 2
+    frames = [np.ascontiguousarray(yuv[i * fsz:(i + 1) * fsz]) for i in range(n)]
+    outs = [[] for _ in range(n_streams)]
+    if not pipelined:
+        for f in frames:
+            bs, _ = enc.encode([f] * n_streams)
+            for s in range(n_streams):
+                outs[s].append(bs[s])
+    else:
+        enc.submit([frames[0]] * n_streams)
+        for i in range(1, n + 1):
+            if i < n:
+                enc.submit([frames[i]] * n_streams)
+            bs, _ = enc.collect()
+            for s in range(n_streams):
+                outs[s].append(bs[s])
+    rec = enc.recon(0)
+    enc.close()
+    return outs, rec
+
+
+@pytest.mark.parametrize("key", sorted(GOLD))
+def test_bitstream_matches_reference_golden(key):
+    w, h, n, qp, fps = parse_key(key)
+    yuv = h264lib.synth_clip(w, h, n)
+    assert hashlib.sha1(yuv.tobytes()).hexdigest() == GOLD[key]["yuv_sha1"]
+    outs, _ = gpu_encode(yuv, w, h, n, qp, fps)
+    assert [len(b) for b in outs[0]] == GOLD[key]["frame_bytes"]
+    assert hashlib.sha1(b"".join(outs[0])).hexdigest() == GOLD[key]["sha1"]
+
+
+def test_batch_and_pipelining_are_transparent():
+    w, h, n, qp, fps = 320, 192, 6, 26, 12.0
+    yuv = h264lib.synth_clip(w, h, n)
+    single, _ = gpu_encode(yuv, w, h, n, qp, fps)
+    batch, _ = gpu_encode(yuv, w, h, n, qp, fps, n_streams=5, pipelined=True)
+    for s in range(5):
+        assert batch[s] == single[0]
+
+
+@pytest.mark.parametrize("whn", [(320, 192, 6), (1920, 1080, 3)])
+def test_reference_decoder_reproduces_our_reconstruction(whn):
+    if not h264lib.have_ref():
+        pytest.skip("oracle/_ref not present")
+    w, h, n = whn
+    yuv = h264lib.synth_clip(w, h, n, seed=77)
+    outs, rec = gpu_encode(yuv, w, h, n, 28, 30.0)
+    bs = np.frombuffer(b"".join(outs[0]), np.uint8)
+    R = C.CDLL(h264lib.REFSHIM_SO)
+    R.ref_decode.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    fsz = w * h * 3 // 2
+    dec = np.zeros(n * fsz + 64, np.uint8)
+    W, H, s = C.c_int(), C.c_int(), C.c_double()
+    nf = R.ref_decode(bs.ctypes.data, len(bs), dec.ctypes.data, len(dec), C.byref(W), C.byref(H), C.byref(s))
+    assert nf == n and W.value == w and H.value == h
+    assert np.array_equal(dec[(n - 1) * fsz:n * fsz], rec)      # decoder output of the last frame == our deblocked recon
+
+
+def test_against_reference_side_by_side():
+    if not h264lib.have_ref():
+        pytest.skip("oracle/_ref not present")
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_encoder_golden import ref_encode
+    for (w, h, n, qp) in [(352, 288, 5, 24), (640, 480, 4, 36)]:
+        yuv = h264lib.synth_clip(w, h, n, seed=5)
+        ref_bs, ref_fb, _ = ref_encode(yuv, w, h, n, qp, 25.0)
+        outs, _ = gpu_encode(yuv, w, h, n, qp, 25.0)
+        assert b"".join(outs[0]) == ref_bs
+
+
+def test_force_idr_and_bad_config():
+    from openh264_b200.binding import BatchEncoder, B2H264Error
+    w, h = 176, 144
+    yuv = h264lib.synth_clip(w, h, 3)
+    fsz = w * h * 3 // 2
+    enc = BatchEncoder(w, h, qp=30, fps=15.0)
+    _, t0 = enc.encode([yuv[:fsz]])
+    _, t1 = enc.encode([yuv[fsz:2 * fsz]])
+    enc.force_idr()
+    bs2, t2 = enc.encode([yuv[2 * fsz:3 * fsz]])
+    assert (t0[0], t1[0], t2[0]) == (1, 2, 1)
+    assert bs2[0][4] & 31 == 7        # an IDR access unit starts with the SPS
+    enc.close()
+    with pytest.raises(B2H264Error):
+        BatchEncoder(15, 15)

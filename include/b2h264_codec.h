@@ -62,8 +62,14 @@ int  b2h264_enc_force_idr (b2h264_enc* e, int stream);
  * (cropped I420, w*h*3/2 bytes, host memory): for parity tests */
 int  b2h264_enc_get_recon (b2h264_enc* e, int stream, uint8_t* h_dst);
 
-/* timing of the last collected batch, microseconds: [0] GPU kernels (CUDA events), [1] host entropy coding */
-int  b2h264_enc_last_timing (b2h264_enc* e, float* us2);
+/* timing of the last collected batch, microseconds: [0] source padding + macroblock wavefront kernel,
+ * [1] deblocking wavefront + border expansion (both from CUDA events on the encoder's stream),
+ * [2] host entropy coding (wall clock) */
+int  b2h264_enc_last_timing (b2h264_enc* e, float* us3);
+
+/* makes the encoder issue all its GPU work on the caller's CUDA stream (cudaStream_t as void*), e.g. so
+ * that a harness can bracket it with its own events; only while nothing is in flight */
+int  b2h264_enc_set_stream (b2h264_enc* e, void* stream);
 
 /* layer 3 (WelsCreateSVCEncoder / ISVCEncoder, codec_api.h:272-339,545-586) is declared in b2h264_wels_api.h */
 

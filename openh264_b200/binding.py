@@ -77,6 +77,7 @@ API = {
     "b2h264_enc_force_idr": [vp, C.c_int],
     "b2h264_enc_get_recon": [vp, C.c_int, vp],
     "b2h264_enc_last_timing": [vp, C.POINTER(C.c_float)],
+    "b2h264_enc_set_stream": [vp, vp],
     "b2h264_table_quant_ff": [C.c_int],
     "b2h264_table_quant_mf": [C.c_int],
     "b2h264_table_dequant": [C.c_int],
@@ -207,9 +208,12 @@ class BatchEncoder:
         return out
 
     def timing_us(self):
-        t = (C.c_float * 2)()
+        t = (C.c_float * 3)()
         check(self.L.b2h264_enc_last_timing(self.h, t))
-        return t[0], t[1]
+        return t[0], t[1], t[2]
+
+    def set_stream(self, cuda_stream_handle):
+        check(self.L.b2h264_enc_set_stream(self.h, cuda_stream_handle))
 
     def close(self):
         if self.h:

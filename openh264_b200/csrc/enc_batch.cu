@@ -89,12 +89,13 @@ struct b2h264_enc {
   StreamFrame* h_sf[2] = {nullptr, nullptr};
   const uint8_t** h_srcptr[2] = {nullptr, nullptr};
   // in-flight bookkeeping
-  struct Slot { bool busy = false; std::vector<uint8_t> idr; cudaEvent_t ev0, ev1, done; };
+  struct Slot { bool busy = false; std::vector<uint8_t> idr; cudaEvent_t ev0, ev1, ev2, done; };
   Slot slot[2];
   int submit_idx = 0, collect_idx = 0;
   std::vector<std::vector<uint8_t>> bs;   // per stream output of the last collect
   Pool* pool = nullptr;
-  float last_us[2] = {0, 0};
+  float last_us[4] = {0, 0, 0, 0};
+  bool own_stream = true;
   size_t frame_bytes = 0, cur_bytes = 0, pic_bytes = 0, pic_y_bytes = 0, pic_c_bytes = 0;
 
   uint8_t* pic_plane0(int set, int s, int pl) const {   // pixel (0,0) of plane pl of stream s
@@ -146,6 +147,7 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
     CK(cudaMallocHost(&e->h_srcptr[i], S * sizeof(uint8_t*)));
     CK(cudaEventCreate(&e->slot[i].ev0));
     CK(cudaEventCreate(&e->slot[i].ev1));
+    CK(cudaEventCreate(&e->slot[i].ev2));
     CK(cudaEventCreateWithFlags(&e->slot[i].done, cudaEventDisableTiming));
   }
   CK(cudaMalloc(&e->d_src, 2 * S * e->frame_bytes + 256));
@@ -173,9 +175,9 @@ void b2h264_enc_destroy(b2h264_enc* e) {
   for (int i = 0; i < 2; i++) {
     cudaFree(e->d_pic[i]); cudaFree(e->d_rinfo[i]); cudaFree(e->d_out[i]); cudaFree(e->d_sf[i]); cudaFree(e->d_srcptr[i]);
     cudaFreeHost(e->h_out[i]); cudaFreeHost(e->h_sf[i]); cudaFreeHost(e->h_srcptr[i]);
-    cudaEventDestroy(e->slot[i].ev0); cudaEventDestroy(e->slot[i].ev1); cudaEventDestroy(e->slot[i].done);
+    cudaEventDestroy(e->slot[i].ev0); cudaEventDestroy(e->slot[i].ev1); cudaEventDestroy(e->slot[i].ev2); cudaEventDestroy(e->slot[i].done);
   }
-  cudaStreamDestroy(e->st);
+  if (e->own_stream) cudaStreamDestroy(e->st);
   delete e;
 }
 
@@ -192,17 +194,32 @@ int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_devic
   if (sl.busy) return -3;                       // two batches already in flight
   const int S = e->S, mbw = e->ctl[0].sp.mb_w, mbh = e->ctl[0].sp.mb_h;
   // stage sources
+  bool staged = false;
   for (int s = 0; s < S; s++) {
-    if (src_on_device) e->h_srcptr[k][s] = src[s];
-    else {
-      uint8_t* hs = e->h_src + ((size_t)k * S + s) * e->frame_bytes;
-      memcpy(hs, src[s], e->frame_bytes);
-      e->h_srcptr[k][s] = e->d_src + ((size_t)k * S + s) * e->frame_bytes;
+    if (src_on_device) { e->h_srcptr[k][s] = src[s]; continue; }
+    uint8_t* dd = e->d_src + ((size_t)k * S + s) * e->frame_bytes;
+    e->h_srcptr[k][s] = dd;
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, src[s]) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    if (pinned) {                               // caller's buffer is page-locked: DMA straight from it
+      CK(cudaMemcpyAsync(dd, src[s], e->frame_bytes, cudaMemcpyHostToDevice, e->st));
+    } else {                                    // pageable memory: stage through the encoder's pinned ring
+      (void)cudaGetLastError();
+      memcpy(e->h_src + ((size_t)k * S + s) * e->frame_bytes, src[s], e->frame_bytes);
+      staged = true;
     }
   }
-  if (!src_on_device)
-    CK(cudaMemcpyAsync(e->d_src + (size_t)k * S * e->frame_bytes, e->h_src + (size_t)k * S * e->frame_bytes,
-                       (size_t)S * e->frame_bytes, cudaMemcpyHostToDevice, e->st));
+  if (staged) {
+    for (int s = 0; s < S; s++) {
+      cudaPointerAttributes at;
+      const bool pinned = !src_on_device && cudaPointerGetAttributes(&at, src[s]) == cudaSuccess && at.type == cudaMemoryTypeHost;
+      if (!pinned) {
+        (void)cudaGetLastError();
+        const size_t o = ((size_t)k * S + s) * e->frame_bytes;
+        CK(cudaMemcpyAsync(e->d_src + o, e->h_src + o, e->frame_bytes, cudaMemcpyHostToDevice, e->st));
+      }
+    }
+  }
   // per-stream frame descriptors
   sl.idr.assign(S, 0);
   const int rec = e->cur_rec;
@@ -231,10 +248,10 @@ int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_devic
   CK(cudaEventRecord(sl.ev0, e->st));
   int rc = enc_launch_frame(e->d_sf[k], e->d_srcptr[k], S, e->cfg.width, e->cfg.height, mbw, mbh, e->d_tickets, e->st);
   if (rc) return rc;
-  // the entropy coder only needs the macroblock records: copy them back while deblocking runs
+  CK(cudaEventRecord(sl.ev1, e->st));
   rc = enc_launch_deblock_expand(e->d_sf[k], S, mbw, mbh, e->d_tickets, e->st);
   if (rc) return rc;
-  CK(cudaEventRecord(sl.ev1, e->st));
+  CK(cudaEventRecord(sl.ev2, e->st));
   CK(cudaMemcpyAsync(e->h_out[k], e->d_out[k], (size_t)S * e->n_mb * sizeof(MbOut), cudaMemcpyDeviceToHost, e->st));
   CK(cudaEventRecord(sl.done, e->st));
   sl.busy = true;
@@ -250,7 +267,9 @@ int b2h264_enc_collect(b2h264_enc* e, const uint8_t** bs, int32_t* bs_bytes, int
   CK(cudaEventSynchronize(sl.done));
   float ms = 0;
   cudaEventElapsedTime(&ms, sl.ev0, sl.ev1);
-  e->last_us[0] = ms * 1000.f;
+  e->last_us[0] = ms * 1000.f;               // source padding + macroblock wavefront kernel
+  cudaEventElapsedTime(&ms, sl.ev1, sl.ev2);
+  e->last_us[1] = ms * 1000.f;               // deblocking wavefront + border expansion
   const auto t0 = std::chrono::steady_clock::now();
   const int n_mb = e->n_mb;
   std::function<void(int)> job = [&](int s) {
@@ -258,7 +277,7 @@ int b2h264_enc_collect(b2h264_enc* e, const uint8_t** bs, int32_t* bs_bytes, int
     e->ctl[s].write_access_unit(sl.idr[s] != 0, e->h_out[k] + (size_t)s * n_mb, &e->bs[s]);
   };
   e->pool->run(e->S, job);
-  e->last_us[1] = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - t0).count();
+  e->last_us[2] = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - t0).count();
   for (int s = 0; s < e->S; s++) {
     if (bs) bs[s] = e->bs[s].data();
     if (bs_bytes) bs_bytes[s] = (int32_t)e->bs[s].size();
@@ -283,9 +302,19 @@ int b2h264_enc_get_recon(b2h264_enc* e, int stream, uint8_t* dst) {
   return 0;
 }
 
-int b2h264_enc_last_timing(b2h264_enc* e, float* us2) {
-  if (!e || !us2) return -1;
-  us2[0] = e->last_us[0]; us2[1] = e->last_us[1];
+int b2h264_enc_last_timing(b2h264_enc* e, float* us3) {
+  if (!e || !us3) return -1;
+  us3[0] = e->last_us[0]; us3[1] = e->last_us[1]; us3[2] = e->last_us[2];
+  return 0;
+}
+
+int b2h264_enc_set_stream(b2h264_enc* e, void* stream) {
+  if (!e) return -1;
+  if (e->slot[0].busy || e->slot[1].busy) return -3;
+  CK(cudaStreamSynchronize(e->st));
+  if (e->own_stream) cudaStreamDestroy(e->st);
+  e->st = (cudaStream_t)stream;
+  e->own_stream = false;
   return 0;
 }
 

@@ -343,3 +343,51 @@ int ref_decode (const uint8_t* bs, long len, uint8_t* out, long out_cap, int* w,
 }
 
 }  // extern "C"
+
+/* persistent-instance variant of ref_encode for throughput runs (bench.py --impl reference / cpu_baseline):
+ * one encoder per stream lives across calls so that only the first picture is an IDR */
+extern "C" {
+void* ref_enc_open (int w, int h, int qp, int complexity, int threads, float fps) {
+  ISVCEncoder* enc = NULL;
+  if (WelsCreateSVCEncoder (&enc) || !enc) return NULL;
+  SEncParamExt p;
+  enc->GetDefaultParams (&p);
+  p.iUsageType = CAMERA_VIDEO_REAL_TIME;
+  p.iPicWidth = w; p.iPicHeight = h; p.iTargetBitrate = 5000000; p.iRCMode = RC_OFF_MODE; p.fMaxFrameRate = fps;
+  p.iTemporalLayerNum = 1; p.iSpatialLayerNum = 1; p.iComplexityMode = (ECOMPLEXITY_MODE) complexity;
+  p.uiIntraPeriod = 0; p.iNumRefFrame = 1; p.iEntropyCodingModeFlag = 0; p.bEnableFrameSkip = false;
+  p.bEnableLongTermReference = false; p.iMultipleThreadIdc = (unsigned short) threads; p.iLoopFilterDisableIdc = 0;
+  p.bEnableDenoise = false; p.bEnableBackgroundDetection = false; p.bEnableAdaptiveQuant = false;
+  p.bEnableFrameCroppingFlag = true; p.bEnableSceneChangeDetect = false;
+  p.sSpatialLayers[0].iVideoWidth = w; p.sSpatialLayers[0].iVideoHeight = h; p.sSpatialLayers[0].fFrameRate = fps;
+  p.sSpatialLayers[0].iSpatialBitrate = 5000000; p.sSpatialLayers[0].iDLayerQp = qp;
+  p.sSpatialLayers[0].uiProfileIdc = PRO_BASELINE;
+  p.sSpatialLayers[0].sSliceArgument.uiSliceMode = threads > 1 ? SM_FIXEDSLCNUM_SLICE : SM_SINGLE_SLICE;
+  if (threads > 1) p.sSpatialLayers[0].sSliceArgument.uiSliceNum = threads;
+  if (enc->InitializeExt (&p)) { WelsDestroySVCEncoder (enc); return NULL; }
+  int lvl = WELS_LOG_QUIET;
+  enc->SetOption (ENCODER_OPTION_TRACE_LEVEL, &lvl);
+  return enc;
+}
+/* encodes n pictures (tightly packed I420); returns bytes produced (discarded) or <0 */
+long ref_enc_frames (void* h, const uint8_t* yuv, int w, int h_, int n, long long* ts_ms) {
+  ISVCEncoder* enc = (ISVCEncoder*) h;
+  long total = 0;
+  const size_t fsz = (size_t) w * h_ * 3 / 2;
+  for (int i = 0; i < n; i++) {
+    SSourcePicture pic;
+    memset (&pic, 0, sizeof (pic));
+    pic.iColorFormat = videoFormatI420; pic.iPicWidth = w; pic.iPicHeight = h_;
+    pic.iStride[0] = w; pic.iStride[1] = pic.iStride[2] = w / 2;
+    pic.pData[0] = (uint8_t*) yuv + i * fsz; pic.pData[1] = pic.pData[0] + (size_t) w * h_; pic.pData[2] = pic.pData[1] + (size_t) w * h_ / 4;
+    pic.uiTimeStamp = (*ts_ms) += 33;
+    SFrameBSInfo info;
+    memset (&info, 0, sizeof (info));
+    if (enc->EncodeFrame (&pic, &info)) return -1;
+    for (int l = 0; l < info.iLayerNum; l++)
+      for (int k = 0; k < info.sLayerInfo[l].iNalCount; k++) total += info.sLayerInfo[l].pNalLengthInByte[k];
+  }
+  return total;
+}
+void ref_enc_close (void* h) { ISVCEncoder* enc = (ISVCEncoder*) h; enc->Uninitialize(); WelsDestroySVCEncoder (enc); }
+}

@@ -157,7 +157,7 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
   CK(cudaMalloc(&e->d_sad, S * e->n_mb * sizeof(int32_t)));
   CK(cudaMemset(e->d_sad, 0, S * e->n_mb * sizeof(int32_t)));
   CK(cudaMalloc(&e->d_prog, S * 2 * mbh * sizeof(int32_t)));
-  CK(cudaMalloc(&e->d_tickets, 2 * sizeof(int)));
+  CK(cudaMalloc(&e->d_tickets, enc_sched_ints((int)S, e->n_mb) * sizeof(int)));
   e->bs.resize(S);
   int nt = cfg->entropy_threads;
   if (nt <= 0) { nt = (int)std::thread::hardware_concurrency(); if (nt > (int)S) nt = (int)S; if (nt < 1) nt = 1; }
@@ -244,7 +244,6 @@ int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_devic
   e->cur_rec = 1 - rec;
   CK(cudaMemcpyAsync(e->d_sf[k], e->h_sf[k], S * sizeof(StreamFrame), cudaMemcpyHostToDevice, e->st));
   CK(cudaMemcpyAsync(e->d_srcptr[k], e->h_srcptr[k], S * sizeof(uint8_t*), cudaMemcpyHostToDevice, e->st));
-  CK(cudaMemsetAsync(e->d_prog, 0, (size_t)S * 2 * mbh * sizeof(int32_t), e->st));
   CK(cudaEventRecord(sl.ev0, e->st));
   int rc = enc_launch_frame(e->d_sf[k], e->d_srcptr[k], S, e->cfg.width, e->cfg.height, mbw, mbh, e->d_tickets, e->st);
   if (rc) return rc;

@@ -1,13 +1,13 @@
 // enc_kernels.cu — frame-level CUDA kernels of the encoder path (sm_100a):
 //   k_pad_source     source I420 -> MB-aligned current picture
-//   k_encode_rows    macroblock mode decision + coding + reconstruction, ONE WARP PER MACROBLOCK ROW,
-//                    rows of all streams of the batch scheduled as a wavefront (persistent warps + ticket)
-//   k_deblock_rows   in-loop deblocking, same wavefront
+//   k_encode_mbs     macroblock mode decision + coding + reconstruction, ONE WARP PER MACROBLOCK; the MBs of
+//                    all streams of the batch are scheduled by dependency (ready list, persistent warps)
+//   k_deblock_mbs    in-loop deblocking, same scheduling
 //   k_expand_*       border replication of the new reference picture (ExpandReferencingPicture)
 // Why a wavefront: MB(x,y) needs the FINAL state of (x-1,y), (x,y-1), (x+1,y-1) — motion-vector / SAD
 // predictors, intra neighbours, skip context (SURVEY.md §7 hard part 1); bit-exactness forbids breaking
 // that chain, so parallelism comes from rows (2-MB lag) x independent streams of the batch.
-#include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "b2h264_internal.h"
 #define B2H264_WITH_INTER 1
@@ -55,50 +55,82 @@ __global__ void k_pad_source(const StreamFrame* __restrict__ sf, const uint8_t* 
   }
 }
 
-// ---- wavefront row scheduling ----------------------------------------------------------------------------
-// ticket t -> (row = t / n_streams, stream = t % n_streams): every stream's row r is handed out before any
-// row r+1, so the row a warp waits on has always been claimed by a warp that is already running.
-template <bool kDeblock, class Body>
-__device__ __forceinline__ void run_rows(const StreamFrame* sf, int n_streams, int* ticket, Body body) {
+// ---- dependency-driven macroblock scheduling -------------------------------------------------------------
+// MB(x,y) may start when (x-1,y) and (x+1,y-1) [(x,y-1) on the last column] are final; those two imply the
+// top and top-left neighbours.  Every finished MB notifies its right neighbour and its bottom-left
+// neighbour; the second notification pushes the MB onto a global ready list.  Persistent warps pop the
+// list: no warp ever holds an SM slot while a row it depends on is still busy (a row-per-warp wavefront
+// spent >80% of its issue slots spinning, profiles/r01_encode_rows_ncu.txt).
+struct Sched {
+  int* dep;        // per (stream, mb): notifications received so far
+  int* queue;      // ready list, capacity = n_streams * n_mb, -1 = not yet pushed
+  int* head;       // next entry to pop
+  int* tail;       // next free entry
+};
+
+__device__ __forceinline__ void sched_push(const Sched& q, int id) {
+  const int slot = atomicAdd(q.tail, 1);
+  *reinterpret_cast<volatile int*>(q.queue + slot) = id;
+}
+__device__ __forceinline__ void sched_notify(const Sched& q, int id, int need) {
+  if (atomicAdd(q.dep + id, 1) + 1 == need) sched_push(q, id);
+}
+
+template <class Body>
+__device__ __forceinline__ void run_mbs(const StreamFrame* sf, int n_streams, const Sched q, Body body) {
   const int lane = threadIdx.x & 31;
+  const int mb_w = sf[0].p.mb_w, mb_h = sf[0].p.mb_h, n_mb = mb_w * mb_h, total = n_streams * n_mb;
   for (;;) {
-    int t = 0;
-    if (lane == 0) t = atomicAdd(ticket, 1);
-    t = __shfl_sync(MBK_FULL, t, 0);
-    const int mb_h = sf[0].p.mb_h;
-    if (t >= n_streams * mb_h) break;
-    const int row = t / n_streams, si = t - row * n_streams;
-    const StreamFrame& F = sf[si];
-    const int mb_w = F.p.mb_w;
-    int* prog = kDeblock ? F.f.row_progress_dbk : F.f.row_progress;
-    int seen = 0;
-    for (int x = 0; x < mb_w; x++) {
-      if (row > 0) {
-        const int need = x + 2 < mb_w ? x + 2 : mb_w;
-        if (seen < need) {
-          if (lane == 0) {
-            while ((seen = ld_volatile(prog + row - 1)) < need) __nanosleep(64);
-          }
-          seen = __shfl_sync(MBK_FULL, seen, 0);
-          __threadfence();
-        }
+    int id = 0;
+    if (lane == 0) {
+      const int t = atomicAdd(q.head, 1);
+      id = -1;
+      if (t < total) {
+        while ((id = ld_volatile(q.queue + t)) < 0) __nanosleep(100);
       }
-      body(F, x, row);
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) *reinterpret_cast<volatile int*>(prog + row) = x + 1;
+    }
+    id = __shfl_sync(MBK_FULL, id, 0);
+    if (id < 0) break;
+    __threadfence();
+    const int si = id / n_mb, mb = id - si * n_mb, y = mb / mb_w, x = mb - y * mb_w;
+    body(sf[si], x, y);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+      if (x + 1 < mb_w) sched_notify(q, id + 1, 1 + (y > 0));                    // right neighbour: we are its left
+      if (y + 1 < mb_h) {
+        if (x > 0) sched_notify(q, id + mb_w - 1, 1 + (x - 1 > 0));              // bottom-left: we are its top-right
+        if (x == mb_w - 1) sched_notify(q, id + mb_w, 1 + (x > 0));              // last column: we are its top
+      }
     }
   }
 }
 
-__global__ void __launch_bounds__(32 * ENC_WPC) k_encode_rows(const StreamFrame* __restrict__ sf, int n_streams, int* ticket) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  MbScratch& s = reinterpret_cast<MbScratch*>(smem)[threadIdx.x >> 5];
-  run_rows<false>(sf, n_streams, ticket, [&](const StreamFrame& F, int x, int row) { encode_one_mb(F.p, F.f, s, x, row); });
+__global__ void k_sched_init(Sched q, int n_streams, int n_mb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_streams) q.queue[i] = i * n_mb;        // MB (0,0) of every stream is ready
+  if (i == 0) { *q.head = 0; *q.tail = n_streams; }
 }
 
-__global__ void __launch_bounds__(32 * ENC_WPC) k_deblock_rows(const StreamFrame* __restrict__ sf, int n_streams, int* ticket) {
-  run_rows<true>(sf, n_streams, ticket, [&](const StreamFrame& F, int x, int row) { deblock_one_mb(F.p, F.f, x, row); });
+// optional per-MB-type cycle statistics (debug): [type*2] = cycles, [type*2+1] = count
+__device__ unsigned long long g_enc_stats[16];
+
+__global__ void __launch_bounds__(32 * ENC_WPC) k_encode_mbs(const StreamFrame* __restrict__ sf, int n_streams, Sched q, int stats) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  MbScratch& s = reinterpret_cast<MbScratch*>(smem)[threadIdx.x >> 5];
+  run_mbs(sf, n_streams, q, [&](const StreamFrame& F, int x, int y) {
+    const long long t0 = stats ? clock64() : 0;
+    encode_one_mb(F.p, F.f, s, x, y);
+    if (stats && (threadIdx.x & 31) == 0) {
+      const int t = s.info.mb_type & 7;
+      atomicAdd(&g_enc_stats[2 * t], (unsigned long long)(clock64() - t0));
+      atomicAdd(&g_enc_stats[2 * t + 1], 1ull);
+    }
+  });
+}
+
+__global__ void __launch_bounds__(32 * ENC_WPC) k_deblock_mbs(const StreamFrame* __restrict__ sf, int n_streams, Sched q) {
+  run_mbs(sf, n_streams, q, [&](const StreamFrame& F, int x, int y) { deblock_one_mb(F.p, F.f, x, y); });
 }
 
 // ---- border replication, all planes of all streams in two launches -------------------------------------------
@@ -154,41 +186,57 @@ int enc_upload_deblock_tables() {
 static int g_enc_blocks = 0;
 static int enc_grid_blocks() {
   if (g_enc_blocks) return g_enc_blocks;
-  cudaFuncSetAttribute(k_encode_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MbScratch) * ENC_WPC));
+  cudaFuncSetAttribute(k_encode_mbs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MbScratch) * ENC_WPC));
   int dev = 0, sms = 0, per_sm = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_rows, 32 * ENC_WPC, sizeof(MbScratch) * ENC_WPC);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_mbs, 32 * ENC_WPC, sizeof(MbScratch) * ENC_WPC);
   if (per_sm < 1) per_sm = 1;
   g_enc_blocks = sms * per_sm;          // persistent: exactly what the chip can hold
   return g_enc_blocks;
 }
 
+// scheduler workspace layout (ints): [0..3] head/tail for encode, deblock; then dep[2][total]; then queue[2][total]
+size_t enc_sched_ints(int n_streams, int n_mb) { return 8 + 4 * (size_t)n_streams * n_mb; }
+
+static Sched make_sched(int* ws, int which, int total) {
+  Sched q;
+  q.head = ws + 2 * which; q.tail = ws + 2 * which + 1;
+  q.dep = ws + 8 + (size_t)which * total;
+  q.queue = ws + 8 + (size_t)(2 + which) * total;
+  return q;
+}
+
 int enc_launch_frame(const StreamFrame* d_sf, const uint8_t* const* d_src, int n_streams, int w, int h, int mb_w, int mb_h,
-                     int* d_tickets /* 2 ints */, cudaStream_t st) {
+                     int* d_ws, cudaStream_t st) {
   int rc;
   if (d_src) {
     dim3 b(32, 8), g((mb_w * 4 + 31) / 32, (mb_h * 16 + 7) / 8, n_streams);
     k_pad_source<<<g, b, 0, st>>>(d_sf, d_src, w, h);
     if ((rc = b2h264_launched())) return rc;
   }
-  cudaMemsetAsync(d_tickets, 0, 2 * sizeof(int), st);
-  const int rows = n_streams * mb_h;
+  const int total = n_streams * mb_w * mb_h;
+  cudaMemsetAsync(d_ws + 8, 0, 2 * (size_t)total * sizeof(int), st);                               // dep counters
+  cudaMemsetAsync(d_ws + 8 + 2 * (size_t)total, 0xff, 2 * (size_t)total * sizeof(int), st);        // ready lists
+  const Sched qe = make_sched(d_ws, 0, total), qd = make_sched(d_ws, 1, total);
+  k_sched_init<<<(n_streams + 127) / 128, 128, 0, st>>>(qe, n_streams, mb_w * mb_h);
+  k_sched_init<<<(n_streams + 127) / 128, 128, 0, st>>>(qd, n_streams, mb_w * mb_h);
   int blocks = enc_grid_blocks();
-  const int need = (rows + ENC_WPC - 1) / ENC_WPC;
+  const int need = (total + ENC_WPC - 1) / ENC_WPC;
   if (blocks > need) blocks = need;
-  k_encode_rows<<<blocks, 32 * ENC_WPC, sizeof(MbScratch) * ENC_WPC, st>>>(d_sf, n_streams, d_tickets);
+  static const int stats = getenv("B2H264_ENC_STATS") ? 1 : 0;
+  k_encode_mbs<<<blocks, 32 * ENC_WPC, sizeof(MbScratch) * ENC_WPC, st>>>(d_sf, n_streams, qe, stats);
   if ((rc = b2h264_launched())) return rc;
   return 0;
 }
 
-int enc_launch_deblock_expand(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h, int* d_tickets, cudaStream_t st) {
+int enc_launch_deblock_expand(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h, int* d_ws, cudaStream_t st) {
   int rc;
-  const int rows = n_streams * mb_h;
-  int blocks = enc_grid_blocks() * 2;
-  const int need = (rows + ENC_WPC - 1) / ENC_WPC;
+  const int total = n_streams * mb_w * mb_h;
+  int blocks = enc_grid_blocks() * 3;
+  const int need = (total + ENC_WPC - 1) / ENC_WPC;
   if (blocks > need) blocks = need;
-  k_deblock_rows<<<blocks, 32 * ENC_WPC, 0, st>>>(d_sf, n_streams, d_tickets + 1);
+  k_deblock_mbs<<<blocks, 32 * ENC_WPC, 0, st>>>(d_sf, n_streams, make_sched(d_ws, 1, total));
   if ((rc = b2h264_launched())) return rc;
   k_expand_lr_batch<<<dim3((mb_h * 16 + 7) / 8, 1, 3 * n_streams), dim3(32, 8), 0, st>>>(d_sf);
   if ((rc = b2h264_launched())) return rc;
@@ -197,3 +245,10 @@ int enc_launch_deblock_expand(const StreamFrame* d_sf, int n_streams, int mb_w, 
 }
 
 size_t enc_scratch_bytes() { return sizeof(MbScratch); }
+
+extern "C" int b2h264_debug_enc_stats(unsigned long long* out16, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out16, g_enc_stats, sizeof(g_enc_stats));
+  if (e != cudaSuccess) return (int)e;
+  if (reset) { unsigned long long z[16] = {0}; e = cudaMemcpyToSymbol(g_enc_stats, z, sizeof(z)); }
+  return (int)e;
+}

@@ -60,32 +60,23 @@ MBK_HD uint32_t ld_cg_u32(const uint32_t* p) {
 #endif
 }
 
-// Neighbour records into the scratch.  The left MB was coded by this warp (its staged record is still in
-// s.info when this is called); the three top neighbours were written by the warp of the previous MB row,
-// possibly on another SM, so they are fetched with L1-bypassing loads.
+// Neighbour records into the scratch.  Neighbouring macroblocks are coded by other warps, possibly on
+// other SMs, during the same launch: they are fetched with L1-bypassing loads (after the scheduler's fence).
 MBK_HD void mb_load_neighbors(const MbCtx& c, MbScratch& s) {
   const int mbw = c.p.mb_w, idx = c.mby * mbw + c.mbx;
-  {
-    const uint32_t* a = reinterpret_cast<const uint32_t*>(&s.info);
-    uint32_t* b = reinterpret_cast<uint32_t*>(&s.nbi[3]);
-    for (int i = lane_id(); i < (int)(sizeof(MbInfo) / 4); i += MBK_WS) b[i] = a[i];
+  const int offs[4] = {-mbw - 1, -mbw, -mbw + 1, -1};
+  const int bits[4] = {NB_TOPLEFT, NB_TOP, NB_TOPRIGHT, NB_LEFT};
+  // 4 records x 30 words: one pass, all loads in flight together
+  for (int i = lane_id(); i < 4 * (int)(sizeof(MbInfo) / 4); i += MBK_WS) {
+    const int k = i / (int)(sizeof(MbInfo) / 4), w = i - k * (int)(sizeof(MbInfo) / 4);
+    if (c.nb & bits[k])
+      reinterpret_cast<uint32_t*>(&s.nbi[k])[w] = ld_cg_u32(reinterpret_cast<const uint32_t*>(c.f.mbi + idx + offs[k]) + w);
   }
-  const int offs[3] = {-mbw - 1, -mbw, -mbw + 1};
-  const int bits[3] = {NB_TOPLEFT, NB_TOP, NB_TOPRIGHT};
-  for (int k = 0; k < 3; k++) {
-    if (!(c.nb & bits[k])) continue;
-    const uint32_t* a = reinterpret_cast<const uint32_t*>(c.f.mbi + idx + offs[k]);
-    uint32_t* b = reinterpret_cast<uint32_t*>(&s.nbi[k]);
-    for (int i = lane_id(); i < (int)(sizeof(MbInfo) / 4); i += MBK_WS) b[i] = ld_cg_u32(a + i);
-  }
-  if (lane_id() == 0) {
-    const int o4[4] = {-mbw - 1, -mbw, -mbw + 1, -1};
-    const int b4[4] = {NB_TOPLEFT, NB_TOP, NB_TOPRIGHT, NB_LEFT};
-    for (int k = 0; k < 4; k++) {
-      const bool av = (c.nb & b4[k]) != 0;
-      s.nb_sad[k] = av ? (int32_t)ld_cg_u32(reinterpret_cast<const uint32_t*>(c.f.sad_cost + idx + o4[k])) : 0;
-      s.nb_skip_sad[k] = av ? (int32_t)ld_cg_u32(reinterpret_cast<const uint32_t*>(&c.f.rec_info[idx + o4[k]].skip_sad)) : 0;
-    }
+  for (int k = lane_id(); k < 8; k += MBK_WS) {
+    const int j = k & 3;
+    const bool av = (c.nb & bits[j]) != 0;
+    if (k < 4) s.nb_sad[j] = av ? (int32_t)ld_cg_u32(reinterpret_cast<const uint32_t*>(c.f.sad_cost + idx + offs[j])) : 0;
+    else s.nb_skip_sad[j] = av ? (int32_t)ld_cg_u32(reinterpret_cast<const uint32_t*>(&c.f.rec_info[idx + offs[j]].skip_sad)) : 0;
   }
   warp_sync();
 }
@@ -105,35 +96,32 @@ MBK_HD void mb_load_cur(const MbCtx& c, MbScratch& s) {
   warp_sync();
 }
 
-// neighbour samples into the tile borders.  Left column / top-left come from the tile of the previous
-// MB of this row (same warp); the top row comes from the picture (row above, other warp).
+// neighbour samples into the tile borders, from the picture being reconstructed (written by other warps)
 MBK_HD void mb_load_borders(const MbCtx& c, MbScratch& s) {
   RecTile& t = s.tile;
-  // left: column 15 of the previous tile -> column -1 (before the tile is overwritten)
-  for (int i = lane_id(); i < 32; i += MBK_WS) {
-    if (i < 16) *tile_y(t, -1, i) = (c.nb & NB_LEFT) ? *tile_y(t, 15, i) : 0;
-    else if (i < 24) *tile_c(t.u, -1, i - 16) = (c.nb & NB_LEFT) ? *tile_c(t.u, 7, i - 16) : 0;
-    else *tile_c(t.v, -1, i - 24) = (c.nb & NB_LEFT) ? *tile_c(t.v, 7, i - 24) : 0;
-  }
-  warp_sync();
-  if (c.nb & (NB_TOP | NB_TOPLEFT | NB_TOPRIGHT)) {
-    const uint8_t* ry = c.f.rec[0] + (ptrdiff_t)(c.mby * 16 - 1) * c.p.rec_stride_y + c.mbx * 16;
-    const uint8_t* ru = c.f.rec[1] + (ptrdiff_t)(c.mby * 8 - 1) * c.p.rec_stride_c + c.mbx * 8;
-    const uint8_t* rv = c.f.rec[2] + (ptrdiff_t)(c.mby * 8 - 1) * c.p.rec_stride_c + c.mbx * 8;
-    for (int i = lane_id(); i < 25 + 9 + 9; i += MBK_WS) {
-      if (i < 25) {             // x = -1 .. 23
-        const int x = i - 1;
-        const bool ok = x < 0 ? (c.nb & NB_TOPLEFT) : x < 16 ? (c.nb & NB_TOP) : (c.nb & NB_TOPRIGHT);
-        *tile_y(t, x, -1) = ok ? ld_cg_u8(ry + x) : 0;
-      } else if (i < 34) {
-        const int x = i - 26;
-        const bool ok = x < 0 ? (c.nb & NB_TOPLEFT) : (c.nb & NB_TOP);
-        *tile_c(t.u, x, -1) = ok ? ld_cg_u8(ru + x) : 0;
-      } else {
-        const int x = i - 35;
-        const bool ok = x < 0 ? (c.nb & NB_TOPLEFT) : (c.nb & NB_TOP);
-        *tile_c(t.v, x, -1) = ok ? ld_cg_u8(rv + x) : 0;
-      }
+  const uint8_t* ry = c.f.rec[0] + (ptrdiff_t)(c.mby * 16 - 1) * c.p.rec_stride_y + c.mbx * 16;
+  const uint8_t* ru = c.f.rec[1] + (ptrdiff_t)(c.mby * 8 - 1) * c.p.rec_stride_c + c.mbx * 8;
+  const uint8_t* rv = c.f.rec[2] + (ptrdiff_t)(c.mby * 8 - 1) * c.p.rec_stride_c + c.mbx * 8;
+  // 43 top samples (luma x = -1..23, chroma x = -1..7 twice) + 32 left samples (16 luma, 8 + 8 chroma)
+  for (int i = lane_id(); i < 43 + 32; i += MBK_WS) {
+    if (i < 25) {
+      const int x = i - 1;
+      const bool ok = x < 0 ? (c.nb & NB_TOPLEFT) : x < 16 ? (c.nb & NB_TOP) : (c.nb & NB_TOPRIGHT);
+      *tile_y(t, x, -1) = ok ? ld_cg_u8(ry + x) : 0;
+    } else if (i < 34) {
+      const int x = i - 26;
+      const bool ok = x < 0 ? (c.nb & NB_TOPLEFT) : (c.nb & NB_TOP);
+      *tile_c(t.u, x, -1) = ok ? ld_cg_u8(ru + x) : 0;
+    } else if (i < 43) {
+      const int x = i - 35;
+      const bool ok = x < 0 ? (c.nb & NB_TOPLEFT) : (c.nb & NB_TOP);
+      *tile_c(t.v, x, -1) = ok ? ld_cg_u8(rv + x) : 0;
+    } else {
+      const int j = i - 43;
+      const bool ok = (c.nb & NB_LEFT) != 0;
+      if (j < 16) *tile_y(t, -1, j) = ok ? ld_cg_u8(ry + (ptrdiff_t)(j + 1) * c.p.rec_stride_y - 1) : 0;
+      else if (j < 24) *tile_c(t.u, -1, j - 16) = ok ? ld_cg_u8(ru + (ptrdiff_t)(j - 15) * c.p.rec_stride_c - 1) : 0;
+      else *tile_c(t.v, -1, j - 24) = ok ? ld_cg_u8(rv + (ptrdiff_t)(j - 23) * c.p.rec_stride_c - 1) : 0;
     }
   }
   warp_sync();

@@ -1,0 +1,17 @@
+import os, sys, ctypes as C, numpy as np
+os.environ["B2H264_ENC_STATS"]="1"
+sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+import h264lib
+from openh264_b200.binding import BatchEncoder, lib
+W,H=1920,1080
+S=int(sys.argv[1]) if len(sys.argv)>1 else 16
+clip=h264lib.synth_clip(W,H,6); fsz=W*H*3//2
+enc=BatchEncoder(W,H,qp=26,fps=30.0,n_streams=S)
+L=lib(0); L.b2h264_debug_enc_stats.argtypes=[C.c_void_p,C.c_int]
+st=np.zeros(16,np.uint64)
+names=['I4x4','I16','P16','P16x8','P8x16','P8x8','SKIP','?']
+for f in range(6):
+    enc.encode([clip[f*fsz:(f+1)*fsz]]*S)
+    L.b2h264_debug_enc_stats(st.ctypes.data,1)
+    t=enc.timing_us()
+    print('frame',f,'kernel us',round(t[0]),'dbk',round(t[1]), {names[i]:(int(st[2*i+1]), int(st[2*i]//max(1,st[2*i+1]))) for i in range(7) if st[2*i+1]})

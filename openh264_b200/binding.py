@@ -7,7 +7,7 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libopenh264_b200.so")
+SO_PATH = os.environ.get("B2H264_LIB") or os.path.join(HERE, "libopenh264_b200.so")   # env override: profiling variants only
 
 u8p, i8p = C.POINTER(C.c_uint8), C.POINTER(C.c_int8)
 i16p, u16p, i32p = C.POINTER(C.c_int16), C.POINTER(C.c_uint16), C.POINTER(C.c_int32)

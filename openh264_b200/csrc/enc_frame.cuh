@@ -16,17 +16,17 @@ MBK_HD void encode_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScra
   c.qp = p.qp;
   c.qp_c = tbl_chroma_qp(p.qp);          // chroma_qp_index_offset = 0
   c.lambda = tbl_lambda(p.qp);
-  mb_load_neighbors(c, s);               // (uses the previous MB's staged record as the left neighbour)
-  // clear the staged records
+  phase_mark(s, 31);
+  // clear the staged records (levels need no clearing: every block that gets written to the bitstream is
+  // produced by this MB's own coding path; only the header part must be deterministic)
   {
     uint32_t* a = reinterpret_cast<uint32_t*>(&s.info);
     for (int i = lane_id(); i < (int)(sizeof(MbInfo) / 4); i += MBK_WS) a[i] = 0;
     uint32_t* b = reinterpret_cast<uint32_t*>(&s.out);
-    for (int i = lane_id(); i < (int)(sizeof(MbOut) / 4); i += MBK_WS) b[i] = 0;
+    for (int i = lane_id(); i < MBOUT_HEADER_WORDS; i += MBK_WS) b[i] = 0;
   }
-  warp_sync();
-  mb_load_cur(c, s);
-  mb_load_borders(c, s);
+  mb_load_all(c, s);
+  phase_mark(s, 0);
   if (p.is_idr) {
     intra_mb_md_enc(c, s, 0x7fffffff);
     if (lane_id() == 0) { s.info.ref_idx = -1; c.f.sad_cost[mby * p.mb_w + mbx] = 0; }   // pSadCost[0] = 0 (:2038)
@@ -37,8 +37,10 @@ MBK_HD void encode_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScra
   }
 #endif
   warp_sync();
+  phase_mark(s, 10);
   mb_store_recon(c, s);
   mb_publish(c, s);
+  phase_mark(s, 11);
 }
 
 }  // namespace mbk

@@ -35,41 +35,36 @@ MBK_HD int median3(int a, int b, int c) {
 }
 
 // ---- neighbour caches (FillNeighborCacheInterWithoutBGD, md.cpp:132) ----------------------------------
-MBK_HD void fill_inter_cache(const MbCtx& c, MbScratch& s) {
-  if (lane_id() == 0) {
-    for (int i = 0; i < 30; i++) { s.mvc[i][0] = s.mvc[i][1] = 0; s.refc[i] = 0; }
-    // slot: 0 top-left, 1 top, 2 top-right, 3 left
-    const int bits[4] = {NB_TOPLEFT, NB_TOP, NB_TOPRIGHT, NB_LEFT};
-    for (int k = 0; k < 4; k++) {
+MBK_FN void fill_inter_cache(const MbCtx& c, MbScratch& s) {
+  // one lane per cache cell: cells 0..5 = top-left, top x4, top-right; cells 6,12,18,24 = left column
+  for (int ci = lane_id(); ci < 30; ci += MBK_WS) {
+    int k = -1, blk = 0;                       // neighbour slot (0 TL, 1 T, 2 TR, 3 L) and its 4x4 block (raster)
+    if (ci == 0) { k = 0; blk = 15; }
+    else if (ci <= 4) { k = 1; blk = 12 + ci - 1; }
+    else if (ci == 5) { k = 2; blk = 12; }
+    else if (ci % 6 == 0) { k = 3; blk = 4 * (ci / 6 - 1) + 3; }
+    int16_t mx = 0, my = 0;
+    int8_t ref = 0;
+    if (k >= 0) {
+      const int bits[4] = {NB_TOPLEFT, NB_TOP, NB_TOPRIGHT, NB_LEFT};
       const bool avail = (c.nb & bits[k]) != 0;
       const MbInfo* n = &s.nbi[k];
-      const bool inter = avail && MBT_IS_INTER(n->mb_type);
-      const int8_t na = avail ? REF_NOT_IN_LIST : REF_NOT_AVAIL;
-      s.sadc[k] = inter ? s.nb_sad[k] : 0;
-      const bool skip = inter && n->mb_type == MBT_PSKIP;
-      s.skip_flag[k] = skip;
-      s.sad_skip[k] = skip ? s.nb_skip_sad[k] : 0;
-      if (k == 3) {          // left column: cache 6,12,18,24 <- right column of the left MB
-        for (int r = 0; r < 4; r++) {
-          const int ci = 6 + 6 * r;
-          if (inter) { s.mvc[ci][0] = n->mv[4 * r + 3][0]; s.mvc[ci][1] = n->mv[4 * r + 3][1]; s.refc[ci] = 0; }
-          else s.refc[ci] = na;
-        }
-      } else if (k == 1) {   // top row: cache 1..4 <- bottom row of the top MB
-        for (int x = 0; x < 4; x++) {
-          if (inter) { s.mvc[1 + x][0] = n->mv[12 + x][0]; s.mvc[1 + x][1] = n->mv[12 + x][1]; s.refc[1 + x] = 0; }
-          else s.refc[1 + x] = na;
-        }
-      } else if (k == 0) {
-        if (inter) { s.mvc[0][0] = n->mv[15][0]; s.mvc[0][1] = n->mv[15][1]; s.refc[0] = 0; }
-        else s.refc[0] = na;
-      } else {
-        if (inter) { s.mvc[5][0] = n->mv[12][0]; s.mvc[5][1] = n->mv[12][1]; s.refc[5] = 0; }
-        else s.refc[5] = na;
-      }
+      if (avail && MBT_IS_INTER(n->mb_type)) { mx = n->mv[blk][0]; my = n->mv[blk][1]; }
+      else ref = avail ? REF_NOT_IN_LIST : REF_NOT_AVAIL;
+    } else if (ci == 9 || ci == 11 || ci == 17 || ci == 21 || ci == 23) {
+      ref = REF_NOT_AVAIL;                     // blocks whose top-right neighbour is never available
     }
-    // blocks whose top-right neighbour is never available
-    s.refc[9] = s.refc[11] = s.refc[17] = s.refc[21] = s.refc[23] = REF_NOT_AVAIL;
+    s.mvc[ci][0] = mx; s.mvc[ci][1] = my; s.refc[ci] = ref;
+  }
+  for (int k = lane_id(); k < 4; k += MBK_WS) {
+    const int bits[4] = {NB_TOPLEFT, NB_TOP, NB_TOPRIGHT, NB_LEFT};
+    const bool avail = (c.nb & bits[k]) != 0;
+    const MbInfo* n = &s.nbi[k];
+    const bool inter = avail && MBT_IS_INTER(n->mb_type);
+    const bool skip = inter && n->mb_type == MBT_PSKIP;
+    s.sadc[k] = inter ? s.nb_sad[k] : 0;
+    s.skip_flag[k] = skip;
+    s.sad_skip[k] = skip ? s.nb_skip_sad[k] : 0;
   }
   warp_sync();
 }
@@ -161,7 +156,7 @@ MBK_HD const uint8_t* ref_chroma(const MbCtx& c, int pl, int px, int py) {
 }
 
 // chroma prediction of a (w x h luma) partition at luma offset (ox, oy) with quarter-pel luma mv
-MBK_HD void mc_chroma_part(const MbCtx& c, uint8_t* dst /*Cb, Cr at +64, stride 8*/, int ox, int oy, int w, int h, int mvx, int mvy) {
+MBK_FN void mc_chroma_part(const MbCtx& c, uint8_t* dst /*Cb, Cr at +64, stride 8*/, int ox, int oy, int w, int h, int mvx, int mvy) {
   const int cx = ox >> 1, cy = oy >> 1;
   for (int pl = 0; pl < 2; pl++) {
     const uint8_t* src = ref_chroma(c, 1 + pl, cx + (mvx >> 3), cy + (mvy >> 3));
@@ -173,38 +168,42 @@ MBK_HD void mc_chroma_part(const MbCtx& c, uint8_t* dst /*Cb, Cr at +64, stride 
 // ---- P-skip test (WelsMdPSkipEnc :1423, WelsTryPYskip / WelsTryPUVskip svc_encode_mb.cpp:325,352) -----------
 struct SkipResult { bool ok; int cost_luma; int cost_skip; int mvx, mvy; };
 
-MBK_HD bool try_py_skip(const MbCtx& c, MbScratch& s) {      // lane-0 logic replicated by every lane (uniform)
+// The reference walks the blocks serially and returns at the first failing test; every term of its running
+// score is >= 0, so the outcome is "no block has a level > 1 AND the total score stays below the threshold" —
+// order independent.  One lane per 4x4 block, two warp reductions.
+MBK_FN bool try_py_skip(const MbCtx& c, MbScratch& s) {
   const int16_t* ff = tbl_quant_ff(c.qp);
   const int16_t* mf = tbl_quant_mf(c.qp);
-  int ctr = 0;
-  for (int k = 0; k < 16; k++) {
+  int big = 0, ctr = 0;
+  for (int k = lane_id(); k < 16; k += MBK_WS) {
     int16_t d[16], l[16];
     for (int i = 0; i < 16; i++) d[i] = s.coef[16 * k + i];
     const uint16_t mx = (uint16_t)quant4x4_max(d, ff, mf);
-    if (mx > 1) return false;
-    if (mx == 1) { scan4x4_dcac(l, d); ctr += single_ctr4x4(l); }
-    if (ctr >= 6) return false;
+    if (mx > 1) big = 1;
+    else if (mx == 1) { scan4x4_dcac(l, d); ctr += single_ctr4x4(l); }
   }
-  return true;
+  big = warp_sum(big); ctr = warp_sum(ctr);
+  return big == 0 && ctr < 6;
 }
-MBK_HD bool try_puv_skip(const MbCtx& c, MbScratch& s, int uv) {
+MBK_FN bool try_puv_skip(const MbCtx& c, MbScratch& s, int uv) {
   const int16_t* res = s.coef + 256 + 64 * uv;
   const int16_t* ff = tbl_quant_ff(c.qp_c);
   const int16_t* mf = tbl_quant_mf(c.qp_c);
   const int16_t dcin[4] = {res[0], res[16], res[32], res[48]};
-  if (hadamard_quant2x2_skip(dcin, (int16_t)(ff[0] << 1), (int16_t)(mf[0] >> 1))) return false;
-  int ctr = 0;
-  for (int j = 0; j < 4; j++) {
+  const bool dc_fail = hadamard_quant2x2_skip(dcin, (int16_t)(ff[0] << 1), (int16_t)(mf[0] >> 1)) != 0;
+  int big = 0, ctr = 0;
+  for (int j = lane_id(); j < 4; j += MBK_WS) {
     int16_t d[16], l[16];
     for (int i = 0; i < 16; i++) d[i] = res[16 * j + i];
+    // WelsTryPUVskip quantises the block WITH its DC still in place (the 2x2 test above does not zero it)
     const uint16_t mx = (uint16_t)quant4x4_max(d, ff, mf);
-    if (mx > 1) return false;
-    if (mx == 1) { scan4x4_ac(l, d); ctr += single_ctr4x4(l); }
-    if (ctr >= 7) return false;
+    if (mx > 1) big = 1;
+    else if (mx == 1) { scan4x4_ac(l, d); ctr += single_ctr4x4(l); }
   }
-  return true;
+  big = warp_sum(big); ctr = warp_sum(ctr);
+  return !dc_fail && big == 0 && ctr < 7;
 }
-MBK_HD void dct_luma_mb(MbScratch& s, const uint8_t* pred /*stride 16*/) {
+MBK_FN void dct_luma_mb(MbScratch& s, const uint8_t* pred /*stride 16*/) {
   for (int k = lane_id(); k < 16; k += MBK_WS) {
     int16_t d[16];
     const int o = blk_y(k) * 4 * 16 + blk_x(k) * 4;
@@ -214,7 +213,7 @@ MBK_HD void dct_luma_mb(MbScratch& s, const uint8_t* pred /*stride 16*/) {
   warp_sync();
 }
 
-MBK_HD SkipResult pskip_enc(const MbCtx& c, MbScratch& s, int sad_pred_skip, int ref_mb_type) {
+MBK_FN SkipResult pskip_enc(const MbCtx& c, MbScratch& s, int sad_pred_skip, int ref_mb_type) {
   SkipResult r;
   r.ok = false; r.cost_luma = 0; r.cost_skip = 0;
   int mvx, mvy;
@@ -226,8 +225,10 @@ MBK_HD SkipResult pskip_enc(const MbCtx& c, MbScratch& s, int sad_pred_skip, int
   n = c.mby * 16 + iy;
   if (n < -29 || n > c.p.mb_h * 16 + 12) return r;
   uint8_t* py = s.skip_pred;
+  phase_mark(s, 12);
   warp_mc_luma(ref_luma(c, ix, iy), c.p.rec_stride_y, py, 16, mvx, mvy, 16, 16);
   warp_sync();
+  phase_mark(s, 13);
   const int sad_y = warp_sad(s.cur_y, 16, py, 16, 4, 4);
   // NB the reference derives the chroma offset from the INTEGER luma vector: (ix >> 1, iy >> 1)
   for (int pl = 0; pl < 2; pl++)
@@ -235,6 +236,7 @@ MBK_HD SkipResult pskip_enc(const MbCtx& c, MbScratch& s, int sad_pred_skip, int
   warp_sync();
   const int sad_c = warp_sad(s.cur_c, 8, s.skip_pred + 256, 8, 3, 3) + warp_sad(s.cur_c + 64, 8, s.skip_pred + 320, 8, 3, 3);
   const int sad_mb = sad_y + sad_c;
+  phase_mark(s, 14);
   bool ok = sad_mb == 0 || sad_mb < sad_pred_skip ||
             (c.p.ref_is_p && ref_mb_type == MBT_PSKIP && sad_mb < c.f.ref_info[c.mby * c.p.mb_w + c.mbx].skip_sad);
   if (!ok) {
@@ -259,16 +261,18 @@ MBK_HD SkipResult pskip_enc(const MbCtx& c, MbScratch& s, int sad_pred_skip, int
       }
     }
   }
+  phase_mark(s, 15);
   if (ok) {
     r.ok = true;
     r.cost_luma = warp_satd(s.cur_y, 16, py, 16, 4, 4);
+    phase_mark(s, 16);
     r.cost_skip = sad_mb;
   }
   return r;
 }
 
 // ---- integer search of one partition ------------------------------------------------------------------------
-MBK_HD void me_partition(const MbCtx& c, MbScratch& s, int blk_size, int ox, int oy, int mvp_x, int mvp_y, uint32_t sad_pred,
+MBK_FN void me_partition(const MbCtx& c, MbScratch& s, int blk_size, int ox, int oy, int mvp_x, int mvp_y, uint32_t sad_pred,
                          int n_mvc, const int16_t* mvc, MeState* st) {
   MeIn in;
   in.enc = s.cur_y + oy * 16 + ox; in.enc_stride = 16;
@@ -296,7 +300,7 @@ MBK_HD void me_partition(const MbCtx& c, MbScratch& s, int blk_size, int ox, int
 // ---- fractional refinement (MeRefineFracPixel, md.cpp:575) ------------------------------------------------------
 // candidate cost = SATD(enc, McLuma(ref, mv)) + mvd cost, visited in the reference's order with strict '<';
 // the winning prediction is left in dst (stride 16).
-MBK_HD void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy, int w, int h, uint8_t* dst) {
+MBK_FN void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy, int w, int h, uint8_t* dst) {
   const int lw = w == 16 ? 4 : 3, lh = h == 16 ? 4 : 3;
   const uint8_t* enc = s.cur_y + oy * 16 + ox;
   const int rs = c.p.rec_stride_y;
@@ -343,7 +347,7 @@ MBK_HD void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy,
 }
 
 // ---- luma residual of an inter MB (WelsEncInterY, svc_encode_mb.cpp:180) -------------------------------------------
-MBK_HD void enc_inter_y(const MbCtx& c, MbScratch& s) {
+MBK_FN void enc_inter_y(const MbCtx& c, MbScratch& s) {
   const int16_t* ff = tbl_quant_ff(c.qp);
   const int16_t* mf = tbl_quant_mf(c.qp);
   // per-block quantisation / scan in parallel; the JVT-O079 accumulation is order dependent -> serial scalar part
@@ -392,7 +396,7 @@ MBK_HD void enc_inter_y(const MbCtx& c, MbScratch& s) {
 }
 
 // luma reconstruction of an inter MB: pred + IDCT(coef) for all 16 blocks (OutputPMbWithoutConstructCsRsNoCopy)
-MBK_HD void rec_luma_inter(MbScratch& s, const uint8_t* pred) {
+MBK_FN void rec_luma_inter(MbScratch& s, const uint8_t* pred) {
   for (int k = lane_id(); k < 16; k += MBK_WS) {
     int16_t d[16];
     for (int i = 0; i < 16; i++) d[i] = s.coef[16 * k + i];
@@ -403,7 +407,7 @@ MBK_HD void rec_luma_inter(MbScratch& s, const uint8_t* pred) {
 }
 
 // ---- decided skip (WelsMdInterDecidedPskip :1954 + WelsRecPskip svc_encode_mb.cpp:315) ------------------------------
-MBK_HD void decided_pskip(const MbCtx& c, MbScratch& s) {
+MBK_FN void decided_pskip(const MbCtx& c, MbScratch& s) {
   for (int i = lane_id(); i < 256; i += MBK_WS) *tile_y(s.tile, i & 15, i >> 4) = s.skip_pred[i];
   for (int i = lane_id(); i < 64; i += MBK_WS) {
     *tile_c(s.tile.u, i & 7, i >> 3) = s.skip_pred[256 + i];
@@ -418,9 +422,10 @@ MBK_HD void decided_pskip(const MbCtx& c, MbScratch& s) {
 }
 
 // ---- the P-slice macroblock (WelsMdInterMb :1858 + WelsMdInterSecondaryModesEnc :1997) --------------------------------
-MBK_HD void inter_mb_md_enc(const MbCtx& c, MbScratch& s) {
+MBK_FN void inter_mb_md_enc(const MbCtx& c, MbScratch& s) {
   const int mbw = c.p.mb_w, idx = c.mby * mbw + c.mbx;
   fill_inter_cache(c, s);
+  phase_mark(s, 1);
   const int ref_mb_type = c.p.ref_is_p ? c.f.ref_info[idx].mb_type : 0xff;
   int p16_mvx = 0, p16_mvy = 0;                       // sP16x16Mv / sMvList (WelsMdInterInit :352-353)
   const bool sk_l = (c.nb & NB_LEFT) && s.nbi[3].mb_type == MBT_PSKIP;
@@ -441,6 +446,7 @@ MBK_HD void inter_mb_md_enc(const MbCtx& c, MbScratch& s) {
       mb_mv_set(s, 0, 4, 4, r.mvx, r.mvy);
     }
   }
+  phase_mark(s, 2);
   MeState me16, me16x8[2], me8x16[2], me8x8[4];
   int final_type = MBT_P16x16;
   bool done = false;
@@ -468,10 +474,12 @@ MBK_HD void inter_mb_md_enc(const MbCtx& c, MbScratch& s) {
     p16_mvx = me16.mv_x; p16_mvy = me16.mv_y;
     cost_luma = (int)me16.satd_cost;
   }
+  phase_mark(s, 3);
   if (!done) {
     // intra check (WelsMdFirstIntraMode :1829)
     int bb;
     const int cost16 = md_i16x16(c, s, &bb);
+    phase_mark(s, 4);
     if (cost16 < cost_luma) {
       int cost = cost16;
       s.info.mb_type = MBT_I16x16;
@@ -489,6 +497,7 @@ MBK_HD void inter_mb_md_enc(const MbCtx& c, MbScratch& s) {
       if (lane_id() == 0) { c.f.sad_cost[idx] = 0; s.info.ref_idx = REF_NOT_IN_LIST; }
       final_type = s.info.mb_type;
       done = true;
+      phase_mark(s, 5);
     }
   }
   if (!done && is_skip) {
@@ -529,6 +538,7 @@ MBK_HD void inter_mb_md_enc(const MbCtx& c, MbScratch& s) {
       }
       if (cst <= cost) { cost = cst; final_type = MBT_P8x16; }
     }
+    phase_mark(s, 6);
     // refinement (WelsMdInterMbRefinement :1573)
     uint8_t* pl = s.pred_y[0];
     uint8_t* pc = s.pred_c[0];
@@ -576,6 +586,7 @@ MBK_HD void inter_mb_md_enc(const MbCtx& c, MbScratch& s) {
       }
     }
     if (lane_id() == 0) c.f.sad_cost[idx] = best_sad;          // pCurMb->pSadCost[0]
+    phase_mark(s, 7);
     // step 7: residual coding (WelsMdInterEncode :1964)
     if (lane_id() == 0) s.info.cbp = 0;
     warp_sync();
@@ -596,6 +607,7 @@ MBK_HD void inter_mb_md_enc(const MbCtx& c, MbScratch& s) {
     if (lane_id() == 0) s.info.mb_type = (uint8_t)final_type;
     warp_sync();
   }
+  phase_mark(s, 8);
   // bookkeeping for the neighbours and the next frame
   if (lane_id() == 0) {
     s.info.mb_type = (uint8_t)final_type;

@@ -58,7 +58,7 @@ MBK_HD PlaneCoef plane_coef(const uint8_t* org, int pitch, int n /*16 or 8*/) {
 }
 
 // fills a 16x16 luma prediction (dst stride 16) for mode m from the tile neighbours
-MBK_HD void pred_i16(uint8_t* dst, const uint8_t* org, int pitch, int m) {
+MBK_FN void pred_i16(uint8_t* dst, const uint8_t* org, int pitch, int m) {
   int dc = 128;
   PlaneCoef pc = {0, 0, 0};
   if (m == I16_DC || m == I16_DC_L || m == I16_DC_T) {
@@ -81,7 +81,7 @@ MBK_HD void pred_i16(uint8_t* dst, const uint8_t* org, int pitch, int m) {
 }
 
 // fills an 8x8 chroma prediction (dst stride 8) for mode m
-MBK_HD void pred_chroma(uint8_t* dst, const uint8_t* org, int pitch, int m) {
+MBK_FN void pred_chroma(uint8_t* dst, const uint8_t* org, int pitch, int m) {
   int dcq[4] = {128, 128, 128, 128};   // per 4x4 quadrant: TL, TR, BL, BR
   PlaneCoef pc = {0, 0, 0};
   if (m == C_DC || m == C_DC_L || m == C_DC_T) {
@@ -111,7 +111,7 @@ MBK_HD void pred_chroma(uint8_t* dst, const uint8_t* org, int pitch, int m) {
 }
 
 // ---- 4x4 predictors: all 16 samples by one thread ----------------------------------------------
-MBK_HD void pred_i4(uint8_t p[16], const uint8_t* org, int pitch, int m) {
+MBK_FN void pred_i4(uint8_t p[16], const uint8_t* org, int pitch, int m) {
   // e[4] = top-left, e[5..12] = top (incl. top-right), e[3..0] = left 0..3
   int t[8], l[4], lt = 0;
   const bool need_top = !(m == I4_H || m == I4_HU || m == I4_DC_L || m == I4_DC_128);
@@ -183,7 +183,7 @@ MBK_HD void pred_i4(uint8_t p[16], const uint8_t* org, int pitch, int m) {
 }
 
 // SATD of a 4x4 block: cur (pixels, stride cs) against a prediction held in registers
-MBK_HD int satd4x4_pred(const uint8_t p[16], const uint8_t* cur, int cs) {
+MBK_FN int satd4x4_pred(const uint8_t p[16], const uint8_t* cur, int cs) {
   int t[4][4];
 #pragma unroll
   for (int y = 0; y < 4; y++) {

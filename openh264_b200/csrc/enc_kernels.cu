@@ -23,7 +23,9 @@ __constant__ uint8_t c_beta[52];
 __constant__ uint8_t c_tc0[52][3];
 }  // namespace mbk
 
-#define ENC_WPC 4          // warps per CTA in the row kernels
+#ifndef ENC_WPC
+#define ENC_WPC 16         // warps per CTA of the macroblock kernels (one CTA per SM at 128 registers)
+#endif
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
@@ -106,6 +108,51 @@ __device__ __forceinline__ void run_mbs(const StreamFrame* sf, int n_streams, co
   }
 }
 
+// CTA-synchronous variant: the CTA takes up to ENC_WPC macroblocks that are ALREADY ready, its warps start
+// them together and meet again before the next batch.  Warps that start together run the same code at the
+// same time, so one instruction-cache fill serves all of them.
+template <class Body>
+__device__ __forceinline__ void run_mbs_cta(const StreamFrame* sf, int n_streams, const Sched q, Body body) {
+  __shared__ int s_base, s_n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int mb_w = sf[0].p.mb_w, mb_h = sf[0].p.mb_h, n_mb = mb_w * mb_h, total = n_streams * n_mb;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      int h, n;
+      for (;;) {
+        h = ld_volatile(q.head);
+        if (h >= total) { n = -1; break; }
+        const int t = ld_volatile(q.tail);
+        n = min(ENC_WPC, t - h);
+        if (n > 0 && atomicCAS(q.head, h, h + n) == h) break;
+        __nanosleep(200);
+      }
+      s_base = h; s_n = n;
+    }
+    __syncthreads();
+    const int base = s_base, n = s_n;
+    if (n < 0) break;
+    if (warp < n) {
+      int id = 0;
+      if (lane == 0) while ((id = ld_volatile(q.queue + base + warp)) < 0) {}
+      id = __shfl_sync(MBK_FULL, id, 0);
+      __threadfence();
+      const int si = id / n_mb, mb = id - si * n_mb, y = mb / mb_w, x = mb - y * mb_w;
+      body(sf[si], x, y);
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        if (x + 1 < mb_w) sched_notify(q, id + 1, 1 + (y > 0));
+        if (y + 1 < mb_h) {
+          if (x > 0) sched_notify(q, id + mb_w - 1, 1 + (x - 1 > 0));
+          if (x == mb_w - 1) sched_notify(q, id + mb_w, 1 + (x > 0));
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void k_sched_init(Sched q, int n_streams, int n_mb) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_streams) q.queue[i] = i * n_mb;        // MB (0,0) of every stream is ready
@@ -114,11 +161,24 @@ __global__ void k_sched_init(Sched q, int n_streams, int n_mb) {
 
 // optional per-MB-type cycle statistics (debug): [type*2] = cycles, [type*2+1] = count
 __device__ unsigned long long g_enc_stats[16];
+#ifdef B2H264_PHASE_STATS
+namespace mbk { __device__ unsigned long long g_phase[32]; }
+extern "C" int b2h264_debug_phase_stats(unsigned long long* out32, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out32, mbk::g_phase, sizeof(mbk::g_phase));
+  if (e == cudaSuccess && reset) { unsigned long long z[32] = {0}; e = cudaMemcpyToSymbol(mbk::g_phase, z, sizeof(z)); }
+  return (int)e;
+}
+#endif
 
 __global__ void __launch_bounds__(32 * ENC_WPC) k_encode_mbs(const StreamFrame* __restrict__ sf, int n_streams, Sched q, int stats) {
   extern __shared__ __align__(16) uint8_t smem[];
   MbScratch& s = reinterpret_cast<MbScratch*>(smem)[threadIdx.x >> 5];
-  run_mbs(sf, n_streams, q, [&](const StreamFrame& F, int x, int y) {
+#ifdef B2H264_WARP_ASYNC
+  run_mbs(sf,
+#else
+  run_mbs_cta(sf,
+#endif
+ n_streams, q, [&](const StreamFrame& F, int x, int y) {
     const long long t0 = stats ? clock64() : 0;
     encode_one_mb(F.p, F.f, s, x, y);
     if (stats && (threadIdx.x & 31) == 0) {

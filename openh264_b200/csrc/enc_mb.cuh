@@ -29,7 +29,18 @@ struct MbScratch {
   int32_t nb_sad[4];            // neighbours' persistent SAD cost (pSadCost[0])
   int32_t nb_skip_sad[4];       // neighbours' skip SAD of THIS picture (pMbSkipSad)
   int32_t red[32];              // small scratch
+  uint32_t t_last;              // phase timer (profiling builds only)
 };
+
+// phase timing, compiled in only with -DB2H264_PHASE_STATS (profiling build): cycles since the previous mark
+#if defined(B2H264_PHASE_STATS) && defined(__CUDA_ARCH__)
+extern __device__ unsigned long long g_phase[32];
+__device__ __forceinline__ void phase_mark(MbScratch& s, int i) {
+  if ((threadIdx.x & 31) == 0) { const uint32_t t = (uint32_t)clock(); atomicAdd(&g_phase[i], (unsigned long long)(uint32_t)(t - s.t_last)); s.t_last = t; }
+}
+#else
+MBK_HD void phase_mark(MbScratch&, int) {}
+#endif
 
 struct MbCtx {
   EncFrameParams p;
@@ -127,8 +138,87 @@ MBK_HD void mb_load_borders(const MbCtx& c, MbScratch& s) {
   warp_sync();
 }
 
+// Fused form of mb_load_neighbors + mb_load_cur + mb_load_borders: every lane first ISSUES all of its loads
+// (11 independent global loads in flight: neighbour records, SAD history, current MB, border samples) and only
+// then stores to the scratch, so the macroblock pays one memory latency here instead of five serialized ones
+// (profiles/r01_phase_cycles.txt: 12k cycles/MB before).
+MBK_FN void mb_load_all(const MbCtx& c, MbScratch& s) {
+  const int mbw = c.p.mb_w, idx = c.mby * mbw + c.mbx, l = lane_id();
+  const int offs[4] = {-mbw - 1, -mbw, -mbw + 1, -1};
+  const int bits[4] = {NB_TOPLEFT, NB_TOP, NB_TOPRIGHT, NB_LEFT};
+  constexpr int kW = (int)(sizeof(MbInfo) / 4);
+#ifdef __CUDA_ARCH__
+  // ---- issue ----
+  uint32_t nbw[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int i = l + 32 * r, k = i / kW, w = i - k * kW;
+    nbw[r] = (i < 4 * kW && (c.nb & bits[k & 3])) ? ld_cg_u32(reinterpret_cast<const uint32_t*>(c.f.mbi + idx + offs[k & 3]) + w) : 0u;
+  }
+  uint32_t hist = 0;
+  if (l < 8 && (c.nb & bits[l & 3]))
+    hist = l < 4 ? ld_cg_u32(reinterpret_cast<const uint32_t*>(c.f.sad_cost + idx + offs[l & 3]))
+                 : ld_cg_u32(reinterpret_cast<const uint32_t*>(&c.f.rec_info[idx + offs[l & 3]].skip_sad));
+  const uint8_t* cy = c.f.cur[0] + (size_t)(c.mby * 16) * c.p.cur_stride_y + c.mbx * 16;
+  const uint32_t cy0 = *reinterpret_cast<const uint32_t*>(cy + (size_t)(l >> 2) * c.p.cur_stride_y + ((l & 3) << 2));
+  const uint32_t cy1 = *reinterpret_cast<const uint32_t*>(cy + (size_t)(8 + (l >> 2)) * c.p.cur_stride_y + ((l & 3) << 2));
+  const uint32_t cc = *reinterpret_cast<const uint32_t*>(c.f.cur[1 + (l >> 4)] + (size_t)(c.mby * 8 + ((l >> 1) & 7)) * c.p.cur_stride_c +
+                                                          c.mbx * 8 + ((l & 1) << 2));
+  const uint8_t* ry = c.f.rec[0] + (ptrdiff_t)(c.mby * 16 - 1) * c.p.rec_stride_y + c.mbx * 16;
+  const uint8_t* ru = c.f.rec[1] + (ptrdiff_t)(c.mby * 8 - 1) * c.p.rec_stride_c + c.mbx * 8;
+  const uint8_t* rv = c.f.rec[2] + (ptrdiff_t)(c.mby * 8 - 1) * c.p.rec_stride_c + c.mbx * 8;
+  uint8_t tb[2] = {0, 0};
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    const int i = l + 32 * r;
+    if (i < 25) {
+      const int x = i - 1;
+      if (x < 0 ? (c.nb & NB_TOPLEFT) : x < 16 ? (c.nb & NB_TOP) : (c.nb & NB_TOPRIGHT)) tb[r] = ld_cg_u8(ry + x);
+    } else if (i < 34) {
+      const int x = i - 26;
+      if (x < 0 ? (c.nb & NB_TOPLEFT) : (c.nb & NB_TOP)) tb[r] = ld_cg_u8(ru + x);
+    } else if (i < 43) {
+      const int x = i - 35;
+      if (x < 0 ? (c.nb & NB_TOPLEFT) : (c.nb & NB_TOP)) tb[r] = ld_cg_u8(rv + x);
+    }
+  }
+  uint8_t lb = 0;
+  if (c.nb & NB_LEFT)
+    lb = l < 16 ? ld_cg_u8(ry + (ptrdiff_t)(l + 1) * c.p.rec_stride_y - 1)
+                : l < 24 ? ld_cg_u8(ru + (ptrdiff_t)(l - 15) * c.p.rec_stride_c - 1) : ld_cg_u8(rv + (ptrdiff_t)(l - 23) * c.p.rec_stride_c - 1);
+  // ---- commit ----
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int i = l + 32 * r;
+    if (i < 4 * kW) reinterpret_cast<uint32_t*>(&s.nbi[0])[i] = nbw[r];
+  }
+  if (l < 4) s.nb_sad[l] = (int32_t)hist;
+  else if (l < 8) s.nb_skip_sad[l - 4] = (int32_t)hist;
+  *reinterpret_cast<uint32_t*>(s.cur_y + (l >> 2) * 16 + ((l & 3) << 2)) = cy0;
+  *reinterpret_cast<uint32_t*>(s.cur_y + (8 + (l >> 2)) * 16 + ((l & 3) << 2)) = cy1;
+  *reinterpret_cast<uint32_t*>(s.cur_c + (l >> 4) * 64 + ((l >> 1) & 7) * 8 + ((l & 1) << 2)) = cc;
+  RecTile& t = s.tile;
+#pragma unroll
+  for (int r = 0; r < 2; r++) {
+    const int i = l + 32 * r;
+    if (i < 25) *tile_y(t, i - 1, -1) = tb[r];
+    else if (i < 34) *tile_c(t.u, i - 26, -1) = tb[r];
+    else if (i < 43) *tile_c(t.v, i - 35, -1) = tb[r];
+  }
+  if (l < 16) *tile_y(t, -1, l) = lb;
+  else if (l < 24) *tile_c(t.u, -1, l - 16) = lb;
+  else *tile_c(t.v, -1, l - 24) = lb;
+  warp_sync();
+#else
+  (void)offs; (void)bits; (void)idx; (void)l;
+  mb_load_neighbors(c, s);
+  mb_load_cur(c, s);
+  mb_load_borders(c, s);
+#endif
+}
+
 // reconstructed tile -> picture
-MBK_HD void mb_store_recon(const MbCtx& c, MbScratch& s) {
+MBK_FN void mb_store_recon(const MbCtx& c, MbScratch& s) {
   uint8_t* ry = c.f.rec[0] + (size_t)(c.mby * 16) * c.p.rec_stride_y + c.mbx * 16;
   for (int i = lane_id(); i < 64; i += MBK_WS) {
     const int r = i >> 2, c4 = (i & 3) << 2;
@@ -147,7 +237,7 @@ MBK_HD void mb_store_recon(const MbCtx& c, MbScratch& s) {
 
 // ---- I16x16 mode decision (WelsMdI16x16, svc_base_layer_md.cpp:365; pfMdCost = SATD) -------------
 // returns the cost; s.out.i16_mode = raw mode id; the winning prediction is in s.pred_y[*best_buf]
-MBK_HD int md_i16x16(const MbCtx& c, MbScratch& s, int* best_buf) {
+MBK_FN int md_i16x16(const MbCtx& c, MbScratch& s, int* best_buf) {
   int modes[4];
   const int n = i16_modes(c.nb & 7, modes);
   int best = 0x7fffffff, best_mode = modes[0], bb = 1;
@@ -165,7 +255,7 @@ MBK_HD int md_i16x16(const MbCtx& c, MbScratch& s, int* best_buf) {
 }
 
 // ---- intra chroma mode decision (WelsMdIntraChroma, :867) ---------------------------------------
-MBK_HD int md_chroma(const MbCtx& c, MbScratch& s, int* best_buf) {
+MBK_FN int md_chroma(const MbCtx& c, MbScratch& s, int* best_buf) {
   int modes[4];
   const int n = chroma_modes(c.nb & 7, modes);
   int best = 0x7fffffff, best_mode = modes[0], bb = 1;
@@ -184,7 +274,7 @@ MBK_HD int md_chroma(const MbCtx& c, MbScratch& s, int* best_buf) {
 }
 
 // ---- I16x16 residual coding + reconstruction (WelsEncRecI16x16Y, svc_encode_mb.cpp:54) ----------
-MBK_HD void enc_rec_i16x16(const MbCtx& c, MbScratch& s, const uint8_t* pred) {
+MBK_FN void enc_rec_i16x16(const MbCtx& c, MbScratch& s, const uint8_t* pred) {
   const int qp = c.qp;
   const int16_t* ff = tbl_quant_ff(qp + 6);
   const int16_t* mf = tbl_quant_mf(qp);
@@ -251,7 +341,7 @@ MBK_HD void enc_rec_i16x16(const MbCtx& c, MbScratch& s, const uint8_t* pred) {
 // ---- I4x4 mode decision with in-loop coding (WelsMdI4x4 :418 + WelsEncRecI4x4Y svc_encode_mb.cpp:139)
 // returns the I4x4 cost; reconstructs into the tile as it goes; stops early once the running cost
 // reaches `cost_limit` (the I16x16 / inter cost), exactly like the reference.
-MBK_HD int md_enc_i4x4(const MbCtx& c, MbScratch& s, int cost_limit) {
+MBK_FN int md_enc_i4x4(const MbCtx& c, MbScratch& s, int cost_limit) {
   const int qp = c.qp;
   const int16_t* ff = tbl_quant_ff(qp + 6);
   const int16_t* mf = tbl_quant_mf(qp);
@@ -309,58 +399,65 @@ MBK_HD int md_enc_i4x4(const MbCtx& c, MbScratch& s, int cost_limit) {
 }
 
 // ---- chroma residual of one plane (WelsEncRecUV, svc_encode_mb.cpp:244); res = s.coef + 256 + 64*uv
-MBK_HD void enc_rec_uv(const MbCtx& c, MbScratch& s, int uv, bool inter) {
+MBK_FN void enc_rec_uv(const MbCtx& c, MbScratch& s, int uv, bool inter) {
   int16_t* res = s.coef + 256 + 64 * uv;
   const int qpc = c.qp_c;
   const int16_t* ff = tbl_quant_ff(qpc + (inter ? 0 : 6));
   const int16_t* mf = tbl_quant_mf(qpc);
-  // the whole plane is 4 blocks: done by lane 0 (cheap), mirrors the serial reference exactly
-  if (lane_id() == 0) {
-    int16_t dcin[4] = {res[0], res[16], res[32], res[48]}, dc[4];
-    const int nz_dc = hadamard_quant2x2(dcin, (int16_t)(ff[0] << 1), (int16_t)(mf[0] >> 1), dc);
-    res[0] = res[16] = res[32] = res[48] = 0;
-    for (int i = 0; i < 4; i++) s.out.chroma_dc[uv][i] = dc[i];
-    int ctr = 0;
-    for (int j = 0; j < 4; j++) {
-      int16_t d[16], l[16];
+  // chroma DC 2x2 (all lanes compute the same 4 values)
+  const int16_t dcin[4] = {res[0], res[16], res[32], res[48]};
+  int16_t dc[4];
+  const int nz_dc = hadamard_quant2x2(dcin, (int16_t)(ff[0] << 1), (int16_t)(mf[0] >> 1), dc);
+  warp_sync();
+  // AC of the 4 blocks: one lane each (the DC position is quantised as 0, as after pfQuantizationHadamard2x2)
+  for (int j = lane_id(); j < 4; j += MBK_WS) {
+    int16_t d[16], l[16];
+    for (int i = 0; i < 16; i++) d[i] = res[16 * j + i];
+    d[0] = 0;
+    const int16_t mx = quant4x4_max(d, ff, mf);
+    if (mx == 0) { for (int i = 0; i < 16; i++) l[i] = 0; }
+    else scan4x4_ac(l, d);
+    for (int i = 0; i < 16; i++) { res[16 * j + i] = d[i]; s.out.chroma_ac[4 * uv + j][i] = l[i]; }
+    s.red[j] = mx;
+    s.red[4 + j] = mx == 0 ? 0 : single_ctr4x4(l);
+    s.red[8 + j] = nonzero_count(l);
+  }
+  if (lane_id() == 0) for (int i = 0; i < 4; i++) s.out.chroma_dc[uv][i] = dc[i];
+  warp_sync();
+  // JVT-O079 decision in the reference's block order (uniform)
+  int ctr = 0;
+  for (int j = 0; j < 4; j++) {
+    const int mx = s.red[j];
+    if (mx == 0) continue;
+    if (inter) {
+      if (mx > 1) ctr += 9;
+      else if (ctr < 7) ctr += s.red[4 + j];
+    } else ctr = 0x7fffffff;
+  }
+  if (ctr < 7) {
+    for (int i = lane_id(); i < 64; i += MBK_WS) res[i] = 0;
+    if (lane_id() == 0) for (int j = 0; j < 4; j++) s.info.nnz[16 + 4 * uv + j] = 0;
+  } else {
+    for (int j = lane_id(); j < 4; j += MBK_WS) {
+      s.info.nnz[16 + 4 * uv + j] = (int8_t)s.red[8 + j];
+      int16_t d[16];
       for (int i = 0; i < 16; i++) d[i] = res[16 * j + i];
-      const int16_t mx = quant4x4_max(d, ff, mf);
+      dequant4x4(d, tbl_dequant(qpc));
       for (int i = 0; i < 16; i++) res[16 * j + i] = d[i];
-      if (mx == 0) {
-        for (int i = 0; i < 16; i++) s.out.chroma_ac[4 * uv + j][i] = 0;
-      } else {
-        scan4x4_ac(l, d);
-        for (int i = 0; i < 16; i++) s.out.chroma_ac[4 * uv + j][i] = l[i];
-        if (inter) {
-          if (mx > 1) ctr += 9;
-          else if (ctr < 7) ctr += single_ctr4x4(l);
-        } else ctr = 0x7fffffff;
-      }
     }
-    if (ctr < 7) {
-      for (int i = 0; i < 64; i++) res[i] = 0;
-      for (int j = 0; j < 4; j++) s.info.nnz[16 + 4 * uv + j] = 0;
-    } else {
-      for (int j = 0; j < 4; j++) {
-        s.info.nnz[16 + 4 * uv + j] = (int8_t)nonzero_count(s.out.chroma_ac[4 * uv + j]);
-        int16_t d[16];
-        for (int i = 0; i < 16; i++) d[i] = res[16 * j + i];
-        dequant4x4(d, tbl_dequant(qpc));
-        for (int i = 0; i < 16; i++) res[16 * j + i] = d[i];
-      }
-      s.info.cbp = (uint8_t)((s.info.cbp & 0x0F) | 0x20);
-    }
-    if (nz_dc > 0) {
-      dequant_ihadamard2x2_dc(dc, tbl_dequant(qpc)[0]);
-      if (2 != (s.info.cbp >> 4)) s.info.cbp |= 0x10;
-      res[0] = dc[0]; res[16] = dc[1]; res[32] = dc[2]; res[48] = dc[3];
-    }
+    if (lane_id() == 0) s.info.cbp = (uint8_t)((s.info.cbp & 0x0F) | 0x20);
+  }
+  warp_sync();
+  if (nz_dc > 0 && lane_id() == 0) {
+    dequant_ihadamard2x2_dc(dc, tbl_dequant(qpc)[0]);
+    if (2 != (s.info.cbp >> 4)) s.info.cbp |= 0x10;
+    res[0] = dc[0]; res[16] = dc[1]; res[32] = dc[2]; res[48] = dc[3];
   }
   warp_sync();
 }
 
 // chroma transform of both planes against prediction `pred` (Cb 0..63, Cr 64..127)
-MBK_HD void dct_chroma(MbScratch& s, const uint8_t* pred) {
+MBK_FN void dct_chroma(MbScratch& s, const uint8_t* pred) {
   for (int t = lane_id(); t < 8; t += MBK_WS) {
     const int uv = t >> 2, j = t & 3, ox = (j & 1) * 4, oy = (j >> 1) * 4;
     int16_t d[16];
@@ -370,7 +467,7 @@ MBK_HD void dct_chroma(MbScratch& s, const uint8_t* pred) {
   warp_sync();
 }
 // chroma reconstruction of both planes into the tile: pred + IDCT(coef)
-MBK_HD void rec_chroma(MbScratch& s, const uint8_t* pred) {
+MBK_FN void rec_chroma(MbScratch& s, const uint8_t* pred) {
   for (int t = lane_id(); t < 8; t += MBK_WS) {
     const int uv = t >> 2, j = t & 3, ox = (j & 1) * 4, oy = (j >> 1) * 4;
     int16_t d[16];
@@ -381,7 +478,7 @@ MBK_HD void rec_chroma(MbScratch& s, const uint8_t* pred) {
 }
 
 // ---- intra4x4 mode cache from the neighbours (FillNeighborCacheIntra, md.cpp:51) -----------------
-MBK_HD void fill_i4_cache(const MbCtx& c, MbScratch& s) {
+MBK_FN void fill_i4_cache(const MbCtx& c, MbScratch& s) {
   if (lane_id() == 0) {
     for (int i = 0; i < 25; i++) s.i4m[i] = -1;
     if (c.nb & NB_LEFT) {
@@ -398,7 +495,7 @@ MBK_HD void fill_i4_cache(const MbCtx& c, MbScratch& s) {
 
 // ---- a macroblock of an I slice (WelsMdIntraMb :956 + WelsMdIntraSecondaryModesEnc :2023) ---------
 // returns the luma cost (iCostLuma)
-MBK_HD int intra_mb_md_enc(const MbCtx& c, MbScratch& s, int cost_limit_for_i16 /*INT_MAX in I slices*/) {
+MBK_FN int intra_mb_md_enc(const MbCtx& c, MbScratch& s, int cost_limit_for_i16 /*INT_MAX in I slices*/) {
   (void)cost_limit_for_i16;
   int bb;
   int cost = md_i16x16(c, s, &bb);
@@ -421,7 +518,7 @@ MBK_HD int intra_mb_md_enc(const MbCtx& c, MbScratch& s, int cost_limit_for_i16 
 }
 
 // publishes MbInfo / RefMbInfo / MbOut of a finished macroblock
-MBK_HD void mb_publish(const MbCtx& c, MbScratch& s) {
+MBK_FN void mb_publish(const MbCtx& c, MbScratch& s) {
   const int idx = c.mby * c.p.mb_w + c.mbx;
   if (lane_id() == 0) {
     s.info.qp = (uint8_t)c.qp; s.info.qp_c = (uint8_t)c.qp_c;
@@ -435,7 +532,8 @@ MBK_HD void mb_publish(const MbCtx& c, MbScratch& s) {
   for (int i = lane_id(); i < (int)(sizeof(MbInfo) / 4); i += MBK_WS) di[i] = si[i];
   const uint32_t* so = reinterpret_cast<const uint32_t*>(&s.out);
   uint32_t* dout = reinterpret_cast<uint32_t*>(c.f.out + idx);
-  for (int i = lane_id(); i < (int)(sizeof(MbOut) / 4); i += MBK_WS) dout[i] = so[i];
+  const int n_out = s.info.mb_type == MBT_PSKIP ? MBOUT_HEADER_WORDS : (int)(sizeof(MbOut) / 4);
+  for (int i = lane_id(); i < n_out; i += MBK_WS) dout[i] = so[i];
   warp_sync();
 }
 

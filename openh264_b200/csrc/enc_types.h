@@ -51,6 +51,7 @@ typedef struct {
   int16_t chroma_dc[2][4];
   int16_t chroma_ac[8][16];               // Cb 0..3, Cr 4..7
 } MbOut;                                  // 8+32+16+24+32+512+16+256 = 896 bytes
+#define MBOUT_HEADER_WORDS 20             /* mb_type .. nnz: all a P_SKIP macroblock needs to hand over */
 
 typedef struct {
   int32_t mb_w, mb_h;

@@ -15,6 +15,10 @@
 // debugging build that is NOT part of the product library) the same source runs as a "1-lane warp":
 // MBK_WS == 1, so every lane-strided loop visits all indices and warp reductions are the identity.
 #define MBK_HD __host__ __device__ __forceinline__
+// Warp-level routines are real functions, not inlined: one inlined copy per call site grew the encode
+// kernel to 774 KB of SASS and the warps (each in a different phase of a different macroblock) spent
+// 58% of their cycles waiting for instruction fetch (profiles/r01_encode_icache.txt).
+#define MBK_FN static __host__ __device__ __noinline__
 #ifdef __CUDA_ARCH__
 #define MBK_WS 32
 #else

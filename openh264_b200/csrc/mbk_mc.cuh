@@ -37,17 +37,29 @@ MBK_HD int luma_qpel_sample(const uint8_t* p, int s, int fx, int fy) {
 }
 
 // w x h luma prediction; src already offset by the integer part of the MV (as McLuma_c expects)
-MBK_HD void warp_mc_luma(const uint8_t* src, int ss, uint8_t* dst, int ds, int mvx, int mvy, int w,
+MBK_FN void warp_mc_luma(const uint8_t* src, int ss, uint8_t* dst, int ds, int mvx, int mvy, int w,
                                              int h) {
   const int fx = mvx & 3, fy = mvy & 3;
+  const int sh = 31 - clz32((uint32_t)w);
+  const bool p2 = (w & (w - 1)) == 0;
+  if ((fx | fy) == 0 && p2 && w >= 4) {           // integer vector: word copy (one unaligned 4-byte load per group)
+    const int gsh = sh - 2;
+    for (int g = lane_id(); g < (w * h) >> 2; g += MBK_WS) {
+      const int y = g >> gsh, x = (g & ((1 << gsh) - 1)) << 2;
+      const uint32_t v = ld4u(src + y * ss + x);
+      uint8_t* d = dst + y * ds + x;
+      d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24);
+    }
+    return;
+  }
   for (int i = lane_id(); i < w * h; i += MBK_WS) {
-    const int y = i / w, x = i - y * w;
+    const int y = p2 ? i >> sh : i / w, x = i - y * w;
     dst[y * ds + x] = (uint8_t)luma_qpel_sample(src + y * ss + x, ss, fx, fy);
   }
 }
 
 // half-sample planes used by the fractional refinement (pfLumaHalfpelHor/Ver/Cen, mc.h:46-49)
-MBK_HD void warp_halfpel(int which, const uint8_t* src, int ss, uint8_t* dst, int ds, int w, int h) {
+MBK_FN void warp_halfpel(int which, const uint8_t* src, int ss, uint8_t* dst, int ds, int w, int h) {
   for (int i = lane_id(); i < w * h; i += MBK_WS) {
     const int y = i / w, x = i - y * w;
     const uint8_t* p = src + y * ss + x;
@@ -56,12 +68,13 @@ MBK_HD void warp_halfpel(int which, const uint8_t* src, int ss, uint8_t* dst, in
 }
 
 // bilinear eighth-sample chroma (mc.cpp:349-380)
-MBK_HD void warp_mc_chroma(const uint8_t* src, int ss, uint8_t* dst, int ds, int mvx, int mvy, int w,
+MBK_FN void warp_mc_chroma(const uint8_t* src, int ss, uint8_t* dst, int ds, int mvx, int mvy, int w,
                                                int h) {
   const int dx = mvx & 7, dy = mvy & 7;
   const int A = (8 - dx) * (8 - dy), B = dx * (8 - dy), Cc = (8 - dx) * dy, D = dx * dy;
+  const int sh = 31 - clz32((uint32_t)w);        // chroma widths are 2, 4, 8
   for (int i = lane_id(); i < w * h; i += MBK_WS) {
-    const int y = i / w, x = i - y * w;
+    const int y = i >> sh, x = i - (y << sh);
     const uint8_t* p = src + y * ss + x;
     int v;
     if ((dx | dy) == 0) v = p[0];
@@ -70,7 +83,7 @@ MBK_HD void warp_mc_chroma(const uint8_t* src, int ss, uint8_t* dst, int ds, int
   }
 }
 
-MBK_HD void warp_pixel_avg(uint8_t* dst, int ds, const uint8_t* a, int sa, const uint8_t* b, int sb,
+MBK_FN void warp_pixel_avg(uint8_t* dst, int ds, const uint8_t* a, int sa, const uint8_t* b, int sb,
                                                int w, int h) {
   for (int i = lane_id(); i < w * h; i += MBK_WS) {
     const int y = i / w, x = i - y * w;

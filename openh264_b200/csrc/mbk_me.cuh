@@ -27,7 +27,7 @@ struct MeOut {
   const uint8_t* ref_best;                 // matched block in the reference plane
 };
 
-MBK_HD void warp_me_search(const MeIn& in, MeOut& out) {
+MBK_FN void warp_me_search(const MeIn& in, MeOut& out) {
   const int lw = blk_lw(in.blk), lh = blk_lh(in.blk);
   const int px = in.mvp_x, py = in.mvp_y, rs = in.ref_stride;
 

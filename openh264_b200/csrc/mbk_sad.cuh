@@ -8,7 +8,7 @@ namespace mbk {
 
 // SAD of a (1<<lw) x (1<<lh) block: the block is cut into 4-pixel groups, lane g takes groups
 // g, g+32, ...; each group is one __vsadu4 on packed bytes; warp total by REDUX.
-MBK_HD int warp_sad(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh) {
+MBK_FN int warp_sad(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh) {
   const int lg = lw - 2;                    // log2(groups per row)
   const int ngroups = 1 << (lg + lh);
   int s = 0;
@@ -20,7 +20,7 @@ MBK_HD int warp_sad(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, 
 }
 
 // SADs against b shifted up, down, left, right by one pixel (pfSample4Sad order), cur read once.
-MBK_HD void warp_sad_four(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh,
+MBK_FN void warp_sad_four(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh,
                                               int out[4]) {
   const int lg = lw - 2;
   const int ngroups = 1 << (lg + lh);
@@ -61,7 +61,7 @@ MBK_HD int satd4x4_thread(const uint8_t* a, int sa, const uint8_t* b, int sb) {
 }
 
 // SATD of a block: one lane per 4x4 sub-block (16 lanes busy for 16x16), warp total by REDUX.
-MBK_HD int warp_satd(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh) {
+MBK_FN int warp_satd(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh) {
   const int lbx = lw - 2;                    // log2(4x4 blocks per row)
   const int nblk = 1 << (lbx + lh - 2);
   int s = 0;

@@ -14,6 +14,8 @@ for f in range(6):
     enc.encode([clip[f*fsz:(f+1)*fsz]]*S)
     L.b2h264_debug_enc_stats(st.ctypes.data,1)
     t=enc.timing_us()
+    if hasattr(L,'b2h264_debug_sched_stats'):
+        sc=np.zeros(8,np.uint64); L.b2h264_debug_sched_stats(sc.ctypes.data,1); print('   sched: gather cyc',int(sc[0]),'poll cyc',int(sc[1]),'tagwait cyc',int(sc[2]),'gens',int(sc[3]),'claimed',int(sc[4]),'wanted',int(sc[5]))
     busy=float(sum(st[0::2])); n=float(sum(st[1::2]))
     print('   avg cyc/MB %.0f  utilisation of 1184 warps @1.9GHz: %.2f'%(busy/n, busy/(1184*t[0]*1900.0)))
     print('frame',f,'kernel us',round(t[0]),'dbk',round(t[1]), {names[i]:(int(st[2*i+1]), int(st[2*i]//max(1,st[2*i+1]))) for i in range(7) if st[2*i+1]})

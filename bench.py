@@ -177,9 +177,9 @@ def main():
     import torch
     import torch.distributed as dist
     from openh264_b200.binding import BatchEncoder, lib
+    from openh264_b200 import shard
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    shard.init("nccl", torch.device("cuda", local))        # one process per GPU; replicas only
     S = args.streams
     L = lib(local)
     clip_h = make_clip()
@@ -218,8 +218,7 @@ def main():
         on_dev = mode == "resident"
         run(enc, on_dev, args.warmup, 0)                           # warm-up (includes the IDR pictures)
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        shard.barrier()
         sampler = ClockSampler(local)
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -252,19 +251,14 @@ def main():
         dev = e0.elapsed_time(e1) / 1e3
         sampler.stop_flag = True
         sampler.join(timeout=2)
-        dt = max(wall, dev)
-        if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        results[mode] = {"dt": dt, "wall": wall, "dev": dev, "bytes": nb, "clocks": sampler.summary()}
+        dt, pics = shard.job_totals(max(wall, dev), S * args.steps, device="cuda")   # MAX over ranks / SUM over ranks
+        results[mode] = {"dt": dt, "pictures": pics, "wall": wall, "dev": dev, "bytes": nb, "clocks": sampler.summary()}
         enc.close()
     launches = L.b2h264_launch_count() - launches0
 
     if rank == 0:
-        frames = world * S * args.steps
-        value = frames / results["resident"]["dt"]
-        e2e = frames / results["e2e"]["dt"]
+        value = results["resident"]["pictures"] / results["resident"]["dt"]
+        e2e = results["e2e"]["pictures"] / results["e2e"]["dt"]
         peak, peak_kind = measured_peaks()
         k_enc = float(np.mean([k[0] for k in kern_us])) * 1e-6        # seconds per launch of pad + macroblock wavefront kernel
         k_dbk = float(np.mean([k[1] for k in kern_us])) * 1e-6
@@ -280,10 +274,10 @@ def main():
                                    "per step; bitstream bit-identical to the reference" % S,
                        "streams_per_gpu": S, "parallelism": "replica x%d (independent streams, no collective)" % world,
                        "l2": "inputs larger than L2 (%.0f MB of pictures in flight per step)" % (S * fsz / 1e6)},
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": S * fsz, "d2h_bytes_per_step": S * MBS_PER_FRAME * 896},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": world * S * fsz, "d2h_bytes_per_step": world * S * MBS_PER_FRAME * 896},
             "gpu_launches": int(launches),
             "clocks": results["resident"]["clocks"],
-            "roofline": {"bound": "hbm", "kernel": "k_encode_rows (macroblock wavefront)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_encode_mbs (macroblock wavefront, all streams)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
                          "note": "wavefront kernel is dependency/latency-bound by construction (SURVEY.md §8d); "
                                  "alg bytes = %d B/MB x %d MB/launch" % (ALG_BYTES_PER_MB, S * MBS_PER_FRAME)},
@@ -296,7 +290,7 @@ def main():
             out["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(out))
     if world > 1:
-        dist.barrier()
+        shard.barrier()
         dist.destroy_process_group()
 
 

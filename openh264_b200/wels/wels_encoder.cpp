@@ -1,0 +1,292 @@
+// wels_encoder.cpp — layer 3: an ISVCEncoder (codec/api/wels/codec_api.h:272-339) over the layer-2 C ABI
+// (include/b2h264_codec.h), one stream per object.  Compiled against the reference's public API headers so that
+// the vtable slot order and the parameter / bitstream-info structures are the reference's own
+// (include/b2h264_wels_api.h).  Behavioural model: CWelsH264SVCEncoder (codec/encoder/plus/src/welsEncoderExt.cpp):
+// Initialize* validate and (re)create the encoder, EncodeFrame is synchronous and returns encoder-owned bitstream
+// memory that stays valid until the next call.  No CPU encoder lives here: every picture goes through
+// b2h264_enc_submit / b2h264_enc_collect, i.e. the CUDA macroblock pipeline; creation fails without a device.
+#include <cuda_runtime_api.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "b2h264_codec.h"
+#include "codec_api.h"
+#include "codec_ver.h"
+
+namespace {
+
+const int kMaxFps = 60, kMinFps = 1;          // MAX_FRAME_RATE / MIN_FRAME_RATE (codec/encoder/core/inc/wels_const.h:60-61)
+
+void why(const char* msg) { fprintf(stderr, "[b2h264] unsupported encoder configuration: %s\n", msg); }
+
+class B2Encoder : public ISVCEncoder {
+ public:
+  B2Encoder() { default_params(&par_); }
+  ~B2Encoder() override { Uninitialize(); }
+
+  int EXTAPI Initialize(const SEncParamBase* p) override {
+    if (!p) return cmInitParaError;
+    // SWelsSvcCodingParam::ParamBaseTranscode (codec/encoder/core/inc/param_svc.h:236): the base parameters
+    // over the defaults
+    SEncParamExt e;
+    default_params(&e);
+    e.iUsageType = p->iUsageType;
+    e.iPicWidth = p->iPicWidth;
+    e.iPicHeight = p->iPicHeight;
+    e.iTargetBitrate = p->iTargetBitrate;
+    e.iRCMode = p->iRCMode;
+    e.fMaxFrameRate = p->fMaxFrameRate;
+    e.sSpatialLayers[0].iVideoWidth = p->iPicWidth;
+    e.sSpatialLayers[0].iVideoHeight = p->iPicHeight;
+    e.sSpatialLayers[0].fFrameRate = p->fMaxFrameRate;
+    e.sSpatialLayers[0].iSpatialBitrate = p->iTargetBitrate;
+    // the defaults switch on tools this pipeline does not implement; Initialize() callers get them only if
+    // they would have no effect, i.e. never: state it instead of guessing
+    e.bEnableSceneChangeDetect = e.bEnableBackgroundDetection = e.bEnableAdaptiveQuant = e.bEnableFrameSkip = false;
+    if (p->iRCMode != RC_OFF_MODE) { why("Initialize(SEncParamBase): rate control is on (only RC_OFF_MODE)"); return cmUnsupportedData; }
+    why("Initialize(SEncParamBase) enables scene-change/background detection/adaptive quant by default; use InitializeExt");
+    return cmUnsupportedData;
+  }
+
+  int EXTAPI InitializeExt(const SEncParamExt* p) override {
+    if (!p) return cmInitParaError;
+    if (p->iPicWidth < 16 || p->iPicHeight < 16) return cmInitParaError;
+    const SSpatialLayerConfig& l = p->sSpatialLayers[0];
+#define REQUIRE(cond, msg) do { if (!(cond)) { why(msg); return cmUnsupportedData; } } while (0)
+    REQUIRE(p->iUsageType == CAMERA_VIDEO_REAL_TIME, "iUsageType != CAMERA_VIDEO_REAL_TIME");
+    REQUIRE(p->iSpatialLayerNum == 1 && p->iTemporalLayerNum == 1, "more than one spatial/temporal layer");
+    REQUIRE(p->iRCMode == RC_OFF_MODE, "iRCMode != RC_OFF_MODE");
+    REQUIRE(l.sSliceArgument.uiSliceMode == SM_SINGLE_SLICE, "uiSliceMode != SM_SINGLE_SLICE");
+    REQUIRE(p->iEntropyCodingModeFlag == 0, "CABAC");
+    REQUIRE(p->iNumRefFrame == 1 || p->iNumRefFrame == AUTO_REF_PIC_COUNT, "iNumRefFrame != 1");
+    REQUIRE(p->uiIntraPeriod == 0, "uiIntraPeriod != 0");
+    REQUIRE(p->iLoopFilterDisableIdc == 0 && p->iLoopFilterAlphaC0Offset == 0 && p->iLoopFilterBetaOffset == 0, "loop filter idc/offsets != 0");
+    REQUIRE(p->iComplexityMode == MEDIUM_COMPLEXITY || p->iComplexityMode == HIGH_COMPLEXITY, "iComplexityMode LOW");
+    REQUIRE(!p->bEnableDenoise && !p->bEnableBackgroundDetection && !p->bEnableAdaptiveQuant && !p->bEnableSceneChangeDetect,
+            "denoise / background detection / adaptive quant / scene change detection enabled");
+    REQUIRE(!p->bEnableLongTermReference && !p->bEnableFrameSkip, "LTR or frame skip enabled");
+    REQUIRE(p->bEnableFrameCroppingFlag, "bEnableFrameCroppingFlag false");
+    REQUIRE(!p->bEnableSSEI && !p->bSimulcastAVC && !p->bPrefixNalAddingCtrl, "SSEI / simulcast / prefix NAL");
+    REQUIRE(p->eSpsPpsIdStrategy == CONSTANT_ID || p->eSpsPpsIdStrategy == INCREASING_ID, "eSpsPpsIdStrategy");
+    REQUIRE(l.uiProfileIdc == PRO_UNKNOWN || l.uiProfileIdc == PRO_BASELINE, "profile != baseline");
+    REQUIRE(l.uiLevelIdc == LEVEL_UNKNOWN, "explicit level");
+    REQUIRE(!l.bAspectRatioPresent && !l.bVideoSignalTypePresent, "VUI");
+    REQUIRE(l.iVideoWidth == p->iPicWidth && l.iVideoHeight == p->iPicHeight, "layer resolution != picture resolution");
+    REQUIRE((p->iPicWidth % 4) == 0 && (p->iPicHeight % 2) == 0, "width % 4 or height % 2");
+    REQUIRE(l.iDLayerQp >= 0 && l.iDLayerQp <= 51, "iDLayerQp out of range");
+    REQUIRE(p->uiMaxNalSize == 0, "uiMaxNalSize");
+#undef REQUIRE
+    Uninitialize();
+    b2h264_enc_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.width = p->iPicWidth;
+    cfg.height = p->iPicHeight;
+    cfg.qp = l.iDLayerQp;
+    float fps = p->fMaxFrameRate;                      // WELS_CLIP3 (param_svc.h:238)
+    fps = fps < kMinFps ? kMinFps : (fps > kMaxFps ? kMaxFps : fps);
+    cfg.fps = fps;
+    cfg.target_bitrate = p->iTargetBitrate;
+    cfg.n_streams = 1;
+    cfg.entropy_threads = 1;
+    cfg.device = 0;
+    if (b2h264_enc_create(&cfg, &enc_) != 0 || !enc_) { enc_ = nullptr; return cmMallocMemeError; }
+    par_ = *p;
+    w_ = cfg.width; h_ = cfg.height;
+    if (cudaHostAlloc((void**)&pinned_, (size_t)w_ * h_ * 3 / 2, cudaHostAllocDefault) != cudaSuccess) {
+      Uninitialize();
+      return cmMallocMemeError;
+    }
+    return cmResultSuccess;
+  }
+
+  int EXTAPI GetDefaultParams(SEncParamExt* p) override {
+    if (!p) return cmInitParaError;
+    default_params(p);
+    return cmResultSuccess;
+  }
+
+  int EXTAPI Uninitialize() override {
+    if (enc_) { b2h264_enc_destroy(enc_); enc_ = nullptr; }
+    if (pinned_) { cudaFreeHost(pinned_); pinned_ = nullptr; }
+    return cmResultSuccess;
+  }
+
+  int EXTAPI EncodeFrame(const SSourcePicture* pic, SFrameBSInfo* info) override {
+    if (!enc_ || !pic || !info) return cmInitParaError;            // welsEncoderExt.cpp:376-379
+    if (pic->iColorFormat != videoFormatI420) return cmInitParaError;   // :380
+    if (pic->iPicWidth != w_ || pic->iPicHeight != h_) return cmInitParaError;
+    // the caller may reuse its planes after return: gather them (any stride) into the pinned staging picture
+    uint8_t* d = pinned_;
+    for (int pl = 0; pl < 3; pl++) {
+      const int pw = pl ? w_ / 2 : w_, ph = pl ? h_ / 2 : h_;
+      if (!pic->pData[pl] || pic->iStride[pl] < pw) return cmInitParaError;
+      for (int y = 0; y < ph; y++) memcpy(d + (size_t)y * pw, pic->pData[pl] + (size_t)y * pic->iStride[pl], pw);
+      d += (size_t)pw * ph;
+    }
+    const uint8_t* src[1] = {pinned_};
+    if (b2h264_enc_submit(enc_, src, 0) != 0) return cmUnknownReason;
+    const uint8_t* bs = nullptr;
+    int32_t bytes = 0, ftype = 0;
+    if (b2h264_enc_collect(enc_, &bs, &bytes, &ftype) != 0) return cmUnknownReason;
+    au_.assign(bs, bs + bytes);
+    fill_info(info, ftype == 1, pic->uiTimeStamp);
+    return cmResultSuccess;
+  }
+
+  int EXTAPI EncodeParameterSets(SFrameBSInfo*) override {
+    why("EncodeParameterSets: parameter sets are emitted with every IDR access unit");
+    return cmUnsupportedData;
+  }
+
+  int EXTAPI ForceIntraFrame(bool idr, int /*layer*/ = -1) override {
+    if (!enc_) return 1;
+    if (!idr) return 1;                                            // welsEncoderExt.cpp: nothing to do
+    return b2h264_enc_force_idr(enc_, 0) == 0 ? 0 : 1;
+  }
+
+  int EXTAPI SetOption(ENCODER_OPTION id, void* v) override {
+    if (!v) return cmInitParaError;
+    switch (id) {
+      case ENCODER_OPTION_TRACE_LEVEL:
+      case ENCODER_OPTION_TRACE_CALLBACK:
+      case ENCODER_OPTION_TRACE_CALLBACK_CONTEXT:
+        return cmResultSuccess;                                    // this library does not trace
+      case ENCODER_OPTION_DATAFORMAT:
+        return *(int*)v == videoFormatI420 ? cmResultSuccess : cmInitParaError;
+      case ENCODER_OPTION_IDR_INTERVAL:
+        if (*(int*)v == 0) return cmResultSuccess;
+        why("ENCODER_OPTION_IDR_INTERVAL != 0");
+        return cmUnsupportedData;
+      default:
+        why("SetOption: option not supported by the constant-QP single-layer pipeline");
+        return cmUnsupportedData;
+    }
+  }
+
+  int EXTAPI GetOption(ENCODER_OPTION id, void* v) override {
+    if (!v) return cmInitParaError;
+    if (!enc_) return cmInitExpected;
+    switch (id) {
+      case ENCODER_OPTION_DATAFORMAT: *(int*)v = videoFormatI420; return cmResultSuccess;
+      case ENCODER_OPTION_IDR_INTERVAL: *(int*)v = 0; return cmResultSuccess;
+      case ENCODER_OPTION_SVC_ENCODE_PARAM_EXT: *(SEncParamExt*)v = par_; return cmResultSuccess;
+      case ENCODER_OPTION_FRAME_RATE: *(float*)v = par_.fMaxFrameRate; return cmResultSuccess;
+      default: return cmInitParaError;
+    }
+  }
+
+ private:
+  // values of SWelsSvcCodingParam::FillDefault (codec/encoder/core/inc/param_svc.h:132-217)
+  static void default_params(SEncParamExt* p) {
+    memset(p, 0, sizeof(*p));
+    p->iUsageType = CAMERA_VIDEO_REAL_TIME;
+    p->iNumRefFrame = AUTO_REF_PIC_COUNT;
+    p->fMaxFrameRate = (float)kMaxFps;
+    p->iComplexityMode = LOW_COMPLEXITY;
+    p->iTargetBitrate = p->iMaxBitrate = UNSPECIFIED_BIT_RATE;
+    p->iMultipleThreadIdc = 1;
+    p->bUseLoadBalancing = true;
+    p->iLtrMarkPeriod = 30;
+    p->bEnableFrameCroppingFlag = true;
+    p->iRCMode = RC_QUALITY_MODE;
+    p->bEnableSceneChangeDetect = p->bEnableBackgroundDetection = p->bEnableAdaptiveQuant = p->bEnableFrameSkip = true;
+    p->eSpsPpsIdStrategy = INCREASING_ID;
+    p->iSpatialLayerNum = p->iTemporalLayerNum = 1;
+    p->iMaxQp = 51;
+    p->iMinQp = 0;
+    p->bFixRCOverShoot = true;
+    p->iIdrBitrateRatio = 4 * 100;                       // IDR_BITRATE_RATIO (rc.h:120)
+    for (int i = 0; i < MAX_SPATIAL_LAYER_NUM; i++) {
+      SSpatialLayerConfig& l = p->sSpatialLayers[i];
+      l.uiProfileIdc = PRO_UNKNOWN;
+      l.uiLevelIdc = LEVEL_UNKNOWN;
+      l.iDLayerQp = 26;                                  // SVC_QUALITY_BASE_QP
+      l.fFrameRate = p->fMaxFrameRate;
+      l.iMaxSpatialBitrate = UNSPECIFIED_BIT_RATE;
+      l.sSliceArgument.uiSliceMode = SM_SINGLE_SLICE;
+      l.sSliceArgument.uiSliceSizeConstraint = 1500;
+      l.eAspectRatio = ASP_UNSPECIFIED;
+      l.uiVideoFormat = VF_UNDEF;
+      l.uiColorPrimaries = CP_UNDEF;
+      l.uiTransferCharacteristics = TRC_UNDEF;
+      l.uiColorMatrix = CM_UNDEF;
+    }
+  }
+
+  // The access unit is [SPS PPS] slice, each NAL behind a 4-byte start code.  The reference reports an IDR as
+  // two layers (parameter sets: NON_VIDEO_CODING_LAYER, then the slice: VIDEO_CODING_LAYER), a P picture as one.
+  void fill_info(SFrameBSInfo* info, bool idr, long long ts) {
+    memset(info, 0, sizeof(*info));
+    nal_len_.clear();
+    std::vector<size_t> start;
+    for (size_t i = 0; i + 3 < au_.size(); i++)
+      if (au_[i] == 0 && au_[i + 1] == 0 && au_[i + 2] == 0 && au_[i + 3] == 1) { start.push_back(i); i += 3; }
+    for (size_t k = 0; k < start.size(); k++)
+      nal_len_.push_back((int)((k + 1 < start.size() ? start[k + 1] : au_.size()) - start[k]));
+    const EVideoFrameType ft = idr ? videoFrameTypeIDR : videoFrameTypeP;
+    int layer = 0;
+    size_t first_vcl = 0;
+    if (idr && nal_len_.size() >= 3) {
+      SLayerBSInfo& l = info->sLayerInfo[layer++];
+      l.eFrameType = ft;
+      l.uiLayerType = NON_VIDEO_CODING_LAYER;
+      l.iNalCount = (int)nal_len_.size() - 1;
+      l.pNalLengthInByte = nal_len_.data();
+      l.pBsBuf = au_.data();
+      first_vcl = nal_len_.size() - 1;
+    }
+    SLayerBSInfo& v = info->sLayerInfo[layer++];
+    v.eFrameType = ft;
+    v.uiLayerType = VIDEO_CODING_LAYER;
+    v.iNalCount = (int)(nal_len_.size() - first_vcl);
+    v.pNalLengthInByte = nal_len_.data() + first_vcl;
+    v.pBsBuf = au_.data() + (first_vcl ? start[first_vcl] : 0);
+    info->iLayerNum = layer;
+    info->eFrameType = ft;
+    info->iFrameSizeInBytes = (int)au_.size();
+    info->uiTimeStamp = ts;
+  }
+
+  b2h264_enc* enc_ = nullptr;
+  SEncParamExt par_;
+  int w_ = 0, h_ = 0;
+  uint8_t* pinned_ = nullptr;
+  std::vector<uint8_t> au_;
+  std::vector<int> nal_len_;
+};
+
+}  // namespace
+
+extern "C" {
+
+int WelsCreateSVCEncoder(ISVCEncoder** pp) {
+  if (!pp) return 1;
+  *pp = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    fprintf(stderr, "[b2h264] WelsCreateSVCEncoder: no CUDA device — this library has no CPU path\n");
+    return 1;
+  }
+  *pp = new B2Encoder();
+  return 0;
+}
+
+void WelsDestroySVCEncoder(ISVCEncoder* p) { delete static_cast<B2Encoder*>(p); }
+
+long WelsCreateDecoder(ISVCDecoder** pp) {
+  if (pp) *pp = nullptr;
+  fprintf(stderr, "[b2h264] WelsCreateDecoder: the decoder path is not built yet (DESIGN.md section 9)\n");
+  return 1;
+}
+void WelsDestroyDecoder(ISVCDecoder*) {}
+int WelsGetDecoderCapability(SDecoderCapability*) { return 1; }
+
+OpenH264Version WelsGetCodecVersion(void) {
+  OpenH264Version v = {OPENH264_MAJOR, OPENH264_MINOR, OPENH264_REVISION, OPENH264_RESERVED};
+  return v;
+}
+void WelsGetCodecVersionEx(OpenH264Version* v) { if (v) *v = WelsGetCodecVersion(); }
+
+}  // extern "C"

@@ -213,7 +213,7 @@ def main():
     launches0 = L.b2h264_launch_count()
     kern_us = []
     for mode in ("resident", "e2e"):
-        enc = BatchEncoder(W, H, qp=QP, fps=FPS, n_streams=S)
+        enc = BatchEncoder(W, H, qp=QP, fps=FPS, n_streams=S, device=local)
         enc.set_stream(stream.cuda_stream)
         on_dev = mode == "resident"
         run(enc, on_dev, args.warmup, 0)                           # warm-up (includes the IDR pictures)

@@ -38,6 +38,7 @@ typedef struct {
   int32_t n_streams;            /* independent streams coded per call */
   int32_t entropy_threads;      /* host threads for CAVLC (0 = min(n_streams, hardware threads)) */
   int32_t device;               /* CUDA device ordinal */
+  int32_t sps_pps_id_strategy;  /* eSpsPpsIdStrategy: 0 CONSTANT_ID, 1 INCREASING_ID (the reference's default) */
 } b2h264_enc_config;
 
 /* returns 0 or a negative b2h264 error / positive cudaError_t */

@@ -17,7 +17,7 @@
  *   with zero offsets, iComplexityMode MEDIUM/HIGH, bEnableDenoise / BackgroundDetection / AdaptiveQuant /
  *   SceneChangeDetect / LongTermReference / FrameSkip all false, bEnableFrameCroppingFlag true,
  *   profile baseline/unknown, no SSEI / simulcast / prefix NAL, eSpsPpsIdStrategy CONSTANT_ID or INCREASING_ID
- *   (identical while no parameter change occurs), width % 4 == 0, height % 2 == 0.
+ *   (every IDR's parameter sets take the next id, as in the reference), width % 4 == 0, height % 2 == 0.
  * Initialize(SEncParamBase*) implies RC on (the reference's default RC_QUALITY_MODE): unsupported unless
  *   iRCMode == RC_OFF_MODE.
  */

@@ -120,7 +120,10 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
   e->cfg = *cfg;
   e->S = cfg->n_streams;
   e->ctl.resize(e->S);
-  for (auto& c : e->ctl) c.init(cfg->width, cfg->height, cfg->qp, cfg->fps, cfg->target_bitrate);
+  for (auto& c : e->ctl) {
+    c.init(cfg->width, cfg->height, cfg->qp, cfg->fps, cfg->target_bitrate);
+    c.increasing_ids = cfg->sps_pps_id_strategy != 0;
+  }
   e->idr_next.assign(e->S, 1);
   e->have_ref_p.assign(e->S, 0);
   const StreamCtl& c0 = e->ctl[0];
@@ -189,6 +192,7 @@ int b2h264_enc_force_idr(b2h264_enc* e, int stream) {
 
 int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_device) {
   if (!e || !src) return -1;
+  CK(cudaSetDevice(e->cfg.device));
   const int k = e->submit_idx & 1;
   b2h264_enc::Slot& sl = e->slot[k];
   if (sl.busy) return -3;                       // two batches already in flight
@@ -260,6 +264,7 @@ int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_devic
 
 int b2h264_enc_collect(b2h264_enc* e, const uint8_t** bs, int32_t* bs_bytes, int32_t* frame_type) {
   if (!e) return -1;
+  CK(cudaSetDevice(e->cfg.device));
   const int k = e->collect_idx & 1;
   b2h264_enc::Slot& sl = e->slot[k];
   if (!sl.busy) return -4;
@@ -289,6 +294,7 @@ int b2h264_enc_collect(b2h264_enc* e, const uint8_t** bs, int32_t* bs_bytes, int
 
 int b2h264_enc_get_recon(b2h264_enc* e, int stream, uint8_t* dst) {
   if (!e || stream < 0 || stream >= e->S || !dst) return -1;
+  CK(cudaSetDevice(e->cfg.device));
   CK(cudaStreamSynchronize(e->st));
   const int set = 1 - e->cur_rec;               // the picture reconstructed last is now the reference
   const int w = e->cfg.width, h = e->cfg.height;

@@ -17,7 +17,7 @@ void StreamCtl::init(int width, int height, int qp, float fps_, int target_bitra
   sp.crop = (sp.mb_w * 16 != width) || (sp.mb_h * 16 != height);
   sp.crop_right = (sp.mb_w * 16 - width) / 2;
   sp.crop_bottom = (sp.mb_h * 16 - height) / 2;
-  frame_num = 0; idr_pic_id = 0; frames_coded = 0; force_idr = true;
+  frame_num = 0; idr_pic_id = 0; frames_coded = 0; force_idr = true; parasets_written = 0;
 }
 
 EncFrameParams StreamCtl::frame_params(bool idr, bool ref_is_p) const {
@@ -39,6 +39,8 @@ void StreamCtl::write_access_unit(bool idr, const MbOut* mbs, std::vector<uint8_
   if (idr) {
     idr_pic_id = idr_pic_id < 65535 ? idr_pic_id + 1 : 0;
     frame_num = 0;
+    if (increasing_ids) { sp.sps_id = parasets_written % 32; sp.pps_id = parasets_written % 57; }
+    parasets_written++;
     write_sps(sp, &rbsp); append_nal(au, 3, 7, rbsp); rbsp.clear();
     write_pps(sp, &rbsp); append_nal(au, 3, 8, rbsp); rbsp.clear();
   }

@@ -19,6 +19,10 @@ struct StreamCtl {
   int idr_pic_id = 0;
   long frames_coded = 0;
   bool force_idr = true;
+  // eSpsPpsIdStrategy: INCREASING_ID (the reference default) gives every emitted SPS/PPS pair the next id
+  // (mod MAX_SPS_COUNT 32 / MAX_PPS_COUNT 57, paraset_strategy.cpp:338-369); CONSTANT_ID keeps 0/0
+  bool increasing_ids = true;
+  int parasets_written = 0;
 
   void init(int width, int height, int qp, float fps_, int target_bitrate);
   bool next_is_idr() const { return force_idr; }

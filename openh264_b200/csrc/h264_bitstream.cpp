@@ -58,7 +58,7 @@ void write_sps(const StreamParams& sp, std::vector<uint8_t>* rbsp) {
   w.bit(1); w.bit(1); w.bit(0); w.bit(sp.constraint_set3);   // constraint_set0..3
   w.put(4, 0);
   w.put(8, (uint32_t)sp.level_idc);
-  w.ue(0);                              // seq_parameter_set_id
+  w.ue((uint32_t)sp.sps_id);            // seq_parameter_set_id
   w.ue(15 - 4);                         // log2_max_frame_num_minus4
   w.ue(2);                              // pic_order_cnt_type
   w.ue((uint32_t)sp.num_ref_frames);
@@ -81,9 +81,8 @@ void write_sps(const StreamParams& sp, std::vector<uint8_t>* rbsp) {
 }
 
 void write_pps(const StreamParams& sp, std::vector<uint8_t>* rbsp) {
-  (void)sp;
   BitWriter w(rbsp);
-  w.ue(0); w.ue(0);                     // pps id, sps id
+  w.ue((uint32_t)sp.pps_id); w.ue((uint32_t)sp.sps_id);   // pps id, sps id
   w.bit(0);                             // entropy_coding_mode_flag: CAVLC
   w.bit(0);                             // bottom_field_pic_order_in_frame_present_flag
   w.ue(0);                              // num_slice_groups_minus1
@@ -177,7 +176,7 @@ void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* mbs,
   // ---- slice header (svc_encode_slice.cpp:275-346) ----
   w.ue(0);                               // first_mb_in_slice
   w.ue(ss.idr ? 2 : 0);                  // slice_type: I / P
-  w.ue(0);                               // pic_parameter_set_id
+  w.ue((uint32_t)sp.pps_id);             // pic_parameter_set_id
   w.put(15, (uint32_t)ss.frame_num);
   if (ss.idr) w.ue((uint32_t)ss.idr_pic_id);
   if (!ss.idr) {

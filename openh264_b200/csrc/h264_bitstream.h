@@ -47,6 +47,7 @@ struct StreamParams {
   int qp;
   bool crop;
   int crop_right, crop_bottom;  // in units of 2 luma samples
+  int sps_id, pps_id;           // ids written into the parameter sets / slice headers (paraset_strategy.cpp)
 };
 
 // level selection (WelsGetLevelIdc, au_set.cpp:51-195; limits = H.264 Table A-1)

@@ -91,6 +91,7 @@ class B2Encoder : public ISVCEncoder {
     cfg.n_streams = 1;
     cfg.entropy_threads = 1;
     cfg.device = 0;
+    cfg.sps_pps_id_strategy = p->eSpsPpsIdStrategy == INCREASING_ID ? 1 : 0;
     if (b2h264_enc_create(&cfg, &enc_) != 0 || !enc_) { enc_ = nullptr; return cmMallocMemeError; }
     par_ = *p;
     w_ = cfg.width; h_ = cfg.height;

@@ -81,6 +81,7 @@ struct b2h264_enc {
   int32_t* d_sad = nullptr;
   int32_t* d_prog = nullptr;              // S x 2 x mb_h
   int* d_tickets = nullptr;
+  void* d_stash = nullptr;          // parked macroblock scratches of the staged scheduler
   StreamFrame* d_sf[2] = {nullptr, nullptr};
   const uint8_t** d_srcptr[2] = {nullptr, nullptr};
   // pinned host memory
@@ -161,6 +162,7 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
   CK(cudaMemset(e->d_sad, 0, S * e->n_mb * sizeof(int32_t)));
   CK(cudaMalloc(&e->d_prog, S * 2 * mbh * sizeof(int32_t)));
   CK(cudaMalloc(&e->d_tickets, enc_sched_ints((int)S, e->n_mb) * sizeof(int)));
+  CK(cudaMalloc(&e->d_stash, enc_stash_bytes((int)S, e->ctl[0].sp.mb_h)));
   e->bs.resize(S);
   int nt = cfg->entropy_threads;
   if (nt <= 0) { nt = (int)std::thread::hardware_concurrency(); if (nt > (int)S) nt = (int)S; if (nt < 1) nt = 1; }
@@ -173,7 +175,7 @@ void b2h264_enc_destroy(b2h264_enc* e) {
   if (!e) return;
   cudaStreamSynchronize(e->st);
   delete e->pool;
-  cudaFree(e->d_cur); cudaFree(e->d_src); cudaFree(e->d_mbi); cudaFree(e->d_sad); cudaFree(e->d_prog); cudaFree(e->d_tickets);
+  cudaFree(e->d_cur); cudaFree(e->d_src); cudaFree(e->d_mbi); cudaFree(e->d_sad); cudaFree(e->d_prog); cudaFree(e->d_tickets); cudaFree(e->d_stash);
   cudaFreeHost(e->h_src);
   for (int i = 0; i < 2; i++) {
     cudaFree(e->d_pic[i]); cudaFree(e->d_rinfo[i]); cudaFree(e->d_out[i]); cudaFree(e->d_sf[i]); cudaFree(e->d_srcptr[i]);
@@ -249,7 +251,7 @@ int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_devic
   CK(cudaMemcpyAsync(e->d_sf[k], e->h_sf[k], S * sizeof(StreamFrame), cudaMemcpyHostToDevice, e->st));
   CK(cudaMemcpyAsync(e->d_srcptr[k], e->h_srcptr[k], S * sizeof(uint8_t*), cudaMemcpyHostToDevice, e->st));
   CK(cudaEventRecord(sl.ev0, e->st));
-  int rc = enc_launch_frame(e->d_sf[k], e->d_srcptr[k], S, e->cfg.width, e->cfg.height, mbw, mbh, e->d_tickets, e->st);
+  int rc = enc_launch_frame(e->d_sf[k], e->d_srcptr[k], S, e->cfg.width, e->cfg.height, mbw, mbh, e->d_tickets, e->d_stash, e->st);
   if (rc) return rc;
   CK(cudaEventRecord(sl.ev1, e->st));
   rc = enc_launch_deblock_expand(e->d_sf[k], S, mbw, mbh, e->d_tickets, e->st);

@@ -8,39 +8,60 @@
 
 namespace mbk {
 
-MBK_HD void encode_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch& s, int mbx, int mby) {
-  MbCtx c;
+MBK_HD void mb_ctx(MbCtx& c, const EncFrameParams& p, const EncFramePtrs& f, int mbx, int mby) {
   c.p = p; c.f = f; c.mbx = mbx; c.mby = mby;
   c.nb = (mbx > 0 ? NB_LEFT : 0) | (mby > 0 ? NB_TOP : 0) | (mbx > 0 && mby > 0 ? NB_TOPLEFT : 0) |
          (mby > 0 && mbx < p.mb_w - 1 ? NB_TOPRIGHT : 0);
   c.qp = p.qp;
   c.qp_c = tbl_chroma_qp(p.qp);          // chroma_qp_index_offset = 0
   c.lambda = tbl_lambda(p.qp);
-  phase_mark(s, 31);
-  // clear the staged records (levels need no clearing: every block that gets written to the bitstream is
-  // produced by this MB's own coding path; only the header part must be deterministic)
-  {
+}
+
+#ifndef B2H264_WITH_INTER
+enum { MBS_DONE = 0, MBS_A = 1, MBS_I = 2, MBS_BSKIP = 3, MBS_B = 4, MBS_C = 5, MBS_COUNT = 6 };
+#endif
+
+// Runs ONE stage of a macroblock (see enc_inter.cuh) and returns the stage to run next (MBS_DONE: the
+// reconstruction and the records are stored and published).  MBS_A / MBS_I are the entry stages of a P / an IDR
+// picture's macroblock: they start from an empty scratch; the others continue on the scratch the previous stage left.
+MBK_HD int mb_run_stage(const MbCtx& c, MbScratch& s, int stage) {
+  int next = MBS_DONE;
+  if (stage == MBS_A || stage == MBS_I) {
+    phase_mark(s, 31);
+    // clear the staged records (levels need no clearing: every block that gets written to the bitstream is
+    // produced by this MB's own coding path; only the header part must be deterministic)
     uint32_t* a = reinterpret_cast<uint32_t*>(&s.info);
     for (int i = lane_id(); i < (int)(sizeof(MbInfo) / 4); i += MBK_WS) a[i] = 0;
     uint32_t* b = reinterpret_cast<uint32_t*>(&s.out);
     for (int i = lane_id(); i < MBOUT_HEADER_WORDS; i += MBK_WS) b[i] = 0;
+    mb_load_all(c, s);
+    phase_mark(s, 0);
   }
-  mb_load_all(c, s);
-  phase_mark(s, 0);
-  if (p.is_idr) {
+  if (stage == MBS_I) {
     intra_mb_md_enc(c, s, 0x7fffffff);
-    if (lane_id() == 0) { s.info.ref_idx = -1; c.f.sad_cost[mby * p.mb_w + mbx] = 0; }   // pSadCost[0] = 0 (:2038)
+    if (lane_id() == 0) { s.info.ref_idx = -1; c.f.sad_cost[c.mby * c.p.mb_w + c.mbx] = 0; }   // pSadCost[0] = 0 (:2038)
   }
 #ifdef B2H264_WITH_INTER
-  else {
-    inter_mb_md_enc(c, s);
-  }
+  else if (stage == MBS_A) next = inter_stage_a(c, s);
+  else if (stage == MBS_B || stage == MBS_BSKIP) next = inter_stage_b(c, s);
+  else if (stage == MBS_C) next = inter_stage_c(c, s);
 #endif
   warp_sync();
-  phase_mark(s, 10);
-  mb_store_recon(c, s);
-  mb_publish(c, s);
-  phase_mark(s, 11);
+  if (next == MBS_DONE) {
+    phase_mark(s, 10);
+    mb_store_recon(c, s);
+    mb_publish(c, s);
+    phase_mark(s, 11);
+  }
+  return next;
+}
+
+// the whole macroblock, stages back to back (host emulation build)
+MBK_HD void encode_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch& s, int mbx, int mby) {
+  MbCtx c;
+  mb_ctx(c, p, f, mbx, mby);
+  int stage = p.is_idr ? MBS_I : MBS_A;
+  while (stage != MBS_DONE) stage = mb_run_stage(c, s, stage);
 }
 
 }  // namespace mbk

@@ -318,23 +318,21 @@ MBK_FN void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy,
   };
   int hx = st->mv_x, hy = st->mv_y;
   {
-    const int ddx[4] = {0, 0, -2, 2}, ddy[4] = {-2, 2, 0, 0};
     int bi = -1;
-    for (int i = 0; i < 4; i++) {
-      const int cst = eval(st->mv_x + ddx[i], st->mv_y + ddy[i]);
+    for (int i = 0; i < 4; i++) {      // up, down, left, right by half a sample
+      const int cst = eval(st->mv_x + (i == 2 ? -2 : i == 3 ? 2 : 0), st->mv_y + (i == 0 ? -2 : i == 1 ? 2 : 0));
       if (cst < best) { best = cst; bi = i; }
     }
-    if (bi >= 0) { hx += ddx[bi]; hy += ddy[bi]; }
+    if (bi >= 0) { hx += (bi == 2 ? -2 : bi == 3 ? 2 : 0); hy += (bi == 0 ? -2 : bi == 1 ? 2 : 0); }
   }
   int fx = hx, fy = hy;
   {
-    const int ddx[4] = {0, 0, -1, 1}, ddy[4] = {-1, 1, 0, 0};
     int bi = -1;
-    for (int i = 0; i < 4; i++) {
-      const int cst = eval(hx + ddx[i], hy + ddy[i]);
+    for (int i = 0; i < 4; i++) {      // the same four directions by a quarter sample
+      const int cst = eval(hx + (i == 2 ? -1 : i == 3 ? 1 : 0), hy + (i == 0 ? -1 : i == 1 ? 1 : 0));
       if (cst < best) { best = cst; bi = i; }
     }
-    if (bi >= 0) { fx += ddx[bi]; fy += ddy[bi]; }
+    if (bi >= 0) { fx += (bi == 2 ? -1 : bi == 3 ? 1 : 0); fy += (bi == 0 ? -1 : bi == 1 ? 1 : 0); }
   }
   // final prediction
   {
@@ -422,7 +420,42 @@ MBK_FN void decided_pskip(const MbCtx& c, MbScratch& s) {
 }
 
 // ---- the P-slice macroblock (WelsMdInterMb :1858 + WelsMdInterSecondaryModesEnc :1997) --------------------------------
-MBK_FN void inter_mb_md_enc(const MbCtx& c, MbScratch& s) {
+// The macroblock is coded in up to three STAGES; the device scheduler runs each stage of many macroblocks as a
+// lock-step batch (enc_kernels.cu) and parks the scratch between stages, the host build runs them back to back.
+//   A  skip test; a decided P_SKIP (left, top and top-right neighbours skipped too) ends here
+//   B  16x16 search (unless A found a skip candidate), intra-16x16 check, sub-partitions, refinement, residual
+//   C  the intra branch of a P macroblock (taken from B when intra 16x16 beats the inter cost)
+// Values that cross a stage boundary live in s.st (warp-uniform; written by lane 0).
+enum { MBS_DONE = 0, MBS_A = 1, MBS_I = 2, MBS_BSKIP = 3, MBS_B = 4, MBS_C = 5, MBS_COUNT = 6 };
+
+// bookkeeping for the neighbours and the next frame
+MBK_FN void inter_tail(const MbCtx& c, MbScratch& s) {
+  const int idx = c.mby * c.p.mb_w + c.mbx;
+  const int final_type = s.st.final_type, p16_mvx = s.st.p16_mvx, p16_mvy = s.st.p16_mvy, cost_skip_mb = s.st.cost_skip_mb;
+  if (lane_id() == 0) {
+    s.info.mb_type = (uint8_t)final_type;
+    s.info.p16x16_mv[0] = (int16_t)p16_mvx; s.info.p16x16_mv[1] = (int16_t)p16_mvy;
+    if (MBT_IS_INTER(final_type)) s.info.ref_idx = 0;
+    RefMbInfo ri;
+    ri.mv16[0] = (int16_t)p16_mvx; ri.mv16[1] = (int16_t)p16_mvy;
+    ri.skip_sad = final_type == MBT_PSKIP ? cost_skip_mb : 0;      // WelsMdInterSaveSadAndRefMbType (:1987)
+    ri.mb_type = (uint8_t)final_type;
+    ri.pad[0] = ri.pad[1] = ri.pad[2] = 0;
+    c.f.rec_info[idx] = ri;
+  }
+  warp_sync();
+}
+
+MBK_HD void st_save(MbScratch& s, int is_skip, int cost_luma, int cost_skip_mb, int p16_mvx, int p16_mvy, int final_type) {
+  warp_sync();
+  if (lane_id() == 0) {
+    s.st.is_skip = is_skip; s.st.cost_luma = cost_luma; s.st.cost_skip_mb = cost_skip_mb;
+    s.st.p16_mvx = p16_mvx; s.st.p16_mvy = p16_mvy; s.st.final_type = final_type;
+  }
+  warp_sync();
+}
+
+MBK_FN int inter_stage_a(const MbCtx& c, MbScratch& s) {
   const int mbw = c.p.mb_w, idx = c.mby * mbw + c.mbx;
   fill_inter_cache(c, s);
   phase_mark(s, 1);
@@ -447,16 +480,24 @@ MBK_FN void inter_mb_md_enc(const MbCtx& c, MbScratch& s) {
     }
   }
   phase_mark(s, 2);
-  MeState me16, me16x8[2], me8x16[2], me8x8[4];
-  int final_type = MBT_P16x16;
-  bool done = false;
   if (is_skip && keep_skip) {
     decided_pskip(c, s);
-    final_type = MBT_PSKIP;
-    done = true;
+    st_save(s, 1, cost_luma, cost_skip_mb, p16_mvx, p16_mvy, MBT_PSKIP);
+    inter_tail(c, s);
+    return MBS_DONE;
   }
+  st_save(s, is_skip ? 1 : 0, cost_luma, cost_skip_mb, p16_mvx, p16_mvy, MBT_P16x16);
+  return is_skip ? MBS_BSKIP : MBS_B;
+}
+
+MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
+  const int mbw = c.p.mb_w, idx = c.mby * mbw + c.mbx;
+  const bool is_skip = s.st.is_skip != 0;
+  int cost_luma = s.st.cost_luma, cost_skip_mb = s.st.cost_skip_mb, p16_mvx = s.st.p16_mvx, p16_mvy = s.st.p16_mvy;
+  MeState me16, me16x8[2], me8x16[2], me8x8[4];
+  int final_type = MBT_P16x16;
   int sad_pred_mb = 0;
-  if (!done && !is_skip) {
+  if (!is_skip) {
     sad_pred_mb = predict_sad(s);
     // step 2: P16x16 (WelsMdP16x16 :978)
     int16_t mvc[5][2];
@@ -475,37 +516,26 @@ MBK_FN void inter_mb_md_enc(const MbCtx& c, MbScratch& s) {
     cost_luma = (int)me16.satd_cost;
   }
   phase_mark(s, 3);
-  if (!done) {
+  {
     // intra check (WelsMdFirstIntraMode :1829)
     int bb;
     const int cost16 = md_i16x16(c, s, &bb);
     phase_mark(s, 4);
     if (cost16 < cost_luma) {
-      int cost = cost16;
-      s.info.mb_type = MBT_I16x16;
-      s.info.cbp = 0;
-      fill_i4_cache(c, s);
-      const int cost4 = md_enc_i4x4(c, s, cost);
-      if (cost4 < cost) { s.info.mb_type = MBT_I4x4; cost = cost4; }
-      if (s.info.mb_type == MBT_I16x16) { s.info.cbp = 0; enc_rec_i16x16(c, s, s.pred_y[bb]); }
-      int cb;
-      md_chroma(c, s, &cb);
-      dct_chroma(s, s.pred_c[cb]);
-      enc_rec_uv(c, s, 0, false);
-      enc_rec_uv(c, s, 1, false);
-      rec_chroma(s, s.pred_c[cb]);
-      if (lane_id() == 0) { c.f.sad_cost[idx] = 0; s.info.ref_idx = REF_NOT_IN_LIST; }
-      final_type = s.info.mb_type;
-      done = true;
-      phase_mark(s, 5);
+      st_save(s, is_skip ? 1 : 0, cost_luma, cost_skip_mb, p16_mvx, p16_mvy, final_type);
+      if (lane_id() == 0) { s.st.cost16 = cost16; s.st.bb = bb; }
+      warp_sync();
+      return MBS_C;
     }
   }
-  if (!done && is_skip) {
+  if (is_skip) {
     decided_pskip(c, s);
-    final_type = MBT_PSKIP;
-    done = true;
+    st_save(s, 1, cost_luma, cost_skip_mb, p16_mvx, p16_mvy, MBT_PSKIP);
+    inter_tail(c, s);
+    return MBS_DONE;
   }
-  if (!done) {
+  {
+
     // step 3: sub-16x16 partitions (WelsMdInterFinePartition :1238)
     const int16_t mvc0[2] = {0, 0};
     int cost8 = 0;
@@ -608,19 +638,46 @@ MBK_FN void inter_mb_md_enc(const MbCtx& c, MbScratch& s) {
     warp_sync();
   }
   phase_mark(s, 8);
-  // bookkeeping for the neighbours and the next frame
-  if (lane_id() == 0) {
-    s.info.mb_type = (uint8_t)final_type;
-    s.info.p16x16_mv[0] = (int16_t)p16_mvx; s.info.p16x16_mv[1] = (int16_t)p16_mvy;
-    if (MBT_IS_INTER(final_type)) s.info.ref_idx = 0;
-    RefMbInfo ri;
-    ri.mv16[0] = (int16_t)p16_mvx; ri.mv16[1] = (int16_t)p16_mvy;
-    ri.skip_sad = final_type == MBT_PSKIP ? cost_skip_mb : 0;      // WelsMdInterSaveSadAndRefMbType (:1987)
-    ri.mb_type = (uint8_t)final_type;
-    ri.pad[0] = ri.pad[1] = ri.pad[2] = 0;
-    c.f.rec_info[idx] = ri;
+  st_save(s, 0, cost_luma, cost_skip_mb, p16_mvx, p16_mvy, final_type);
+  inter_tail(c, s);
+  return MBS_DONE;
+}
+
+// the intra branch of a P macroblock (WelsMdFirstIntraMode :1829 after the 16x16 cost won)
+MBK_FN int inter_stage_c(const MbCtx& c, MbScratch& s) {
+  const int idx = c.mby * c.p.mb_w + c.mbx;
+  const int bb = s.st.bb;
+  int cost = s.st.cost16;
+  {
+    {
+      s.info.mb_type = MBT_I16x16;
+      s.info.cbp = 0;
+      fill_i4_cache(c, s);
+      const int cost4 = md_enc_i4x4(c, s, cost);
+      if (cost4 < cost) { s.info.mb_type = MBT_I4x4; cost = cost4; }
+      if (s.info.mb_type == MBT_I16x16) { s.info.cbp = 0; enc_rec_i16x16(c, s, s.pred_y[bb]); }
+      int cb;
+      md_chroma(c, s, &cb);
+      dct_chroma(s, s.pred_c[cb]);
+      enc_rec_uv(c, s, 0, false);
+      enc_rec_uv(c, s, 1, false);
+      rec_chroma(s, s.pred_c[cb]);
+      if (lane_id() == 0) { c.f.sad_cost[idx] = 0; s.info.ref_idx = REF_NOT_IN_LIST; }
+      phase_mark(s, 5);
+    }
   }
   warp_sync();
+  if (lane_id() == 0) s.st.final_type = s.info.mb_type;
+  warp_sync();
+  inter_tail(c, s);
+  return MBS_DONE;
+}
+
+// the whole macroblock, stages back to back (host emulation build; WelsMdInterMb :1858 + WelsMdInterSecondaryModesEnc :1997)
+MBK_FN void inter_mb_md_enc(const MbCtx& c, MbScratch& s) {
+  int nx = inter_stage_a(c, s);
+  if (nx == MBS_B || nx == MBS_BSKIP) nx = inter_stage_b(c, s);
+  if (nx == MBS_C) inter_stage_c(c, s);
 }
 
 }  // namespace mbk

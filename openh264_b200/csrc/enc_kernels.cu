@@ -108,48 +108,131 @@ __device__ __forceinline__ void run_mbs(const StreamFrame* sf, int n_streams, co
   }
 }
 
-// CTA-synchronous variant: the CTA takes up to ENC_WPC macroblocks that are ALREADY ready, its warps start
-// them together and meet again before the next batch.  Warps that start together run the same code at the
-// same time, so one instruction-cache fill serves all of them.
+// ---- staged lock-step scheduler of the encode kernel -------------------------------------------------------------
+// The SM's instruction cache holds ~32 KB; the code one macroblock walks through is several times that.  Warps
+// that execute different code thrash it (profiles/r01_encode_icache.txt), warps that start the same code together
+// share every fill.  So (1) the CTA claims up to ENC_WPC tasks AT ONCE, its warps start them together and meet
+// again before the next batch, and (2) a batch is homogeneous: a macroblock is coded in stages (enc_inter.cuh:
+// A skip test, B motion search + inter coding, C intra branch; I = a whole IDR-picture macroblock), every stage has
+// its own ready list, and a batch comes from ONE list.  A macroblock that needs another stage parks its scratch in
+// global memory (one slot per stream and macroblock ROW: at most one macroblock of a row is in flight) and is
+// pushed onto the next stage's list; whichever CTA takes it continues from the parked scratch.
+enum { NQ = MBS_COUNT - 1 };                       // ready lists, index = stage - 1
+struct EncSched {
+  int* dep;          // per (stream, mb): notifications received so far
+  int* queue;        // NQ ready lists of capacity `total` each, -1 = slot not yet written
+  int* ctl;          // [0..NQ) heads, [NQ..2NQ) tails, [2NQ] macroblocks finished
+  uint4* stash;      // parked scratches
+};
+static_assert(sizeof(MbScratch) % 16 == 0, "scratch is copied as uint4");
+constexpr int kStashU4 = (int)(sizeof(MbScratch) / 16);
+
+__device__ __forceinline__ void esched_push(const EncSched& q, int total, int stage, int id) {
+  const int k = stage - 1;
+  const int slot = atomicAdd(q.ctl + NQ + k, 1);
+  *reinterpret_cast<volatile int*>(q.queue + (size_t)k * total + slot) = id;
+}
+
+// optional batch statistics (debug, B2H264_ENC_STATS): per ready list [batches, tasks, batch cycles]; [NQ] = leader wait cycles
+__device__ unsigned long long g_batch_stats[NQ + 1][3];
+extern "C" int b2h264_debug_batch_stats(unsigned long long* out, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_batch_stats, sizeof(g_batch_stats));
+  if (e == cudaSuccess && reset) { unsigned long long z[NQ + 1][3] = {}; e = cudaMemcpyToSymbol(g_batch_stats, z, sizeof(z)); }
+  return (int)e;
+}
+
 template <class Body>
-__device__ __forceinline__ void run_mbs_cta(const StreamFrame* sf, int n_streams, const Sched q, Body body) {
-  __shared__ int s_base, s_n;
+__device__ __forceinline__ void run_stages(const StreamFrame* sf, int n_streams, const EncSched q, MbScratch& s, int stats, Body body) {
+  __shared__ int s_k, s_base, s_n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int mb_w = sf[0].p.mb_w, mb_h = sf[0].p.mb_h, n_mb = mb_w * mb_h, total = n_streams * n_mb;
   for (;;) {
+    long long t_batch = 0;
     if (threadIdx.x == 0) {
-      int h, n;
+      int k = 0, h = 0, n = 0;
+      const long long t_wait = stats ? clock64() : 0;
       for (;;) {
-        h = ld_volatile(q.head);
-        if (h >= total) { n = -1; break; }
-        const int t = ld_volatile(q.tail);
-        n = min(ENC_WPC, t - h);
-        if (n > 0 && atomicCAS(q.head, h, h + n) == h) break;
-        __nanosleep(200);
+        if (ld_volatile(q.ctl + 2 * NQ) >= total) { n = -1; break; }
+        // later stages first (they finish macroblocks others wait for); a FULL batch beats a partial one
+        int best = -1, best_avail = 0;
+#pragma unroll
+        for (int kk = NQ - 1; kk >= 0; kk--) {
+          const int avail = ld_volatile(q.ctl + NQ + kk) - ld_volatile(q.ctl + kk);
+          if (avail >= ENC_WPC) { best = kk; best_avail = avail; break; }
+          if (avail > best_avail) { best = kk; best_avail = avail; }
+        }
+        if (best >= 0) {
+          h = ld_volatile(q.ctl + best);
+          n = min(ENC_WPC, ld_volatile(q.ctl + NQ + best) - h);
+          if (n > 0 && atomicCAS(q.ctl + best, h, h + n) == h) { k = best; break; }
+          continue;
+        }
+        __nanosleep(100);
       }
-      s_base = h; s_n = n;
+      s_k = k; s_base = h; s_n = n;
+      if (stats) { t_batch = clock64(); atomicAdd(&g_batch_stats[NQ][2], (unsigned long long)(t_batch - t_wait)); }
     }
     __syncthreads();
-    const int base = s_base, n = s_n;
+    const int k = s_k, base = s_base, n = s_n;
     if (n < 0) break;
     if (warp < n) {
       int id = 0;
-      if (lane == 0) while ((id = ld_volatile(q.queue + base + warp)) < 0) {}
+      if (lane == 0) while ((id = ld_volatile(q.queue + (size_t)k * total + base + warp)) < 0) {}
       id = __shfl_sync(MBK_FULL, id, 0);
       __threadfence();
       const int si = id / n_mb, mb = id - si * n_mb, y = mb / mb_w, x = mb - y * mb_w;
-      body(sf[si], x, y);
-      __threadfence();
+      uint4* park = q.stash + (size_t)(si * mb_h + y) * kStashU4;
+      uint4* sc = reinterpret_cast<uint4*>(&s);
+      const int stage = k + 1;
+      if (stage != MBS_A && stage != MBS_I) {            // continue a parked macroblock
+        for (int i = lane; i < kStashU4; i += 32) sc[i] = __ldcg(park + i);
+        __syncwarp();
+      }
+      const int next = body(sf[si], x, y, stage);
       __syncwarp();
-      if (lane == 0) {
-        if (x + 1 < mb_w) sched_notify(q, id + 1, 1 + (y > 0));
-        if (y + 1 < mb_h) {
-          if (x > 0) sched_notify(q, id + mb_w - 1, 1 + (x - 1 > 0));
-          if (x == mb_w - 1) sched_notify(q, id + mb_w, 1 + (x > 0));
+      if (next == MBS_DONE) {
+        __threadfence();
+        if (lane == 0) {
+          if (x + 1 < mb_w) {                                                       // right neighbour: we are its left
+            if (atomicAdd(q.dep + id + 1, 1) + 1 == 1 + (y > 0)) esched_push(q, total, sf[si].p.is_idr ? MBS_I : MBS_A, id + 1);
+          }
+          if (y + 1 < mb_h) {
+            if (x > 0 && atomicAdd(q.dep + id + mb_w - 1, 1) + 1 == 1 + (x - 1 > 0))   // bottom-left: we are its top-right
+              esched_push(q, total, sf[si].p.is_idr ? MBS_I : MBS_A, id + mb_w - 1);
+            if (x == mb_w - 1 && atomicAdd(q.dep + id + mb_w, 1) + 1 == 1 + (x > 0))   // last column: we are its top
+              esched_push(q, total, sf[si].p.is_idr ? MBS_I : MBS_A, id + mb_w);
+          }
+          atomicAdd(q.ctl + 2 * NQ, 1);
         }
+      } else {
+        for (int i = lane; i < kStashU4; i += 32) park[i] = sc[i];
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) esched_push(q, total, next, id);
       }
     }
     __syncthreads();
+    if (stats && threadIdx.x == 0) {
+      atomicAdd(&g_batch_stats[k][0], 1ull);
+      atomicAdd(&g_batch_stats[k][1], (unsigned long long)n);
+      atomicAdd(&g_batch_stats[k][2], (unsigned long long)(clock64() - t_batch));
+    }
+  }
+}
+
+__global__ void k_esched_init(EncSched q, const StreamFrame* __restrict__ sf, int n_streams, int n_mb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    // MB (0,0) of every stream is ready: IDR pictures on list I, P pictures on list A
+    int na = 0, ni = 0;
+    const int total = n_streams * n_mb;
+    for (int s = 0; s < n_streams; s++) {
+      if (sf[s].p.is_idr) q.queue[(size_t)(MBS_I - 1) * total + ni++] = s * n_mb;
+      else q.queue[(size_t)(MBS_A - 1) * total + na++] = s * n_mb;
+    }
+    for (int k = 0; k < 2 * NQ + 1; k++) q.ctl[k] = 0;
+    q.ctl[NQ + MBS_A - 1] = na;
+    q.ctl[NQ + MBS_I - 1] = ni;
   }
 }
 
@@ -170,22 +253,20 @@ extern "C" int b2h264_debug_phase_stats(unsigned long long* out32, int reset) {
 }
 #endif
 
-__global__ void __launch_bounds__(32 * ENC_WPC) k_encode_mbs(const StreamFrame* __restrict__ sf, int n_streams, Sched q, int stats) {
+__global__ void __launch_bounds__(32 * ENC_WPC) k_encode_mbs(const StreamFrame* __restrict__ sf, int n_streams, EncSched q, int stats) {
   extern __shared__ __align__(16) uint8_t smem[];
   MbScratch& s = reinterpret_cast<MbScratch*>(smem)[threadIdx.x >> 5];
-#ifdef B2H264_WARP_ASYNC
-  run_mbs(sf,
-#else
-  run_mbs_cta(sf,
-#endif
- n_streams, q, [&](const StreamFrame& F, int x, int y) {
-    const long long t0 = stats ? clock64() : 0;
-    encode_one_mb(F.p, F.f, s, x, y);
-    if (stats && (threadIdx.x & 31) == 0) {
-      const int t = s.info.mb_type & 7;
-      atomicAdd(&g_enc_stats[2 * t], (unsigned long long)(clock64() - t0));
-      atomicAdd(&g_enc_stats[2 * t + 1], 1ull);
+  run_stages(sf, n_streams, q, s, stats & 1, [&](const StreamFrame& F, int x, int y, int stage) {
+    const long long t0 = (stats & 1) ? clock64() : 0;
+    MbCtx c;
+    mb_ctx(c, F.p, F.f, x, y);
+    int next = mb_run_stage(c, s, stage);
+    if (stats & 2) while (next != MBS_DONE) next = mb_run_stage(c, s, next);      // debugging: all stages in one task
+    if ((stats & 1) && (threadIdx.x & 31) == 0) {          // cycles and count per stage
+      atomicAdd(&g_enc_stats[2 * stage], (unsigned long long)(clock64() - t0));
+      atomicAdd(&g_enc_stats[2 * stage + 1], 1ull);
     }
+    return next;
   });
 }
 
@@ -256,19 +337,30 @@ static int enc_grid_blocks() {
   return g_enc_blocks;
 }
 
-// scheduler workspace layout (ints): [0..3] head/tail for encode, deblock; then dep[2][total]; then queue[2][total]
-size_t enc_sched_ints(int n_streams, int n_mb) { return 8 + 4 * (size_t)n_streams * n_mb; }
+// scheduler workspace layout (ints): [0..3] head/tail of the deblock list, [8..8+2NQ] encode list heads/tails/finished;
+// then dep[2][total] (encode, deblock); then queue[1 + NQ][total] (deblock list, encode lists)
+size_t enc_sched_ints(int n_streams, int n_mb) { return 32 + (size_t)(3 + NQ) * n_streams * n_mb; }
+size_t enc_stash_bytes(int n_streams, int mb_h) { return (size_t)n_streams * mb_h * kStashU4 * sizeof(uint4); }
 
 static Sched make_sched(int* ws, int which, int total) {
   Sched q;
   q.head = ws + 2 * which; q.tail = ws + 2 * which + 1;
-  q.dep = ws + 8 + (size_t)which * total;
-  q.queue = ws + 8 + (size_t)(2 + which) * total;
+  (void)which;                                     // only the deblock list (1) uses the simple scheduler
+  q.dep = ws + 32 + (size_t)total;
+  q.queue = ws + 32 + (size_t)2 * total;
+  return q;
+}
+static EncSched make_esched(int* ws, int total, void* stash) {
+  EncSched q;
+  q.ctl = ws + 8;
+  q.dep = ws + 32;
+  q.queue = ws + 32 + (size_t)3 * total;
+  q.stash = reinterpret_cast<uint4*>(stash);
   return q;
 }
 
 int enc_launch_frame(const StreamFrame* d_sf, const uint8_t* const* d_src, int n_streams, int w, int h, int mb_w, int mb_h,
-                     int* d_ws, cudaStream_t st) {
+                     int* d_ws, void* d_stash, cudaStream_t st) {
   int rc;
   if (d_src) {
     dim3 b(32, 8), g((mb_w * 4 + 31) / 32, (mb_h * 16 + 7) / 8, n_streams);
@@ -276,15 +368,16 @@ int enc_launch_frame(const StreamFrame* d_sf, const uint8_t* const* d_src, int n
     if ((rc = b2h264_launched())) return rc;
   }
   const int total = n_streams * mb_w * mb_h;
-  cudaMemsetAsync(d_ws + 8, 0, 2 * (size_t)total * sizeof(int), st);                               // dep counters
-  cudaMemsetAsync(d_ws + 8 + 2 * (size_t)total, 0xff, 2 * (size_t)total * sizeof(int), st);        // ready lists
-  const Sched qe = make_sched(d_ws, 0, total), qd = make_sched(d_ws, 1, total);
-  k_sched_init<<<(n_streams + 127) / 128, 128, 0, st>>>(qe, n_streams, mb_w * mb_h);
+  cudaMemsetAsync(d_ws + 32, 0, 2 * (size_t)total * sizeof(int), st);                                     // dep counters
+  cudaMemsetAsync(d_ws + 32 + 2 * (size_t)total, 0xff, (size_t)(1 + NQ) * total * sizeof(int), st);       // ready lists
+  const Sched qd = make_sched(d_ws, 1, total);
+  const EncSched qe = make_esched(d_ws, total, d_stash);
+  k_esched_init<<<1, 32, 0, st>>>(qe, d_sf, n_streams, mb_w * mb_h);
   k_sched_init<<<(n_streams + 127) / 128, 128, 0, st>>>(qd, n_streams, mb_w * mb_h);
   int blocks = enc_grid_blocks();
   const int need = (total + ENC_WPC - 1) / ENC_WPC;
   if (blocks > need) blocks = need;
-  static const int stats = getenv("B2H264_ENC_STATS") ? 1 : 0;
+  static const int stats = (getenv("B2H264_ENC_STATS") ? 1 : 0) | (getenv("B2H264_FUSE_STAGES") ? 2 : 0);
   k_encode_mbs<<<blocks, 32 * ENC_WPC, sizeof(MbScratch) * ENC_WPC, st>>>(d_sf, n_streams, qe, stats);
   if ((rc = b2h264_launched())) return rc;
   return 0;

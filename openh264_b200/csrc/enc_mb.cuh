@@ -6,8 +6,14 @@
 
 namespace mbk {
 
+// values of a P macroblock that cross a stage boundary (enc_inter.cuh: inter_stage_a/b/c); warp-uniform
+struct InterState {
+  int32_t is_skip, cost_luma, cost_skip_mb, p16_mvx, p16_mvy, final_type, cost16, bb;
+};
+
 // Per-warp working set (shared memory on the device, a plain struct in the host emulation build).
-struct MbScratch {
+// Plain data only (no pointers): the device scheduler parks it in global memory between stages.
+struct alignas(16) MbScratch {
   RecTile tile;                 // reconstruction tile incl. neighbour samples
   uint8_t cur_y[256];           // current MB, stride 16
   uint8_t cur_c[128];           // Cb 0..63, Cr 64..127, stride 8
@@ -29,6 +35,7 @@ struct MbScratch {
   int32_t nb_sad[4];            // neighbours' persistent SAD cost (pSadCost[0])
   int32_t nb_skip_sad[4];       // neighbours' skip SAD of THIS picture (pMbSkipSad)
   int32_t red[32];              // small scratch
+  InterState st;
   uint32_t t_last;              // phase timer (profiling builds only)
 };
 

@@ -18,7 +18,12 @@
 // Warp-level routines are real functions, not inlined: one inlined copy per call site grew the encode
 // kernel to 774 KB of SASS and the warps (each in a different phase of a different macroblock) spent
 // 58% of their cycles waiting for instruction fetch (profiles/r01_encode_icache.txt).
-#define MBK_FN static __host__ __device__ __noinline__
+// External (weak, ODR-merged) linkage on purpose: with `static`, ptxas specialises the calling convention of each
+// function inside the translation unit, and one such specialisation returned a stale register for a field the
+// callee had just stored through a pointer into the caller's frame (me_refine -> MeState::mv_y, r01 debugging
+// notes in profiles/r01_encode_stages.txt).  Externally visible functions follow the standard ABI.  Every
+// translation unit is compiled with the same register cap because nvlink keeps one copy of each function.
+#define MBK_FN inline __host__ __device__ __noinline__
 #ifdef __CUDA_ARCH__
 #define MBK_WS 32
 #else

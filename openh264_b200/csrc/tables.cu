@@ -2,6 +2,7 @@
 // The tables are closed forms of the H.264 quantiser design; tests check them entry-by-entry against
 // the reference's literal arrays (g_kiQuantInterFF / g_kiQuantMF encode_mb_aux.cpp:38,103;
 // g_kuiDequantCoeff common_tables.cpp:208; g_kiQpCostTable encoder_data_tables.cpp:59).
+#include <stdlib.h>
 #include <atomic>
 #include <math.h>
 
@@ -67,6 +68,7 @@ int b2h264_init(int device) {
   if (e != cudaSuccess) return (int)e;
   if (count == 0) return (int)cudaErrorNoDevice;
   if ((e = cudaSetDevice(device)) != cudaSuccess) return (int)e;
+  if (const char* ss = getenv("B2H264_STACK")) cudaDeviceSetLimit(cudaLimitStackSize, (size_t)atoi(ss));   // debugging knob
   build_host_tables();
   if ((e = cudaMemcpyToSymbol(mbk::c_quant_ff, h_quant_ff, sizeof(h_quant_ff))) != cudaSuccess) return (int)e;
   if ((e = cudaMemcpyToSymbol(mbk::c_quant_mf, h_quant_mf, sizeof(h_quant_mf))) != cudaSuccess) return (int)e;

@@ -70,7 +70,9 @@ struct b2h264_enc {
   std::vector<uint8_t> idr_next;          // per stream: code next picture as IDR
   std::vector<uint8_t> have_ref_p;        // reference picture of the stream was a P picture
   int cur_rec = 0;                        // which of the two picture sets is being written
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr;        // kernels (may be the caller's stream, b2h264_enc_set_stream)
+  cudaStream_t st_in = nullptr;     // source uploads: overlap the previous picture's kernels
+  cudaStream_t st_out = nullptr;    // record downloads: overlap deblocking and the next picture's kernels
   // device memory
   uint8_t* d_cur = nullptr;               // S x (Y,U,V) MB-aligned current pictures
   uint8_t* d_pic[2] = {nullptr, nullptr}; // S x padded (Y,U,V), ping-pong
@@ -90,7 +92,7 @@ struct b2h264_enc {
   StreamFrame* h_sf[2] = {nullptr, nullptr};
   const uint8_t** h_srcptr[2] = {nullptr, nullptr};
   // in-flight bookkeeping
-  struct Slot { bool busy = false; std::vector<uint8_t> idr; cudaEvent_t ev0, ev1, ev2, done; };
+  struct Slot { bool busy = false; std::vector<uint8_t> idr; cudaEvent_t ev0, ev1, ev2, done, in_done, enc_done; };
   Slot slot[2];
   int submit_idx = 0, collect_idx = 0;
   std::vector<std::vector<uint8_t>> bs;   // per stream output of the last collect
@@ -137,6 +139,8 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
   e->pic_bytes = (e->pic_y_bytes + 2 * e->pic_c_bytes + 255) & ~(size_t)255;
   const size_t S = e->S;
   CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->st_in, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->st_out, cudaStreamNonBlocking));
   CK(cudaMalloc(&e->d_cur, S * e->cur_bytes + 256));
   for (int i = 0; i < 2; i++) {
     CK(cudaMalloc(&e->d_pic[i], S * e->pic_bytes + 256));
@@ -153,6 +157,8 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
     CK(cudaEventCreate(&e->slot[i].ev1));
     CK(cudaEventCreate(&e->slot[i].ev2));
     CK(cudaEventCreateWithFlags(&e->slot[i].done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->slot[i].in_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->slot[i].enc_done, cudaEventDisableTiming));
   }
   CK(cudaMalloc(&e->d_src, 2 * S * e->frame_bytes + 256));
   CK(cudaMallocHost(&e->h_src, 2 * S * e->frame_bytes));
@@ -180,9 +186,10 @@ void b2h264_enc_destroy(b2h264_enc* e) {
   for (int i = 0; i < 2; i++) {
     cudaFree(e->d_pic[i]); cudaFree(e->d_rinfo[i]); cudaFree(e->d_out[i]); cudaFree(e->d_sf[i]); cudaFree(e->d_srcptr[i]);
     cudaFreeHost(e->h_out[i]); cudaFreeHost(e->h_sf[i]); cudaFreeHost(e->h_srcptr[i]);
-    cudaEventDestroy(e->slot[i].ev0); cudaEventDestroy(e->slot[i].ev1); cudaEventDestroy(e->slot[i].ev2); cudaEventDestroy(e->slot[i].done);
+    cudaEventDestroy(e->slot[i].ev0); cudaEventDestroy(e->slot[i].ev1); cudaEventDestroy(e->slot[i].ev2); cudaEventDestroy(e->slot[i].done); cudaEventDestroy(e->slot[i].in_done); cudaEventDestroy(e->slot[i].enc_done);
   }
   if (e->own_stream) cudaStreamDestroy(e->st);
+  cudaStreamDestroy(e->st_in); cudaStreamDestroy(e->st_out);
   delete e;
 }
 
@@ -208,7 +215,7 @@ int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_devic
     cudaPointerAttributes at;
     const bool pinned = cudaPointerGetAttributes(&at, src[s]) == cudaSuccess && at.type == cudaMemoryTypeHost;
     if (pinned) {                               // caller's buffer is page-locked: DMA straight from it
-      CK(cudaMemcpyAsync(dd, src[s], e->frame_bytes, cudaMemcpyHostToDevice, e->st));
+      CK(cudaMemcpyAsync(dd, src[s], e->frame_bytes, cudaMemcpyHostToDevice, e->st_in));
     } else {                                    // pageable memory: stage through the encoder's pinned ring
       (void)cudaGetLastError();
       memcpy(e->h_src + ((size_t)k * S + s) * e->frame_bytes, src[s], e->frame_bytes);
@@ -222,7 +229,7 @@ int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_devic
       if (!pinned) {
         (void)cudaGetLastError();
         const size_t o = ((size_t)k * S + s) * e->frame_bytes;
-        CK(cudaMemcpyAsync(e->d_src + o, e->h_src + o, e->frame_bytes, cudaMemcpyHostToDevice, e->st));
+        CK(cudaMemcpyAsync(e->d_src + o, e->h_src + o, e->frame_bytes, cudaMemcpyHostToDevice, e->st_in));
       }
     }
   }
@@ -248,6 +255,10 @@ int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_devic
     e->have_ref_p[s] = !idr;
   }
   e->cur_rec = 1 - rec;
+  if (!src_on_device) {                        // the kernels of this picture wait for its uploads only
+    CK(cudaEventRecord(sl.in_done, e->st_in));
+    CK(cudaStreamWaitEvent(e->st, sl.in_done, 0));
+  }
   CK(cudaMemcpyAsync(e->d_sf[k], e->h_sf[k], S * sizeof(StreamFrame), cudaMemcpyHostToDevice, e->st));
   CK(cudaMemcpyAsync(e->d_srcptr[k], e->h_srcptr[k], S * sizeof(uint8_t*), cudaMemcpyHostToDevice, e->st));
   CK(cudaEventRecord(sl.ev0, e->st));
@@ -257,8 +268,10 @@ int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_devic
   rc = enc_launch_deblock_expand(e->d_sf[k], S, mbw, mbh, e->d_tickets, e->st);
   if (rc) return rc;
   CK(cudaEventRecord(sl.ev2, e->st));
-  CK(cudaMemcpyAsync(e->h_out[k], e->d_out[k], (size_t)S * e->n_mb * sizeof(MbOut), cudaMemcpyDeviceToHost, e->st));
-  CK(cudaEventRecord(sl.done, e->st));
+  // the macroblock records are final once the encode kernel is done (deblocking does not touch them)
+  CK(cudaStreamWaitEvent(e->st_out, sl.ev1, 0));
+  CK(cudaMemcpyAsync(e->h_out[k], e->d_out[k], (size_t)S * e->n_mb * sizeof(MbOut), cudaMemcpyDeviceToHost, e->st_out));
+  CK(cudaEventRecord(sl.done, e->st_out));
   sl.busy = true;
   e->submit_idx++;
   return 0;
@@ -274,8 +287,11 @@ int b2h264_enc_collect(b2h264_enc* e, const uint8_t** bs, int32_t* bs_bytes, int
   float ms = 0;
   cudaEventElapsedTime(&ms, sl.ev0, sl.ev1);
   e->last_us[0] = ms * 1000.f;               // source padding + macroblock wavefront kernel
-  cudaEventElapsedTime(&ms, sl.ev1, sl.ev2);
-  e->last_us[1] = ms * 1000.f;               // deblocking wavefront + border expansion
+  // deblocking of this picture may still be running (the records were downloaded as soon as the encode kernel
+  // finished): report it when it is done, otherwise keep the previous picture's figure
+  if (cudaEventQuery(sl.ev2) == cudaSuccess && cudaEventElapsedTime(&ms, sl.ev1, sl.ev2) == cudaSuccess)
+    e->last_us[1] = ms * 1000.f;             // deblocking wavefront + border expansion
+  (void)cudaGetLastError();
   const auto t0 = std::chrono::steady_clock::now();
   const int n_mb = e->n_mb;
   std::function<void(int)> job = [&](int s) {

@@ -306,7 +306,7 @@ MBK_FN void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy,
   const int rs = c.p.rec_stride_y;
   const int px = st->mvp_x, py = st->mvp_y;
   int best = st->satd + mvd_cost(c.lambda, st->mv_x - px, st->mv_y - py);
-  uint8_t* tmp = s.me_buf[0];
+  uint8_t* tmp = s.me_buf;
   auto eval = [&](int mvx, int mvy) {
     // st->ref sits at the integer MV; candidate integer part relative to it
     const int dx = (mvx >> 2) - (st->mv_x >> 2), dy = (mvy >> 2) - (st->mv_y >> 2);

@@ -253,7 +253,10 @@ extern "C" int b2h264_debug_phase_stats(unsigned long long* out32, int reset) {
 }
 #endif
 
-__global__ void __launch_bounds__(32 * ENC_WPC) k_encode_mbs(const StreamFrame* __restrict__ sf, int n_streams, EncSched q, int stats) {
+#ifndef ENC_MIN_CTAS
+#define ENC_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(32 * ENC_WPC, ENC_MIN_CTAS) k_encode_mbs(const StreamFrame* __restrict__ sf, int n_streams, EncSched q, int stats) {
   extern __shared__ __align__(16) uint8_t smem[];
   MbScratch& s = reinterpret_cast<MbScratch*>(smem)[threadIdx.x >> 5];
   run_stages(sf, n_streams, q, s, stats & 1, [&](const StreamFrame& F, int x, int y, int stage) {

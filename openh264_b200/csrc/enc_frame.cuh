@@ -8,13 +8,25 @@
 
 namespace mbk {
 
+// fills the context kept in the scratch (s.ctx); the warp copies the frame descriptor word by word
 MBK_HD void mb_ctx(MbCtx& c, const EncFrameParams& p, const EncFramePtrs& f, int mbx, int mby) {
-  c.p = p; c.f = f; c.mbx = mbx; c.mby = mby;
-  c.nb = (mbx > 0 ? NB_LEFT : 0) | (mby > 0 ? NB_TOP : 0) | (mbx > 0 && mby > 0 ? NB_TOPLEFT : 0) |
-         (mby > 0 && mbx < p.mb_w - 1 ? NB_TOPRIGHT : 0);
-  c.qp = p.qp;
-  c.qp_c = tbl_chroma_qp(p.qp);          // chroma_qp_index_offset = 0
-  c.lambda = tbl_lambda(p.qp);
+  static_assert(sizeof(EncFrameParams) % 4 == 0 && sizeof(EncFramePtrs) % 4 == 0, "copied as words");
+  warp_sync();
+  const uint32_t* sp = reinterpret_cast<const uint32_t*>(&p);
+  const uint32_t* sfp = reinterpret_cast<const uint32_t*>(&f);
+  uint32_t* dp = reinterpret_cast<uint32_t*>(&c.p);
+  uint32_t* df = reinterpret_cast<uint32_t*>(&c.f);
+  for (int i = lane_id(); i < (int)(sizeof(EncFrameParams) / 4); i += MBK_WS) dp[i] = sp[i];
+  for (int i = lane_id(); i < (int)(sizeof(EncFramePtrs) / 4); i += MBK_WS) df[i] = sfp[i];
+  if (lane_id() == 0) {
+    c.mbx = mbx; c.mby = mby;
+    c.nb = (mbx > 0 ? NB_LEFT : 0) | (mby > 0 ? NB_TOP : 0) | (mbx > 0 && mby > 0 ? NB_TOPLEFT : 0) |
+           (mby > 0 && mbx < p.mb_w - 1 ? NB_TOPRIGHT : 0);
+    c.qp = p.qp;
+    c.qp_c = tbl_chroma_qp(p.qp);          // chroma_qp_index_offset = 0
+    c.lambda = tbl_lambda(p.qp);
+  }
+  warp_sync();
 }
 
 #ifndef B2H264_WITH_INTER
@@ -58,10 +70,9 @@ MBK_HD int mb_run_stage(const MbCtx& c, MbScratch& s, int stage) {
 
 // the whole macroblock, stages back to back (host emulation build)
 MBK_HD void encode_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch& s, int mbx, int mby) {
-  MbCtx c;
-  mb_ctx(c, p, f, mbx, mby);
+  mb_ctx(s.ctx, p, f, mbx, mby);
   int stage = p.is_idr ? MBS_I : MBS_A;
-  while (stage != MBS_DONE) stage = mb_run_stage(c, s, stage);
+  while (stage != MBS_DONE) stage = mb_run_stage(s.ctx, s, stage);
 }
 
 }  // namespace mbk

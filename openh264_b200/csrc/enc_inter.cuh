@@ -21,13 +21,6 @@ namespace mbk {
 // (g_kuiCache30ScanIdx, common_tables.cpp): cache index of 4x4 block k (coding order)
 MBK_HD int cache30(int k) { return 7 + blk_y(k) * 6 + blk_x(k); }
 
-struct MeState {            // the parts of SWelsME the later stages need
-  int mv_x, mv_y;           // quarter-pel
-  int mvp_x, mvp_y;
-  uint32_t sad_cost, satd_cost;
-  int satd;                 // raw SATD at the integer position (uSadPredISatd.uiSatd)
-  const uint8_t* ref;       // integer-position block in the reference plane
-};
 
 MBK_HD int median3(int a, int b, int c) {
   const int mn = a < b ? a : b, mx = a < b ? b : a;
@@ -291,10 +284,13 @@ MBK_FN void me_partition(const MbCtx& c, MbScratch& s, int blk_size, int ox, int
   in.calc_satd = true;
   MeOut o;
   warp_me_search(in, o);
-  st->mv_x = o.mv_x; st->mv_y = o.mv_y; st->mvp_x = mvp_x; st->mvp_y = mvp_y;
-  st->sad_cost = o.sad_cost; st->satd_cost = o.satd_cost;
-  st->satd = (int)o.satd_cost - mvd_cost(c.lambda, o.mv_x - mvp_x, o.mv_y - mvp_y);
-  st->ref = o.ref_best;
+  if (lane_id() == 0) {                    // st lives in the scratch: one writer
+    st->mv_x = o.mv_x; st->mv_y = o.mv_y; st->mvp_x = mvp_x; st->mvp_y = mvp_y;
+    st->sad_cost = o.sad_cost; st->satd_cost = o.satd_cost;
+    st->satd = (int)o.satd_cost - mvd_cost(c.lambda, o.mv_x - mvp_x, o.mv_y - mvp_y);
+    st->ref = o.ref_best;
+  }
+  warp_sync();
 }
 
 // ---- fractional refinement (MeRefineFracPixel, md.cpp:575) ------------------------------------------------------
@@ -307,20 +303,22 @@ MBK_FN void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy,
   const int px = st->mvp_x, py = st->mvp_y;
   int best = st->satd + mvd_cost(c.lambda, st->mv_x - px, st->mv_y - py);
   uint8_t* tmp = s.me_buf;
+  const int mv0x = st->mv_x, mv0y = st->mv_y;
+  const uint8_t* ref0 = st->ref;
   auto eval = [&](int mvx, int mvy) {
-    // st->ref sits at the integer MV; candidate integer part relative to it
-    const int dx = (mvx >> 2) - (st->mv_x >> 2), dy = (mvy >> 2) - (st->mv_y >> 2);
-    warp_mc_luma(st->ref + dy * rs + dx, rs, tmp, 32, mvx, mvy, w, h);
+    // ref0 sits at the integer MV; candidate integer part relative to it
+    const int dx = (mvx >> 2) - (mv0x >> 2), dy = (mvy >> 2) - (mv0y >> 2);
+    warp_mc_luma(ref0 + dy * rs + dx, rs, tmp, 32, mvx, mvy, w, h);
     warp_sync();
     const int cost = warp_satd(enc, 16, tmp, 32, lw, lh) + mvd_cost(c.lambda, mvx - px, mvy - py);
     warp_sync();
     return cost;
   };
-  int hx = st->mv_x, hy = st->mv_y;
+  int hx = mv0x, hy = mv0y;
   {
     int bi = -1;
     for (int i = 0; i < 4; i++) {      // up, down, left, right by half a sample
-      const int cst = eval(st->mv_x + (i == 2 ? -2 : i == 3 ? 2 : 0), st->mv_y + (i == 0 ? -2 : i == 1 ? 2 : 0));
+      const int cst = eval(mv0x + (i == 2 ? -2 : i == 3 ? 2 : 0), mv0y + (i == 0 ? -2 : i == 1 ? 2 : 0));
       if (cst < best) { best = cst; bi = i; }
     }
     if (bi >= 0) { hx += (bi == 2 ? -2 : bi == 3 ? 2 : 0); hy += (bi == 0 ? -2 : bi == 1 ? 2 : 0); }
@@ -336,12 +334,12 @@ MBK_FN void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy,
   }
   // final prediction
   {
-    const int dx = (fx >> 2) - (st->mv_x >> 2), dy = (fy >> 2) - (st->mv_y >> 2);
-    warp_mc_luma(st->ref + dy * rs + dx, rs, dst, 16, fx, fy, w, h);
+    const int dx = (fx >> 2) - (mv0x >> 2), dy = (fy >> 2) - (mv0y >> 2);
+    warp_mc_luma(ref0 + dy * rs + dx, rs, dst, 16, fx, fy, w, h);
     warp_sync();
   }
-  st->mv_x = fx; st->mv_y = fy;
-  st->satd_cost = (uint32_t)best;
+  if (lane_id() == 0) { st->mv_x = fx; st->mv_y = fy; st->satd_cost = (uint32_t)best; }
+  warp_sync();
 }
 
 // ---- luma residual of an inter MB (WelsEncInterY, svc_encode_mb.cpp:180) -------------------------------------------
@@ -494,21 +492,31 @@ MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
   const int mbw = c.p.mb_w, idx = c.mby * mbw + c.mbx;
   const bool is_skip = s.st.is_skip != 0;
   int cost_luma = s.st.cost_luma, cost_skip_mb = s.st.cost_skip_mb, p16_mvx = s.st.p16_mvx, p16_mvy = s.st.p16_mvy;
-  MeState me16, me16x8[2], me8x16[2], me8x8[4];
+  MeState& me16 = s.me[0];
+  MeState* me16x8 = &s.me[1];
+  MeState* me8x16 = &s.me[3];
+  MeState* me8x8 = &s.me[5];
   int final_type = MBT_P16x16;
   int sad_pred_mb = 0;
   if (!is_skip) {
     sad_pred_mb = predict_sad(s);
     // step 2: P16x16 (WelsMdP16x16 :978)
-    int16_t mvc[5][2];
-    int n = 0;
-    mvc[n][0] = 0; mvc[n][1] = 0; n++;                                    // sMvBase
-    if (c.nb & NB_LEFT) { mvc[n][0] = s.nbi[3].p16x16_mv[0]; mvc[n][1] = s.nbi[3].p16x16_mv[1]; n++; }
-    if (c.nb & NB_TOP) { mvc[n][0] = s.nbi[1].p16x16_mv[0]; mvc[n][1] = s.nbi[1].p16x16_mv[1]; n++; }
-    if (c.p.ref_is_p) {
-      if (c.mbx < mbw - 1) { mvc[n][0] = c.f.ref_info[idx + 1].mv16[0]; mvc[n][1] = c.f.ref_info[idx + 1].mv16[1]; n++; }
-      if (c.mby < c.p.mb_h - 1) { mvc[n][0] = c.f.ref_info[idx + mbw].mv16[0]; mvc[n][1] = c.f.ref_info[idx + mbw].mv16[1]; n++; }
+    int16_t (*mvc)[2] = s.mvcand;
+    int n = 1;                                                            // [0] = sMvBase (0,0)
+    n += (c.nb & NB_LEFT) ? 1 : 0;
+    n += (c.nb & NB_TOP) ? 1 : 0;
+    if (c.p.ref_is_p) { n += c.mbx < mbw - 1 ? 1 : 0; n += c.mby < c.p.mb_h - 1 ? 1 : 0; }
+    if (lane_id() == 0) {
+      int k = 0;
+      mvc[k][0] = 0; mvc[k][1] = 0; k++;
+      if (c.nb & NB_LEFT) { mvc[k][0] = s.nbi[3].p16x16_mv[0]; mvc[k][1] = s.nbi[3].p16x16_mv[1]; k++; }
+      if (c.nb & NB_TOP) { mvc[k][0] = s.nbi[1].p16x16_mv[0]; mvc[k][1] = s.nbi[1].p16x16_mv[1]; k++; }
+      if (c.p.ref_is_p) {
+        if (c.mbx < mbw - 1) { mvc[k][0] = c.f.ref_info[idx + 1].mv16[0]; mvc[k][1] = c.f.ref_info[idx + 1].mv16[1]; k++; }
+        if (c.mby < c.p.mb_h - 1) { mvc[k][0] = c.f.ref_info[idx + mbw].mv16[0]; mvc[k][1] = c.f.ref_info[idx + mbw].mv16[1]; k++; }
+      }
     }
+    warp_sync();
     int px, py;
     pred_mv(s, 0, 4, 0, &px, &py);
     me_partition(c, s, BLK_16x16, 0, 0, px, py, (uint32_t)sad_pred_mb, n, &mvc[0][0], &me16);
@@ -583,7 +591,7 @@ MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
       cost_skip_mb = warp_sad(s.cur_y, 16, pl, 16, 4, 4) + warp_sad(s.cur_c, 8, pc, 8, 3, 3) + warp_sad(s.cur_c + 64, 8, pc + 64, 8, 3, 3);
     } else if (final_type == MBT_P16x8) {
       for (int i = 0; i < 2; i++) {
-        pred_16x8_mv(s, 8 * i, 0, &me16x8[i].mvp_x, &me16x8[i].mvp_y);
+        { int qx, qy; pred_16x8_mv(s, 8 * i, 0, &qx, &qy); if (lane_id() == 0) { me16x8[i].mvp_x = qx; me16x8[i].mvp_y = qy; } warp_sync(); }
         me_refine(c, s, &me16x8[i], 0, 8 * i, 16, 8, pl + 128 * i);
         cache_set(s, 8 * i, 4, 2, me16x8[i].mv_x, me16x8[i].mv_y);
         mb_mv_set(s, 8 * i, 4, 2, me16x8[i].mv_x, me16x8[i].mv_y);
@@ -593,7 +601,7 @@ MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
       }
     } else if (final_type == MBT_P8x16) {
       for (int i = 0; i < 2; i++) {
-        pred_8x16_mv(s, 4 * i, 0, &me8x16[i].mvp_x, &me8x16[i].mvp_y);
+        { int qx, qy; pred_8x16_mv(s, 4 * i, 0, &qx, &qy); if (lane_id() == 0) { me8x16[i].mvp_x = qx; me8x16[i].mvp_y = qy; } warp_sync(); }
         me_refine(c, s, &me8x16[i], 8 * i, 0, 8, 16, pl + 8 * i);
         cache_set(s, 4 * i, 2, 4, me8x16[i].mv_x, me8x16[i].mv_y);
         mb_mv_set(s, 4 * i, 2, 4, me8x16[i].mv_x, me8x16[i].mv_y);
@@ -606,7 +614,7 @@ MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
       warp_sync();
       for (int i = 0; i < 4; i++) {
         const int ox = (i & 1) * 8, oy = (i >> 1) * 8;
-        pred_mv(s, 4 * i, 2, 0, &me8x8[i].mvp_x, &me8x8[i].mvp_y);
+        { int qx, qy; pred_mv(s, 4 * i, 2, 0, &qx, &qy); if (lane_id() == 0) { me8x8[i].mvp_x = qx; me8x8[i].mvp_y = qy; } warp_sync(); }
         me_refine(c, s, &me8x8[i], ox, oy, 8, 8, pl + oy * 16 + ox);
         cache_set(s, 4 * i, 2, 2, me8x8[i].mv_x, me8x8[i].mv_y);
         mb_mv_set(s, 4 * i, 2, 2, me8x8[i].mv_x, me8x8[i].mv_y);

@@ -24,7 +24,7 @@ __constant__ uint8_t c_tc0[52][3];
 }  // namespace mbk
 
 #ifndef ENC_WPC
-#define ENC_WPC 16         // warps per CTA of the macroblock kernels (one CTA per SM at 128 registers)
+#define ENC_WPC 24         // warps per CTA of the macroblock kernels (one CTA per SM at 80 registers)
 #endif
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
@@ -261,10 +261,9 @@ __global__ void __launch_bounds__(32 * ENC_WPC, ENC_MIN_CTAS) k_encode_mbs(const
   MbScratch& s = reinterpret_cast<MbScratch*>(smem)[threadIdx.x >> 5];
   run_stages(sf, n_streams, q, s, stats & 1, [&](const StreamFrame& F, int x, int y, int stage) {
     const long long t0 = (stats & 1) ? clock64() : 0;
-    MbCtx c;
-    mb_ctx(c, F.p, F.f, x, y);
-    int next = mb_run_stage(c, s, stage);
-    if (stats & 2) while (next != MBS_DONE) next = mb_run_stage(c, s, next);      // debugging: all stages in one task
+    mb_ctx(s.ctx, F.p, F.f, x, y);
+    int next = mb_run_stage(s.ctx, s, stage);
+    if (stats & 2) while (next != MBS_DONE) next = mb_run_stage(s.ctx, s, next);      // debugging: all stages in one task
     if ((stats & 1) && (threadIdx.x & 31) == 0) {          // cycles and count per stage
       atomicAdd(&g_enc_stats[2 * stage], (unsigned long long)(clock64() - t0));
       atomicAdd(&g_enc_stats[2 * stage + 1], 1ull);

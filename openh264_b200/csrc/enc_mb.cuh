@@ -6,6 +6,21 @@
 
 namespace mbk {
 
+struct MbCtx {
+  EncFrameParams p;
+  EncFramePtrs f;
+  int mbx, mby, nb;             // position, neighbour availability (NB_*)
+  int qp, qp_c, lambda;
+};
+
+struct MeState {            // the parts of SWelsME the later steps of a partition need
+  int mv_x, mv_y;           // quarter-pel
+  int mvp_x, mvp_y;
+  uint32_t sad_cost, satd_cost;
+  int satd;                 // raw SATD at the integer position (uSadPredISatd.uiSatd)
+  const uint8_t* ref;       // integer-position block in the reference plane
+};
+
 // values of a P macroblock that cross a stage boundary (enc_inter.cuh: inter_stage_a/b/c); warp-uniform
 struct InterState {
   int32_t is_skip, cost_luma, cost_skip_mb, p16_mvx, p16_mvy, final_type, cost16, bb;
@@ -36,6 +51,11 @@ struct alignas(16) MbScratch {
   int32_t nb_skip_sad[4];       // neighbours' skip SAD of THIS picture (pMbSkipSad)
   int32_t red[32];              // small scratch
   InterState st;
+  // kept in the scratch rather than on the per-thread stack: the stack of 512 threads does not fit L1 next to the
+  // scratches, and these are touched all the time (profiles/r01_encode_stages.txt)
+  MbCtx ctx;                    // frame parameters / pointers / position of the macroblock being coded
+  MeState me[9];                // 16x16, 16x8 x2, 8x16 x2, 8x8 x4 (warp-uniform; written by lane 0)
+  int16_t mvcand[5][2];         // 16x16 search candidates
   uint32_t t_last;              // phase timer (profiling builds only)
 };
 
@@ -49,12 +69,6 @@ __device__ __forceinline__ void phase_mark(MbScratch& s, int i) {
 MBK_HD void phase_mark(MbScratch&, int) {}
 #endif
 
-struct MbCtx {
-  EncFrameParams p;
-  EncFramePtrs f;
-  int mbx, mby, nb;             // position, neighbour availability (NB_*)
-  int qp, qp_c, lambda;
-};
 
 // position of 4x4 block k (coding / z order) in units of 4 pixels
 MBK_HD int blk_x(int k) { return (k & 1) | ((k >> 1) & 2); }

@@ -294,34 +294,86 @@ MBK_FN void me_partition(const MbCtx& c, MbScratch& s, int blk_size, int ox, int
 }
 
 // ---- fractional refinement (MeRefineFracPixel, md.cpp:575) ------------------------------------------------------
-// candidate cost = SATD(enc, McLuma(ref, mv)) + mvd cost, visited in the reference's order with strict '<';
-// the winning prediction is left in dst (stride 16).
+// candidate cost = SATD(enc, prediction(mv)) + mvd cost, visited in the reference's order with strict '<'; the
+// winning prediction is left in dst (stride 16).
+// Like the reference, the half-sample planes of the partition are filtered ONCE: the (w+6) x (h+6) integer window
+// around the matched block is staged in shared memory, H / V (and C, only if a half-sample point won) are computed
+// from it, and every quarter-sample prediction is the rounded average of two plane samples (H.264 8.4.2.2.1; equal
+// to McLuma_c for every phase; the bitstream tests against the reference cover it).  Plane coordinates are relative to
+// the integer-sample position of the block: G covers [-3, w+3) x [-3, h+3), H/V/C start at (-1, -1); stride 32.
+struct QpelPlanes { const uint8_t* g; const uint8_t* hh; const uint8_t* vv; const uint8_t* cc; };
+enum { QP_STRIDE = 32 };
+// the two plane samples whose average is the prediction at quarter-sample offset (dx, dy) in [-3, 3]^2
+MBK_HD void qpel_pair(const QpelPlanes& q, int dx, int dy, const uint8_t** pa, const uint8_t** pb) {
+  const int ix = dx < 0 ? -1 : 0, iy = dy < 0 ? -1 : 0, fx = dx & 3, fy = dy & 3;
+  const uint8_t* G = q.g + (iy + 3) * QP_STRIDE + (ix + 3);       // integer sample (ix, iy)
+  const uint8_t* H = q.hh + (iy + 1) * QP_STRIDE + (ix + 1);
+  const uint8_t* V = q.vv + (iy + 1) * QP_STRIDE + (ix + 1);
+  const uint8_t* C = q.cc + (iy + 1) * QP_STRIDE + (ix + 1);
+  const int x3 = fx == 3 ? 1 : 0, y3 = fy == 3 ? QP_STRIDE : 0;
+  if ((fx | fy) == 0) { *pa = G; *pb = G; }
+  else if (fy == 0) { *pa = H; *pb = fx == 2 ? H : G + x3; }
+  else if (fx == 0) { *pa = V; *pb = fy == 2 ? V : G + y3; }
+  else if (fx == 2 && fy == 2) { *pa = C; *pb = C; }
+  else if (fx == 2) { *pa = H + y3; *pb = C; }
+  else if (fy == 2) { *pa = V + x3; *pb = C; }
+  else { *pa = H + y3; *pb = V + x3; }
+}
+
 MBK_FN void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy, int w, int h, uint8_t* dst) {
   const int lw = w == 16 ? 4 : 3, lh = h == 16 ? 4 : 3;
   const uint8_t* enc = s.cur_y + oy * 16 + ox;
   const int rs = c.p.rec_stride_y;
   const int px = st->mvp_x, py = st->mvp_y;
-  int best = st->satd + mvd_cost(c.lambda, st->mv_x - px, st->mv_y - py);
-  uint8_t* tmp = s.me_buf;
   const int mv0x = st->mv_x, mv0y = st->mv_y;
+  int best = st->satd + mvd_cost(c.lambda, mv0x - px, mv0y - py);
   const uint8_t* ref0 = st->ref;
-  auto eval = [&](int mvx, int mvy) {
-    // ref0 sits at the integer MV; candidate integer part relative to it
-    const int dx = (mvx >> 2) - (mv0x >> 2), dy = (mvy >> 2) - (mv0y >> 2);
-    warp_mc_luma(ref0 + dy * rs + dx, rs, tmp, 32, mvx, mvy, w, h);
-    warp_sync();
-    const int cost = warp_satd(enc, 16, tmp, 32, lw, lh) + mvd_cost(c.lambda, mvx - px, mvy - py);
-    warp_sync();
-    return cost;
+  // ---- stage the integer window (the coefficient buffer is free until the residual is coded) ----
+  uint8_t* win = reinterpret_cast<uint8_t*>(s.coef);
+  static_assert(sizeof(s.coef) >= 22 * QP_STRIDE, "window aliases the coefficient buffer");
+  const int ww = w + 6, wh = h + 6, wq = (ww + 3) >> 2;            // words per row (the padded reference allows the overshoot)
+  for (int i = lane_id(); i < wq * wh; i += MBK_WS) {
+    const int r = i / wq, q4 = (i - r * wq) << 2;
+    const uint32_t v = ld4u(ref0 + (ptrdiff_t)(r - 3) * rs + (q4 - 3));
+    uint8_t* d = win + r * QP_STRIDE + q4;
+    d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24);
+  }
+  warp_sync();
+  uint8_t* ph = s.qplane[0];
+  uint8_t* pv = s.qplane[1];
+  uint8_t* pc = s.qplane[2];
+  // H(X, Y): X in [-1, w-1], Y in [-1, h];  V(X, Y): X in [-1, w], Y in [-1, h-1]
+  for (int i = lane_id(); i < (w + 1) * (h + 2); i += MBK_WS) {
+    const int r = i / (w + 1), x = i - r * (w + 1);
+    ph[r * QP_STRIDE + x] = (uint8_t)half_h(win + (r + 2) * QP_STRIDE + (x + 2));
+  }
+  for (int i = lane_id(); i < (w + 2) * (h + 1); i += MBK_WS) {
+    const int r = i / (w + 2), x = i - r * (w + 2);
+    pv[r * QP_STRIDE + x] = (uint8_t)half_v(win + (r + 2) * QP_STRIDE + (x + 2), QP_STRIDE);
+  }
+  warp_sync();
+  QpelPlanes q;
+  q.g = win; q.hh = ph; q.vv = pv; q.cc = pc;
+  auto eval = [&](int dx, int dy) {
+    const uint8_t *a, *b;
+    qpel_pair(q, dx, dy, &a, &b);
+    return warp_satd_avg(enc, 16, a, b, QP_STRIDE, lw, lh) + mvd_cost(c.lambda, mv0x + dx - px, mv0y + dy - py);
   };
-  int hx = mv0x, hy = mv0y;
+  int hx = 0, hy = 0;                    // offsets from the integer vector
   {
     int bi = -1;
     for (int i = 0; i < 4; i++) {      // up, down, left, right by half a sample
-      const int cst = eval(mv0x + (i == 2 ? -2 : i == 3 ? 2 : 0), mv0y + (i == 0 ? -2 : i == 1 ? 2 : 0));
+      const int cst = eval(i == 2 ? -2 : i == 3 ? 2 : 0, i == 0 ? -2 : i == 1 ? 2 : 0);
       if (cst < best) { best = cst; bi = i; }
     }
-    if (bi >= 0) { hx += (bi == 2 ? -2 : bi == 3 ? 2 : 0); hy += (bi == 0 ? -2 : bi == 1 ? 2 : 0); }
+    if (bi >= 0) { hx = bi == 2 ? -2 : bi == 3 ? 2 : 0; hy = bi == 0 ? -2 : bi == 1 ? 2 : 0; }
+  }
+  if (hx | hy) {                         // quarter positions around a half-sample point need the centre plane
+    for (int i = lane_id(); i < (w + 1) * (h + 1); i += MBK_WS) {
+      const int r = i / (w + 1), x = i - r * (w + 1);
+      pc[r * QP_STRIDE + x] = (uint8_t)half_c(win + (r + 2) * QP_STRIDE + (x + 2), QP_STRIDE);
+    }
+    warp_sync();
   }
   int fx = hx, fy = hy;
   {
@@ -334,11 +386,18 @@ MBK_FN void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy,
   }
   // final prediction
   {
-    const int dx = (fx >> 2) - (mv0x >> 2), dy = (fy >> 2) - (mv0y >> 2);
-    warp_mc_luma(ref0 + dy * rs + dx, rs, dst, 16, fx, fy, w, h);
+    const uint8_t *a, *b;
+    qpel_pair(q, fx, fy, &a, &b);
+    const int gsh = lw - 2;
+    for (int g = lane_id(); g < (w * h) >> 2; g += MBK_WS) {
+      const int y = g >> gsh, x = (g & ((1 << gsh) - 1)) << 2;
+      const uint32_t v = vavgu4(ld4u(a + y * QP_STRIDE + x), ld4u(b + y * QP_STRIDE + x));
+      uint8_t* d = dst + y * 16 + x;
+      d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24);
+    }
     warp_sync();
   }
-  if (lane_id() == 0) { st->mv_x = fx; st->mv_y = fy; st->satd_cost = (uint32_t)best; }
+  if (lane_id() == 0) { st->mv_x = mv0x + fx; st->mv_y = mv0y + fy; st->satd_cost = (uint32_t)best; }
   warp_sync();
 }
 

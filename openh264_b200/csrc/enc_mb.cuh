@@ -35,7 +35,8 @@ struct alignas(16) MbScratch {
   uint8_t pred_y[2][256];       // luma prediction ping-pong (pMemPredMb)
   uint8_t pred_c[2][128];       // chroma prediction ping-pong (Cb, Cr)
   uint8_t skip_pred[384];       // P-skip prediction (pSkipMb): Y 256, Cb 64, Cr 64
-  uint8_t me_buf[17 * 32];      // fractional-refinement candidate, stride 32 (one of pBufferInterPredMe's four)
+  uint8_t qplane[3][18 * 32];   // fractional refinement: half-sample planes H, V, C of the partition, stride 32
+                                // (pBufferInterPredMe, md.cpp:505-510)
   int16_t coef[384];            // pCoeffLevel: transform coefficients (coding order, 16 per 4x4)
   int16_t dc16[16];
   int8_t  i4m[25];              // intra4x4 mode cache: (by+1)*5+(bx+1), -1 = unavailable

@@ -67,6 +67,16 @@ MBK_HD uint32_t vsadu4(uint32_t a, uint32_t b) {
   return s;
 #endif
 }
+// per-byte rounded average (a + b + 1) >> 1 of packed bytes
+MBK_HD uint32_t vavgu4(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __vavgu4(a, b);
+#else
+  uint32_t r = 0;
+  for (int i = 0; i < 4; i++) r |= ((((a >> (8 * i)) & 0xff) + ((b >> (8 * i)) & 0xff) + 1) >> 1) << (8 * i);
+  return r;
+#endif
+}
 MBK_HD int clz32(uint32_t v) {
 #ifdef __CUDA_ARCH__
   return __clz((int)v);

@@ -60,6 +60,37 @@ MBK_HD int satd4x4_thread(const uint8_t* a, int sa, const uint8_t* b, int sb) {
   return (sum + 1) >> 1;
 }
 
+// as satd4x4_thread, the prediction being the rounded average of two byte planes of stride sp
+MBK_HD int satd4x4_avg_thread(const uint8_t* a, int sa, const uint8_t* p0, const uint8_t* p1, int sp) {
+  int t[4][4];
+#pragma unroll
+  for (int y = 0; y < 4; y++) {
+    const uint32_t wa = ld4u(a + y * sa), wb = vavgu4(ld4u(p0 + y * sp), ld4u(p1 + y * sp));
+    const int d0 = (int)(wa & 0xff) - (int)(wb & 0xff), d1 = (int)((wa >> 8) & 0xff) - (int)((wb >> 8) & 0xff);
+    const int d2 = (int)((wa >> 16) & 0xff) - (int)((wb >> 16) & 0xff), d3 = (int)(wa >> 24) - (int)(wb >> 24);
+    const int e0 = d0 + d2, e1 = d1 + d3, e2 = d0 - d2, e3 = d1 - d3;
+    t[y][0] = e0 + e1; t[y][1] = e2 + e3; t[y][2] = e2 - e3; t[y][3] = e0 - e1;
+  }
+  int sum = 0;
+#pragma unroll
+  for (int x = 0; x < 4; x++) {
+    const int e0 = t[0][x] + t[2][x], e1 = t[1][x] + t[3][x], e2 = t[0][x] - t[2][x], e3 = t[1][x] - t[3][x];
+    sum += iabs(e0 + e1) + iabs(e2 + e3) + iabs(e2 - e3) + iabs(e0 - e1);
+  }
+  return (sum + 1) >> 1;
+}
+MBK_FN int warp_satd_avg(const uint8_t* a, int sa, const uint8_t* p0, const uint8_t* p1, int sp, int lw, int lh) {
+  const int lbx = lw - 2;
+  const int nblk = 1 << (lbx + lh - 2);
+  int s = 0;
+  for (int l = lane_id(); l < nblk; l += MBK_WS) {
+    const int by = l >> lbx, bx = l & ((1 << lbx) - 1);
+    const int o = 4 * by * sp + 4 * bx;
+    s += satd4x4_avg_thread(a + 4 * by * sa + 4 * bx, sa, p0 + o, p1 + o, sp);
+  }
+  return warp_sum(s);
+}
+
 // SATD of a block: one lane per 4x4 sub-block (16 lanes busy for 16x16), warp total by REDUX.
 MBK_FN int warp_satd(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh) {
   const int lbx = lw - 2;                    // log2(4x4 blocks per row)

@@ -155,6 +155,57 @@ def cpu_baseline_sample(seconds_budget=15.0):
                       "C-only build (USE_ASM=No: nasm absent)" % n}
 
 
+def ncu_traffic(kernel):
+    """per-launch DRAM bytes of `kernel` from the committed ncu capture (profiles/ncu_traffic.json), or None"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(kernel)
+    except Exception:
+        return None
+
+
+def mc_sad_roofline(L, local, peak):
+    """BASELINE metric 2: the MC+SAD unit (b2h264_k_mc_sad, layer 1) against the HBM roofline.  64 stacked 1080p
+    planes (cur + padded ref = 302 MB, larger than L2), one candidate per macroblock; algorithmic bytes per MB =
+    256 cur + 256 ref + 4 vector + 4 cost."""
+    import torch
+    from openh264_b200.binding import check
+    S, stride, rows_per = 64, 2048, 1152                      # 1088 + 2 x 32 rows of padding per picture
+    g = torch.Generator(device="cuda"); g.manual_seed(264)
+    cur = torch.randint(0, 256, (S * rows_per, stride), dtype=torch.uint8, device="cuda", generator=g)
+    ref = torch.randint(0, 256, (S * rows_per, stride), dtype=torch.uint8, device="cuda", generator=g)
+    mbw, mbh = 120, (S * rows_per) // 16 - 4                  # skip two MB rows at either end: the halo stays inside
+    o0 = 32 * stride + 32
+    n = mbw * mbh
+    out = {}
+    st = torch.cuda.current_stream().cuda_stream
+    for name, frac in (("integer", False), ("quarter", True)):
+        mv = torch.randint(-8, 9, (n, 1, 2), dtype=torch.int16, device="cuda", generator=g) * 4
+        if frac:
+            mv += torch.randint(0, 4, (n, 1, 2), dtype=torch.int16, device="cuda", generator=g)
+        cost = torch.empty((n, 1), dtype=torch.int32, device="cuda")
+        run = lambda: check(L.b2h264_k_mc_sad(cur.data_ptr() + o0, stride, ref.data_ptr() + o0, stride, mbw, mbh,
+                                              mv.data_ptr(), 1, cost.data_ptr(), st))
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 10
+        e0.record()
+        for _ in range(iters):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        sec = e0.elapsed_time(e1) / 1e3 / iters
+        gbs = n * 520 / sec / 1e9
+        out[name] = {"achieved": gbs, "frac": gbs / peak, "us_per_launch": sec * 1e6, "mb_per_launch": n}
+    t = ncu_traffic("k_mc_sad_tma")
+    return {"kernel": "k_mc_sad_tma (b2h264_k_mc_sad: 8x4-MB tiles staged by TMA bulk tensor copies)", "bound": "hbm", "unit": "GB/s",
+            "traffic": t["dram_bytes"] if t and t.get("mb_per_launch") == n else None,
+            "peak": peak, "alg_bytes_per_mb": 520, "candidates_per_mb": 1, "achieved": out["integer"]["achieved"],
+            "frac": out["integer"]["frac"], "integer_mv": out["integer"], "quarter_pel_mv": out["quarter"],
+            "note": "64 stacked padded 1080p planes per launch (302 MB of pixels, larger than L2)"}
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -278,7 +329,9 @@ def main():
             "gpu_launches": int(launches),
             "clocks": results["resident"]["clocks"],
             "roofline": {"bound": "hbm", "kernel": "k_encode_mbs (macroblock wavefront, all streams)", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (ncu_traffic("k_encode_mbs") or {}).get("dram_bytes") if S == (ncu_traffic("k_encode_mbs") or {}).get("streams") else None,
+                         "peak_source": peak_kind,
                          "note": "wavefront kernel is dependency/latency-bound by construction (SURVEY.md §8d); "
                                  "alg bytes = %d B/MB x %d MB/launch" % (ALG_BYTES_PER_MB, S * MBS_PER_FRAME)},
             "breakdown_ms_per_step": {"encode_kernel": k_enc * 1e3, "deblock_expand": k_dbk * 1e3, "host_entropy": ent * 1e3,
@@ -286,6 +339,8 @@ def main():
                                       "wall_e2e": results["e2e"]["wall"] / args.steps * 1e3},
             "bitstream_kbytes_per_frame": results["resident"]["bytes"] / (S * args.steps) / 1e3,
         }
+        if world == 1:
+            out["roofline_mc_sad"] = mc_sad_roofline(L, local, peak)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(out))

@@ -1,6 +1,9 @@
 // k_pixel.cu — batched pixel-domain kernels behind include/b2h264.h: SAD/SATD, sub-pel MC, deblocking
 // edge filters, border expansion, integer motion search, and the MC+SAD roofline unit.
 // One warp per job; 8 warps per CTA; grid sized to cover n jobs.
+#include <stdlib.h>
+#include <cuda.h>               // CUtensorMap (the encode entry point is fetched through the runtime)
+
 #include "b2h264_internal.h"
 #include "mbk_deblock.cuh"
 #include "mbk_mc.cuh"
@@ -185,6 +188,193 @@ __global__ void __launch_bounds__(256) k_mc_sad(const uint8_t* __restrict__ cur,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiled form of the MC + SAD unit (the one launched when the planes are 16-byte aligned): a CTA owns a tile of
+// 8 x 4 macroblocks (128 x 64 luma samples), one warp per macroblock column.  The CTA first stages the current tile and
+// the reference tile with its search halo ([-16, +144) x [-10, +75): 160 B x 85 rows) into shared memory with
+// 16-byte asynchronous copies (cp.async / LDGSTS: whole 128-byte lines, every reference byte of the tile is read
+// from HBM once and the halo rows / columns shared with the neighbouring tiles come from L2), then every warp
+// evaluates the candidates of its column of 4 macroblocks from shared memory.  8 warps per CTA, 8 CTAs per SM:
+// 8 x 21.6 KB of copies in flight per SM hide the HBM latency while other CTAs compute.  Algorithmic HBM bytes per macroblock: 256 (cur) + 256 (ref) + 8k (vectors, costs).
+#define MCT_W 8
+#define MCT_H 4
+#define MCT_HALO_X 16                       // left/right halo in bytes (>= R + 3, multiple of 16)
+#define MCT_TOP (MCS_R + 2)                 // rows above the tile
+#define MCT_ROWS (16 * MCT_H + MCS_R + 2 + MCS_R + 3)
+#define MCT_PITCH (16 * MCT_W + 2 * MCT_HALO_X)
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__global__ void __launch_bounds__(32 * MCT_W, 8)
+k_mc_sad_tiled(const uint8_t* __restrict__ cur, int cs, const uint8_t* __restrict__ ref, int rs, int mb_w, int mb_h,
+               const int16_t* __restrict__ mv, int k, int32_t* __restrict__ cost) {
+  __shared__ __align__(16) uint8_t t_cur[16 * MCT_H][16 * MCT_W];
+  __shared__ __align__(16) uint8_t t_ref[MCT_ROWS][MCT_PITCH];
+  const int mbx0 = blockIdx.x * MCT_W, mby0 = blockIdx.y * MCT_H;
+  const int W = mb_w * 16, H = mb_h * 16;
+  // ---- stage (16-byte chunks; chunks no macroblock of the picture can touch are skipped) ----
+  constexpr int kCurChunks = 16 * MCT_H * MCT_W, kRefCols = MCT_PITCH / 16, kRefChunks = MCT_ROWS * kRefCols;
+  for (int i = threadIdx.x; i < kCurChunks + kRefChunks; i += blockDim.x) {
+    if (i < kCurChunks) {
+      const int r = i / MCT_W, c16 = (i - r * MCT_W) * 16;
+      const int y = mby0 * 16 + r, x = mbx0 * 16 + c16;
+      if (y < H && x < W) cp_async16(&t_cur[r][c16], cur + (size_t)y * cs + x);
+    } else {
+      const int j = i - kCurChunks, r = j / kRefCols, c16 = (j - r * kRefCols) * 16;
+      const int y = mby0 * 16 - MCT_TOP + r, x = mbx0 * 16 - MCT_HALO_X + c16;
+      if (y < H + MCS_R + 3 && x < W + MCT_HALO_X) cp_async16(&t_ref[r][c16], ref + (ptrdiff_t)y * rs + x);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // while the copies fly: lane ty fetches the first vector of macroblock (tx, ty) of this warp's column
+  const int tx = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int mbx = mbx0 + tx;
+  int first_mv = 0;
+  if (l < MCT_H && mbx < mb_w && mby0 + l < mb_h)
+    first_mv = __ldg(reinterpret_cast<const int*>(mv + (size_t)((mby0 + l) * mb_w + mbx) * k * 2));   // (mvx, mvy) as one word
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // ---- one warp per macroblock column of the tile ----
+  if (mbx >= mb_w) return;
+  for (int ty = 0; ty < MCT_H; ty++) {
+  const int mv0 = __shfl_sync(0xffffffffu, first_mv, ty);
+  const int mby = mby0 + ty;
+  if (mby >= mb_h) break;
+  const int m = mby * mb_w + mbx;
+  const uint8_t* cm = &t_cur[16 * ty][16 * tx];
+  const uint8_t* w0 = &t_ref[MCT_TOP + 16 * ty][MCT_HALO_X + 16 * tx];        // pixel (0,0) of the co-located block
+  for (int c = 0; c < k; c++) {
+    const int mvw = c == 0 ? mv0 : __ldg(reinterpret_cast<const int*>(mv + (size_t)(m * k + c) * 2));
+    const int mvx = (int16_t)(mvw & 0xffff), mvy = mvw >> 16;
+    const uint8_t* p = w0 + (mvy >> 2) * MCT_PITCH + (mvx >> 2);
+    const int fx = mvx & 3, fy = mvy & 3;
+    int s = 0;
+    if ((fx | fy) == 0) {                    // integer vector: packed SAD, 2 words per lane
+#pragma unroll
+      for (int i = l; i < 64; i += 32) {
+        const int y = i >> 2, x = (i & 3) << 2;
+        s += vsadu4(*reinterpret_cast<const uint32_t*>(cm + y * (16 * MCT_W) + x), ld4u(p + y * MCT_PITCH + x));
+      }
+    } else {
+#pragma unroll 2
+      for (int i = l; i < 256; i += 32) {
+        const int y = i >> 4, x = i & 15;
+        s += iabs((int)cm[y * (16 * MCT_W) + x] - luma_qpel_sample(p + y * MCT_PITCH + x, MCT_PITCH, fx, fy));
+      }
+    }
+    s = warp_sum(s);
+    if (l == 0) cost[(size_t)m * k + c] = s;
+  }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA form of the tiled unit (sm_100a: cp.async.bulk.tensor + mbarrier complete_tx).  Same tile geometry; ONE
+// thread issues two bulk tensor copies (current tile 128 x 64, reference tile + halo 160 x 85) and every warp
+// waits on the mbarrier: no per-thread address arithmetic for staging, out-of-picture parts are zero-filled by
+// the copy engine.  ncu on the cp.async form showed the SMs issue-bound (89 % issue-active, 187 warp instructions
+// per macroblock, a third of them staging arithmetic): profiles/r01_mc_sad_ncu.txt.
+__global__ void __launch_bounds__(32 * MCT_W, 8)
+k_mc_sad_tma(const __grid_constant__ CUtensorMap tm_cur, const __grid_constant__ CUtensorMap tm_ref, int mb_w, int mb_h,
+             const int16_t* __restrict__ mv, int k, int32_t* __restrict__ cost) {
+  __shared__ __align__(128) uint8_t t_cur[16 * MCT_H][16 * MCT_W];
+  __shared__ __align__(128) uint8_t t_ref[MCT_ROWS][MCT_PITCH];
+  __shared__ __align__(8) unsigned long long bar;
+  const int mbx0 = blockIdx.x * MCT_W, mby0 = blockIdx.y * MCT_H;
+  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    constexpr uint32_t kBytes = sizeof(t_cur) + sizeof(t_ref);
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar_a), "r"(kBytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(&t_cur[0][0])), "l"(&tm_cur), "r"(mbx0 * 16), "r"(mby0 * 16), "r"(bar_a)
+                 : "memory");
+    // the reference map starts at the padded origin (-32, -32)
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(&t_ref[0][0])), "l"(&tm_ref), "r"(mbx0 * 16 - MCT_HALO_X + 32),
+                   "r"(mby0 * 16 - MCT_TOP + 32), "r"(bar_a)
+                 : "memory");
+  }
+  // while the copies fly: lane ty fetches the first vector of macroblock (tx, ty) of this warp's column
+  const int tx = threadIdx.x >> 5, l = threadIdx.x & 31;
+  const int mbx = mbx0 + tx;
+  int first_mv = 0;
+  if (l < MCT_H && mbx < mb_w && mby0 + l < mb_h)
+    first_mv = __ldg(reinterpret_cast<const int*>(mv + (size_t)((mby0 + l) * mb_w + mbx) * k * 2));
+  __syncthreads();                                   // the barrier object is initialised for everybody
+  {
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok) : "r"(bar_a) : "memory");
+  }
+  if (mbx >= mb_w) return;
+  const uint32_t cur_s = (uint32_t)__cvta_generic_to_shared(&t_cur[0][16 * tx]);
+  const uint32_t ref_s = (uint32_t)__cvta_generic_to_shared(&t_ref[MCT_TOP][MCT_HALO_X + 16 * tx]);
+  for (int ty = 0; ty < MCT_H; ty++) {
+    const int mby = mby0 + ty;
+    if (mby >= mb_h) break;
+    const int m = mby * mb_w + mbx;
+    const int mv0 = __shfl_sync(0xffffffffu, first_mv, ty);
+    for (int c = 0; c < k; c++) {
+      const int mvw = c == 0 ? mv0 : __ldg(reinterpret_cast<const int*>(mv + (size_t)(m * k + c) * 2));
+      const int mvx = (int16_t)(mvw & 0xffff), mvy = mvw >> 16;
+      const int fx = mvx & 3, fy = mvy & 3;
+      int s = 0;
+      if ((fx | fy) == 0) {                    // integer vector: packed SAD on shared-space addresses, 2 words per lane
+        const uint32_t pb = ref_s + (16 * ty + (mvy >> 2)) * MCT_PITCH + (mvx >> 2);
+        const uint32_t sh = (pb & 3) * 8, pa = pb & ~3u;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const int y = (l >> 2) + 8 * i, x = (l & 3) << 2;
+          uint32_t cw, lo, hi;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(cur_s + (16 * ty + y) * (16 * MCT_W) + x));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(pa + y * MCT_PITCH + x));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(pa + y * MCT_PITCH + x + 4));
+          s += __vsadu4(cw, __funnelshift_r(lo, hi, sh));
+        }
+      } else {
+        const uint8_t* cm = &t_cur[16 * ty][16 * tx];
+        const uint8_t* p = &t_ref[MCT_TOP + 16 * ty][MCT_HALO_X + 16 * tx] + (mvy >> 2) * MCT_PITCH + (mvx >> 2);
+#pragma unroll 2
+        for (int i = l; i < 256; i += 32) {
+          const int y = i >> 4, x = i & 15;
+          s += iabs((int)cm[y * (16 * MCT_W) + x] - luma_qpel_sample(p + y * MCT_PITCH + x, MCT_PITCH, fx, fy));
+        }
+      }
+      s = warp_sum(s);
+      if (l == 0) cost[(size_t)m * k + c] = s;
+    }
+  }
+}
+
+// tensor maps of the two planes (host): uint8, rank 2, no swizzle, zero fill outside the extents
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder() {
+  static tmap_encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (tmap_encode_fn)p;
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+static bool make_plane_map(CUtensorMap* tm, const uint8_t* base, uint64_t w, uint64_t h, uint64_t stride, uint32_t bw, uint32_t bh) {
+  tmap_encode_fn enc = tmap_encoder();
+  if (!enc) return false;
+  const cuuint64_t dims[2] = {w, h}, strides[1] = {stride};
+  const cuuint32_t box[2] = {bw, bh}, es[2] = {1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // ================================================================================================
 // C-ABI
 // ================================================================================================
@@ -248,7 +438,23 @@ int b2h264_k_mc_sad(const uint8_t* cur, int cs, const uint8_t* ref, int rs, int 
   const int n = mb_w * mb_h;
   if (n <= 0 || k <= 0) return 0;
   if ((rs & 3) || (cs & 3)) return cudaErrorInvalidValue;
-  k_mc_sad<<<JOB_GRID(n), 0, (cudaStream_t)stream>>>(cur, cs, ref, rs, mb_w, mb_h, mv, k, cost);
+  const bool aligned = !((rs | cs) & 15) && !((reinterpret_cast<uintptr_t>(cur) | reinterpret_cast<uintptr_t>(ref)) & 15);
+  if (aligned && !getenv("B2H264_MC_SAD_NO_TMA")) {
+    // TMA: the reference plane is described from its padded origin (pad >= 32 is part of the contract)
+    CUtensorMap tc, tr;
+    if (make_plane_map(&tc, cur, (uint64_t)mb_w * 16, (uint64_t)mb_h * 16, (uint64_t)cs, 16 * MCT_W, 16 * MCT_H) &&
+        make_plane_map(&tr, ref - (ptrdiff_t)32 * rs - 32, (uint64_t)mb_w * 16 + 64, (uint64_t)mb_h * 16 + 64, (uint64_t)rs, MCT_PITCH,
+                       MCT_ROWS)) {
+      k_mc_sad_tma<<<dim3((mb_w + MCT_W - 1) / MCT_W, (mb_h + MCT_H - 1) / MCT_H), 32 * MCT_W, 0, (cudaStream_t)stream>>>(
+          tc, tr, mb_w, mb_h, mv, k, cost);
+      return b2h264_launched();
+    }
+  }
+  if (aligned)
+    k_mc_sad_tiled<<<dim3((mb_w + MCT_W - 1) / MCT_W, (mb_h + MCT_H - 1) / MCT_H), 32 * MCT_W, 0, (cudaStream_t)stream>>>(
+        cur, cs, ref, rs, mb_w, mb_h, mv, k, cost);
+  else
+    k_mc_sad<<<JOB_GRID(n), 0, (cudaStream_t)stream>>>(cur, cs, ref, rs, mb_w, mb_h, mv, k, cost);
   return b2h264_launched();
 }
 

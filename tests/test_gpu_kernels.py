@@ -369,11 +369,13 @@ def test_me_search(env, calc_satd):
     assert got == exp
 
 
-@pytest.mark.parametrize("wh", [(320, 192), (1920, 1088)])
-def test_mc_sad_unit(env, wh):
+@pytest.mark.parametrize("wh,shift", [((320, 192), 0), ((1920, 1088), 0), ((320, 192), 4), ((336, 208), 0)])
+def test_mc_sad_unit(env, wh, shift):
     """MC+SAD roofline unit.  Small frame: every cost against the oracle.  1080p (BASELINE.json's full
     size): a deterministic sample against the oracle plus two size-independent properties —
-    (i) at integer MVs MC is a copy, so cost == plain SAD; (ii) cost(mv) for cur := ref is 0 at mv = 0."""
+    (i) at integer MVs MC is a copy, so cost == plain SAD; (ii) cost(mv) for cur := ref is 0 at mv = 0.
+    shift = 0: 16-byte aligned planes -> the tiled cp.async kernel; shift = 4: the per-warp fallback kernel;
+    336x208: a picture that is not a whole number of 8x4-macroblock tiles."""
     m, lm, L, orc = env
     w, h = wh
     cur, ref, stride, pad = _padded_pair(w, h)
@@ -383,7 +385,7 @@ def test_mc_sad_unit(env, wh):
     mv = rng.randint(-32, 33, size=(mbw * mbh, k, 2)).astype(np.int16)
     mv[:, 0] = 0
     mv[:, 1] = (mv[:, 1] // 4) * 4               # integer candidates
-    o0 = pad * stride + pad
+    o0 = pad * stride + pad + shift
     dcur, dref, dmv = m.DeviceArray(cur), m.DeviceArray(ref), m.DeviceArray(mv)
     cost = m.DeviceArray(shape=(mbw * mbh, k), dtype=np.int32)
     lm.check(L.b2h264_k_mc_sad(dcur.at(o0), stride, dref.at(o0), stride, mbw, mbh, dmv.ptr, k, cost.ptr, None))

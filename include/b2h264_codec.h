@@ -67,6 +67,9 @@ int  b2h264_enc_get_recon (b2h264_enc* e, int stream, uint8_t* h_dst);
  * [1] deblocking wavefront + border expansion (both from CUDA events on the encoder's stream),
  * [2] host entropy coding (wall clock) */
 int  b2h264_enc_last_timing (b2h264_enc* e, float* us3);
+/* bytes the device handed to the host for the batch collected last: the index table plus the records of the
+ * coded (non P_SKIP) macroblocks, written by the GPU straight into mapped pinned memory */
+int  b2h264_enc_last_d2h_bytes (b2h264_enc* e, unsigned long long* bytes);
 
 /* makes the encoder issue all its GPU work on the caller's CUDA stream (cudaStream_t as void*), e.g. so
  * that a harness can bracket it with its own events; only while nothing is in flight */

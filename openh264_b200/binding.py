@@ -77,6 +77,7 @@ API = {
     "b2h264_enc_force_idr": [vp, C.c_int],
     "b2h264_enc_get_recon": [vp, C.c_int, vp],
     "b2h264_enc_last_timing": [vp, C.POINTER(C.c_float)],
+    "b2h264_enc_last_d2h_bytes": [vp, C.POINTER(C.c_ulonglong)],
     "b2h264_enc_set_stream": [vp, vp],
     "b2h264_table_quant_ff": [C.c_int],
     "b2h264_table_quant_mf": [C.c_int],
@@ -212,6 +213,12 @@ class BatchEncoder:
         t = (C.c_float * 3)()
         check(self.L.b2h264_enc_last_timing(self.h, t))
         return t[0], t[1], t[2]
+
+    def d2h_bytes(self):
+        """bytes the device handed over for the batch collected last (index table + coded records)"""
+        v = C.c_ulonglong(0)
+        check(self.L.b2h264_enc_last_d2h_bytes(self.h, C.byref(v)))
+        return int(v.value)
 
     def set_stream(self, cuda_stream_handle):
         check(self.L.b2h264_enc_set_stream(self.h, cuda_stream_handle))

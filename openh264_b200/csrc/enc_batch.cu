@@ -88,7 +88,11 @@ struct b2h264_enc {
   const uint8_t** d_srcptr[2] = {nullptr, nullptr};
   // pinned host memory
   uint8_t* h_src = nullptr;               // 2 slots x S x frame
-  MbOut* h_out[2] = {nullptr, nullptr};
+  MbOut* h_out[2] = {nullptr, nullptr};      // mapped pinned: coded records, packed per stream (worst case sized)
+  int32_t* h_idx[2] = {nullptr, nullptr};    // mapped pinned: per MB rank in the packed records or -1
+  int32_t* h_cnt[2] = {nullptr, nullptr};    // mapped pinned: coded macroblocks per stream
+  int32_t* d_list = nullptr;                 // device scratch of the pack kernel
+  unsigned long long last_d2h = 0;
   StreamFrame* h_sf[2] = {nullptr, nullptr};
   const uint8_t** h_srcptr[2] = {nullptr, nullptr};
   // in-flight bookkeeping
@@ -140,8 +144,13 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
   const size_t S = e->S;
   CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&e->st_in, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&e->st_out, cudaStreamNonBlocking));
+  {
+    int lo = 0, hi = 0;                       // record hand-over runs behind the kernels of the pictures
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    CK(cudaStreamCreateWithPriority(&e->st_out, cudaStreamNonBlocking, lo));
+  }
   CK(cudaMalloc(&e->d_cur, S * e->cur_bytes + 256));
+  CK(cudaMalloc(&e->d_list, S * e->n_mb * sizeof(int32_t)));
   for (int i = 0; i < 2; i++) {
     CK(cudaMalloc(&e->d_pic[i], S * e->pic_bytes + 256));
     CK(cudaMemset(e->d_pic[i], 0, S * e->pic_bytes + 256));
@@ -150,7 +159,9 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
     CK(cudaMalloc(&e->d_out[i], S * e->n_mb * sizeof(MbOut)));
     CK(cudaMalloc(&e->d_sf[i], S * sizeof(StreamFrame)));
     CK(cudaMalloc(&e->d_srcptr[i], S * sizeof(uint8_t*)));
-    CK(cudaMallocHost(&e->h_out[i], S * e->n_mb * sizeof(MbOut)));
+    CK(cudaHostAlloc(&e->h_out[i], S * e->n_mb * sizeof(MbOut), cudaHostAllocMapped));
+    CK(cudaHostAlloc(&e->h_idx[i], S * e->n_mb * sizeof(int32_t), cudaHostAllocMapped));
+    CK(cudaHostAlloc(&e->h_cnt[i], S * sizeof(int32_t), cudaHostAllocMapped));
     CK(cudaMallocHost(&e->h_sf[i], S * sizeof(StreamFrame)));
     CK(cudaMallocHost(&e->h_srcptr[i], S * sizeof(uint8_t*)));
     CK(cudaEventCreate(&e->slot[i].ev0));
@@ -181,11 +192,11 @@ void b2h264_enc_destroy(b2h264_enc* e) {
   if (!e) return;
   cudaStreamSynchronize(e->st);
   delete e->pool;
-  cudaFree(e->d_cur); cudaFree(e->d_src); cudaFree(e->d_mbi); cudaFree(e->d_sad); cudaFree(e->d_prog); cudaFree(e->d_tickets); cudaFree(e->d_stash);
+  cudaFree(e->d_cur); cudaFree(e->d_src); cudaFree(e->d_mbi); cudaFree(e->d_sad); cudaFree(e->d_prog); cudaFree(e->d_tickets); cudaFree(e->d_stash); cudaFree(e->d_list);
   cudaFreeHost(e->h_src);
   for (int i = 0; i < 2; i++) {
     cudaFree(e->d_pic[i]); cudaFree(e->d_rinfo[i]); cudaFree(e->d_out[i]); cudaFree(e->d_sf[i]); cudaFree(e->d_srcptr[i]);
-    cudaFreeHost(e->h_out[i]); cudaFreeHost(e->h_sf[i]); cudaFreeHost(e->h_srcptr[i]);
+    cudaFreeHost(e->h_out[i]); cudaFreeHost(e->h_idx[i]); cudaFreeHost(e->h_cnt[i]); cudaFreeHost(e->h_sf[i]); cudaFreeHost(e->h_srcptr[i]);
     cudaEventDestroy(e->slot[i].ev0); cudaEventDestroy(e->slot[i].ev1); cudaEventDestroy(e->slot[i].ev2); cudaEventDestroy(e->slot[i].done); cudaEventDestroy(e->slot[i].in_done); cudaEventDestroy(e->slot[i].enc_done);
   }
   if (e->own_stream) cudaStreamDestroy(e->st);
@@ -270,7 +281,8 @@ int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_devic
   CK(cudaEventRecord(sl.ev2, e->st));
   // the macroblock records are final once the encode kernel is done (deblocking does not touch them)
   CK(cudaStreamWaitEvent(e->st_out, sl.ev1, 0));
-  CK(cudaMemcpyAsync(e->h_out[k], e->d_out[k], (size_t)S * e->n_mb * sizeof(MbOut), cudaMemcpyDeviceToHost, e->st_out));
+  rc = enc_launch_pack(e->d_sf[k], S, e->n_mb, e->h_out[k], e->h_idx[k], e->h_cnt[k], e->d_list, e->st_out);
+  if (rc) return rc;
   CK(cudaEventRecord(sl.done, e->st_out));
   sl.busy = true;
   e->submit_idx++;
@@ -294,9 +306,11 @@ int b2h264_enc_collect(b2h264_enc* e, const uint8_t** bs, int32_t* bs_bytes, int
   (void)cudaGetLastError();
   const auto t0 = std::chrono::steady_clock::now();
   const int n_mb = e->n_mb;
+  e->last_d2h = (unsigned long long)e->S * (n_mb + 1) * sizeof(int32_t);
+  for (int s = 0; s < e->S; s++) e->last_d2h += (unsigned long long)e->h_cnt[k][s] * sizeof(MbOut);
   std::function<void(int)> job = [&](int s) {
     e->bs[s].clear();
-    e->ctl[s].write_access_unit(sl.idr[s] != 0, e->h_out[k] + (size_t)s * n_mb, &e->bs[s]);
+    e->ctl[s].write_access_unit_packed(sl.idr[s] != 0, e->h_out[k] + (size_t)s * n_mb, e->h_idx[k] + (size_t)s * n_mb, &e->bs[s]);
   };
   e->pool->run(e->S, job);
   e->last_us[2] = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - t0).count();
@@ -307,6 +321,12 @@ int b2h264_enc_collect(b2h264_enc* e, const uint8_t** bs, int32_t* bs_bytes, int
   }
   sl.busy = false;
   e->collect_idx++;
+  return 0;
+}
+
+int b2h264_enc_last_d2h_bytes(b2h264_enc* e, unsigned long long* bytes) {
+  if (!e || !bytes) return -1;
+  *bytes = e->last_d2h;
   return 0;
 }
 

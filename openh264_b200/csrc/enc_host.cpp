@@ -35,6 +35,21 @@ EncFrameParams StreamCtl::frame_params(bool idr, bool ref_is_p) const {
 }
 
 void StreamCtl::write_access_unit(bool idr, const MbOut* mbs, std::vector<uint8_t>* au) {
+  const int n = sp.mb_w * sp.mb_h;
+  recs_.resize(n);
+  for (int i = 0; i < n; i++) recs_[i] = mbs + i;
+  write_au(idr, recs_.data(), au);
+}
+
+void StreamCtl::write_access_unit_packed(bool idr, const MbOut* packed, const int32_t* idx, std::vector<uint8_t>* au) {
+  static const MbOut kSkip = [] { MbOut m; memset(&m, 0, sizeof(m)); m.mb_type = MBT_PSKIP; return m; }();
+  const int n = sp.mb_w * sp.mb_h;
+  recs_.resize(n);
+  for (int i = 0; i < n; i++) recs_[i] = idx[i] < 0 ? &kSkip : packed + idx[i];
+  write_au(idr, recs_.data(), au);
+}
+
+void StreamCtl::write_au(bool idr, const MbOut* const* mbs, std::vector<uint8_t>* au) {
   std::vector<uint8_t> rbsp;
   if (idr) {
     idr_pic_id = idr_pic_id < 65535 ? idr_pic_id + 1 : 0;

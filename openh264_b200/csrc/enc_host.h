@@ -33,7 +33,13 @@ struct StreamCtl {
   int rec_rows_c() const { return sp.mb_h * 8 + 32; }
   EncFrameParams frame_params(bool idr, bool ref_is_p) const;
   // serialises the access unit of the frame just coded (SPS+PPS+IDR slice, or P slice)
-  void write_access_unit(bool idr, const MbOut* mbs, std::vector<uint8_t>* au);
+  void write_access_unit(bool idr, const MbOut* mbs, std::vector<uint8_t>* au);                 // one record per MB
+  // packed form: idx[mb] = position of the macroblock's record in `packed`, or -1 for a P_SKIP macroblock
+  void write_access_unit_packed(bool idr, const MbOut* packed, const int32_t* idx, std::vector<uint8_t>* au);
+ private:
+  void write_au(bool idr, const MbOut* const* recs, std::vector<uint8_t>* au);
+  std::vector<const MbOut*> recs_;
+ public:
 };
 
 // copies a w x h I420 picture into MB-aligned planes; rows/cols beyond the picture are 0 (luma) / 0x80

@@ -20,3 +20,5 @@ int enc_launch_deblock_expand(const StreamFrame* d_sf, int n_streams, int mb_w, 
 size_t enc_sched_ints(int n_streams, int n_mb);
 size_t enc_stash_bytes(int n_streams, int mb_h);      // parked macroblock scratches (one per stream and MB row)
 size_t enc_scratch_bytes();
+// compacts the records of the picture just coded into (mapped pinned) `pack`; idx / cnt likewise host-visible
+int enc_launch_pack(const StreamFrame* d_sf, int n_streams, int n_mb, MbOut* pack, int32_t* idx, int32_t* cnt, int32_t* d_list, cudaStream_t st);

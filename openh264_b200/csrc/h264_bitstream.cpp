@@ -171,7 +171,7 @@ inline int nc_of(int a, int b) {          // a/b = neighbour counts or -1 when u
 
 }  // namespace
 
-void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* mbs, std::vector<uint8_t>* rbsp) {
+void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* const* recs, std::vector<uint8_t>* rbsp) {
   BitWriter w(rbsp);
   // ---- slice header (svc_encode_slice.cpp:275-346) ----
   w.ue(0);                               // first_mb_in_slice
@@ -194,7 +194,7 @@ void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* mbs,
   int skip_run = 0;
   int last_qp = ss.qp;
   for (int idx = 0; idx < n; idx++) {
-    const MbOut& m = mbs[idx];
+    const MbOut& m = *recs[idx];
     const int mbx = idx % mbw, mby = idx / mbw;
     if (m.mb_type == MBT_PSKIP) { skip_run++; continue; }
     if (!ss.idr) { w.ue((uint32_t)skip_run); skip_run = 0; }
@@ -229,8 +229,8 @@ void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* mbs,
       w.se(m.qp - last_qp);
       last_qp = m.qp;
       // neighbour counts
-      const int8_t* L = mbx > 0 ? mbs[idx - 1].nnz : nullptr;
-      const int8_t* T = mby > 0 ? mbs[idx - mbw].nnz : nullptr;
+      const int8_t* L = mbx > 0 ? recs[idx - 1]->nnz : nullptr;
+      const int8_t* T = mby > 0 ? recs[idx - mbw]->nnz : nullptr;
       auto luma_nc = [&](int bx, int by) {
         const int a = bx > 0 ? m.nnz[by * 4 + bx - 1] : (L ? L[by * 4 + 3] : -1);
         const int b = by > 0 ? m.nnz[(by - 1) * 4 + bx] : (T ? T[12 + bx] : -1);

@@ -66,6 +66,7 @@ struct SliceState {
   int qp;
 };
 // slice header + all macroblocks + trailing bits of a single-slice picture
-void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* mbs, std::vector<uint8_t>* rbsp);
+// recs[i] = the record of macroblock i (P_SKIP macroblocks may all point at one shared all-zero-nnz record)
+void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* const* recs, std::vector<uint8_t>* rbsp);
 
 }  // namespace b2h264

@@ -210,9 +210,9 @@ def mc_sad_roofline(L, local, peak):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=4)
-    ap.add_argument("--streams", type=int, default=128, help="independent 1080p streams per GPU")
+    ap.add_argument("--streams", type=int, default=256, help="independent 1080p streams per GPU")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--ref-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

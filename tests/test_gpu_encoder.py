@@ -113,3 +113,36 @@ def test_force_idr_and_bad_config():
     enc.close()
     with pytest.raises(B2H264Error):
         BatchEncoder(15, 15)
+
+
+def test_heterogeneous_streams_with_one_forced_idr():
+    """7 streams with different content in one encoder; stream 3 is forced to an IDR at picture 2 while the others
+    code P pictures, so one launch carries IDR-picture macroblocks (list I) and P-picture macroblocks (lists A/B/C)
+    together.  Every stream must equal what the reference's own API produces for that stream (API driver through
+    the compiled reference, with the same ForceIntraFrame call)."""
+    from test_wels_api import DRIVER, REFLIB, drive
+    if not (os.path.exists(DRIVER) and os.path.exists(REFLIB)):
+        pytest.skip("oracle/_ref not present")
+    import tempfile
+    from openh264_b200.binding import BatchEncoder
+    w, h, n, qp, S = 176, 144, 5, 27, 7
+    clips = [h264lib.synth_clip(w, h, n, seed=100 + s) for s in range(S)]
+    fsz = w * h * 3 // 2
+    enc = BatchEncoder(w, h, qp=qp, fps=30.0, n_streams=S)
+    got = [b""] * S
+    enc.submit([c[:fsz] for c in clips])
+    for f in range(1, n + 1):
+        if f < n:
+            if f == 2:
+                enc.force_idr(3)
+            enc.submit([c[f * fsz:(f + 1) * fsz] for c in clips])
+        bs, types = enc.collect()
+        if f - 1 == 2:
+            assert [int(t) for t in types] == [2, 2, 2, 1, 2, 2, 2]
+        got = [got[s] + bytes(bs[s]) for s in range(S)]
+    enc.close()
+    with tempfile.TemporaryDirectory() as tmp:
+        for s in range(S):
+            r, ref_bs, _ = drive(REFLIB, clips[s], w, h, n, qp, 2 if s == 3 else -1, tmp, "ref%d" % s)
+            assert r.returncode == 0, r.stderr
+            assert got[s] == ref_bs, "stream %d differs from the reference" % s

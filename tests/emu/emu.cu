@@ -68,7 +68,25 @@ struct HostFrameEncoder {
     f.sad_cost = sad_cost.data();
     return f;
   }
+  bool packed_writer_ok = true;
   void finish_frame(std::vector<uint8_t>* bs) {
+    // the product hands the host only the coded macroblocks' records plus an index table (k_pack_records):
+    // write the access unit through that form too and insist on the same bytes
+    {
+      b2h264::StreamCtl twin = ctl;
+      std::vector<MbOut> packed;
+      std::vector<int32_t> index(out.size());
+      for (size_t i = 0; i < out.size(); i++) {
+        if (out[i].mb_type == MBT_PSKIP) { index[i] = -1; continue; }
+        index[i] = (int32_t)packed.size();
+        packed.push_back(out[i]);
+      }
+      std::vector<uint8_t> a, b;
+      b2h264::StreamCtl plain = ctl;
+      plain.write_access_unit(idr, out.data(), &a);
+      twin.write_access_unit_packed(idr, packed.data(), index.data(), &b);
+      if (a != b) packed_writer_ok = false;
+    }
     ctl.write_access_unit(idr, out.data(), bs);
     have_ref_p = !idr;
     cur_rec = 1 - cur_rec;            // the picture just reconstructed becomes the reference
@@ -129,6 +147,7 @@ extern "C" long emu_encode(const uint8_t* yuv, int w, int h, int nframes, int qp
     // --- host entropy coding
     g_last_out = enc.out; g_last_info = enc.mbi;
     enc.finish_frame(&bs);
+    if (!enc.packed_writer_ok) return -9;          // packed hand-over form wrote different bytes
     if (total + (long)bs.size() > cap) return -1;
     memcpy(out + total, bs.data(), bs.size());
     total += bs.size();

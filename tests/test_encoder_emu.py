@@ -59,3 +59,54 @@ def test_emu_matches_reference_on_its_own_clip(emu):
         ref_bs, ref_fb, _ = ref_encode(yuv, 320, 192, 9, qp, 12.0)
         bs, fb = emu_encode(emu, yuv, 320, 192, 9, qp, 12.0)
         assert fb == ref_fb and bs == ref_bs
+
+
+EDGE_CASES = [
+    # (w, h, n, qp, seed): QP extremes, pictures that need cropping in one or both directions, the smallest
+    # picture the encoder accepts, a wide flat one (long rows: long top-right chains), level-1.0 vector limit (qcif)
+    (176, 144, 4, 0, 3), (176, 144, 4, 51, 3), (176, 144, 4, 12, 4), (176, 144, 4, 45, 4),
+    (180, 148, 4, 26, 5), (164, 130, 4, 30, 6), (16, 16, 4, 26, 7), (32, 18, 4, 20, 8),
+    (480, 32, 4, 28, 9), (64, 256, 4, 33, 10), (352, 288, 3, 38, 11),
+]
+
+
+@pytest.mark.parametrize("case", EDGE_CASES)
+def test_emu_matches_reference_edge_cases(emu, case):
+    """the same macroblock SOURCE the GPU runs, against the compiled reference, on the edge cases the reference's own
+    encoder tests sweep (QP range, odd resolutions: test/api/encoder_test.cpp, test/encoder/EncUT_*.cpp)"""
+    if not h264lib.have_ref():
+        pytest.skip("reference build not on this machine")
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_encoder_golden import ref_encode
+    w, h, n, qp, seed = case
+    yuv = h264lib.synth_clip(w, h, n, seed=seed)
+    ref_bs, ref_fb, _ = ref_encode(yuv, w, h, n, qp, 30.0)
+    bs, fb = emu_encode(emu, yuv, w, h, n, qp, 30.0)
+    assert fb == ref_fb and bs == bytes(ref_bs)
+
+
+def test_emu_matches_reference_on_other_reference_clips(emu):
+    """more of the reference's own res/*.yuv clips (first pictures), where they exist"""
+    if not h264lib.have_ref():
+        pytest.skip("reference build not on this machine")
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_encoder_golden import ref_encode
+    clips = [("/root/reference/res/Cisco_Absolute_Power_1280x720_30fps.yuv", 1280, 720, 2, 30),
+             ("/root/reference/res/CiscoVT2people_160x96_6fps.yuv", 160, 96, 6, 24),
+             ("/root/reference/res/Static_152_100.yuv", 152, 100, 8, 28)]
+    ran = 0
+    for path, w, h, n, qp in clips:
+        if not os.path.exists(path):
+            continue
+        fsz = w * h * 3 // 2
+        yuv = np.fromfile(path, dtype=np.uint8, count=n * fsz)
+        if yuv.size < n * fsz:
+            continue
+        ref_bs, ref_fb, _ = ref_encode(yuv, w, h, n, qp, 30.0)
+        bs, fb = emu_encode(emu, yuv, w, h, n, qp, 30.0)
+        assert fb == ref_fb and bs == bytes(ref_bs), path
+        ran += 1
+    if not ran:
+        pytest.skip("no reference clips on this machine")

@@ -121,6 +121,12 @@ void deblock_frame_host(const EncFrameParams& p, const EncFramePtrs& f) {
 
 }  // namespace
 
+static std::vector<uint8_t> g_last_path;
+extern "C" int emu_last_path(uint8_t* path, int n) {
+  if ((int)g_last_path.size() < n) return -1;
+  memcpy(path, g_last_path.data(), n);
+  return 0;
+}
 static std::vector<MbOut> g_last_out;
 static std::vector<MbInfo> g_last_info;
 extern "C" int emu_last(MbOut* out, MbInfo* info, int n) {
@@ -140,8 +146,19 @@ extern "C" long emu_encode(const uint8_t* yuv, int w, int h, int nframes, int qp
     enc.load_source(yuv + i * fsz);
     enc.begin_frame();
     // --- the part the GPU does in the product: macroblocks (raster order here), deblocking, expansion
+    g_last_path.assign((size_t)enc.p.mb_w * enc.p.mb_h, 0);
     for (int mby = 0; mby < enc.p.mb_h; mby++)
-      for (int mbx = 0; mbx < enc.p.mb_w; mbx++) encode_one_mb(enc.p, enc.ptrs(), enc.scratch, mbx, mby);
+      for (int mbx = 0; mbx < enc.p.mb_w; mbx++) {
+        // encode_one_mb, with the stages the macroblock goes through recorded (bit s = stage s ran): the device
+        // scheduler runs them as separate tasks (tools/sched_sim.py replays these paths)
+        const EncFramePtrs f = enc.ptrs();
+        mb_ctx(enc.scratch.ctx, enc.p, f, mbx, mby);
+        int stage = enc.p.is_idr ? MBS_I : MBS_A;
+        while (stage != MBS_DONE) {
+          g_last_path[(size_t)mby * enc.p.mb_w + mbx] |= (uint8_t)(1u << stage);
+          stage = mb_run_stage(enc.scratch.ctx, enc.scratch, stage);
+        }
+      }
     deblock_frame_host(enc.p, enc.ptrs());
     expand_frame_host(enc.p, enc.ptrs());
     // --- host entropy coding

@@ -171,6 +171,8 @@ inline int nc_of(int a, int b) {          // a/b = neighbour counts or -1 when u
 
 }  // namespace
 
+const uint8_t* cbp_me_table(bool intra) { return intra ? kCbpIntra : kCbpInter; }
+
 void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* const* recs, std::vector<uint8_t>* rbsp) {
   BitWriter w(rbsp);
   // ---- slice header (svc_encode_slice.cpp:275-346) ----

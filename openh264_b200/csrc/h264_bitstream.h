@@ -66,6 +66,9 @@ struct SliceState {
   int qp;
 };
 // slice header + all macroblocks + trailing bits of a single-slice picture
+// coded_block_pattern me(v) mapping (Rec. H.264 Table 9-4, chroma_format_idc 1): codeNum indexed by cbp (48 entries)
+const uint8_t* cbp_me_table(bool intra);
+
 // recs[i] = the record of macroblock i (P_SKIP macroblocks may all point at one shared all-zero-nnz record)
 void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* const* recs, std::vector<uint8_t>* rbsp);
 

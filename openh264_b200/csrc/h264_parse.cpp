@@ -1,0 +1,394 @@
+// h264_parse.cpp — see h264_parse.h.  Syntax: Rec. H.264 7.3 (NAL, SPS 7.3.2.1, PPS 7.3.2.2, slice header 7.3.3,
+// slice data 7.3.4, macroblock layer 7.3.5, residual CAVLC 7.3.5.3.2 / 9.2).  The reference's counterparts:
+// codec/decoder/core/src/au_parser.cpp (ParseSps :~900, ParsePps), decode_slice.cpp (ParseSliceHeaderSyntaxes),
+// parse_mb_syn_cavlc.cpp (WelsResidualBlockCavlc :~700, ParseInterInfo, ParseIntra4x4Mode).
+#include "h264_parse.h"
+
+#include <string.h>
+
+#include "cavlc_tables.h"
+
+namespace b2h264 {
+
+namespace {
+
+class BitReader {
+ public:
+  BitReader(const uint8_t* p, size_t n) : p_(p), nbits_(n * 8) {}
+  bool ok() const { return !err_; }
+  size_t pos() const { return pos_; }
+  size_t left() const { return pos_ <= nbits_ ? nbits_ - pos_ : 0; }
+  uint32_t peek(int n) const {            // n <= 24; bits beyond the end read as 0
+    uint32_t v = 0;
+    for (int i = 0; i < n; i++) {
+      const size_t b = pos_ + i;
+      v = (v << 1) | (b < nbits_ ? (p_[b >> 3] >> (7 - (b & 7))) & 1u : 0u);
+    }
+    return v;
+  }
+  void skip(int n) { pos_ += n; if (pos_ > nbits_) err_ = true; }
+  uint32_t get(int n) { const uint32_t v = n ? peek(n) : 0; skip(n); return v; }
+  int bit() { return (int)get(1); }
+  uint32_t ue() {
+    int z = 0;
+    while (left() && !peek(1)) { skip(1); if (++z > 31) { err_ = true; return 0; } }
+    if (!left()) { err_ = true; return 0; }
+    skip(1);
+    return z ? ((1u << z) - 1 + get(z)) : 0;
+  }
+  int32_t se() { const uint32_t k = ue(); return (k & 1) ? (int32_t)((k + 1) >> 1) : -(int32_t)(k >> 1); }
+  // 7.2 more_rbsp_data(): anything before the final stop bit?
+  bool more_data() const {
+    if (left() == 0) return false;
+    size_t last = nbits_;
+    while (last > pos_ && !((p_[(last - 1) >> 3] >> (7 - ((last - 1) & 7))) & 1)) last--;   // last = index after the stop bit
+    return last > pos_ + 1;
+  }
+ private:
+  const uint8_t* p_;
+  size_t nbits_, pos_ = 0;
+  bool err_ = false;
+};
+
+struct Nal { int ref_idc, type; std::vector<uint8_t> rbsp; };
+
+// splits an Annex-B buffer into NAL units and strips the emulation prevention bytes (7.4.1)
+std::vector<Nal> split_nals(const uint8_t* d, size_t n) {
+  std::vector<Nal> out;
+  size_t i = 0;
+  auto start_at = [&](size_t k) { return k + 2 < n && d[k] == 0 && d[k + 1] == 0 && d[k + 2] == 1; };
+  while (i + 3 <= n && !start_at(i)) i++;
+  while (i + 3 <= n) {
+    i += 3;                                                 // past 00 00 01
+    size_t e = i;
+    while (e + 3 <= n && !start_at(e)) e++;
+    size_t end = e + 3 <= n ? e : n;
+    if (e + 3 <= n && end > i && d[end - 1] == 0) end--;    // the zero_byte of a 4-byte start code belongs to the next NAL
+    if (end > i) {
+      Nal u;
+      u.ref_idc = (d[i] >> 5) & 3; u.type = d[i] & 31;
+      int zeros = 0;
+      for (size_t k = i + 1; k < end; k++) {
+        if (zeros >= 2 && d[k] == 3) { zeros = 0; continue; }
+        u.rbsp.push_back(d[k]);
+        zeros = d[k] == 0 ? zeros + 1 : 0;
+      }
+      out.push_back(std::move(u));
+    }
+    i = e;
+  }
+  return out;
+}
+
+int parse_sps(BitReader& r, ParserState* st) {
+  const int profile = (int)r.get(8);
+  r.get(8);                                   // constraint flags + reserved
+  const int level = (int)r.get(8);
+  const int sps_id = (int)r.ue();
+  if (profile != 66) return PARSE_UNSUPPORTED;            // Baseline only (no chroma_format_idc / scaling lists)
+  st->log2_max_frame_num = (int)r.ue() + 4;
+  st->poc_type = (int)r.ue();
+  if (st->poc_type == 0) st->log2_max_poc_lsb = (int)r.ue() + 4;
+  else if (st->poc_type != 2) return PARSE_UNSUPPORTED;
+  StreamParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.num_ref_frames = (int)r.ue();
+  r.bit();                                    // gaps_in_frame_num_value_allowed_flag
+  sp.mb_w = (int)r.ue() + 1;
+  sp.mb_h = (int)r.ue() + 1;
+  if (!r.bit()) return PARSE_UNSUPPORTED;     // frame_mbs_only_flag
+  r.bit();                                    // direct_8x8_inference_flag
+  sp.crop = r.bit() != 0;
+  int cl = 0, ct = 0;
+  if (sp.crop) { cl = (int)r.ue(); sp.crop_right = (int)r.ue(); ct = (int)r.ue(); sp.crop_bottom = (int)r.ue(); }
+  if (!r.ok()) return PARSE_TRUNCATED;
+  if (sp.mb_w < 1 || sp.mb_h < 1 || sp.mb_w > 512 || sp.mb_h > 512 || sp.num_ref_frames > 16) return PARSE_INVALID;
+  sp.width = sp.mb_w * 16 - 2 * (cl + sp.crop_right);
+  sp.height = sp.mb_h * 16 - 2 * (ct + sp.crop_bottom);
+  sp.level_idc = level;
+  sp.sps_id = sps_id;
+  if (cl || ct) return PARSE_UNSUPPORTED;     // left / top cropping: never produced by the encoders this mirrors
+  sp.pps_id = st->sp.pps_id;
+  sp.qp = st->sp.qp;
+  st->sp = sp;
+  st->have_sps = true;                        // VUI (if any) is not needed for reconstruction
+  return PARSE_OK;
+}
+
+int parse_pps(BitReader& r, ParserState* st) {
+  const int pps_id = (int)r.ue();
+  const int sps_id = (int)r.ue();
+  if (!st->have_sps || sps_id != st->sp.sps_id) return PARSE_NO_PARAMETER_SETS;
+  if (r.bit()) return PARSE_UNSUPPORTED;      // entropy_coding_mode_flag: CABAC
+  const int bottom_field_poc = r.bit();
+  if (r.ue() != 0) return PARSE_UNSUPPORTED;  // slice groups
+  st->num_ref_idx_default = (int)r.ue() + 1;
+  r.ue();
+  if (r.bit()) return PARSE_UNSUPPORTED;      // weighted_pred_flag
+  r.get(2);
+  st->pic_init_qp = 26 + r.se();
+  r.se();
+  if (r.se() != 0) return PARSE_UNSUPPORTED;  // chroma_qp_index_offset
+  st->deblocking_control = r.bit() != 0;
+  if (r.bit()) return PARSE_UNSUPPORTED;      // constrained_intra_pred_flag
+  if (r.bit()) return PARSE_UNSUPPORTED;      // redundant_pic_cnt_present_flag
+  if (bottom_field_poc) return PARSE_UNSUPPORTED;
+  if (!r.ok()) return PARSE_TRUNCATED;
+  st->sp.pps_id = pps_id;
+  st->have_pps = true;
+  return PARSE_OK;
+}
+
+// ---- residual block (9.2): the inverse of write_block() ------------------------------------------------------------
+// table entry = (bits << 8) | codeword; returns the index whose code matches the next bits, or -1
+template <int N>
+int match_code(BitReader& r, const uint16_t (&tbl)[N], int n_valid) {
+  const uint32_t look = r.peek(16);
+  for (int i = 0; i < n_valid; i++) {
+    const int bits = tbl[i] >> 8;
+    if (bits && (look >> (16 - bits)) == (uint32_t)(tbl[i] & 0xff)) { r.skip(bits); return i; }
+  }
+  return -1;
+}
+
+// reads one block into lv[0..max_coef) (scan order); returns total_coeff or a negative ParseError
+int read_block(BitReader& r, int16_t* lv, int max_coef, int nc) {
+  for (int i = 0; i < 16; i++) lv[i] = 0;
+  const int cls = nc < 0 ? 4 : kNcClass[nc > 16 ? 16 : nc];
+  int total = -1, t1 = 0;
+  {
+    const uint32_t look = r.peek(16);
+    const int max_total = nc < 0 ? 4 : 16;
+    for (int t = 0; t <= max_total && total < 0; t++)
+      for (int o = 0; o < 4 && o <= t; o++) {
+        const uint16_t e = kCoeffToken[cls][t][o];
+        const int bits = e >> 8;
+        if (bits && (look >> (16 - bits)) == (uint32_t)(e & 0xff)) { total = t; t1 = o; r.skip(bits); break; }
+      }
+  }
+  if (total < 0) return PARSE_INVALID;
+  if (total > max_coef) return PARSE_INVALID;
+  if (total == 0) return 0;
+  int level[16];
+  for (int k = 0; k < t1; k++) level[k] = r.bit() ? -1 : 1;
+  int suffix_len = (total > 10 && t1 < 3) ? 1 : 0;
+  for (int k = t1; k < total; k++) {
+    int prefix = 0;
+    while (r.left() && !r.peek(1)) { r.skip(1); if (++prefix > 32) return PARSE_INVALID; }
+    r.skip(1);
+    int suffix_size = (prefix == 14 && suffix_len == 0) ? 4 : (prefix >= 15 ? prefix - 3 : suffix_len);
+    int code = ((prefix < 15 ? prefix : 15) << suffix_len) + (suffix_size ? (int)r.get(suffix_size) : 0);
+    if (prefix >= 15 && suffix_len == 0) code += 15;
+    if (prefix >= 16) code += (1 << (prefix - 3)) - 4096;
+    if (k == t1 && t1 < 3) code += 2;
+    level[k] = (code & 1) ? (-code - 1) >> 1 : (code + 2) >> 1;
+    if (suffix_len == 0) suffix_len = 1;
+    const int a = level[k] < 0 ? -level[k] : level[k];
+    if (a > (3 << (suffix_len - 1)) && suffix_len < 6) suffix_len++;
+  }
+  int zeros_left = 0;
+  if (total < max_coef) {
+    const int tz = nc >= 0 ? match_code(r, kTotalZeros[total], 16) : match_code(r, kTotalZerosChromaDc[total], 4);
+    if (tz < 0) return PARSE_INVALID;
+    zeros_left = tz;
+  }
+  int run[16];
+  for (int k = 0; k < total; k++) run[k] = 0;
+  for (int k = 0; k + 1 < total && zeros_left > 0; k++) {
+    const int rb = match_code(r, kRunBefore[zeros_left > 7 ? 7 : zeros_left], 15);
+    if (rb < 0 || rb > zeros_left) return PARSE_INVALID;
+    run[k] = rb;
+    zeros_left -= rb;
+  }
+  run[total - 1] = zeros_left;
+  int pos = -1;
+  for (int k = total - 1; k >= 0; k--) {
+    pos += run[k] + 1;
+    if (pos >= max_coef) return PARSE_INVALID;
+    lv[pos] = (int16_t)level[k];
+  }
+  if (!r.ok()) return PARSE_TRUNCATED;
+  return total;
+}
+
+inline int nc_of(int a, int b) {
+  if (a >= 0 && b >= 0) return (a + b + 1) >> 1;
+  if (a >= 0) return a;
+  if (b >= 0) return b;
+  return 0;
+}
+
+// inverse of the me(v) mapping of coded_block_pattern (Table 9-4): built from the writer's table
+int cbp_from_code(int code, bool intra) {
+  static uint8_t inv[2][48];
+  static bool built = false;
+  if (!built) {
+    for (int t = 0; t < 2; t++) {
+      const uint8_t* fwd = cbp_me_table(t != 0);
+      for (int cbp = 0; cbp < 48; cbp++) inv[t][fwd[cbp]] = (uint8_t)cbp;
+    }
+    built = true;
+  }
+  if (code < 0 || code > 47) return -1;
+  return inv[intra ? 1 : 0][code];
+}
+
+int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pic) {
+  if (!st->have_sps || !st->have_pps) return PARSE_NO_PARAMETER_SETS;
+  const bool idr = nal.type == 5;
+  if (r.ue() != 0) return PARSE_UNSUPPORTED;                  // first_mb_in_slice: one slice per picture
+  const int slice_type = (int)r.ue() % 5;
+  if (slice_type != 0 && slice_type != 2) return PARSE_UNSUPPORTED;
+  const bool is_p = slice_type == 0;
+  if (idr && is_p) return PARSE_INVALID;
+  if ((int)r.ue() != st->sp.pps_id) return PARSE_NO_PARAMETER_SETS;
+  SliceState& ss = pic->ss;
+  ss.idr = idr;
+  ss.frame_num = (int)r.get(st->log2_max_frame_num);
+  ss.idr_pic_id = idr ? (int)r.ue() : 0;
+  if (st->poc_type == 0) r.get(st->log2_max_poc_lsb);
+  if (is_p) {
+    int n_ref = st->num_ref_idx_default;
+    if (r.bit()) n_ref = (int)r.ue() + 1;
+    if (n_ref != 1) return PARSE_UNSUPPORTED;
+    if (r.bit()) {                                            // ref_pic_list_modification_flag_l0
+      for (;;) {
+        const uint32_t idc = r.ue();
+        if (idc == 3) break;
+        if (idc > 3 || !r.ok()) return PARSE_INVALID;
+        r.ue();
+      }
+    }
+  }
+  if (nal.ref_idc) {                                          // dec_ref_pic_marking
+    if (idr) { r.bit(); if (r.bit()) return PARSE_UNSUPPORTED; }
+    else if (r.bit()) return PARSE_UNSUPPORTED;               // adaptive marking (MMCO)
+  }
+  ss.qp = st->pic_init_qp + r.se();
+  pic->disable_deblocking_idc = 0;
+  if (st->deblocking_control) {
+    pic->disable_deblocking_idc = (int)r.ue();
+    if (pic->disable_deblocking_idc != 1) { if (r.se() != 0 || r.se() != 0) return PARSE_UNSUPPORTED; }
+  }
+  if (!r.ok()) return PARSE_TRUNCATED;
+  if (ss.qp < 0 || ss.qp > 51) return PARSE_INVALID;
+
+  // ---- slice data ----
+  const int mbw = st->sp.mb_w, n = st->sp.mb_w * st->sp.mb_h;
+  pic->mbs.assign(n, MbOut());
+  for (MbOut& m : pic->mbs) { memset(&m, 0, sizeof(m)); m.mb_type = MBT_PSKIP; }
+  int qp = ss.qp;
+  int idx = 0;
+  while (idx < n) {
+    if (is_p) {
+      const int run = (int)r.ue();
+      if (!r.ok() || idx + run > n) return PARSE_INVALID;
+      for (int k = 0; k < run; k++) pic->mbs[idx++].qp = (uint8_t)qp;
+      if (idx == n) break;
+      if (!r.more_data()) return PARSE_INVALID;
+    }
+    MbOut& m = pic->mbs[idx];
+    const int mbx = idx % mbw, mby = idx / mbw;
+    int t = (int)r.ue();
+    bool intra = !is_p;
+    if (is_p) {
+      if (t >= 5) { intra = true; t -= 5; }
+    }
+    int cbp = -1;
+    if (!intra) {
+      if (t == 0) { m.mb_type = MBT_P16x16; m.mvd[0][0] = (int16_t)r.se(); m.mvd[0][1] = (int16_t)r.se(); }
+      else if (t == 1 || t == 2) {
+        m.mb_type = t == 1 ? MBT_P16x8 : MBT_P8x16;
+        for (int k = 0; k < 2; k++) { m.mvd[k][0] = (int16_t)r.se(); m.mvd[k][1] = (int16_t)r.se(); }
+      } else if (t == 3 || t == 4) {
+        if (t == 3) return PARSE_UNSUPPORTED;                 // P_8x8 with explicit reference indices
+        m.mb_type = MBT_P8x8;
+        for (int k = 0; k < 4; k++) if (r.ue() != 0) return PARSE_UNSUPPORTED;   // sub-8x8 partitions
+        for (int k = 0; k < 4; k++) { m.mvd[k][0] = (int16_t)r.se(); m.mvd[k][1] = (int16_t)r.se(); }
+      } else return PARSE_INVALID;
+    } else {
+      if (t == 0) {
+        m.mb_type = MBT_I4x4;
+        for (int k = 0; k < 16; k++) { m.prev_i4_flag[k] = (int8_t)r.bit(); m.rem_i4_mode[k] = m.prev_i4_flag[k] ? 0 : (int8_t)r.get(3); }
+        m.chroma_mode = (uint8_t)r.ue();
+      } else if (t <= 24) {
+        m.mb_type = MBT_I16x16;
+        const int v = t - 1;
+        m.i16_mode = (uint8_t)(v & 3);
+        cbp = (((v >> 2) % 3) << 4) | (v >= 12 ? 15 : 0);
+        m.chroma_mode = (uint8_t)r.ue();
+      } else return PARSE_UNSUPPORTED;                        // I_PCM
+      if (m.chroma_mode > 3) return PARSE_INVALID;
+    }
+    if (cbp < 0) {
+      cbp = cbp_from_code((int)r.ue(), m.mb_type == MBT_I4x4);
+      if (cbp < 0) return PARSE_INVALID;
+    }
+    m.cbp = (uint8_t)cbp;
+    const int cbp_l = cbp & 15, cbp_c = cbp >> 4;
+    if (cbp > 0 || m.mb_type == MBT_I16x16) {
+      qp += r.se();
+      if (qp < 0 || qp > 51) return PARSE_INVALID;
+      const int8_t* L = mbx > 0 ? pic->mbs[idx - 1].nnz : nullptr;
+      const int8_t* T = mby > 0 ? pic->mbs[idx - mbw].nnz : nullptr;
+      auto luma_nc = [&](int bx, int by) {
+        const int a = bx > 0 ? m.nnz[by * 4 + bx - 1] : (L ? L[by * 4 + 3] : -1);
+        const int b = by > 0 ? m.nnz[(by - 1) * 4 + bx] : (T ? T[12 + bx] : -1);
+        return nc_of(a, b);
+      };
+      int rc;
+      if (m.mb_type == MBT_I16x16 && (rc = read_block(r, m.luma_dc, 16, luma_nc(0, 0))) < 0) return rc;
+      for (int k = 0; k < 16; k++) {
+        if (!(cbp_l & (1 << (k >> 2)))) continue;
+        const int bx = (k & 1) | ((k >> 1) & 2), by = ((k >> 1) & 1) | ((k >> 2) & 2);
+        rc = read_block(r, m.luma[k], m.mb_type == MBT_I16x16 ? 15 : 16, luma_nc(bx, by));
+        if (rc < 0) return rc;
+        m.nnz[by * 4 + bx] = (int8_t)rc;
+      }
+      if (cbp_c) {
+        if ((rc = read_block(r, m.chroma_dc[0], 4, -1)) < 0) return rc;
+        if ((rc = read_block(r, m.chroma_dc[1], 4, -1)) < 0) return rc;
+        if (cbp_c == 2) {
+          for (int uv = 0; uv < 2; uv++)
+            for (int j = 0; j < 4; j++) {
+              const int bx = j & 1, by = j >> 1, base = 16 + 4 * uv;
+              const int a = bx > 0 ? m.nnz[base + by * 2] : (L ? L[base + by * 2 + 1] : -1);
+              const int b = by > 0 ? m.nnz[base + bx] : (T ? T[base + 2 + bx] : -1);
+              rc = read_block(r, m.chroma_ac[4 * uv + j], 15, nc_of(a, b));
+              if (rc < 0) return rc;
+              m.nnz[base + j] = (int8_t)rc;
+            }
+        }
+      }
+    }
+    m.qp = (uint8_t)qp;
+    if (!r.ok()) return PARSE_TRUNCATED;
+    idx++;
+    if (!is_p && idx < n && !r.more_data()) return PARSE_INVALID;
+    if (is_p && idx < n && !r.more_data()) return PARSE_INVALID;
+  }
+  return PARSE_OK;
+}
+
+}  // namespace
+
+int parse_access_unit(const uint8_t* au, size_t len, ParserState* st, ParsedPicture* pic) {
+  if (!au || !st || !pic) return PARSE_INVALID;
+  bool got_slice = false;
+  for (const Nal& nal : split_nals(au, len)) {
+    BitReader r(nal.rbsp.data(), nal.rbsp.size());
+    int rc = PARSE_OK;
+    if (nal.type == 7) rc = parse_sps(r, st);
+    else if (nal.type == 8) rc = parse_pps(r, st);
+    else if (nal.type == 1 || nal.type == 5) {
+      if (got_slice) return PARSE_UNSUPPORTED;                // several slices per picture
+      rc = parse_slice(r, nal, st, pic);
+      got_slice = true;
+    } else if (nal.type == 6 || nal.type == 9 || nal.type == 12) continue;   // SEI, AUD, filler: nothing to reconstruct
+    else return PARSE_UNSUPPORTED;
+    if (rc != PARSE_OK) return rc;
+  }
+  return got_slice ? PARSE_OK : PARSE_INVALID;
+}
+
+}  // namespace b2h264

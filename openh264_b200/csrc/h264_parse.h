@@ -1,0 +1,48 @@
+// h264_parse.h — host-side bitstream PARSER: the inverse of h264_bitstream.{h,cpp} for the stream class this
+// library produces (Baseline, CAVLC, one slice per picture, one reference frame, I and P slices, 8x8 as the
+// smallest partition).  Groundwork for the decoder construct path (SURVEY.md section 8f / DESIGN.md section 9): the
+// reference parses on the host too (codec/decoder/core/src/{au_parser,parse_mb_syn_cavlc,decode_slice}.cpp) and
+// hands macroblock arrays to the pixel stage; here the macroblock array is the same MbOut record the encoder's
+// entropy coder consumes, so "parse(write(x)) == x" is checked for every picture the host build encodes
+// (tests/emu) and the device-side construct stage can be the mirror image of the encoder's reconstruction.
+// Anything outside that stream class is REJECTED with an error code, never guessed.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "enc_types.h"
+#include "h264_bitstream.h"
+
+namespace b2h264 {
+
+enum ParseError {
+  PARSE_OK = 0,
+  PARSE_TRUNCATED = -1,        // ran out of bits
+  PARSE_UNSUPPORTED = -2,      // valid H.264 outside the supported class (CABAC, B slices, FMO, sub-8x8 partitions, ...)
+  PARSE_INVALID = -3,          // not valid H.264 syntax / values out of range
+  PARSE_NO_PARAMETER_SETS = -4 // a slice before its SPS / PPS
+};
+
+// parameter sets carried from access unit to access unit
+struct ParserState {
+  bool have_sps = false, have_pps = false;
+  StreamParams sp;               // width / height / mb_w / mb_h / crop / level / ids (num_ref_frames)
+  int log2_max_frame_num = 0;
+  int poc_type = 2, log2_max_poc_lsb = 0;
+  int pic_init_qp = 26;
+  bool deblocking_control = true;
+  int num_ref_idx_default = 1;
+};
+
+struct ParsedPicture {
+  SliceState ss;                 // idr, frame_num, idr_pic_id, slice qp
+  int disable_deblocking_idc = 0;
+  std::vector<MbOut> mbs;        // mb_w * mb_h records, same meaning as the encoder's hand-over records
+};
+
+// Parses one access unit: [SPS] [PPS] slice, each NAL behind a 3- or 4-byte start code.  Returns PARSE_OK or an error.
+int parse_access_unit(const uint8_t* au, size_t len, ParserState* st, ParsedPicture* pic);
+
+}  // namespace b2h264

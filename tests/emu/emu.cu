@@ -16,6 +16,7 @@
 #include "../../openh264_b200/csrc/h264_bitstream.h"
 
 #include "../../openh264_b200/csrc/enc_host.h"
+#include "../../openh264_b200/csrc/h264_parse.h"
 
 using namespace mbk;
 
@@ -69,6 +70,41 @@ struct HostFrameEncoder {
     return f;
   }
   bool packed_writer_ok = true;
+  // parser round trip (h264_parse.h): parse(write(records)) must give the records back
+  b2h264::ParserState parser;
+  int parse_status = 0;              // 0 ok, <0 ParseError, >0 = 1 + index of the first macroblock that differs
+  void check_parse(const std::vector<uint8_t>& au) {
+    b2h264::ParsedPicture pic;
+    const int rc = b2h264::parse_access_unit(au.data(), au.size(), &parser, &pic);
+    if (rc != 0) { parse_status = rc; return; }
+    if (pic.ss.idr != idr || pic.mbs.size() != out.size() || parser.sp.mb_w != ctl.sp.mb_w || parser.sp.width != ctl.sp.width ||
+        parser.sp.height != ctl.sp.height) { parse_status = -100; return; }
+    for (size_t i = 0; i < out.size(); i++) {
+      const MbOut& a = out[i];
+      const MbOut& b = pic.mbs[i];
+      bool same = a.mb_type == b.mb_type;
+      if (same && a.mb_type != MBT_PSKIP) {
+        same = a.cbp == b.cbp && memcmp(a.nnz, b.nnz, 24) == 0;
+        if (a.cbp > 0 || a.mb_type == MBT_I16x16) same = same && a.qp == b.qp;
+        if (MBT_IS_INTRA(a.mb_type)) same = same && a.chroma_mode == b.chroma_mode;
+        if (a.mb_type == MBT_I16x16) same = same && a.i16_mode == b.i16_mode && memcmp(a.luma_dc, b.luma_dc, 32) == 0;
+        if (a.mb_type == MBT_I4x4)
+          for (int k = 0; k < 16; k++) same = same && a.prev_i4_flag[k] == b.prev_i4_flag[k] && (a.prev_i4_flag[k] || a.rem_i4_mode[k] == b.rem_i4_mode[k]);
+        const int nparts = a.mb_type == MBT_P16x16 ? 1 : (a.mb_type == MBT_P16x8 || a.mb_type == MBT_P8x16) ? 2 : a.mb_type == MBT_P8x8 ? 4 : 0;
+        for (int k = 0; k < nparts; k++) same = same && a.mvd[k][0] == b.mvd[k][0] && a.mvd[k][1] == b.mvd[k][1];
+        for (int k = 0; k < 16 && same; k++) {
+          const int bx = (k & 1) | ((k >> 1) & 2), by = ((k >> 1) & 1) | ((k >> 2) & 2);
+          if (!(a.cbp & (1 << (k >> 2))) || a.nnz[by * 4 + bx] == 0) continue;     // not coded / written as empty
+          same = memcmp(a.luma[k], b.luma[k], (a.mb_type == MBT_I16x16 ? 15 : 16) * 2) == 0;
+        }
+        if (same && (a.cbp >> 4)) same = memcmp(a.chroma_dc, b.chroma_dc, 16) == 0;
+        if (same && (a.cbp >> 4) == 2)
+          for (int j = 0; j < 8 && same; j++)
+            if (a.nnz[16 + j] > 0) same = memcmp(a.chroma_ac[j], b.chroma_ac[j], 30) == 0;
+      }
+      if (!same) { parse_status = 1 + (int)i; return; }
+    }
+  }
   void finish_frame(std::vector<uint8_t>* bs) {
     // the product hands the host only the coded macroblocks' records plus an index table (k_pack_records):
     // write the access unit through that form too and insist on the same bytes
@@ -88,6 +124,7 @@ struct HostFrameEncoder {
       if (a != b) packed_writer_ok = false;
     }
     ctl.write_access_unit(idr, out.data(), bs);
+    if (parse_status == 0) check_parse(*bs);
     have_ref_p = !idr;
     cur_rec = 1 - cur_rec;            // the picture just reconstructed becomes the reference
   }
@@ -165,6 +202,7 @@ extern "C" long emu_encode(const uint8_t* yuv, int w, int h, int nframes, int qp
     g_last_out = enc.out; g_last_info = enc.mbi;
     enc.finish_frame(&bs);
     if (!enc.packed_writer_ok) return -9;          // packed hand-over form wrote different bytes
+    if (enc.parse_status != 0) return -1000 - (enc.parse_status < 0 ? -enc.parse_status : 100 + enc.parse_status);   // parser round trip failed
     if (total + (long)bs.size() > cap) return -1;
     memcpy(out + total, bs.data(), bs.size());
     total += bs.size();

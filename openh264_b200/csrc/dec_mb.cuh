@@ -1,0 +1,184 @@
+// dec_mb.cuh — decoder CONSTRUCT stage of one macroblock by one warp: prediction (intra / motion compensated) +
+// dequantisation + inverse transform + reconstruction from a parsed MbOut record (h264_parse.h).  It is the mirror
+// image of the encoder's reconstruction path and is built from the same pieces (mbk_mc / mbk_xform / enc_intra /
+// the MV-prediction cache of enc_inter.cuh), so what the encoder reconstructs and what this stage reconstructs from
+// the encoder's own bitstream are the same samples by construction — and both are checked against the reference
+// decoder (tests/test_decoder_emu.py runs the host build of this file against ISVCDecoder::DecodeFrameNoDelay).
+// Reference counterparts: codec/decoder/core/src/rec_mb.cpp (BaseMC :244, GetInterPred :462, RecI4x4Mb / RecI16x16Mb
+// :64-215), decode_mb_aux.cpp (IdctResAddPred_c :42), mv_pred.cpp (PredMv, PredPSkipMvFromNeighbor), parse side
+// ParseIntra4x4Mode (parse_mb_syn_cavlc.cpp).
+// STATUS: groundwork — host build only this round (the device kernel that batches it is the next step).
+#pragma once
+#include "enc_inter.cuh"
+
+namespace mbk {
+
+MBK_HD void unscan16(int16_t d[16], const int16_t lv[16]) {
+  for (int i = 0; i < 16; i++) d[zigzag_pos(i)] = lv[i];
+}
+MBK_HD void unscan15(int16_t d[16], const int16_t lv[16]) {     // AC levels: scan positions 1..15
+  d[0] = 0;
+  for (int i = 1; i < 16; i++) d[zigzag_pos(i)] = lv[i - 1];
+}
+
+// neighbour records only (the encoder's loader also fetches SAD history the decoder does not have)
+MBK_HD void dec_load_neighbors(const MbCtx& c, MbScratch& s) {
+  const int mbw = c.p.mb_w, idx = c.mby * mbw + c.mbx;
+  const int offs[4] = {-mbw - 1, -mbw, -mbw + 1, -1};
+  const int bits[4] = {NB_TOPLEFT, NB_TOP, NB_TOPRIGHT, NB_LEFT};
+  constexpr int kW = (int)(sizeof(MbInfo) / 4);
+  for (int i = lane_id(); i < 4 * kW; i += MBK_WS) {
+    const int k = i / kW, w = i - k * kW;
+    reinterpret_cast<uint32_t*>(&s.nbi[k])[w] =
+        (c.nb & bits[k]) ? ld_cg_u32(reinterpret_cast<const uint32_t*>(c.f.mbi + idx + offs[k]) + w) : 0u;
+  }
+  for (int k = lane_id(); k < 4; k += MBK_WS) { s.nb_sad[k] = 0; s.nb_skip_sad[k] = 0; }
+  warp_sync();
+}
+
+// luma residual of the 16 blocks into s.coef (dequantised, raster within a block), zero where nothing is coded
+MBK_HD void dec_luma_coef(MbScratch& s, const MbOut& m, int qp, bool i16, const int16_t* dcq) {
+  for (int k = lane_id(); k < 16; k += MBK_WS) {
+    int16_t d[16];
+    for (int i = 0; i < 16; i++) d[i] = 0;
+    if (m.cbp & (1 << (k >> 2))) {
+      if (i16) unscan15(d, m.luma[k]);
+      else unscan16(d, m.luma[k]);
+      dequant4x4(d, tbl_dequant(qp));
+    }
+    if (i16) d[0] = dcq[blk_raster(k)];
+    for (int i = 0; i < 16; i++) s.coef[16 * k + i] = d[i];
+  }
+  warp_sync();
+}
+
+MBK_HD void dec_chroma_coef(MbScratch& s, const MbOut& m, int qp_c) {
+  const int cbp_c = m.cbp >> 4;
+  for (int t = lane_id(); t < 8; t += MBK_WS) {
+    const int uv = t >> 2, j = t & 3;
+    int16_t d[16];
+    for (int i = 0; i < 16; i++) d[i] = 0;
+    if (cbp_c == 2) { unscan15(d, m.chroma_ac[t]); dequant4x4(d, tbl_dequant(qp_c)); }
+    if (cbp_c) {
+      int16_t dc[4] = {m.chroma_dc[uv][0], m.chroma_dc[uv][1], m.chroma_dc[uv][2], m.chroma_dc[uv][3]};
+      if (dc[0] | dc[1] | dc[2] | dc[3]) { dequant_ihadamard2x2_dc(dc, tbl_dequant(qp_c)[0]); d[0] = dc[j]; }
+    }
+    for (int i = 0; i < 16; i++) s.coef[256 + 64 * uv + 16 * j + i] = d[i];
+  }
+  warp_sync();
+}
+
+// One macroblock.  f.rec = picture being reconstructed, f.ref = reference picture (padded), f.mbi = MbInfo array of
+// the picture (neighbour lookups + what deblocking reads).  Raster / wavefront order like the encoder.
+MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch& s, int mbx, int mby, const MbOut& m) {
+  mb_ctx(s.ctx, p, f, mbx, mby);
+  if (lane_id() == 0) { s.ctx.qp = m.qp; s.ctx.qp_c = tbl_chroma_qp(m.qp); }
+  warp_sync();
+  const MbCtx& c = s.ctx;
+  {
+    uint32_t* a = reinterpret_cast<uint32_t*>(&s.info);
+    for (int i = lane_id(); i < (int)(sizeof(MbInfo) / 4); i += MBK_WS) a[i] = 0;
+  }
+  warp_sync();
+  dec_load_neighbors(c, s);
+  mb_load_borders(c, s);
+  const int type = m.mb_type, qp = m.qp, qp_c = c.qp_c;
+  if (lane_id() == 0) {
+    s.info.mb_type = (uint8_t)type; s.info.cbp = m.cbp;
+    for (int i = 0; i < 24; i++) s.info.nnz[i] = m.nnz[i];
+    s.info.ref_idx = MBT_IS_INTER(type) ? 0 : REF_NOT_IN_LIST;
+  }
+  warp_sync();
+  uint8_t* pl = s.pred_y[0];
+  uint8_t* pc = s.pred_c[0];
+  const bool L = (c.nb & NB_LEFT) != 0, T = (c.nb & NB_TOP) != 0;
+  if (MBT_IS_INTER(type)) {
+    fill_inter_cache(c, s);
+    const int nparts = type == MBT_P8x8 ? 4 : (type == MBT_P16x8 || type == MBT_P8x16) ? 2 : 1;
+    if (type == MBT_P8x8) { if (lane_id() == 0) { s.refc[9] = s.refc[21] = REF_NOT_AVAIL; } warp_sync(); }
+    for (int i = 0; i < nparts; i++) {
+      int blk = 0, w4 = 4, h4 = 4, px = 0, py = 0;
+      if (type == MBT_PSKIP) pred_skip_mv(s, &px, &py);
+      else if (type == MBT_P16x16) pred_mv(s, 0, 4, 0, &px, &py);
+      else if (type == MBT_P16x8) { blk = 8 * i; h4 = 2; pred_16x8_mv(s, blk, 0, &px, &py); }
+      else if (type == MBT_P8x16) { blk = 4 * i; w4 = 2; pred_8x16_mv(s, blk, 0, &px, &py); }
+      else { blk = 4 * i; w4 = 2; h4 = 2; pred_mv(s, blk, 2, 0, &px, &py); }
+      const int mvx = px + (type == MBT_PSKIP ? 0 : m.mvd[i][0]), mvy = py + (type == MBT_PSKIP ? 0 : m.mvd[i][1]);
+      cache_set(s, blk, w4, h4, mvx, mvy);
+      mb_mv_set(s, blk, w4, h4, mvx, mvy);
+      const int ox = blk_x(blk) * 4, oy = blk_y(blk) * 4, w = w4 * 4, h = h4 * 4;
+      // absolute quarter-sample position, clipped like BaseMC (rec_mb.cpp:248-253: the padded reference is 32 wide);
+      // luma and chroma both derive from the clipped position
+      int fx = ((c.mbx * 16 + ox) << 2) + mvx, fy = ((c.mby * 16 + oy) << 2) + mvy;
+      fx = clip3(fx, (-32 + 2) * 4, (c.p.mb_w * 16 + 32 - 19) * 4);
+      fy = clip3(fy, (-32 + 2) * 4, (c.p.mb_h * 16 + 32 - 19) * 4);
+      warp_mc_luma(c.f.ref[0] + (ptrdiff_t)(fy >> 2) * c.p.rec_stride_y + (fx >> 2), c.p.rec_stride_y, pl + oy * 16 + ox, 16, fx, fy, w, h);
+      for (int cpl = 0; cpl < 2; cpl++)
+        warp_mc_chroma(c.f.ref[1 + cpl] + (ptrdiff_t)(fy >> 3) * c.p.rec_stride_c + (fx >> 3), c.p.rec_stride_c,
+                       pc + 64 * cpl + (oy >> 1) * 8 + (ox >> 1), 8, fx, fy, w >> 1, h >> 1);
+      warp_sync();
+    }
+    warp_sync();
+    dec_luma_coef(s, m, qp, false, nullptr);
+    rec_luma_inter(s, pl);
+  } else if (type == MBT_I16x16) {
+    const int mode = m.i16_mode == 2 ? (L && T ? I16_DC : L ? I16_DC_L : T ? I16_DC_T : I16_DC_128) : m.i16_mode;
+    pred_i16(pl, tile_y(s.tile, 0, 0), TY_PITCH, mode);
+    warp_sync();
+    int16_t dcq[16];
+    unscan16(dcq, m.luma_dc);
+    bool any = false;
+    for (int i = 0; i < 16; i++) any = any || dcq[i] != 0;
+    if (any) {
+      if (qp < 12) { ihadamard4x4(dcq); dequant_luma_dc4x4(dcq, qp); }
+      else dequant_ihadamard4x4(dcq, (uint16_t)(tbl_dequant(qp)[0] >> 2));
+    }
+    dec_luma_coef(s, m, qp, true, dcq);
+    rec_luma_inter(s, pl);                       // inverse transform + prediction for all 16 blocks
+  } else {                                       // I4x4: block by block, each predicts from what was just reconstructed
+    fill_i4_cache(c, s);
+    for (int k = 0; k < 16; k++) {
+      const int bx = blk_x(k), by = blk_y(k);
+      uint8_t* org = tile_y(s.tile, bx * 4, by * 4);
+      const int lm = s.i4m[(by + 1) * 5 + bx], tm = s.i4m[by * 5 + bx + 1];
+      const int pm = (lm == -1 || tm == -1) ? 2 : (lm < tm ? lm : tm);
+      const int coded = m.prev_i4_flag[k] ? pm : (m.rem_i4_mode[k] < pm ? m.rem_i4_mode[k] : m.rem_i4_mode[k] + 1);
+      const int av = i4_avail(c.nb, k);
+      const int mode = coded == 2 ? ((av & 1) && (av & 2) ? I4_DC : (av & 1) ? I4_DC_L : (av & 2) ? I4_DC_T : I4_DC_128) : coded;
+      if (lane_id() == 0) {
+        s.i4m[(by + 1) * 5 + bx + 1] = (int8_t)coded;
+        s.info.i4_mode[by * 4 + bx] = (int8_t)coded;
+        // 8.3.1.2: when the top-right 4 samples are not available they are replaced by the last top sample.  (The
+        // encoder never selects DDL / VL in that situation, a decoder has to cope; the tile cells written here belong
+        // to a block that is decoded later or to nobody.)
+        if ((mode == I4_DDL || mode == I4_VL) && !(av & 8))
+          for (int i = 4; i < 8; i++) org[-TY_PITCH + i] = org[-TY_PITCH + 3];
+        uint8_t pr[16];
+        int16_t d[16];
+        for (int i = 0; i < 16; i++) d[i] = 0;
+        pred_i4(pr, org, TY_PITCH, mode);
+        if (m.cbp & (1 << (k >> 2))) { unscan16(d, m.luma[k]); dequant4x4(d, tbl_dequant(qp)); }
+        idct4x4_rec(org, TY_PITCH, pr, 4, d);
+      }
+      warp_sync();
+    }
+  }
+  if (MBT_IS_INTRA(type)) {
+    const int cm = m.chroma_mode == 0 ? (L && T ? C_DC : L ? C_DC_L : T ? C_DC_T : C_DC_128) : m.chroma_mode;
+    pred_chroma(pc, tile_c(s.tile.u, 0, 0), TC_PITCH, cm);
+    pred_chroma(pc + 64, tile_c(s.tile.v, 0, 0), TC_PITCH, cm);
+    warp_sync();
+  }
+  dec_chroma_coef(s, m, qp_c);
+  rec_chroma(s, pc);
+  mb_store_recon(c, s);
+  // what the neighbours and the deblocking filter read
+  if (lane_id() == 0) { s.info.qp = (uint8_t)qp; s.info.qp_c = (uint8_t)qp_c; }
+  warp_sync();
+  const uint32_t* si = reinterpret_cast<const uint32_t*>(&s.info);
+  uint32_t* di = reinterpret_cast<uint32_t*>(c.f.mbi + (mby * p.mb_w + mbx));
+  for (int i = lane_id(); i < (int)(sizeof(MbInfo) / 4); i += MBK_WS) di[i] = si[i];
+  warp_sync();
+}
+
+}  // namespace mbk

@@ -252,14 +252,18 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     if (r.bit()) n_ref = (int)r.ue() + 1;
     if (n_ref != 1) return PARSE_UNSUPPORTED;
     if (r.bit()) {                                            // ref_pic_list_modification_flag_l0
+      // the construct stage keeps ONE reference picture (the previous one): the only list modification that still
+      // selects it is "short-term, one picture back" (what the encoders this mirrors emit); anything else needs a DPB
       for (;;) {
         const uint32_t idc = r.ue();
         if (idc == 3) break;
         if (idc > 3 || !r.ok()) return PARSE_INVALID;
-        r.ue();
+        const uint32_t v = r.ue();
+        if (idc != 0 || v != 0) return PARSE_UNSUPPORTED;
       }
     }
   }
+  if (!nal.ref_idc) return PARSE_UNSUPPORTED;                 // non-reference pictures (temporal layers): needs a DPB
   if (nal.ref_idc) {                                          // dec_ref_pic_marking
     if (idr) { r.bit(); if (r.bit()) return PARSE_UNSUPPORTED; }
     else if (r.bit()) return PARSE_UNSUPPORTED;               // adaptive marking (MMCO)

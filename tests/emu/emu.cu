@@ -17,6 +17,7 @@
 
 #include "../../openh264_b200/csrc/enc_host.h"
 #include "../../openh264_b200/csrc/h264_parse.h"
+#include "../../openh264_b200/csrc/dec_mb.cuh"
 
 using namespace mbk;
 
@@ -210,4 +211,77 @@ extern "C" long emu_encode(const uint8_t* yuv, int w, int h, int nframes, int qp
     if (recon_out) enc.copy_recon(recon_out + i * fsz);
   }
   return total;
+}
+
+
+// ---- decoder construct path, host build (groundwork: dec_mb.cuh + h264_parse.h) ---------------------------------------
+// Decodes an Annex-B stream of the supported class; writes the cropped I420 pictures back to back into out.
+// Returns the number of pictures, or a negative error (-1000 - k: parse error k).
+extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, int* w, int* h) {
+  b2h264_build_host_tables();
+  b2h264::ParserState st;
+  std::vector<uint8_t> pic[2][3];
+  std::vector<MbInfo> mbi;
+  static MbScratch scratch;
+  int cur_rec = 0, frames = 0;
+  long outpos = 0;
+  bool have_buffers = false;
+  auto is_start = [&](long k) { return k + 2 < len && bs[k] == 0 && bs[k + 1] == 0 && bs[k + 2] == 1; };
+  long pos = 0;
+  while (pos + 3 < len && !is_start(pos)) pos++;
+  long au_begin = pos > 0 && bs[pos - 1] == 0 ? pos - 1 : pos;
+  while (pos + 3 < len) {
+    // walk NAL by NAL; an access unit ends with its (single) slice NAL
+    const int type = bs[pos + 3] & 31;
+    long next = pos + 3;
+    while (next + 3 < len && !is_start(next)) next++;
+    if (next + 3 >= len) next = len;
+    if (type == 1 || type == 5) {
+      long au_end = next;
+      if (au_end < len && au_end > 0 && bs[au_end - 1] == 0) au_end--;        // zero_byte of the next 4-byte start code
+      b2h264::ParsedPicture pp;
+      const int rc = b2h264::parse_access_unit(bs + au_begin, (size_t)(au_end - au_begin), &st, &pp);
+      if (rc != 0) return -1000 + rc;
+      b2h264::StreamCtl geo;                                                    // picture geometry helpers
+      geo.sp = st.sp;
+      if (!have_buffers) {
+        for (int b = 0; b < 2; b++) {
+          pic[b][0].assign((size_t)geo.rec_stride_y() * geo.rec_rows_y() + 64, 0);
+          pic[b][1].assign((size_t)geo.rec_stride_c() * geo.rec_rows_c() + 64, 0);
+          pic[b][2].assign((size_t)geo.rec_stride_c() * geo.rec_rows_c() + 64, 0);
+        }
+        mbi.assign((size_t)st.sp.mb_w * st.sp.mb_h, MbInfo());
+        have_buffers = true;
+      }
+      EncFrameParams p;
+      memset(&p, 0, sizeof(p));
+      p.mb_w = st.sp.mb_w; p.mb_h = st.sp.mb_h;
+      p.rec_stride_y = geo.rec_stride_y(); p.rec_stride_c = geo.rec_stride_c();
+      p.qp = pp.ss.qp; p.is_idr = pp.ss.idr; p.ref_is_p = !pp.ss.idr; p.mv_range = 64;
+      EncFramePtrs f;
+      memset(&f, 0, sizeof(f));
+      for (int pl = 0; pl < 3; pl++) {
+        const int pad = pl ? 16 : 32, stp = pl ? p.rec_stride_c : p.rec_stride_y;
+        f.rec[pl] = pic[cur_rec][pl].data() + (size_t)pad * stp + pad;
+        f.ref[pl] = pic[1 - cur_rec][pl].data() + (size_t)pad * stp + pad;
+      }
+      f.mbi = mbi.data();
+      for (int mby = 0; mby < p.mb_h; mby++)
+        for (int mbx = 0; mbx < p.mb_w; mbx++) dec_one_mb(p, f, scratch, mbx, mby, pp.mbs[(size_t)mby * p.mb_w + mbx]);
+      if (pp.disable_deblocking_idc != 1) deblock_frame_host(p, f);
+      expand_frame_host(p, f);
+      const int W = st.sp.width, H = st.sp.height;
+      *w = W; *h = H;
+      if (outpos + (long)W * H * 3 / 2 > cap) return -2;
+      for (int pl = 0; pl < 3; pl++) {
+        const int pw = pl ? W / 2 : W, ph = pl ? H / 2 : H, stp = pl ? p.rec_stride_c : p.rec_stride_y;
+        for (int y = 0; y < ph; y++) { memcpy(out + outpos, f.rec[pl] + (size_t)y * stp, pw); outpos += pw; }
+      }
+      frames++;
+      cur_rec = 1 - cur_rec;
+      au_begin = au_end;
+    }
+    pos = next;
+  }
+  return frames > 0 ? frames : -3;          // nothing decodable is an error, not an empty success
 }

@@ -1,0 +1,112 @@
+"""Decoder construct path, CPU side (groundwork for the next SURVEY section-8 row): the host build of
+openh264_b200/csrc/dec_mb.cuh (prediction + dequant + inverse transform + reconstruction from parsed macroblock
+records, then the same deblocking code the encoder path uses) behind the host bitstream parser
+(openh264_b200/csrc/h264_parse.cpp) must reproduce the reference decoder's pictures bit for bit
+(ISVCDecoder::DecodeFrameNoDelay through oracle/_ref) on streams the REFERENCE ENCODER produced.
+The device kernel that batches this stage does not exist yet; the product decoder entry points still fail loudly."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import h264lib
+
+ROOT = h264lib.ROOT
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tests", "emu")])
+    E = C.CDLL(os.path.join(ROOT, "tests", "emu", "libb2h264_emu.so"))
+    E.emu_decode.restype = C.c_int
+    E.emu_decode.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    return E
+
+
+def ref_decode(bs):
+    R = C.CDLL(h264lib.REFSHIM_SO)
+    R.ref_decode.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    out = np.zeros(64 << 20, np.uint8)
+    w, h, s = C.c_int(), C.c_int(), C.c_double()
+    a = np.frombuffer(bs, np.uint8)
+    n = R.ref_decode(a.ctypes.data, len(a), out.ctypes.data, out.size, C.byref(w), C.byref(h), C.byref(s))
+    return n, w.value, h.value, out[:max(0, n) * w.value * h.value * 3 // 2]
+
+
+CASES = [(176, 144, 6, 26, 1), (176, 144, 5, 0, 2), (176, 144, 5, 51, 2), (320, 192, 6, 30, 3), (180, 148, 5, 24, 4),
+         (16, 16, 4, 26, 5), (640, 360, 4, 34, 6), (64, 256, 4, 18, 7)]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_host_decoder_matches_reference_decoder(emu, case):
+    if not h264lib.have_ref():
+        pytest.skip("reference build not on this machine")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_encoder_golden import ref_encode
+    w, h, n, qp, seed = case
+    yuv = h264lib.synth_clip(w, h, n, seed=seed)
+    bs, _, _ = ref_encode(yuv, w, h, n, qp, 30.0)                      # stream from the REFERENCE encoder
+    bs = bytes(bs)
+    nr, rw, rh, want = ref_decode(bs)
+    assert nr == n and (rw, rh) == (w, h)
+    a = np.frombuffer(bs, np.uint8)
+    out = np.zeros(n * w * h * 3 // 2 + 64, np.uint8)
+    W, H = C.c_int(), C.c_int()
+    got_n = emu.emu_decode(a.ctypes.data, len(a), out.ctypes.data, out.size, C.byref(W), C.byref(H))
+    assert got_n == n, got_n
+    assert (W.value, H.value) == (w, h)
+    fsz = w * h * 3 // 2
+    for f in range(n):
+        assert np.array_equal(out[f * fsz:(f + 1) * fsz], want[f * fsz:(f + 1) * fsz]), "picture %d differs" % f
+
+
+def test_host_decoder_on_the_references_own_clip(emu):
+    clip = "/root/reference/res/CiscoVT2people_320x192_12fps.yuv"
+    if not (h264lib.have_ref() and os.path.exists(clip)):
+        pytest.skip("reference build / clip not on this machine")
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_encoder_golden import ref_encode
+    yuv = np.fromfile(clip, dtype=np.uint8)
+    bs = bytes(ref_encode(yuv, 320, 192, 9, 28, 12.0)[0])
+    nr, rw, rh, want = ref_decode(bs)
+    a = np.frombuffer(bs, np.uint8)
+    out = np.zeros(want.size + 64, np.uint8)
+    W, H = C.c_int(), C.c_int()
+    assert emu.emu_decode(a.ctypes.data, len(a), out.ctypes.data, out.size, C.byref(W), C.byref(H)) == nr == 9
+    assert np.array_equal(out[:want.size], want)
+
+
+def test_unsupported_streams_are_rejected_not_guessed(emu):
+    """a CABAC / B-frame stream of the reference's test set must come back as a parse error, never as pictures"""
+    path = "/root/reference/res/test_cif_P_CABAC_slice.264"
+    if not os.path.exists(path):
+        pytest.skip("reference bitstreams not on this machine")
+    a = np.fromfile(path, dtype=np.uint8)
+    out = np.zeros(1 << 20, np.uint8)
+    W, H = C.c_int(), C.c_int()
+    assert emu.emu_decode(a.ctypes.data, len(a), out.ctypes.data, out.size, C.byref(W), C.byref(H)) < 0
+
+
+def test_reference_conformance_table_exact_or_rejected(emu):
+    """every bitstream of the reference's decoder golden table (test/api/decoder_test.cpp) either decodes to the
+    PUBLISHED hash or is rejected as outside the supported stream class — never a wrong picture"""
+    import hashlib
+    import json
+    tab = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_decoder_hashes.json")))["pairs"]
+    if not os.path.exists("/root/reference/" + tab[0][0]):
+        pytest.skip("reference bitstreams not on this machine")
+    out = np.zeros(400 << 20, np.uint8)
+    exact, wrong = [], []
+    for path, sha in tab:
+        a = np.fromfile("/root/reference/" + path, dtype=np.uint8)
+        W, H = C.c_int(), C.c_int()
+        n = emu.emu_decode(a.ctypes.data, len(a), out.ctypes.data, out.size, C.byref(W), C.byref(H))
+        if n < 0:
+            continue
+        h = hashlib.sha1(out[:n * W.value * H.value * 3 // 2].tobytes()).hexdigest()
+        (exact if h == sha else wrong).append(os.path.basename(path))
+    assert not wrong, wrong
+    assert {"BA1_Sony_D.jsv", "NL1_Sony_D.jsv", "SVA_BA1_B.264", "SVA_NL1_B.264"} <= set(exact)

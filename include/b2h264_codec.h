@@ -77,6 +77,24 @@ int  b2h264_enc_set_stream (b2h264_enc* e, void* stream);
 
 /* layer 3 (WelsCreateSVCEncoder / ISVCEncoder, codec_api.h:272-339,545-586) is declared in b2h264_wels_api.h */
 
+/* ---- batched decoder (first device version of the decoder construct path) -----------------
+ * Replaces, for Baseline / CAVLC / one slice per picture / one reference frame / partitions >= 8x8 streams (what this
+ * library's encoder and the reference encoder in the same configuration produce), ISVCDecoder::DecodeFrameNoDelay
+ * (codec/api/wels/codec_api.h:383; codec/decoder/plus/src/welsDecoderExt.cpp:~700).  The host parses, the GPU
+ * reconstructs, deblocks and pads.  Anything else is rejected: -101 truncated, -102 unsupported stream feature,
+ * -103 invalid syntax, -104 slice before its parameter sets; -2 picture size differs from the configuration. */
+typedef struct b2h264_dec b2h264_dec;
+typedef struct {
+  int32_t width, height;        /* cropped picture size the streams must have */
+  int32_t n_streams;            /* independent streams decoded per call */
+  int32_t device;               /* CUDA device ordinal */
+} b2h264_dec_config;
+int  b2h264_dec_create (const b2h264_dec_config* cfg, b2h264_dec** out);
+void b2h264_dec_destroy (b2h264_dec* d);
+/* au[s] / au_bytes[s]: one access unit ([SPS PPS] slice, Annex B) of stream s; yuv[s]: host buffer for the decoded
+ * picture, tightly packed I420 of width x height.  Synchronous. */
+int  b2h264_dec_decode (b2h264_dec* d, const uint8_t* const* au, const int32_t* au_bytes, uint8_t* const* yuv);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,9 @@ API = {
     "b2h264_enc_get_recon": [vp, C.c_int, vp],
     "b2h264_enc_last_timing": [vp, C.POINTER(C.c_float)],
     "b2h264_enc_last_d2h_bytes": [vp, C.POINTER(C.c_ulonglong)],
+    "b2h264_dec_create": [vp, C.POINTER(vp)],
+    "b2h264_dec_destroy": [vp],
+    "b2h264_dec_decode": [vp, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(vp)],
     "b2h264_enc_set_stream": [vp, vp],
     "b2h264_table_quant_ff": [C.c_int],
     "b2h264_table_quant_mf": [C.c_int],
@@ -91,7 +94,7 @@ class EncConfig(C.Structure):
                 ("device", C.c_int32), ("sps_pps_id_strategy", C.c_int32)]
 
 
-_RESTYPES = {"b2h264_enc_destroy": None, "b2h264_error_string": C.c_char_p, "b2h264_launch_count": C.c_ulonglong,
+_RESTYPES = {"b2h264_enc_destroy": None, "b2h264_dec_destroy": None, "b2h264_error_string": C.c_char_p, "b2h264_launch_count": C.c_ulonglong,
              "b2h264_table_quant_ff": i16p, "b2h264_table_quant_mf": i16p, "b2h264_table_dequant": u16p}
 
 _lib = None
@@ -233,3 +236,34 @@ class BatchEncoder:
             self.close()
         except Exception:
             pass
+
+
+class DecConfig(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("n_streams", C.c_int32), ("device", C.c_int32)]
+
+
+class BatchDecoder:
+    """include/b2h264_codec.h b2h264_dec_*: one access unit per stream per call -> one I420 picture per stream."""
+
+    def __init__(self, width, height, n_streams=1, device=0):
+        self.L = lib(device)
+        self.cfg = DecConfig(width, height, n_streams, device)
+        self.h = vp()
+        check(self.L.b2h264_dec_create(C.byref(self.cfg), C.byref(self.h)))
+        self.n = n_streams
+        self.frame_bytes = width * height * 3 // 2
+
+    def decode(self, access_units):
+        """access_units: list of n_streams bytes objects; returns a list of numpy uint8 pictures (packed I420)."""
+        bufs = [np.frombuffer(bytes(a), np.uint8) for a in access_units]
+        outs = [np.empty(self.frame_bytes, np.uint8) for _ in range(self.n)]
+        au = (vp * self.n)(*[b.ctypes.data for b in bufs])
+        nb = (C.c_int32 * self.n)(*[len(b) for b in bufs])
+        yo = (vp * self.n)(*[o.ctypes.data for o in outs])
+        check(self.L.b2h264_dec_decode(self.h, au, nb, yo))
+        return outs
+
+    def close(self):
+        if self.h:
+            self.L.b2h264_dec_destroy(self.h)
+            self.h = None

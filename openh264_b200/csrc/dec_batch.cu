@@ -1,0 +1,137 @@
+// dec_batch.cu — layer-2 batched decoder: S independent streams, one access unit per stream per call.
+// Host: Annex-B parsing (h264_parse.cpp, like the reference parses on the host: codec/decoder/core/src/au_parser.cpp,
+// parse_mb_syn_cavlc.cpp), device: reconstruction of every macroblock by one warp (dec_mb.cuh, k_decode_mbs),
+// in-loop deblocking and border replication (the encoder's kernels).  Replaces, for the supported stream class,
+// CWelsDecoder::DecodeFrameNoDelay -> WelsDecodeBs -> DecodeCurrentAccessUnit -> WelsTargetSliceConstruction /
+// WelsTargetMbConstruction (codec/decoder/core/src/decoder_core.cpp, decode_slice.cpp:~100) and
+// WelsDeblockingFilterSlice (deblocking.cpp).  Streams outside the class are rejected with the parser's error
+// code; there is no CPU reconstruction path in this library.
+// STATUS: first device version of the next SURVEY row: synchronous, not yet pipelined.
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/b2h264_codec.h"
+#include "b2h264_internal.h"
+#include "enc_host.h"
+#include "enc_launch.h"
+#include "h264_parse.h"
+
+using namespace b2h264;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+struct b2h264_dec {
+  b2h264_dec_config cfg;
+  int S = 0, mb_w = 0, mb_h = 0, n_mb = 0;
+  StreamCtl geo;                          // picture geometry (strides, padded rows)
+  std::vector<ParserState> parser;
+  int cur_rec = 0;
+  cudaStream_t st = nullptr;
+  uint8_t* d_pic[2] = {nullptr, nullptr};
+  MbInfo* d_mbi = nullptr;
+  MbOut* d_recs = nullptr;
+  MbOut* h_recs = nullptr;                // pinned
+  StreamFrame* d_sf = nullptr;
+  StreamFrame* h_sf = nullptr;            // pinned
+  int* d_ws = nullptr;
+  size_t pic_bytes = 0, pic_y_bytes = 0, pic_c_bytes = 0;
+  int last_error_stream = -1;
+
+  uint8_t* plane0(int set, int s, int pl) const {
+    const int sty = geo.rec_stride_y(), stc = geo.rec_stride_c();
+    uint8_t* base = d_pic[set] + (size_t)s * pic_bytes;
+    if (pl == 0) return base + (size_t)32 * sty + 32;
+    return base + pic_y_bytes + (size_t)(pl - 1) * pic_c_bytes + (size_t)16 * stc + 16;
+  }
+};
+
+extern "C" {
+
+int b2h264_dec_create(const b2h264_dec_config* cfg, b2h264_dec** out) {
+  if (!cfg || !out) return -1;
+  if (cfg->width < 16 || cfg->height < 16 || (cfg->width & 1) || (cfg->height & 1) || cfg->n_streams < 1) return -2;
+  int rc = b2h264_init(cfg->device);
+  if (rc) return rc;
+  if ((rc = enc_upload_deblock_tables())) return rc;
+  b2h264_dec* d = new b2h264_dec();
+  d->cfg = *cfg;
+  d->S = cfg->n_streams;
+  d->geo.init(cfg->width, cfg->height, 26, 30.0f, 0);
+  d->mb_w = d->geo.sp.mb_w; d->mb_h = d->geo.sp.mb_h; d->n_mb = d->mb_w * d->mb_h;
+  d->parser.resize(d->S);
+  d->pic_y_bytes = (size_t)d->geo.rec_stride_y() * d->geo.rec_rows_y();
+  d->pic_c_bytes = (size_t)d->geo.rec_stride_c() * d->geo.rec_rows_c();
+  d->pic_bytes = d->pic_y_bytes + 2 * d->pic_c_bytes;
+  const size_t S = d->S;
+  CK(cudaStreamCreateWithFlags(&d->st, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    CK(cudaMalloc(&d->d_pic[i], S * d->pic_bytes + 256));
+    CK(cudaMemset(d->d_pic[i], 0, S * d->pic_bytes + 256));
+  }
+  CK(cudaMalloc(&d->d_mbi, S * d->n_mb * sizeof(MbInfo)));
+  CK(cudaMemset(d->d_mbi, 0, S * d->n_mb * sizeof(MbInfo)));
+  CK(cudaMalloc(&d->d_recs, S * d->n_mb * sizeof(MbOut)));
+  CK(cudaMallocHost(&d->h_recs, S * d->n_mb * sizeof(MbOut)));
+  CK(cudaMalloc(&d->d_sf, S * sizeof(StreamFrame)));
+  CK(cudaMallocHost(&d->h_sf, S * sizeof(StreamFrame)));
+  CK(cudaMalloc(&d->d_ws, dec_sched_ints((int)S, d->n_mb) * sizeof(int)));
+  *out = d;
+  return 0;
+}
+
+void b2h264_dec_destroy(b2h264_dec* d) {
+  if (!d) return;
+  cudaSetDevice(d->cfg.device);
+  if (d->st) cudaStreamSynchronize(d->st);
+  for (int i = 0; i < 2; i++) cudaFree(d->d_pic[i]);
+  cudaFree(d->d_mbi); cudaFree(d->d_recs); cudaFree(d->d_sf); cudaFree(d->d_ws);
+  cudaFreeHost(d->h_recs); cudaFreeHost(d->h_sf);
+  if (d->st) cudaStreamDestroy(d->st);
+  delete d;
+}
+
+int b2h264_dec_decode(b2h264_dec* d, const uint8_t* const* au, const int32_t* au_bytes, uint8_t* const* yuv) {
+  if (!d || !au || !au_bytes || !yuv) return -1;
+  CK(cudaSetDevice(d->cfg.device));
+  const int S = d->S, rec = d->cur_rec;
+  int deblock = 1;
+  for (int s = 0; s < S; s++) {
+    ParsedPicture pic;
+    const int rc = parse_access_unit(au[s], (size_t)au_bytes[s], &d->parser[s], &pic);
+    if (rc != PARSE_OK) { d->last_error_stream = s; return -100 + rc; }          // -101 truncated, -102 unsupported, -103 invalid, -104 no parameter sets
+    const StreamParams& sp = d->parser[s].sp;
+    if (sp.mb_w != d->mb_w || sp.mb_h != d->mb_h || sp.width != d->cfg.width || sp.height != d->cfg.height) { d->last_error_stream = s; return -2; }
+    const int want_deblock = pic.disable_deblocking_idc != 1;
+    if (s == 0) deblock = want_deblock;
+    else if (want_deblock != deblock) { d->last_error_stream = s; return -2; }   // one setting per batch
+    memcpy(d->h_recs + (size_t)s * d->n_mb, pic.mbs.data(), (size_t)d->n_mb * sizeof(MbOut));
+    StreamFrame& F = d->h_sf[s];
+    memset(&F, 0, sizeof(F));
+    F.p.mb_w = d->mb_w; F.p.mb_h = d->mb_h;
+    F.p.rec_stride_y = d->geo.rec_stride_y(); F.p.rec_stride_c = d->geo.rec_stride_c();
+    F.p.qp = pic.ss.qp; F.p.is_idr = pic.ss.idr; F.p.ref_is_p = !pic.ss.idr; F.p.mv_range = 64;
+    for (int pl = 0; pl < 3; pl++) { F.f.rec[pl] = d->plane0(rec, s, pl); F.f.ref[pl] = d->plane0(1 - rec, s, pl); }
+    F.f.mbi = d->d_mbi + (size_t)s * d->n_mb;
+  }
+  CK(cudaMemcpyAsync(d->d_recs, d->h_recs, (size_t)S * d->n_mb * sizeof(MbOut), cudaMemcpyHostToDevice, d->st));
+  CK(cudaMemcpyAsync(d->d_sf, d->h_sf, (size_t)S * sizeof(StreamFrame), cudaMemcpyHostToDevice, d->st));
+  const int rc = dec_launch_frame(d->d_sf, S, d->mb_w, d->mb_h, d->d_ws, d->d_recs, deblock, d->st);
+  if (rc) return rc;
+  const int w = d->cfg.width, h = d->cfg.height;
+  for (int s = 0; s < S; s++) {
+    uint8_t* dst = yuv[s];
+    for (int pl = 0; pl < 3; pl++) {
+      const int pw = pl ? w / 2 : w, ph = pl ? h / 2 : h;
+      const int stp = pl ? d->geo.rec_stride_c() : d->geo.rec_stride_y();
+      CK(cudaMemcpy2DAsync(dst, pw, d->plane0(rec, s, pl), stp, pw, ph, cudaMemcpyDeviceToHost, d->st));
+      dst += (size_t)pw * ph;
+    }
+  }
+  CK(cudaStreamSynchronize(d->st));
+  d->cur_rec = 1 - rec;
+  return 0;
+}
+
+}  // extern "C"

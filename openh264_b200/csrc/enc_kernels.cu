@@ -13,6 +13,7 @@
 #define B2H264_WITH_INTER 1
 #include "enc_deblock.cuh"
 #include "enc_frame.cuh"
+#include "dec_mb.cuh"
 #include "enc_launch.h"
 
 using namespace mbk;
@@ -309,6 +310,19 @@ __global__ void __launch_bounds__(32 * ENC_WPC) k_deblock_mbs(const StreamFrame*
   run_mbs(sf, n_streams, q, [&](const StreamFrame& F, int x, int y) { deblock_one_mb(F.p, F.f, x, y); });
 }
 
+// ---- decoder construct path (groundwork of the next SURVEY row: dec_mb.cuh) ------------------------------------------------
+// One warp reconstructs one macroblock from its parsed record (h264_parse.h); the macroblocks of all streams are
+// scheduled by the same dependency rule as the encoder (left + top-right done), with the simple per-warp ready list.
+__global__ void __launch_bounds__(32 * ENC_WPC) k_decode_mbs(const StreamFrame* __restrict__ sf, int n_streams, Sched q,
+                                                            const MbOut* __restrict__ recs) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  MbScratch& s = reinterpret_cast<MbScratch*>(smem)[threadIdx.x >> 5];
+  run_mbs(sf, n_streams, q, [&](const StreamFrame& F, int x, int y) {
+    const int n_mb = F.p.mb_w * F.p.mb_h, si = (int)(&F - sf);
+    dec_one_mb(F.p, F.f, s, x, y, recs[(size_t)si * n_mb + y * F.p.mb_w + x]);
+  });
+}
+
 // ---- border replication, all planes of all streams in two launches -------------------------------------------
 __global__ void k_expand_lr_batch(const StreamFrame* __restrict__ sf) {
   const StreamFrame& F = sf[blockIdx.z / 3];
@@ -426,6 +440,48 @@ int enc_launch_deblock_expand(const StreamFrame* d_sf, int n_streams, int mb_w, 
   if (blocks > need) blocks = need;
   k_deblock_mbs<<<blocks, 32 * ENC_WPC, 0, st>>>(d_sf, n_streams, make_sched(d_ws, 1, total));
   if ((rc = b2h264_launched())) return rc;
+  k_expand_lr_batch<<<dim3((mb_h * 16 + 7) / 8, 1, 3 * n_streams), dim3(32, 8), 0, st>>>(d_sf);
+  if ((rc = b2h264_launched())) return rc;
+  k_expand_tb_batch<<<dim3((mb_w * 16 + 64 + 127) / 128, 4, 3 * n_streams), dim3(128), 0, st>>>(d_sf);
+  return b2h264_launched();
+}
+
+// decoder: workspace (ints) = [0..3] heads / tails, then dep[2][total], then queue[2][total] (construct, deblock)
+size_t dec_sched_ints(int n_streams, int n_mb) { return 8 + 4 * (size_t)n_streams * n_mb; }
+static Sched make_dec_sched(int* ws, int which, int total) {
+  Sched q;
+  q.head = ws + 2 * which; q.tail = ws + 2 * which + 1;
+  q.dep = ws + 8 + (size_t)which * total;
+  q.queue = ws + 8 + (size_t)(2 + which) * total;
+  return q;
+}
+int dec_launch_frame(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h, int* d_ws, const MbOut* d_recs, int deblock,
+                     cudaStream_t st) {
+  static int blocks_per_launch = 0;
+  if (!blocks_per_launch) {
+    cudaFuncSetAttribute(k_decode_mbs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MbScratch) * ENC_WPC));
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_mbs, 32 * ENC_WPC, sizeof(MbScratch) * ENC_WPC);
+    blocks_per_launch = sms * (per_sm < 1 ? 1 : per_sm);
+  }
+  int rc;
+  const int total = n_streams * mb_w * mb_h;
+  cudaMemsetAsync(d_ws + 8, 0, 2 * (size_t)total * sizeof(int), st);
+  cudaMemsetAsync(d_ws + 8 + 2 * (size_t)total, 0xff, 2 * (size_t)total * sizeof(int), st);
+  const Sched qc = make_dec_sched(d_ws, 0, total), qd = make_dec_sched(d_ws, 1, total);
+  k_sched_init<<<(n_streams + 127) / 128, 128, 0, st>>>(qc, n_streams, mb_w * mb_h);
+  k_sched_init<<<(n_streams + 127) / 128, 128, 0, st>>>(qd, n_streams, mb_w * mb_h);
+  const int need = (total + ENC_WPC - 1) / ENC_WPC;
+  k_decode_mbs<<<blocks_per_launch < need ? blocks_per_launch : need, 32 * ENC_WPC, sizeof(MbScratch) * ENC_WPC, st>>>(d_sf, n_streams, qc, d_recs);
+  if ((rc = b2h264_launched())) return rc;
+  if (deblock) {
+    int blocks = enc_grid_blocks() * 2;
+    if (blocks > need) blocks = need;
+    k_deblock_mbs<<<blocks, 32 * ENC_WPC, 0, st>>>(d_sf, n_streams, qd);
+    if ((rc = b2h264_launched())) return rc;
+  }
   k_expand_lr_batch<<<dim3((mb_h * 16 + 7) / 8, 1, 3 * n_streams), dim3(32, 8), 0, st>>>(d_sf);
   if ((rc = b2h264_launched())) return rc;
   k_expand_tb_batch<<<dim3((mb_w * 16 + 64 + 127) / 128, 4, 3 * n_streams), dim3(128), 0, st>>>(d_sf);

@@ -28,7 +28,7 @@ enum ParseError {
 // parameter sets carried from access unit to access unit
 struct ParserState {
   bool have_sps = false, have_pps = false;
-  StreamParams sp;               // width / height / mb_w / mb_h / crop / level / ids (num_ref_frames)
+  StreamParams sp{};             // width / height / mb_w / mb_h / crop / level / ids (num_ref_frames)
   int log2_max_frame_num = 0;
   int poc_type = 2, log2_max_poc_lsb = 0;
   int pic_init_qp = 26;

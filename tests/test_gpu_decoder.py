@@ -1,0 +1,61 @@
+"""Decoder construct path on the GPU (include/b2h264_codec.h b2h264_dec_*): host parser + one warp per macroblock
+(k_decode_mbs) + the encoder path's deblocking / padding kernels must reproduce the reference decoder's pictures
+bit for bit on streams produced by the REFERENCE encoder; batches of different streams decode independently."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import h264lib
+
+pytestmark = pytest.mark.gpu
+ROOT = h264lib.ROOT
+
+
+def ref_streams(w, h, n, qp, seeds):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_encoder_golden import ref_encode
+    out = []
+    for seed in seeds:
+        yuv = h264lib.synth_clip(w, h, n, seed=seed)
+        bs, fb, _ = ref_encode(yuv, w, h, n, qp, 30.0)
+        bs = bytes(bs)
+        off = np.concatenate([[0], np.cumsum(fb)])
+        out.append((bs, [bs[off[i]:off[i + 1]] for i in range(n)]))
+    return out
+
+
+def ref_decode(bs, w, h, n):
+    R = C.CDLL(h264lib.REFSHIM_SO)
+    R.ref_decode.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    out = np.zeros(n * w * h * 3 // 2 + 64, np.uint8)
+    W, H, s = C.c_int(), C.c_int(), C.c_double()
+    a = np.frombuffer(bs, np.uint8)
+    assert R.ref_decode(a.ctypes.data, len(a), out.ctypes.data, out.size, C.byref(W), C.byref(H), C.byref(s)) == n
+    return out
+
+
+@pytest.mark.parametrize("w,h,n,qp,seeds", [(176, 144, 6, 26, (1, 2, 3)), (640, 360, 4, 32, (4, 5)), (180, 148, 4, 12, (6,))])
+def test_gpu_decoder_matches_reference_decoder(w, h, n, qp, seeds):
+    if not h264lib.have_ref():
+        pytest.skip("oracle/_ref not present")
+    from openh264_b200.binding import BatchDecoder
+    streams = ref_streams(w, h, n, qp, seeds)
+    want = [ref_decode(bs, w, h, n) for bs, _ in streams]
+    dec = BatchDecoder(w, h, n_streams=len(seeds))
+    fsz = w * h * 3 // 2
+    for f in range(n):
+        pics = dec.decode([aus[f] for _, aus in streams])
+        for s in range(len(seeds)):
+            assert np.array_equal(pics[s], want[s][f * fsz:(f + 1) * fsz]), "stream %d picture %d differs" % (s, f)
+    dec.close()
+
+
+def test_gpu_decoder_rejects_unsupported_stream():
+    from openh264_b200.binding import BatchDecoder, B2H264Error
+    dec = BatchDecoder(176, 144)
+    with pytest.raises(B2H264Error):
+        dec.decode([b"\x00\x00\x00\x01\x67\x64\x00\x1f\xac\xd9\x40\x50\x05\xbb\x01\x10"])      # a High-profile SPS
+    dec.close()

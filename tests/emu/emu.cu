@@ -244,6 +244,7 @@ extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, i
       if (rc != 0) return -1000 + rc;
       b2h264::StreamCtl geo;                                                    // picture geometry helpers
       geo.sp = st.sp;
+      if (have_buffers && (int)mbi.size() != st.sp.mb_w * st.sp.mb_h) return -4;   // picture size changed mid-stream
       if (!have_buffers) {
         for (int b = 0; b < 2; b++) {
           pic[b][0].assign((size_t)geo.rec_stride_y() * geo.rec_rows_y() + 64, 0);

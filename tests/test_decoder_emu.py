@@ -110,3 +110,34 @@ def test_reference_conformance_table_exact_or_rejected(emu):
         (exact if h == sha else wrong).append(os.path.basename(path))
     assert not wrong, wrong
     assert {"BA1_Sony_D.jsv", "NL1_Sony_D.jsv", "SVA_BA1_B.264", "SVA_NL1_B.264"} <= set(exact)
+
+
+def test_parser_survives_corrupted_streams(emu):
+    """bit flips, byte substitutions and deletions: the parser / host construct path must return (a picture or an
+    error code), never crash; the same parser guards the GPU decoder's input (run under ASan during development)"""
+    if not h264lib.have_ref():
+        pytest.skip("reference build not on this machine")
+    import random
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_encoder_golden import ref_encode
+    clip = h264lib.synth_clip(64, 48, 4, seed=3)
+    bs = bytes(ref_encode(clip, 64, 48, 4, 24, 30.0)[0])
+    out = np.zeros(8 << 20, np.uint8)
+    rng = random.Random(7)
+    seen_error = 0
+    for _ in range(600):
+        b = bytearray(bs)
+        for _ in range(rng.randint(1, 6)):
+            k = rng.randrange(len(b))
+            mode = rng.randrange(3)
+            if mode == 0:
+                b[k] ^= 1 << rng.randrange(8)
+            elif mode == 1:
+                b[k] = rng.randrange(256)
+            else:
+                del b[k:k + rng.randint(1, 8)]
+        a = np.frombuffer(bytes(b), np.uint8)
+        W, H = C.c_int(), C.c_int()
+        n = emu.emu_decode(a.ctypes.data, len(a), out.ctypes.data, out.size, C.byref(W), C.byref(H))
+        seen_error += n < 0
+    assert seen_error > 100

@@ -278,7 +278,7 @@ void WelsDestroySVCEncoder(ISVCEncoder* p) { delete static_cast<B2Encoder*>(p); 
 
 long WelsCreateDecoder(ISVCDecoder** pp) {
   if (pp) *pp = nullptr;
-  fprintf(stderr, "[b2h264] WelsCreateDecoder: the decoder path is not built yet (DESIGN.md section 9)\n");
+  fprintf(stderr, "[b2h264] WelsCreateDecoder: the ISVCDecoder object is not built yet (the batched decoder is b2h264_dec_*, DESIGN.md section 9)\n");
   return 1;
 }
 void WelsDestroyDecoder(ISVCDecoder*) {}

@@ -23,6 +23,8 @@ using namespace mbk;
 
 extern "C" void b2h264_build_host_tables();
 
+static bool same_record(const MbOut& a, const MbOut& b);
+
 namespace {
 
 // host-memory twin of the product's device-side frame buffers
@@ -81,28 +83,7 @@ struct HostFrameEncoder {
     if (pic.ss.idr != idr || pic.mbs.size() != out.size() || parser.sp.mb_w != ctl.sp.mb_w || parser.sp.width != ctl.sp.width ||
         parser.sp.height != ctl.sp.height) { parse_status = -100; return; }
     for (size_t i = 0; i < out.size(); i++) {
-      const MbOut& a = out[i];
-      const MbOut& b = pic.mbs[i];
-      bool same = a.mb_type == b.mb_type;
-      if (same && a.mb_type != MBT_PSKIP) {
-        same = a.cbp == b.cbp && memcmp(a.nnz, b.nnz, 24) == 0;
-        if (a.cbp > 0 || a.mb_type == MBT_I16x16) same = same && a.qp == b.qp;
-        if (MBT_IS_INTRA(a.mb_type)) same = same && a.chroma_mode == b.chroma_mode;
-        if (a.mb_type == MBT_I16x16) same = same && a.i16_mode == b.i16_mode && memcmp(a.luma_dc, b.luma_dc, 32) == 0;
-        if (a.mb_type == MBT_I4x4)
-          for (int k = 0; k < 16; k++) same = same && a.prev_i4_flag[k] == b.prev_i4_flag[k] && (a.prev_i4_flag[k] || a.rem_i4_mode[k] == b.rem_i4_mode[k]);
-        const int nparts = a.mb_type == MBT_P16x16 ? 1 : (a.mb_type == MBT_P16x8 || a.mb_type == MBT_P8x16) ? 2 : a.mb_type == MBT_P8x8 ? 4 : 0;
-        for (int k = 0; k < nparts; k++) same = same && a.mvd[k][0] == b.mvd[k][0] && a.mvd[k][1] == b.mvd[k][1];
-        for (int k = 0; k < 16 && same; k++) {
-          const int bx = (k & 1) | ((k >> 1) & 2), by = ((k >> 1) & 1) | ((k >> 2) & 2);
-          if (!(a.cbp & (1 << (k >> 2))) || a.nnz[by * 4 + bx] == 0) continue;     // not coded / written as empty
-          same = memcmp(a.luma[k], b.luma[k], (a.mb_type == MBT_I16x16 ? 15 : 16) * 2) == 0;
-        }
-        if (same && (a.cbp >> 4)) same = memcmp(a.chroma_dc, b.chroma_dc, 16) == 0;
-        if (same && (a.cbp >> 4) == 2)
-          for (int j = 0; j < 8 && same; j++)
-            if (a.nnz[16 + j] > 0) same = memcmp(a.chroma_ac[j], b.chroma_ac[j], 30) == 0;
-      }
+      const bool same = same_record(out[i], pic.mbs[i]);
       if (!same) { parse_status = 1 + (int)i; return; }
     }
   }
@@ -158,6 +139,31 @@ void deblock_frame_host(const EncFrameParams& p, const EncFramePtrs& f) {
 }
 
 }  // namespace
+
+// do two records describe the same coded macroblock?  (only what the bitstream carries is compared)
+static bool same_record(const MbOut& a, const MbOut& b) {
+  bool same = a.mb_type == b.mb_type;
+  if (same && a.mb_type != MBT_PSKIP) {
+    same = a.cbp == b.cbp && memcmp(a.nnz, b.nnz, 24) == 0;
+    if (a.cbp > 0 || a.mb_type == MBT_I16x16) same = same && a.qp == b.qp;
+    if (MBT_IS_INTRA(a.mb_type)) same = same && a.chroma_mode == b.chroma_mode;
+    if (a.mb_type == MBT_I16x16) same = same && a.i16_mode == b.i16_mode && memcmp(a.luma_dc, b.luma_dc, 32) == 0;
+    if (a.mb_type == MBT_I4x4)
+      for (int k = 0; k < 16; k++) same = same && a.prev_i4_flag[k] == b.prev_i4_flag[k] && (a.prev_i4_flag[k] || a.rem_i4_mode[k] == b.rem_i4_mode[k]);
+    const int nparts = a.mb_type == MBT_P16x16 ? 1 : (a.mb_type == MBT_P16x8 || a.mb_type == MBT_P8x16) ? 2 : a.mb_type == MBT_P8x8 ? 4 : 0;
+    for (int k = 0; k < nparts; k++) same = same && a.mvd[k][0] == b.mvd[k][0] && a.mvd[k][1] == b.mvd[k][1];
+    for (int k = 0; k < 16 && same; k++) {
+      const int bx = (k & 1) | ((k >> 1) & 2), by = ((k >> 1) & 1) | ((k >> 2) & 2);
+      if (!(a.cbp & (1 << (k >> 2))) || a.nnz[by * 4 + bx] == 0) continue;     // not coded / written as empty
+      same = memcmp(a.luma[k], b.luma[k], (a.mb_type == MBT_I16x16 ? 15 : 16) * 2) == 0;
+    }
+    if (same && (a.cbp >> 4)) same = memcmp(a.chroma_dc, b.chroma_dc, 16) == 0;
+    if (same && (a.cbp >> 4) == 2)
+      for (int j = 0; j < 8 && same; j++)
+        if (a.nnz[16 + j] > 0) same = memcmp(a.chroma_ac[j], b.chroma_ac[j], 30) == 0;
+  }
+  return same;
+}
 
 static std::vector<uint8_t> g_last_path;
 extern "C" int emu_last_path(uint8_t* path, int n) {
@@ -285,4 +291,108 @@ extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, i
     pos = next;
   }
   return frames > 0 ? frames : -3;          // nothing decodable is an error, not an empty success
+}
+
+
+// ---- randomized writer <-> parser round trip (levels up to the Baseline escape range, every macroblock type) -----------
+// Returns 0, a negative ParseError, or 1 + index of the first macroblock that came back different.
+static int random_pictures(unsigned seed, int pictures, bool decodable, uint8_t* stream_out, long cap, long* stream_len);
+extern "C" int emu_roundtrip_random(unsigned seed, int pictures) { return random_pictures(seed, pictures, false, nullptr, 0, nullptr); }
+// the same generator restricted to streams every conforming decoder reconstructs identically (DC intra prediction only,
+// bounded coefficient energy, bounded vectors): the Annex-B stream is returned for tests/test_decoder_emu.py, which
+// decodes it with the host construct path AND with the reference decoder
+extern "C" long emu_random_stream(unsigned seed, int pictures, uint8_t* out, long cap) {
+  long len = 0;
+  const int rc = random_pictures(seed, pictures, true, out, cap, &len);
+  return rc == 0 ? len : (long)rc;
+}
+static int random_pictures(unsigned seed, int pictures, bool decodable, uint8_t* stream_out, long cap, long* stream_len) {
+  uint32_t x = seed * 2654435761u + 12345u;
+  auto rnd = [&](uint32_t n) { x = x * 1664525u + 1013904223u; return (x >> 8) % n; };
+  const int W = 5, H = 4;
+  b2h264::StreamCtl ctl;
+  ctl.init(W * 16, H * 16, 26, 30.0f, 0);
+  b2h264::ParserState st;
+  int cur_qp = 26;                                            // qp the block being filled will be dequantised with
+  auto rand_level = [&]() {
+    const uint32_t c = rnd(100);
+    int v = c < 60 ? 1 : c < 85 ? 2 + (int)rnd(6) : c < 97 ? 8 + (int)rnd(120) : 128 + (int)rnd(1872);
+    return (int16_t)(rnd(2) ? -v : v);
+  };
+  auto fill_block = [&](int16_t* lv, int max_coef) {          // returns the number of non-zero levels
+    for (int i = 0; i < 16; i++) lv[i] = 0;
+    const uint32_t style = rnd(10);
+    int nz = 0;
+    // decodable streams keep the residual inside the range real encoders produce: one larger level at most, bounded by
+    // the quantiser step, the rest small (a conforming stream never overflows the 16-bit transform path)
+    const int big_cap = 1 + (1500 >> (cur_qp / 6));
+    bool big_used = false;
+    for (int i = 0; i < max_coef; i++) {
+      const bool on = style == 0 ? true : style < 4 ? rnd(2) == 0 : rnd(8) == 0;
+      if (!on) continue;
+      int16_t v = rand_level();
+      if (decodable) {
+        int a = v < 0 ? -v : v;
+        if (a > 2) { if (big_used) a = 1 + (int)rnd(2); else { a = a > big_cap ? big_cap : a; big_used = true; } }
+        v = (int16_t)(v < 0 ? -a : a);
+      }
+      lv[i] = v; nz++;
+    }
+    return nz;
+  };
+  for (int pic = 0; pic < pictures; pic++) {
+    const bool idr = pic == 0 || rnd(8) == 0;
+    if (idr) ctl.force_idr = true;
+    std::vector<MbOut> recs((size_t)W * H);
+    int qp = 26;
+    for (MbOut& m : recs) {
+      memset(&m, 0, sizeof(m));
+      const uint32_t t = rnd(idr ? 2 : 8);
+      m.mb_type = (uint8_t)(idr ? (t ? MBT_I16x16 : MBT_I4x4)
+                                : t == 0 ? MBT_I4x4 : t == 1 ? MBT_I16x16 : t == 2 ? MBT_P16x16 : t == 3 ? MBT_P16x8 : t == 4 ? MBT_P8x16
+                                  : t == 5 ? MBT_P8x8 : MBT_PSKIP);
+      if (m.mb_type == MBT_PSKIP) { m.qp = (uint8_t)qp; continue; }
+      int cbp_l = m.mb_type == MBT_I16x16 ? (rnd(2) ? 15 : 0) : (int)rnd(16);
+      const int cbp_c = (int)rnd(3);
+      // the quantiser this macroblock will carry is drawn first so that the level generator can respect it
+      if ((cbp_l | cbp_c) > 0 || m.mb_type == MBT_I16x16) {
+        qp += (int)rnd(41) - 20;                               // mb_qp_delta stays inside [-26, 25]
+        qp = qp < 10 ? 10 : qp > 45 ? 45 : qp;
+      }
+      cur_qp = qp;
+      if (MBT_IS_INTRA(m.mb_type)) m.chroma_mode = (uint8_t)(decodable ? 0 : rnd(4));          // 0 = DC: valid everywhere
+      if (m.mb_type == MBT_I16x16) { m.i16_mode = (uint8_t)(decodable ? 2 : rnd(4)); fill_block(m.luma_dc, 16); }
+      if (m.mb_type == MBT_I4x4)
+        for (int k = 0; k < 16; k++) {
+          m.prev_i4_flag[k] = (int8_t)(decodable ? 1 : rnd(2));                                  // predicted mode: DC all the way
+          m.rem_i4_mode[k] = m.prev_i4_flag[k] ? 0 : (int8_t)rnd(8);
+        }
+      const int nparts = m.mb_type == MBT_P16x16 ? 1 : (m.mb_type == MBT_P16x8 || m.mb_type == MBT_P8x16) ? 2 : m.mb_type == MBT_P8x8 ? 4 : 0;
+      const int mr = decodable ? 300 : 2000;
+      for (int k = 0; k < nparts; k++) { m.mvd[k][0] = (int16_t)((int)rnd(2 * mr + 1) - mr); m.mvd[k][1] = (int16_t)((int)rnd(401) - 200); }
+      for (int k = 0; k < 16; k++) {
+        if (!(cbp_l & (1 << (k >> 2)))) continue;
+        const int bx = (k & 1) | ((k >> 1) & 2), by = ((k >> 1) & 1) | ((k >> 2) & 2);
+        m.nnz[by * 4 + bx] = (int8_t)fill_block(m.luma[k], m.mb_type == MBT_I16x16 ? 15 : 16);
+      }
+      if (cbp_c) { fill_block(m.chroma_dc[0], 4); fill_block(m.chroma_dc[1], 4); }
+      if (cbp_c == 2) for (int j = 0; j < 8; j++) m.nnz[16 + j] = (int8_t)fill_block(m.chroma_ac[j], 15);
+      m.cbp = (uint8_t)(cbp_l | (cbp_c << 4));
+      m.qp = (uint8_t)qp;
+    }
+    std::vector<uint8_t> au;
+    ctl.write_access_unit(ctl.next_is_idr(), recs.data(), &au);
+    b2h264::ParsedPicture got;
+    const int rc = b2h264::parse_access_unit(au.data(), au.size(), &st, &got);
+    if (rc != 0) return rc;
+    if (got.mbs.size() != recs.size()) return -100;
+    for (size_t i = 0; i < recs.size(); i++)
+      if (!same_record(recs[i], got.mbs[i])) return 1 + (int)i;
+    if (stream_out) {
+      if (*stream_len + (long)au.size() > cap) return -200;
+      memcpy(stream_out + *stream_len, au.data(), au.size());
+      *stream_len += (long)au.size();
+    }
+  }
+  return 0;
 }

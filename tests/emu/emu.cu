@@ -344,8 +344,12 @@ static int random_pictures(unsigned seed, int pictures, bool decodable, uint8_t*
     const bool idr = pic == 0 || rnd(8) == 0;
     if (idr) ctl.force_idr = true;
     std::vector<MbOut> recs((size_t)W * H);
+    std::vector<int8_t> i4modes((size_t)W * H * 16, 2);         // final I4x4 modes per MB (raster blocks), for mode prediction
     int qp = 26;
-    for (MbOut& m : recs) {
+    for (size_t mi = 0; mi < recs.size(); mi++) {
+      MbOut& m = recs[mi];
+      const int mbx = (int)mi % W, mby = (int)mi / W;
+      const int nbav = (mbx > 0 ? NB_LEFT : 0) | (mby > 0 ? NB_TOP : 0) | (mbx > 0 && mby > 0 ? NB_TOPLEFT : 0) | (mby > 0 && mbx < W - 1 ? NB_TOPRIGHT : 0);
       memset(&m, 0, sizeof(m));
       const uint32_t t = rnd(idr ? 2 : 8);
       m.mb_type = (uint8_t)(idr ? (t ? MBT_I16x16 : MBT_I4x4)
@@ -360,13 +364,47 @@ static int random_pictures(unsigned seed, int pictures, bool decodable, uint8_t*
         qp = qp < 10 ? 10 : qp > 45 ? 45 : qp;
       }
       cur_qp = qp;
-      if (MBT_IS_INTRA(m.mb_type)) m.chroma_mode = (uint8_t)(decodable ? 0 : rnd(4));          // 0 = DC: valid everywhere
-      if (m.mb_type == MBT_I16x16) { m.i16_mode = (uint8_t)(decodable ? 2 : rnd(4)); fill_block(m.luma_dc, 16); }
-      if (m.mb_type == MBT_I4x4)
+      // intra modes: in decodable streams only modes whose neighbours exist (a conforming stream never uses others);
+      // DDL / VL without a top-right neighbour ARE allowed (8.3.1.2 substitutes samples) and are generated on purpose
+      const bool L = (nbav & NB_LEFT) != 0, T = (nbav & NB_TOP) != 0, TL = (nbav & NB_TOPLEFT) != 0;
+      if (MBT_IS_INTRA(m.mb_type)) {
+        int cm = (int)rnd(4);                                    // 0 DC, 1 H, 2 V, 3 plane
+        if (decodable && ((cm == 1 && !L) || (cm == 2 && !T) || (cm == 3 && !(L && T && TL)))) cm = 0;
+        m.chroma_mode = (uint8_t)cm;
+      }
+      if (m.mb_type == MBT_I16x16) {
+        int im = (int)rnd(4);                                    // 0 V, 1 H, 2 DC, 3 plane
+        if (decodable && ((im == 0 && !T) || (im == 1 && !L) || (im == 3 && !(L && T && TL)))) im = 2;
+        m.i16_mode = (uint8_t)im;
+        fill_block(m.luma_dc, 16);
+      }
+      if (m.mb_type == MBT_I4x4) {
         for (int k = 0; k < 16; k++) {
-          m.prev_i4_flag[k] = (int8_t)(decodable ? 1 : rnd(2));                                  // predicted mode: DC all the way
-          m.rem_i4_mode[k] = m.prev_i4_flag[k] ? 0 : (int8_t)rnd(8);
+          if (!decodable) { m.prev_i4_flag[k] = (int8_t)rnd(2); m.rem_i4_mode[k] = m.prev_i4_flag[k] ? 0 : (int8_t)rnd(8); continue; }
+          const int bx = (k & 1) | ((k >> 1) & 2), by = ((k >> 1) & 1) | ((k >> 2) & 2);
+          const int av = i4_avail(nbav, k);
+          const bool l = av & 1, t = av & 2, tl = av & 4;
+          int mode = (int)rnd(9);                                // 0 V 1 H 2 DC 3 DDL 4 DDR 5 VR 6 HD 7 VL 8 HU
+          const bool need_t = mode == 0 || mode == 3 || mode == 7, need_l = mode == 1 || mode == 8;
+          const bool need_all = mode == 4 || mode == 5 || mode == 6;
+          if ((need_t && !t) || (need_l && !l) || (need_all && !(l && t && tl))) mode = 2;
+          // predicted mode from the neighbours' final modes (DC for non-I4x4 / missing neighbours)
+          auto mode_at = [&](int x, int y) -> int {            // block coordinates relative to this MB, may be -1
+            int mx = mbx, my = mby;
+            if (x < 0) { mx--; x += 4; }
+            if (y < 0) { my--; y += 4; }
+            if (mx < 0 || my < 0) return -1;
+            const size_t ni = (size_t)my * W + mx;
+            if (ni == mi) return i4modes[ni * 16 + y * 4 + x];
+            return recs[ni].mb_type == MBT_I4x4 ? i4modes[ni * 16 + y * 4 + x] : 2;
+          };
+          const int lm = mode_at(bx - 1, by), tm = mode_at(bx, by - 1);
+          const int pm = (lm < 0 || tm < 0) ? 2 : (lm < tm ? lm : tm);
+          m.prev_i4_flag[k] = (int8_t)(mode == pm);
+          m.rem_i4_mode[k] = (int8_t)(mode == pm ? 0 : (mode < pm ? mode : mode - 1));
+          i4modes[mi * 16 + by * 4 + bx] = (int8_t)mode;
         }
+      }
       const int nparts = m.mb_type == MBT_P16x16 ? 1 : (m.mb_type == MBT_P16x8 || m.mb_type == MBT_P8x16) ? 2 : m.mb_type == MBT_P8x8 ? 4 : 0;
       const int mr = decodable ? 300 : 2000;
       for (int k = 0; k < nparts; k++) { m.mvd[k][0] = (int16_t)((int)rnd(2 * mr + 1) - mr); m.mvd[k][1] = (int16_t)((int)rnd(401) - 200); }

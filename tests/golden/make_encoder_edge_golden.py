@@ -1,0 +1,39 @@
+"""Writes tests/golden/encoder_edge.json: SHA-1 of the UNMODIFIED reference encoder's bitstream (oracle/_ref,
+ref_shim.cpp:ref_encode, constant QP, complexity HIGH) for
+  * BASELINE.json configs[1]: the reference's own res/CiscoVT2people_320x192_12fps.yuv (committed as
+    tests/golden/CiscoVT2people_320x192_12fps.yuv: a reference-held test vector, 9 pictures), QP 26 and 34;
+  * the edge-case list the reference's encoder tests sweep (test/api/encoder_test.cpp:103-180 resolution / QP
+    sweep): QP 0 / 51, pictures that need cropping, 16x16, very wide / very tall pictures.
+    python tests/golden/make_encoder_edge_golden.py
+"""
+import hashlib, json, os, shutil, sys
+import numpy as np
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import h264lib  # noqa: E402
+from make_encoder_golden import ref_encode  # noqa: E402
+
+CLIP = "CiscoVT2people_320x192_12fps.yuv"
+EDGE_CASES = [  # (w, h, n, qp, seed)
+    (176, 144, 4, 0, 3), (176, 144, 4, 51, 3), (176, 144, 4, 12, 4), (176, 144, 4, 45, 4),
+    (180, 148, 4, 26, 5), (164, 130, 4, 30, 6), (16, 16, 4, 26, 7), (32, 18, 4, 20, 8),
+    (480, 32, 4, 28, 9), (64, 256, 4, 33, 10), (352, 288, 3, 38, 11),
+]
+
+if __name__ == "__main__":
+    assert h264lib.have_ref()
+    src = os.path.join("/root/reference/res", CLIP)
+    if not os.path.exists(os.path.join(HERE, CLIP)):
+        shutil.copyfile(src, os.path.join(HERE, CLIP))
+    gold = {"clip": {}, "edge": {}}
+    yuv = np.fromfile(os.path.join(HERE, CLIP), dtype=np.uint8)
+    for qp in (26, 34):
+        bs, fb, _ = ref_encode(yuv, 320, 192, 9, qp, 12.0)
+        gold["clip"]["qp%d" % qp] = {"sha1": hashlib.sha1(bs).hexdigest(), "frame_bytes": fb,
+                                     "yuv_sha1": hashlib.sha1(yuv.tobytes()).hexdigest()}
+    for (w, h, n, qp, seed) in EDGE_CASES:
+        y = h264lib.synth_clip(w, h, n, seed=seed)
+        bs, fb, _ = ref_encode(y, w, h, n, qp, 30.0)
+        gold["edge"]["%dx%d_n%d_qp%d_seed%d" % (w, h, n, qp, seed)] = {"sha1": hashlib.sha1(bs).hexdigest(), "frame_bytes": fb}
+    json.dump(gold, open(os.path.join(HERE, "encoder_edge.json"), "w"), indent=1, sort_keys=True)
+    print(json.dumps(gold, indent=1))

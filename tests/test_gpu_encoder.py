@@ -146,3 +146,32 @@ def test_heterogeneous_streams_with_one_forced_idr():
             r, ref_bs, _ = drive(REFLIB, clips[s], w, h, n, qp, 2 if s == 3 else -1, tmp, "ref%d" % s)
             assert r.returncode == 0, r.stderr
             assert got[s] == ref_bs, "stream %d differs from the reference" % s
+
+
+# ---- BASELINE.json configs[1] and the edge-case sweep through the CUDA path ------------------------------------------
+EDGE = json.load(open(os.path.join(ROOT, "tests", "golden", "encoder_edge.json")))
+
+
+@pytest.mark.parametrize("qp", [26, 34])
+def test_config1_reference_clip_through_cuda(qp):
+    """BASELINE.json configs[1]: the reference's own res/CiscoVT2people_320x192_12fps.yuv (committed test vector),
+    constant QP, single slice, through BatchEncoder on the GPU; golden = the unmodified reference's bitstream."""
+    yuv = np.fromfile(os.path.join(ROOT, "tests", "golden", "CiscoVT2people_320x192_12fps.yuv"), dtype=np.uint8)
+    g = EDGE["clip"]["qp%d" % qp]
+    assert hashlib.sha1(yuv.tobytes()).hexdigest() == g["yuv_sha1"]
+    outs, _ = gpu_encode(yuv, 320, 192, 9, qp, 12.0, n_streams=2, pipelined=True)
+    assert [len(b) for b in outs[0]] == g["frame_bytes"]
+    assert hashlib.sha1(b"".join(outs[0])).hexdigest() == g["sha1"]
+    assert outs[1] == outs[0]
+
+
+@pytest.mark.parametrize("key", sorted(EDGE["edge"]))
+def test_edge_cases_through_cuda(key):
+    """QP 0 / 51, pictures that need cropping, 16x16, very wide / tall pictures (the reference's encoder_test.cpp
+    resolution / QP sweep) on the GPU; golden = the unmodified reference's bitstream."""
+    w, h = map(int, key.split("_")[0].split("x"))
+    n, qp, seed = int(key.split("_n")[1].split("_")[0]), int(key.split("_qp")[1].split("_")[0]), int(key.split("_seed")[1])
+    yuv = h264lib.synth_clip(w, h, n, seed=seed)
+    outs, _ = gpu_encode(yuv, w, h, n, qp, 30.0)
+    assert [len(b) for b in outs[0]] == EDGE["edge"][key]["frame_bytes"]
+    assert hashlib.sha1(b"".join(outs[0])).hexdigest() == EDGE["edge"][key]["sha1"]

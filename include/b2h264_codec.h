@@ -45,10 +45,14 @@ typedef struct {
 int  b2h264_enc_create (const b2h264_enc_config* cfg, b2h264_enc** out);
 void b2h264_enc_destroy (b2h264_enc* e);
 
-/* Submits one picture per stream.  src[i] = I420 picture of stream i (w*h*3/2 bytes, tightly packed).
- * src_on_device = 0: host pointers; the pictures are staged through pinned memory and copied H2D
- * inside this call's asynchronous pipeline.  src_on_device = 1: device pointers (already in HBM).
- * At most 2 submissions may be in flight before b2h264_enc_collect is called. */
+/* Submits one picture per stream.  src[i] = I420 picture of stream i (w*h*3/2 bytes, tightly packed), or NULL: stream
+ * i sits this batch out (its state is untouched; collect reports 0 bytes / frame type 0 for it) — this is how
+ * ISVCEncoder objects that call EncodeFrame at their own pace share one batched encoder (layer 3's broker).
+ * src_on_device = 0: host pointers.  Pageable pictures are copied into the encoder's pinned ring inside this
+ * call (the caller may reuse them on return).  PAGE-LOCKED pictures (cudaHostAlloc / cudaHostRegister) are DMA'd
+ * straight from the caller's memory by the asynchronous pipeline: they must stay untouched until the matching
+ * b2h264_enc_collect returns.  src_on_device = 1: device pointers (already in HBM), same lifetime rule.
+ * At most 2 submissions may be in flight before b2h264_enc_collect is called (-3 otherwise; -5: every src NULL). */
 int  b2h264_enc_submit (b2h264_enc* e, const uint8_t* const* src, int src_on_device);
 
 /* Waits for the oldest submitted batch, entropy-codes it, and returns per-stream Annex-B access units.
@@ -58,6 +62,10 @@ int  b2h264_enc_collect (b2h264_enc* e, const uint8_t** bs, int32_t* bs_bytes, i
 
 /* next picture of stream i (or all streams when i < 0) is coded as IDR (ISVCEncoder::ForceIntraFrame) */
 int  b2h264_enc_force_idr (b2h264_enc* e, int stream);
+
+/* stream i starts over as a fresh encoder would (next picture IDR, parameter-set ids, frame_num, SAD / reference
+ * history cleared); only while nothing is in flight.  Used when an ISVCEncoder slot of a shared encoder is re-used. */
+int  b2h264_enc_reset_stream (b2h264_enc* e, int stream);
 
 /* copies the reconstructed (deblocked) picture of stream i that is currently the reference into dst
  * (cropped I420, w*h*3/2 bytes, host memory): for parity tests */
@@ -94,6 +102,12 @@ void b2h264_dec_destroy (b2h264_dec* d);
 /* au[s] / au_bytes[s]: one access unit ([SPS PPS] slice, Annex B) of stream s; yuv[s]: host buffer for the decoded
  * picture, tightly packed I420 of width x height.  Synchronous. */
 int  b2h264_dec_decode (b2h264_dec* d, const uint8_t* const* au, const int32_t* au_bytes, uint8_t* const* yuv);
+/* as b2h264_dec_decode; streams whose au[s] is NULL or carries no slice (parameter sets only) sit the call out:
+ * got_picture[s] = 1 where yuv[s] was written, else 0 (the parameter sets are kept for the stream) */
+int  b2h264_dec_decode2 (b2h264_dec* d, const uint8_t* const* au, const int32_t* au_bytes, uint8_t* const* yuv, int32_t* got_picture);
+/* stateless look at an access unit: *has_slice, and — if it carries an SPS of the supported class — the cropped picture
+ * size (so that a caller can create the decoder for it: ISVCDecoder learns the size from the stream) */
+int  b2h264_dec_probe (const uint8_t* au, int32_t au_bytes, int32_t* width, int32_t* height, int32_t* has_slice);
 
 #ifdef __cplusplus
 }

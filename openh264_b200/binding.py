@@ -75,12 +75,15 @@ API = {
     "b2h264_enc_submit": [vp, C.POINTER(vp), C.c_int],
     "b2h264_enc_collect": [vp, C.POINTER(vp), i32p, i32p],
     "b2h264_enc_force_idr": [vp, C.c_int],
+    "b2h264_enc_reset_stream": [vp, C.c_int],
     "b2h264_enc_get_recon": [vp, C.c_int, vp],
     "b2h264_enc_last_timing": [vp, C.POINTER(C.c_float)],
     "b2h264_enc_last_d2h_bytes": [vp, C.POINTER(C.c_ulonglong)],
     "b2h264_dec_create": [vp, C.POINTER(vp)],
     "b2h264_dec_destroy": [vp],
     "b2h264_dec_decode": [vp, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(vp)],
+    "b2h264_dec_decode2": [vp, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(vp), C.POINTER(C.c_int32)],
+    "b2h264_dec_probe": [vp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
     "b2h264_enc_set_stream": [vp, vp],
     "b2h264_table_quant_ff": [C.c_int],
     "b2h264_table_quant_mf": [C.c_int],
@@ -189,8 +192,9 @@ class BatchEncoder:
 
     def submit(self, frames, on_device=False):
         """frames: list of n_streams numpy uint8 arrays (host) or raw device pointers (on_device=True)."""
-        ptrs = (vp * self.n)(*[(f if on_device else f.ctypes.data) for f in frames])
-        self._keep = frames
+        ptrs = (vp * self.n)(*[(None if f is None else f if on_device else f.ctypes.data) for f in frames])
+        # two submissions can be in flight and pinned sources are DMA'd in place: keep both alive until their collect
+        self._keep = getattr(self, "_keep", [])[-1:] + [frames]
         check(self.L.b2h264_enc_submit(self.h, ptrs, 1 if on_device else 0))
 
     def collect(self):
@@ -198,11 +202,14 @@ class BatchEncoder:
         nb = (C.c_int32 * self.n)()
         ft = (C.c_int32 * self.n)()
         check(self.L.b2h264_enc_collect(self.h, bs, nb, ft))
-        return [C.string_at(bs[i], nb[i]) for i in range(self.n)], list(ft)
+        return [C.string_at(bs[i], nb[i]) if bs[i] else b"" for i in range(self.n)], list(ft)
 
     def encode(self, frames):
         self.submit(frames)
         return self.collect()
+
+    def reset_stream(self, stream):
+        check(self.L.b2h264_enc_reset_stream(self.h, stream))
 
     def force_idr(self, stream=-1):
         check(self.L.b2h264_enc_force_idr(self.h, stream))

@@ -6,7 +6,7 @@
 // WelsTargetMbConstruction (codec/decoder/core/src/decoder_core.cpp, decode_slice.cpp:~100) and
 // WelsDeblockingFilterSlice (deblocking.cpp).  Streams outside the class are rejected with the parser's error
 // code; there is no CPU reconstruction path in this library.
-// STATUS: first device version of the next SURVEY row: synchronous, not yet pipelined.
+// Synchronous per call (parse -> H2D -> kernels -> D2H); streams without a slice in their access unit sit the call out.
 #include <cuda_runtime.h>
 #include <string.h>
 
@@ -27,7 +27,8 @@ struct b2h264_dec {
   int S = 0, mb_w = 0, mb_h = 0, n_mb = 0;
   StreamCtl geo;                          // picture geometry (strides, padded rows)
   std::vector<ParserState> parser;
-  int cur_rec = 0;
+  std::vector<uint8_t> stream_rec;        // per stream: which of its two pictures is written next
+  std::vector<int> act;
   cudaStream_t st = nullptr;
   uint8_t* d_pic[2] = {nullptr, nullptr};
   MbInfo* d_mbi = nullptr;
@@ -61,6 +62,7 @@ int b2h264_dec_create(const b2h264_dec_config* cfg, b2h264_dec** out) {
   d->geo.init(cfg->width, cfg->height, 26, 30.0f, 0);
   d->mb_w = d->geo.sp.mb_w; d->mb_h = d->geo.sp.mb_h; d->n_mb = d->mb_w * d->mb_h;
   d->parser.resize(d->S);
+  d->stream_rec.assign(d->S, 0);
   d->pic_y_bytes = (size_t)d->geo.rec_stride_y() * d->geo.rec_rows_y();
   d->pic_c_bytes = (size_t)d->geo.rec_stride_c() * d->geo.rec_rows_c();
   d->pic_bytes = d->pic_y_bytes + 2 * d->pic_c_bytes;
@@ -92,35 +94,51 @@ void b2h264_dec_destroy(b2h264_dec* d) {
   delete d;
 }
 
-int b2h264_dec_decode(b2h264_dec* d, const uint8_t* const* au, const int32_t* au_bytes, uint8_t* const* yuv) {
+// got_picture (may be NULL): per stream 1 = a picture was decoded into yuv[s], 0 = the access unit carried no slice
+// (parameter sets only / au[s] == NULL).  With got_picture == NULL an access unit without a slice is an error.
+int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* au_bytes, uint8_t* const* yuv, int32_t* got_picture) {
   if (!d || !au || !au_bytes || !yuv) return -1;
   CK(cudaSetDevice(d->cfg.device));
-  const int S = d->S, rec = d->cur_rec;
+  const int S = d->S;
   int deblock = 1;
+  d->act.clear();
   for (int s = 0; s < S; s++) {
+    if (got_picture) got_picture[s] = 0;
+    if (!au[s] || au_bytes[s] <= 0) {
+      if (!got_picture) { d->last_error_stream = s; return -1; }
+      continue;
+    }
     ParsedPicture pic;
     const int rc = parse_access_unit(au[s], (size_t)au_bytes[s], &d->parser[s], &pic);
-    if (rc != PARSE_OK) { d->last_error_stream = s; return -100 + rc; }          // -101 truncated, -102 unsupported, -103 invalid, -104 no parameter sets
+    if (rc == PARSE_NO_PICTURE && got_picture) continue;
+    if (rc != PARSE_OK) { d->last_error_stream = s; return -100 + (rc == PARSE_NO_PICTURE ? PARSE_INVALID : rc); }   // -101 truncated, -102 unsupported, -103 invalid, -104 no parameter sets
     const StreamParams& sp = d->parser[s].sp;
     if (sp.mb_w != d->mb_w || sp.mb_h != d->mb_h || sp.width != d->cfg.width || sp.height != d->cfg.height) { d->last_error_stream = s; return -2; }
+    if ((int)pic.mbs.size() != d->n_mb) { d->last_error_stream = s; return -103; }
     const int want_deblock = pic.disable_deblocking_idc != 1;
-    if (s == 0) deblock = want_deblock;
+    if (d->act.empty()) deblock = want_deblock;
     else if (want_deblock != deblock) { d->last_error_stream = s; return -2; }   // one setting per batch
-    memcpy(d->h_recs + (size_t)s * d->n_mb, pic.mbs.data(), (size_t)d->n_mb * sizeof(MbOut));
-    StreamFrame& F = d->h_sf[s];
+    const int i = (int)d->act.size();
+    d->act.push_back(s);
+    memcpy(d->h_recs + (size_t)i * d->n_mb, pic.mbs.data(), (size_t)d->n_mb * sizeof(MbOut));
+    StreamFrame& F = d->h_sf[i];
     memset(&F, 0, sizeof(F));
     F.p.mb_w = d->mb_w; F.p.mb_h = d->mb_h;
     F.p.rec_stride_y = d->geo.rec_stride_y(); F.p.rec_stride_c = d->geo.rec_stride_c();
     F.p.qp = pic.ss.qp; F.p.is_idr = pic.ss.idr; F.p.ref_is_p = !pic.ss.idr; F.p.mv_range = 64;
+    const int rec = d->stream_rec[s];
     for (int pl = 0; pl < 3; pl++) { F.f.rec[pl] = d->plane0(rec, s, pl); F.f.ref[pl] = d->plane0(1 - rec, s, pl); }
     F.f.mbi = d->d_mbi + (size_t)s * d->n_mb;
   }
-  CK(cudaMemcpyAsync(d->d_recs, d->h_recs, (size_t)S * d->n_mb * sizeof(MbOut), cudaMemcpyHostToDevice, d->st));
-  CK(cudaMemcpyAsync(d->d_sf, d->h_sf, (size_t)S * sizeof(StreamFrame), cudaMemcpyHostToDevice, d->st));
-  const int rc = dec_launch_frame(d->d_sf, S, d->mb_w, d->mb_h, d->d_ws, d->d_recs, deblock, d->st);
+  const int n = (int)d->act.size();
+  if (n == 0) return 0;
+  CK(cudaMemcpyAsync(d->d_recs, d->h_recs, (size_t)n * d->n_mb * sizeof(MbOut), cudaMemcpyHostToDevice, d->st));
+  CK(cudaMemcpyAsync(d->d_sf, d->h_sf, (size_t)n * sizeof(StreamFrame), cudaMemcpyHostToDevice, d->st));
+  const int rc = dec_launch_frame(d->d_sf, n, d->mb_w, d->mb_h, d->d_ws, d->d_recs, deblock, d->st);
   if (rc) return rc;
   const int w = d->cfg.width, h = d->cfg.height;
-  for (int s = 0; s < S; s++) {
+  for (int i = 0; i < n; i++) {
+    const int s = d->act[i], rec = d->stream_rec[s];
     uint8_t* dst = yuv[s];
     for (int pl = 0; pl < 3; pl++) {
       const int pw = pl ? w / 2 : w, ph = pl ? h / 2 : h;
@@ -128,9 +146,27 @@ int b2h264_dec_decode(b2h264_dec* d, const uint8_t* const* au, const int32_t* au
       CK(cudaMemcpy2DAsync(dst, pw, d->plane0(rec, s, pl), stp, pw, ph, cudaMemcpyDeviceToHost, d->st));
       dst += (size_t)pw * ph;
     }
+    d->stream_rec[s] ^= 1;
+    if (got_picture) got_picture[s] = 1;
   }
   CK(cudaStreamSynchronize(d->st));
-  d->cur_rec = 1 - rec;
+  return 0;
+}
+
+int b2h264_dec_decode(b2h264_dec* d, const uint8_t* const* au, const int32_t* au_bytes, uint8_t* const* yuv) {
+  return b2h264_dec_decode2(d, au, au_bytes, yuv, nullptr);
+}
+
+// Looks at an access unit without a decoder: *has_slice = a coded slice NAL is present; if it carries an SPS of the
+// supported class, *width / *height = the cropped picture size (else left untouched).  0, or a parser error (-10x).
+int b2h264_dec_probe(const uint8_t* au, int32_t au_bytes, int32_t* width, int32_t* height, int32_t* has_slice) {
+  if (!au || au_bytes <= 0) return -1;
+  int w = 0, h = 0, sl = 0;
+  const int rc = probe_access_unit(au, (size_t)au_bytes, &w, &h, &sl);
+  if (has_slice) *has_slice = sl;
+  if (rc != PARSE_OK) return -100 + rc;
+  if (w > 0 && width) *width = w;
+  if (h > 0 && height) *height = h;
   return 0;
 }
 

@@ -69,13 +69,15 @@ struct b2h264_enc {
   std::vector<StreamCtl> ctl;
   std::vector<uint8_t> idr_next;          // per stream: code next picture as IDR
   std::vector<uint8_t> have_ref_p;        // reference picture of the stream was a P picture
-  int cur_rec = 0;                        // which of the two picture sets is being written
+  int cur_rec = 0;                        // (unused: every stream keeps its own parity, stream_rec)
+  std::vector<uint8_t> stream_rec;        // per stream: which of its two pictures is written next
   cudaStream_t st = nullptr;        // kernels (may be the caller's stream, b2h264_enc_set_stream)
   cudaStream_t st_in = nullptr;     // source uploads: overlap the previous picture's kernels
   cudaStream_t st_out = nullptr;    // record downloads: overlap deblocking and the next picture's kernels
   // device memory
   uint8_t* d_cur = nullptr;               // S x (Y,U,V) MB-aligned current pictures
-  uint8_t* d_pic[2] = {nullptr, nullptr}; // S x padded (Y,U,V), ping-pong
+  uint8_t* d_pic_all = nullptr;           // 2 x S x padded (Y,U,V)
+  uint8_t* d_pic[2] = {nullptr, nullptr}; // the two picture sets inside d_pic_all
   uint8_t* d_src = nullptr;               // S x raw I420 staging (2 slots)
   MbInfo* d_mbi = nullptr;
   RefMbInfo* d_rinfo[2] = {nullptr, nullptr};
@@ -85,6 +87,8 @@ struct b2h264_enc {
   int* d_tickets = nullptr;
   void* d_stash = nullptr;          // parked macroblock scratches of the staged scheduler
   StreamFrame* d_sf[2] = {nullptr, nullptr};
+  alignas(64) unsigned char tmap_pic[128];      // CUtensorMap of the luma planes of both picture sets of all streams
+  bool have_tmap = false;
   const uint8_t** d_srcptr[2] = {nullptr, nullptr};
   // pinned host memory
   uint8_t* h_src = nullptr;               // 2 slots x S x frame
@@ -96,7 +100,8 @@ struct b2h264_enc {
   StreamFrame* h_sf[2] = {nullptr, nullptr};
   const uint8_t** h_srcptr[2] = {nullptr, nullptr};
   // in-flight bookkeeping
-  struct Slot { bool busy = false; std::vector<uint8_t> idr; cudaEvent_t ev0, ev1, ev2, done, in_done, enc_done; };
+  struct Slot { bool busy = false; std::vector<uint8_t> idr; std::vector<int> act;   // act: streams of this batch (compact order)
+                cudaEvent_t ev0, ev1, ev2, done, in_done, enc_done; };
   Slot slot[2];
   int submit_idx = 0, collect_idx = 0;
   std::vector<std::vector<uint8_t>> bs;   // per stream output of the last collect
@@ -133,6 +138,7 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
   }
   e->idr_next.assign(e->S, 1);
   e->have_ref_p.assign(e->S, 0);
+  e->stream_rec.assign(e->S, 0);
   const StreamCtl& c0 = e->ctl[0];
   const int mbw = c0.sp.mb_w, mbh = c0.sp.mb_h;
   e->n_mb = mbw * mbh;
@@ -149,11 +155,13 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     CK(cudaStreamCreateWithPriority(&e->st_out, cudaStreamNonBlocking, lo));
   }
+  // both picture sets of all streams in ONE allocation: plane index set * S + stream (the reference tensor map's z)
+  CK(cudaMalloc(&e->d_pic_all, 2 * S * e->pic_bytes + 256));
+  CK(cudaMemset(e->d_pic_all, 0, 2 * S * e->pic_bytes + 256));
   CK(cudaMalloc(&e->d_cur, S * e->cur_bytes + 256));
   CK(cudaMalloc(&e->d_list, S * e->n_mb * sizeof(int32_t)));
   for (int i = 0; i < 2; i++) {
-    CK(cudaMalloc(&e->d_pic[i], S * e->pic_bytes + 256));
-    CK(cudaMemset(e->d_pic[i], 0, S * e->pic_bytes + 256));
+    e->d_pic[i] = e->d_pic_all + (size_t)i * S * e->pic_bytes;
     CK(cudaMalloc(&e->d_rinfo[i], S * e->n_mb * sizeof(RefMbInfo)));
     CK(cudaMemset(e->d_rinfo[i], 0, S * e->n_mb * sizeof(RefMbInfo)));
     CK(cudaMalloc(&e->d_out[i], S * e->n_mb * sizeof(MbOut)));
@@ -171,6 +179,9 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
     CK(cudaEventCreateWithFlags(&e->slot[i].in_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->slot[i].enc_done, cudaEventDisableTiming));
   }
+  // TMA descriptors of the two picture sets: (x, y) from the padded origin of the luma plane, z = stream
+  e->have_tmap = b2h264_make_tmap_planes(e->tmap_pic, e->d_pic_all, (uint64_t)c0.rec_stride_y(), (uint64_t)c0.rec_rows_y(), 2 * (uint64_t)S,
+                                         (uint64_t)c0.rec_stride_y(), (uint64_t)e->pic_bytes, 48, 48) == 0;
   CK(cudaMalloc(&e->d_src, 2 * S * e->frame_bytes + 256));
   CK(cudaMallocHost(&e->h_src, 2 * S * e->frame_bytes));
   CK(cudaMalloc(&e->d_mbi, S * e->n_mb * sizeof(MbInfo)));
@@ -190,12 +201,13 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
 
 void b2h264_enc_destroy(b2h264_enc* e) {
   if (!e) return;
+  cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->st);
   delete e->pool;
-  cudaFree(e->d_cur); cudaFree(e->d_src); cudaFree(e->d_mbi); cudaFree(e->d_sad); cudaFree(e->d_prog); cudaFree(e->d_tickets); cudaFree(e->d_stash); cudaFree(e->d_list);
+  cudaFree(e->d_pic_all); cudaFree(e->d_cur); cudaFree(e->d_src); cudaFree(e->d_mbi); cudaFree(e->d_sad); cudaFree(e->d_prog); cudaFree(e->d_tickets); cudaFree(e->d_stash); cudaFree(e->d_list);
   cudaFreeHost(e->h_src);
   for (int i = 0; i < 2; i++) {
-    cudaFree(e->d_pic[i]); cudaFree(e->d_rinfo[i]); cudaFree(e->d_out[i]); cudaFree(e->d_sf[i]); cudaFree(e->d_srcptr[i]);
+    cudaFree(e->d_rinfo[i]); cudaFree(e->d_out[i]); cudaFree(e->d_sf[i]); cudaFree(e->d_srcptr[i]);
     cudaFreeHost(e->h_out[i]); cudaFreeHost(e->h_idx[i]); cudaFreeHost(e->h_cnt[i]); cudaFreeHost(e->h_sf[i]); cudaFreeHost(e->h_srcptr[i]);
     cudaEventDestroy(e->slot[i].ev0); cudaEventDestroy(e->slot[i].ev1); cudaEventDestroy(e->slot[i].ev2); cudaEventDestroy(e->slot[i].done); cudaEventDestroy(e->slot[i].in_done); cudaEventDestroy(e->slot[i].enc_done);
   }
@@ -217,71 +229,72 @@ int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_devic
   b2h264_enc::Slot& sl = e->slot[k];
   if (sl.busy) return -3;                       // two batches already in flight
   const int S = e->S, mbw = e->ctl[0].sp.mb_w, mbh = e->ctl[0].sp.mb_h;
-  // stage sources
-  bool staged = false;
-  for (int s = 0; s < S; s++) {
-    if (src_on_device) { e->h_srcptr[k][s] = src[s]; continue; }
+  // streams with a NULL source sit this batch out (their state does not change); the kernels see the others as a
+  // compact list of n streams, each carrying its slot index (EncFrameParams::stream) for the reference tensor map
+  sl.act.clear();
+  for (int s = 0; s < S; s++) if (src[s]) sl.act.push_back(s);
+  const int n = (int)sl.act.size();
+  if (n == 0) return -5;
+  // stage sources: page-locked caller memory is DMA'd from where it lies (the caller keeps it untouched until the
+  // matching collect: include/b2h264_codec.h), pageable memory goes through the encoder's pinned ring
+  for (int i = 0; i < n; i++) {
+    const int s = sl.act[i];
+    if (src_on_device) { e->h_srcptr[k][i] = src[s]; continue; }
     uint8_t* dd = e->d_src + ((size_t)k * S + s) * e->frame_bytes;
-    e->h_srcptr[k][s] = dd;
+    e->h_srcptr[k][i] = dd;
     cudaPointerAttributes at;
     const bool pinned = cudaPointerGetAttributes(&at, src[s]) == cudaSuccess && at.type == cudaMemoryTypeHost;
-    if (pinned) {                               // caller's buffer is page-locked: DMA straight from it
-      CK(cudaMemcpyAsync(dd, src[s], e->frame_bytes, cudaMemcpyHostToDevice, e->st_in));
-    } else {                                    // pageable memory: stage through the encoder's pinned ring
+    const uint8_t* from = src[s];
+    if (!pinned) {
       (void)cudaGetLastError();
-      memcpy(e->h_src + ((size_t)k * S + s) * e->frame_bytes, src[s], e->frame_bytes);
-      staged = true;
+      uint8_t* hs = e->h_src + ((size_t)k * S + s) * e->frame_bytes;
+      memcpy(hs, src[s], e->frame_bytes);
+      from = hs;
     }
-  }
-  if (staged) {
-    for (int s = 0; s < S; s++) {
-      cudaPointerAttributes at;
-      const bool pinned = !src_on_device && cudaPointerGetAttributes(&at, src[s]) == cudaSuccess && at.type == cudaMemoryTypeHost;
-      if (!pinned) {
-        (void)cudaGetLastError();
-        const size_t o = ((size_t)k * S + s) * e->frame_bytes;
-        CK(cudaMemcpyAsync(e->d_src + o, e->h_src + o, e->frame_bytes, cudaMemcpyHostToDevice, e->st_in));
-      }
-    }
+    CK(cudaMemcpyAsync(dd, from, e->frame_bytes, cudaMemcpyHostToDevice, e->st_in));
   }
   // per-stream frame descriptors
   sl.idr.assign(S, 0);
-  const int rec = e->cur_rec;
-  for (int s = 0; s < S; s++) {
+  for (int i = 0; i < n; i++) {
+    const int s = sl.act[i];
     const bool idr = e->idr_next[s] != 0;
     sl.idr[s] = idr;
-    StreamFrame& F = e->h_sf[k][s];
+    StreamFrame& F = e->h_sf[k][i];
     F.p = e->ctl[s].frame_params(idr, e->have_ref_p[s] != 0);
     uint8_t* cur = e->d_cur + (size_t)s * e->cur_bytes;
     F.f.cur[0] = cur; F.f.cur[1] = cur + (size_t)e->n_mb * 256; F.f.cur[2] = cur + (size_t)e->n_mb * 320;
-    for (int pl = 0; pl < 3; pl++) { F.f.rec[pl] = e->pic_plane0(rec, s, pl); F.f.ref[pl] = e->pic_plane0(1 - rec, s, pl); }
+    // every stream has its OWN picture parity (a stream that sat a batch out keeps its reference where it is)
+    const int prec = e->stream_rec[s];
+    F.p.ref_plane = (1 - prec) * S + s; F.p.pad0 = 0;
+    for (int pl = 0; pl < 3; pl++) { F.f.rec[pl] = e->pic_plane0(prec, s, pl); F.f.ref[pl] = e->pic_plane0(1 - prec, s, pl); }
     F.f.mbi = e->d_mbi + (size_t)s * e->n_mb;
-    F.f.rec_info = e->d_rinfo[rec] + (size_t)s * e->n_mb;
-    F.f.ref_info = e->d_rinfo[1 - rec] + (size_t)s * e->n_mb;
-    F.f.out = e->d_out[k] + (size_t)s * e->n_mb;
+    F.f.rec_info = e->d_rinfo[prec] + (size_t)s * e->n_mb;
+    F.f.ref_info = e->d_rinfo[1 - prec] + (size_t)s * e->n_mb;
+    F.f.out = e->d_out[k] + (size_t)i * e->n_mb;
     F.f.sad_cost = e->d_sad + (size_t)s * e->n_mb;
     F.f.row_progress = e->d_prog + (size_t)s * 2 * mbh;
     F.f.row_progress_dbk = F.f.row_progress + mbh;
     e->idr_next[s] = 0;
     e->have_ref_p[s] = !idr;
   }
-  e->cur_rec = 1 - rec;
+  for (int i = 0; i < n; i++) e->stream_rec[sl.act[i]] ^= 1;
   if (!src_on_device) {                        // the kernels of this picture wait for its uploads only
     CK(cudaEventRecord(sl.in_done, e->st_in));
     CK(cudaStreamWaitEvent(e->st, sl.in_done, 0));
   }
-  CK(cudaMemcpyAsync(e->d_sf[k], e->h_sf[k], S * sizeof(StreamFrame), cudaMemcpyHostToDevice, e->st));
-  CK(cudaMemcpyAsync(e->d_srcptr[k], e->h_srcptr[k], S * sizeof(uint8_t*), cudaMemcpyHostToDevice, e->st));
+  CK(cudaMemcpyAsync(e->d_sf[k], e->h_sf[k], n * sizeof(StreamFrame), cudaMemcpyHostToDevice, e->st));
+  CK(cudaMemcpyAsync(e->d_srcptr[k], e->h_srcptr[k], n * sizeof(uint8_t*), cudaMemcpyHostToDevice, e->st));
   CK(cudaEventRecord(sl.ev0, e->st));
-  int rc = enc_launch_frame(e->d_sf[k], e->d_srcptr[k], S, e->cfg.width, e->cfg.height, mbw, mbh, e->d_tickets, e->d_stash, e->st);
+  int rc = enc_launch_frame(e->d_sf[k], e->d_srcptr[k], n, e->cfg.width, e->cfg.height, mbw, mbh, e->d_tickets, e->d_stash,
+                            e->have_tmap ? e->tmap_pic : nullptr, e->st);
   if (rc) return rc;
   CK(cudaEventRecord(sl.ev1, e->st));
-  rc = enc_launch_deblock_expand(e->d_sf[k], S, mbw, mbh, e->d_tickets, e->st);
+  rc = enc_launch_deblock_expand(e->d_sf[k], n, mbw, mbh, e->d_tickets, e->st);
   if (rc) return rc;
   CK(cudaEventRecord(sl.ev2, e->st));
   // the macroblock records are final once the encode kernel is done (deblocking does not touch them)
   CK(cudaStreamWaitEvent(e->st_out, sl.ev1, 0));
-  rc = enc_launch_pack(e->d_sf[k], S, e->n_mb, e->h_out[k], e->h_idx[k], e->h_cnt[k], e->d_list, e->st_out);
+  rc = enc_launch_pack(e->d_sf[k], n, e->n_mb, e->h_out[k], e->h_idx[k], e->h_cnt[k], e->d_list, e->st_out);
   if (rc) return rc;
   CK(cudaEventRecord(sl.done, e->st_out));
   sl.busy = true;
@@ -305,22 +318,42 @@ int b2h264_enc_collect(b2h264_enc* e, const uint8_t** bs, int32_t* bs_bytes, int
     e->last_us[1] = ms * 1000.f;             // deblocking wavefront + border expansion
   (void)cudaGetLastError();
   const auto t0 = std::chrono::steady_clock::now();
-  const int n_mb = e->n_mb;
-  e->last_d2h = (unsigned long long)e->S * (n_mb + 1) * sizeof(int32_t);
-  for (int s = 0; s < e->S; s++) e->last_d2h += (unsigned long long)e->h_cnt[k][s] * sizeof(MbOut);
-  std::function<void(int)> job = [&](int s) {
-    e->bs[s].clear();
-    e->ctl[s].write_access_unit_packed(sl.idr[s] != 0, e->h_out[k] + (size_t)s * n_mb, e->h_idx[k] + (size_t)s * n_mb, &e->bs[s]);
+  const int n_mb = e->n_mb, n = (int)sl.act.size();
+  e->last_d2h = (unsigned long long)n * (n_mb + 1) * sizeof(int32_t);
+  for (int i = 0; i < n; i++) e->last_d2h += (unsigned long long)e->h_cnt[k][i] * sizeof(MbOut);
+  for (int s = 0; s < e->S; s++) e->bs[s].clear();
+  std::function<void(int)> job = [&](int i) {
+    const int s = sl.act[i];
+    e->ctl[s].write_access_unit_packed(sl.idr[s] != 0, e->h_out[k] + (size_t)i * n_mb, e->h_idx[k] + (size_t)i * n_mb, &e->bs[s]);
   };
-  e->pool->run(e->S, job);
+  e->pool->run(n, job);
   e->last_us[2] = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - t0).count();
+  std::vector<uint8_t> active(e->S, 0);
+  for (int i = 0; i < n; i++) active[sl.act[i]] = 1;
   for (int s = 0; s < e->S; s++) {
-    if (bs) bs[s] = e->bs[s].data();
+    if (bs) bs[s] = active[s] ? e->bs[s].data() : nullptr;
     if (bs_bytes) bs_bytes[s] = (int32_t)e->bs[s].size();
-    if (frame_type) frame_type[s] = sl.idr[s] ? 1 : 2;
+    if (frame_type) frame_type[s] = !active[s] ? 0 : sl.idr[s] ? 1 : 2;
   }
   sl.busy = false;
   e->collect_idx++;
+  return 0;
+}
+
+int b2h264_enc_reset_stream(b2h264_enc* e, int stream) {
+  if (!e || stream < 0 || stream >= e->S) return -1;
+  if (e->slot[0].busy || e->slot[1].busy) return -3;
+  CK(cudaSetDevice(e->cfg.device));
+  e->ctl[stream] = StreamCtl();
+  e->ctl[stream].init(e->cfg.width, e->cfg.height, e->cfg.qp, e->cfg.fps, e->cfg.target_bitrate);
+  e->ctl[stream].increasing_ids = e->cfg.sps_pps_id_strategy != 0;
+  e->idr_next[stream] = 1;
+  e->have_ref_p[stream] = 0;
+  // what a fresh encoder starts from: no SAD history, no reference-picture records
+  CK(cudaMemsetAsync(e->d_sad + (size_t)stream * e->n_mb, 0, e->n_mb * sizeof(int32_t), e->st));
+  for (int i = 0; i < 2; i++) CK(cudaMemsetAsync(e->d_rinfo[i] + (size_t)stream * e->n_mb, 0, e->n_mb * sizeof(RefMbInfo), e->st));
+  CK(cudaMemsetAsync(e->d_mbi + (size_t)stream * e->n_mb, 0, e->n_mb * sizeof(MbInfo), e->st));
+  CK(cudaStreamSynchronize(e->st));
   return 0;
 }
 
@@ -334,7 +367,7 @@ int b2h264_enc_get_recon(b2h264_enc* e, int stream, uint8_t* dst) {
   if (!e || stream < 0 || stream >= e->S || !dst) return -1;
   CK(cudaSetDevice(e->cfg.device));
   CK(cudaStreamSynchronize(e->st));
-  const int set = 1 - e->cur_rec;               // the picture reconstructed last is now the reference
+  const int set = 1 - e->stream_rec[stream];    // the picture reconstructed last is now the reference
   const int w = e->cfg.width, h = e->cfg.height;
   for (int pl = 0; pl < 3; pl++) {
     const int pw = pl ? w / 2 : w, ph = pl ? h / 2 : h;

@@ -36,15 +36,55 @@ MBK_HD void edge_bs(const MbInfo* cur, const MbInfo* nb /*other MB for edge 0, e
   }
 }
 
-MBK_HD void deblock_one_mb(const EncFrameParams& p, const EncFramePtrs& f, int mbx, int mby) {
+// Working set of one macroblock's deblocking (shared memory on the device): the macroblock's samples plus the 4
+// columns / rows of the left / top macroblock its edge-0 filters read and modify, and the three MbInfo records.
+// Staging turns 8 dependent read-modify-write round trips to L2 per macroblock into one load phase, the edge
+// filters in shared memory, one store phase: the kernel is a dependency wavefront, its time is the per-MB latency.
+enum { DBK_PY = 32, DBK_PC = 16 };
+struct alignas(16) DbkTile {
+  uint8_t y[20 * DBK_PY];          // rows -4..15, cols -4..15 (sample (0,0) at y[4 * DBK_PY + 4])
+  uint8_t c[2][12 * DBK_PC];       // rows -4..7, cols -4..7
+  MbInfo m[3];                     // cur, left, top
+};
+
+MBK_HD uint32_t dbk_ld32(const uint8_t* p) {
+#ifdef __CUDA_ARCH__
+  return __ldcg(reinterpret_cast<const uint32_t*>(p));   // written by other warps of this launch
+#else
+  return *reinterpret_cast<const uint32_t*>(p);
+#endif
+}
+
+MBK_HD void deblock_one_mb(const EncFrameParams& p, const EncFramePtrs& f, int mbx, int mby, DbkTile& t) {
   const int idx = mby * p.mb_w + mbx;
-  const MbInfo* cur = f.mbi + idx;
   uint8_t* y = f.rec[0] + (size_t)(mby * 16) * p.rec_stride_y + mbx * 16;
   uint8_t* u = f.rec[1] + (size_t)(mby * 8) * p.rec_stride_c + mbx * 8;
   uint8_t* v = f.rec[2] + (size_t)(mby * 8) * p.rec_stride_c + mbx * 8;
+  const int sy = p.rec_stride_y, sc = p.rec_stride_c;
+  // ---- load phase: 100 luma words, 2 x 36 chroma words, 3 x 30 record words; all loads independent ----
+  warp_sync();
+  for (int i = lane_id(); i < 100; i += MBK_WS) {
+    const int r = i / 5, w = i - r * 5;
+    *reinterpret_cast<uint32_t*>(t.y + r * DBK_PY + 4 * w) = dbk_ld32(y + (ptrdiff_t)(r - 4) * sy + 4 * w - 4);
+  }
+  for (int i = lane_id(); i < 72; i += MBK_WS) {
+    const int pl = i / 36, j = i - pl * 36, r = j / 3, w = j - r * 3;
+    *reinterpret_cast<uint32_t*>(t.c[pl] + r * DBK_PC + 4 * w) = dbk_ld32((pl ? v : u) + (ptrdiff_t)(r - 4) * sc + 4 * w - 4);
+  }
+  {
+    constexpr int kW = (int)(sizeof(MbInfo) / 4);
+    const int nidx[3] = {idx, mbx > 0 ? idx - 1 : idx, mby > 0 ? idx - p.mb_w : idx};
+    for (int i = lane_id(); i < 3 * kW; i += MBK_WS) {
+      const int k = i / kW, w = i - k * kW;
+      reinterpret_cast<uint32_t*>(&t.m[k])[w] = reinterpret_cast<const uint32_t*>(f.mbi + nidx[k])[w];
+    }
+  }
+  warp_sync();
+  const MbInfo* cur = &t.m[0];
+  uint8_t* ty = t.y + 4 * DBK_PY + 4;
   for (int dir = 0; dir < 2; dir++) {
     const bool have_nb = dir == 0 ? mbx > 0 : mby > 0;
-    const MbInfo* nbm = dir == 0 ? cur - 1 : cur - p.mb_w;
+    const MbInfo* nbm = dir == 0 ? &t.m[1] : &t.m[2];
     for (int edge = 0; edge < 4; edge++) {
       if (edge == 0 && !have_nb) continue;
       const MbInfo* other = edge == 0 ? nbm : cur;
@@ -53,35 +93,52 @@ MBK_HD void deblock_one_mb(const EncFrameParams& p, const EncFramePtrs& f, int m
       if ((bs[0] | bs[1] | bs[2] | bs[3]) == 0) continue;
       const int qp_y = edge == 0 ? (cur->qp + other->qp + 1) >> 1 : cur->qp;
       const int qp_c = edge == 0 ? (cur->qp_c + other->qp_c + 1) >> 1 : cur->qp_c;
-      const int sx_y = dir == 0 ? 1 : p.rec_stride_y, sy_y = dir == 0 ? p.rec_stride_y : 1;
-      // luma: 16 lines, one lane each
-      {
-        const int a = tbl_alpha(qp_y), b = tbl_beta(qp_y);      // slice alpha/beta offsets are 0
-        if (a | b) {
-          uint8_t* e = y + (dir == 0 ? 4 * edge : 4 * edge * p.rec_stride_y);
-          for (int l = lane_id(); l < 16; l += MBK_WS) {
-            uint8_t* px = e + l * sy_y;
-            if (bs[0] == 4) deblock_luma_eq4_line(px, sx_y, a, b);
-            else deblock_luma_lt4_line(px, sx_y, a, b, tbl_tc0(qp_y, bs[l >> 2]));
+      // lanes 0..15: one luma line each; lanes 16..31 (device) / the same loop (host): the 8 + 8 chroma lines
+      for (int l = lane_id(); l < 32; l += MBK_WS) {
+        if (l < 16) {
+          const int a = tbl_alpha(qp_y), b = tbl_beta(qp_y);      // slice alpha/beta offsets are 0
+          if (a | b) {
+            uint8_t* px = ty + (dir == 0 ? 4 * edge + l * DBK_PY : 4 * edge * DBK_PY + l);
+            const int sx = dir == 0 ? 1 : DBK_PY;
+            if (bs[0] == 4) deblock_luma_eq4_line<false>(px, sx, a, b);
+            else deblock_luma_lt4_line<false>(px, sx, a, b, tbl_tc0(qp_y, bs[l >> 2]));
           }
-        }
-      }
-      // chroma: edges 0 and 2 only, 8 lines per plane
-      if (!(edge & 1)) {
-        const int a = tbl_alpha(qp_c), b = tbl_beta(qp_c);
-        if (a | b) {
-          const int sx_c = dir == 0 ? 1 : p.rec_stride_c, sy_c = dir == 0 ? p.rec_stride_c : 1;
-          const int off = dir == 0 ? 2 * edge : 2 * edge * p.rec_stride_c;
-          for (int l = lane_id(); l < 16; l += MBK_WS) {
-            uint8_t* px = (l < 8 ? u : v) + off + (l & 7) * sy_c;
-            if (bs[0] == 4) deblock_chroma_eq4_line(px, sx_c, a, b);
-            else deblock_chroma_lt4_line(px, sx_c, a, b, tbl_tc0(qp_c, bs[(l & 7) >> 1]) + 1);
+        } else if (!(edge & 1)) {                                  // chroma: edges 0 and 2 only
+          const int a = tbl_alpha(qp_c), b = tbl_beta(qp_c);
+          if (a | b) {
+            const int k = l - 16, ln = k & 7;
+            uint8_t* px = t.c[k >> 3] + 4 * DBK_PC + 4 + (dir == 0 ? 2 * edge + ln * DBK_PC : 2 * edge * DBK_PC + ln);
+            const int sx = dir == 0 ? 1 : DBK_PC;
+            if (bs[0] == 4) deblock_chroma_eq4_line<false>(px, sx, a, b);
+            else deblock_chroma_lt4_line<false>(px, sx, a, b, tbl_tc0(qp_c, bs[ln >> 1]) + 1);
           }
         }
       }
       warp_sync();
     }
   }
+  // ---- store phase: the macroblock, the 4 columns to its left (if any), the 3 luma rows / 1 chroma row above ----
+  const int w0 = mbx > 0 ? 0 : 1;
+  for (int i = lane_id(); i < 80; i += MBK_WS) {
+    const int r = i / 5, w = i - r * 5;
+    if (w >= w0) *reinterpret_cast<uint32_t*>(y + (ptrdiff_t)r * sy + 4 * w - 4) = *reinterpret_cast<const uint32_t*>(t.y + (r + 4) * DBK_PY + 4 * w);
+  }
+  for (int i = lane_id(); i < 48; i += MBK_WS) {
+    const int pl = i / 24, j = i - pl * 24, r = j / 3, w = j - r * 3;
+    if (w >= w0) *reinterpret_cast<uint32_t*>((pl ? v : u) + (ptrdiff_t)r * sc + 4 * w - 4) = *reinterpret_cast<const uint32_t*>(t.c[pl] + (r + 4) * DBK_PC + 4 * w);
+  }
+  if (mby > 0) {
+    for (int i = lane_id(); i < 12 + 4; i += MBK_WS) {
+      if (i < 12) {
+        const int r = i / 4 - 3, w = i & 3;
+        *reinterpret_cast<uint32_t*>(y + (ptrdiff_t)r * sy + 4 * w) = *reinterpret_cast<const uint32_t*>(t.y + (r + 4) * DBK_PY + 4 + 4 * w);
+      } else {
+        const int pl = (i - 12) >> 1, w = (i - 12) & 1;
+        *reinterpret_cast<uint32_t*>((pl ? v : u) - (ptrdiff_t)sc + 4 * w) = *reinterpret_cast<const uint32_t*>(t.c[pl] + 3 * DBK_PC + 4 + 4 * w);
+      }
+    }
+  }
+  warp_sync();
 }
 
 }  // namespace mbk

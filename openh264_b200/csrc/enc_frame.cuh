@@ -25,6 +25,7 @@ MBK_HD void mb_ctx(MbCtx& c, const EncFrameParams& p, const EncFramePtrs& f, int
     c.qp = p.qp;
     c.qp_c = tbl_chroma_qp(p.qp);          // chroma_qp_index_offset = 0
     c.lambda = tbl_lambda(p.qp);
+    c.tmap_ref = nullptr; c.wbar = nullptr;       // the device encode kernel fills these in after mb_ctx
   }
   warp_sync();
 }
@@ -48,6 +49,8 @@ MBK_HD int mb_run_stage(const MbCtx& c, MbScratch& s, int stage) {
     for (int i = lane_id(); i < MBOUT_HEADER_WORDS; i += MBK_WS) b[i] = 0;
     mb_load_all(c, s);
     phase_mark(s, 0);
+  } else {
+    mb_load_cur(c, s);                     // not parked: the source picture is read-only
   }
   if (stage == MBS_I) {
     intra_mb_md_enc(c, s, 0x7fffffff);

@@ -264,6 +264,46 @@ MBK_FN SkipResult pskip_enc(const MbCtx& c, MbScratch& s, int sad_pred_skip, int
   return r;
 }
 
+// ---- search window of the macroblock (device: one bulk tensor copy into shared memory) -----------------------------
+// (sx, sy) = integer start point of the 16x16 search relative to the macroblock; the window covers
+// [sx-16, sx+32) x [sy-16, sy+32).  win_issue starts the copy (one lane), win_wait makes it visible to the warp.
+MBK_HD void win_issue(const MbCtx& c, MbScratch& s, int sx, int sy) {
+#ifdef __CUDA_ARCH__
+  warp_sync();
+  if (c.tmap_ref != nullptr && lane_id() == 0) {
+    s.win_x0 = sx - 16; s.win_y0 = sy - 16; s.win_ok = 1;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(scratch_win(s));
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&c.wbar->bar);
+    const int X = 32 + c.mbx * 16 + s.win_x0, Y = 32 + c.mby * 16 + s.win_y0, Z = c.p.ref_plane;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic accesses to the window bytes
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(WIN_W * WIN_H) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(c.tmap_ref), "r"(X), "r"(Y), "r"(Z), "r"(bar) : "memory");
+  }
+  warp_sync();
+#else
+  (void)c; (void)sx; (void)sy;
+  s.win_ok = 0;
+#endif
+}
+MBK_HD void win_wait(const MbCtx& c, MbScratch& s) {
+#ifdef __CUDA_ARCH__
+  if (c.tmap_ref != nullptr && s.win_ok) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&c.wbar->bar);
+    const uint32_t ph = c.wbar->phase;
+    uint32_t ok = 0;
+    while (!ok)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(ok) : "r"(bar), "r"(ph) : "memory");
+    warp_sync();
+    if (lane_id() == 0) c.wbar->phase = ph ^ 1;
+    warp_sync();
+  }
+#else
+  (void)c; (void)s;
+#endif
+}
+
 // ---- integer search of one partition ------------------------------------------------------------------------
 MBK_FN void me_partition(const MbCtx& c, MbScratch& s, int blk_size, int ox, int oy, int mvp_x, int mvp_y, uint32_t sad_pred,
                          int n_mvc, const int16_t* mvc, MeState* st) {
@@ -282,6 +322,9 @@ MBK_FN void me_partition(const MbCtx& c, MbScratch& s, int blk_size, int ox, int
   in.sad_pred = sad_pred;
   in.lambda = c.lambda;
   in.calc_satd = true;
+  in.win = s.win_ok ? scratch_win(s) : nullptr;
+  in.win_w = WIN_W; in.win_h = WIN_H;
+  in.win_dx = s.win_x0 - ox; in.win_dy = s.win_y0 - oy;
   MeOut o;
   warp_me_search(in, o);
   if (lane_id() == 0) {                    // st lives in the scratch: one writer
@@ -291,6 +334,14 @@ MBK_FN void me_partition(const MbCtx& c, MbScratch& s, int blk_size, int ox, int
     st->ref = o.ref_best;
   }
   warp_sync();
+}
+// the same integer-pel range clip as me_partition: start point of a search with predictor (mvp_x, mvp_y), relative to the MB
+MBK_HD void me_start_point(const MbCtx& c, int mvp_x, int mvp_y, int* sx, int* sy) {
+  const int r = c.p.mv_range;
+  const int lo_x = -((c.mbx + 1) << 4) + 3, lo_y = -((c.mby + 1) << 4) + 3;
+  const int hi_x = ((c.p.mb_w - c.mbx) << 4) - 3, hi_y = ((c.p.mb_h - c.mby) << 4) - 3;
+  *sx = clip3((2 + mvp_x) >> 2, lo_x > -r ? lo_x : -r, hi_x < r ? hi_x : r);
+  *sy = clip3((2 + mvp_y) >> 2, lo_y > -r ? lo_y : -r, hi_y < r ? hi_y : r);
 }
 
 // ---- fractional refinement (MeRefineFracPixel, md.cpp:575) ------------------------------------------------------
@@ -332,12 +383,21 @@ MBK_FN void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy,
   uint8_t* win = reinterpret_cast<uint8_t*>(s.coef);
   static_assert(sizeof(s.coef) >= 22 * QP_STRIDE, "window aliases the coefficient buffer");
   const int ww = w + 6, wh = h + 6, wq = (ww + 3) >> 2;            // words per row (the padded reference allows the overshoot)
+  // source: the search window of the macroblock while it is still intact and covers the region, else the plane
+  const uint8_t* src = ref0 - (ptrdiff_t)3 * rs - 3;
+  int srs = rs;
+  if (s.win_ok) {
+    const int x0 = ox + (mv0x >> 2) - 3 - s.win_x0, y0 = oy + (mv0y >> 2) - 3 - s.win_y0;
+    if (x0 >= 0 && y0 >= 0 && x0 + 4 * wq <= WIN_W && y0 + wh <= WIN_H) { src = scratch_win(s) + y0 * WIN_W + x0; srs = WIN_W; }
+  }
   for (int i = lane_id(); i < wq * wh; i += MBK_WS) {
     const int r = i / wq, q4 = (i - r * wq) << 2;
-    const uint32_t v = ld4u(ref0 + (ptrdiff_t)(r - 3) * rs + (q4 - 3));
+    const uint32_t v = ld4u(src + (ptrdiff_t)r * srs + q4);
     uint8_t* d = win + r * QP_STRIDE + q4;
     d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24);
   }
+  warp_sync();
+  if (lane_id() == 0) s.win_ok = 0;          // the planes below overwrite the window bytes
   warp_sync();
   uint8_t* ph = s.qplane[0];
   uint8_t* pv = s.qplane[1];
@@ -557,7 +617,16 @@ MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
   MeState* me8x8 = &s.me[5];
   int final_type = MBT_P16x16;
   int sad_pred_mb = 0;
+  if (lane_id() == 0) s.win_ok = 0;
+  warp_sync();
   if (!is_skip) {
+    int px, py;
+    pred_mv(s, 0, 4, 0, &px, &py);
+    {                                      // the window copy flies while the candidate list is put together
+      int sx, sy;
+      me_start_point(c, px, py, &sx, &sy);
+      win_issue(c, s, sx, sy);
+    }
     sad_pred_mb = predict_sad(s);
     // step 2: P16x16 (WelsMdP16x16 :978)
     int16_t (*mvc)[2] = s.mvcand;
@@ -576,8 +645,7 @@ MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
       }
     }
     warp_sync();
-    int px, py;
-    pred_mv(s, 0, 4, 0, &px, &py);
+    win_wait(c, s);
     me_partition(c, s, BLK_16x16, 0, 0, px, py, (uint32_t)sad_pred_mb, n, &mvc[0][0], &me16);
     p16_mvx = me16.mv_x; p16_mvy = me16.mv_y;
     cost_luma = (int)me16.satd_cost;

@@ -7,7 +7,9 @@
 // Why a wavefront: MB(x,y) needs the FINAL state of (x-1,y), (x,y-1), (x+1,y-1) — motion-vector / SAD
 // predictors, intra neighbours, skip context (SURVEY.md §7 hard part 1); bit-exactness forbids breaking
 // that chain, so parallelism comes from rows (2-MB lag) x independent streams of the batch.
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "b2h264_internal.h"
 #define B2H264_WITH_INTER 1
@@ -125,8 +127,15 @@ struct EncSched {
   int* ctl;          // [0..NQ) heads, [NQ..2NQ) tails, [2NQ] macroblocks finished
   uint4* stash;      // parked scratches
 };
-static_assert(sizeof(MbScratch) % 16 == 0, "scratch is copied as uint4");
-constexpr int kStashU4 = (int)(sizeof(MbScratch) / 16);
+// Only the live part of a scratch is parked (enc_mb.cuh: kParkCore + skip_pred or pred_y): slot = kParkSlot bytes
+constexpr int kStashU4 = kParkSlot / 16, kCoreU4 = kParkCore / 16;
+static_assert(kParkSlot % 16 == 0 && kParkCore % 16 == 0, "parked ranges are copied as uint4");
+// second parked range of a macroblock that continues at `stage`: offset (uint4 units) and length
+__device__ __forceinline__ void park_extra(int stage, int* off, int* n) {
+  if (stage == MBS_BSKIP) { *off = (int)(offsetof(MbScratch, skip_pred) / 16); *n = 384 / 16; }
+  else if (stage == MBS_C) { *off = (int)(offsetof(MbScratch, pred_y) / 16); *n = 512 / 16; }
+  else { *off = 0; *n = 0; }
+}
 
 __device__ __forceinline__ void esched_push(const EncSched& q, int total, int stage, int id) {
   const int k = stage - 1;
@@ -152,7 +161,12 @@ __device__ __forceinline__ void run_task(const StreamFrame* sf, const EncSched& 
   uint4* park = q.stash + (size_t)(si * mb_h + y) * kStashU4;
   uint4* sc = reinterpret_cast<uint4*>(&s);
   if (stage != MBS_A && stage != MBS_I) {            // continue a parked macroblock
-    for (int i = lane; i < kStashU4; i += 32) sc[i] = __ldcg(park + i);
+    int xo, xn;
+    park_extra(stage, &xo, &xn);
+    for (int i = lane; i < kCoreU4 + xn; i += 32) {
+      const uint4 v = __ldcg(park + i);
+      if (i < kCoreU4) sc[i] = v; else sc[xo + i - kCoreU4] = v;
+    }
     __syncwarp();
   }
   const int next = body(sf[si], x, y, stage);
@@ -172,7 +186,9 @@ __device__ __forceinline__ void run_task(const StreamFrame* sf, const EncSched& 
       atomicAdd(q.ctl + 2 * NQ, 1);
     }
   } else {
-    for (int i = lane; i < kStashU4; i += 32) park[i] = sc[i];
+    int xo, xn;
+    park_extra(next, &xo, &xn);
+    for (int i = lane; i < kCoreU4 + xn; i += 32) park[i] = i < kCoreU4 ? sc[i] : sc[xo + i - kCoreU4];
     __threadfence();
     __syncwarp();
     if (lane == 0) esched_push(q, total, next, id);
@@ -290,12 +306,33 @@ extern "C" int b2h264_debug_phase_stats(unsigned long long* out32, int reset) {
 #ifndef ENC_MIN_CTAS
 #define ENC_MIN_CTAS 1
 #endif
-__global__ void __launch_bounds__(32 * ENC_WPC, ENC_MIN_CTAS) k_encode_mbs(const StreamFrame* __restrict__ sf, int n_streams, EncSched q, int stats) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  MbScratch& s = reinterpret_cast<MbScratch*>(smem)[threadIdx.x >> 5];
+// dynamic shared memory of the macroblock kernels: ENC_WPC scratches from a 128-byte aligned base (+128 bytes of slack)
+constexpr size_t kScratchSmem = sizeof(MbScratch) * ENC_WPC + 128;
+__device__ __forceinline__ MbScratch& my_scratch(uint8_t* smem) {
+  const uintptr_t a = (reinterpret_cast<uintptr_t>(smem) + 127) & ~uintptr_t(127);
+  return reinterpret_cast<MbScratch*>(a)[threadIdx.x >> 5];
+}
+
+// tm_ref: reference luma planes of all streams (x, y from the padded origin, z = stream); stage B stages its
+// search window out of it with one bulk tensor copy per macroblock (enc_inter.cuh: win_issue / win_wait)
+__global__ void __launch_bounds__(32 * ENC_WPC, ENC_MIN_CTAS) k_encode_mbs(const StreamFrame* __restrict__ sf, int n_streams, EncSched q, int stats,
+                                                                          const __grid_constant__ CUtensorMap tm_ref, int use_tma) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ WinBar s_wbar[ENC_WPC];
+  MbScratch& s = my_scratch(smem);
+  WinBar* wb = &s_wbar[threadIdx.x >> 5];
+  if ((threadIdx.x & 31) == 0) {
+    wb->phase = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&wb->bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const void* tmap = use_tma ? &tm_ref : nullptr;
   run_stages(sf, n_streams, q, s, stats & 1, [&](const StreamFrame& F, int x, int y, int stage) {
     const long long t0 = (stats & 1) ? clock64() : 0;
     mb_ctx(s.ctx, F.p, F.f, x, y);
+    if ((threadIdx.x & 31) == 0) { s.ctx.tmap_ref = tmap; s.ctx.wbar = wb; }
+    __syncwarp();
     int next = mb_run_stage(s.ctx, s, stage);
     if (stats & 2) while (next != MBS_DONE) next = mb_run_stage(s.ctx, s, next);      // debugging: all stages in one task
     if ((stats & 1) && (threadIdx.x & 31) == 0) {          // cycles and count per stage
@@ -307,7 +344,9 @@ __global__ void __launch_bounds__(32 * ENC_WPC, ENC_MIN_CTAS) k_encode_mbs(const
 }
 
 __global__ void __launch_bounds__(32 * ENC_WPC) k_deblock_mbs(const StreamFrame* __restrict__ sf, int n_streams, Sched q) {
-  run_mbs(sf, n_streams, q, [&](const StreamFrame& F, int x, int y) { deblock_one_mb(F.p, F.f, x, y); });
+  __shared__ DbkTile tiles[ENC_WPC];
+  DbkTile& t = tiles[threadIdx.x >> 5];
+  run_mbs(sf, n_streams, q, [&](const StreamFrame& F, int x, int y) { deblock_one_mb(F.p, F.f, x, y, t); });
 }
 
 // ---- decoder construct path (groundwork of the next SURVEY row: dec_mb.cuh) ------------------------------------------------
@@ -315,8 +354,8 @@ __global__ void __launch_bounds__(32 * ENC_WPC) k_deblock_mbs(const StreamFrame*
 // scheduled by the same dependency rule as the encoder (left + top-right done), with the simple per-warp ready list.
 __global__ void __launch_bounds__(32 * ENC_WPC) k_decode_mbs(const StreamFrame* __restrict__ sf, int n_streams, Sched q,
                                                             const MbOut* __restrict__ recs) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  MbScratch& s = reinterpret_cast<MbScratch*>(smem)[threadIdx.x >> 5];
+  extern __shared__ __align__(128) uint8_t smem[];
+  MbScratch& s = my_scratch(smem);
   run_mbs(sf, n_streams, q, [&](const StreamFrame& F, int x, int y) {
     const int n_mb = F.p.mb_w * F.p.mb_h, si = (int)(&F - sf);
     dec_one_mb(F.p, F.f, s, x, y, recs[(size_t)si * n_mb + y * F.p.mb_w + x]);
@@ -373,17 +412,31 @@ int enc_upload_deblock_tables() {
   return 0;
 }
 
-static int g_enc_blocks = 0;
-static int enc_grid_blocks() {
-  if (g_enc_blocks) return g_enc_blocks;
-  cudaFuncSetAttribute(k_encode_mbs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MbScratch) * ENC_WPC));
-  int dev = 0, sms = 0, per_sm = 0;
+// Persistent grids: exactly what the chip can hold.  cudaFuncSetAttribute and the occupancy are PER DEVICE: cached per
+// device ordinal under a lock (encoders / decoders on several devices and threads of one process).
+#include <mutex>
+template <class K>
+static int grid_blocks_for(K kernel, int* cache /*[64]*/) {
+  static std::mutex mu;
+  int dev = 0;
   cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cache[dev]) return cache[dev];
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScratchSmem);
+  int sms = 0, per_sm = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_encode_mbs, 32 * ENC_WPC, sizeof(MbScratch) * ENC_WPC);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * ENC_WPC, kScratchSmem);
   if (per_sm < 1) per_sm = 1;
-  g_enc_blocks = sms * per_sm;          // persistent: exactly what the chip can hold
-  return g_enc_blocks;
+  return cache[dev] = sms * per_sm;
+}
+static int enc_grid_blocks() {
+  static int cache[64];
+  return grid_blocks_for(k_encode_mbs, cache);
+}
+static int dec_grid_blocks() {
+  static int cache[64];
+  return grid_blocks_for(k_decode_mbs, cache);
 }
 
 // scheduler workspace layout (ints): [0..3] head/tail of the deblock list, [8..8+2NQ] encode list heads/tails/finished;
@@ -409,7 +462,7 @@ static EncSched make_esched(int* ws, int total, void* stash) {
 }
 
 int enc_launch_frame(const StreamFrame* d_sf, const uint8_t* const* d_src, int n_streams, int w, int h, int mb_w, int mb_h,
-                     int* d_ws, void* d_stash, cudaStream_t st) {
+                     int* d_ws, void* d_stash, const void* tmap_ref, cudaStream_t st) {
   int rc;
   if (d_src) {
     dim3 b(32, 8), g((mb_w * 4 + 31) / 32, (mb_h * 16 + 7) / 8, n_streams);
@@ -427,7 +480,12 @@ int enc_launch_frame(const StreamFrame* d_sf, const uint8_t* const* d_src, int n
   const int need = (total + ENC_WPC - 1) / ENC_WPC;
   if (blocks > need) blocks = need;
   static const int stats = (getenv("B2H264_ENC_STATS") ? 1 : 0) | (getenv("B2H264_FUSE_STAGES") ? 2 : 0);
-  k_encode_mbs<<<blocks, 32 * ENC_WPC, sizeof(MbScratch) * ENC_WPC, st>>>(d_sf, n_streams, qe, stats);
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  static const int no_tma = getenv("B2H264_ENC_NO_TMA") ? 1 : 0;          // debugging: search out of the plane only
+  const int use_tma = tmap_ref != nullptr && !no_tma;
+  if (use_tma) memcpy(&tm, tmap_ref, sizeof(tm));
+  k_encode_mbs<<<blocks, 32 * ENC_WPC, kScratchSmem, st>>>(d_sf, n_streams, qe, stats, tm, use_tma);
   if ((rc = b2h264_launched())) return rc;
   return 0;
 }
@@ -457,15 +515,7 @@ static Sched make_dec_sched(int* ws, int which, int total) {
 }
 int dec_launch_frame(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h, int* d_ws, const MbOut* d_recs, int deblock,
                      cudaStream_t st) {
-  static int blocks_per_launch = 0;
-  if (!blocks_per_launch) {
-    cudaFuncSetAttribute(k_decode_mbs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(MbScratch) * ENC_WPC));
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_mbs, 32 * ENC_WPC, sizeof(MbScratch) * ENC_WPC);
-    blocks_per_launch = sms * (per_sm < 1 ? 1 : per_sm);
-  }
+  const int blocks_per_launch = dec_grid_blocks();
   int rc;
   const int total = n_streams * mb_w * mb_h;
   cudaMemsetAsync(d_ws + 8, 0, 2 * (size_t)total * sizeof(int), st);
@@ -474,7 +524,7 @@ int dec_launch_frame(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h,
   k_sched_init<<<(n_streams + 127) / 128, 128, 0, st>>>(qc, n_streams, mb_w * mb_h);
   k_sched_init<<<(n_streams + 127) / 128, 128, 0, st>>>(qd, n_streams, mb_w * mb_h);
   const int need = (total + ENC_WPC - 1) / ENC_WPC;
-  k_decode_mbs<<<blocks_per_launch < need ? blocks_per_launch : need, 32 * ENC_WPC, sizeof(MbScratch) * ENC_WPC, st>>>(d_sf, n_streams, qc, d_recs);
+  k_decode_mbs<<<blocks_per_launch < need ? blocks_per_launch : need, 32 * ENC_WPC, kScratchSmem, st>>>(d_sf, n_streams, qc, d_recs);
   if ((rc = b2h264_launched())) return rc;
   if (deblock) {
     int blocks = enc_grid_blocks() * 2;

@@ -1,16 +1,25 @@
 // enc_mb.cuh — one macroblock, one warp: scratch layout, neighbour plumbing, intra mode decision and
 // intra residual coding.  (Inter: enc_inter.cuh.)  See enc_intra.cuh for the reference map.
 #pragma once
+#include <stddef.h>
+
 #include "enc_intra.cuh"
 #include "enc_types.h"
 
 namespace mbk {
+
+// per-warp mbarrier of the search-window copy (static shared memory of the encode kernel; never parked)
+struct WinBar { unsigned long long bar; uint32_t phase; uint32_t pad; };
 
 struct MbCtx {
   EncFrameParams p;
   EncFramePtrs f;
   int mbx, mby, nb;             // position, neighbour availability (NB_*)
   int qp, qp_c, lambda;
+  // device only (null elsewhere): TMA descriptor of the reference luma planes of all streams of the launch
+  // (x, y from the padded origin, z = stream) and this warp's mbarrier
+  const void* tmap_ref;
+  WinBar* wbar;
 };
 
 struct MeState {            // the parts of SWelsME the later steps of a partition need
@@ -26,39 +35,62 @@ struct InterState {
   int32_t is_skip, cost_luma, cost_skip_mb, p16_mvx, p16_mvy, final_type, cost16, bb;
 };
 
+// integer-search window of stage B: WIN_W x WIN_H reference luma samples around the 16x16 start point, staged by
+// ONE cp.async.bulk.tensor copy per macroblock (svc_motion_estimate.cpp:222-386 runs out of it: the 16-step
+// diamond never leaves +-16 samples around its start)
+enum { WIN_W = 48, WIN_H = 48 };
+
 // Per-warp working set (shared memory on the device, a plain struct in the host emulation build).
-// Plain data only (no pointers): the device scheduler parks it in global memory between stages.
-struct alignas(16) MbScratch {
+// Plain data only: the device scheduler parks the LIVE PART in global memory between stages — the prefix up to
+// and including the header of `out` (kParkCore) plus, per transition, skip_pred (A -> Bs) or pred_y (B -> C);
+// everything behind is dead across a stage boundary (cur_y / cur_c are re-read from the source picture).
+struct alignas(128) MbScratch {
+  // ---- parked prefix -------------------------------------------------------------------------------------
   RecTile tile;                 // reconstruction tile incl. neighbour samples
-  uint8_t cur_y[256];           // current MB, stride 16
-  uint8_t cur_c[128];           // Cb 0..63, Cr 64..127, stride 8
-  uint8_t pred_y[2][256];       // luma prediction ping-pong (pMemPredMb)
-  uint8_t pred_c[2][128];       // chroma prediction ping-pong (Cb, Cr)
-  uint8_t skip_pred[384];       // P-skip prediction (pSkipMb): Y 256, Cb 64, Cr 64
-  uint8_t qplane[3][18 * 32];   // fractional refinement: half-sample planes H, V, C of the partition, stride 32
-                                // (pBufferInterPredMe, md.cpp:505-510)
-  int16_t coef[384];            // pCoeffLevel: transform coefficients (coding order, 16 per 4x4)
-  int16_t dc16[16];
-  int8_t  i4m[25];              // intra4x4 mode cache: (by+1)*5+(bx+1), -1 = unavailable
+  InterState st;
   int16_t mvc[30][2];           // motion vector cache (6 wide: col 0 = left MB, row 0 = top MBs)
   int8_t  refc[30];             // reference index cache (REF_NOT_AVAIL -2 / REF_NOT_IN_LIST -1)
+  int8_t  i4m[25];              // intra4x4 mode cache: (by+1)*5+(bx+1), -1 = unavailable
+  int8_t  skip_flag[4];
   int32_t sadc[4];              // neighbour SAD costs (topleft, top, topright, left)
   int32_t sad_skip[4];
-  int8_t  skip_flag[4];
-  MbOut   out;                  // staged output record
   MbInfo  info;                 // staged MbInfo
   MbInfo  nbi[4];               // neighbours' MbInfo: 0 top-left, 1 top, 2 top-right, 3 left (valid per c.nb)
   int32_t nb_sad[4];            // neighbours' persistent SAD cost (pSadCost[0])
   int32_t nb_skip_sad[4];       // neighbours' skip SAD of THIS picture (pMbSkipSad)
+  alignas(16) MbOut out;        // staged output record: the header (MBOUT_HEADER_WORDS) is live, the levels are not
+  // ---- not parked (except skip_pred / pred_y, see above) ------------------------------------------------------
+  alignas(16) uint8_t pred_y[2][256];       // luma prediction ping-pong (pMemPredMb)
+  // The next three are contiguous and double as the search window (2304 of their 2368 bytes, 128-byte aligned for
+  // the bulk tensor copy): the window lives from the start of stage B's 16x16 search to the last sub-partition
+  // search; pred_c / qplane are first written by the refinement that follows, skip_pred is dead on that path.
+  alignas(128) uint8_t pred_c[2][128];      // chroma prediction ping-pong (Cb, Cr)
+  uint8_t skip_pred[384];       // P-skip prediction (pSkipMb): Y 256, Cb 64, Cr 64
+  uint8_t qplane[3][18 * 32];   // fractional refinement: half-sample planes H, V, C of the partition, stride 32
+                                // (pBufferInterPredMe, md.cpp:505-510)
+  alignas(16) uint8_t cur_y[256];           // current MB, stride 16
+  uint8_t cur_c[128];           // Cb 0..63, Cr 64..127, stride 8
+  int16_t coef[384];            // pCoeffLevel: transform coefficients (coding order, 16 per 4x4)
+  int16_t dc16[16];
   int32_t red[32];              // small scratch
-  InterState st;
-  // kept in the scratch rather than on the per-thread stack: the stack of 512 threads does not fit L1 next to the
+  // kept in the scratch rather than on the per-thread stack: the stack of 768 threads does not fit L1 next to the
   // scratches, and these are touched all the time (profiles/r01_encode_stages.txt)
   MbCtx ctx;                    // frame parameters / pointers / position of the macroblock being coded
   MeState me[9];                // 16x16, 16x8 x2, 8x16 x2, 8x8 x4 (warp-uniform; written by lane 0)
   int16_t mvcand[5][2];         // 16x16 search candidates
+  int32_t win_x0, win_y0, win_ok;   // search window: origin relative to the macroblock, valid flag
   uint32_t t_last;              // phase timer (profiling builds only)
 };
+static_assert(offsetof(MbScratch, skip_pred) == offsetof(MbScratch, pred_c) + 256 &&
+              offsetof(MbScratch, qplane) == offsetof(MbScratch, skip_pred) + 384 && 256 + 384 + 3 * 18 * 32 >= WIN_W * WIN_H,
+              "pred_c / skip_pred / qplane double as the search window");
+static_assert(offsetof(MbScratch, pred_c) % 128 == 0 && offsetof(MbScratch, skip_pred) % 16 == 0 && offsetof(MbScratch, pred_y) % 16 == 0 &&
+              offsetof(MbScratch, out) % 16 == 0, "alignment of the parked ranges / the bulk copy destination");
+// bytes of the scratch that cross every stage boundary
+constexpr int kParkCore = (int)((offsetof(MbScratch, out) + 4 * MBOUT_HEADER_WORDS + 15) / 16 * 16);
+constexpr int kParkExtra = 512;                               // skip_pred (384) or pred_y (512)
+constexpr int kParkSlot = kParkCore + kParkExtra;
+MBK_HD uint8_t* scratch_win(MbScratch& s) { return &s.pred_c[0][0]; }
 
 // phase timing, compiled in only with -DB2H264_PHASE_STATS (profiling build): cycles since the previous mark
 #if defined(B2H264_PHASE_STATS) && defined(__CUDA_ARCH__)

@@ -61,6 +61,8 @@ typedef struct {
   int32_t is_idr;                         // 1: I slice, 0: P slice
   int32_t mv_range;                       // iMvRange (integer pel)
   int32_t ref_is_p;                       // reference picture was coded as P (temporal candidates valid)
+  int32_t ref_plane;                      // z coordinate of the stream's reference picture in the encoder's luma tensor map
+  int32_t pad0;
 } EncFrameParams;
 
 typedef struct {

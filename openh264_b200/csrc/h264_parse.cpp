@@ -86,10 +86,17 @@ int parse_sps(BitReader& r, ParserState* st) {
   const int level = (int)r.get(8);
   const int sps_id = (int)r.ue();
   if (profile != 66) return PARSE_UNSUPPORTED;            // Baseline only (no chroma_format_idc / scaling lists)
-  st->log2_max_frame_num = (int)r.ue() + 4;
+  {
+    const uint32_t v = r.ue();
+    if (v > 12) return PARSE_INVALID;                     // log2_max_frame_num_minus4 in 0..12 (7.4.2.1.1)
+    st->log2_max_frame_num = (int)v + 4;
+  }
   st->poc_type = (int)r.ue();
-  if (st->poc_type == 0) st->log2_max_poc_lsb = (int)r.ue() + 4;
-  else if (st->poc_type != 2) return PARSE_UNSUPPORTED;
+  if (st->poc_type == 0) {
+    const uint32_t v = r.ue();
+    if (v > 12) return PARSE_INVALID;
+    st->log2_max_poc_lsb = (int)v + 4;
+  } else if (st->poc_type != 2) return PARSE_UNSUPPORTED;
   StreamParams sp;
   memset(&sp, 0, sizeof(sp));
   sp.num_ref_frames = (int)r.ue();
@@ -100,11 +107,16 @@ int parse_sps(BitReader& r, ParserState* st) {
   r.bit();                                    // direct_8x8_inference_flag
   sp.crop = r.bit() != 0;
   int cl = 0, ct = 0;
-  if (sp.crop) { cl = (int)r.ue(); sp.crop_right = (int)r.ue(); ct = (int)r.ue(); sp.crop_bottom = (int)r.ue(); }
+  if (sp.crop) {
+    const uint32_t a = r.ue(), b = r.ue(), c = r.ue(), e = r.ue();
+    if (a > 4096 || b > 4096 || c > 4096 || e > 4096) return PARSE_INVALID;
+    cl = (int)a; sp.crop_right = (int)b; ct = (int)c; sp.crop_bottom = (int)e;
+  }
   if (!r.ok()) return PARSE_TRUNCATED;
   if (sp.mb_w < 1 || sp.mb_h < 1 || sp.mb_w > 512 || sp.mb_h > 512 || sp.num_ref_frames > 16) return PARSE_INVALID;
   sp.width = sp.mb_w * 16 - 2 * (cl + sp.crop_right);
   sp.height = sp.mb_h * 16 - 2 * (ct + sp.crop_bottom);
+  if (sp.width <= (sp.mb_w - 1) * 16 || sp.height <= (sp.mb_h - 1) * 16) return PARSE_INVALID;   // cropping may only cut into the last MB
   sp.level_idc = level;
   sp.sps_id = sps_id;
   if (cl || ct) return PARSE_UNSUPPORTED;     // left / top cropping: never produced by the encoders this mirrors
@@ -153,7 +165,7 @@ int match_code(BitReader& r, const uint16_t (&tbl)[N], int n_valid) {
 
 // reads one block into lv[0..max_coef) (scan order); returns total_coeff or a negative ParseError
 int read_block(BitReader& r, int16_t* lv, int max_coef, int nc) {
-  for (int i = 0; i < 16; i++) lv[i] = 0;
+  for (int i = 0; i < max_coef; i++) lv[i] = 0;
   const int cls = nc < 0 ? 4 : kNcClass[nc > 16 ? 16 : nc];
   int total = -1, t1 = 0;
   {
@@ -236,6 +248,7 @@ int cbp_from_code(int code, bool intra) {
 int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pic) {
   if (!st->have_sps || !st->have_pps) return PARSE_NO_PARAMETER_SETS;
   const bool idr = nal.type == 5;
+  if (!idr && !st->have_ref) return PARSE_INVALID;            // a P picture before any IDR: nothing to predict from
   if (r.ue() != 0) return PARSE_UNSUPPORTED;                  // first_mb_in_slice: one slice per picture
   const int slice_type = (int)r.ue() % 5;
   if (slice_type != 0 && slice_type != 2) return PARSE_UNSUPPORTED;
@@ -272,10 +285,13 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
   pic->disable_deblocking_idc = 0;
   if (st->deblocking_control) {
     pic->disable_deblocking_idc = (int)r.ue();
+    if (pic->disable_deblocking_idc > 2) return PARSE_INVALID;
     if (pic->disable_deblocking_idc != 1) { if (r.se() != 0 || r.se() != 0) return PARSE_UNSUPPORTED; }
   }
   if (!r.ok()) return PARSE_TRUNCATED;
   if (ss.qp < 0 || ss.qp > 51) return PARSE_INVALID;
+  if (idr) { if (ss.frame_num != 0) return PARSE_INVALID; }
+  else if (ss.frame_num != ((st->last_frame_num + 1) & ((1 << st->log2_max_frame_num) - 1))) return PARSE_UNSUPPORTED;   // a gap: needs error concealment
 
   // ---- slice data ----
   const int mbw = st->sp.mb_w, n = st->sp.mb_w * st->sp.mb_h;
@@ -323,6 +339,12 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
         m.chroma_mode = (uint8_t)r.ue();
       } else return PARSE_UNSUPPORTED;                        // I_PCM
       if (m.chroma_mode > 3) return PARSE_INVALID;
+      {                                                       // prediction modes must have their neighbours (8.3.3, 8.3.4)
+        const bool L = mbx > 0, T = mby > 0;
+        if ((m.chroma_mode == 1 && !L) || (m.chroma_mode == 2 && !T) || (m.chroma_mode == 3 && !(L && T))) return PARSE_INVALID;
+        if (m.mb_type == MBT_I16x16 &&
+            ((m.i16_mode == 0 && !T) || (m.i16_mode == 1 && !L) || (m.i16_mode == 3 && !(L && T)))) return PARSE_INVALID;
+      }
     }
     if (cbp < 0) {
       cbp = cbp_from_code((int)r.ue(), m.mb_type == MBT_I4x4);
@@ -382,9 +404,10 @@ int parse_access_unit(const uint8_t* au, size_t len, ParserState* st, ParsedPict
   for (const Nal& nal : split_nals(au, len)) {
     BitReader r(nal.rbsp.data(), nal.rbsp.size());
     int rc = PARSE_OK;
-    if (nal.type == 7) rc = parse_sps(r, st);
-    else if (nal.type == 8) rc = parse_pps(r, st);
-    else if (nal.type == 1 || nal.type == 5) {
+    if (nal.type == 7 || nal.type == 8) {
+      if (got_slice) return PARSE_UNSUPPORTED;                // parameter sets after the slice of the same unit
+      rc = nal.type == 7 ? parse_sps(r, st) : parse_pps(r, st);
+    } else if (nal.type == 1 || nal.type == 5) {
       if (got_slice) return PARSE_UNSUPPORTED;                // several slices per picture
       rc = parse_slice(r, nal, st, pic);
       got_slice = true;
@@ -392,7 +415,25 @@ int parse_access_unit(const uint8_t* au, size_t len, ParserState* st, ParsedPict
     else return PARSE_UNSUPPORTED;
     if (rc != PARSE_OK) return rc;
   }
-  return got_slice ? PARSE_OK : PARSE_INVALID;
+  if (!got_slice) return PARSE_NO_PICTURE;
+  st->have_ref = true;
+  st->last_frame_num = pic->ss.frame_num;
+  return PARSE_OK;
+}
+
+int probe_access_unit(const uint8_t* au, size_t len, int* width, int* height, int* has_slice) {
+  *width = *height = *has_slice = 0;
+  for (const Nal& nal : split_nals(au, len)) {
+    if (nal.type == 1 || nal.type == 5) *has_slice = 1;
+    if (nal.type == 7) {
+      BitReader r(nal.rbsp.data(), nal.rbsp.size());
+      ParserState tmp;
+      const int rc = parse_sps(r, &tmp);
+      if (rc != PARSE_OK) return rc;
+      *width = tmp.sp.width; *height = tmp.sp.height;
+    }
+  }
+  return PARSE_OK;
 }
 
 }  // namespace b2h264

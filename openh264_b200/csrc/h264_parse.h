@@ -19,6 +19,7 @@ namespace b2h264 {
 
 enum ParseError {
   PARSE_OK = 0,
+  PARSE_NO_PICTURE = 1,        // the access unit was parsed (parameter sets taken) but holds no slice
   PARSE_TRUNCATED = -1,        // ran out of bits
   PARSE_UNSUPPORTED = -2,      // valid H.264 outside the supported class (CABAC, B slices, FMO, sub-8x8 partitions, ...)
   PARSE_INVALID = -3,          // not valid H.264 syntax / values out of range
@@ -34,6 +35,8 @@ struct ParserState {
   int pic_init_qp = 26;
   bool deblocking_control = true;
   int num_ref_idx_default = 1;
+  bool have_ref = false;         // a picture has been decoded (a P slice has something to predict from)
+  int last_frame_num = 0;
 };
 
 struct ParsedPicture {
@@ -44,5 +47,7 @@ struct ParsedPicture {
 
 // Parses one access unit: [SPS] [PPS] slice, each NAL behind a 3- or 4-byte start code.  Returns PARSE_OK or an error.
 int parse_access_unit(const uint8_t* au, size_t len, ParserState* st, ParsedPicture* pic);
+// without state: is there a slice, and the cropped size of the SPS the unit carries (0 x 0 if none)
+int probe_access_unit(const uint8_t* au, size_t len, int* width, int* height, int* has_slice);
 
 }  // namespace b2h264

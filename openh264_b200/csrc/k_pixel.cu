@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(256) k_me_search(const uint8_t* __restrict__ c
   in.sad_pred = jb->sad_pred;
   in.lambda = c_lambda[jb->qp];
   in.calc_satd = jb->calc_satd != 0;
+  in.win = nullptr; in.win_w = in.win_h = in.win_dx = in.win_dy = 0;
   MeOut o;
   warp_me_search(in, o);
   if (lane_id() == 0) {
@@ -373,6 +374,19 @@ static bool make_plane_map(CUtensorMap* tm, const uint8_t* base, uint64_t w, uin
   const cuuint32_t box[2] = {bw, bh}, es[2] = {1, 1};
   return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// rank-3 map over a stack of n equally sized byte planes (x, y, plane): the encoder's reference pictures of all
+// streams of a batch (enc_batch.cu); `out` = 128 bytes, 64-byte aligned
+int b2h264_make_tmap_planes(void* out, const void* base, uint64_t w, uint64_t h, uint64_t n, uint64_t stride_y, uint64_t stride_plane,
+                            uint32_t box_w, uint32_t box_h) {
+  tmap_encode_fn enc = tmap_encoder();
+  if (!enc) return -1;
+  const cuuint64_t dims[3] = {w, h, n}, strides[2] = {stride_y, stride_plane};
+  const cuuint32_t box[3] = {box_w, box_h, 1}, es[3] = {1, 1, 1};
+  return enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : -1;
 }
 
 // ================================================================================================

@@ -20,6 +20,10 @@ struct MeIn {
   uint32_t sad_pred;                       // early-stop threshold
   int lambda;                              // g_kiQpCostTable[qp]
   bool calc_satd;
+  // optional copy of a part of the reference plane in shared memory (stride win_w): sample (0,0) of the copy is
+  // the plane sample at integer offset (win_dx, win_dy) from `ref`; null = none.  Same bytes as the plane, so
+  // which of the two a SAD reads cannot change a result.
+  const uint8_t* win; int win_w, win_h, win_dx, win_dy;
 };
 struct MeOut {
   int mv_x, mv_y;                          // quarter-pel
@@ -27,21 +31,33 @@ struct MeOut {
   const uint8_t* ref_best;                 // matched block in the reference plane
 };
 
+// the w x h block at integer offset (mx, my) from the co-located block, readable with `m` samples of margin all
+// round: out of the shared-memory copy when it covers that, else out of the plane
+MBK_HD const uint8_t* me_block(const MeIn& in, int mx, int my, int w, int h, int m, int* stride) {
+  if (in.win) {
+    const int x = mx - in.win_dx, y = my - in.win_dy;
+    if (x >= m && y >= m && x + w + m <= in.win_w && y + h + m <= in.win_h) { *stride = in.win_w; return in.win + y * in.win_w + x; }
+  }
+  *stride = in.ref_stride;
+  return in.ref + my * in.ref_stride + mx;
+}
+
 MBK_FN void warp_me_search(const MeIn& in, MeOut& out) {
-  const int lw = blk_lw(in.blk), lh = blk_lh(in.blk);
-  const int px = in.mvp_x, py = in.mvp_y, rs = in.ref_stride;
+  const int lw = blk_lw(in.blk), lh = blk_lh(in.blk), w = 1 << lw, h = 1 << lh;
+  const int px = in.mvp_x, py = in.mvp_y;
+  int rs;
 
   int mx = clip3((2 + px) >> 2, in.min_x, in.max_x);
   int my = clip3((2 + py) >> 2, in.min_y, in.max_y);
-  const uint8_t* best_ref = in.ref + my * rs + mx;
-  int best = warp_sad(in.enc, in.enc_stride, best_ref, rs, lw, lh) + mvd_cost(in.lambda, mx * 4 - px, my * 4 - py);
+  const uint8_t* r = me_block(in, mx, my, w, h, 0, &rs);
+  int best = warp_sad(in.enc, in.enc_stride, r, rs, lw, lh) + mvd_cost(in.lambda, mx * 4 - px, my * 4 - py);
   for (int i = 0; i < in.n_mvc; i++) {
     const int cx = clip3((2 + in.mvc[2 * i]) >> 2, in.min_x, in.max_x);
     const int cy = clip3((2 + in.mvc[2 * i + 1]) >> 2, in.min_y, in.max_y);
     if (cx == mx && cy == my) continue;
-    const uint8_t* r = in.ref + cy * rs + cx;
+    r = me_block(in, cx, cy, w, h, 0, &rs);
     const int c = warp_sad(in.enc, in.enc_stride, r, rs, lw, lh) + mvd_cost(in.lambda, cx * 4 - px, cy * 4 - py);
-    if (c < best) { best = c; mx = cx; my = cy; best_ref = r; }
+    if (c < best) { best = c; mx = cx; my = cy; }
   }
   if (!(best < (int)in.sad_pred)) {
     int dx = mx * 4 - px, dy = my * 4 - py;
@@ -49,7 +65,8 @@ MBK_FN void warp_me_search(const MeIn& in, MeOut& out) {
       const int tx = (dx + px) >> 2, ty = (dy + py) >> 2;
       if (!(tx >= in.min_x && tx < in.max_x && ty >= in.min_y && ty < in.max_y)) continue;
       int s[4];
-      warp_sad_four(in.enc, in.enc_stride, best_ref, rs, lw, lh, s);
+      r = me_block(in, tx, ty, w, h, 1, &rs);
+      warp_sad_four(in.enc, in.enc_stride, r, rs, lw, lh, s);
       const int cu = s[0] + mvd_cost(in.lambda, dx, dy - 4), cd = s[1] + mvd_cost(in.lambda, dx, dy + 4);
       const int cl = s[2] + mvd_cost(in.lambda, dx - 4, dy), cr = s[3] + mvd_cost(in.lambda, dx + 4, dy);
       int sx = 0, sy = 0;
@@ -60,17 +77,18 @@ MBK_FN void warp_me_search(const MeIn& in, MeOut& out) {
       if (cr < best) { best = cr; sx = 1; sy = 0; moved = true; }
       if (!moved) break;
       dx += 4 * sx; dy += 4 * sy;
-      best_ref += sx + sy * rs;
     }
     mx = (dx + px) >> 2; my = (dy + py) >> 2;
   }
   out.mv_x = mx * 4; out.mv_y = my * 4;
   out.sad_cost = (uint32_t)best;
   out.satd_cost = (uint32_t)best;
-  out.ref_best = best_ref;
-  if (in.calc_satd)
-    out.satd_cost = (uint32_t)(warp_satd(in.enc, in.enc_stride, best_ref, rs, lw, lh) +
+  out.ref_best = in.ref + my * in.ref_stride + mx;
+  if (in.calc_satd) {
+    r = me_block(in, mx, my, w, h, 0, &rs);
+    out.satd_cost = (uint32_t)(warp_satd(in.enc, in.enc_stride, r, rs, lw, lh) +
                                mvd_cost(in.lambda, out.mv_x - px, out.mv_y - py));
+  }
 }
 
 }  // namespace mbk

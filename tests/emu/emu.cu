@@ -135,7 +135,7 @@ void expand_frame_host(const EncFrameParams& p, const EncFramePtrs& f) {
 }
 void deblock_frame_host(const EncFrameParams& p, const EncFramePtrs& f) {
   for (int mby = 0; mby < p.mb_h; mby++)
-    for (int mbx = 0; mbx < p.mb_w; mbx++) deblock_one_mb(p, f, mbx, mby);
+    for (int mbx = 0; mbx < p.mb_w; mbx++) { static DbkTile tile; deblock_one_mb(p, f, mbx, mby, tile); }
 }
 
 }  // namespace
@@ -364,17 +364,18 @@ static int random_pictures(unsigned seed, int pictures, bool decodable, uint8_t*
         qp = qp < 10 ? 10 : qp > 45 ? 45 : qp;
       }
       cur_qp = qp;
-      // intra modes: in decodable streams only modes whose neighbours exist (a conforming stream never uses others);
+      // intra 16x16 / chroma modes: only modes whose neighbours exist (the parser rejects others as invalid); I4x4 modes
+      // likewise in decodable streams;
       // DDL / VL without a top-right neighbour ARE allowed (8.3.1.2 substitutes samples) and are generated on purpose
       const bool L = (nbav & NB_LEFT) != 0, T = (nbav & NB_TOP) != 0, TL = (nbav & NB_TOPLEFT) != 0;
       if (MBT_IS_INTRA(m.mb_type)) {
         int cm = (int)rnd(4);                                    // 0 DC, 1 H, 2 V, 3 plane
-        if (decodable && ((cm == 1 && !L) || (cm == 2 && !T) || (cm == 3 && !(L && T && TL)))) cm = 0;
+        if (((cm == 1 && !L) || (cm == 2 && !T) || (cm == 3 && !(L && T && TL)))) cm = 0;
         m.chroma_mode = (uint8_t)cm;
       }
       if (m.mb_type == MBT_I16x16) {
         int im = (int)rnd(4);                                    // 0 V, 1 H, 2 DC, 3 plane
-        if (decodable && ((im == 0 && !T) || (im == 1 && !L) || (im == 3 && !(L && T && TL)))) im = 2;
+        if (((im == 0 && !T) || (im == 1 && !L) || (im == 3 && !(L && T && TL)))) im = 2;
         m.i16_mode = (uint8_t)im;
         fill_block(m.luma_dc, 16);
       }

@@ -1,0 +1,152 @@
+// broker.cpp — see broker.h
+#include "broker.h"
+
+#include <cuda_runtime_api.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace b2wels {
+
+static long env_long(const char* name, long dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atol(v) : dflt;
+}
+
+Pool::Pool(const PoolKey& key, int capacity, int device) : key_(key), cap_(capacity), device_(device) {
+  frame_bytes_ = (size_t)key.width * key.height * 3 / 2;
+  wait_us_ = env_long("B2H264_BROKER_WAIT_US", 2000);
+  b2h264_enc_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.width = key.width; cfg.height = key.height; cfg.qp = key.qp; cfg.fps = key.fps;
+  cfg.target_bitrate = key.bitrate;
+  cfg.n_streams = capacity;
+  cfg.entropy_threads = 0;
+  cfg.device = device;
+  cfg.sps_pps_id_strategy = key.strategy;
+  if (b2h264_enc_create(&cfg, &enc_) != 0) { enc_ = nullptr; return; }
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaHostAlloc((void**)&pinned_, frame_bytes_ * capacity, cudaHostAllocPortable) != cudaSuccess) {
+    b2h264_enc_destroy(enc_);
+    enc_ = nullptr; pinned_ = nullptr;
+    return;
+  }
+  state_.assign(capacity, FREE);
+  au_.resize(capacity);
+  idr_.assign(capacity, 0);
+}
+
+Pool::~Pool() {
+  if (enc_) b2h264_enc_destroy(enc_);
+  if (pinned_) cudaFreeHost(pinned_);
+}
+
+int Pool::acquire() {
+  std::unique_lock<std::mutex> lk(m_);
+  for (int s = 0; s < cap_; s++)
+    if (state_[s] == FREE) { state_[s] = IDLE; n_registered_++; return s; }
+  return -1;
+}
+
+void Pool::release(int slot) {
+  std::unique_lock<std::mutex> lk(m_);
+  cv_.wait(lk, [&] { return !flushing_; });            // nothing of this pool is in flight now
+  b2h264_enc_reset_stream(enc_, slot);
+  state_[slot] = FREE;
+  n_registered_--;
+  cv_.notify_all();                                    // "everybody is waiting" may have become true
+}
+
+int Pool::registered() {
+  std::unique_lock<std::mutex> lk(m_);
+  return n_registered_;
+}
+
+int Pool::force_idr(int slot) {
+  std::unique_lock<std::mutex> lk(m_);
+  cv_.wait(lk, [&] { return !flushing_; });
+  return b2h264_enc_force_idr(enc_, slot);
+}
+
+// codes every PENDING picture as one batch; called with the lock held, returns with it held
+void Pool::flush_locked(std::unique_lock<std::mutex>& lk) {
+  flushing_ = true;
+  std::vector<const uint8_t*> src(cap_, nullptr);
+  for (int s = 0; s < cap_; s++)
+    if (state_[s] == PENDING) { state_[s] = INFLIGHT; src[s] = staging(s); }
+  n_pending_ = 0;
+  lk.unlock();
+  std::vector<const uint8_t*> bs(cap_, nullptr);
+  std::vector<int32_t> nb(cap_, 0), ft(cap_, 0);
+  int rc = b2h264_enc_submit(enc_, src.data(), 0);
+  if (rc == 0) rc = b2h264_enc_collect(enc_, bs.data(), nb.data(), ft.data());
+  lk.lock();
+  for (int s = 0; s < cap_; s++) {
+    if (state_[s] != INFLIGHT) continue;
+    if (rc == 0 && bs[s]) { au_[s].assign(bs[s], bs[s] + nb[s]); idr_[s] = ft[s] == 1; state_[s] = DONE; }
+    else state_[s] = FAILED;
+  }
+  last_rc_ = rc;
+  flushing_ = false;
+  cv_.notify_all();
+}
+
+int Pool::encode(int slot, std::vector<uint8_t>* au, bool* idr) {
+  std::unique_lock<std::mutex> lk(m_);
+  if (slot < 0 || slot >= cap_ || state_[slot] != IDLE) return -1;
+  state_[slot] = PENDING;
+  n_pending_++;
+  const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(wait_us_);
+  while (state_[slot] != DONE && state_[slot] != FAILED) {
+    if (state_[slot] == PENDING && !flushing_) {
+      if (n_pending_ >= n_registered_ || std::chrono::steady_clock::now() >= deadline) { flush_locked(lk); continue; }
+      cv_.wait_until(lk, deadline);
+    } else {
+      cv_.wait(lk);
+    }
+  }
+  const bool ok = state_[slot] == DONE;
+  if (ok) { au->swap(au_[slot]); *idr = idr_[slot] != 0; }
+  state_[slot] = IDLE;
+  return ok ? 0 : (last_rc_ ? last_rc_ : -1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+Broker& Broker::get() {
+  static Broker* b = new Broker();       // never destroyed: encoder objects may outlive static destruction order
+  return *b;
+}
+
+std::shared_ptr<Pool> Broker::attach(const PoolKey& key, int* slot) {
+  std::lock_guard<std::mutex> g(m_);
+  int same_class = 0;
+  for (auto& p : pools_) {
+    if (!(p->key() == key)) continue;
+    same_class++;
+    const int s = p->acquire();
+    if (s >= 0) { *slot = s; return p; }
+  }
+  // capacity: B2H264_BROKER_SLOTS, else 4, 16, 64, 128, 128, ... for successive pools of a class (a lone encoder stays
+  // small: a slot costs ~30 MB of HBM and ~25 MB of pinned host memory at 1080p)
+  long cap = env_long("B2H264_BROKER_SLOTS", 0);
+  if (cap <= 0) { cap = 4L << (2 * (same_class < 3 ? same_class : 3)); if (cap > 128) cap = 128; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return nullptr;
+  const long dev_env = env_long("B2H264_DEVICE", -1);
+  const int device = dev_env >= 0 ? (int)(dev_env % ndev) : (next_device_++ % ndev);
+  auto p = std::make_shared<Pool>(key, (int)cap, device);
+  if (!p->ok()) return nullptr;
+  pools_.push_back(p);
+  *slot = p->acquire();
+  return p;
+}
+
+void Broker::detach(const std::shared_ptr<Pool>& pool, int slot) {
+  pool->release(slot);
+  std::lock_guard<std::mutex> g(m_);
+  if (pool->registered() == 0)
+    for (size_t i = 0; i < pools_.size(); i++)
+      if (pools_[i] == pool) { pools_.erase(pools_.begin() + i); break; }     // the last reference frees the encoder
+}
+
+}  // namespace b2wels

@@ -1,0 +1,83 @@
+// broker.h — process-wide batching broker behind layer 3 (include/b2h264_wels_api.h).
+//
+// The reference's ISVCEncoder is one object per stream and EncodeFrame is synchronous
+// (codec/encoder/plus/src/welsEncoderExt.cpp:375).  The B200 pipeline earns its throughput by coding MANY streams
+// per kernel launch (include/b2h264_codec.h, layer 2).  The broker reconciles the two: ISVCEncoder objects with
+// equal configuration register as streams (slots) of ONE shared b2h264_enc ("pool"); EncodeFrame stages its picture,
+// and the callers that arrive within a short window are coded as one batch — the caller that completes the set
+// (or whose wait expires) runs submit + collect for everybody, the others sleep on a condition variable.
+//   * pool capacity: B2H264_BROKER_SLOTS streams (default 128); further objects of the class open another pool,
+//     pools are placed round-robin over the visible CUDA devices;
+//   * wait: B2H264_BROKER_WAIT_US (default 2000) after a caller's arrival, skipped when every registered stream
+//     of the pool is already waiting (so a lone encoder never waits).
+// Streams that do not take part in a batch are passed as NULL sources to b2h264_enc_submit and keep their state.
+#pragma once
+#include <stdint.h>
+
+#include <chrono>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "b2h264_codec.h"
+
+namespace b2wels {
+
+struct PoolKey {
+  int width, height, qp, bitrate, strategy;
+  float fps;
+  bool operator==(const PoolKey& o) const {
+    return width == o.width && height == o.height && qp == o.qp && bitrate == o.bitrate && strategy == o.strategy && fps == o.fps;
+  }
+};
+
+class Pool {
+ public:
+  Pool(const PoolKey& key, int capacity, int device);
+  ~Pool();
+  bool ok() const { return enc_ != nullptr; }
+  const PoolKey& key() const { return key_; }
+  int device() const { return device_; }
+  int acquire();                     // a free slot (fresh stream state) or -1
+  void release(int slot);
+  int registered();
+  // synchronous: codes `planes` (tightly packed I420 already gathered into the slot's staging picture by stage())
+  // as the next picture of `slot`; *au receives the access unit, *idr its type.  0 or a negative / CUDA error.
+  uint8_t* staging(int slot) { return pinned_ + (size_t)slot * frame_bytes_; }
+  int encode(int slot, std::vector<uint8_t>* au, bool* idr);
+  int force_idr(int slot);
+
+ private:
+  enum State { FREE, IDLE, PENDING, INFLIGHT, DONE, FAILED };
+  void flush_locked(std::unique_lock<std::mutex>& lk);
+  PoolKey key_;
+  int cap_, device_;
+  size_t frame_bytes_;
+  b2h264_enc* enc_ = nullptr;
+  uint8_t* pinned_ = nullptr;
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::vector<State> state_;
+  std::vector<std::vector<uint8_t>> au_;
+  std::vector<uint8_t> idr_;
+  int n_registered_ = 0, n_pending_ = 0, last_rc_ = 0;
+  bool flushing_ = false;
+  long wait_us_;
+};
+
+// the pools of the process
+class Broker {
+ public:
+  static Broker& get();
+  // registers a stream; returns its pool + slot (nullptr on failure)
+  std::shared_ptr<Pool> attach(const PoolKey& key, int* slot);
+  void detach(const std::shared_ptr<Pool>& pool, int slot);
+
+ private:
+  std::mutex m_;
+  std::vector<std::shared_ptr<Pool>> pools_;
+  int next_device_ = 0;
+};
+
+}  // namespace b2wels

@@ -1,5 +1,6 @@
 // wels_encoder.cpp — layer 3: an ISVCEncoder (codec/api/wels/codec_api.h:272-339) over the layer-2 C ABI
-// (include/b2h264_codec.h), one stream per object.  Compiled against the reference's public API headers so that
+// (include/b2h264_codec.h).  One object = one stream, but NOT one private GPU encoder: objects of equal configuration
+// are streams of a shared batched encoder and their EncodeFrame calls are coded together (broker.h).  Compiled against the reference's public API headers so that
 // the vtable slot order and the parameter / bitstream-info structures are the reference's own
 // (include/b2h264_wels_api.h).  Behavioural model: CWelsH264SVCEncoder (codec/encoder/plus/src/welsEncoderExt.cpp):
 // Initialize* validate and (re)create the encoder, EncodeFrame is synchronous and returns encoder-owned bitstream
@@ -12,6 +13,7 @@
 #include <vector>
 
 #include "b2h264_codec.h"
+#include "broker.h"
 #include "codec_api.h"
 #include "codec_ver.h"
 
@@ -42,11 +44,14 @@ class B2Encoder : public ISVCEncoder {
     e.sSpatialLayers[0].iVideoHeight = p->iPicHeight;
     e.sSpatialLayers[0].fFrameRate = p->fMaxFrameRate;
     e.sSpatialLayers[0].iSpatialBitrate = p->iTargetBitrate;
-    // the defaults switch on tools this pipeline does not implement; Initialize() callers get them only if
-    // they would have no effect, i.e. never: state it instead of guessing
-    e.bEnableSceneChangeDetect = e.bEnableBackgroundDetection = e.bEnableAdaptiveQuant = e.bEnableFrameSkip = false;
-    if (p->iRCMode != RC_OFF_MODE) { why("Initialize(SEncParamBase): rate control is on (only RC_OFF_MODE)"); return cmUnsupportedData; }
-    why("Initialize(SEncParamBase) enables scene-change/background detection/adaptive quant by default; use InitializeExt");
+    // ParamBaseTranscode keeps FillDefault's tools switched on: scene-change detection (inserts IDRs), background
+    // detection (changes the skip decision), adaptive quantisation (per-MB QP even with RC off: WelsRcMbInitDisable,
+    // ratectl.cpp:1301), frame skipping, and LOW_COMPLEXITY mode decision.  None of them is a no-op for the output,
+    // so this entry point cannot be honoured bit-exactly; it is refused with the reason instead of approximated.
+    if (p->iRCMode != RC_OFF_MODE) { why("Initialize(SEncParamBase): rate control is on (only RC_OFF_MODE; needs the on-device bit count)"); return cmUnsupportedData; }
+    why("Initialize(SEncParamBase) implies bEnableSceneChangeDetect, bEnableBackgroundDetection, bEnableAdaptiveQuant and "
+        "iComplexityMode = LOW_COMPLEXITY, which change the bitstream; use InitializeExt with them off");
+    (void)e;
     return cmUnsupportedData;
   }
 
@@ -79,26 +84,23 @@ class B2Encoder : public ISVCEncoder {
     REQUIRE(p->uiMaxNalSize == 0, "uiMaxNalSize");
 #undef REQUIRE
     Uninitialize();
-    b2h264_enc_config cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.width = p->iPicWidth;
-    cfg.height = p->iPicHeight;
-    cfg.qp = l.iDLayerQp;
-    float fps = p->fMaxFrameRate;                      // WELS_CLIP3 (param_svc.h:238)
-    fps = fps < kMinFps ? kMinFps : (fps > kMaxFps ? kMaxFps : fps);
-    cfg.fps = fps;
-    cfg.target_bitrate = p->iTargetBitrate;
-    cfg.n_streams = 1;
-    cfg.entropy_threads = 1;
-    cfg.device = 0;
-    cfg.sps_pps_id_strategy = p->eSpsPpsIdStrategy == INCREASING_ID ? 1 : 0;
-    if (b2h264_enc_create(&cfg, &enc_) != 0 || !enc_) { enc_ = nullptr; return cmMallocMemeError; }
+    b2wels::PoolKey key;
+    key.width = p->iPicWidth;
+    key.height = p->iPicHeight;
+    key.qp = l.iDLayerQp;
+    // level selection inputs exactly as the reference derives them (param_svc.h:409-437, au_set.cpp:526):
+    // the layer's frame rate clipped to [MIN_FRAME_RATE, clipped fMaxFrameRate], the layer's bitrate (total as fallback)
+    float fmax = p->fMaxFrameRate;                      // WELS_CLIP3 (param_svc.h:238)
+    fmax = fmax < kMinFps ? kMinFps : (fmax > kMaxFps ? kMaxFps : fmax);
+    float fps = l.fFrameRate;
+    fps = fps < kMinFps ? kMinFps : (fps > fmax ? fmax : fps);
+    key.fps = fps;
+    key.bitrate = l.iSpatialBitrate ? l.iSpatialBitrate : p->iTargetBitrate;
+    key.strategy = p->eSpsPpsIdStrategy == INCREASING_ID ? 1 : 0;
+    pool_ = b2wels::Broker::get().attach(key, &slot_);
+    if (!pool_ || slot_ < 0) { pool_.reset(); slot_ = -1; return cmMallocMemeError; }
     par_ = *p;
-    w_ = cfg.width; h_ = cfg.height;
-    if (cudaHostAlloc((void**)&pinned_, (size_t)w_ * h_ * 3 / 2, cudaHostAllocDefault) != cudaSuccess) {
-      Uninitialize();
-      return cmMallocMemeError;
-    }
+    w_ = key.width; h_ = key.height;
     return cmResultSuccess;
   }
 
@@ -109,30 +111,27 @@ class B2Encoder : public ISVCEncoder {
   }
 
   int EXTAPI Uninitialize() override {
-    if (enc_) { b2h264_enc_destroy(enc_); enc_ = nullptr; }
-    if (pinned_) { cudaFreeHost(pinned_); pinned_ = nullptr; }
+    if (pool_) { b2wels::Broker::get().detach(pool_, slot_); pool_.reset(); slot_ = -1; }
     return cmResultSuccess;
   }
 
   int EXTAPI EncodeFrame(const SSourcePicture* pic, SFrameBSInfo* info) override {
-    if (!enc_ || !pic || !info) return cmInitParaError;            // welsEncoderExt.cpp:376-379
+    if (!pool_ || !pic || !info) return cmInitParaError;            // welsEncoderExt.cpp:376-379
     if (pic->iColorFormat != videoFormatI420) return cmInitParaError;   // :380
     if (pic->iPicWidth != w_ || pic->iPicHeight != h_) return cmInitParaError;
-    // the caller may reuse its planes after return: gather them (any stride) into the pinned staging picture
-    uint8_t* d = pinned_;
+    // the caller may reuse its planes after return: gather them (any stride) into this stream's page-locked staging
+    // picture, which the batch DMA reads in place
+    uint8_t* d = pool_->staging(slot_);
     for (int pl = 0; pl < 3; pl++) {
       const int pw = pl ? w_ / 2 : w_, ph = pl ? h_ / 2 : h_;
       if (!pic->pData[pl] || pic->iStride[pl] < pw) return cmInitParaError;
-      for (int y = 0; y < ph; y++) memcpy(d + (size_t)y * pw, pic->pData[pl] + (size_t)y * pic->iStride[pl], pw);
+      if (pic->iStride[pl] == pw) memcpy(d, pic->pData[pl], (size_t)pw * ph);
+      else for (int y = 0; y < ph; y++) memcpy(d + (size_t)y * pw, pic->pData[pl] + (size_t)y * pic->iStride[pl], pw);
       d += (size_t)pw * ph;
     }
-    const uint8_t* src[1] = {pinned_};
-    if (b2h264_enc_submit(enc_, src, 0) != 0) return cmUnknownReason;
-    const uint8_t* bs = nullptr;
-    int32_t bytes = 0, ftype = 0;
-    if (b2h264_enc_collect(enc_, &bs, &bytes, &ftype) != 0) return cmUnknownReason;
-    au_.assign(bs, bs + bytes);
-    fill_info(info, ftype == 1, pic->uiTimeStamp);
+    bool idr = false;
+    if (pool_->encode(slot_, &au_, &idr) != 0) return cmUnknownReason;
+    fill_info(info, idr, pic->uiTimeStamp);
     return cmResultSuccess;
   }
 
@@ -142,9 +141,9 @@ class B2Encoder : public ISVCEncoder {
   }
 
   int EXTAPI ForceIntraFrame(bool idr, int /*layer*/ = -1) override {
-    if (!enc_) return 1;
+    if (!pool_) return 1;
     if (!idr) return 1;                                            // welsEncoderExt.cpp: nothing to do
-    return b2h264_enc_force_idr(enc_, 0) == 0 ? 0 : 1;
+    return pool_->force_idr(slot_) == 0 ? 0 : 1;
   }
 
   int EXTAPI SetOption(ENCODER_OPTION id, void* v) override {
@@ -168,7 +167,7 @@ class B2Encoder : public ISVCEncoder {
 
   int EXTAPI GetOption(ENCODER_OPTION id, void* v) override {
     if (!v) return cmInitParaError;
-    if (!enc_) return cmInitExpected;
+    if (!pool_) return cmInitExpected;
     switch (id) {
       case ENCODER_OPTION_DATAFORMAT: *(int*)v = videoFormatI420; return cmResultSuccess;
       case ENCODER_OPTION_IDR_INTERVAL: *(int*)v = 0; return cmResultSuccess;
@@ -250,10 +249,10 @@ class B2Encoder : public ISVCEncoder {
     info->uiTimeStamp = ts;
   }
 
-  b2h264_enc* enc_ = nullptr;
+  std::shared_ptr<b2wels::Pool> pool_;
+  int slot_ = -1;
   SEncParamExt par_;
   int w_ = 0, h_ = 0;
-  uint8_t* pinned_ = nullptr;
   std::vector<uint8_t> au_;
   std::vector<int> nal_len_;
 };
@@ -276,13 +275,7 @@ int WelsCreateSVCEncoder(ISVCEncoder** pp) {
 
 void WelsDestroySVCEncoder(ISVCEncoder* p) { delete static_cast<B2Encoder*>(p); }
 
-long WelsCreateDecoder(ISVCDecoder** pp) {
-  if (pp) *pp = nullptr;
-  fprintf(stderr, "[b2h264] WelsCreateDecoder: the ISVCDecoder object is not built yet (the batched decoder is b2h264_dec_*, DESIGN.md section 9)\n");
-  return 1;
-}
-void WelsDestroyDecoder(ISVCDecoder*) {}
-int WelsGetDecoderCapability(SDecoderCapability*) { return 1; }
+// WelsCreateDecoder / WelsDestroyDecoder / WelsGetDecoderCapability: wels_decoder.cpp
 
 OpenH264Version WelsGetCodecVersion(void) {
   OpenH264Version v = {OPENH264_MAJOR, OPENH264_MINOR, OPENH264_REVISION, OPENH264_RESERVED};

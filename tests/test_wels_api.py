@@ -73,3 +73,61 @@ def test_drop_in_same_driver_two_libraries(tmp_path, w, h, n, qp, idr_at):
     assert r1.returncode == 0, r1.stderr
     assert bs0 == bs1, "bitstream through ISVCEncoder differs from the reference"
     assert lay0 == lay1, "SFrameBSInfo layout / defaults differ:\n" + lay0 + "\n---\n" + lay1
+
+
+# ---- ISVCDecoder object and the batching broker behind ISVCEncoder -------------------------------------------------------
+DEC_DRIVER = os.path.join(ROOT, "oracle", "_ref", "wels_dec_driver")
+MT_DRIVER = os.path.join(ROOT, "oracle", "_ref", "wels_mt_driver")
+
+
+def drive_dec(lib, bs, tmp, tag):
+    src = os.path.join(tmp, tag + ".264")
+    with open(src, "wb") as f:
+        f.write(bs)
+    out, log = os.path.join(tmp, tag + ".yuv"), os.path.join(tmp, tag + ".log")
+    r = subprocess.run([DEC_DRIVER, lib, src, out, log], capture_output=True, text=True, timeout=300)
+    return r, (open(out, "rb").read() if os.path.exists(out) else b""), (open(log).read() if os.path.exists(log) else "")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,n,qp", [(176, 144, 6, 26), (640, 360, 4, 34), (180, 148, 3, 20)])
+def test_decoder_drop_in_same_driver_two_libraries(tmp_path, w, h, n, qp):
+    """ISVCDecoder (Initialize / DecodeFrameNoDelay / GetOption / FlushFrame, SBufferInfo contract): the same
+    application binary, NAL by NAL like the reference's h264dec, with the compiled reference and with our library —
+    identical pictures, identical call log (states, ready flags, sizes, timestamps, frames left)."""
+    assert os.path.exists(DEC_DRIVER) and os.path.exists(OURLIB), "prebuilt layer-3 artefacts missing on the GPU box"
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_encoder_golden import ref_encode
+    clip = h264lib.synth_clip(w, h, n, seed=21)
+    bs, _, _ = ref_encode(clip, w, h, n, qp, 30.0)
+    r0, y0, l0 = drive_dec(REFLIB, bytes(bs), str(tmp_path), "ref")
+    r1, y1, l1 = drive_dec(OURLIB, bytes(bs), str(tmp_path), "b2")
+    assert r0.returncode == 0, r0.stderr
+    assert r1.returncode == 0, r1.stderr
+    assert len(y0) == n * w * h * 3 // 2 and y0 == y1, "pictures through ISVCDecoder differ from the reference"
+    assert l0 == l1, "call log differs:\n" + l0 + "\n---\n" + l1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("threads,slots", [(6, 0), (5, 2)])
+def test_broker_many_encoder_objects_one_batch(tmp_path, threads, slots):
+    """T application threads, each with its own ISVCEncoder object, different phases of the clip: behind the API the
+    objects are streams of shared batched encoders (B2H264_BROKER_SLOTS = 2 forces several pools).  Every thread's
+    stream must equal what the reference's API produces for the same pictures."""
+    assert os.path.exists(MT_DRIVER) and os.path.exists(OURLIB), "prebuilt layer-3 artefacts missing on the GPU box"
+    w, h, n, qp, frames = 320, 192, 8, 27, 7
+    clip = h264lib.synth_clip(w, h, n, seed=31)
+    yuv = os.path.join(str(tmp_path), "clip.yuv")
+    open(yuv, "wb").write(clip.tobytes())
+    outs = {}
+    for tag, lib in (("ref", REFLIB), ("b2", OURLIB)):
+        env = dict(os.environ)
+        if slots:
+            env["B2H264_BROKER_SLOTS"] = str(slots)
+        r = subprocess.run([MT_DRIVER, lib, yuv, str(w), str(h), str(n), str(qp), str(threads), str(frames), "0", "3",
+                            os.path.join(str(tmp_path), tag)], capture_output=True, text=True, timeout=600, env=env)
+        assert r.returncode == 0, r.stderr + r.stdout
+        outs[tag] = [open(os.path.join(str(tmp_path), "%s.%d.264" % (tag, t)), "rb").read() for t in range(threads)]
+    for t in range(threads):
+        assert len(outs["ref"][t]) > 0 and outs["ref"][t] == outs["b2"][t], "thread %d differs from the reference" % t

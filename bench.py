@@ -4,8 +4,19 @@
 A "step" = one batch-frame: every one of the S independent 1080p streams resident on this GPU advances by
 one picture (mode decision + ME + transform/quant + reconstruction + deblocking + border expansion on the
 GPU, CAVLC on host threads).  Workload = BASELINE.json configs[2]: synthetic 1920x1080 I420, constant
-QP 26, camera mode, single slice, complexity HIGH ("full ME": SATD costs, all partitions), IDR + P...;
-the bitstream is bit-identical to the reference encoder's (tests/test_gpu_encoder.py).
+QP 26, camera mode, single slice, complexity HIGH ("full ME": SATD costs, all partitions), IDR + P...
+
+Three measurements per run, all on the same pictures:
+  value        layer 2 (b2h264_enc_submit / collect), sources already resident in HBM
+  e2e          THE REFERENCE'S OWN API: S application threads, each with its own ISVCEncoder object, calling
+               EncodeFrame with host pictures (tests/wels/wels_mt_driver.cpp against libopenh264_b200_wels.so; the
+               objects are streams of shared batched encoders, openh264_b200/wels/broker.h); host->device and
+               device->host copies inside the timed region
+  e2e_layer2   layer 2 with pinned host pictures (what round 1 reported as e2e)
+After the timed regions the access units of EVERY stream of every mode are hashed and compared with the unmodified
+reference encoder (oracle/_ref) run on the same picture order: "parity_checked" = number of streams compared; a
+mismatch fails the run.  A second workload point ("workload_hard": +-8 noise, few skipped macroblocks, ~27x the bits) is reported
+next to the headline.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--streams S] [--impl reference]
 
@@ -15,10 +26,12 @@ max-over-ranks of the timed interval.
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -30,13 +43,41 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 W, H, QP, FPS = 1920, 1080, 26, 30.0
 CLIP_FRAMES = 16                      # distinct synthetic pictures; played forward/backward (no scene cuts)
+PHASE_STEP = 2                        # stream s starts PHASE_STEP * s pictures into the ping-pong order: 15 distinct sequences
+HARD_NOISE, HARD_FRAMES = 8, 8        # second workload point: +-8 per-frame noise (~130 KB per P picture = 31 Mbit/s at 30 fps; +-12 gives 400 KB)
 ALG_BYTES_PER_MB = 2016               # cur 384 + ref 384 + recon 384 + levels 768 + MVs 64 + meta 32
 MBS_PER_FRAME = 120 * 68
+FSZ = W * H * 3 // 2
+WORKLOAD = "encode synthetic 1920x1080 I420, constant QP 26, camera, single slice, complexity HIGH, CAVLC (BASELINE.json configs[2])"
 
 
-def clip_order(n):
-    seq = list(range(CLIP_FRAMES)) + list(range(CLIP_FRAMES - 2, 0, -1))
-    return [seq[i % len(seq)] for i in range(n)]
+def ping_pong(n_clip):
+    return list(range(n_clip)) + list(range(n_clip - 2, 0, -1))
+
+
+def stream_frame(seq, s, i):
+    """index into the clip of picture i of stream s"""
+    return seq[(i + PHASE_STEP * s) % len(seq)]
+
+
+def host_cores():
+    """cores this process may really use: the affinity mask, capped by the cgroup CPU quota"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max",):
+        try:
+            q, p = open(path).read().split()[:2]
+            if q != "max":
+                n = min(n, max(1, int(float(q) / float(p))))
+        except Exception:
+            pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0 and p > 0:
+            n = min(n, max(1, q // p))
+    except Exception:
+        pass
+    return max(1, n)
 
 
 def measured_peaks():
@@ -76,68 +117,86 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons}
 
 
-def make_clip():
+def make_clip(noise=3, frames=CLIP_FRAMES):
     import h264lib
-    return h264lib.synth_clip(W, H, CLIP_FRAMES)
+    return h264lib.synth_clip(W, H, frames, noise=noise)
 
 
-# ---------------------------------------------------------------------------------------------------------------
-def reference_arm(args, rank, world):
-    """The reference's own CPU encoder (oracle/_ref, unmodified, public API) on the box's host cores: one
-    single-threaded encoder instance per host thread, each coding its own 1080p stream — the same batched
-    independent-stream workload as the GPU arm.  A step = `frames_per_step` pictures per stream."""
-    if rank != 0:
-        return
+def ref_shim():
     import h264lib
-    if not h264lib.have_ref():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built on this machine"}))
-        return
     R = C.CDLL(h264lib.REFSHIM_SO)
     R.ref_enc_open.restype = C.c_void_p
     R.ref_enc_open.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
     R.ref_enc_frames.restype = C.c_long
     R.ref_enc_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)]
     R.ref_enc_close.argtypes = [C.c_void_p]
-    clip = make_clip()
-    fsz = W * H * 3 // 2
-    cores = min(os.cpu_count() or 1, args.ref_threads or (os.cpu_count() or 1))
-    fps_guess = 25.0
-    frames_per_step = 1
-    order = clip_order((args.steps + args.warmup) * frames_per_step)
+    return R
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def ref_threads_fps(R, clip, seq, cores, steps, warmup):
+    """`cores` single-threaded reference encoders, one stream each (same phases as the GPU arm), `steps` timed pictures"""
     encs = [R.ref_enc_open(W, H, QP, 2, 1, FPS) for _ in range(cores)]
     ts = [C.c_longlong(0) for _ in range(cores)]
+    nbytes = [0] * cores
 
-    def run_steps(lo, hi):
+    def run_steps(lo, hi, count):
         def worker(i):
             for st in range(lo, hi):
-                f = order[(st + 3 * i) % len(order)]
-                R.ref_enc_frames(encs[i], clip[f * fsz:].ctypes.data, W, H, 1, C.byref(ts[i]))
+                f = stream_frame(seq, i, st)
+                n = R.ref_enc_frames(encs[i], clip[f * FSZ:].ctypes.data, W, H, 1, C.byref(ts[i]))
+                if count:
+                    nbytes[i] += max(0, int(n))
         th = [threading.Thread(target=worker, args=(i,)) for i in range(cores)]
         [t.start() for t in th]
         [t.join() for t in th]
 
-    run_steps(0, args.warmup)
+    run_steps(0, warmup, False)
     t0 = time.perf_counter()
-    run_steps(args.warmup, args.warmup + args.steps)
+    run_steps(warmup, warmup + steps, True)
     dt = time.perf_counter() - t0
     for e in encs:
         R.ref_enc_close(e)
-    fps = cores * args.steps * frames_per_step / dt
+    return cores * steps / dt, dt, sum(nbytes) / max(1, cores * steps)
+
+
+def reference_arm(args, rank, world):
+    """The reference's own CPU encoder (oracle/_ref, unmodified, public API) on the box's host cores: one
+    single-threaded encoder instance per usable host core, each coding its own 1080p stream — the same batched
+    independent-stream workload as the GPU arm.  A step = 1 picture per stream."""
+    if rank != 0:
+        return
+    import h264lib
+    if not h264lib.have_ref():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built on this machine"}))
+        return
+    R = ref_shim()
+    cores = min(host_cores(), args.ref_threads or host_cores())
+    clip = make_clip()
+    seq = ping_pong(CLIP_FRAMES)
+    fps, dt, kb = ref_threads_fps(R, clip, seq, cores, args.steps, args.warmup)
+    hard = None
+    if not args.no_hard:
+        hclip = make_clip(HARD_NOISE, HARD_FRAMES)
+        hfps, _, hkb = ref_threads_fps(R, hclip, ping_pong(HARD_FRAMES), cores, max(2, args.steps // 4), 2)
+        hard = {"generator": "same synthetic generator, +-%d per-frame noise" % HARD_NOISE, "value": hfps, "unit": "frames/s",
+                "bitstream_kbytes_per_frame": hkb / 1e3}
+    asm = "C-only build (USE_ASM=No: nasm / yasm are absent from this image, the reference's x86 assembly cannot be assembled)"
     print(json.dumps({
         "impl": "reference", "metric": "1080p_encode_fps", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "encode synthetic 1920x1080 I420, constant QP 26, camera, single slice, complexity HIGH, CAVLC "
-                               "(BASELINE.json configs[2]); %d independent streams, 1 picture per stream per step" % cores,
-                   "streams": cores},
+        "config": {"workload": WORKLOAD + "; %d independent streams, 1 picture per stream per step" % cores,
+                   "streams": cores, "workload_hard": hard},
+        "bitstream_kbytes_per_frame": kb / 1e3,
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference",
-                         "sample": "%d single-thread reference encoders (C-only build, no nasm on this image) x %d pictures each"
-                                   % (cores, args.steps)},
+                         "cores_source": "sched_getaffinity capped by the cgroup quota (os.cpu_count() = %d)" % (os.cpu_count() or 0),
+                         "sample": "%d single-thread reference encoders, %s, x %d pictures each" % (cores, asm, args.steps)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def cpu_baseline_sample(seconds_budget=15.0):
+def cpu_baseline_sample():
     """reference encoder, 1 thread, bounded sample of the same workload (rank 0, N=1)."""
     import h264lib
     if not h264lib.have_ref():
@@ -145,14 +204,28 @@ def cpu_baseline_sample(seconds_budget=15.0):
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     from make_encoder_golden import ref_encode
     clip = make_clip()
-    fsz = W * H * 3 // 2
+    seq = ping_pong(CLIP_FRAMES)
     n = 24
-    order = clip_order(n)
-    yuv = np.concatenate([clip[f * fsz:(f + 1) * fsz] for f in order])
+    yuv = np.concatenate([clip[stream_frame(seq, 0, i) * FSZ:(stream_frame(seq, 0, i) + 1) * FSZ] for i in range(n)])
     _, _, secs = ref_encode(yuv, W, H, n, QP, FPS, complexity=2, threads=1)
     return {"value": n / secs, "unit": "frames/s", "cores": 1, "kind": "reference",
             "sample": "%d pictures of the bench clip through the reference's ISVCEncoder::EncodeFrame, 1 thread, "
-                      "C-only build (USE_ASM=No: nasm absent)" % n}
+                      "C-only build (USE_ASM=No: nasm absent, the SSE2/AVX2 assembly cannot be built here)" % n}
+
+
+def reference_hashes(clip, seq, n_pictures, classes):
+    """SHA-1 of the unmodified reference's bitstream for every phase class (first picture of the stream -> hash)"""
+    import h264lib
+    if not h264lib.have_ref():
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_encoder_golden import ref_encode
+    out = {}
+    for c in classes:
+        yuv = np.concatenate([clip[seq[(i + c) % len(seq)] * FSZ:(seq[(i + c) % len(seq)] + 1) * FSZ] for i in range(n_pictures)])
+        bs, _, _ = ref_encode(yuv, W, H, n_pictures, QP, FPS, complexity=2, threads=1)
+        out[c] = hashlib.sha1(bytes(bs)).hexdigest()
+    return out
 
 
 def ncu_traffic(kernel):
@@ -165,8 +238,8 @@ def ncu_traffic(kernel):
 
 def mc_sad_roofline(L, local, peak):
     """BASELINE metric 2: the MC+SAD unit (b2h264_k_mc_sad, layer 1) against the HBM roofline.  64 stacked 1080p
-    planes (cur + padded ref = 302 MB, larger than L2), one candidate per macroblock; algorithmic bytes per MB =
-    256 cur + 256 ref + 4 vector + 4 cost."""
+    planes (cur + padded ref = 302 MB, larger than L2); algorithmic bytes per MB = 256 cur + 256 ref + 4 K vector +
+    4 K cost.  Three points: K = 1 integer vectors, K = 1 quarter-sample vectors, K = 9 mixed."""
     import torch
     from openh264_b200.binding import check
     S, stride, rows_per = 64, 2048, 1152                      # 1088 + 2 x 32 rows of padding per picture
@@ -178,13 +251,17 @@ def mc_sad_roofline(L, local, peak):
     n = mbw * mbh
     out = {}
     st = torch.cuda.current_stream().cuda_stream
-    for name, frac in (("integer", False), ("quarter", True)):
-        mv = torch.randint(-8, 9, (n, 1, 2), dtype=torch.int16, device="cuda", generator=g) * 4
-        if frac:
-            mv += torch.randint(0, 4, (n, 1, 2), dtype=torch.int16, device="cuda", generator=g)
-        cost = torch.empty((n, 1), dtype=torch.int32, device="cuda")
+    for name, k, frac in (("integer", 1, 0), ("quarter", 1, 1), ("mixed9", 9, 2)):
+        mv = torch.randint(-8, 9, (n, k, 2), dtype=torch.int16, device="cuda", generator=g) * 4
+        if frac == 1:
+            mv += torch.randint(0, 4, (n, k, 2), dtype=torch.int16, device="cuda", generator=g)
+        elif frac == 2:                                        # candidate 0 integer, the others quarter-sample neighbours of it
+            mv = mv[:, :1, :].repeat(1, k, 1)
+            mv[:, 1:, :] += torch.randint(-3, 4, (n, k - 1, 2), dtype=torch.int16, device="cuda", generator=g)
+        mv = mv.contiguous()
+        cost = torch.empty((n, k), dtype=torch.int32, device="cuda")
         run = lambda: check(L.b2h264_k_mc_sad(cur.data_ptr() + o0, stride, ref.data_ptr() + o0, stride, mbw, mbh,
-                                              mv.data_ptr(), 1, cost.data_ptr(), st))
+                                              mv.data_ptr(), k, cost.data_ptr(), st))
         for _ in range(3):
             run()
         torch.cuda.synchronize()
@@ -196,14 +273,35 @@ def mc_sad_roofline(L, local, peak):
         e1.record()
         torch.cuda.synchronize()
         sec = e0.elapsed_time(e1) / 1e3 / iters
-        gbs = n * 520 / sec / 1e9
-        out[name] = {"achieved": gbs, "frac": gbs / peak, "us_per_launch": sec * 1e6, "mb_per_launch": n}
+        alg = 512 + 8 * k
+        gbs = n * alg / sec / 1e9
+        out[name] = {"achieved": gbs, "frac": gbs / peak, "us_per_launch": sec * 1e6, "mb_per_launch": n, "candidates_per_mb": k,
+                     "alg_bytes_per_mb": alg}
     t = ncu_traffic("k_mc_sad_tma")
-    return {"kernel": "k_mc_sad_tma (b2h264_k_mc_sad: 8x4-MB tiles staged by TMA bulk tensor copies)", "bound": "hbm", "unit": "GB/s",
+    return {"kernel": "k_mc_sad_tma (b2h264_k_mc_sad: 8x4-MB tiles staged by TMA bulk tensor copies, separable half-sample planes per tile)",
+            "bound": "hbm", "unit": "GB/s",
             "traffic": t["dram_bytes"] if t and t.get("mb_per_launch") == n else None,
             "peak": peak, "alg_bytes_per_mb": 520, "candidates_per_mb": 1, "achieved": out["integer"]["achieved"],
-            "frac": out["integer"]["frac"], "integer_mv": out["integer"], "quarter_pel_mv": out["quarter"],
+            "frac": out["integer"]["frac"], "integer_mv": out["integer"], "quarter_pel_mv": out["quarter"], "mixed_9_candidates": out["mixed9"],
             "note": "64 stacked padded 1080p planes per launch (302 MB of pixels, larger than L2)"}
+
+
+def api_run(args, local, clip_path, out_prefix, S):
+    """S threads x S ISVCEncoder objects through libopenh264_b200_wels.so (the reference's API), timed inside the driver"""
+    drv = os.path.join(ROOT, "oracle", "_ref", "wels_mt_driver")
+    lib = os.path.join(ROOT, "openh264_b200", "libopenh264_b200_wels.so")
+    if not (os.path.exists(drv) and os.path.exists(lib)):
+        return None
+    env = dict(os.environ)
+    env.setdefault("B2H264_BROKER_SLOTS", str(max(1, S // 2)))       # two shared encoders: one's copies / entropy overlap the other's kernels
+    env["B2H264_DEVICE"] = str(local)
+    r = subprocess.run([drv, lib, clip_path, str(W), str(H), str(CLIP_FRAMES), str(QP), str(S), str(args.steps), str(args.warmup),
+                        str(PHASE_STEP), out_prefix], capture_output=True, text=True, env=env, timeout=1800)
+    if r.returncode != 0:
+        return {"error": (r.stderr + r.stdout)[-400:]}
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    res["broker_slots"] = int(env["B2H264_BROKER_SLOTS"])
+    return res
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -216,6 +314,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--ref-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hard", action="store_true", help="skip the second (hard content) workload point")
+    ap.add_argument("--no-api", action="store_true", help="skip the run through ISVCEncoder::EncodeFrame")
+    ap.add_argument("--no-parity", action="store_true", help="skip the reference comparison of the produced bitstreams")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -234,42 +335,42 @@ def main():
     S = args.streams
     L = lib(local)
     clip_h = make_clip()
-    fsz = W * H * 3 // 2
+    seq = ping_pong(CLIP_FRAMES)
     clip_d = torch.from_numpy(clip_h).cuda()
     clip_pinned = torch.from_numpy(clip_h).pin_memory()
     stream = torch.cuda.Stream()
-    total = args.steps + args.warmup + 1
-    order = clip_order(total + S)
+    n_pictures = args.warmup + args.steps
+    ent_threads = min(S, max(8, host_cores() // max(1, min(world, torch.cuda.device_count()))))
 
-    def run(enc, on_device, n_steps, first):
-        """pipelined submit/collect; returns bytes of bitstream produced"""
-        nbytes = 0
+    def srcs(step, on_dev, clip_dev=None, clip_pin=None, sq=None):
+        cd, cp, q = clip_dev if clip_dev is not None else clip_d, clip_pin if clip_pin is not None else clip_pinned, sq or seq
+        if on_dev:
+            base = cd.data_ptr()
+            return [base + stream_frame(q, s, step) * FSZ for s in range(S)]
+        a = cp.numpy()
+        return [a[stream_frame(q, s, step) * FSZ:(stream_frame(q, s, step) + 1) * FSZ] for s in range(S)]
 
-        def srcs(step):
-            base = clip_d.data_ptr() if on_device else None
-            out = []
-            for s in range(S):
-                f = order[step + s % 5]
-                out.append(base + f * fsz if on_device else clip_pinned.numpy()[f * fsz:(f + 1) * fsz])
-            return out
-        enc.submit(srcs(first), on_device=on_device)
-        for i in range(1, n_steps + 1):
-            if i < n_steps:
-                enc.submit(srcs(first + i), on_device=on_device)
-            bs, _ = enc.collect()
-            nbytes += sum(len(b) for b in bs)
-        return nbytes
+    def timed_run(enc, on_dev, warmup, steps, keep, **kw):
+        """pipelined submit/collect (two batches in flight); returns timing + per-stream access units (if keep)"""
+        aus = [[] for _ in range(S)] if keep else None
+        kern, d2h = [], []
+        nb = 0
 
-    results = {}
-    launches0 = L.b2h264_launch_count()
-    kern_us = []
-    d2h_bytes = []
-    for mode in ("resident", "e2e"):
-        enc = BatchEncoder(W, H, qp=QP, fps=FPS, n_streams=S, device=local,
-                           entropy_threads=min(S, max(8, (os.cpu_count() or 8) // world)))
-        enc.set_stream(stream.cuda_stream)
-        on_dev = mode == "resident"
-        run(enc, on_dev, args.warmup, 0)                           # warm-up (includes the IDR pictures)
+        def loop(first, count, timed):
+            nonlocal nb
+            enc.submit(srcs(first, on_dev, **kw), on_device=on_dev)
+            for i in range(1, count + 1):
+                if i < count:
+                    enc.submit(srcs(first + i, on_dev, **kw), on_device=on_dev)
+                bs, _ = enc.collect()
+                if keep:
+                    for s in range(S):
+                        aus[s].append(bs[s])
+                if timed:
+                    nb += sum(len(b) for b in bs)
+                    kern.append(enc.timing_us())
+                    d2h.append(enc.d2h_bytes())
+        loop(0, warmup, False)                                     # warm-up (includes the IDR pictures)
         torch.cuda.synchronize()
         shard.barrier()
         sampler = ClockSampler(local)
@@ -279,26 +380,7 @@ def main():
         with torch.cuda.stream(stream):
             e0.record(stream)
         t0 = time.perf_counter()
-        # timed region: exactly args.steps batch-frames
-        nb = 0
-
-        def srcs(step):
-            out = []
-            for s in range(S):
-                f = order[step + s % 5]
-                out.append(clip_d.data_ptr() + f * fsz if on_dev else clip_pinned.numpy()[f * fsz:(f + 1) * fsz])
-            return out
-        first = args.warmup
-        enc.submit(srcs(first), on_device=on_dev)
-        for i in range(1, args.steps + 1):
-            if i < args.steps:
-                enc.submit(srcs(first + i), on_device=on_dev)
-            bs, _ = enc.collect()
-            nb += sum(len(b) for b in bs)
-            if mode == "resident":
-                kern_us.append(enc.timing_us())
-            else:
-                d2h_bytes.append(enc.d2h_bytes())
+        loop(warmup, steps, True)                                  # timed region: exactly `steps` batch-frames
         with torch.cuda.stream(stream):
             e1.record(stream)
         torch.cuda.synchronize()
@@ -306,33 +388,117 @@ def main():
         dev = e0.elapsed_time(e1) / 1e3
         sampler.stop_flag = True
         sampler.join(timeout=2)
-        dt, pics = shard.job_totals(max(wall, dev), S * args.steps, device="cuda")   # MAX over ranks / SUM over ranks
-        results[mode] = {"dt": dt, "pictures": pics, "wall": wall, "dev": dev, "bytes": nb, "clocks": sampler.summary()}
+        dt, pics = shard.job_totals(max(wall, dev), S * steps, device="cuda")   # MAX over ranks / SUM over ranks
+        return {"dt": dt, "pictures": pics, "wall": wall, "dev": dev, "bytes": nb, "clocks": sampler.summary(), "kern": kern, "d2h": d2h,
+                "aus": aus}
+
+    results = {}
+    launches0 = L.b2h264_launch_count()
+    keep = not args.no_parity
+    for mode in ("resident", "e2e_layer2"):
+        enc = BatchEncoder(W, H, qp=QP, fps=FPS, n_streams=S, device=local, entropy_threads=ent_threads)
+        enc.set_stream(stream.cuda_stream)
+        results[mode] = timed_run(enc, mode == "resident", args.warmup, args.steps, keep)
         enc.close()
     launches = L.b2h264_launch_count() - launches0
 
+    # ---- the same workload through the reference's API (ISVCEncoder objects behind the batching broker) ----
+    api = None
+    tmpdir = tempfile.mkdtemp(prefix="b2h264_bench_")
+    if not args.no_api:
+        clip_path = os.path.join(tmpdir, "clip.yuv")
+        clip_h.tofile(clip_path)
+        shard.barrier()
+        api = api_run(args, local, clip_path, os.path.join(tmpdir, "api") if keep else "-", S)
+        ok = bool(api) and "fps" in api
+        dt, pics = shard.job_totals(api["seconds"] if ok else 1e9, S * args.steps, device="cuda")   # every rank takes part
+        if ok and dt < 1e8:
+            api["job_fps"] = pics / dt
+
+    # ---- parity at bench scale: every stream of every mode against the unmodified reference (outside the timed regions) ----
+    parity = {"parity_checked": 0, "note": "skipped (--no-parity)"}
+    if keep and rank == 0:
+        classes = sorted({(PHASE_STEP * s) % len(seq) for s in range(S)})
+        want = reference_hashes(clip_h, seq, n_pictures, classes)
+        if want is None:
+            parity = {"parity_checked": 0, "note": "oracle/_ref not present on this machine"}
+        else:
+            checked, bad = 0, []
+            for mode in ("resident", "e2e_layer2"):
+                for s in range(S):
+                    got = hashlib.sha1(b"".join(results[mode]["aus"][s])).hexdigest()
+                    checked += 1
+                    if got != want[(PHASE_STEP * s) % len(seq)]:
+                        bad.append((mode, s))
+            if api and "fps" in api:
+                for s in range(S):
+                    got = hashlib.sha1(open(os.path.join(tmpdir, "api.%d.264" % s), "rb").read()).hexdigest()
+                    checked += 1
+                    if got != want[(PHASE_STEP * s) % len(seq)]:
+                        bad.append(("api", s))
+            if bad:
+                print(json.dumps({"error": "bitstream differs from the reference", "streams": bad[:16], "n_bad": len(bad)}))
+                sys.exit(1)
+            parity = {"parity_checked": checked, "distinct_sequences": len(classes), "pictures_per_stream": n_pictures,
+                      "note": "SHA-1 of all access units of every stream (resident, e2e_layer2%s) == the unmodified reference encoder "
+                              "on the same picture order" % (", EncodeFrame API" if api and "fps" in api else "")}
+    try:
+        for f in os.listdir(tmpdir):
+            os.unlink(os.path.join(tmpdir, f))
+        os.rmdir(tmpdir)
+    except Exception:
+        pass
+
+    # ---- second workload point: hard content ----
+    hard = None
+    if not args.no_hard:
+        hclip = make_clip(HARD_NOISE, HARD_FRAMES)
+        hd = torch.from_numpy(hclip).cuda()
+        enc = BatchEncoder(W, H, qp=QP, fps=FPS, n_streams=S, device=local, entropy_threads=ent_threads)
+        enc.set_stream(stream.cuda_stream)
+        hsteps = max(4, args.steps // 2)
+        r = timed_run(enc, True, 3, hsteps, False, clip_dev=hd, sq=ping_pong(HARD_FRAMES))
+        enc.close()
+        coded = (float(np.mean(r["d2h"])) - S * (MBS_PER_FRAME + 1) * 4) / 896.0
+        hard = {"generator": "same synthetic generator, +-%d per-frame noise" % HARD_NOISE, "value": r["pictures"] / r["dt"], "unit": "frames/s",
+                "steps": hsteps, "skip_ratio": 1.0 - coded / (S * MBS_PER_FRAME), "bitstream_kbytes_per_frame": r["bytes"] / (S * hsteps) / 1e3,
+                "encode_kernel_ms": float(np.mean([k[0] for k in r["kern"]])) * 1e-3, "host_entropy_ms": float(np.mean([k[2] for k in r["kern"]])) * 1e-3}
+
     if rank == 0:
-        value = results["resident"]["pictures"] / results["resident"]["dt"]
-        e2e = results["e2e"]["pictures"] / results["e2e"]["dt"]
+        res, l2 = results["resident"], results["e2e_layer2"]
+        value = res["pictures"] / res["dt"]
+        e2e_l2 = l2["pictures"] / l2["dt"]
         peak, peak_kind = measured_peaks()
-        k_enc = float(np.mean([k[0] for k in kern_us])) * 1e-6        # seconds per launch of pad + macroblock wavefront kernel
-        k_dbk = float(np.mean([k[1] for k in kern_us])) * 1e-6
-        ent = float(np.mean([k[2] for k in kern_us])) * 1e-6
+        k_enc = float(np.mean([k[0] for k in res["kern"]])) * 1e-6        # seconds per launch of pad + macroblock wavefront kernel
+        k_dbk = float(np.mean([k[1] for k in res["kern"]])) * 1e-6
+        ent = float(np.mean([k[2] for k in res["kern"]])) * 1e-6
         alg = S * MBS_PER_FRAME * ALG_BYTES_PER_MB
         achieved = alg / k_enc / 1e9
+        coded = (float(np.mean(l2["d2h"])) - S * (MBS_PER_FRAME + 1) * 4) / 896.0
+        d2h = int(world * np.mean(l2["d2h"]))
+        if api and "job_fps" in api:
+            e2e = {"value": api["job_fps"], "unit": "frames/s", "h2d_bytes_per_step": world * S * FSZ, "d2h_bytes_per_step": d2h,
+                   "path": "ISVCEncoder::EncodeFrame (the reference's API): %d application threads, one encoder object each, host "
+                           "pictures; objects share batched GPU encoders of %d streams (openh264_b200/wels/broker.h)" % (S, api["broker_slots"]),
+                   "d2h_note": "index table + records of the coded macroblocks only, written by the GPU into mapped pinned memory (figure of the "
+                               "layer-2 run on the same pictures)"}
+        else:
+            e2e = {"value": e2e_l2, "unit": "frames/s", "h2d_bytes_per_step": world * S * FSZ, "d2h_bytes_per_step": d2h,
+                   "path": "layer 2 (b2h264_enc_submit / collect) with pinned host pictures; the EncodeFrame run was not possible: %s"
+                           % (api or "driver or layer-3 library not built")}
         out = {
             "metric": "1080p_encode_fps", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": results["resident"]["dt"] / args.steps * 1e3, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": res["dt"] / args.steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "encode synthetic 1920x1080 I420, constant QP 26, camera, single slice, complexity HIGH, "
-                                   "CAVLC (BASELINE.json configs[2]); %d independent streams per GPU, 1 picture per stream "
-                                   "per step; bitstream bit-identical to the reference" % S,
+            "config": {"workload": WORKLOAD + "; %d independent streams per GPU (%d distinct picture sequences), 1 picture per stream per step"
+                                   % (S, len({(PHASE_STEP * s) % len(seq) for s in range(S)})),
                        "streams_per_gpu": S, "parallelism": "replica x%d (independent streams, no collective)" % world,
-                       "l2": "inputs larger than L2 (%.0f MB of pictures in flight per step)" % (S * fsz / 1e6)},
-            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": world * S * fsz, "d2h_bytes_per_step": int(world * np.mean(d2h_bytes)),
-                    "d2h_note": "index table + records of the coded macroblocks only, written by the GPU into mapped pinned memory"},
+                       "l2": "inputs larger than L2 (%.0f MB of source pictures per step, %.0f MB of reference pictures)" % (S * FSZ / 1e6, S * 3.43),
+                       "skip_ratio": 1.0 - coded / (S * MBS_PER_FRAME), "workload_hard": hard},
+            "e2e": e2e,
+            "e2e_layer2": {"value": e2e_l2, "unit": "frames/s", "path": "b2h264_enc_submit / collect, pinned host pictures, two batches in flight"},
             "gpu_launches": int(launches),
-            "clocks": results["resident"]["clocks"],
+            "clocks": res["clocks"],
             "roofline": {"bound": "hbm", "kernel": "k_encode_mbs (macroblock wavefront, all streams)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (ncu_traffic("k_encode_mbs") or {}).get("dram_bytes") if S == (ncu_traffic("k_encode_mbs") or {}).get("streams") else None,
@@ -340,10 +506,11 @@ def main():
                          "note": "wavefront kernel is dependency/latency-bound by construction (SURVEY.md §8d); "
                                  "alg bytes = %d B/MB x %d MB/launch" % (ALG_BYTES_PER_MB, S * MBS_PER_FRAME)},
             "breakdown_ms_per_step": {"encode_kernel": k_enc * 1e3, "deblock_expand": k_dbk * 1e3, "host_entropy": ent * 1e3,
-                                      "wall_resident": results["resident"]["wall"] / args.steps * 1e3,
-                                      "wall_e2e": results["e2e"]["wall"] / args.steps * 1e3},
-            "bitstream_kbytes_per_frame": results["resident"]["bytes"] / (S * args.steps) / 1e3,
+                                      "wall_resident": res["wall"] / args.steps * 1e3, "wall_e2e_layer2": l2["wall"] / args.steps * 1e3},
+            "bitstream_kbytes_per_frame": res["bytes"] / (S * args.steps) / 1e3,
+            "host_cores": host_cores(),
         }
+        out.update({"parity_checked": parity["parity_checked"], "parity": parity})
         if world == 1:
             out["roofline_mc_sad"] = mc_sad_roofline(L, local, peak)
         if world == 1 and not args.no_cpu_baseline:

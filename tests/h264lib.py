@@ -160,11 +160,12 @@ def synth_frame(w, h, t=0, seed=264):
     return np.clip(v, 16, 235).astype(np.uint8)
 
 
-def synth_clip(w, h, n, seed=264):
+def synth_clip(w, h, n, seed=264, noise=3):
     """Deterministic INTEGER-ONLY I420 clip (bit-identical on every machine): multi-octave value noise from a
     32-bit LCG, bilinearly upsampled with integer weights, global pan (+3,+1)/frame, 6 moving textured
     rectangles, +-3 per-frame noise; chroma = low-amplitude functions of the half-resolution luma.
-    Returns a uint8 array of n*w*h*3/2 bytes."""
+    `noise` = amplitude of the per-frame noise (3 = the default clip; 12 = the bench's "hard" workload: far fewer
+    skipped macroblocks, several times the bits).  Returns a uint8 array of n*w*h*3/2 bytes."""
     def lcg_field(gh, gw, s):
         idx = (np.arange(gh * gw, dtype=np.uint64).reshape(gh, gw) + np.uint64(s) * np.uint64(7919)) & np.uint64(0xffffffff)
         x = (idx * np.uint64(1664525) + np.uint64(1013904223)) & np.uint64(0xffffffff)
@@ -195,7 +196,7 @@ def synth_clip(w, h, n, seed=264):
             rx = (k * 211 + (2 * (k % 3) + 1) * t * 2) % max(1, w - rw)
             ry = (k * 97 + ((k % 2) + 1) * t) % max(1, h - rh)
             y[ry:ry + rh, rx:rx + rw] = ((xx[ry:ry + rh, rx:rx + rw] * (k + 3) + yy[ry:ry + rh, rx:rx + rw] * (k + 1)) % 64) + 60 + 12 * k
-        nz = lcg_field(h, w, seed + 1000 + t) % 7 - 3
+        nz = lcg_field(h, w, seed + 1000 + t) % (2 * noise + 1) - noise
         y = np.clip(y + nz, 16, 235).astype(np.uint8)
         sub = y[::2, ::2].astype(np.int64)
         u = np.clip(128 + (sub - 128) // 4, 16, 240).astype(np.uint8)

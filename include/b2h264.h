@@ -111,6 +111,15 @@ int b2h264_k_deblock_chroma (uint8_t* cb, uint8_t* cr, const b2h264_edge_job* jo
 /* ---- ExpandReferencingPicture (expand_pic.cpp:388): pad = 32 (luma) or 16 (chroma) ----------- */
 int b2h264_k_expand_plane (uint8_t* pic, int stride, int w, int h, int pad, void* stream);
 
+/* VPP bilinear down-sampler (codec/processing/src/downsample/downsamplefuncs.cpp): mode 0 = DyadicBilinearDownsampler_c :47,
+ * 1 = ...QuarterDownsampler_c :73, 2 = ...OneThirdDownsampler_c :99, 3 = GeneralBilinearFastDownsampler_c :118 (luma),
+ * 4 = GeneralBilinearAccurateDownsampler_c :189 (chroma).  n_planes planes of identical geometry, plane p at
+ * dst + p * dst_plane_bytes / src + p * src_plane_bytes (the same plane of n streams in one launch). */
+int b2h264_k_downsample (int mode, uint8_t* dst, int dst_stride, int dst_w, int dst_h, const uint8_t* src, int src_stride,
+                         int src_w, int src_h, int n_planes, size_t dst_plane_bytes, size_t src_plane_bytes, void* stream);
+/* the function CDownsampling::Process (downsample.cpp:143-215) picks for a plane: 0..2 dyadic forms, else 3 (luma) / 4 (chroma) */
+int b2h264_downsample_mode (int src_w, int src_h, int dst_w, int dst_h, int is_chroma);
+
 /* ---- WelsMotionEstimateSearch (svc_motion_estimate.cpp:170) --------------------------------- */
 typedef struct {
   int32_t blk;

@@ -68,6 +68,8 @@ API = {
     "b2h264_k_deblock_luma": [vp, vp, C.c_int, vp],
     "b2h264_k_deblock_chroma": [vp, vp, vp, C.c_int, vp],
     "b2h264_k_expand_plane": [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
+    "b2h264_k_downsample": [C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, vp],
+    "b2h264_downsample_mode": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
     "b2h264_k_me_search": [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp],
     "b2h264_k_mc_sad": [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp],
     "b2h264_enc_create": [vp, C.POINTER(vp)],

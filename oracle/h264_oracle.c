@@ -620,3 +620,61 @@ void orc_me_search (const uint8_t* cur, int cs, const uint8_t* ref, int rs, cons
   if (j->calc_satd)                                  /* CalculateSatdCost (:286-291) */
     out->satd_cost = (uint32_t) (orc_satd (j->blk, enc, cs, best_ref, rs) + mvd[out->mv_x - px] + mvd[out->mv_y - py]);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * VPP bilinear down-sampler: codec/processing/src/downsample/downsamplefuncs.cpp
+ *   mode 0 DyadicBilinearDownsampler_c :47      dst = src / 2
+ *   mode 1 DyadicBilinearQuarterDownsampler_c :73   dst = src / 4 (top-left 2x2 of every 4x4)
+ *   mode 2 DyadicBilinearOneThirdDownsampler_c :99  dst = src / 3 (top-left 2x2 of every 3x3)
+ *   mode 3 GeneralBilinearFastDownsampler_c :118    (luma, 16.15 fixed point, 32-bit products)
+ *   mode 4 GeneralBilinearAccurateDownsampler_c :189 (chroma, 15.15 fixed point, 64-bit products)
+ * dst_w / dst_h are the destination dimensions in every mode.
+ * ------------------------------------------------------------------------------------------ */
+static int orc_round_ratio (int src, int dst, int scale) {       /* WELS_ROUND ((float)src / (float)dst * scale), macros.h:120 */
+  return (int) (0.5 + ((float) src / (float) dst * scale));
+}
+void orc_downsample (int mode, uint8_t* dst, int ds, int dst_w, int dst_h, const uint8_t* src, int ss, int src_w, int src_h) {
+  if (mode <= 2) {
+    const int step = mode == 0 ? 2 : mode == 1 ? 4 : 3;
+    for (int j = 0; j < dst_h; j++)
+      for (int i = 0; i < dst_w; i++) {
+        const uint8_t* p = src + (size_t) j * step * ss + i * step;
+        const int r1 = (p[0] + p[1] + 1) >> 1, r2 = (p[ss] + p[ss + 1] + 1) >> 1;
+        dst[(size_t) j * ds + i] = (uint8_t) ((r1 + r2 + 1) >> 1);
+      }
+    return;
+  }
+  const int bw = mode == 3 ? 16 : 15, bh = 15;
+  const int sx = orc_round_ratio (src_w, dst_w, 1 << bw), sy = orc_round_ratio (src_h, dst_h, 1 << bh);
+  for (int i = 0; i < dst_h; i++) {
+    const int yinv = (1 << (bh - 1)) + i * sy;
+    const int yy = yinv >> bh, fv = yinv & ((1 << bh) - 1);
+    const uint8_t* row = src + (size_t) yy * ss;
+    for (int j = 0; j < dst_w; j++) {
+      const int xinv = (1 << (bw - 1)) + j * sx;
+      const int xx = xinv >> bw, fu = xinv & ((1 << bw) - 1);
+      uint8_t v;
+      if (i == dst_h - 1 || j == dst_w - 1) v = row[xx];          /* last row / last column: nearest sample */
+      else {
+        const uint32_t a = row[xx], b = row[xx + 1], c = row[xx + ss], d = row[xx + ss + 1];
+        if (mode == 3) {
+          const uint32_t W = 1u << bw, Hh = 1u << bh;
+          uint32_t x = (((uint32_t) (W - 1 - fu)) * (Hh - 1 - fv) >> bw) * a;
+          x += (((uint32_t) fu) * (Hh - 1 - fv) >> bw) * b;
+          x += (((uint32_t) (W - 1 - fu)) * (uint32_t) fv >> bw) * c;
+          x += (((uint32_t) fu) * (uint32_t) fv >> bw) * d;
+          x >>= (bh - 1);
+          x += 1;
+          x >>= 1;
+          v = (uint8_t) (x > 255 ? 255 : x);
+        } else {
+          const int64_t S = 1 << 15;
+          int64_t x = ((S - 1 - fu) * (S - 1 - fv) * a + (int64_t) fu * (S - 1 - fv) * b + (S - 1 - fu) * fv * c + (int64_t) fu * fv * d +
+                       ((int64_t) 1 << 29)) >> 30;
+          v = (uint8_t) (x < 0 ? 0 : x > 255 ? 255 : x);
+        }
+      }
+      dst[(size_t) i * ds + j] = v;
+    }
+  }
+}

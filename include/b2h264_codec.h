@@ -67,6 +67,14 @@ int  b2h264_enc_force_idr (b2h264_enc* e, int stream);
  * history cleared); only while nothing is in flight.  Used when an ISVCEncoder slot of a shared encoder is re-used. */
 int  b2h264_enc_reset_stream (b2h264_enc* e, int stream);
 
+/* Exact CAVLC bit count on the device (the reference's rate control reads it from the bitstream position per macroblock:
+ * ratectl.cpp:1239-1278, svc_set_mb_syn_cavlc.cpp:260).  set_mb_bits(on): every following picture also yields, per
+ * macroblock, the number of bits its macroblock_layer() takes (0 for P_SKIP; mb_skip_run excluded), computed by the
+ * macroblock kernel without emitting a bit.  get_mb_bits: device_bits[n_mb] = that array for the last COLLECTED picture
+ * of a stream, host_bits[n_mb] = what the host CAVLC writer actually spent (either may be NULL): they are equal. */
+int  b2h264_enc_set_mb_bits (b2h264_enc* e, int on);
+int  b2h264_enc_get_mb_bits (b2h264_enc* e, int stream, int32_t* device_bits, int32_t* host_bits);
+
 /* copies the reconstructed (deblocked) picture of stream i that is currently the reference into dst
  * (cropped I420, w*h*3/2 bytes, host memory): for parity tests */
 int  b2h264_enc_get_recon (b2h264_enc* e, int stream, uint8_t* h_dst);

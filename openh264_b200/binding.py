@@ -78,6 +78,8 @@ API = {
     "b2h264_enc_collect": [vp, C.POINTER(vp), i32p, i32p],
     "b2h264_enc_force_idr": [vp, C.c_int],
     "b2h264_enc_reset_stream": [vp, C.c_int],
+    "b2h264_enc_set_mb_bits": [vp, C.c_int],
+    "b2h264_enc_get_mb_bits": [vp, C.c_int, i32p, i32p],
     "b2h264_enc_get_recon": [vp, C.c_int, vp],
     "b2h264_enc_last_timing": [vp, C.POINTER(C.c_float)],
     "b2h264_enc_last_d2h_bytes": [vp, C.POINTER(C.c_ulonglong)],
@@ -209,6 +211,16 @@ class BatchEncoder:
     def encode(self, frames):
         self.submit(frames)
         return self.collect()
+
+    def set_mb_bits(self, on=True):
+        check(self.L.b2h264_enc_set_mb_bits(self.h, 1 if on else 0))
+
+    def mb_bits(self, stream=0):
+        """(device count, host writer's count) of CAVLC bits per macroblock of the picture collected last"""
+        n = ((self.cfg.width + 15) // 16) * ((self.cfg.height + 15) // 16)
+        d, h = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        check(self.L.b2h264_enc_get_mb_bits(self.h, stream, d.ctypes.data_as(i32p), h.ctypes.data_as(i32p)))
+        return d, h
 
     def reset_stream(self, stream):
         check(self.L.b2h264_enc_reset_stream(self.h, stream))

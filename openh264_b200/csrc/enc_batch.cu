@@ -84,6 +84,8 @@ struct b2h264_enc {
   MbOut* d_out[2] = {nullptr, nullptr};
   int32_t* d_sad = nullptr;
   int32_t* d_prog = nullptr;              // S x 2 x mb_h
+  int32_t* d_bits = nullptr;              // S x n_mb: exact CAVLC bits per macroblock (when enabled)
+  bool mb_bits_on = false;
   int* d_tickets = nullptr;
   void* d_stash = nullptr;          // parked macroblock scratches of the staged scheduler
   StreamFrame* d_sf[2] = {nullptr, nullptr};
@@ -189,6 +191,7 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
   CK(cudaMalloc(&e->d_sad, S * e->n_mb * sizeof(int32_t)));
   CK(cudaMemset(e->d_sad, 0, S * e->n_mb * sizeof(int32_t)));
   CK(cudaMalloc(&e->d_prog, S * 2 * mbh * sizeof(int32_t)));
+  CK(cudaMalloc(&e->d_bits, S * e->n_mb * sizeof(int32_t)));
   CK(cudaMalloc(&e->d_tickets, enc_sched_ints((int)S, e->n_mb) * sizeof(int)));
   CK(cudaMalloc(&e->d_stash, enc_stash_bytes((int)S, e->ctl[0].sp.mb_h)));
   e->bs.resize(S);
@@ -204,7 +207,7 @@ void b2h264_enc_destroy(b2h264_enc* e) {
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->st);
   delete e->pool;
-  cudaFree(e->d_pic_all); cudaFree(e->d_cur); cudaFree(e->d_src); cudaFree(e->d_mbi); cudaFree(e->d_sad); cudaFree(e->d_prog); cudaFree(e->d_tickets); cudaFree(e->d_stash); cudaFree(e->d_list);
+  cudaFree(e->d_pic_all); cudaFree(e->d_cur); cudaFree(e->d_src); cudaFree(e->d_mbi); cudaFree(e->d_sad); cudaFree(e->d_prog); cudaFree(e->d_bits); cudaFree(e->d_tickets); cudaFree(e->d_stash); cudaFree(e->d_list);
   cudaFreeHost(e->h_src);
   for (int i = 0; i < 2; i++) {
     cudaFree(e->d_rinfo[i]); cudaFree(e->d_out[i]); cudaFree(e->d_sf[i]); cudaFree(e->d_srcptr[i]);
@@ -273,7 +276,7 @@ int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_devic
     F.f.out = e->d_out[k] + (size_t)i * e->n_mb;
     F.f.sad_cost = e->d_sad + (size_t)s * e->n_mb;
     F.f.row_progress = e->d_prog + (size_t)s * 2 * mbh;
-    F.f.row_progress_dbk = F.f.row_progress + mbh;
+    F.f.mb_bits = e->mb_bits_on ? e->d_bits + (size_t)s * e->n_mb : nullptr;
     e->idr_next[s] = 0;
     e->have_ref_p[s] = !idr;
   }
@@ -354,6 +357,27 @@ int b2h264_enc_reset_stream(b2h264_enc* e, int stream) {
   for (int i = 0; i < 2; i++) CK(cudaMemsetAsync(e->d_rinfo[i] + (size_t)stream * e->n_mb, 0, e->n_mb * sizeof(RefMbInfo), e->st));
   CK(cudaMemsetAsync(e->d_mbi + (size_t)stream * e->n_mb, 0, e->n_mb * sizeof(MbInfo), e->st));
   CK(cudaStreamSynchronize(e->st));
+  return 0;
+}
+
+int b2h264_enc_set_mb_bits(b2h264_enc* e, int on) {
+  if (!e) return -1;
+  if (e->slot[0].busy || e->slot[1].busy) return -3;
+  e->mb_bits_on = on != 0;
+  for (auto& c : e->ctl) c.record_mb_bits = on != 0;
+  return 0;
+}
+
+int b2h264_enc_get_mb_bits(b2h264_enc* e, int stream, int32_t* device_bits, int32_t* host_bits) {
+  if (!e || stream < 0 || stream >= e->S || !e->mb_bits_on) return -1;
+  if (e->slot[0].busy || e->slot[1].busy) return -3;
+  CK(cudaSetDevice(e->cfg.device));
+  CK(cudaStreamSynchronize(e->st));
+  if (device_bits) CK(cudaMemcpy(device_bits, e->d_bits + (size_t)stream * e->n_mb, e->n_mb * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (host_bits) {
+    if ((int)e->ctl[stream].last_mb_bits.size() != e->n_mb) return -1;
+    memcpy(host_bits, e->ctl[stream].last_mb_bits.data(), e->n_mb * sizeof(int32_t));
+  }
   return 0;
 }
 

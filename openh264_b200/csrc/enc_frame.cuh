@@ -2,6 +2,7 @@
 // host emulation build (tests/emu).  One call = one macroblock = one warp.
 #pragma once
 #include "enc_mb.cuh"
+#include "enc_cavlc_bits.cuh"
 #ifdef B2H264_WITH_INTER
 #include "enc_inter.cuh"
 #endif
@@ -66,6 +67,10 @@ MBK_HD int mb_run_stage(const MbCtx& c, MbScratch& s, int stage) {
     phase_mark(s, 10);
     mb_store_recon(c, s);
     mb_publish(c, s);
+    if (c.f.mb_bits != nullptr) {          // exact entropy-coded size of this macroblock, without emitting a bit
+      const int b = mb_cavlc_bits(c, s);
+      if (lane_id() == 0) c.f.mb_bits[c.mby * c.p.mb_w + c.mbx] = b;
+    }
     phase_mark(s, 11);
   }
   return next;

@@ -61,7 +61,7 @@ void StreamCtl::write_au(bool idr, const MbOut* const* mbs, std::vector<uint8_t>
   }
   SliceState ss;
   ss.idr = idr; ss.frame_num = frame_num; ss.idr_pic_id = idr_pic_id; ss.qp = sp.qp;
-  write_slice(sp, ss, mbs, &rbsp);
+  write_slice(sp, ss, mbs, &rbsp, record_mb_bits ? &last_mb_bits : nullptr);
   append_nal(au, 3, idr ? 5 : 1, rbsp);
   frame_num = (frame_num + 1) & 0x7fff;
   frames_coded++;

@@ -76,5 +76,5 @@ typedef struct {
   int32_t* sad_cost;                      // mb_w*mb_h, PERSISTS across frames like the reference's pSadCostMb
                                           // (encoder_ext.cpp:1675): a decided-skip MB keeps its older value
   int32_t* row_progress;                  // wavefront: number of finished MBs per MB row (device only)
-  int32_t* row_progress_dbk;              // same for the deblocking pass
+  int32_t* mb_bits;                       // optional (NULL = off): exact CAVLC bits of every macroblock (enc_cavlc_bits.cuh)
 } EncFramePtrs;

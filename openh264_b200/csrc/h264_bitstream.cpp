@@ -173,7 +173,8 @@ inline int nc_of(int a, int b) {          // a/b = neighbour counts or -1 when u
 
 const uint8_t* cbp_me_table(bool intra) { return intra ? kCbpIntra : kCbpInter; }
 
-void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* const* recs, std::vector<uint8_t>* rbsp) {
+void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* const* recs, std::vector<uint8_t>* rbsp,
+                 std::vector<int32_t>* mb_bits) {
   BitWriter w(rbsp);
   // ---- slice header (svc_encode_slice.cpp:275-346) ----
   w.ue(0);                               // first_mb_in_slice
@@ -195,11 +196,13 @@ void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* cons
   const int mbw = sp.mb_w, n = sp.mb_w * sp.mb_h;
   int skip_run = 0;
   int last_qp = ss.qp;
+  if (mb_bits) mb_bits->assign(n, 0);
   for (int idx = 0; idx < n; idx++) {
     const MbOut& m = *recs[idx];
     const int mbx = idx % mbw, mby = idx / mbw;
     if (m.mb_type == MBT_PSKIP) { skip_run++; continue; }
     if (!ss.idr) { w.ue((uint32_t)skip_run); skip_run = 0; }
+    const size_t mb_start = w.bit_pos();
     const int off = ss.idr ? 0 : 5;
     const int cbp_l = m.cbp & 15, cbp_c = m.cbp >> 4;
     switch (m.mb_type) {
@@ -260,6 +263,7 @@ void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* cons
         }
       }
     }
+    if (mb_bits) (*mb_bits)[idx] = (int32_t)(w.bit_pos() - mb_start);
   }
   if (skip_run) w.ue((uint32_t)skip_run);
   w.trailing();

@@ -70,6 +70,8 @@ struct SliceState {
 const uint8_t* cbp_me_table(bool intra);
 
 // recs[i] = the record of macroblock i (P_SKIP macroblocks may all point at one shared all-zero-nnz record)
-void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* const* recs, std::vector<uint8_t>* rbsp);
+// mb_bits (optional): bits of macroblock_layer() of every macroblock (0 for P_SKIP; mb_skip_run not included)
+void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* const* recs, std::vector<uint8_t>* rbsp,
+                 std::vector<int32_t>* mb_bits = nullptr);
 
 }  // namespace b2h264

@@ -7,6 +7,9 @@
 #include <math.h>
 
 #include "b2h264_internal.h"
+#include "cavlc_tables.h"
+#include "enc_cavlc_bits.cuh"
+#include "h264_bitstream.h"
 
 namespace mbk {
 __constant__ int16_t c_quant_ff[58][8];
@@ -14,6 +17,11 @@ __constant__ int16_t c_quant_mf[52][8];
 __constant__ uint16_t c_dequant[52][8];
 __constant__ uint8_t c_lambda[52];
 __constant__ uint8_t c_chroma_qp[52];
+}  // namespace mbk
+
+namespace mbk {
+__device__ CavlcLen d_cavlc_len;
+CavlcLen h_cavlc_len;
 }  // namespace mbk
 
 static std::atomic<unsigned long long> g_launches{0};
@@ -56,6 +64,14 @@ static void build_host_tables() {
     static const uint8_t hi[22] = {29, 30, 31, 32, 32, 33, 34, 34, 35, 35, 36, 36, 37, 37, 37, 38, 38, 38, 39, 39, 39, 39};
     h_chroma_qp[qp] = (uint8_t)(qp < 30 ? qp : hi[qp - 30]);            // H.264 Table 8-15
   }
+  // code lengths of the CAVLC tables the host writer uses (cavlc_tables.h: entry = bits << 8 | codeword)
+  CavlcLen& T = h_cavlc_len;
+  for (int c = 0; c < 5; c++) for (int t = 0; t < 17; t++) for (int o = 0; o < 4; o++) T.coeff_token[c][t][o] = (uint8_t)(kCoeffToken[c][t][o] >> 8);
+  for (int t = 0; t < 16; t++) for (int z = 0; z < 16; z++) T.total_zeros[t][z] = (uint8_t)(kTotalZeros[t][z] >> 8);
+  for (int t = 0; t < 4; t++) for (int z = 0; z < 4; z++) T.total_zeros_cdc[t][z] = (uint8_t)(kTotalZerosChromaDc[t][z] >> 8);
+  for (int z = 0; z < 8; z++) for (int r = 0; r < 15; r++) T.run_before[z][r] = (uint8_t)(kRunBefore[z][r] >> 8);
+  for (int i = 0; i < 18; i++) T.nc_class[i] = kNcClass[i];
+  for (int i = 0; i < 48; i++) { T.cbp_intra[i] = b2h264::cbp_me_table(true)[i]; T.cbp_inter[i] = b2h264::cbp_me_table(false)[i]; }
 }
 
 extern "C" {
@@ -75,6 +91,7 @@ int b2h264_init(int device) {
   if ((e = cudaMemcpyToSymbol(mbk::c_dequant, h_dequant, sizeof(h_dequant))) != cudaSuccess) return (int)e;
   if ((e = cudaMemcpyToSymbol(mbk::c_lambda, h_lambda, sizeof(h_lambda))) != cudaSuccess) return (int)e;
   if ((e = cudaMemcpyToSymbol(mbk::c_chroma_qp, h_chroma_qp, sizeof(h_chroma_qp))) != cudaSuccess) return (int)e;
+  if ((e = cudaMemcpyToSymbol(mbk::d_cavlc_len, &h_cavlc_len, sizeof(h_cavlc_len))) != cudaSuccess) return (int)e;
   return (int)cudaDeviceSynchronize();
 }
 

@@ -35,7 +35,8 @@ struct HostFrameEncoder {
   std::vector<MbInfo> mbi;
   std::vector<RefMbInfo> rinfo[2];
   std::vector<MbOut> out;
-  std::vector<int32_t> sad_cost;
+  std::vector<int32_t> sad_cost, mb_bits;     // mb_bits: the macroblock code's own CAVLC bit count (enc_cavlc_bits.cuh)
+  bool mb_bits_ok = true;
   MbScratch scratch;
   int cur_rec = 0;
   bool idr = true, have_ref_p = false;
@@ -50,7 +51,8 @@ struct HostFrameEncoder {
       pic[b][2].assign((size_t)ctl.rec_stride_c() * ctl.rec_rows_c() + 64, 0);
       rinfo[b].resize(n);
     }
-    mbi.resize(n); out.resize(n); sad_cost.assign(n, 0);
+    mbi.resize(n); out.resize(n); sad_cost.assign(n, 0); mb_bits.assign(n, -1);
+    ctl.record_mb_bits = true;
     memset(&scratch, 0, sizeof(scratch));
   }
   void load_source(const uint8_t* yuv) {
@@ -70,6 +72,7 @@ struct HostFrameEncoder {
     for (int pl = 0; pl < 3; pl++) { f.cur[pl] = cur[pl].data(); f.rec[pl] = plane0(cur_rec, pl); f.ref[pl] = plane0(1 - cur_rec, pl); }
     f.mbi = mbi.data(); f.rec_info = rinfo[cur_rec].data(); f.ref_info = rinfo[1 - cur_rec].data(); f.out = out.data();
     f.sad_cost = sad_cost.data();
+    f.mb_bits = mb_bits.data();
     return f;
   }
   bool packed_writer_ok = true;
@@ -106,6 +109,8 @@ struct HostFrameEncoder {
       if (a != b) packed_writer_ok = false;
     }
     ctl.write_access_unit(idr, out.data(), bs);
+    // the bit count the macroblock code computed without writing must equal what the writer spent, macroblock by macroblock
+    if (ctl.last_mb_bits != mb_bits) mb_bits_ok = false;
     if (parse_status == 0) check_parse(*bs);
     have_ref_p = !idr;
     cur_rec = 1 - cur_rec;            // the picture just reconstructed becomes the reference
@@ -209,6 +214,7 @@ extern "C" long emu_encode(const uint8_t* yuv, int w, int h, int nframes, int qp
     g_last_out = enc.out; g_last_info = enc.mbi;
     enc.finish_frame(&bs);
     if (!enc.packed_writer_ok) return -9;          // packed hand-over form wrote different bytes
+    if (!enc.mb_bits_ok) return -8;                // exact CAVLC bit count differs from the writer
     if (enc.parse_status != 0) return -1000 - (enc.parse_status < 0 ? -enc.parse_status : 100 + enc.parse_status);   // parser round trip failed
     if (total + (long)bs.size() > cap) return -1;
     memcpy(out + total, bs.data(), bs.size());

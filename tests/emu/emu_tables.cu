@@ -1,12 +1,17 @@
 // host copies of the quantiser tables for the emulation build (same closed forms as tables.cu)
 #include <math.h>
 #include <stdint.h>
+
+#include "../../openh264_b200/csrc/cavlc_tables.h"
+#include "../../openh264_b200/csrc/enc_cavlc_bits.cuh"
+#include "../../openh264_b200/csrc/h264_bitstream.h"
 namespace mbk {
 int16_t h_quant_ff[58][8];
 int16_t h_quant_mf[52][8];
 uint16_t h_dequant[52][8];
 uint8_t h_lambda[52];
 uint8_t h_chroma_qp[52];
+CavlcLen h_cavlc_len;
 // H.264 Tables 8-16 / 8-17 (alpha, beta, tc0 for bS 1..3), indexA/indexB 0..51
 uint8_t h_alpha[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 4, 5, 6, 7, 8, 9, 10, 12, 13, 15, 17, 20, 22, 25, 28,
                        32, 36, 40, 45, 50, 56, 63, 71, 80, 90, 101, 113, 127, 144, 162, 182, 203, 226, 255, 255};
@@ -42,4 +47,11 @@ extern "C" void b2h264_build_host_tables() {
     h_lambda[qp] = (uint8_t)(l < 1.0 ? 1 : (int)floor(l + 0.5));
     h_chroma_qp[qp] = (uint8_t)(qp < 30 ? qp : hi[qp - 30]);
   }
+  CavlcLen& T = h_cavlc_len;             // as tables.cu: code lengths of the writer's own tables
+  for (int c = 0; c < 5; c++) for (int t = 0; t < 17; t++) for (int o = 0; o < 4; o++) T.coeff_token[c][t][o] = (uint8_t)(kCoeffToken[c][t][o] >> 8);
+  for (int t = 0; t < 16; t++) for (int z = 0; z < 16; z++) T.total_zeros[t][z] = (uint8_t)(kTotalZeros[t][z] >> 8);
+  for (int t = 0; t < 4; t++) for (int z = 0; z < 4; z++) T.total_zeros_cdc[t][z] = (uint8_t)(kTotalZerosChromaDc[t][z] >> 8);
+  for (int z = 0; z < 8; z++) for (int r = 0; r < 15; r++) T.run_before[z][r] = (uint8_t)(kRunBefore[z][r] >> 8);
+  for (int i = 0; i < 18; i++) T.nc_class[i] = kNcClass[i];
+  for (int i = 0; i < 48; i++) { T.cbp_intra[i] = b2h264::cbp_me_table(true)[i]; T.cbp_inter[i] = b2h264::cbp_me_table(false)[i]; }
 }

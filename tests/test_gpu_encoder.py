@@ -175,3 +175,27 @@ def test_edge_cases_through_cuda(key):
     outs, _ = gpu_encode(yuv, w, h, n, qp, 30.0)
     assert [len(b) for b in outs[0]] == EDGE["edge"][key]["frame_bytes"]
     assert hashlib.sha1(b"".join(outs[0])).hexdigest() == EDGE["edge"][key]["sha1"]
+
+
+def test_device_cavlc_bit_count_is_exact():
+    """the macroblock kernel's CAVLC bit count (no bits emitted on the device) equals, macroblock by
+    macroblock, what the host writer spends — IDR and P pictures, low and high QP, real clip and synthetic content."""
+    from openh264_b200.binding import BatchEncoder
+    clip = np.fromfile(os.path.join(ROOT, "tests", "golden", "CiscoVT2people_320x192_12fps.yuv"), dtype=np.uint8)
+    cases = [(320, 192, 9, 12, clip), (320, 192, 9, 30, clip), (176, 144, 4, 0, h264lib.synth_clip(176, 144, 4, seed=3)),
+             (640, 360, 3, 44, h264lib.synth_clip(640, 360, 3, seed=9, noise=8))]
+    for w, h, n, qp, yuv in cases:
+        enc = BatchEncoder(w, h, qp=qp, fps=30.0, n_streams=2)
+        enc.set_mb_bits(True)
+        fsz = w * h * 3 // 2
+        coded = 0
+        for f in range(n):
+            bs, _ = enc.encode([yuv[f * fsz:(f + 1) * fsz]] * 2)
+            for s in range(2):
+                dev, host = enc.mb_bits(s)
+                assert np.array_equal(dev, host), (w, h, qp, f, s, np.nonzero(dev != host)[0][:8])
+                coded += int((host > 0).sum())
+                # the macroblock bits account for the slice payload up to header, skip runs and trailing bits
+                assert int(host.sum()) <= 8 * len(bs[s])
+        assert coded > 0
+        enc.close()

@@ -16,7 +16,7 @@
  *
  * Supported configuration (everything else is rejected with an error, never silently approximated):
  * CAMERA_VIDEO_REAL_TIME, 1 spatial / 1 temporal layer, RC_OFF_MODE (constant QP), SM_SINGLE_SLICE,
- * CAVLC, complexity MEDIUM/HIGH, 1 reference frame, deblocking idc 0, IDR at the first frame (and on
+ * CAVLC, any iComplexityMode (LOW / MEDIUM / HIGH), 1 reference frame, deblocking idc 0, IDR at the first frame (and on
  * ForceIntraFrame), no denoise / background detection / adaptive quant / scene-change / LTR.
  * For that configuration the bitstream is bit-identical to the reference's.
  */
@@ -39,6 +39,8 @@ typedef struct {
   int32_t entropy_threads;      /* host threads for CAVLC (0 = min(n_streams, hardware threads)) */
   int32_t device;               /* CUDA device ordinal */
   int32_t sps_pps_id_strategy;  /* eSpsPpsIdStrategy: 0 CONSTANT_ID, 1 INCREASING_ID (the reference's default) */
+  int32_t complexity_low;       /* 1: iComplexityMode = LOW_COMPLEXITY (the reference's default: SAD mode costs, VAA-driven
+                                 * partition choice, pruned I4x4 search); 0: MEDIUM / HIGH (identical bitstreams for this class) */
 } b2h264_enc_config;
 
 /* returns 0 or a negative b2h264 error / positive cudaError_t */

@@ -75,7 +75,8 @@ struct b2h264_enc {
   cudaStream_t st_in = nullptr;     // source uploads: overlap the previous picture's kernels
   cudaStream_t st_out = nullptr;    // record downloads: overlap deblocking and the next picture's kernels
   // device memory
-  uint8_t* d_cur = nullptr;               // S x (Y,U,V) MB-aligned current pictures
+  uint8_t* d_cur = nullptr;               // 2 x S x (Y,U,V) MB-aligned source pictures (current / previous: VAA statistics)
+  int32_t* d_vaa = nullptr;               // S x n_mb x 4: 8x8 SADs against the previous source picture (LOW_COMPLEXITY)
   uint8_t* d_pic_all = nullptr;           // 2 x S x padded (Y,U,V)
   uint8_t* d_pic[2] = {nullptr, nullptr}; // the two picture sets inside d_pic_all
   uint8_t* d_src = nullptr;               // S x raw I420 staging (2 slots)
@@ -91,6 +92,7 @@ struct b2h264_enc {
   StreamFrame* d_sf[2] = {nullptr, nullptr};
   alignas(64) unsigned char tmap_pic[128];      // CUtensorMap of the luma planes of both picture sets of all streams
   bool have_tmap = false;
+  void* d_tmap = nullptr;                       // the descriptor in device memory (B2H264_ENC_WIN=3)
   const uint8_t** d_srcptr[2] = {nullptr, nullptr};
   // pinned host memory
   uint8_t* h_src = nullptr;               // 2 slots x S x frame
@@ -136,6 +138,7 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
   e->ctl.resize(e->S);
   for (auto& c : e->ctl) {
     c.init(cfg->width, cfg->height, cfg->qp, cfg->fps, cfg->target_bitrate);
+    c.fast_mode = cfg->complexity_low != 0;
     c.increasing_ids = cfg->sps_pps_id_strategy != 0;
   }
   e->idr_next.assign(e->S, 1);
@@ -160,7 +163,10 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
   // both picture sets of all streams in ONE allocation: plane index set * S + stream (the reference tensor map's z)
   CK(cudaMalloc(&e->d_pic_all, 2 * S * e->pic_bytes + 256));
   CK(cudaMemset(e->d_pic_all, 0, 2 * S * e->pic_bytes + 256));
-  CK(cudaMalloc(&e->d_cur, S * e->cur_bytes + 256));
+  CK(cudaMalloc(&e->d_cur, 2 * S * e->cur_bytes + 256));
+  CK(cudaMemset(e->d_cur, 0, 2 * S * e->cur_bytes + 256));
+  CK(cudaMalloc(&e->d_vaa, S * e->n_mb * 4 * sizeof(int32_t)));
+  CK(cudaMemset(e->d_vaa, 0, S * e->n_mb * 4 * sizeof(int32_t)));
   CK(cudaMalloc(&e->d_list, S * e->n_mb * sizeof(int32_t)));
   for (int i = 0; i < 2; i++) {
     e->d_pic[i] = e->d_pic_all + (size_t)i * S * e->pic_bytes;
@@ -184,6 +190,10 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
   // TMA descriptors of the two picture sets: (x, y) from the padded origin of the luma plane, z = stream
   e->have_tmap = b2h264_make_tmap_planes(e->tmap_pic, e->d_pic_all, (uint64_t)c0.rec_stride_y(), (uint64_t)c0.rec_rows_y(), 2 * (uint64_t)S,
                                          (uint64_t)c0.rec_stride_y(), (uint64_t)e->pic_bytes, 48, 48) == 0;
+  if (e->have_tmap) {
+    CK(cudaMalloc(&e->d_tmap, 128));
+    CK(cudaMemcpy(e->d_tmap, e->tmap_pic, 128, cudaMemcpyHostToDevice));
+  }
   CK(cudaMalloc(&e->d_src, 2 * S * e->frame_bytes + 256));
   CK(cudaMallocHost(&e->h_src, 2 * S * e->frame_bytes));
   CK(cudaMalloc(&e->d_mbi, S * e->n_mb * sizeof(MbInfo)));
@@ -207,7 +217,7 @@ void b2h264_enc_destroy(b2h264_enc* e) {
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->st);
   delete e->pool;
-  cudaFree(e->d_pic_all); cudaFree(e->d_cur); cudaFree(e->d_src); cudaFree(e->d_mbi); cudaFree(e->d_sad); cudaFree(e->d_prog); cudaFree(e->d_bits); cudaFree(e->d_tickets); cudaFree(e->d_stash); cudaFree(e->d_list);
+  cudaFree(e->d_pic_all); cudaFree(e->d_cur); cudaFree(e->d_vaa); cudaFree(e->d_tmap); cudaFree(e->d_src); cudaFree(e->d_mbi); cudaFree(e->d_sad); cudaFree(e->d_prog); cudaFree(e->d_bits); cudaFree(e->d_tickets); cudaFree(e->d_stash); cudaFree(e->d_list);
   cudaFreeHost(e->h_src);
   for (int i = 0; i < 2; i++) {
     cudaFree(e->d_rinfo[i]); cudaFree(e->d_out[i]); cudaFree(e->d_sf[i]); cudaFree(e->d_srcptr[i]);
@@ -264,18 +274,20 @@ int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_devic
     sl.idr[s] = idr;
     StreamFrame& F = e->h_sf[k][i];
     F.p = e->ctl[s].frame_params(idr, e->have_ref_p[s] != 0);
-    uint8_t* cur = e->d_cur + (size_t)s * e->cur_bytes;
+    const int cpar = e->stream_rec[s];              // the source pictures alternate with the reconstructed ones
+    uint8_t* cur = e->d_cur + ((size_t)cpar * S + s) * e->cur_bytes;
+    F.f.prev_luma = e->cfg.complexity_low ? e->d_cur + ((size_t)(1 - cpar) * S + s) * e->cur_bytes : nullptr;
+    F.f.vaa_sad8x8 = e->cfg.complexity_low ? e->d_vaa + (size_t)s * e->n_mb * 4 : nullptr;
     F.f.cur[0] = cur; F.f.cur[1] = cur + (size_t)e->n_mb * 256; F.f.cur[2] = cur + (size_t)e->n_mb * 320;
     // every stream has its OWN picture parity (a stream that sat a batch out keeps its reference where it is)
     const int prec = e->stream_rec[s];
-    F.p.ref_plane = (1 - prec) * S + s; F.p.pad0 = 0;
+    F.p.ref_plane = (1 - prec) * S + s;
     for (int pl = 0; pl < 3; pl++) { F.f.rec[pl] = e->pic_plane0(prec, s, pl); F.f.ref[pl] = e->pic_plane0(1 - prec, s, pl); }
     F.f.mbi = e->d_mbi + (size_t)s * e->n_mb;
     F.f.rec_info = e->d_rinfo[prec] + (size_t)s * e->n_mb;
     F.f.ref_info = e->d_rinfo[1 - prec] + (size_t)s * e->n_mb;
     F.f.out = e->d_out[k] + (size_t)i * e->n_mb;
     F.f.sad_cost = e->d_sad + (size_t)s * e->n_mb;
-    F.f.row_progress = e->d_prog + (size_t)s * 2 * mbh;
     F.f.mb_bits = e->mb_bits_on ? e->d_bits + (size_t)s * e->n_mb : nullptr;
     e->idr_next[s] = 0;
     e->have_ref_p[s] = !idr;
@@ -289,7 +301,7 @@ int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_devic
   CK(cudaMemcpyAsync(e->d_srcptr[k], e->h_srcptr[k], n * sizeof(uint8_t*), cudaMemcpyHostToDevice, e->st));
   CK(cudaEventRecord(sl.ev0, e->st));
   int rc = enc_launch_frame(e->d_sf[k], e->d_srcptr[k], n, e->cfg.width, e->cfg.height, mbw, mbh, e->d_tickets, e->d_stash,
-                            e->have_tmap ? e->tmap_pic : nullptr, e->st);
+                            e->have_tmap ? e->tmap_pic : nullptr, e->d_tmap, e->cfg.complexity_low != 0, e->st);
   if (rc) return rc;
   CK(cudaEventRecord(sl.ev1, e->st));
   rc = enc_launch_deblock_expand(e->d_sf[k], n, mbw, mbh, e->d_tickets, e->st);
@@ -350,6 +362,8 @@ int b2h264_enc_reset_stream(b2h264_enc* e, int stream) {
   e->ctl[stream] = StreamCtl();
   e->ctl[stream].init(e->cfg.width, e->cfg.height, e->cfg.qp, e->cfg.fps, e->cfg.target_bitrate);
   e->ctl[stream].increasing_ids = e->cfg.sps_pps_id_strategy != 0;
+  e->ctl[stream].fast_mode = e->cfg.complexity_low != 0;
+  e->ctl[stream].record_mb_bits = e->mb_bits_on;
   e->idr_next[stream] = 1;
   e->have_ref_p[stream] = 0;
   // what a fresh encoder starts from: no SAD history, no reference-picture records

@@ -26,7 +26,7 @@ MBK_HD void mb_ctx(MbCtx& c, const EncFrameParams& p, const EncFramePtrs& f, int
     c.qp = p.qp;
     c.qp_c = tbl_chroma_qp(p.qp);          // chroma_qp_index_offset = 0
     c.lambda = tbl_lambda(p.qp);
-    c.tmap_ref = nullptr; c.wbar = nullptr;       // the device encode kernel fills these in after mb_ctx
+    c.tmap_ref = nullptr; c.wbar = nullptr; c.win_mode = 0;       // the device encode kernel fills these in after mb_ctx
   }
   warp_sync();
 }

@@ -31,6 +31,7 @@ EncFrameParams StreamCtl::frame_params(bool idr, bool ref_is_p) const {
   // GetMvMvdRange (encoder_ext.cpp:1508): min(level vertical MV limit / 4, CAMERA_STARTMV_RANGE = 64)
   p.mv_range = sp.level_idc <= 10 ? 63 : 64;
   p.ref_is_p = ref_is_p;
+  p.fast_mode = fast_mode ? 1 : 0;
   return p;
 }
 

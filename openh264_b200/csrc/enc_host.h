@@ -23,6 +23,7 @@ struct StreamCtl {
   // (mod MAX_SPS_COUNT 32 / MAX_PPS_COUNT 57, paraset_strategy.cpp:338-369); CONSTANT_ID keeps 0/0
   bool increasing_ids = true;
   int parasets_written = 0;
+  bool fast_mode = false;                   // iComplexityMode == LOW_COMPLEXITY
   bool record_mb_bits = false;              // keep the writer's bits per macroblock of the last picture (parity of the device count)
   std::vector<int32_t> last_mb_bits;
 

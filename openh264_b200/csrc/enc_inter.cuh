@@ -257,7 +257,12 @@ MBK_FN SkipResult pskip_enc(const MbCtx& c, MbScratch& s, int sad_pred_skip, int
   phase_mark(s, 15);
   if (ok) {
     r.ok = true;
-    r.cost_luma = warp_satd(s.cur_y, 16, py, 16, 4, 4);
+    if (c.p.fast_mode) {                   // bMdUsingSad (:1493,:1524): the luma SAD is the cost AND goes into pSadCost[0]
+      r.cost_luma = sad_y;
+      if (lane_id() == 0) c.f.sad_cost[c.mby * c.p.mb_w + c.mbx] = sad_y;
+    } else {
+      r.cost_luma = warp_satd(s.cur_y, 16, py, 16, 4, 4);
+    }
     phase_mark(s, 16);
     r.cost_skip = sad_mb;
   }
@@ -270,15 +275,28 @@ MBK_FN SkipResult pskip_enc(const MbCtx& c, MbScratch& s, int sad_pred_skip, int
 MBK_HD void win_issue(const MbCtx& c, MbScratch& s, int sx, int sy) {
 #ifdef __CUDA_ARCH__
   warp_sync();
-  if (c.tmap_ref != nullptr && lane_id() == 0) {
-    s.win_x0 = sx - 16; s.win_y0 = sy - 16; s.win_ok = 1;
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(scratch_win(s));
-    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&c.wbar->bar);
-    const int X = 32 + c.mbx * 16 + s.win_x0, Y = 32 + c.mby * 16 + s.win_y0, Z = c.p.ref_plane;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic accesses to the window bytes
-    asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(WIN_W * WIN_H) : "memory");
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(dst), "l"(c.tmap_ref), "r"(X), "r"(Y), "r"(Z), "r"(bar) : "memory");
+  if (c.win_mode == 0) { if (lane_id() == 0) s.win_ok = 0; warp_sync(); return; }
+  if (lane_id() == 0) { s.win_x0 = sx - 16; s.win_y0 = sy - 16; s.win_ok = 1; }
+  if (c.win_mode == 1) {
+    if (lane_id() == 0) {
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(scratch_win(s));
+      const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&c.wbar->bar);
+      const int X = 32 + c.mbx * 16 + sx - 16, Y = 32 + c.mby * 16 + sy - 16, Z = c.p.ref_plane;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic accesses to the window bytes
+      asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(WIN_W * WIN_H) : "memory");
+      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                   ::"r"(dst), "l"(c.tmap_ref), "r"(X), "r"(Y), "r"(Z), "r"(bar) : "memory");
+    }
+  } else {
+    // the warp's own loads: 48 rows x 12 words, unaligned source (two aligned loads + funnel shift each), all in flight together
+    const uint8_t* src = ref_luma(c, sx - 16, sy - 16);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(scratch_win(s));
+    const int rs = c.p.rec_stride_y;
+#pragma unroll 6
+    for (int i = lane_id(); i < WIN_H * (WIN_W / 4); i += MBK_WS) {
+      const int r = i / (WIN_W / 4), w = i - r * (WIN_W / 4);
+      dst[i] = ld4u(src + (ptrdiff_t)r * rs + 4 * w);
+    }
   }
   warp_sync();
 #else
@@ -288,7 +306,7 @@ MBK_HD void win_issue(const MbCtx& c, MbScratch& s, int sx, int sy) {
 }
 MBK_HD void win_wait(const MbCtx& c, MbScratch& s) {
 #ifdef __CUDA_ARCH__
-  if (c.tmap_ref != nullptr && s.win_ok) {
+  if (c.win_mode == 1 && s.win_ok) {
     const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&c.wbar->bar);
     const uint32_t ph = c.wbar->phase;
     uint32_t ok = 0;
@@ -321,7 +339,7 @@ MBK_FN void me_partition(const MbCtx& c, MbScratch& s, int blk_size, int ox, int
   in.n_mvc = n_mvc; in.mvc = mvc;
   in.sad_pred = sad_pred;
   in.lambda = c.lambda;
-  in.calc_satd = true;
+  in.calc_satd = !c.p.fast_mode;            // NotCalculateSatdCost in LOW_COMPLEXITY (encoder_ext.cpp:2687)
   in.win = s.win_ok ? scratch_win(s) : nullptr;
   in.win_w = WIN_W; in.win_h = WIN_H;
   in.win_dx = s.win_x0 - ox; in.win_dy = s.win_y0 - oy;
@@ -377,8 +395,10 @@ MBK_FN void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy,
   const int rs = c.p.rec_stride_y;
   const int px = st->mvp_x, py = st->mvp_y;
   const int mv0x = st->mv_x, mv0y = st->mv_y;
-  int best = st->satd + mvd_cost(c.lambda, mv0x - px, mv0y - py);
   const uint8_t* ref0 = st->ref;
+  // bSatdInMdFlag (md.cpp:601-606): with SATD mode costs the search already holds the SATD at the integer position;
+  // in LOW_COMPLEXITY (SAD mode costs) it is computed here — pfMeCost stays SATD either way
+  int best = (c.p.fast_mode ? warp_satd(enc, 16, ref0, rs, lw, lh) : st->satd) + mvd_cost(c.lambda, mv0x - px, mv0y - py);
   // ---- stage the integer window (the coefficient buffer is free until the residual is coded) ----
   uint8_t* win = reinterpret_cast<uint8_t*>(s.coef);
   static_assert(sizeof(s.coef) >= 22 * QP_STRIDE, "window aliases the coefficient buffer");
@@ -671,19 +691,20 @@ MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
   }
   {
 
-    // step 3: sub-16x16 partitions (WelsMdInterFinePartition :1238)
+    // step 3: sub-16x16 partitions (WelsMdInterFinePartition :1238 / WelsMdInterFinePartitionVaa :1270)
     const int16_t mvc0[2] = {0, 0};
-    int cost8 = 0;
-    for (int i = 0; i < 4; i++) {
-      int px, py;
-      pred_mv(s, 4 * i, 2, 0, &px, &py);
-      me_partition(c, s, BLK_8x8, (i & 1) * 8, (i >> 1) * 8, px, py, (uint32_t)(sad_pred_mb >> 2), 1, mvc0, &me8x8[i]);
-      cache_set(s, 4 * i, 2, 2, me8x8[i].mv_x, me8x8[i].mv_y);
-      cost8 += (int)me8x8[i].satd_cost;
-    }
-    if (cost8 < cost_luma) {
-      int cost = cost8;
-      final_type = MBT_P8x8;
+    auto md_p8x8 = [&]() {
+      int cost8 = 0;
+      for (int i = 0; i < 4; i++) {
+        int px, py;
+        pred_mv(s, 4 * i, 2, 0, &px, &py);
+        me_partition(c, s, BLK_8x8, (i & 1) * 8, (i >> 1) * 8, px, py, (uint32_t)(sad_pred_mb >> 2), 1, mvc0, &me8x8[i]);
+        cache_set(s, 4 * i, 2, 2, me8x8[i].mv_x, me8x8[i].mv_y);
+        cost8 += (int)me8x8[i].satd_cost;
+      }
+      return cost8;
+    };
+    auto md_p16x8 = [&]() {
       int cst = 0;
       for (int i = 0; i < 2; i++) {
         int px, py;
@@ -692,8 +713,10 @@ MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
         cache_set(s, 8 * i, 4, 2, me16x8[i].mv_x, me16x8[i].mv_y);
         cst += (int)me16x8[i].satd_cost;
       }
-      if (cst <= cost) { cost = cst; final_type = MBT_P16x8; }
-      cst = 0;
+      return cst;
+    };
+    auto md_p8x16 = [&]() {
+      int cst = 0;
       for (int i = 0; i < 2; i++) {
         int px, py;
         pred_8x16_mv(s, 4 * i, 0, &px, &py);
@@ -701,7 +724,36 @@ MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
         cache_set(s, 4 * i, 2, 4, me8x16[i].mv_x, me8x16[i].mv_y);
         cst += (int)me8x16[i].satd_cost;
       }
-      if (cst <= cost) { cost = cst; final_type = MBT_P8x16; }
+      return cst;
+    };
+    // LOW_COMPLEXITY: the four 8x8 SADs of the macroblock against the previous source picture say which partition shapes
+    // are worth a search (MdInterAnalysisVaaInfo_c md.cpp:389): 15 = homogeneous, none; 3/12 -> 16x8; 5/10 -> 8x16;
+    // 6/9 -> 8x8; anything else -> the full sequence of the other complexity modes
+    int vaa_sign = 0;
+    if (c.p.fast_mode) {
+      const int32_t* v = c.f.vaa_sad8x8 + 4 * idx;
+      const int b0 = v[0], b1 = v[1], b2 = v[2], b3 = v[3], avg = (b0 + b1 + b2 + b3) >> 2;
+      const int d0 = (b0 >> 6) - (avg >> 6), d1 = (b1 >> 6) - (avg >> 6), d2 = (b2 >> 6) - (avg >> 6), d3 = (b3 >> 6) - (avg >> 6);
+      if (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3 < 20) vaa_sign = 15;               // INTER_VARIANCE_SAD_THRESHOLD
+      else vaa_sign = (b0 > avg ? 8 : 0) | (b1 > avg ? 4 : 0) | (b2 > avg ? 2 : 0) | (b3 > avg ? 1 : 0);
+    }
+    if (c.p.fast_mode && vaa_sign == 15) {
+    } else if (c.p.fast_mode && (vaa_sign == 3 || vaa_sign == 12)) {
+      if (md_p16x8() < cost_luma) final_type = MBT_P16x8;
+    } else if (c.p.fast_mode && (vaa_sign == 5 || vaa_sign == 10)) {
+      if (md_p8x16() < cost_luma) final_type = MBT_P8x16;
+    } else if (c.p.fast_mode && (vaa_sign == 6 || vaa_sign == 9)) {
+      if (md_p8x8() < cost_luma) final_type = MBT_P8x8;
+    } else {
+      const int cost8 = md_p8x8();
+      if (cost8 < cost_luma) {
+        int cost = cost8;
+        final_type = MBT_P8x8;
+        int cst = md_p16x8();
+        if (cst <= cost) { cost = cst; final_type = MBT_P16x8; }
+        cst = md_p8x16();
+        if (cst <= cost) { cost = cst; final_type = MBT_P8x16; }
+      }
     }
     phase_mark(s, 6);
     // refinement (WelsMdInterMbRefinement :1573)
@@ -788,8 +840,10 @@ MBK_FN int inter_stage_c(const MbCtx& c, MbScratch& s) {
       s.info.mb_type = MBT_I16x16;
       s.info.cbp = 0;
       fill_i4_cache(c, s);
-      const int cost4 = md_enc_i4x4(c, s, cost);
-      if (cost4 < cost) { s.info.mb_type = MBT_I4x4; cost = cost4; }
+      if (intra_try_i4x4(c, s)) {
+        const int cost4 = md_enc_i4x4(c, s, cost);
+        if (cost4 < cost) { s.info.mb_type = MBT_I4x4; cost = cost4; }
+      }
       if (s.info.mb_type == MBT_I16x16) { s.info.cbp = 0; enc_rec_i16x16(c, s, s.pred_y[bb]); }
       int cb;
       md_chroma(c, s, &cb);

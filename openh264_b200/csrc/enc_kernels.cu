@@ -60,6 +60,25 @@ __global__ void k_pad_source(const StreamFrame* __restrict__ sf, const uint8_t* 
   }
 }
 
+// ---- VAA statistics of LOW_COMPLEXITY (VAACalcSad_c, codec/processing/src/vaacalc/vaacalcfuncs.cpp:254) -------------------------
+// SAD of the four 8x8 blocks of every macroblock between the current and the PREVIOUS source picture (both MB-aligned,
+// stride 16 * mb_w): one warp per macroblock, lane = (row, 8-pixel half), two packed SADs per lane, three shuffles.
+// out[(stream, mb) * 4 + k], k = 0 top-left, 1 top-right, 2 bottom-left, 3 bottom-right.  Pure streaming: 512 B read, 16 B written per MB.
+__global__ void __launch_bounds__(256) k_vaa_sad8x8(const StreamFrame* __restrict__ sf, int n_mb) {
+  const int lane = threadIdx.x & 31, mb = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (mb >= n_mb) return;
+  const StreamFrame& F = sf[blockIdx.y];
+  if (F.f.vaa_sad8x8 == nullptr || F.f.prev_luma == nullptr) return;
+  const int st = F.p.cur_stride_y, mbx = mb % F.p.mb_w, mby = mb / F.p.mb_w;
+  const size_t off = (size_t)(mby * 16 + (lane >> 1)) * st + mbx * 16 + (lane & 1) * 8;
+  const uint2 a = *reinterpret_cast<const uint2*>(F.f.cur[0] + off), b = *reinterpret_cast<const uint2*>(F.f.prev_luma + off);
+  int v = (int)(__vsadu4(a.x, b.x) + __vsadu4(a.y, b.y));
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);                 // lanes 0, 1, 16, 17 hold the four block sums
+  if ((lane & 14) == 0) const_cast<int32_t*>(F.f.vaa_sad8x8)[(size_t)mb * 4 + (lane >> 4) * 2 + (lane & 1)] = v;
+}
+
 // ---- dependency-driven macroblock scheduling -------------------------------------------------------------
 // MB(x,y) may start when (x-1,y) and (x+1,y-1) [(x,y-1) on the last column] are final; those two imply the
 // top and top-left neighbours.  Every finished MB notifies its right neighbour and its bottom-left
@@ -316,7 +335,8 @@ __device__ __forceinline__ MbScratch& my_scratch(uint8_t* smem) {
 // tm_ref: reference luma planes of all streams (x, y from the padded origin, z = stream); stage B stages its
 // search window out of it with one bulk tensor copy per macroblock (enc_inter.cuh: win_issue / win_wait)
 __global__ void __launch_bounds__(32 * ENC_WPC, ENC_MIN_CTAS) k_encode_mbs(const StreamFrame* __restrict__ sf, int n_streams, EncSched q, int stats,
-                                                                          const __grid_constant__ CUtensorMap tm_ref, int use_tma) {
+                                                                          const __grid_constant__ CUtensorMap tm_ref, const void* tm_global,
+                                                                          int win_mode /* 0 none, 1 TMA (descriptor = kernel parameter), 2 warp loads, 3 TMA (descriptor in global memory) */) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ WinBar s_wbar[ENC_WPC];
   MbScratch& s = my_scratch(smem);
@@ -327,11 +347,12 @@ __global__ void __launch_bounds__(32 * ENC_WPC, ENC_MIN_CTAS) k_encode_mbs(const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const void* tmap = use_tma ? &tm_ref : nullptr;
+  const void* tmap = win_mode == 1 ? (const void*)&tm_ref : win_mode == 3 ? tm_global : nullptr;
+  const int wmode = win_mode == 3 ? 1 : win_mode;
   run_stages(sf, n_streams, q, s, stats & 1, [&](const StreamFrame& F, int x, int y, int stage) {
     const long long t0 = (stats & 1) ? clock64() : 0;
     mb_ctx(s.ctx, F.p, F.f, x, y);
-    if ((threadIdx.x & 31) == 0) { s.ctx.tmap_ref = tmap; s.ctx.wbar = wb; }
+    if ((threadIdx.x & 31) == 0) { s.ctx.tmap_ref = tmap; s.ctx.wbar = wb; s.ctx.win_mode = wmode; }
     __syncwarp();
     int next = mb_run_stage(s.ctx, s, stage);
     if (stats & 2) while (next != MBS_DONE) next = mb_run_stage(s.ctx, s, next);      // debugging: all stages in one task
@@ -462,11 +483,16 @@ static EncSched make_esched(int* ws, int total, void* stash) {
 }
 
 int enc_launch_frame(const StreamFrame* d_sf, const uint8_t* const* d_src, int n_streams, int w, int h, int mb_w, int mb_h,
-                     int* d_ws, void* d_stash, const void* tmap_ref, cudaStream_t st) {
+                     int* d_ws, void* d_stash, const void* tmap_ref, const void* d_tmap, int fast_mode, cudaStream_t st) {
   int rc;
   if (d_src) {
     dim3 b(32, 8), g((mb_w * 4 + 31) / 32, (mb_h * 16 + 7) / 8, n_streams);
     k_pad_source<<<g, b, 0, st>>>(d_sf, d_src, w, h);
+    if ((rc = b2h264_launched())) return rc;
+  }
+  if (fast_mode) {                                    // LOW_COMPLEXITY: the partition choice reads these statistics
+    const int n_mb = mb_w * mb_h;
+    k_vaa_sad8x8<<<dim3((n_mb + 7) / 8, n_streams), 256, 0, st>>>(d_sf, n_mb);
     if ((rc = b2h264_launched())) return rc;
   }
   const int total = n_streams * mb_w * mb_h;
@@ -482,10 +508,14 @@ int enc_launch_frame(const StreamFrame* d_sf, const uint8_t* const* d_src, int n
   static const int stats = (getenv("B2H264_ENC_STATS") ? 1 : 0) | (getenv("B2H264_FUSE_STAGES") ? 2 : 0);
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
-  static const int no_tma = getenv("B2H264_ENC_NO_TMA") ? 1 : 0;          // debugging: search out of the plane only
-  const int use_tma = tmap_ref != nullptr && !no_tma;
-  if (use_tma) memcpy(&tm, tmap_ref, sizeof(tm));
-  k_encode_mbs<<<blocks, 32 * ENC_WPC, kScratchSmem, st>>>(d_sf, n_streams, qe, stats, tm, use_tma);
+  // B2H264_ENC_WIN: 0 = search out of the plane, 1 = TMA window, descriptor passed as kernel parameter (default),
+  // 2 = window staged by the warp's own loads, 3 = TMA window, descriptor read from global memory
+  static const int win_env = getenv("B2H264_ENC_WIN") ? atoi(getenv("B2H264_ENC_WIN")) : 1;
+  int win_mode = win_env;
+  if ((win_mode == 1 || win_mode == 3) && tmap_ref == nullptr) win_mode = 2;
+  if (win_mode == 3 && d_tmap == nullptr) win_mode = 2;
+  if (win_mode == 1) memcpy(&tm, tmap_ref, sizeof(tm));
+  k_encode_mbs<<<blocks, 32 * ENC_WPC, kScratchSmem, st>>>(d_sf, n_streams, qe, stats, tm, d_tmap, win_mode);
   if ((rc = b2h264_launched())) return rc;
   return 0;
 }

@@ -14,7 +14,8 @@ int enc_upload_deblock_tables();
 // pad (if d_src != NULL) + wavefront macroblock kernel for n_streams pictures of identical geometry
 int enc_launch_frame(const StreamFrame* d_sf, const uint8_t* const* d_src, int n_streams, int w, int h, int mb_w, int mb_h,
                      int* d_sched_ws, void* d_stash, const void* tmap_ref /* CUtensorMap of the reference luma planes or NULL */,
-                     cudaStream_t st);
+                     const void* d_tmap /* the same descriptor in device memory or NULL */,
+                     int fast_mode /* LOW_COMPLEXITY: also computes the VAA 8x8 SADs */, cudaStream_t st);
 // wavefront deblocking + border expansion of the pictures just reconstructed
 int enc_launch_deblock_expand(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h, int* d_sched_ws, cudaStream_t st);
 // number of ints of scheduler workspace (dependency counters + ready lists) for a batch

@@ -20,6 +20,7 @@ struct MbCtx {
   // (x, y from the padded origin, z = stream) and this warp's mbarrier
   const void* tmap_ref;
   WinBar* wbar;
+  int win_mode;                 // 0: search out of the plane; 1: window staged by TMA; 2: window staged by the warp's own loads
 };
 
 struct MeState {            // the parts of SWelsME the later steps of a partition need
@@ -299,7 +300,8 @@ MBK_FN int md_i16x16(const MbCtx& c, MbScratch& s, int* best_buf) {
   for (int i = 0; i < n; i++) {
     uint8_t* dst = s.pred_y[1 - bb];
     pred_i16(dst, org, TY_PITCH, modes[i]);
-    const int cost = warp_satd(dst, 16, s.cur_y, 16, 4, 4) + c.lambda * ue_bits(map_i16(modes[i]));
+    const int cost = (c.p.fast_mode ? warp_sad(dst, 16, s.cur_y, 16, 4, 4) : warp_satd(dst, 16, s.cur_y, 16, 4, 4)) +
+                     c.lambda * ue_bits(map_i16(modes[i]));        // pfMdCost: SAD in LOW_COMPLEXITY (encoder_ext.cpp:2618)
     if (cost < best) { best = cost; best_mode = modes[i]; bb = 1 - bb; }
     warp_sync();
   }
@@ -317,7 +319,8 @@ MBK_FN int md_chroma(const MbCtx& c, MbScratch& s, int* best_buf) {
     uint8_t* dst = s.pred_c[1 - bb];
     pred_chroma(dst, tile_c(s.tile.u, 0, 0), TC_PITCH, modes[i]);
     pred_chroma(dst + 64, tile_c(s.tile.v, 0, 0), TC_PITCH, modes[i]);
-    const int cost = warp_satd(dst, 8, s.cur_c, 8, 3, 3) + warp_satd(dst + 64, 8, s.cur_c + 64, 8, 3, 3) +
+    const int cost = (c.p.fast_mode ? warp_sad(dst, 8, s.cur_c, 8, 3, 3) + warp_sad(dst + 64, 8, s.cur_c + 64, 8, 3, 3)
+                                     : warp_satd(dst, 8, s.cur_c, 8, 3, 3) + warp_satd(dst + 64, 8, s.cur_c + 64, 8, 3, 3)) +
                      c.lambda * ue_bits(map_chroma(modes[i]));
     if (cost < best) { best = cost; best_mode = modes[i]; bb = 1 - bb; }
     warp_sync();
@@ -410,17 +413,59 @@ MBK_FN int md_enc_i4x4(const MbCtx& c, MbScratch& s, int cost_limit) {
     const int pm = (lm == -1 || tm == -1) ? 2 : (lm < tm ? lm : tm);
     int modes[9];
     const int n = i4_modes(i4_avail(c.nb, k), modes);
-    // all candidates in parallel (one lane each); ties resolve to the earliest list entry like the serial '<'
-    int key = 0x7fffffff;
-    for (int j = lane_id(); j < n; j += MBK_WS) {
-      uint8_t p[16];
-      pred_i4(p, org, TY_PITCH, modes[j]);
-      const int cost = satd4x4_pred(p, cur, 16) + (pm == map_i4(modes[j]) ? lam1 : lam4);
-      const int kj = (cost << 4) | j;
-      if (kj < key) key = kj;
+    int best_cost, best_mode;
+    if (!c.p.fast_mode) {
+      // all candidates in parallel (one lane each); ties resolve to the earliest list entry like the serial '<'
+      int key = 0x7fffffff;
+      for (int j = lane_id(); j < n; j += MBK_WS) {
+        uint8_t p[16];
+        pred_i4(p, org, TY_PITCH, modes[j]);
+        const int cost = satd4x4_pred(p, cur, 16) + (pm == map_i4(modes[j]) ? lam1 : lam4);
+        const int kj = (cost << 4) | j;
+        if (kj < key) key = kj;
+      }
+      key = warp_min(key);
+      best_cost = key >> 4; best_mode = modes[key & 15];
+    } else {
+      // LOW_COMPLEXITY (WelsMdI4x4Fast, svc_base_layer_md.cpp:548): SAD costs and a pruned candidate tree.  Every
+      // candidate's cost is computed (one lane each, into s.red); the tree is then walked on the costs — a cost is a
+      // pure function of the mode, so evaluating more modes than the reference cannot change which one it picks.
+      for (int j = lane_id(); j < n; j += MBK_WS) {
+        uint8_t p[16];
+        pred_i4(p, org, TY_PITCH, modes[j]);
+        int sad = 0;
+        for (int q = 0; q < 16; q++) sad += iabs((int)p[q] - (int)cur[(q >> 2) * 16 + (q & 3)]);
+        s.red[modes[j]] = sad + (pm == map_i4(modes[j]) ? lam1 : lam4);
+      }
+      warp_sync();
+      const int32_t* cst = s.red;
+      if (n == 9 || n == 7) {
+        best_mode = I4_DC; best_cost = cst[I4_DC];
+        const int cH = cst[I4_H], cV = cst[I4_V];
+        if (cH < best_cost) { best_cost = cH; best_mode = I4_H; }
+        if (cV < best_cost) { best_cost = cV; best_mode = I4_V; }
+#define I4_TRY(m) do { if (cst[m] < best_cost) { best_cost = cst[m]; best_mode = (m); } } while (0)
+        if (cV < cH) {
+          if (n == 9) {
+            I4_TRY(I4_VR); I4_TRY(I4_VL);
+            if (cst[I4_VR] < cV || cst[I4_VL] < cV) {               // vertical is not the (fake) best: go on
+              if (cst[I4_VR] < cst[I4_VL]) I4_TRY(I4_DDR); else I4_TRY(I4_DDL);
+            }
+          } else { I4_TRY(I4_DDR); I4_TRY(I4_VR); }
+        } else {
+          I4_TRY(I4_HD); I4_TRY(I4_HU);
+          if (cst[I4_HD] < cH || cst[I4_HU] < cH) {
+            if (cst[I4_HD] < cst[I4_HU]) I4_TRY(I4_DDR);
+            else if (n == 9) I4_TRY(I4_DDL);
+          }
+        }
+#undef I4_TRY
+      } else {
+        best_cost = 0x7fffffff; best_mode = modes[0];
+        for (int j = 0; j < n; j++) if (cst[modes[j]] < best_cost) { best_cost = cst[modes[j]]; best_mode = modes[j]; }
+      }
+      warp_sync();
     }
-    key = warp_min(key);
-    const int best_cost = key >> 4, best_mode = modes[key & 15];
     total += best_cost;
     if (total >= cost_limit) break;
     const int fm = map_i4(best_mode);
@@ -547,6 +592,22 @@ MBK_FN void fill_i4_cache(const MbCtx& c, MbScratch& s) {
   warp_sync();
 }
 
+// LOW_COMPLEXITY tries I4x4 only on textured macroblocks (WelsMdIntraFinePartitionVaa :942, MdIntraAnalysisVaaInfo /
+// AnalysisVaaInfoIntra_c md.cpp:435-500): variance of the sixteen 4x4 block means of the SOURCE macroblock >= 150
+MBK_FN bool intra_try_i4x4(const MbCtx& c, MbScratch& s) {
+  if (!c.p.fast_mode) return true;
+  int sum = 0, sqr = 0;
+  for (int k = lane_id(); k < 16; k += MBK_WS) {
+    const uint8_t* p = s.cur_y + (k >> 2) * 4 * 16 + (k & 3) * 4;
+    int a = 0;
+    for (int q = 0; q < 16; q++) a += p[(q >> 2) * 16 + (q & 3)];
+    a >>= 4;
+    sum += a; sqr += a * a;
+  }
+  sum = warp_sum(sum); sqr = warp_sum(sqr);
+  return sqr - ((sum * sum) >> 4) >= 150;                // INTRA_VARIANCE_SAD_THRESHOLD
+}
+
 // ---- a macroblock of an I slice (WelsMdIntraMb :956 + WelsMdIntraSecondaryModesEnc :2023) ---------
 // returns the luma cost (iCostLuma)
 MBK_FN int intra_mb_md_enc(const MbCtx& c, MbScratch& s, int cost_limit_for_i16 /*INT_MAX in I slices*/) {
@@ -556,8 +617,10 @@ MBK_FN int intra_mb_md_enc(const MbCtx& c, MbScratch& s, int cost_limit_for_i16 
   s.info.mb_type = MBT_I16x16;
   s.info.cbp = 0;
   fill_i4_cache(c, s);
-  const int cost4 = md_enc_i4x4(c, s, cost);           // pfIntraFineMd = WelsMdIntraFinePartition (:932)
-  if (cost4 < cost) { s.info.mb_type = MBT_I4x4; cost = cost4; }
+  if (intra_try_i4x4(c, s)) {
+    const int cost4 = md_enc_i4x4(c, s, cost);         // pfIntraFineMd = WelsMdIntraFinePartition[Vaa] (:932, :942)
+    if (cost4 < cost) { s.info.mb_type = MBT_I4x4; cost = cost4; }
+  }
   if (s.info.mb_type == MBT_I16x16) {
     s.info.cbp = 0;
     enc_rec_i16x16(c, s, s.pred_y[bb]);

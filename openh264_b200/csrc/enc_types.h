@@ -62,7 +62,8 @@ typedef struct {
   int32_t mv_range;                       // iMvRange (integer pel)
   int32_t ref_is_p;                       // reference picture was coded as P (temporal candidates valid)
   int32_t ref_plane;                      // z coordinate of the stream's reference picture in the encoder's luma tensor map
-  int32_t pad0;
+  int32_t fast_mode;                      // iComplexityMode == LOW_COMPLEXITY: SAD mode costs, VAA-driven partition choice
+                                          // (SetFastCodingFunc / WelsMdInterFinePartitionVaa, encoder_ext.cpp:2616,2688)
 } EncFrameParams;
 
 typedef struct {
@@ -75,6 +76,8 @@ typedef struct {
   MbOut* out;                             // mb_w*mb_h
   int32_t* sad_cost;                      // mb_w*mb_h, PERSISTS across frames like the reference's pSadCostMb
                                           // (encoder_ext.cpp:1675): a decided-skip MB keeps its older value
-  int32_t* row_progress;                  // wavefront: number of finished MBs per MB row (device only)
+  const int32_t* vaa_sad8x8;              // fast mode: SAD of the four 8x8 blocks of every macroblock against the PREVIOUS
+                                          // SOURCE picture (VAACalcSad_c), indexed like the reference: [iMbXY * 4 + k]
+  const uint8_t* prev_luma;               // fast mode: luma of the previous SOURCE picture (same layout as cur[0])
   int32_t* mb_bits;                       // optional (NULL = off): exact CAVLC bits of every macroblock (enc_cavlc_bits.cuh)
 } EncFramePtrs;

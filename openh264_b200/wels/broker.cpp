@@ -24,6 +24,7 @@ Pool::Pool(const PoolKey& key, int capacity, int device) : key_(key), cap_(capac
   cfg.entropy_threads = 0;
   cfg.device = device;
   cfg.sps_pps_id_strategy = key.strategy;
+  cfg.complexity_low = key.complexity_low;
   if (b2h264_enc_create(&cfg, &enc_) != 0) { enc_ = nullptr; return; }
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaHostAlloc((void**)&pinned_, frame_bytes_ * capacity, cudaHostAllocPortable) != cudaSuccess) {

@@ -25,10 +25,10 @@
 namespace b2wels {
 
 struct PoolKey {
-  int width, height, qp, bitrate, strategy;
+  int width, height, qp, bitrate, strategy, complexity_low;
   float fps;
   bool operator==(const PoolKey& o) const {
-    return width == o.width && height == o.height && qp == o.qp && bitrate == o.bitrate && strategy == o.strategy && fps == o.fps;
+    return width == o.width && height == o.height && qp == o.qp && bitrate == o.bitrate && strategy == o.strategy && complexity_low == o.complexity_low && fps == o.fps;
   }
 };
 

@@ -68,7 +68,8 @@ class B2Encoder : public ISVCEncoder {
     REQUIRE(p->iNumRefFrame == 1 || p->iNumRefFrame == AUTO_REF_PIC_COUNT, "iNumRefFrame != 1");
     REQUIRE(p->uiIntraPeriod == 0, "uiIntraPeriod != 0");
     REQUIRE(p->iLoopFilterDisableIdc == 0 && p->iLoopFilterAlphaC0Offset == 0 && p->iLoopFilterBetaOffset == 0, "loop filter idc/offsets != 0");
-    REQUIRE(p->iComplexityMode == MEDIUM_COMPLEXITY || p->iComplexityMode == HIGH_COMPLEXITY, "iComplexityMode LOW");
+    REQUIRE(p->iComplexityMode == LOW_COMPLEXITY || p->iComplexityMode == MEDIUM_COMPLEXITY || p->iComplexityMode == HIGH_COMPLEXITY,
+            "iComplexityMode");
     REQUIRE(!p->bEnableDenoise && !p->bEnableBackgroundDetection && !p->bEnableAdaptiveQuant && !p->bEnableSceneChangeDetect,
             "denoise / background detection / adaptive quant / scene change detection enabled");
     REQUIRE(!p->bEnableLongTermReference && !p->bEnableFrameSkip, "LTR or frame skip enabled");
@@ -97,6 +98,7 @@ class B2Encoder : public ISVCEncoder {
     key.fps = fps;
     key.bitrate = l.iSpatialBitrate ? l.iSpatialBitrate : p->iTargetBitrate;
     key.strategy = p->eSpsPpsIdStrategy == INCREASING_ID ? 1 : 0;
+    key.complexity_low = p->iComplexityMode == LOW_COMPLEXITY ? 1 : 0;
     pool_ = b2wels::Broker::get().attach(key, &slot_);
     if (!pool_ || slot_ < 0) { pool_.reset(); slot_ = -1; return cmMallocMemeError; }
     par_ = *p;

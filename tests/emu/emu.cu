@@ -35,6 +35,8 @@ struct HostFrameEncoder {
   std::vector<MbInfo> mbi;
   std::vector<RefMbInfo> rinfo[2];
   std::vector<MbOut> out;
+  std::vector<uint8_t> prev_y;                // previous SOURCE luma (MB-aligned), reference of the VAA statistics
+  std::vector<int32_t> vaa;                   // pSad8x8, indexed [iMbXY * 4 + k] as the reference does
   std::vector<int32_t> sad_cost, mb_bits;     // mb_bits: the macroblock code's own CAVLC bit count (enc_cavlc_bits.cuh)
   bool mb_bits_ok = true;
   MbScratch scratch;
@@ -52,6 +54,7 @@ struct HostFrameEncoder {
       rinfo[b].resize(n);
     }
     mbi.resize(n); out.resize(n); sad_cost.assign(n, 0); mb_bits.assign(n, -1);
+    prev_y.assign(cur[0].size(), 0); vaa.assign((size_t)n * 4, 0);
     ctl.record_mb_bits = true;
     memset(&scratch, 0, sizeof(scratch));
   }
@@ -61,6 +64,21 @@ struct HostFrameEncoder {
   void begin_frame() {
     idr = ctl.next_is_idr();
     p = ctl.frame_params(idr, have_ref_p);
+    if (ctl.fast_mode) {
+      // VAACalcSad_c (codec/processing/src/vaacalc/vaacalcfuncs.cpp:254): 8x8 SADs of the (w >> 4) x (h >> 4) whole macroblocks
+      // of the picture against the previous source picture, stored with a running macroblock index of THAT width
+      const int st = ctl.sp.mb_w * 16, vw = ctl.sp.mb_w, vh = ctl.sp.mb_h;
+      int mb_index = 0;
+      for (int i = 0; i < vh; i++)
+        for (int j = 0; j < vw; j++, mb_index++)
+          for (int k = 0; k < 4; k++) {
+            const uint8_t* a = cur[0].data() + (size_t)(i * 16 + (k >> 1) * 8) * st + j * 16 + (k & 1) * 8;
+            const uint8_t* b = prev_y.data() + (a - cur[0].data());
+            int sad = 0;
+            for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) sad += abs((int)a[y * st + x] - (int)b[y * st + x]);
+            vaa[(size_t)mb_index * 4 + k] = sad;
+          }
+    }
   }
   uint8_t* plane0(int b, int pl) {   // pixel (0,0) inside the padding
     const int pad = pl ? 16 : 32, st = pl ? ctl.rec_stride_c() : ctl.rec_stride_y();
@@ -73,6 +91,7 @@ struct HostFrameEncoder {
     f.mbi = mbi.data(); f.rec_info = rinfo[cur_rec].data(); f.ref_info = rinfo[1 - cur_rec].data(); f.out = out.data();
     f.sad_cost = sad_cost.data();
     f.mb_bits = mb_bits.data();
+    f.vaa_sad8x8 = vaa.data();
     return f;
   }
   bool packed_writer_ok = true;
@@ -113,6 +132,7 @@ struct HostFrameEncoder {
     if (ctl.last_mb_bits != mb_bits) mb_bits_ok = false;
     if (parse_status == 0) check_parse(*bs);
     have_ref_p = !idr;
+    prev_y = cur[0];
     cur_rec = 1 - cur_rec;            // the picture just reconstructed becomes the reference
   }
   void copy_recon(uint8_t* dst) {     // cropped I420 of the picture just finished (now the reference)
@@ -184,10 +204,13 @@ extern "C" int emu_last(MbOut* out, MbInfo* info, int n) {
   if (info) memcpy(info, g_last_info.data(), sizeof(MbInfo) * n);
   return 0;
 }
+static int g_emu_fast_mode = 0;
+extern "C" void emu_set_complexity_low(int on) { g_emu_fast_mode = on; }
 extern "C" long emu_encode(const uint8_t* yuv, int w, int h, int nframes, int qp, float fps, uint8_t* out, long cap,
                            int32_t* frame_bytes, uint8_t* recon_out /* nframes * w*h*3/2 or NULL */) {
   b2h264_build_host_tables();
   HostFrameEncoder enc(w, h, qp, fps);
+  enc.ctl.fast_mode = g_emu_fast_mode != 0;
   long total = 0;
   const size_t fsz = (size_t)w * h * 3 / 2;
   for (int i = 0; i < nframes; i++) {

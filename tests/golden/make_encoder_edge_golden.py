@@ -20,6 +20,11 @@ EDGE_CASES = [  # (w, h, n, qp, seed)
     (480, 32, 4, 28, 9), (64, 256, 4, 33, 10), (352, 288, 3, 38, 11),
 ]
 
+LOW_CASES = [  # (w, h, n, qp, seed, noise)
+    (640, 360, 4, 28, 4, 7), (180, 148, 4, 22, 5, 3), (176, 130, 5, 24, 3, 6), (352, 288, 5, 18, 4, 8), (1280, 720, 3, 30, 2, 6),
+    (32, 18, 4, 20, 8, 3), (176, 144, 4, 51, 3, 3),
+]
+
 if __name__ == "__main__":
     assert h264lib.have_ref()
     src = os.path.join("/root/reference/res", CLIP)
@@ -35,5 +40,14 @@ if __name__ == "__main__":
         y = h264lib.synth_clip(w, h, n, seed=seed)
         bs, fb, _ = ref_encode(y, w, h, n, qp, 30.0)
         gold["edge"]["%dx%d_n%d_qp%d_seed%d" % (w, h, n, qp, seed)] = {"sha1": hashlib.sha1(bs).hexdigest(), "frame_bytes": fb}
+    # iComplexityMode = LOW_COMPLEXITY (the reference's default; BASELINE.json configs[1] as SURVEY 8d defines it)
+    gold["low"] = {}
+    for qp in (26, 34):
+        bs, fb, _ = ref_encode(yuv, 320, 192, 9, qp, 12.0, complexity=0)
+        gold["low"]["clip_qp%d" % qp] = {"sha1": hashlib.sha1(bs).hexdigest(), "frame_bytes": fb}
+    for (w, h, n, qp, seed, noise) in LOW_CASES:
+        y = h264lib.synth_clip(w, h, n, seed=seed, noise=noise)
+        bs, fb, _ = ref_encode(y, w, h, n, qp, 30.0, complexity=0)
+        gold["low"]["%dx%d_n%d_qp%d_seed%d_noise%d" % (w, h, n, qp, seed, noise)] = {"sha1": hashlib.sha1(bs).hexdigest(), "frame_bytes": fb}
     json.dump(gold, open(os.path.join(HERE, "encoder_edge.json"), "w"), indent=1, sort_keys=True)
     print(json.dumps(gold, indent=1))

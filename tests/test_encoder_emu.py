@@ -28,7 +28,8 @@ def emu():
     return E
 
 
-def emu_encode(E, yuv, w, h, n, qp, fps):
+def emu_encode(E, yuv, w, h, n, qp, fps, low=False):
+    E.emu_set_complexity_low(1 if low else 0)
     cap = 32 << 20
     out, fb = np.zeros(cap, np.uint8), np.zeros(n, np.int32)
     tot = E.emu_encode(yuv.ctypes.data, w, h, n, qp, fps, out.ctypes.data, cap, fb.ctypes.data, None)
@@ -110,3 +111,24 @@ def test_emu_matches_reference_on_other_reference_clips(emu):
         ran += 1
     if not ran:
         pytest.skip("no reference clips on this machine")
+
+
+EDGE = json.load(open(os.path.join(ROOT, "tests", "golden", "encoder_edge.json")))
+
+
+@pytest.mark.parametrize("key", sorted(EDGE["low"]))
+def test_emu_low_complexity_matches_reference_golden(emu, key):
+    """LOW_COMPLEXITY (SAD mode costs, VAA-driven partitions, pruned I4x4 search) in the host build of the macroblock source
+    against goldens generated from the unmodified reference at iComplexityMode = LOW_COMPLEXITY"""
+    import numpy as np
+    g = EDGE["low"][key]
+    if key.startswith("clip"):
+        w, h, n, qp, fps = 320, 192, 9, int(key.split("qp")[1]), 12.0
+        yuv = np.fromfile(os.path.join(ROOT, "tests", "golden", "CiscoVT2people_320x192_12fps.yuv"), dtype=np.uint8)
+    else:
+        w, h = map(int, key.split("_")[0].split("x"))
+        n, qp = int(key.split("_n")[1].split("_")[0]), int(key.split("_qp")[1].split("_")[0])
+        yuv = h264lib.synth_clip(w, h, n, seed=int(key.split("_seed")[1].split("_")[0]), noise=int(key.split("_noise")[1]))
+        fps = 30.0
+    bs, fb = emu_encode(emu, yuv, w, h, n, qp, fps, low=True)
+    assert fb == g["frame_bytes"] and hashlib.sha1(bs).hexdigest() == g["sha1"]

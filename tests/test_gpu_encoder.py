@@ -199,3 +199,29 @@ def test_device_cavlc_bit_count_is_exact():
                 assert int(host.sum()) <= 8 * len(bs[s])
         assert coded > 0
         enc.close()
+
+
+@pytest.mark.parametrize("key", sorted(EDGE["low"]))
+def test_low_complexity_through_cuda(key):
+    """iComplexityMode = LOW_COMPLEXITY (the reference's default and what SURVEY 8d defines BASELINE configs[1] on): SAD
+    mode costs, VAA statistics kernel (8x8 SADs against the previous source picture) driving the partition search, pruned
+    I4x4 search; golden = the unmodified reference at LOW_COMPLEXITY."""
+    from openh264_b200.binding import BatchEncoder
+    g = EDGE["low"][key]
+    if key.startswith("clip"):
+        w, h, n, qp, fps = 320, 192, 9, int(key.split("qp")[1]), 12.0
+        yuv = np.fromfile(os.path.join(ROOT, "tests", "golden", "CiscoVT2people_320x192_12fps.yuv"), dtype=np.uint8)
+    else:
+        w, h = map(int, key.split("_")[0].split("x"))
+        n, qp = int(key.split("_n")[1].split("_")[0]), int(key.split("_qp")[1].split("_")[0])
+        yuv = h264lib.synth_clip(w, h, n, seed=int(key.split("_seed")[1].split("_")[0]), noise=int(key.split("_noise")[1]))
+        fps = 30.0
+    enc = BatchEncoder(w, h, qp=qp, fps=fps, n_streams=2, complexity_low=True)
+    fsz = w * h * 3 // 2
+    out = [[], []]
+    for f in range(n):
+        bs, _ = enc.encode([yuv[f * fsz:(f + 1) * fsz]] * 2)
+        out[0].append(bs[0]); out[1].append(bs[1])
+    enc.close()
+    assert [len(b) for b in out[0]] == g["frame_bytes"]
+    assert hashlib.sha1(b"".join(out[0])).hexdigest() == g["sha1"] and out[1] == out[0]

@@ -2,7 +2,8 @@
 # builds the product libraries into /tmp and moves them into place atomically (a gpurun snapshot may be taken at any time)
 set -e
 cd /root/repo/openh264_b200/csrc
-make -s -j8 OUT=/tmp/libopenh264_b200.so.new 2>&1 | grep -v "Warray-bounds\|cavlc_tables.h\|match_code\|tbl\[i\]\|note:\|In function\|inlined from\|^\s*[0-9]* |\|^\s*|\|In file included" || true
+rm -f /tmp/libopenh264_b200.so.new
+make -s -j8 OUT=/tmp/libopenh264_b200.so.new > /tmp/build_atomic.log 2>&1 || { grep -B2 -A8 "error" /tmp/build_atomic.log | head -60; echo BUILD FAILED; exit 1; }
 test -f /tmp/libopenh264_b200.so.new
 cp /tmp/libopenh264_b200.so.new ../libopenh264_b200.so.tmp && mv ../libopenh264_b200.so.tmp ../libopenh264_b200.so
 if [ -d /root/reference/codec ]; then

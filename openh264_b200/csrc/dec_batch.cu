@@ -29,11 +29,14 @@ struct b2h264_dec {
   std::vector<ParserState> parser;
   std::vector<uint8_t> stream_rec;        // per stream: which of its two pictures is written next
   std::vector<int> act;
+  std::vector<uint8_t> act_ref;           // is the picture of act[i] a reference picture
   cudaStream_t st = nullptr;
   uint8_t* d_pic[2] = {nullptr, nullptr};
   MbInfo* d_mbi = nullptr;
   MbOut* d_recs = nullptr;
   MbOut* h_recs = nullptr;                // pinned
+  DecMbAux* d_aux = nullptr;
+  DecMbAux* h_aux = nullptr;              // pinned
   StreamFrame* d_sf = nullptr;
   StreamFrame* h_sf = nullptr;            // pinned
   int* d_ws = nullptr;
@@ -76,6 +79,8 @@ int b2h264_dec_create(const b2h264_dec_config* cfg, b2h264_dec** out) {
   CK(cudaMemset(d->d_mbi, 0, S * d->n_mb * sizeof(MbInfo)));
   CK(cudaMalloc(&d->d_recs, S * d->n_mb * sizeof(MbOut)));
   CK(cudaMallocHost(&d->h_recs, S * d->n_mb * sizeof(MbOut)));
+  CK(cudaMalloc(&d->d_aux, S * d->n_mb * sizeof(DecMbAux)));
+  CK(cudaMallocHost(&d->h_aux, S * d->n_mb * sizeof(DecMbAux)));
   CK(cudaMalloc(&d->d_sf, S * sizeof(StreamFrame)));
   CK(cudaMallocHost(&d->h_sf, S * sizeof(StreamFrame)));
   CK(cudaMalloc(&d->d_ws, dec_sched_ints((int)S, d->n_mb) * sizeof(int)));
@@ -88,7 +93,7 @@ void b2h264_dec_destroy(b2h264_dec* d) {
   cudaSetDevice(d->cfg.device);
   if (d->st) cudaStreamSynchronize(d->st);
   for (int i = 0; i < 2; i++) cudaFree(d->d_pic[i]);
-  cudaFree(d->d_mbi); cudaFree(d->d_recs); cudaFree(d->d_sf); cudaFree(d->d_ws);
+  cudaFree(d->d_mbi); cudaFree(d->d_recs); cudaFree(d->d_aux); cudaFreeHost(d->h_aux); cudaFree(d->d_sf); cudaFree(d->d_ws);
   cudaFreeHost(d->h_recs); cudaFreeHost(d->h_sf);
   if (d->st) cudaStreamDestroy(d->st);
   delete d;
@@ -101,7 +106,7 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
   CK(cudaSetDevice(d->cfg.device));
   const int S = d->S;
   int deblock = 1;
-  d->act.clear();
+  d->act.clear(); d->act_ref.clear();
   for (int s = 0; s < S; s++) {
     if (got_picture) got_picture[s] = 0;
     if (!au[s] || au_bytes[s] <= 0) {
@@ -115,17 +120,18 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
     const StreamParams& sp = d->parser[s].sp;
     if (sp.mb_w != d->mb_w || sp.mb_h != d->mb_h || sp.width != d->cfg.width || sp.height != d->cfg.height) { d->last_error_stream = s; return -2; }
     if ((int)pic.mbs.size() != d->n_mb) { d->last_error_stream = s; return -103; }
-    const int want_deblock = pic.disable_deblocking_idc != 1;
-    if (d->act.empty()) deblock = want_deblock;
-    else if (want_deblock != deblock) { d->last_error_stream = s; return -2; }   // one setting per batch
+    if ((int)pic.aux.size() != d->n_mb) { d->last_error_stream = s; return -103; }
+    if (d->act.empty()) deblock = 0;
+    if (pic.any_deblock) deblock = 1;               // the filter kernel runs if any slice of any stream wants it (per-MB control inside)
     const int i = (int)d->act.size();
-    d->act.push_back(s);
+    d->act.push_back(s); d->act_ref.push_back(pic.is_ref ? 1 : 0);
     memcpy(d->h_recs + (size_t)i * d->n_mb, pic.mbs.data(), (size_t)d->n_mb * sizeof(MbOut));
+    memcpy(d->h_aux + (size_t)i * d->n_mb, pic.aux.data(), (size_t)d->n_mb * sizeof(DecMbAux));
     StreamFrame& F = d->h_sf[i];
     memset(&F, 0, sizeof(F));
     F.p.mb_w = d->mb_w; F.p.mb_h = d->mb_h;
     F.p.rec_stride_y = d->geo.rec_stride_y(); F.p.rec_stride_c = d->geo.rec_stride_c();
-    F.p.qp = pic.ss.qp; F.p.is_idr = pic.ss.idr; F.p.ref_is_p = !pic.ss.idr; F.p.mv_range = 64;
+    F.p.qp = pic.ss.qp; F.p.is_idr = pic.ss.idr; F.p.ref_is_p = !pic.ss.idr; F.p.mv_range = 64; F.p.dec_mode = 1;
     const int rec = d->stream_rec[s];
     for (int pl = 0; pl < 3; pl++) { F.f.rec[pl] = d->plane0(rec, s, pl); F.f.ref[pl] = d->plane0(1 - rec, s, pl); }
     F.f.mbi = d->d_mbi + (size_t)s * d->n_mb;
@@ -133,8 +139,9 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
   const int n = (int)d->act.size();
   if (n == 0) return 0;
   CK(cudaMemcpyAsync(d->d_recs, d->h_recs, (size_t)n * d->n_mb * sizeof(MbOut), cudaMemcpyHostToDevice, d->st));
+  CK(cudaMemcpyAsync(d->d_aux, d->h_aux, (size_t)n * d->n_mb * sizeof(DecMbAux), cudaMemcpyHostToDevice, d->st));
   CK(cudaMemcpyAsync(d->d_sf, d->h_sf, (size_t)n * sizeof(StreamFrame), cudaMemcpyHostToDevice, d->st));
-  const int rc = dec_launch_frame(d->d_sf, n, d->mb_w, d->mb_h, d->d_ws, d->d_recs, deblock, d->st);
+  const int rc = dec_launch_frame(d->d_sf, n, d->mb_w, d->mb_h, d->d_ws, d->d_recs, d->d_aux, deblock, d->st);
   if (rc) return rc;
   const int w = d->cfg.width, h = d->cfg.height;
   for (int i = 0; i < n; i++) {
@@ -146,7 +153,7 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
       CK(cudaMemcpy2DAsync(dst, pw, d->plane0(rec, s, pl), stp, pw, ph, cudaMemcpyDeviceToHost, d->st));
       dst += (size_t)pw * ph;
     }
-    d->stream_rec[s] ^= 1;
+    if (d->act_ref[i]) d->stream_rec[s] ^= 1;       // a non-reference picture leaves the reference where it is
     if (got_picture) got_picture[s] = 1;
   }
   CK(cudaStreamSynchronize(d->st));

@@ -7,7 +7,7 @@
 // Reference counterparts: codec/decoder/core/src/rec_mb.cpp (BaseMC :244, GetInterPred :462, RecI4x4Mb / RecI16x16Mb
 // :64-215), decode_mb_aux.cpp (IdctResAddPred_c :42), mv_pred.cpp (PredMv, PredPSkipMvFromNeighbor), parse side
 // ParseIntra4x4Mode (parse_mb_syn_cavlc.cpp).
-// STATUS: groundwork — host build only this round (the device kernel that batches it is the next step).
+// Runs on the device as k_decode_mbs (enc_kernels.cu) and, compiled for the host, as the debugging build of tests/emu.
 #pragma once
 #include "enc_inter.cuh"
 
@@ -70,9 +70,10 @@ MBK_HD void dec_chroma_coef(MbScratch& s, const MbOut& m, int qp_c) {
 
 // One macroblock.  f.rec = picture being reconstructed, f.ref = reference picture (padded), f.mbi = MbInfo array of
 // the picture (neighbour lookups + what deblocking reads).  Raster / wavefront order like the encoder.
-MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch& s, int mbx, int mby, const MbOut& m) {
+MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch& s, int mbx, int mby, const MbOut& m, const DecMbAux& aux) {
   mb_ctx(s.ctx, p, f, mbx, mby);
-  if (lane_id() == 0) { s.ctx.qp = m.qp; s.ctx.qp_c = tbl_chroma_qp(m.qp); }
+  // neighbour availability comes from the parser: macroblocks of other slices do not count (6.4.x)
+  if (lane_id() == 0) { s.ctx.qp = m.qp; s.ctx.qp_c = tbl_chroma_qp(m.qp); s.ctx.nb = aux.avail; }
   warp_sync();
   const MbCtx& c = s.ctx;
   {
@@ -91,8 +92,47 @@ MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch
   warp_sync();
   uint8_t* pl = s.pred_y[0];
   uint8_t* pc = s.pred_c[0];
-  const bool L = (c.nb & NB_LEFT) != 0, T = (c.nb & NB_TOP) != 0;
-  if (MBT_IS_INTER(type)) {
+  // constrained intra prediction: inter-coded neighbours do not count for INTRA prediction (8.3.1.2, 8.3.3, 8.3.4)
+  int nb_i = c.nb;
+  if (aux.flags & DECAUX_CIP) {
+    if ((nb_i & NB_TOPLEFT) && MBT_IS_INTER(s.nbi[0].mb_type)) nb_i &= ~NB_TOPLEFT;
+    if ((nb_i & NB_TOP) && MBT_IS_INTER(s.nbi[1].mb_type)) nb_i &= ~NB_TOP;
+    if ((nb_i & NB_TOPRIGHT) && MBT_IS_INTER(s.nbi[2].mb_type)) nb_i &= ~NB_TOPRIGHT;
+    if ((nb_i & NB_LEFT) && MBT_IS_INTER(s.nbi[3].mb_type)) nb_i &= ~NB_LEFT;
+  }
+  const bool L = (nb_i & NB_LEFT) != 0, T = (nb_i & NB_TOP) != 0;
+  if (type == MBT_P8x8 && (aux.flags & DECAUX_SUB)) {
+    // sub-macroblock partitions (8x4, 4x8, 4x4): every partition predicts its vector from the cells decoded so far —
+    // the in-macroblock cells start as "not available" and are filled in decoding order (8.4.1.3.2: a partition that
+    // comes later in decoding order is not available as neighbour C, the top-left neighbour D steps in)
+    fill_inter_cache(c, s);
+    if (lane_id() == 0)
+      for (int r = 1; r < 5; r++) for (int q = 1; q < 5; q++) s.refc[r * 6 + q] = REF_NOT_AVAIL;
+    warp_sync();
+    for (int k = 0; k < 4; k++) {
+      const int st = aux.sub_type[k];
+      const int w4 = (st == 0 || st == 1) ? 2 : 1, h4 = (st == 0 || st == 2) ? 2 : 1, np = st == 0 ? 1 : st == 3 ? 4 : 2;
+      for (int j = 0; j < np; j++) {
+        const int blk = 4 * k + (st == 1 ? 2 * j : j);           // 8x4: rows of the 8x8; 4x8 / 4x4: blocks in coding order
+        int px, py;
+        pred_mv(s, blk, w4, 0, &px, &py);
+        const int mvx = px + aux.mvd[4 * k + j][0], mvy = py + aux.mvd[4 * k + j][1];
+        cache_set(s, blk, w4, h4, mvx, mvy);
+        mb_mv_set(s, blk, w4, h4, mvx, mvy);
+        const int ox = blk_x(blk) * 4, oy = blk_y(blk) * 4, w = w4 * 4, h = h4 * 4;
+        int fx = ((c.mbx * 16 + ox) << 2) + mvx, fy = ((c.mby * 16 + oy) << 2) + mvy;
+        fx = clip3(fx, (-32 + 2) * 4, (c.p.mb_w * 16 + 32 - 19) * 4);
+        fy = clip3(fy, (-32 + 2) * 4, (c.p.mb_h * 16 + 32 - 19) * 4);
+        warp_mc_luma(c.f.ref[0] + (ptrdiff_t)(fy >> 2) * c.p.rec_stride_y + (fx >> 2), c.p.rec_stride_y, pl + oy * 16 + ox, 16, fx, fy, w, h);
+        for (int cpl = 0; cpl < 2; cpl++)
+          warp_mc_chroma(c.f.ref[1 + cpl] + (ptrdiff_t)(fy >> 3) * c.p.rec_stride_c + (fx >> 3), c.p.rec_stride_c,
+                         pc + 64 * cpl + (oy >> 1) * 8 + (ox >> 1), 8, fx, fy, w >> 1, h >> 1);
+        warp_sync();
+      }
+    }
+    dec_luma_coef(s, m, qp, false, nullptr);
+    rec_luma_inter(s, pl);
+  } else if (MBT_IS_INTER(type)) {
     fill_inter_cache(c, s);
     const int nparts = type == MBT_P8x8 ? 4 : (type == MBT_P16x8 || type == MBT_P8x16) ? 2 : 1;
     if (type == MBT_P8x8) { if (lane_id() == 0) { s.refc[9] = s.refc[21] = REF_NOT_AVAIL; } warp_sync(); }
@@ -137,13 +177,20 @@ MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch
     rec_luma_inter(s, pl);                       // inverse transform + prediction for all 16 blocks
   } else {                                       // I4x4: block by block, each predicts from what was just reconstructed
     fill_i4_cache(c, s);
+    if (aux.flags & DECAUX_CIP) {              // 8.3.1.1: an Inter neighbour under constrained_intra_pred forces the DC prediction of the
+      if (lane_id() == 0) {                    // mode (dcPredModePredictedFlag), exactly like a missing neighbour — not "mode 2 in the min"
+        if ((c.nb & NB_LEFT) && MBT_IS_INTER(s.nbi[3].mb_type)) for (int y = 0; y < 4; y++) s.i4m[(y + 1) * 5] = -1;
+        if ((c.nb & NB_TOP) && MBT_IS_INTER(s.nbi[1].mb_type)) for (int x = 0; x < 4; x++) s.i4m[x + 1] = -1;
+      }
+      warp_sync();
+    }
     for (int k = 0; k < 16; k++) {
       const int bx = blk_x(k), by = blk_y(k);
       uint8_t* org = tile_y(s.tile, bx * 4, by * 4);
       const int lm = s.i4m[(by + 1) * 5 + bx], tm = s.i4m[by * 5 + bx + 1];
       const int pm = (lm == -1 || tm == -1) ? 2 : (lm < tm ? lm : tm);
       const int coded = m.prev_i4_flag[k] ? pm : (m.rem_i4_mode[k] < pm ? m.rem_i4_mode[k] : m.rem_i4_mode[k] + 1);
-      const int av = i4_avail(c.nb, k);
+      const int av = i4_avail(nb_i, k);
       const int mode = coded == 2 ? ((av & 1) && (av & 2) ? I4_DC : (av & 1) ? I4_DC_L : (av & 2) ? I4_DC_T : I4_DC_128) : coded;
       if (lane_id() == 0) {
         s.i4m[(by + 1) * 5 + bx + 1] = (int8_t)coded;
@@ -173,7 +220,12 @@ MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch
   rec_chroma(s, pc);
   mb_store_recon(c, s);
   // what the neighbours and the deblocking filter read
-  if (lane_id() == 0) { s.info.qp = (uint8_t)qp; s.info.qp_c = (uint8_t)qp_c; }
+  if (lane_id() == 0) {
+    s.info.qp = (uint8_t)qp; s.info.qp_c = (uint8_t)qp_c;
+    // the decoder has no use for sP16x16Mv: the field carries what the deblocking pass needs to know about the slice
+    s.info.p16x16_mv[0] = (int16_t)aux.slice;
+    s.info.p16x16_mv[1] = (int16_t)(aux.dbk_idc | ((aux.alpha_off + 16) << 2) | ((aux.beta_off + 16) << 7));
+  }
   warp_sync();
   const uint32_t* si = reinterpret_cast<const uint32_t*>(&s.info);
   uint32_t* di = reinterpret_cast<uint32_t*>(c.f.mbi + (mby * p.mb_w + mbx));

@@ -82,8 +82,16 @@ MBK_HD void deblock_one_mb(const EncFrameParams& p, const EncFramePtrs& f, int m
   warp_sync();
   const MbInfo* cur = &t.m[0];
   uint8_t* ty = t.y + 4 * DBK_PY + 4;
-  for (int dir = 0; dir < 2; dir++) {
-    const bool have_nb = dir == 0 ? mbx > 0 : mby > 0;
+  // decoder: per-slice control travels in MbInfo::p16x16_mv (dec_mb.cuh): disable_deblocking_filter_idc, FilterOffsetA / B and the
+  // slice number (idc 2: edges between slices stay unfiltered).  The encoder path always filters with offsets 0.
+  int idc = 0, off_a = 0, off_b = 0;
+  if (p.dec_mode) {
+    const int v = (uint16_t)cur->p16x16_mv[1];
+    idc = v & 3; off_a = ((v >> 2) & 31) - 16; off_b = ((v >> 7) & 31) - 16;
+  }
+  for (int dir = 0; dir < 2 && idc != 1; dir++) {
+    bool have_nb = dir == 0 ? mbx > 0 : mby > 0;
+    if (have_nb && idc == 2 && t.m[1 + dir].p16x16_mv[0] != cur->p16x16_mv[0]) have_nb = false;
     const MbInfo* nbm = dir == 0 ? &t.m[1] : &t.m[2];
     for (int edge = 0; edge < 4; edge++) {
       if (edge == 0 && !have_nb) continue;
@@ -96,21 +104,23 @@ MBK_HD void deblock_one_mb(const EncFrameParams& p, const EncFramePtrs& f, int m
       // lanes 0..15: one luma line each; lanes 16..31 (device) / the same loop (host): the 8 + 8 chroma lines
       for (int l = lane_id(); l < 32; l += MBK_WS) {
         if (l < 16) {
-          const int a = tbl_alpha(qp_y), b = tbl_beta(qp_y);      // slice alpha/beta offsets are 0
+          const int ia = clip3(qp_y + off_a, 0, 51), ib = clip3(qp_y + off_b, 0, 51);
+          const int a = tbl_alpha(ia), b = tbl_beta(ib);
           if (a | b) {
             uint8_t* px = ty + (dir == 0 ? 4 * edge + l * DBK_PY : 4 * edge * DBK_PY + l);
             const int sx = dir == 0 ? 1 : DBK_PY;
             if (bs[0] == 4) deblock_luma_eq4_line<false>(px, sx, a, b);
-            else deblock_luma_lt4_line<false>(px, sx, a, b, tbl_tc0(qp_y, bs[l >> 2]));
+            else deblock_luma_lt4_line<false>(px, sx, a, b, tbl_tc0(ia, bs[l >> 2]));
           }
         } else if (!(edge & 1)) {                                  // chroma: edges 0 and 2 only
-          const int a = tbl_alpha(qp_c), b = tbl_beta(qp_c);
+          const int ia = clip3(qp_c + off_a, 0, 51), ib = clip3(qp_c + off_b, 0, 51);
+          const int a = tbl_alpha(ia), b = tbl_beta(ib);
           if (a | b) {
             const int k = l - 16, ln = k & 7;
             uint8_t* px = t.c[k >> 3] + 4 * DBK_PC + 4 + (dir == 0 ? 2 * edge + ln * DBK_PC : 2 * edge * DBK_PC + ln);
             const int sx = dir == 0 ? 1 : DBK_PC;
             if (bs[0] == 4) deblock_chroma_eq4_line<false>(px, sx, a, b);
-            else deblock_chroma_lt4_line<false>(px, sx, a, b, tbl_tc0(qp_c, bs[ln >> 1]) + 1);
+            else deblock_chroma_lt4_line<false>(px, sx, a, b, tbl_tc0(ia, bs[ln >> 1]) + 1);
           }
         }
       }

@@ -374,12 +374,13 @@ __global__ void __launch_bounds__(32 * ENC_WPC) k_deblock_mbs(const StreamFrame*
 // One warp reconstructs one macroblock from its parsed record (h264_parse.h); the macroblocks of all streams are
 // scheduled by the same dependency rule as the encoder (left + top-right done), with the simple per-warp ready list.
 __global__ void __launch_bounds__(32 * ENC_WPC) k_decode_mbs(const StreamFrame* __restrict__ sf, int n_streams, Sched q,
-                                                            const MbOut* __restrict__ recs) {
+                                                            const MbOut* __restrict__ recs, const DecMbAux* __restrict__ aux) {
   extern __shared__ __align__(128) uint8_t smem[];
   MbScratch& s = my_scratch(smem);
   run_mbs(sf, n_streams, q, [&](const StreamFrame& F, int x, int y) {
     const int n_mb = F.p.mb_w * F.p.mb_h, si = (int)(&F - sf);
-    dec_one_mb(F.p, F.f, s, x, y, recs[(size_t)si * n_mb + y * F.p.mb_w + x]);
+    const size_t r = (size_t)si * n_mb + y * F.p.mb_w + x;
+    dec_one_mb(F.p, F.f, s, x, y, recs[r], aux[r]);
   });
 }
 
@@ -543,7 +544,7 @@ static Sched make_dec_sched(int* ws, int which, int total) {
   q.queue = ws + 8 + (size_t)(2 + which) * total;
   return q;
 }
-int dec_launch_frame(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h, int* d_ws, const MbOut* d_recs, int deblock,
+int dec_launch_frame(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h, int* d_ws, const MbOut* d_recs, const DecMbAux* d_aux, int deblock,
                      cudaStream_t st) {
   const int blocks_per_launch = dec_grid_blocks();
   int rc;
@@ -554,7 +555,7 @@ int dec_launch_frame(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h,
   k_sched_init<<<(n_streams + 127) / 128, 128, 0, st>>>(qc, n_streams, mb_w * mb_h);
   k_sched_init<<<(n_streams + 127) / 128, 128, 0, st>>>(qd, n_streams, mb_w * mb_h);
   const int need = (total + ENC_WPC - 1) / ENC_WPC;
-  k_decode_mbs<<<blocks_per_launch < need ? blocks_per_launch : need, 32 * ENC_WPC, kScratchSmem, st>>>(d_sf, n_streams, qc, d_recs);
+  k_decode_mbs<<<blocks_per_launch < need ? blocks_per_launch : need, 32 * ENC_WPC, kScratchSmem, st>>>(d_sf, n_streams, qc, d_recs, d_aux);
   if ((rc = b2h264_launched())) return rc;
   if (deblock) {
     int blocks = enc_grid_blocks() * 2;

@@ -51,6 +51,22 @@ typedef struct {
   int16_t chroma_dc[2][4];
   int16_t chroma_ac[8][16];               // Cb 0..3, Cr 4..7
 } MbOut;                                  // 8+32+16+24+32+512+16+256 = 896 bytes
+/* Decoder only: what the parser knows about a macroblock beyond MbOut (slices, sub-macroblock partitions, deblocking control).
+ * One record per macroblock next to the MbOut array (h264_parse.h -> dec_mb.cuh / enc_deblock.cuh). */
+typedef struct {
+  uint8_t avail;                          // NB_LEFT | NB_TOP | NB_TOPLEFT | NB_TOPRIGHT: neighbours in the SAME slice (6.4.x availability)
+  uint8_t flags;                          // bit 0: sub_type / mvd[16] below are used; bit 1: constrained_intra_pred_flag
+  uint8_t dbk_idc;                        // disable_deblocking_filter_idc of the macroblock's slice
+  int8_t  alpha_off, beta_off;            // FilterOffsetA / FilterOffsetB (already x2)
+  uint8_t pad;
+  uint16_t slice;                         // slice number inside the picture
+  uint8_t sub_type[4];                    // per 8x8: 0 8x8, 1 8x4, 2 4x8, 3 4x4
+  int8_t  ref_idx[4];                     // per 8x8 (0: one reference picture)
+  int16_t mvd[16][2];                     // sub-macroblock partition j of 8x8 k at [4 * k + j]
+} DecMbAux;                               // 16 + 64 = 80 bytes
+#define DECAUX_SUB 1
+#define DECAUX_CIP 2
+
 #define MBOUT_HEADER_WORDS 20             /* mb_type .. nnz: all a P_SKIP macroblock needs to hand over */
 
 typedef struct {
@@ -62,6 +78,7 @@ typedef struct {
   int32_t mv_range;                       // iMvRange (integer pel)
   int32_t ref_is_p;                       // reference picture was coded as P (temporal candidates valid)
   int32_t ref_plane;                      // z coordinate of the stream's reference picture in the encoder's luma tensor map
+  int32_t dec_mode;                       // 1: decoder construct path (MbInfo::p16x16_mv carries slice / deblocking control)
   int32_t fast_mode;                      // iComplexityMode == LOW_COMPLEXITY: SAD mode costs, VAA-driven partition choice
                                           // (SetFastCodingFunc / WelsMdInterFinePartitionVaa, encoder_ext.cpp:2616,2688)
 } EncFrameParams;
@@ -78,6 +95,7 @@ typedef struct {
                                           // (encoder_ext.cpp:1675): a decided-skip MB keeps its older value
   const int32_t* vaa_sad8x8;              // fast mode: SAD of the four 8x8 blocks of every macroblock against the PREVIOUS
                                           // SOURCE picture (VAACalcSad_c), indexed like the reference: [iMbXY * 4 + k]
+  const DecMbAux* dec_aux;                // decoder: per-macroblock side records (NULL in the encoder)
   const uint8_t* prev_luma;               // fast mode: luma of the previous SOURCE picture (same layout as cur[0])
   int32_t* mb_bits;                       // optional (NULL = off): exact CAVLC bits of every macroblock (enc_cavlc_bits.cuh)
 } EncFramePtrs;

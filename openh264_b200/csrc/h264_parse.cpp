@@ -10,7 +10,12 @@
 
 namespace b2h264 {
 
+int g_reject_line = 0;      // source line of the last rejection (diagnostics: why a stream is outside the supported class)
+
 namespace {
+#define PARSE_UNSUPPORTED (g_reject_line = __LINE__, b2h264::PARSE_UNSUPPORTED)
+#define PARSE_INVALID (g_reject_line = __LINE__, b2h264::PARSE_INVALID)
+
 
 class BitReader {
  public:
@@ -96,7 +101,15 @@ int parse_sps(BitReader& r, ParserState* st) {
     const uint32_t v = r.ue();
     if (v > 12) return PARSE_INVALID;
     st->log2_max_poc_lsb = (int)v + 4;
-  } else if (st->poc_type != 2) return PARSE_UNSUPPORTED;
+  } else if (st->poc_type == 1) {
+    // picture order count type 1 (7.3.2.1.1): only parsed — pictures leave the decoder in decoding order (no B slices in this
+    // stream class, so that is also the output order)
+    st->delta_pic_order_always_zero = r.bit() != 0;
+    r.se(); r.se();                                       // offset_for_non_ref_pic, offset_for_top_to_bottom_field
+    const uint32_t n_cycle = r.ue();
+    if (n_cycle > 255) return PARSE_INVALID;
+    for (uint32_t i = 0; i < n_cycle; i++) r.se();
+  } else if (st->poc_type != 2) return PARSE_INVALID;
   StreamParams sp;
   memset(&sp, 0, sizeof(sp));
   sp.num_ref_frames = (int)r.ue();
@@ -116,7 +129,7 @@ int parse_sps(BitReader& r, ParserState* st) {
   if (sp.mb_w < 1 || sp.mb_h < 1 || sp.mb_w > 512 || sp.mb_h > 512 || sp.num_ref_frames > 16) return PARSE_INVALID;
   sp.width = sp.mb_w * 16 - 2 * (cl + sp.crop_right);
   sp.height = sp.mb_h * 16 - 2 * (ct + sp.crop_bottom);
-  if (sp.width <= (sp.mb_w - 1) * 16 || sp.height <= (sp.mb_h - 1) * 16) return PARSE_INVALID;   // cropping may only cut into the last MB
+  if (sp.width < 2 || sp.height < 2) return PARSE_INVALID;
   sp.level_idc = level;
   sp.sps_id = sps_id;
   if (cl || ct) return PARSE_UNSUPPORTED;     // left / top cropping: never produced by the encoders this mirrors
@@ -142,7 +155,7 @@ int parse_pps(BitReader& r, ParserState* st) {
   r.se();
   if (r.se() != 0) return PARSE_UNSUPPORTED;  // chroma_qp_index_offset
   st->deblocking_control = r.bit() != 0;
-  if (r.bit()) return PARSE_UNSUPPORTED;      // constrained_intra_pred_flag
+  st->constrained_intra_pred = r.bit() != 0;
   if (r.bit()) return PARSE_UNSUPPORTED;      // redundant_pic_cnt_present_flag
   if (bottom_field_poc) return PARSE_UNSUPPORTED;
   if (!r.ok()) return PARSE_TRUNCATED;
@@ -249,17 +262,21 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
   if (!st->have_sps || !st->have_pps) return PARSE_NO_PARAMETER_SETS;
   const bool idr = nal.type == 5;
   if (!idr && !st->have_ref) return PARSE_INVALID;            // a P picture before any IDR: nothing to predict from
-  if (r.ue() != 0) return PARSE_UNSUPPORTED;                  // first_mb_in_slice: one slice per picture
+  const int mbw = st->sp.mb_w, n = st->sp.mb_w * st->sp.mb_h;
+  const bool first_slice = pic->n_slices == 0;
+  const int first_mb = (int)r.ue();
+  if (first_mb != pic->next_mb) return PARSE_UNSUPPORTED;     // slices out of raster order / missing slices (ASO, FMO, losses)
   const int slice_type = (int)r.ue() % 5;
   if (slice_type != 0 && slice_type != 2) return PARSE_UNSUPPORTED;
   const bool is_p = slice_type == 0;
   if (idr && is_p) return PARSE_INVALID;
   if ((int)r.ue() != st->sp.pps_id) return PARSE_NO_PARAMETER_SETS;
-  SliceState& ss = pic->ss;
+  SliceState ss;
   ss.idr = idr;
   ss.frame_num = (int)r.get(st->log2_max_frame_num);
   ss.idr_pic_id = idr ? (int)r.ue() : 0;
   if (st->poc_type == 0) r.get(st->log2_max_poc_lsb);
+  else if (st->poc_type == 1 && !st->delta_pic_order_always_zero) r.se();          // delta_pic_order_cnt[0]
   if (is_p) {
     int n_ref = st->num_ref_idx_default;
     if (r.bit()) n_ref = (int)r.ue() + 1;
@@ -276,39 +293,68 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
       }
     }
   }
-  if (!nal.ref_idc) return PARSE_UNSUPPORTED;                 // non-reference pictures (temporal layers): needs a DPB
+  const bool is_ref = nal.ref_idc != 0;                       // a non-reference picture is output but never predicted from
   if (nal.ref_idc) {                                          // dec_ref_pic_marking
     if (idr) { r.bit(); if (r.bit()) return PARSE_UNSUPPORTED; }
     else if (r.bit()) return PARSE_UNSUPPORTED;               // adaptive marking (MMCO)
   }
   ss.qp = st->pic_init_qp + r.se();
-  pic->disable_deblocking_idc = 0;
+  int dbk_idc = 0, alpha_off = 0, beta_off = 0;
   if (st->deblocking_control) {
-    pic->disable_deblocking_idc = (int)r.ue();
-    if (pic->disable_deblocking_idc > 2) return PARSE_INVALID;
-    if (pic->disable_deblocking_idc != 1) { if (r.se() != 0 || r.se() != 0) return PARSE_UNSUPPORTED; }
+    dbk_idc = (int)r.ue();
+    if (dbk_idc > 2) return PARSE_INVALID;
+    if (dbk_idc != 1) {
+      alpha_off = 2 * r.se(); beta_off = 2 * r.se();
+      if (alpha_off < -12 || alpha_off > 12 || beta_off < -12 || beta_off > 12) return PARSE_INVALID;
+    }
   }
   if (!r.ok()) return PARSE_TRUNCATED;
   if (ss.qp < 0 || ss.qp > 51) return PARSE_INVALID;
   if (idr) { if (ss.frame_num != 0) return PARSE_INVALID; }
-  else if (ss.frame_num != ((st->last_frame_num + 1) & ((1 << st->log2_max_frame_num) - 1))) return PARSE_UNSUPPORTED;   // a gap: needs error concealment
+  else if (ss.frame_num != ((st->last_frame_num + 1) & ((1 << st->log2_max_frame_num) - 1))) return PARSE_UNSUPPORTED;   // a gap (7.4.3: frame_num
+                                                            // follows the last REFERENCE picture): needs error concealment
+  if (first_slice) {
+    pic->ss = ss;
+    pic->is_ref = is_ref;
+    pic->disable_deblocking_idc = dbk_idc;
+    pic->mbs.assign(n, MbOut());
+    for (MbOut& m : pic->mbs) { memset(&m, 0, sizeof(m)); m.mb_type = MBT_PSKIP; }
+    DecMbAux za;
+    memset(&za, 0, sizeof(za));
+    pic->aux.assign(n, za);
+  } else if (ss.idr != pic->ss.idr || ss.frame_num != pic->ss.frame_num || is_ref != pic->is_ref) {
+    return PARSE_INVALID;                                     // slices of one access unit must agree
+  }
+  if (pic->n_slices >= 65535) return PARSE_UNSUPPORTED;
+  const int slice_no = pic->n_slices++;
+  if (dbk_idc != 1) pic->any_deblock = true;
 
   // ---- slice data ----
-  const int mbw = st->sp.mb_w, n = st->sp.mb_w * st->sp.mb_h;
-  pic->mbs.assign(n, MbOut());
-  for (MbOut& m : pic->mbs) { memset(&m, 0, sizeof(m)); m.mb_type = MBT_PSKIP; }
+  auto same_slice = [&](int other) { return other >= first_mb; };          // raster-ordered slices: a neighbour is in this slice iff it is not before its start
   int qp = ss.qp;
-  int idx = 0;
+  int idx = first_mb;
   while (idx < n) {
     if (is_p) {
       const int run = (int)r.ue();
       if (!r.ok() || idx + run > n) return PARSE_INVALID;
-      for (int k = 0; k < run; k++) pic->mbs[idx++].qp = (uint8_t)qp;
-      if (idx == n) break;
-      if (!r.more_data()) return PARSE_INVALID;
+      for (int k = 0; k < run; k++, idx++) {
+        pic->mbs[idx].qp = (uint8_t)qp;
+        DecMbAux& a = pic->aux[idx];
+        a.slice = (uint16_t)slice_no; a.dbk_idc = (uint8_t)dbk_idc; a.alpha_off = (int8_t)alpha_off; a.beta_off = (int8_t)beta_off;
+        const int x = idx % mbw, y = idx / mbw;
+        a.avail = (uint8_t)((x > 0 && same_slice(idx - 1) ? 1 : 0) | (y > 0 && same_slice(idx - mbw) ? 2 : 0) |
+                            (x > 0 && y > 0 && same_slice(idx - mbw - 1) ? 4 : 0) | (y > 0 && x < mbw - 1 && same_slice(idx - mbw + 1) ? 8 : 0));
+      }
+      if (idx == n || !r.more_data()) break;                  // the slice may end with a skip run
     }
     MbOut& m = pic->mbs[idx];
+    DecMbAux& ax = pic->aux[idx];
     const int mbx = idx % mbw, mby = idx / mbw;
+    ax.slice = (uint16_t)slice_no; ax.dbk_idc = (uint8_t)dbk_idc; ax.alpha_off = (int8_t)alpha_off; ax.beta_off = (int8_t)beta_off;
+    ax.flags = st->constrained_intra_pred ? DECAUX_CIP : 0;
+    const bool avL = mbx > 0 && same_slice(idx - 1), avT = mby > 0 && same_slice(idx - mbw);
+    ax.avail = (uint8_t)((avL ? 1 : 0) | (avT ? 2 : 0) | (mbx > 0 && mby > 0 && same_slice(idx - mbw - 1) ? 4 : 0) |
+                         (mby > 0 && mbx < mbw - 1 && same_slice(idx - mbw + 1) ? 8 : 0));
     int t = (int)r.ue();
     bool intra = !is_p;
     if (is_p) {
@@ -320,11 +366,20 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
       else if (t == 1 || t == 2) {
         m.mb_type = t == 1 ? MBT_P16x8 : MBT_P8x16;
         for (int k = 0; k < 2; k++) { m.mvd[k][0] = (int16_t)r.se(); m.mvd[k][1] = (int16_t)r.se(); }
-      } else if (t == 3 || t == 4) {
-        if (t == 3) return PARSE_UNSUPPORTED;                 // P_8x8 with explicit reference indices
+      } else if (t == 3 || t == 4) {                          // P_8x8 / P_8x8ref0: with ONE active reference picture neither carries ref_idx
         m.mb_type = MBT_P8x8;
-        for (int k = 0; k < 4; k++) if (r.ue() != 0) return PARSE_UNSUPPORTED;   // sub-8x8 partitions
-        for (int k = 0; k < 4; k++) { m.mvd[k][0] = (int16_t)r.se(); m.mvd[k][1] = (int16_t)r.se(); }
+        bool sub = false;
+        for (int k = 0; k < 4; k++) {
+          const uint32_t v = r.ue();
+          if (v > 3) return PARSE_INVALID;
+          ax.sub_type[k] = (uint8_t)v;
+          sub = sub || v != 0;
+        }
+        static const int kParts[4] = {1, 2, 2, 4};
+        for (int k = 0; k < 4; k++)
+          for (int j = 0; j < kParts[ax.sub_type[k]]; j++) { ax.mvd[4 * k + j][0] = (int16_t)r.se(); ax.mvd[4 * k + j][1] = (int16_t)r.se(); }
+        if (sub) ax.flags |= DECAUX_SUB;
+        else for (int k = 0; k < 4; k++) { m.mvd[k][0] = ax.mvd[4 * k][0]; m.mvd[k][1] = ax.mvd[4 * k][1]; }
       } else return PARSE_INVALID;
     } else {
       if (t == 0) {
@@ -339,8 +394,8 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
         m.chroma_mode = (uint8_t)r.ue();
       } else return PARSE_UNSUPPORTED;                        // I_PCM
       if (m.chroma_mode > 3) return PARSE_INVALID;
-      {                                                       // prediction modes must have their neighbours (8.3.3, 8.3.4)
-        const bool L = mbx > 0, T = mby > 0;
+      if (!st->constrained_intra_pred) {                      // prediction modes must have their neighbours (8.3.3, 8.3.4); with
+        const bool L = avL, T = avT;                          // constrained intra prediction the construct stage knows which count
         if ((m.chroma_mode == 1 && !L) || (m.chroma_mode == 2 && !T) || (m.chroma_mode == 3 && !(L && T))) return PARSE_INVALID;
         if (m.mb_type == MBT_I16x16 &&
             ((m.i16_mode == 0 && !T) || (m.i16_mode == 1 && !L) || (m.i16_mode == 3 && !(L && T)))) return PARSE_INVALID;
@@ -353,10 +408,11 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     m.cbp = (uint8_t)cbp;
     const int cbp_l = cbp & 15, cbp_c = cbp >> 4;
     if (cbp > 0 || m.mb_type == MBT_I16x16) {
-      qp += r.se();
-      if (qp < 0 || qp > 51) return PARSE_INVALID;
-      const int8_t* L = mbx > 0 ? pic->mbs[idx - 1].nnz : nullptr;
-      const int8_t* T = mby > 0 ? pic->mbs[idx - mbw].nnz : nullptr;
+      const int dqp = r.se();
+      if (dqp < -26 || dqp > 25) return PARSE_INVALID;
+      qp = (qp + dqp + 52) % 52;                              // 7.4.5: QP_Y wraps modulo 52
+      const int8_t* L = avL ? pic->mbs[idx - 1].nnz : nullptr;
+      const int8_t* T = avT ? pic->mbs[idx - mbw].nnz : nullptr;
       auto luma_nc = [&](int bx, int by) {
         const int a = bx > 0 ? m.nnz[by * 4 + bx - 1] : (L ? L[by * 4 + 3] : -1);
         const int b = by > 0 ? m.nnz[(by - 1) * 4 + bx] : (T ? T[12 + bx] : -1);
@@ -390,9 +446,9 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     m.qp = (uint8_t)qp;
     if (!r.ok()) return PARSE_TRUNCATED;
     idx++;
-    if (!is_p && idx < n && !r.more_data()) return PARSE_INVALID;
-    if (is_p && idx < n && !r.more_data()) return PARSE_INVALID;
+    if (!r.more_data()) break;                                // end of this slice
   }
+  pic->next_mb = idx;
   return PARSE_OK;
 }
 
@@ -408,16 +464,15 @@ int parse_access_unit(const uint8_t* au, size_t len, ParserState* st, ParsedPict
       if (got_slice) return PARSE_UNSUPPORTED;                // parameter sets after the slice of the same unit
       rc = nal.type == 7 ? parse_sps(r, st) : parse_pps(r, st);
     } else if (nal.type == 1 || nal.type == 5) {
-      if (got_slice) return PARSE_UNSUPPORTED;                // several slices per picture
-      rc = parse_slice(r, nal, st, pic);
+      rc = parse_slice(r, nal, st, pic);                      // one of possibly several slices of the picture
       got_slice = true;
     } else if (nal.type == 6 || nal.type == 9 || nal.type == 12) continue;   // SEI, AUD, filler: nothing to reconstruct
     else return PARSE_UNSUPPORTED;
     if (rc != PARSE_OK) return rc;
   }
   if (!got_slice) return PARSE_NO_PICTURE;
-  st->have_ref = true;
-  st->last_frame_num = pic->ss.frame_num;
+  if (pic->next_mb != st->sp.mb_w * st->sp.mb_h) return PARSE_UNSUPPORTED;   // macroblocks missing: needs error concealment
+  if (pic->is_ref) { st->have_ref = true; st->last_frame_num = pic->ss.frame_num; }
   return PARSE_OK;
 }
 

@@ -1,6 +1,6 @@
 // h264_parse.h — host-side bitstream PARSER: the inverse of h264_bitstream.{h,cpp} for the stream class this
-// library produces (Baseline, CAVLC, one slice per picture, one reference frame, I and P slices, 8x8 as the
-// smallest partition).  Groundwork for the decoder construct path (SURVEY.md section 8f / DESIGN.md section 9): the
+// library decodes: Baseline, CAVLC, I and P slices (several per picture, in raster order: no FMO / ASO), one reference
+// frame, all partition shapes down to 4x4, non-reference pictures, constrained intra prediction, per-slice deblocking control.  Groundwork for the decoder construct path (SURVEY.md section 8f / DESIGN.md section 9): the
 // reference parses on the host too (codec/decoder/core/src/{au_parser,parse_mb_syn_cavlc,decode_slice}.cpp) and
 // hands macroblock arrays to the pixel stage; here the macroblock array is the same MbOut record the encoder's
 // entropy coder consumes, so "parse(write(x)) == x" is checked for every picture the host build encodes
@@ -32,8 +32,10 @@ struct ParserState {
   StreamParams sp{};             // width / height / mb_w / mb_h / crop / level / ids (num_ref_frames)
   int log2_max_frame_num = 0;
   int poc_type = 2, log2_max_poc_lsb = 0;
+  bool delta_pic_order_always_zero = false;
   int pic_init_qp = 26;
   bool deblocking_control = true;
+  bool constrained_intra_pred = false;
   int num_ref_idx_default = 1;
   bool have_ref = false;         // a picture has been decoded (a P slice has something to predict from)
   int last_frame_num = 0;
@@ -42,7 +44,12 @@ struct ParserState {
 struct ParsedPicture {
   SliceState ss;                 // idr, frame_num, idr_pic_id, slice qp
   int disable_deblocking_idc = 0;
+  bool is_ref = true;            // nal_ref_idc != 0
   std::vector<MbOut> mbs;        // mb_w * mb_h records, same meaning as the encoder's hand-over records
+  std::vector<DecMbAux> aux;     // one per macroblock: slice membership, sub-macroblock partitions, deblocking control
+  int next_mb = 0;               // macroblocks parsed so far (slices arrive in raster order)
+  int n_slices = 0;
+  bool any_deblock = false;      // some slice wants its macroblocks filtered
 };
 
 // Parses one access unit: [SPS] [PPS] slice, each NAL behind a 3- or 4-byte start code.  Returns PARSE_OK or an error.

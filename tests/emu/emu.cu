@@ -271,7 +271,18 @@ extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, i
     long next = pos + 3;
     while (next + 3 < len && !is_start(next)) next++;
     if (next + 3 >= len) next = len;
+    // an access unit ends with its last slice NAL: the NAL that follows is not a slice, or is a slice that starts a new
+    // picture (first_mb_in_slice == 0: its ue(v) is the single bit 1 right after the NAL header)
+    bool last_slice = false;
     if (type == 1 || type == 5) {
+      last_slice = true;
+      if (next + 4 < len) {
+        const long hdr = next + 3;                      // NAL header byte of the next unit
+        const int ntype = bs[hdr] & 31;
+        if ((ntype == 1 || ntype == 5) && !(bs[hdr + 1] & 0x80)) last_slice = false;   // next slice continues this picture
+      }
+    }
+    if (last_slice) {
       long au_end = next;
       if (au_end < len && au_end > 0 && bs[au_end - 1] == 0) au_end--;        // zero_byte of the next 4-byte start code
       b2h264::ParsedPicture pp;
@@ -293,7 +304,7 @@ extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, i
       memset(&p, 0, sizeof(p));
       p.mb_w = st.sp.mb_w; p.mb_h = st.sp.mb_h;
       p.rec_stride_y = geo.rec_stride_y(); p.rec_stride_c = geo.rec_stride_c();
-      p.qp = pp.ss.qp; p.is_idr = pp.ss.idr; p.ref_is_p = !pp.ss.idr; p.mv_range = 64;
+      p.qp = pp.ss.qp; p.is_idr = pp.ss.idr; p.ref_is_p = !pp.ss.idr; p.mv_range = 64; p.dec_mode = 1;
       EncFramePtrs f;
       memset(&f, 0, sizeof(f));
       for (int pl = 0; pl < 3; pl++) {
@@ -303,8 +314,8 @@ extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, i
       }
       f.mbi = mbi.data();
       for (int mby = 0; mby < p.mb_h; mby++)
-        for (int mbx = 0; mbx < p.mb_w; mbx++) dec_one_mb(p, f, scratch, mbx, mby, pp.mbs[(size_t)mby * p.mb_w + mbx]);
-      if (pp.disable_deblocking_idc != 1) deblock_frame_host(p, f);
+        for (int mbx = 0; mbx < p.mb_w; mbx++) dec_one_mb(p, f, scratch, mbx, mby, pp.mbs[(size_t)mby * p.mb_w + mbx], pp.aux[(size_t)mby * p.mb_w + mbx]);
+      if (pp.any_deblock) deblock_frame_host(p, f);
       expand_frame_host(p, f);
       const int W = st.sp.width, H = st.sp.height;
       *w = W; *h = H;
@@ -314,7 +325,7 @@ extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, i
         for (int y = 0; y < ph; y++) { memcpy(out + outpos, f.rec[pl] + (size_t)y * stp, pw); outpos += pw; }
       }
       frames++;
-      cur_rec = 1 - cur_rec;
+      if (pp.is_ref) cur_rec = 1 - cur_rec;     // a non-reference picture leaves the reference where it is
       au_begin = au_end;
     }
     pos = next;
@@ -464,3 +475,6 @@ static int random_pictures(unsigned seed, int pictures, bool decodable, uint8_t*
   }
   return 0;
 }
+
+namespace b2h264 { extern int g_reject_line; }
+extern "C" int emu_last_reject_line() { return b2h264::g_reject_line; }

@@ -96,11 +96,12 @@ int  b2h264_enc_set_stream (b2h264_enc* e, void* stream);
 /* layer 3 (WelsCreateSVCEncoder / ISVCEncoder, codec_api.h:272-339,545-586) is declared in b2h264_wels_api.h */
 
 /* ---- batched decoder (first device version of the decoder construct path) -----------------
- * Replaces, for Baseline / CAVLC / one slice per picture / one reference frame / partitions >= 8x8 streams (what this
- * library's encoder and the reference encoder in the same configuration produce), ISVCDecoder::DecodeFrameNoDelay
+ * Replaces, for Baseline CAVLC streams (I and P slices, several slices per picture in raster order, up to 16 reference frames with
+ * list modification and sliding-window / "unused" marking, all partition shapes down to 4x4, constrained intra prediction,
+ * per-slice deblocking control, non-reference pictures; no FMO / ASO, long-term references, I_PCM, B slices or CABAC), ISVCDecoder::DecodeFrameNoDelay
  * (codec/api/wels/codec_api.h:383; codec/decoder/plus/src/welsDecoderExt.cpp:~700).  The host parses, the GPU
  * reconstructs, deblocks and pads.  Anything else is rejected: -101 truncated, -102 unsupported stream feature,
- * -103 invalid syntax, -104 slice before its parameter sets; -2 picture size differs from the configuration. */
+ * -103 invalid syntax, -104 slice before its parameter sets, -105 the slices given do not cover the picture; -2 picture size differs from the configuration. */
 typedef struct b2h264_dec b2h264_dec;
 typedef struct {
   int32_t width, height;        /* cropped picture size the streams must have */

@@ -285,7 +285,26 @@ class BatchDecoder:
         check(self.L.b2h264_dec_decode(self.h, au, nb, yo))
         return outs
 
+    def decode2(self, access_units):
+        """like decode(); entries may be None (stream sits the call out).  Returns (pictures or None per stream)."""
+        bufs = [None if a is None else np.frombuffer(bytes(a), np.uint8) for a in access_units]
+        outs = [np.empty(self.frame_bytes, np.uint8) for _ in range(self.n)]
+        au = (vp * self.n)(*[None if b is None else b.ctypes.data for b in bufs])
+        nb = (C.c_int32 * self.n)(*[0 if b is None else len(b) for b in bufs])
+        yo = (vp * self.n)(*[o.ctypes.data for o in outs])
+        got = (C.c_int32 * self.n)()
+        check(self.L.b2h264_dec_decode2(self.h, au, nb, yo, got))
+        return [outs[i] if got[i] else None for i in range(self.n)]
+
     def close(self):
         if self.h:
             self.L.b2h264_dec_destroy(self.h)
             self.h = None
+
+
+def probe_access_unit(au):
+    """(width, height, has_slice) of an access unit (width / height 0 when it carries no SPS); no device needed"""
+    a = np.frombuffer(bytes(au), np.uint8)
+    w, h, s = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    check(load().b2h264_dec_probe(a.ctypes.data, len(a), C.byref(w), C.byref(h), C.byref(s)))
+    return w.value, h.value, bool(s.value)

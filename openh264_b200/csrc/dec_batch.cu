@@ -27,11 +27,12 @@ struct b2h264_dec {
   int S = 0, mb_w = 0, mb_h = 0, n_mb = 0;
   StreamCtl geo;                          // picture geometry (strides, padded rows)
   std::vector<ParserState> parser;
-  std::vector<uint8_t> stream_rec;        // per stream: which of its two pictures is written next
+  int slots = 2;                          // picture slots per stream (num_ref_frames + 1 of the most demanding stream so far)
+  std::vector<int> out_slot;              // per active stream: slot of the picture decoded in this call
   std::vector<int> act;
   std::vector<uint8_t> act_ref;           // is the picture of act[i] a reference picture
   cudaStream_t st = nullptr;
-  uint8_t* d_pic[2] = {nullptr, nullptr};
+  uint8_t* d_pic = nullptr;               // S x slots padded pictures: picture (s, slot) at (s * slots + slot) * pic_bytes
   MbInfo* d_mbi = nullptr;
   MbOut* d_recs = nullptr;
   MbOut* h_recs = nullptr;                // pinned
@@ -43,9 +44,9 @@ struct b2h264_dec {
   size_t pic_bytes = 0, pic_y_bytes = 0, pic_c_bytes = 0;
   int last_error_stream = -1;
 
-  uint8_t* plane0(int set, int s, int pl) const {
+  uint8_t* plane0(int slot, int s, int pl) const {
     const int sty = geo.rec_stride_y(), stc = geo.rec_stride_c();
-    uint8_t* base = d_pic[set] + (size_t)s * pic_bytes;
+    uint8_t* base = d_pic + ((size_t)s * slots + slot) * pic_bytes;
     if (pl == 0) return base + (size_t)32 * sty + 32;
     return base + pic_y_bytes + (size_t)(pl - 1) * pic_c_bytes + (size_t)16 * stc + 16;
   }
@@ -65,16 +66,13 @@ int b2h264_dec_create(const b2h264_dec_config* cfg, b2h264_dec** out) {
   d->geo.init(cfg->width, cfg->height, 26, 30.0f, 0);
   d->mb_w = d->geo.sp.mb_w; d->mb_h = d->geo.sp.mb_h; d->n_mb = d->mb_w * d->mb_h;
   d->parser.resize(d->S);
-  d->stream_rec.assign(d->S, 0);
   d->pic_y_bytes = (size_t)d->geo.rec_stride_y() * d->geo.rec_rows_y();
   d->pic_c_bytes = (size_t)d->geo.rec_stride_c() * d->geo.rec_rows_c();
   d->pic_bytes = d->pic_y_bytes + 2 * d->pic_c_bytes;
   const size_t S = d->S;
   CK(cudaStreamCreateWithFlags(&d->st, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; i++) {
-    CK(cudaMalloc(&d->d_pic[i], S * d->pic_bytes + 256));
-    CK(cudaMemset(d->d_pic[i], 0, S * d->pic_bytes + 256));
-  }
+  CK(cudaMalloc(&d->d_pic, S * d->slots * d->pic_bytes + 256));
+  CK(cudaMemset(d->d_pic, 0, S * d->slots * d->pic_bytes + 256));
   CK(cudaMalloc(&d->d_mbi, S * d->n_mb * sizeof(MbInfo)));
   CK(cudaMemset(d->d_mbi, 0, S * d->n_mb * sizeof(MbInfo)));
   CK(cudaMalloc(&d->d_recs, S * d->n_mb * sizeof(MbOut)));
@@ -92,7 +90,7 @@ void b2h264_dec_destroy(b2h264_dec* d) {
   if (!d) return;
   cudaSetDevice(d->cfg.device);
   if (d->st) cudaStreamSynchronize(d->st);
-  for (int i = 0; i < 2; i++) cudaFree(d->d_pic[i]);
+  cudaFree(d->d_pic);
   cudaFree(d->d_mbi); cudaFree(d->d_recs); cudaFree(d->d_aux); cudaFreeHost(d->h_aux); cudaFree(d->d_sf); cudaFree(d->d_ws);
   cudaFreeHost(d->h_recs); cudaFreeHost(d->h_sf);
   if (d->st) cudaStreamDestroy(d->st);
@@ -106,7 +104,7 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
   CK(cudaSetDevice(d->cfg.device));
   const int S = d->S;
   int deblock = 1;
-  d->act.clear(); d->act_ref.clear();
+  d->act.clear(); d->act_ref.clear(); d->out_slot.clear();
   for (int s = 0; s < S; s++) {
     if (got_picture) got_picture[s] = 0;
     if (!au[s] || au_bytes[s] <= 0) {
@@ -116,15 +114,32 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
     ParsedPicture pic;
     const int rc = parse_access_unit(au[s], (size_t)au_bytes[s], &d->parser[s], &pic);
     if (rc == PARSE_NO_PICTURE && got_picture) continue;
-    if (rc != PARSE_OK) { d->last_error_stream = s; return -100 + (rc == PARSE_NO_PICTURE ? PARSE_INVALID : rc); }   // -101 truncated, -102 unsupported, -103 invalid, -104 no parameter sets
+    if (rc != PARSE_OK) { d->last_error_stream = s; return -100 + (rc == PARSE_NO_PICTURE ? PARSE_INVALID : rc); }   // -101 truncated, -102 unsupported, -103 invalid, -104 no parameter sets, -105 picture incomplete
     const StreamParams& sp = d->parser[s].sp;
     if (sp.mb_w != d->mb_w || sp.mb_h != d->mb_h || sp.width != d->cfg.width || sp.height != d->cfg.height) { d->last_error_stream = s; return -2; }
     if ((int)pic.mbs.size() != d->n_mb) { d->last_error_stream = s; return -103; }
     if ((int)pic.aux.size() != d->n_mb) { d->last_error_stream = s; return -103; }
+    if (pic.n_slots > d->slots) {                   // a stream with more reference frames: widen every stream's slot array, keeping the pictures
+      if (pic.n_slots > 17) { d->last_error_stream = s; return -103; }
+      uint8_t* np = nullptr;
+      CK(cudaMalloc(&np, (size_t)S * pic.n_slots * d->pic_bytes + 256));
+      CK(cudaMemsetAsync(np, 0, (size_t)S * pic.n_slots * d->pic_bytes + 256, d->st));
+      for (int q = 0; q < S; q++)
+        CK(cudaMemcpyAsync(np + (size_t)q * pic.n_slots * d->pic_bytes, d->d_pic + (size_t)q * d->slots * d->pic_bytes,
+                           (size_t)d->slots * d->pic_bytes, cudaMemcpyDeviceToDevice, d->st));
+      CK(cudaStreamSynchronize(d->st));
+      cudaFree(d->d_pic);
+      d->d_pic = np; d->slots = pic.n_slots;
+      for (int q = 0; q < (int)d->act.size(); q++) {      // descriptors built before the move
+        StreamFrame& G = d->h_sf[q];
+        const int qs = d->act[q];
+        for (int pl = 0; pl < 3; pl++) { G.f.rec[pl] = d->plane0(d->out_slot[q], qs, pl); G.f.ref[pl] = G.f.dpb0[pl] = d->plane0(0, qs, pl); }
+      }
+    }
     if (d->act.empty()) deblock = 0;
     if (pic.any_deblock) deblock = 1;               // the filter kernel runs if any slice of any stream wants it (per-MB control inside)
     const int i = (int)d->act.size();
-    d->act.push_back(s); d->act_ref.push_back(pic.is_ref ? 1 : 0);
+    d->act.push_back(s); d->act_ref.push_back(pic.is_ref ? 1 : 0); d->out_slot.push_back(pic.cur_slot);
     memcpy(d->h_recs + (size_t)i * d->n_mb, pic.mbs.data(), (size_t)d->n_mb * sizeof(MbOut));
     memcpy(d->h_aux + (size_t)i * d->n_mb, pic.aux.data(), (size_t)d->n_mb * sizeof(DecMbAux));
     StreamFrame& F = d->h_sf[i];
@@ -132,8 +147,9 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
     F.p.mb_w = d->mb_w; F.p.mb_h = d->mb_h;
     F.p.rec_stride_y = d->geo.rec_stride_y(); F.p.rec_stride_c = d->geo.rec_stride_c();
     F.p.qp = pic.ss.qp; F.p.is_idr = pic.ss.idr; F.p.ref_is_p = !pic.ss.idr; F.p.mv_range = 64; F.p.dec_mode = 1;
-    const int rec = d->stream_rec[s];
-    for (int pl = 0; pl < 3; pl++) { F.f.rec[pl] = d->plane0(rec, s, pl); F.f.ref[pl] = d->plane0(1 - rec, s, pl); }
+    if (pic.cur_slot >= d->slots) { d->last_error_stream = s; return -103; }
+    for (int pl = 0; pl < 3; pl++) { F.f.rec[pl] = d->plane0(pic.cur_slot, s, pl); F.f.ref[pl] = F.f.dpb0[pl] = d->plane0(0, s, pl); }
+    F.f.dpb_stride = (int64_t)d->pic_bytes;
     F.f.mbi = d->d_mbi + (size_t)s * d->n_mb;
   }
   const int n = (int)d->act.size();
@@ -145,7 +161,7 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
   if (rc) return rc;
   const int w = d->cfg.width, h = d->cfg.height;
   for (int i = 0; i < n; i++) {
-    const int s = d->act[i], rec = d->stream_rec[s];
+    const int s = d->act[i], rec = d->out_slot[i];
     uint8_t* dst = yuv[s];
     for (int pl = 0; pl < 3; pl++) {
       const int pw = pl ? w / 2 : w, ph = pl ? h / 2 : h;
@@ -153,7 +169,6 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
       CK(cudaMemcpy2DAsync(dst, pw, d->plane0(rec, s, pl), stp, pw, ph, cudaMemcpyDeviceToHost, d->st));
       dst += (size_t)pw * ph;
     }
-    if (d->act_ref[i]) d->stream_rec[s] ^= 1;       // a non-reference picture leaves the reference where it is
     if (got_picture) got_picture[s] = 1;
   }
   CK(cudaStreamSynchronize(d->st));

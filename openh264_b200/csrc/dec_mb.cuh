@@ -68,6 +68,25 @@ MBK_HD void dec_chroma_coef(MbScratch& s, const MbOut& m, int qp_c) {
   warp_sync();
 }
 
+// picture slot -> plane pointers (pixel (0,0)); REF_NOT_AVAIL cells of the motion cache sit below the slot numbers (0..16)
+MBK_HD const uint8_t* dec_ref_plane(const MbCtx& c, int pl, int slot) { return c.f.dpb0[pl] + (ptrdiff_t)slot * c.f.dpb_stride; }
+// motion compensation of one partition from picture `slot` into the prediction buffers (BaseMC, rec_mb.cpp:244)
+MBK_HD void dec_mc_part(const MbCtx& c, uint8_t* pl, uint8_t* pc, int slot, int blk, int w4, int h4, int mvx, int mvy) {
+  const int ox = blk_x(blk) * 4, oy = blk_y(blk) * 4, w = w4 * 4, h = h4 * 4;
+  // absolute quarter-sample position, clipped like BaseMC (rec_mb.cpp:248-253: the padded reference is 32 wide);
+  // luma and chroma both derive from the clipped position
+  int fx = ((c.mbx * 16 + ox) << 2) + mvx, fy = ((c.mby * 16 + oy) << 2) + mvy;
+  fx = clip3(fx, (-32 + 2) * 4, (c.p.mb_w * 16 + 32 - 19) * 4);
+  fy = clip3(fy, (-32 + 2) * 4, (c.p.mb_h * 16 + 32 - 19) * 4);
+  warp_mc_luma(dec_ref_plane(c, 0, slot) + (ptrdiff_t)(fy >> 2) * c.p.rec_stride_y + (fx >> 2), c.p.rec_stride_y, pl + oy * 16 + ox, 16, fx, fy, w, h);
+  for (int cpl = 0; cpl < 2; cpl++)
+    warp_mc_chroma(dec_ref_plane(c, 1 + cpl, slot) + (ptrdiff_t)(fy >> 3) * c.p.rec_stride_c + (fx >> 3), c.p.rec_stride_c,
+                   pc + 64 * cpl + (oy >> 1) * 8 + (ox >> 1), 8, fx, fy, w >> 1, h >> 1);
+  warp_sync();
+}
+// reference slot of the 8x8 quadrant that holds 4x4 block `blk` (coding order)
+MBK_HD int dec_ref_of(const DecMbAux& aux, int blk) { return aux.ref_idx[blk >> 2]; }
+
 // One macroblock.  f.rec = picture being reconstructed, f.ref = reference picture (padded), f.mbi = MbInfo array of
 // the picture (neighbour lookups + what deblocking reads).  Raster / wavefront order like the encoder.
 MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch& s, int mbx, int mby, const MbOut& m, const DecMbAux& aux) {
@@ -105,7 +124,7 @@ MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch
     // sub-macroblock partitions (8x4, 4x8, 4x4): every partition predicts its vector from the cells decoded so far —
     // the in-macroblock cells start as "not available" and are filled in decoding order (8.4.1.3.2: a partition that
     // comes later in decoding order is not available as neighbour C, the top-left neighbour D steps in)
-    fill_inter_cache(c, s);
+    fill_inter_cache(c, s, true);
     if (lane_id() == 0)
       for (int r = 1; r < 5; r++) for (int q = 1; q < 5; q++) s.refc[r * 6 + q] = REF_NOT_AVAIL;
     warp_sync();
@@ -115,48 +134,35 @@ MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch
       for (int j = 0; j < np; j++) {
         const int blk = 4 * k + (st == 1 ? 2 * j : j);           // 8x4: rows of the 8x8; 4x8 / 4x4: blocks in coding order
         int px, py;
-        pred_mv(s, blk, w4, 0, &px, &py);
+        const int ref = aux.ref_idx[k];
+        pred_mv(s, blk, w4, ref, &px, &py);
         const int mvx = px + aux.mvd[4 * k + j][0], mvy = py + aux.mvd[4 * k + j][1];
-        cache_set(s, blk, w4, h4, mvx, mvy);
+        cache_set(s, blk, w4, h4, mvx, mvy, ref);
         mb_mv_set(s, blk, w4, h4, mvx, mvy);
-        const int ox = blk_x(blk) * 4, oy = blk_y(blk) * 4, w = w4 * 4, h = h4 * 4;
-        int fx = ((c.mbx * 16 + ox) << 2) + mvx, fy = ((c.mby * 16 + oy) << 2) + mvy;
-        fx = clip3(fx, (-32 + 2) * 4, (c.p.mb_w * 16 + 32 - 19) * 4);
-        fy = clip3(fy, (-32 + 2) * 4, (c.p.mb_h * 16 + 32 - 19) * 4);
-        warp_mc_luma(c.f.ref[0] + (ptrdiff_t)(fy >> 2) * c.p.rec_stride_y + (fx >> 2), c.p.rec_stride_y, pl + oy * 16 + ox, 16, fx, fy, w, h);
-        for (int cpl = 0; cpl < 2; cpl++)
-          warp_mc_chroma(c.f.ref[1 + cpl] + (ptrdiff_t)(fy >> 3) * c.p.rec_stride_c + (fx >> 3), c.p.rec_stride_c,
-                         pc + 64 * cpl + (oy >> 1) * 8 + (ox >> 1), 8, fx, fy, w >> 1, h >> 1);
-        warp_sync();
+        dec_mc_part(c, pl, pc, ref, blk, w4, h4, mvx, mvy);
       }
     }
     dec_luma_coef(s, m, qp, false, nullptr);
     rec_luma_inter(s, pl);
   } else if (MBT_IS_INTER(type)) {
-    fill_inter_cache(c, s);
+    fill_inter_cache(c, s, true);
     const int nparts = type == MBT_P8x8 ? 4 : (type == MBT_P16x8 || type == MBT_P8x16) ? 2 : 1;
     if (type == MBT_P8x8) { if (lane_id() == 0) { s.refc[9] = s.refc[21] = REF_NOT_AVAIL; } warp_sync(); }
     for (int i = 0; i < nparts; i++) {
       int blk = 0, w4 = 4, h4 = 4, px = 0, py = 0;
-      if (type == MBT_PSKIP) pred_skip_mv(s, &px, &py);
-      else if (type == MBT_P16x16) pred_mv(s, 0, 4, 0, &px, &py);
-      else if (type == MBT_P16x8) { blk = 8 * i; h4 = 2; pred_16x8_mv(s, blk, 0, &px, &py); }
-      else if (type == MBT_P8x16) { blk = 4 * i; w4 = 2; pred_8x16_mv(s, blk, 0, &px, &py); }
-      else { blk = 4 * i; w4 = 2; h4 = 2; pred_mv(s, blk, 2, 0, &px, &py); }
+      if (type == MBT_P16x8) { blk = 8 * i; h4 = 2; }
+      else if (type == MBT_P8x16) { blk = 4 * i; w4 = 2; }
+      else if (type == MBT_P8x8) { blk = 4 * i; w4 = 2; h4 = 2; }
+      const int ref = dec_ref_of(aux, blk);                       // picture slot of this partition's reference
+      if (type == MBT_PSKIP) pred_skip_mv(s, &px, &py, ref);
+      else if (type == MBT_P16x16) pred_mv(s, 0, 4, ref, &px, &py);
+      else if (type == MBT_P16x8) pred_16x8_mv(s, blk, ref, &px, &py);
+      else if (type == MBT_P8x16) pred_8x16_mv(s, blk, ref, &px, &py);
+      else pred_mv(s, blk, 2, ref, &px, &py);
       const int mvx = px + (type == MBT_PSKIP ? 0 : m.mvd[i][0]), mvy = py + (type == MBT_PSKIP ? 0 : m.mvd[i][1]);
-      cache_set(s, blk, w4, h4, mvx, mvy);
+      cache_set(s, blk, w4, h4, mvx, mvy, ref);
       mb_mv_set(s, blk, w4, h4, mvx, mvy);
-      const int ox = blk_x(blk) * 4, oy = blk_y(blk) * 4, w = w4 * 4, h = h4 * 4;
-      // absolute quarter-sample position, clipped like BaseMC (rec_mb.cpp:248-253: the padded reference is 32 wide);
-      // luma and chroma both derive from the clipped position
-      int fx = ((c.mbx * 16 + ox) << 2) + mvx, fy = ((c.mby * 16 + oy) << 2) + mvy;
-      fx = clip3(fx, (-32 + 2) * 4, (c.p.mb_w * 16 + 32 - 19) * 4);
-      fy = clip3(fy, (-32 + 2) * 4, (c.p.mb_h * 16 + 32 - 19) * 4);
-      warp_mc_luma(c.f.ref[0] + (ptrdiff_t)(fy >> 2) * c.p.rec_stride_y + (fx >> 2), c.p.rec_stride_y, pl + oy * 16 + ox, 16, fx, fy, w, h);
-      for (int cpl = 0; cpl < 2; cpl++)
-        warp_mc_chroma(c.f.ref[1 + cpl] + (ptrdiff_t)(fy >> 3) * c.p.rec_stride_c + (fx >> 3), c.p.rec_stride_c,
-                       pc + 64 * cpl + (oy >> 1) * 8 + (ox >> 1), 8, fx, fy, w >> 1, h >> 1);
-      warp_sync();
+      dec_mc_part(c, pl, pc, ref, blk, w4, h4, mvx, mvy);
     }
     warp_sync();
     dec_luma_coef(s, m, qp, false, nullptr);
@@ -222,6 +228,8 @@ MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch
   // what the neighbours and the deblocking filter read
   if (lane_id() == 0) {
     s.info.qp = (uint8_t)qp; s.info.qp_c = (uint8_t)qp_c;
+    if (MBT_IS_INTER(type))                     // reference picture slot of every 4x4 block (raster): MV prediction of the neighbours, bS
+      for (int b = 0; b < 16; b++) s.info.i4_mode[b] = aux.ref_idx[(b >> 3) * 2 + ((b >> 1) & 1)];
     // the decoder has no use for sP16x16Mv: the field carries what the deblocking pass needs to know about the slice
     s.info.p16x16_mv[0] = (int16_t)aux.slice;
     s.info.p16x16_mv[1] = (int16_t)(aux.dbk_idc | ((aux.alpha_off + 16) << 2) | ((aux.beta_off + 16) << 7));

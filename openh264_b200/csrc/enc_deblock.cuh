@@ -22,7 +22,8 @@ MBK_HD int tbl_beta(int i) { return MBK_TBL(c_beta, h_beta)[i]; }
 MBK_HD int tbl_tc0(int i, int bs) { return bs == 0 ? -1 : MBK_TBL(c_tc0, h_tc0)[i][bs - 1]; }
 
 // boundary strength of the 4 segments of one edge; dir 0 = vertical edge (left neighbour), 1 = horizontal
-MBK_HD void edge_bs(const MbInfo* cur, const MbInfo* nb /*other MB for edge 0, else == cur*/, int dir, int edge, int bs[4]) {
+MBK_HD void edge_bs(const MbInfo* cur, const MbInfo* nb /*other MB for edge 0, else == cur*/, int dir, int edge, int bs[4],
+                    bool ref_ids = false /* decoder: i4_mode holds the reference picture of every 4x4 block */) {
   const bool mb_edge = edge == 0;
   for (int i = 0; i < 4; i++) {
     // q block in cur, p block in nb (raster 4x4 indices)
@@ -31,6 +32,7 @@ MBK_HD void edge_bs(const MbInfo* cur, const MbInfo* nb /*other MB for edge 0, e
     if (MBT_IS_INTRA(cur->mb_type) || MBT_IS_INTRA(nb->mb_type)) { bs[i] = mb_edge ? 4 : 3; continue; }
     if (!mb_edge && cur->mb_type == MBT_PSKIP) { bs[i] = 0; continue; }
     if (cur->nnz[q] | nb->nnz[p]) { bs[i] = 2; continue; }
+    if (ref_ids && cur->i4_mode[q] != nb->i4_mode[p]) { bs[i] = 1; continue; }      // different reference pictures
     const int dx = cur->mv[q][0] - nb->mv[p][0], dy = cur->mv[q][1] - nb->mv[p][1];
     bs[i] = (iabs(dx) >= 4 || iabs(dy) >= 4) ? 1 : 0;
   }
@@ -97,7 +99,7 @@ MBK_HD void deblock_one_mb(const EncFrameParams& p, const EncFramePtrs& f, int m
       if (edge == 0 && !have_nb) continue;
       const MbInfo* other = edge == 0 ? nbm : cur;
       int bs[4];
-      edge_bs(cur, other, dir, edge, bs);
+      edge_bs(cur, other, dir, edge, bs, p.dec_mode != 0);
       if ((bs[0] | bs[1] | bs[2] | bs[3]) == 0) continue;
       const int qp_y = edge == 0 ? (cur->qp + other->qp + 1) >> 1 : cur->qp;
       const int qp_c = edge == 0 ? (cur->qp_c + other->qp_c + 1) >> 1 : cur->qp_c;

@@ -28,7 +28,9 @@ MBK_HD int median3(int a, int b, int c) {
 }
 
 // ---- neighbour caches (FillNeighborCacheInterWithoutBGD, md.cpp:132) ----------------------------------
-MBK_FN void fill_inter_cache(const MbCtx& c, MbScratch& s) {
+// ref_ids: the decoder keeps, per 4x4 block of an inter macroblock, the picture slot of its reference in MbInfo::i4_mode
+// (unused for inter macroblocks otherwise); the encoder has one reference picture (index 0 everywhere)
+MBK_FN void fill_inter_cache(const MbCtx& c, MbScratch& s, bool ref_ids = false) {
   // one lane per cache cell: cells 0..5 = top-left, top x4, top-right; cells 6,12,18,24 = left column
   for (int ci = lane_id(); ci < 30; ci += MBK_WS) {
     int k = -1, blk = 0;                       // neighbour slot (0 TL, 1 T, 2 TR, 3 L) and its 4x4 block (raster)
@@ -42,7 +44,7 @@ MBK_FN void fill_inter_cache(const MbCtx& c, MbScratch& s) {
       const int bits[4] = {NB_TOPLEFT, NB_TOP, NB_TOPRIGHT, NB_LEFT};
       const bool avail = (c.nb & bits[k]) != 0;
       const MbInfo* n = &s.nbi[k];
-      if (avail && MBT_IS_INTER(n->mb_type)) { mx = n->mv[blk][0]; my = n->mv[blk][1]; }
+      if (avail && MBT_IS_INTER(n->mb_type)) { mx = n->mv[blk][0]; my = n->mv[blk][1]; if (ref_ids) ref = n->i4_mode[blk]; }
       else ref = avail ? REF_NOT_IN_LIST : REF_NOT_AVAIL;
     } else if (ci == 9 || ci == 11 || ci == 17 || ci == 21 || ci == 23) {
       ref = REF_NOT_AVAIL;                     // blocks whose top-right neighbour is never available
@@ -90,18 +92,18 @@ MBK_HD void pred_8x16_mv(const MbScratch& s, int blk, int ref, int* px, int* py)
   }
   pred_mv(s, blk, 2, ref, px, py);
 }
-MBK_HD void pred_skip_mv(const MbScratch& s, int* px, int* py) {
+MBK_HD void pred_skip_mv(const MbScratch& s, int* px, int* py, int ref0 = 0 /* id of reference index 0 */) {
   const int lr = s.refc[6], tr = s.refc[1];
-  if (lr == REF_NOT_AVAIL || tr == REF_NOT_AVAIL || (lr == 0 && s.mvc[6][0] == 0 && s.mvc[6][1] == 0) ||
-      (tr == 0 && s.mvc[1][0] == 0 && s.mvc[1][1] == 0)) { *px = 0; *py = 0; return; }
-  pred_mv(s, 0, 4, 0, px, py);
+  if (lr == REF_NOT_AVAIL || tr == REF_NOT_AVAIL || (lr == ref0 && s.mvc[6][0] == 0 && s.mvc[6][1] == 0) ||
+      (tr == ref0 && s.mvc[1][0] == 0 && s.mvc[1][1] == 0)) { *px = 0; *py = 0; return; }
+  pred_mv(s, 0, 4, ref0, px, py);
 }
 // writes (ref 0, mv) into a w4 x h4 rectangle of cache cells starting at block `blk`
-MBK_HD void cache_set(MbScratch& s, int blk, int w4, int h4, int mvx, int mvy) {
+MBK_HD void cache_set(MbScratch& s, int blk, int w4, int h4, int mvx, int mvy, int ref = 0) {
   if (lane_id() == 0) {
     const int c0 = cache30(blk);
     for (int y = 0; y < h4; y++)
-      for (int x = 0; x < w4; x++) { s.mvc[c0 + 6 * y + x][0] = (int16_t)mvx; s.mvc[c0 + 6 * y + x][1] = (int16_t)mvy; s.refc[c0 + 6 * y + x] = 0; }
+      for (int x = 0; x < w4; x++) { s.mvc[c0 + 6 * y + x][0] = (int16_t)mvx; s.mvc[c0 + 6 * y + x][1] = (int16_t)mvy; s.refc[c0 + 6 * y + x] = (int8_t)ref; }
   }
   warp_sync();
 }

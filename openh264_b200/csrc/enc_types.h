@@ -61,7 +61,7 @@ typedef struct {
   uint8_t pad;
   uint16_t slice;                         // slice number inside the picture
   uint8_t sub_type[4];                    // per 8x8: 0 8x8, 1 8x4, 2 4x8, 3 4x4
-  int8_t  ref_idx[4];                     // per 8x8 (0: one reference picture)
+  int8_t  ref_idx[4];                     // per 8x8: PICTURE SLOT of its reference picture (the parser resolves RefPicList0)
   int16_t mvd[16][2];                     // sub-macroblock partition j of 8x8 k at [4 * k + j]
 } DecMbAux;                               // 16 + 64 = 80 bytes
 #define DECAUX_SUB 1
@@ -95,6 +95,8 @@ typedef struct {
                                           // (encoder_ext.cpp:1675): a decided-skip MB keeps its older value
   const int32_t* vaa_sad8x8;              // fast mode: SAD of the four 8x8 blocks of every macroblock against the PREVIOUS
                                           // SOURCE picture (VAACalcSad_c), indexed like the reference: [iMbXY * 4 + k]
+  const uint8_t* dpb0[3];                 // decoder: planes (pixel (0,0)) of picture slot 0; slot k lies dpb_stride bytes further
+  int64_t dpb_stride;
   const DecMbAux* dec_aux;                // decoder: per-macroblock side records (NULL in the encoder)
   const uint8_t* prev_luma;               // fast mode: luma of the previous SOURCE picture (same layout as cur[0])
   int32_t* mb_bits;                       // optional (NULL = off): exact CAVLC bits of every macroblock (enc_cavlc_bits.cuh)

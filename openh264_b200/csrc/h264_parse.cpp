@@ -135,6 +135,7 @@ int parse_sps(BitReader& r, ParserState* st) {
   if (cl || ct) return PARSE_UNSUPPORTED;     // left / top cropping: never produced by the encoders this mirrors
   sp.pps_id = st->sp.pps_id;
   sp.qp = st->sp.qp;
+  st->n_slots = sp.num_ref_frames + 1 < 2 ? 2 : sp.num_ref_frames + 1;
   st->sp = sp;
   st->have_sps = true;                        // VUI (if any) is not needed for reconstruction
   return PARSE_OK;
@@ -277,26 +278,72 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
   ss.idr_pic_id = idr ? (int)r.ue() : 0;
   if (st->poc_type == 0) r.get(st->log2_max_poc_lsb);
   else if (st->poc_type == 1 && !st->delta_pic_order_always_zero) r.se();          // delta_pic_order_cnt[0]
+  // RefPicList0 of this slice as picture slots (8.2.4.2.1 + 8.2.4.3.1): short-term pictures by descending PicNum, then the
+  // slice's modification commands.  Long-term pictures are outside the supported class.
+  int list0[32];
+  int n_ref = 0;
   if (is_p) {
-    int n_ref = st->num_ref_idx_default;
+    n_ref = st->num_ref_idx_default;
     if (r.bit()) n_ref = (int)r.ue() + 1;
-    if (n_ref != 1) return PARSE_UNSUPPORTED;
+    if (n_ref < 1 || n_ref > 32) return PARSE_INVALID;
+    const int max_fn = 1 << st->log2_max_frame_num;
+    struct Cand { int slot, pic_num; };
+    Cand cand[32];
+    int nc = 0;
+    for (const ParserState::RefPic& rp : st->refs) {
+      if (nc >= 32) break;
+      cand[nc].slot = rp.slot;
+      cand[nc].pic_num = rp.frame_num > ss.frame_num ? rp.frame_num - max_fn : rp.frame_num;      // FrameNumWrap
+      nc++;
+    }
+    if (nc == 0) return PARSE_INVALID;
+    for (int i = 1; i < nc; i++)                              // descending PicNum
+      for (int j = i; j > 0 && cand[j].pic_num > cand[j - 1].pic_num; j--) { const Cand t = cand[j]; cand[j] = cand[j - 1]; cand[j - 1] = t; }
+    int pn[33];
+    for (int i = 0; i < 32; i++) { list0[i] = cand[i < nc ? i : nc - 1].slot; pn[i] = i < nc ? cand[i].pic_num : -0x40000000; }   // entries past the
+                                                              // available pictures repeat the last one (a conforming stream does not use them)
     if (r.bit()) {                                            // ref_pic_list_modification_flag_l0
-      // the construct stage keeps ONE reference picture (the previous one): the only list modification that still
-      // selects it is "short-term, one picture back" (what the encoders this mirrors emit); anything else needs a DPB
+      int pred = ss.frame_num, idx = 0;
       for (;;) {
         const uint32_t idc = r.ue();
         if (idc == 3) break;
         if (idc > 3 || !r.ok()) return PARSE_INVALID;
         const uint32_t v = r.ue();
-        if (idc != 0 || v != 0) return PARSE_UNSUPPORTED;
+        if (idc == 2) return PARSE_UNSUPPORTED;               // long-term reference pictures
+        if (v >= (uint32_t)max_fn || idx >= n_ref) return PARSE_INVALID;
+        int no_wrap = idc == 0 ? pred - ((int)v + 1) : pred + ((int)v + 1);
+        if (no_wrap < 0) no_wrap += max_fn;
+        if (no_wrap >= max_fn) no_wrap -= max_fn;
+        pred = no_wrap;
+        const int pic_num = no_wrap > ss.frame_num ? no_wrap - max_fn : no_wrap;
+        int found = -1;
+        for (int i = 0; i < nc; i++) if (cand[i].pic_num == pic_num) found = cand[i].slot;
+        if (found < 0) return PARSE_UNSUPPORTED;              // refers to a picture that is not in the buffer (loss): needs concealment
+        // 8.2.4.3.1: insert at idx, shift the rest, drop the later duplicate
+        for (int c = n_ref; c > idx; c--) { list0[c < 32 ? c : 31] = list0[c - 1]; pn[c < 33 ? c : 32] = pn[c - 1]; }
+        list0[idx] = found; pn[idx] = pic_num;
+        idx++;
+        int nidx = idx;
+        for (int c = idx; c <= n_ref && c < 32; c++)
+          if (pn[c] != pic_num) { list0[nidx] = list0[c]; pn[nidx] = pn[c]; nidx++; }
       }
     }
   }
   const bool is_ref = nal.ref_idc != 0;                       // a non-reference picture is output but never predicted from
+  bool adaptive = false;
+  std::vector<int> mmco1;
   if (nal.ref_idc) {                                          // dec_ref_pic_marking
-    if (idr) { r.bit(); if (r.bit()) return PARSE_UNSUPPORTED; }
-    else if (r.bit()) return PARSE_UNSUPPORTED;               // adaptive marking (MMCO)
+    if (idr) { r.bit(); if (r.bit()) return PARSE_UNSUPPORTED; }          // long_term_reference_flag
+    else if (r.bit()) {                                       // adaptive marking: only "mark a short-term picture unused" (operation 1)
+      adaptive = true;
+      for (;;) {
+        const uint32_t op = r.ue();
+        if (op == 0) break;
+        if (op != 1 || !r.ok()) return PARSE_UNSUPPORTED;     // long-term operations (2..6)
+        mmco1.push_back((int)r.ue());
+        if (mmco1.size() > 64) return PARSE_INVALID;
+      }
+    }
   }
   ss.qp = st->pic_init_qp + r.se();
   int dbk_idc = 0, alpha_off = 0, beta_off = 0;
@@ -316,6 +363,19 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
   if (first_slice) {
     pic->ss = ss;
     pic->is_ref = is_ref;
+    pic->adaptive_marking = adaptive;
+    pic->mmco1_diff = mmco1;
+    pic->n_slots = st->n_slots;
+    {                                                         // a slot no reference picture occupies
+      int slot = 0;
+      for (;; slot++) {
+        bool used = false;
+        if (!idr) for (const ParserState::RefPic& rp : st->refs) used = used || rp.slot == slot;
+        if (!used) break;
+      }
+      if (slot >= st->n_slots) return PARSE_INVALID;
+      pic->cur_slot = slot;
+    }
     pic->disable_deblocking_idc = dbk_idc;
     pic->mbs.assign(n, MbOut());
     for (MbOut& m : pic->mbs) { memset(&m, 0, sizeof(m)); m.mb_type = MBT_PSKIP; }
@@ -341,6 +401,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
         pic->mbs[idx].qp = (uint8_t)qp;
         DecMbAux& a = pic->aux[idx];
         a.slice = (uint16_t)slice_no; a.dbk_idc = (uint8_t)dbk_idc; a.alpha_off = (int8_t)alpha_off; a.beta_off = (int8_t)beta_off;
+        for (int q = 0; q < 4; q++) a.ref_idx[q] = (int8_t)list0[0];
         const int x = idx % mbw, y = idx / mbw;
         a.avail = (uint8_t)((x > 0 && same_slice(idx - 1) ? 1 : 0) | (y > 0 && same_slice(idx - mbw) ? 2 : 0) |
                             (x > 0 && y > 0 && same_slice(idx - mbw - 1) ? 4 : 0) | (y > 0 && x < mbw - 1 && same_slice(idx - mbw + 1) ? 8 : 0));
@@ -362,11 +423,23 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     }
     int cbp = -1;
     if (!intra) {
-      if (t == 0) { m.mb_type = MBT_P16x16; m.mvd[0][0] = (int16_t)r.se(); m.mvd[0][1] = (int16_t)r.se(); }
-      else if (t == 1 || t == 2) {
+      // ref_idx_l0: te(v) with range num_ref_idx_active - 1 (9.1): absent for one picture, an inverted bit for two, else ue(v)
+      auto read_ref = [&]() -> int {
+        if (n_ref == 1) return 0;
+        const int v = n_ref == 2 ? !r.bit() : (int)r.ue();
+        return v;
+      };
+      int ri[4] = {0, 0, 0, 0};
+      if (t == 0) {
+        m.mb_type = MBT_P16x16;
+        ri[0] = ri[1] = ri[2] = ri[3] = read_ref();
+        m.mvd[0][0] = (int16_t)r.se(); m.mvd[0][1] = (int16_t)r.se();
+      } else if (t == 1 || t == 2) {
         m.mb_type = t == 1 ? MBT_P16x8 : MBT_P8x16;
+        const int r0 = read_ref(), r1 = read_ref();
+        if (t == 1) { ri[0] = ri[1] = r0; ri[2] = ri[3] = r1; } else { ri[0] = ri[2] = r0; ri[1] = ri[3] = r1; }
         for (int k = 0; k < 2; k++) { m.mvd[k][0] = (int16_t)r.se(); m.mvd[k][1] = (int16_t)r.se(); }
-      } else if (t == 3 || t == 4) {                          // P_8x8 / P_8x8ref0: with ONE active reference picture neither carries ref_idx
+      } else if (t == 3 || t == 4) {                          // P_8x8 / P_8x8ref0 (the latter: every reference index is 0)
         m.mb_type = MBT_P8x8;
         bool sub = false;
         for (int k = 0; k < 4; k++) {
@@ -375,12 +448,17 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
           ax.sub_type[k] = (uint8_t)v;
           sub = sub || v != 0;
         }
+        if (t == 3) for (int k = 0; k < 4; k++) ri[k] = read_ref();
         static const int kParts[4] = {1, 2, 2, 4};
         for (int k = 0; k < 4; k++)
           for (int j = 0; j < kParts[ax.sub_type[k]]; j++) { ax.mvd[4 * k + j][0] = (int16_t)r.se(); ax.mvd[4 * k + j][1] = (int16_t)r.se(); }
         if (sub) ax.flags |= DECAUX_SUB;
         else for (int k = 0; k < 4; k++) { m.mvd[k][0] = ax.mvd[4 * k][0]; m.mvd[k][1] = ax.mvd[4 * k][1]; }
       } else return PARSE_INVALID;
+      for (int k = 0; k < 4; k++) {
+        if (ri[k] < 0 || ri[k] >= n_ref) return PARSE_INVALID;
+        ax.ref_idx[k] = (int8_t)list0[ri[k]];
+      }
     } else {
       if (t == 0) {
         m.mb_type = MBT_I4x4;
@@ -471,8 +549,37 @@ int parse_access_unit(const uint8_t* au, size_t len, ParserState* st, ParsedPict
     if (rc != PARSE_OK) return rc;
   }
   if (!got_slice) return PARSE_NO_PICTURE;
-  if (pic->next_mb != st->sp.mb_w * st->sp.mb_h) return PARSE_UNSUPPORTED;   // macroblocks missing: needs error concealment
-  if (pic->is_ref) { st->have_ref = true; st->last_frame_num = pic->ss.frame_num; }
+  if (pic->next_mb != st->sp.mb_w * st->sp.mb_h) return PARSE_INCOMPLETE;    // macroblocks missing: more slices to come (or lost: needs concealment)
+  if (pic->is_ref) {
+    // decoded reference picture marking (8.2.5): an IDR picture empties the buffer; otherwise either the explicit "unused"
+    // commands or the sliding window make room, then the picture joins the short-term references
+    if (pic->ss.idr) st->refs.clear();
+    else if (pic->adaptive_marking) {
+      const int max_fn = 1 << st->log2_max_frame_num;
+      for (int diff : pic->mmco1_diff) {
+        const int pic_num = pic->ss.frame_num - (diff + 1);
+        for (size_t i = 0; i < st->refs.size(); i++) {
+          const int fn = st->refs[i].frame_num, wrap = fn > pic->ss.frame_num ? fn - max_fn : fn;
+          if (wrap == pic_num) { st->refs.erase(st->refs.begin() + i); break; }
+        }
+      }
+    }
+    const int cap = st->sp.num_ref_frames < 1 ? 1 : st->sp.num_ref_frames;
+    while ((int)st->refs.size() >= cap) {                      // sliding window (8.2.5.3): the smallest FrameNumWrap goes
+      const int max_fn = 1 << st->log2_max_frame_num;
+      size_t victim = 0;
+      int best = 0x7fffffff;
+      for (size_t i = 0; i < st->refs.size(); i++) {
+        const int fn = st->refs[i].frame_num, wrap = fn > pic->ss.frame_num ? fn - max_fn : fn;
+        if (wrap < best) { best = wrap; victim = i; }
+      }
+      st->refs.erase(st->refs.begin() + victim);
+    }
+    ParserState::RefPic rp;
+    rp.slot = pic->cur_slot; rp.frame_num = pic->ss.frame_num;
+    st->refs.push_back(rp);
+    st->have_ref = true; st->last_frame_num = pic->ss.frame_num;
+  }
   return PARSE_OK;
 }
 

@@ -23,7 +23,8 @@ enum ParseError {
   PARSE_TRUNCATED = -1,        // ran out of bits
   PARSE_UNSUPPORTED = -2,      // valid H.264 outside the supported class (CABAC, B slices, FMO, sub-8x8 partitions, ...)
   PARSE_INVALID = -3,          // not valid H.264 syntax / values out of range
-  PARSE_NO_PARAMETER_SETS = -4 // a slice before its SPS / PPS
+  PARSE_NO_PARAMETER_SETS = -4,// a slice before its SPS / PPS
+  PARSE_INCOMPLETE = -5        // the slices seen so far do not cover the picture (more slices of the access unit to come, or lost)
 };
 
 // parameter sets carried from access unit to access unit
@@ -39,6 +40,11 @@ struct ParserState {
   int num_ref_idx_default = 1;
   bool have_ref = false;         // a picture has been decoded (a P slice has something to predict from)
   int last_frame_num = 0;
+  // decoded picture buffer bookkeeping (8.2.4, 8.2.5.3): the short-term reference pictures in decoding order, each in one
+  // of n_slots picture slots of the construct stage (num_ref_frames + 1: the picture being decoded needs one too)
+  struct RefPic { int slot, frame_num; };
+  std::vector<RefPic> refs;
+  int n_slots = 2;
 };
 
 struct ParsedPicture {
@@ -49,6 +55,11 @@ struct ParsedPicture {
   std::vector<DecMbAux> aux;     // one per macroblock: slice membership, sub-macroblock partitions, deblocking control
   int next_mb = 0;               // macroblocks parsed so far (slices arrive in raster order)
   int n_slices = 0;
+  int cur_slot = 0;              // picture slot this picture is reconstructed into
+  int n_slots = 2;               // slots the stream needs (from its SPS)
+  // dec_ref_pic_marking of the picture (first slice): sliding window, or memory_management_control_operation 1 commands
+  bool adaptive_marking = false;
+  std::vector<int> mmco1_diff;   // difference_of_pic_nums_minus1 of each "mark short-term picture unused" command
   bool any_deblock = false;      // some slice wants its macroblocks filtered
 };
 

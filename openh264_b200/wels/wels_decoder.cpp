@@ -63,26 +63,31 @@ class B2Decoder : public ISVCDecoder {
     const unsigned long long ts = info->uiInBsTimeStamp;
     info->iBufferStatus = 0;
     dst[0] = dst[1] = dst[2] = nullptr;
-    if (!src || len <= 0) return dsErrorFree;                     // flush: nothing is buffered
+    if (!src || len <= 0) { pending_.clear(); return dsErrorFree; }   // flush: no picture is ever held back (an incomplete one is dropped)
+    // Applications feed whole access units or, like the reference's console decoder, one NAL unit per call.  A picture may
+    // be coded as several slices: units are collected until they cover the picture (layer 2 answers -105 while they do not).
+    pending_.insert(pending_.end(), src, src + len);
     int32_t w = 0, h = 0, has_slice = 0;
-    int rc = b2h264_dec_probe(src, len, &w, &h, &has_slice);
-    if (rc) return refuse(rc);
+    int rc = b2h264_dec_probe(pending_.data(), (int32_t)pending_.size(), &w, &h, &has_slice);
+    if (rc) { pending_.clear(); return refuse(rc); }
     vcl_ = has_slice;
     if (w > 0 && h > 0 && (w != w_ || h != h_)) {                 // a (new) SPS: size the GPU decoder for it
       if (dec_) { b2h264_dec_destroy(dec_); dec_ = nullptr; }
       if (pic_) { cudaFreeHost(pic_); pic_ = nullptr; }
       b2h264_dec_config cfg;
       cfg.width = w; cfg.height = h; cfg.n_streams = 1; cfg.device = 0;
-      if (b2h264_dec_create(&cfg, &dec_) != 0 || !dec_) { dec_ = nullptr; return dsOutOfMemory; }
-      if (cudaHostAlloc((void**)&pic_, (size_t)w * h * 3 / 2, cudaHostAllocDefault) != cudaSuccess) { pic_ = nullptr; return dsOutOfMemory; }
+      if (b2h264_dec_create(&cfg, &dec_) != 0 || !dec_) { dec_ = nullptr; pending_.clear(); return dsOutOfMemory; }
+      if (cudaHostAlloc((void**)&pic_, (size_t)w * h * 3 / 2, cudaHostAllocDefault) != cudaSuccess) { pic_ = nullptr; pending_.clear(); return dsOutOfMemory; }
       w_ = w; h_ = h;
     }
-    if (!dec_) return dsNoParamSets;
-    const uint8_t* au[1] = {src};
-    const int32_t nb[1] = {len};
+    if (!dec_) { pending_.clear(); return dsNoParamSets; }
+    const uint8_t* au[1] = {pending_.data()};
+    const int32_t nb[1] = {(int32_t)pending_.size()};
     uint8_t* out[1] = {pic_};
     int32_t got[1] = {0};
     rc = b2h264_dec_decode2(dec_, au, nb, out, got);
+    if (rc == -105) return dsErrorFree;                           // more slices of this picture to come
+    pending_.clear();
     if (rc) return refuse(rc);
     if (got[0]) {
       frames_++;
@@ -168,6 +173,7 @@ class B2Decoder : public ISVCDecoder {
   uint8_t* pic_ = nullptr;
   int w_ = 0, h_ = 0;
   long frames_ = 0;
+  std::vector<uint8_t> pending_;         // NAL units of a picture whose slices have not all arrived yet
 };
 
 }  // namespace

@@ -255,10 +255,13 @@ extern "C" long emu_encode(const uint8_t* yuv, int w, int h, int nframes, int qp
 extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, int* w, int* h) {
   b2h264_build_host_tables();
   b2h264::ParserState st;
-  std::vector<uint8_t> pic[2][3];
+  // picture slots (decoded picture buffer): one contiguous buffer per plane, slot k at k * slot_bytes[pl]
+  std::vector<uint8_t> dpb;                 // slot k = one whole padded picture (Y, U, V) at k * pic_bytes, like the device layout
+  size_t pic_bytes = 0, y_bytes = 0, c_bytes = 0;
+  int n_slots = 0;
   std::vector<MbInfo> mbi;
   static MbScratch scratch;
-  int cur_rec = 0, frames = 0;
+  int frames = 0;
   long outpos = 0;
   bool have_buffers = false;
   auto is_start = [&](long k) { return k + 2 < len && bs[k] == 0 && bs[k + 1] == 0 && bs[k + 2] == 1; };
@@ -291,12 +294,13 @@ extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, i
       b2h264::StreamCtl geo;                                                    // picture geometry helpers
       geo.sp = st.sp;
       if (have_buffers && (int)mbi.size() != st.sp.mb_w * st.sp.mb_h) return -4;   // picture size changed mid-stream
-      if (!have_buffers) {
-        for (int b = 0; b < 2; b++) {
-          pic[b][0].assign((size_t)geo.rec_stride_y() * geo.rec_rows_y() + 64, 0);
-          pic[b][1].assign((size_t)geo.rec_stride_c() * geo.rec_rows_c() + 64, 0);
-          pic[b][2].assign((size_t)geo.rec_stride_c() * geo.rec_rows_c() + 64, 0);
-        }
+      if (!have_buffers || pp.n_slots > n_slots) {
+        if (have_buffers && !pp.ss.idr) return -5;                               // more slots needed mid-sequence
+        n_slots = pp.n_slots;
+        y_bytes = (size_t)geo.rec_stride_y() * geo.rec_rows_y() + 64;
+        c_bytes = (size_t)geo.rec_stride_c() * geo.rec_rows_c() + 64;
+        pic_bytes = y_bytes + 2 * c_bytes;
+        dpb.assign(pic_bytes * n_slots, 0);
         mbi.assign((size_t)st.sp.mb_w * st.sp.mb_h, MbInfo());
         have_buffers = true;
       }
@@ -309,9 +313,11 @@ extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, i
       memset(&f, 0, sizeof(f));
       for (int pl = 0; pl < 3; pl++) {
         const int pad = pl ? 16 : 32, stp = pl ? p.rec_stride_c : p.rec_stride_y;
-        f.rec[pl] = pic[cur_rec][pl].data() + (size_t)pad * stp + pad;
-        f.ref[pl] = pic[1 - cur_rec][pl].data() + (size_t)pad * stp + pad;
+        f.dpb0[pl] = dpb.data() + (pl == 0 ? 0 : y_bytes + (pl - 1) * c_bytes) + (size_t)pad * stp + pad;
+        f.rec[pl] = const_cast<uint8_t*>(f.dpb0[pl]) + (size_t)pp.cur_slot * pic_bytes;
+        f.ref[pl] = f.dpb0[pl];
       }
+      f.dpb_stride = (int64_t)pic_bytes;
       f.mbi = mbi.data();
       for (int mby = 0; mby < p.mb_h; mby++)
         for (int mbx = 0; mbx < p.mb_w; mbx++) dec_one_mb(p, f, scratch, mbx, mby, pp.mbs[(size_t)mby * p.mb_w + mbx], pp.aux[(size_t)mby * p.mb_w + mbx]);
@@ -325,7 +331,6 @@ extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, i
         for (int y = 0; y < ph; y++) { memcpy(out + outpos, f.rec[pl] + (size_t)y * stp, pw); outpos += pw; }
       }
       frames++;
-      if (pp.is_ref) cur_rec = 1 - cur_rec;     // a non-reference picture leaves the reference where it is
       au_begin = au_end;
     }
     pos = next;

@@ -203,3 +203,31 @@ def synth_clip(w, h, n, seed=264, noise=3):
         v = np.clip(128 - (sub - 128) // 6, 16, 240).astype(np.uint8)
         frames.append(np.concatenate([y.ravel(), u[:h // 2, :w // 2].ravel(), v[:h // 2, :w // 2].ravel()]))
     return np.concatenate(frames)
+
+
+def split_access_units(bs):
+    """Annex-B stream -> list of access units (bytes).  An access unit ends with a slice NAL (type 1 / 5) that is followed by a
+    non-slice NAL or by a slice with first_mb_in_slice == 0 (its ue(v) is the single bit 1 right after the NAL header)."""
+    bs = bytes(bs)
+    starts, i, n = [], 0, len(bs)
+    while i + 3 <= n:
+        if bs[i] == 0 and bs[i + 1] == 0 and bs[i + 2] == 1:
+            starts.append((i - 1 if i > 0 and bs[i - 1] == 0 else i, i + 3))      # (unit start incl. zero_byte, header position)
+            i += 3
+        else:
+            i += 1
+    aus, begin = [], starts[0][0] if starts else 0
+    for k, (_, hdr) in enumerate(starts):
+        t = bs[hdr] & 31
+        if t not in (1, 5):
+            continue
+        last = True
+        if k + 1 < len(starts):
+            nh = starts[k + 1][1]
+            if (bs[nh] & 31) in (1, 5) and nh + 1 < n and not (bs[nh + 1] & 0x80):
+                last = False
+        if last:
+            end = starts[k + 1][0] if k + 1 < len(starts) else n
+            aus.append(bs[begin:end])
+            begin = end
+    return aus

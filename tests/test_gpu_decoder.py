@@ -59,3 +59,50 @@ def test_gpu_decoder_rejects_unsupported_stream():
     with pytest.raises(B2H264Error):
         dec.decode([b"\x00\x00\x00\x01\x67\x64\x00\x1f\xac\xd9\x40\x50\x05\xbb\x01\x10"])      # a High-profile SPS
     dec.close()
+
+
+# ---- the reference's own conformance vectors through the GPU decoder ----------------------------------------------------
+CONF_DIR = os.path.join(ROOT, "tests", "golden", "conformance")
+
+
+def _conformance():
+    import json
+    tab = dict((p.split("/")[-1], s) for p, s in json.load(open(os.path.join(ROOT, "tests", "golden", "reference_decoder_hashes.json")))["pairs"])
+    return sorted((f, tab[f]) for f in os.listdir(CONF_DIR) if f in tab)
+
+
+def test_gpu_decoder_conformance_batch():
+    """17 of the reference's decoder test vectors (test/api/decoder_test.cpp:90-142) — BASELINE.json configs[0]'s BA_MW_D.264 among
+    them — decoded TOGETHER as one batch of streams by the GPU decoder: different slice structures, reference-frame counts
+    (the picture-slot array grows while others are mid-stream), partition shapes; every stream must reproduce the PUBLISHED
+    SHA-1 of its pictures."""
+    import hashlib
+    from openh264_b200.binding import BatchDecoder, probe_access_unit
+    items = [(f, s) for f, s in _conformance() if f != "Static.264"]                  # the 176x144 ones
+    streams = [h264lib.split_access_units(open(os.path.join(CONF_DIR, f), "rb").read()) for f, _ in items]
+    assert all(probe_access_unit(aus[0])[:2] == (176, 144) for aus in streams)
+    dec = BatchDecoder(176, 144, n_streams=len(items))
+    hashes = [hashlib.sha1() for _ in items]
+    for k in range(max(len(a) for a in streams)):
+        pics = dec.decode2([a[k] if k < len(a) else None for a in streams])
+        for i, p in enumerate(pics):
+            assert (p is not None) == (k < len(streams[i])), (items[i][0], k)
+            if p is not None:
+                hashes[i].update(p.tobytes())
+    dec.close()
+    bad = [items[i][0] for i in range(len(items)) if hashes[i].hexdigest() != items[i][1]]
+    assert not bad, bad
+
+
+def test_gpu_decoder_conformance_other_size():
+    import hashlib
+    from openh264_b200.binding import BatchDecoder, probe_access_unit
+    sha = dict(_conformance())["Static.264"]
+    aus = h264lib.split_access_units(open(os.path.join(CONF_DIR, "Static.264"), "rb").read())
+    w, h, _ = probe_access_unit(aus[0])
+    dec = BatchDecoder(w, h)
+    hs = hashlib.sha1()
+    for au in aus:
+        hs.update(dec.decode([au])[0].tobytes())
+    dec.close()
+    assert hs.hexdigest() == sha

@@ -131,3 +131,18 @@ def test_broker_many_encoder_objects_one_batch(tmp_path, threads, slots):
         outs[tag] = [open(os.path.join(str(tmp_path), "%s.%d.264" % (tag, t)), "rb").read() for t in range(threads)]
     for t in range(threads):
         assert len(outs["ref"][t]) > 0 and outs["ref"][t] == outs["b2"][t], "thread %d differs from the reference" % t
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["BA_MW_D.264", "SVA_Base_B.264", "MR1_MW_A.264"])
+def test_decoder_drop_in_on_conformance_streams(tmp_path, name):
+    """the reference's test vectors through ISVCDecoder, one NAL unit per DecodeFrameNoDelay call (several slices per
+    picture: the picture appears with its last slice; multiple reference frames): identical pictures and call log with the
+    compiled reference and with our library.  BA_MW_D.264 is BASELINE.json configs[0]."""
+    assert os.path.exists(DEC_DRIVER) and os.path.exists(OURLIB), "prebuilt layer-3 artefacts missing on the GPU box"
+    bs = open(os.path.join(ROOT, "tests", "golden", "conformance", name), "rb").read()
+    r0, y0, l0 = drive_dec(REFLIB, bs, str(tmp_path), "ref")
+    r1, y1, l1 = drive_dec(OURLIB, bs, str(tmp_path), "b2")
+    assert r0.returncode == 0 and r1.returncode == 0, r0.stderr + r1.stderr
+    assert len(y0) > 0 and y0 == y1
+    assert l0 == l1, "call log differs:\n" + l0[:2000] + "\n---\n" + l1[:2000]

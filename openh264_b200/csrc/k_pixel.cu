@@ -270,6 +270,115 @@ k_mc_sad_tiled(const uint8_t* __restrict__ cur, int cs, const uint8_t* __restric
 }
 
 // ------------------------------------------------------------------------------------------------
+// Packed sub-sample interpolation out of a staged tile (shared memory, row pitch P): one lane produces EIGHT horizontally
+// adjacent prediction samples of one row as two words, from word loads only.
+//   horizontal 6-tap: two DP4A per sample (unsigned samples x signed taps (1,-5,20,20) and (-5,1,0,0) on byte windows)
+//   vertical 6-tap:   two samples per register as 16-bit halves, biased so that every intermediate stays non-negative
+//   centre:           vertical pass (unrounded, 16 columns) in the packed form, horizontal pass on the 16-bit intermediates
+// Same arithmetic as McHorVer20 / McHorVer02 / McHorVer22 (codec/common/src/mc.cpp:187-231): (x + 16) >> 5, (x + 512) >> 10, clip.
+template <int N>
+__device__ __forceinline__ void seg_words(const uint8_t* a, uint32_t* s) {      // N words starting at ANY byte address
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(a) & ~uintptr_t(3));
+  const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(a) & 3) * 8;
+  uint32_t r[N + 1];
+#pragma unroll
+  for (int k = 0; k <= N; k++) r[k] = w[k];
+#pragma unroll
+  for (int k = 0; k < N; k++) s[k] = __funnelshift_r(r[k], r[k + 1], sh);
+}
+// four unsigned bytes of a times four signed bytes of b, plus c (dp4a.u32.s32)
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
+  return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
+}
+// half-sample row H(x0 .. x0+7) at row pointer `row` (sample x0 at row[0])
+__device__ __forceinline__ uint2 h8(const uint8_t* row) {
+  uint32_t s[4];
+  seg_words<4>(row - 2, s);
+  int v[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const uint32_t w0 = (i & 3) ? __funnelshift_r(s[i >> 2], s[(i >> 2) + 1], 8 * (i & 3)) : s[i >> 2];
+    const int j = i + 4;
+    const uint32_t w1 = (j & 3) ? __funnelshift_r(s[j >> 2], s[(j >> 2) + 1], 8 * (j & 3)) : s[j >> 2];
+    v[i] = dp4a_us(w0, (int)0x1414FB01, dp4a_us(w1, (int)0x000001FB, 16));
+    v[i] = min(max(v[i] >> 5, 0), 255);
+  }
+  return make_uint2(pack4(v[0], v[1], v[2], v[3]), pack4(v[4], v[5], v[6], v[7]));
+}
+// packed vertical 6-tap of NW words per row: t[q] = (tap(col 2q) + 2560) | (tap(col 2q + 1) + 2560) << 16, rows a..f at base + k * P
+template <int NW>
+__device__ __forceinline__ void v_taps(const uint8_t* base, int P, uint32_t* t) {
+#pragma unroll
+  for (int q = 0; q < 2 * NW; q++) t[q] = 0x0A000A00u;
+  // rows in the order c, d (x20), a, f (x1), b, e (x -5): every partial sum stays positive in both halves
+  const int order[6] = {2, 3, 0, 5, 1, 4};
+#pragma unroll
+  for (int o = 0; o < 6; o++) {
+    uint32_t s[NW];
+    seg_words<NW>(base + order[o] * P, s);
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+      const uint32_t lo = __byte_perm(s[k], 0, 0x4140), hi = __byte_perm(s[k], 0, 0x4342);
+      if (o < 2) { t[2 * k] += 20u * lo; t[2 * k + 1] += 20u * hi; }
+      else if (o < 4) { t[2 * k] += lo; t[2 * k + 1] += hi; }
+      else { t[2 * k] -= 5u * lo; t[2 * k + 1] -= 5u * hi; }
+    }
+  }
+}
+// half-sample column V(x0 .. x0+7): `p` points at sample (x0, row) of the integer plane
+__device__ __forceinline__ uint2 v8(const uint8_t* p, int P) {
+  uint32_t t[4];
+  v_taps<2>(p - 2 * P, P, t);
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint32_t r = ((t[q] + 0x00100010u) >> 5) & 0x07FF07FFu;            // ((tap + 16) >> 5) + 80 in each half
+    t[q] = __vminu2(__vmaxu2(r, 0x00500050u), 0x014F014Fu) - 0x00500050u;    // clip to 0..255
+  }
+  return make_uint2(__byte_perm(t[0], t[1], 0x6420), __byte_perm(t[2], t[3], 0x6420));
+}
+// centre samples C(x0 .. x0+7) of the row of `p`
+__device__ __forceinline__ uint2 c8(const uint8_t* p, int P) {
+  uint32_t t[8];
+  v_taps<4>(p - 2 * P - 2, P, t);                       // unrounded vertical taps (+2560) of columns x0-2 .. x0+13
+  int m[13];
+#pragma unroll
+  for (int j = 0; j < 13; j++) m[j] = (int)((j & 1) ? (t[j >> 1] >> 16) : (t[j >> 1] & 0xffffu));
+  int v[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int x = (m[i] + m[i + 5]) - 5 * (m[i + 1] + m[i + 4]) + 20 * (m[i + 2] + m[i + 3]) - 32 * 2560 + 512;
+    v[i] = min(max(x >> 10, 0), 255);
+  }
+  return make_uint2(pack4(v[0], v[1], v[2], v[3]), pack4(v[4], v[5], v[6], v[7]));
+}
+__device__ __forceinline__ uint2 g8(const uint8_t* p) {
+  uint32_t s[2];
+  seg_words<2>(p, s);
+  return make_uint2(s[0], s[1]);
+}
+__device__ __forceinline__ uint2 avg8(uint2 a, uint2 b) { return make_uint2(__vavgu4(a.x, b.x), __vavgu4(a.y, b.y)); }
+// eight prediction samples at quarter-sample phase (fx, fy); p = integer sample (x0, row) in the tile
+__device__ __forceinline__ uint2 qpel8(const uint8_t* p, int P, int fx, int fy) {
+  if (fy == 0) {
+    const uint2 b = h8(p);
+    return fx == 2 ? b : avg8(b, g8(p + (fx == 3)));
+  }
+  if (fx == 0) {
+    const uint2 h = v8(p, P);
+    return fy == 2 ? h : avg8(h, g8(p + (fy == 3 ? P : 0)));
+  }
+  if (fx == 2 && fy == 2) return c8(p, P);
+  if (fx == 2) return avg8(h8(p + (fy == 3 ? P : 0)), c8(p, P));
+  if (fy == 2) return avg8(v8(p + (fx == 3), P), c8(p, P));
+  return avg8(h8(p + (fy == 3 ? P : 0)), v8(p + (fx == 3), P));
+}
+
+// ------------------------------------------------------------------------------------------------
 // TMA form of the tiled unit (sm_100a: cp.async.bulk.tensor + mbarrier complete_tx).  Same tile geometry; ONE
 // thread issues two bulk tensor copies (current tile 128 x 64, reference tile + halo 160 x 85) and every warp
 // waits on the mbarrier: no per-thread address arithmetic for staging, out-of-picture parts are zero-filled by
@@ -335,14 +444,12 @@ k_mc_sad_tma(const __grid_constant__ CUtensorMap tm_cur, const __grid_constant__
           asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(pa + y * MCT_PITCH + x + 4));
           s += __vsadu4(cw, __funnelshift_r(lo, hi, sh));
         }
-      } else {
-        const uint8_t* cm = &t_cur[16 * ty][16 * tx];
-        const uint8_t* p = &t_ref[MCT_TOP + 16 * ty][MCT_HALO_X + 16 * tx] + (mvy >> 2) * MCT_PITCH + (mvx >> 2);
-#pragma unroll 2
-        for (int i = l; i < 256; i += 32) {
-          const int y = i >> 4, x = i & 15;
-          s += iabs((int)cm[y * (16 * MCT_W) + x] - luma_qpel_sample(p + y * MCT_PITCH + x, MCT_PITCH, fx, fy));
-        }
+      } else {                                 // fractional vector: lane = (row, 8-sample half), packed interpolation, packed SAD
+        const int r = l >> 1, x0 = (l & 1) * 8;
+        const uint8_t* p = &t_ref[MCT_TOP + 16 * ty + r][MCT_HALO_X + 16 * tx + x0] + (mvy >> 2) * MCT_PITCH + (mvx >> 2);
+        const uint2 pr = qpel8(p, MCT_PITCH, fx, fy);
+        const uint2 cw = *reinterpret_cast<const uint2*>(&t_cur[16 * ty + r][16 * tx + x0]);
+        s = (int)(__vsadu4(cw.x, pr.x) + __vsadu4(cw.y, pr.y));
       }
       s = warp_sum(s);
       if (l == 0) cost[(size_t)m * k + c] = s;

@@ -6,6 +6,8 @@ for cfg in "2 48 48" "2 64 48" "2 128 48" "3 64 48" "3 128 48" "3 48 48" "3 48 3
   timeout 60 tools/_build/tma_probe $cfg 0 2>&1 | head -2
 done | tee $O/tma_probe.txt
 export B2H264_ENC_WIN=2
+echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -15 | tee $O/gpu_tests.txt
+echo "== MC+SAD roofline"; timeout 300 python tools/mc_sad_roofline.py | tee $O/mc_sad.txt
 echo "== CTA shape variants (256 streams)"
 for v in "" openh264_b200/variants/lib_wpc12x2.so openh264_b200/variants/lib_wpc8x3.so; do
   B2H264_LIB=$v timeout 600 python tools/enc_stats.py 256 > $O/enc_stats_$(basename "${v:-default}").txt 2>&1

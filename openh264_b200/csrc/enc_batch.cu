@@ -189,7 +189,7 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
   }
   // TMA descriptors of the two picture sets: (x, y) from the padded origin of the luma plane, z = stream
   e->have_tmap = b2h264_make_tmap_planes(e->tmap_pic, e->d_pic_all, (uint64_t)c0.rec_stride_y(), (uint64_t)c0.rec_rows_y(), 2 * (uint64_t)S,
-                                         (uint64_t)c0.rec_stride_y(), (uint64_t)e->pic_bytes, 48, 48) == 0;
+                                         (uint64_t)c0.rec_stride_y(), (uint64_t)e->pic_bytes, 64, 48) == 0;
   if (e->have_tmap) {
     CK(cudaMalloc(&e->d_tmap, 128));
     CK(cudaMemcpy(e->d_tmap, e->tmap_pic, 128, cudaMemcpyHostToDevice));

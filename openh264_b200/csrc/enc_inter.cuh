@@ -278,26 +278,29 @@ MBK_HD void win_issue(const MbCtx& c, MbScratch& s, int sx, int sy) {
 #ifdef __CUDA_ARCH__
   warp_sync();
   if (c.win_mode == 0) { if (lane_id() == 0) s.win_ok = 0; warp_sync(); return; }
-  if (lane_id() == 0) { s.win_x0 = sx - 16; s.win_y0 = sy - 16; s.win_ok = 1; }
+  // plane coordinates (from the padded origin) of the window; X rounded down to a 16-byte boundary (bulk tensor copies need
+  // an aligned start; the padded stride is a multiple of 16, so the alignment is the same in every row)
+  const int X = (32 + c.mbx * 16 + sx - 16) & ~15, Y = 32 + c.mby * 16 + sy - 16, Z = c.p.ref_plane;
+  const int wx0 = X - 32 - c.mbx * 16;                  // window origin relative to the macroblock
+  if (lane_id() == 0) { s.win_x0 = wx0; s.win_y0 = sy - 16; s.win_ok = 1; }
   if (c.win_mode == 1) {
     if (lane_id() == 0) {
       const uint32_t dst = (uint32_t)__cvta_generic_to_shared(scratch_win(s));
       const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&c.wbar->bar);
-      const int X = 32 + c.mbx * 16 + sx - 16, Y = 32 + c.mby * 16 + sy - 16, Z = c.p.ref_plane;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // earlier generic accesses to the window bytes
       asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(WIN_W * WIN_H) : "memory");
       asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                    ::"r"(dst), "l"(c.tmap_ref), "r"(X), "r"(Y), "r"(Z), "r"(bar) : "memory");
     }
   } else {
-    // the warp's own loads: 48 rows x 12 words, unaligned source (two aligned loads + funnel shift each), all in flight together
-    const uint8_t* src = ref_luma(c, sx - 16, sy - 16);
+    // the warp's own loads: 48 rows x 16 aligned words, all in flight together
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(ref_luma(c, wx0, sy - 16));
     uint32_t* dst = reinterpret_cast<uint32_t*>(scratch_win(s));
-    const int rs = c.p.rec_stride_y;
-#pragma unroll 6
+    const int rs4 = c.p.rec_stride_y >> 2;
+#pragma unroll 8
     for (int i = lane_id(); i < WIN_H * (WIN_W / 4); i += MBK_WS) {
       const int r = i / (WIN_W / 4), w = i - r * (WIN_W / 4);
-      dst[i] = ld4u(src + (ptrdiff_t)r * rs + 4 * w);
+      dst[i] = src[(ptrdiff_t)r * rs4 + w];
     }
   }
   warp_sync();
@@ -412,12 +415,36 @@ MBK_FN void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy,
     const int x0 = ox + (mv0x >> 2) - 3 - s.win_x0, y0 = oy + (mv0y >> 2) - 3 - s.win_y0;
     if (x0 >= 0 && y0 >= 0 && x0 + 4 * wq <= WIN_W && y0 + wh <= WIN_H) { src = scratch_win(s) + y0 * WIN_W + x0; srs = WIN_W; }
   }
+#ifdef __CUDA_ARCH__
+  {
+    // the window's last rows share their bytes with the coefficient buffer this copy writes to: read everything into registers
+    // (at most 6 x 22 = 132 words: 5 per lane), then store
+    uint32_t v[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      const int i = lane_id() + 32 * k;
+      const int r = i / wq, q4 = (i - r * wq) << 2;
+      v[k] = i < wq * wh ? ld4u(src + (ptrdiff_t)r * srs + q4) : 0u;
+    }
+    warp_sync();
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      const int i = lane_id() + 32 * k;
+      if (i < wq * wh) {
+        const int r = i / wq, q4 = (i - r * wq) << 2;
+        uint8_t* d = win + r * QP_STRIDE + q4;
+        d[0] = (uint8_t)v[k]; d[1] = (uint8_t)(v[k] >> 8); d[2] = (uint8_t)(v[k] >> 16); d[3] = (uint8_t)(v[k] >> 24);
+      }
+    }
+  }
+#else
   for (int i = lane_id(); i < wq * wh; i += MBK_WS) {
     const int r = i / wq, q4 = (i - r * wq) << 2;
     const uint32_t v = ld4u(src + (ptrdiff_t)r * srs + q4);
     uint8_t* d = win + r * QP_STRIDE + q4;
     d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24);
   }
+#endif
   warp_sync();
   if (lane_id() == 0) s.win_ok = 0;          // the planes below overwrite the window bytes
   warp_sync();

@@ -39,7 +39,9 @@ struct InterState {
 // integer-search window of stage B: WIN_W x WIN_H reference luma samples around the 16x16 start point, staged by
 // ONE cp.async.bulk.tensor copy per macroblock (svc_motion_estimate.cpp:222-386 runs out of it: the 16-step
 // diamond never leaves +-16 samples around its start)
-enum { WIN_W = 48, WIN_H = 48 };
+// The bulk tensor copy needs a 16-byte aligned start in the plane: the window is 64 wide and starts at the aligned
+// address at or below (start - 16), which still covers [start - 16, start + 32).
+enum { WIN_W = 64, WIN_H = 48 };
 
 // Per-warp working set (shared memory on the device, a plain struct in the host emulation build).
 // Plain data only: the device scheduler parks the LIVE PART in global memory between stages — the prefix up to
@@ -62,16 +64,16 @@ struct alignas(128) MbScratch {
   alignas(16) MbOut out;        // staged output record: the header (MBOUT_HEADER_WORDS) is live, the levels are not
   // ---- not parked (except skip_pred / pred_y, see above) ------------------------------------------------------
   alignas(16) uint8_t pred_y[2][256];       // luma prediction ping-pong (pMemPredMb)
-  // The next three are contiguous and double as the search window (2304 of their 2368 bytes, 128-byte aligned for
+  // The next four are contiguous and double as the search window (3072 of their 3136 bytes, 128-byte aligned for
   // the bulk tensor copy): the window lives from the start of stage B's 16x16 search to the last sub-partition
-  // search; pred_c / qplane are first written by the refinement that follows, skip_pred is dead on that path.
+  // search; pred_c / qplane / coef are first written by the refinement that follows, skip_pred is dead on that path.
   alignas(128) uint8_t pred_c[2][128];      // chroma prediction ping-pong (Cb, Cr)
   uint8_t skip_pred[384];       // P-skip prediction (pSkipMb): Y 256, Cb 64, Cr 64
   uint8_t qplane[3][18 * 32];   // fractional refinement: half-sample planes H, V, C of the partition, stride 32
                                 // (pBufferInterPredMe, md.cpp:505-510)
+  int16_t coef[384];            // pCoeffLevel: transform coefficients (coding order, 16 per 4x4)
   alignas(16) uint8_t cur_y[256];           // current MB, stride 16
   uint8_t cur_c[128];           // Cb 0..63, Cr 64..127, stride 8
-  int16_t coef[384];            // pCoeffLevel: transform coefficients (coding order, 16 per 4x4)
   int16_t dc16[16];
   int32_t red[32];              // small scratch
   // kept in the scratch rather than on the per-thread stack: the stack of 768 threads does not fit L1 next to the
@@ -83,8 +85,9 @@ struct alignas(128) MbScratch {
   uint32_t t_last;              // phase timer (profiling builds only)
 };
 static_assert(offsetof(MbScratch, skip_pred) == offsetof(MbScratch, pred_c) + 256 &&
-              offsetof(MbScratch, qplane) == offsetof(MbScratch, skip_pred) + 384 && 256 + 384 + 3 * 18 * 32 >= WIN_W * WIN_H,
-              "pred_c / skip_pred / qplane double as the search window");
+              offsetof(MbScratch, qplane) == offsetof(MbScratch, skip_pred) + 384 && offsetof(MbScratch, coef) == offsetof(MbScratch, qplane) + 3 * 18 * 32 &&
+              256 + 384 + 3 * 18 * 32 + 768 >= WIN_W * WIN_H,
+              "pred_c / skip_pred / qplane / coef double as the search window");
 static_assert(offsetof(MbScratch, pred_c) % 128 == 0 && offsetof(MbScratch, skip_pred) % 16 == 0 && offsetof(MbScratch, pred_y) % 16 == 0 &&
               offsetof(MbScratch, out) % 16 == 0, "alignment of the parked ranges / the bulk copy destination");
 // bytes of the scratch that cross every stage boundary

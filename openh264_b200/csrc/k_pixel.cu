@@ -363,7 +363,8 @@ __device__ __forceinline__ uint2 g8(const uint8_t* p) {
 }
 __device__ __forceinline__ uint2 avg8(uint2 a, uint2 b) { return make_uint2(__vavgu4(a.x, b.x), __vavgu4(a.y, b.y)); }
 // eight prediction samples at quarter-sample phase (fx, fy); p = integer sample (x0, row) in the tile
-__device__ __forceinline__ uint2 qpel8(const uint8_t* p, int P, int fx, int fy) {
+// out of line on purpose: the integer-vector path of the tiled kernels keeps its own (small) register allocation
+__device__ __noinline__ uint2 qpel8(const uint8_t* p, int P, int fx, int fy) {
   if (fy == 0) {
     const uint2 b = h8(p);
     return fx == 2 ? b : avg8(b, g8(p + (fx == 3)));

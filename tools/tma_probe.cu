@@ -38,17 +38,17 @@ __global__ void k_probe(const __grid_constant__ CUtensorMap tm, const void* tm_g
     ctx[w].bar = &bar[w];
   }
   __syncthreads();
-  if ((variant & 2) && rank == 3 && bw == 48 && bh == 48) issue(&ctx[w], win[w], x + w, y, z);               // through a real function, pointer out of shared memory
+  if ((variant & 2) && rank == 3 && bw == 48 && bh == 48) issue(&ctx[w], win[w], x + 16 * w, y, z);               // through a real function, pointer out of shared memory
   else if (lane == 0) {
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(win[w]), b = (uint32_t)__cvta_generic_to_shared(&bar[w]);
     const void* t = (variant & 1) ? tm_global : (const void*)&tm;
     asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(b), "r"(bw * bh) : "memory");
     if (rank == 3)
       asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                   ::"r"(dst), "l"(t), "r"(x + w), "r"(y), "r"(z), "r"(b) : "memory");
+                   ::"r"(dst), "l"(t), "r"(x + 16 * w), "r"(y), "r"(z), "r"(b) : "memory");
     else
       asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                   ::"r"(dst), "l"(t), "r"(x + w), "r"(y), "r"(b) : "memory");
+                   ::"r"(dst), "l"(t), "r"(x + 16 * w), "r"(y), "r"(b) : "memory");
   }
   uint32_t ok = 0;
   const uint32_t b = (uint32_t)__cvta_generic_to_shared(&bar[w]);
@@ -59,6 +59,7 @@ __global__ void k_probe(const __grid_constant__ CUtensorMap tm, const void* tm_g
 int main(int argc, char** argv) {
   const int rank = argc > 1 ? atoi(argv[1]) : 3, bw = argc > 2 ? atoi(argv[2]) : 48, bh = argc > 3 ? atoi(argv[3]) : 48;
   const int only_variant = argc > 4 ? atoi(argv[4]) : -1;
+  const int x_arg = argc > 5 ? atoi(argv[5]) : 37;
   CKR(cudaSetDevice(0));
   CKR(cudaFree(0));
   const int W = 384, H = 256, N = 6;
@@ -78,11 +79,11 @@ int main(int argc, char** argv) {
     CKR(cudaMemcpy(dtm, &tm, 128, cudaMemcpyHostToDevice));
     for (int variant = 0; variant < 4; variant++) {
       if (only_variant >= 0 && variant != only_variant) continue;
-      const int x = 37, y = 11, z = rank == 3 ? 4 : 0;
+      const int x = x_arg, y = 11, z = rank == 3 ? 4 : 0;
       k_probe<<<1, 128>>>(tm, dtm, variant, x, y, z, dout, rank, bw, bh);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) {
-        printf("rank=%d box=%dx%d l2promo=%d variant=%d (desc %s, issued from %s): FAILED %s\n", rank, bw, bh, l2, variant, (variant & 1) ? "global" : "param",
+        printf("x=%d rank=%d box=%dx%d l2promo=%d variant=%d (desc %s, issued from %s): FAILED %s\n", x_arg, rank, bw, bh, l2, variant, (variant & 1) ? "global" : "param",
                (variant & 2) ? "function" : "kernel body", cudaGetErrorString(e));
         return 2;                                       // sticky error: the context is gone
       }
@@ -90,8 +91,8 @@ int main(int argc, char** argv) {
       CKR(cudaMemcpy(got, dout, sizeof(got), cudaMemcpyDeviceToHost));
       int bad = 0;
       for (int w = 0; w < 4; w++) for (int r = 0; r < bh; r++) for (int c = 0; c < bw; c++)
-        if (got[w * 4096 + r * bw + c] != h[z * plane + (size_t)(y + r) * W + x + w + c]) bad++;
-      printf("rank=%d box=%dx%d l2promo=%d variant=%d (desc %s, issued from %s): %s (%d wrong bytes)\n", rank, bw, bh, l2, variant, (variant & 1) ? "global" : "param",
+        if (got[w * 4096 + r * bw + c] != h[z * plane + (size_t)(y + r) * W + x + 16 * w + c]) bad++;
+      printf("x=%d rank=%d box=%dx%d l2promo=%d variant=%d (desc %s, issued from %s): %s (%d wrong bytes)\n", x_arg, rank, bw, bh, l2, variant, (variant & 1) ? "global" : "param",
              (variant & 2) ? "function" : "kernel body", bad ? "WRONG DATA" : "ok", bad);
     }
   }

@@ -28,6 +28,7 @@ struct b2h264_dec {
   StreamCtl geo;                          // picture geometry (strides, padded rows)
   std::vector<ParserState> parser;
   int slots = 2;                          // picture slots per stream (num_ref_frames + 1 of the most demanding stream so far)
+  std::vector<int> out_cx, out_cy;        // per active stream: luma samples cropped at the left / top of the output
   std::vector<int> out_slot;              // per active stream: slot of the picture decoded in this call
   std::vector<int> act;
   std::vector<uint8_t> act_ref;           // is the picture of act[i] a reference picture
@@ -104,7 +105,7 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
   CK(cudaSetDevice(d->cfg.device));
   const int S = d->S;
   int deblock = 1;
-  d->act.clear(); d->act_ref.clear(); d->out_slot.clear();
+  d->act.clear(); d->act_ref.clear(); d->out_slot.clear(); d->out_cx.clear(); d->out_cy.clear();
   for (int s = 0; s < S; s++) {
     if (got_picture) got_picture[s] = 0;
     if (!au[s] || au_bytes[s] <= 0) {
@@ -139,7 +140,7 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
     if (d->act.empty()) deblock = 0;
     if (pic.any_deblock) deblock = 1;               // the filter kernel runs if any slice of any stream wants it (per-MB control inside)
     const int i = (int)d->act.size();
-    d->act.push_back(s); d->act_ref.push_back(pic.is_ref ? 1 : 0); d->out_slot.push_back(pic.cur_slot);
+    d->act.push_back(s); d->act_ref.push_back(pic.is_ref ? 1 : 0); d->out_slot.push_back(pic.cur_slot); d->out_cx.push_back(pic.crop_left); d->out_cy.push_back(pic.crop_top);
     memcpy(d->h_recs + (size_t)i * d->n_mb, pic.mbs.data(), (size_t)d->n_mb * sizeof(MbOut));
     memcpy(d->h_aux + (size_t)i * d->n_mb, pic.aux.data(), (size_t)d->n_mb * sizeof(DecMbAux));
     StreamFrame& F = d->h_sf[i];
@@ -166,7 +167,8 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
     for (int pl = 0; pl < 3; pl++) {
       const int pw = pl ? w / 2 : w, ph = pl ? h / 2 : h;
       const int stp = pl ? d->geo.rec_stride_c() : d->geo.rec_stride_y();
-      CK(cudaMemcpy2DAsync(dst, pw, d->plane0(rec, s, pl), stp, pw, ph, cudaMemcpyDeviceToHost, d->st));
+      const uint8_t* from = d->plane0(rec, s, pl) + (size_t)(d->out_cy[i] >> (pl ? 1 : 0)) * stp + (d->out_cx[i] >> (pl ? 1 : 0));
+      CK(cudaMemcpy2DAsync(dst, pw, from, stp, pw, ph, cudaMemcpyDeviceToHost, d->st));
       dst += (size_t)pw * ph;
     }
     if (got_picture) got_picture[s] = 1;

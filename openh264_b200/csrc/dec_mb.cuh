@@ -120,6 +120,28 @@ MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch
     if ((nb_i & NB_LEFT) && MBT_IS_INTER(s.nbi[3].mb_type)) nb_i &= ~NB_LEFT;
   }
   const bool L = (nb_i & NB_LEFT) != 0, T = (nb_i & NB_TOP) != 0;
+  if (type == MBT_IPCM) {                       // raw samples: straight into the tile; nothing to predict or transform
+    const uint8_t* py = reinterpret_cast<const uint8_t*>(m.luma);
+    const uint8_t* pcs = reinterpret_cast<const uint8_t*>(m.chroma_ac);
+    for (int i = lane_id(); i < 256; i += MBK_WS) *tile_y(s.tile, i & 15, i >> 4) = py[i];
+    for (int i = lane_id(); i < 64; i += MBK_WS) {
+      *tile_c(s.tile.u, i & 7, i >> 3) = pcs[i];
+      *tile_c(s.tile.v, i & 7, i >> 3) = pcs[64 + i];
+    }
+    warp_sync();
+    mb_store_recon(c, s);
+    if (lane_id() == 0) {
+      s.info.qp = 0; s.info.qp_c = (uint8_t)tbl_chroma_qp(0);
+      s.info.p16x16_mv[0] = (int16_t)aux.slice;
+      s.info.p16x16_mv[1] = (int16_t)(aux.dbk_idc | ((aux.alpha_off + 16) << 2) | ((aux.beta_off + 16) << 7));
+    }
+    warp_sync();
+    const uint32_t* si0 = reinterpret_cast<const uint32_t*>(&s.info);
+    uint32_t* di0 = reinterpret_cast<uint32_t*>(c.f.mbi + (mby * p.mb_w + mbx));
+    for (int i = lane_id(); i < (int)(sizeof(MbInfo) / 4); i += MBK_WS) di0[i] = si0[i];
+    warp_sync();
+    return;
+  }
   if (type == MBT_P8x8 && (aux.flags & DECAUX_SUB)) {
     // sub-macroblock partitions (8x4, 4x8, 4x4): every partition predicts its vector from the cells decoded so far —
     // the in-macroblock cells start as "not available" and are filled in decoding order (8.4.1.3.2: a partition that

@@ -5,10 +5,11 @@
 
 // macroblock types (own numbering)
 enum {
-  MBT_I4x4 = 0, MBT_I16x16 = 1, MBT_P16x16 = 2, MBT_P16x8 = 3, MBT_P8x16 = 4, MBT_P8x8 = 5, MBT_PSKIP = 6
+  MBT_I4x4 = 0, MBT_I16x16 = 1, MBT_P16x16 = 2, MBT_P16x8 = 3, MBT_P8x16 = 4, MBT_P8x8 = 5, MBT_PSKIP = 6,
+  MBT_IPCM = 7               // decoder only: raw samples (luma in MbOut::luma as 256 bytes, Cb / Cr in MbOut::chroma_ac as 2 x 64 bytes)
 };
-#define MBT_IS_INTRA(t) ((t) <= MBT_I16x16)
-#define MBT_IS_INTER(t) ((t) >= MBT_P16x16)
+#define MBT_IS_INTRA(t) ((t) <= MBT_I16x16 || (t) == MBT_IPCM)
+#define MBT_IS_INTER(t) ((t) >= MBT_P16x16 && (t) <= MBT_PSKIP)
 
 // Per-macroblock state kept in HBM for the frame being coded: read by the neighbours' mode decision,
 // by the deblocking pass and (through MbOut) by the host entropy coder.

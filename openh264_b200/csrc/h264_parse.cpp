@@ -85,31 +85,44 @@ std::vector<Nal> split_nals(const uint8_t* d, size_t n) {
   return out;
 }
 
+void activate_sps(ParserState* st, int id) {
+  const SpsFields& f = st->sps_tab[id];
+  const int pps_id = st->sp.pps_id, qp = st->sp.qp;
+  st->sp = f.sp; st->sp.pps_id = pps_id; st->sp.qp = qp;
+  st->log2_max_frame_num = f.log2_max_frame_num; st->poc_type = f.poc_type; st->log2_max_poc_lsb = f.log2_max_poc_lsb;
+  st->delta_pic_order_always_zero = f.delta_pic_order_always_zero;
+  st->n_slots = f.n_slots; st->crop_left = f.crop_left; st->crop_top = f.crop_top;
+  st->have_sps = true;
+}
+
 int parse_sps(BitReader& r, ParserState* st) {
   const int profile = (int)r.get(8);
-  r.get(8);                                   // constraint flags + reserved
+  const int flags = (int)r.get(8);            // constraint flags + reserved
   const int level = (int)r.get(8);
   const int sps_id = (int)r.ue();
-  if (profile != 66) return PARSE_UNSUPPORTED;            // Baseline only (no chroma_format_idc / scaling lists)
+  if (sps_id < 0 || sps_id > 31) return PARSE_INVALID;
+  // Baseline, or Main / Extended streams that declare Baseline conformance (constraint_set0_flag): no chroma_format_idc / scaling lists
+  if (!(profile == 66 || ((profile == 77 || profile == 88) && (flags & 0x80)))) return PARSE_UNSUPPORTED;
+  SpsFields f;
   {
     const uint32_t v = r.ue();
     if (v > 12) return PARSE_INVALID;                     // log2_max_frame_num_minus4 in 0..12 (7.4.2.1.1)
-    st->log2_max_frame_num = (int)v + 4;
+    f.log2_max_frame_num = (int)v + 4;
   }
-  st->poc_type = (int)r.ue();
-  if (st->poc_type == 0) {
+  f.poc_type = (int)r.ue();
+  if (f.poc_type == 0) {
     const uint32_t v = r.ue();
     if (v > 12) return PARSE_INVALID;
-    st->log2_max_poc_lsb = (int)v + 4;
-  } else if (st->poc_type == 1) {
+    f.log2_max_poc_lsb = (int)v + 4;
+  } else if (f.poc_type == 1) {
     // picture order count type 1 (7.3.2.1.1): only parsed — pictures leave the decoder in decoding order (no B slices in this
     // stream class, so that is also the output order)
-    st->delta_pic_order_always_zero = r.bit() != 0;
+    f.delta_pic_order_always_zero = r.bit() != 0;
     r.se(); r.se();                                       // offset_for_non_ref_pic, offset_for_top_to_bottom_field
     const uint32_t n_cycle = r.ue();
     if (n_cycle > 255) return PARSE_INVALID;
     for (uint32_t i = 0; i < n_cycle; i++) r.se();
-  } else if (st->poc_type != 2) return PARSE_INVALID;
+  } else if (f.poc_type != 2) return PARSE_INVALID;
   StreamParams sp;
   memset(&sp, 0, sizeof(sp));
   sp.num_ref_frames = (int)r.ue();
@@ -132,36 +145,47 @@ int parse_sps(BitReader& r, ParserState* st) {
   if (sp.width < 2 || sp.height < 2) return PARSE_INVALID;
   sp.level_idc = level;
   sp.sps_id = sps_id;
-  if (cl || ct) return PARSE_UNSUPPORTED;     // left / top cropping: never produced by the encoders this mirrors
-  sp.pps_id = st->sp.pps_id;
-  sp.qp = st->sp.qp;
-  st->n_slots = sp.num_ref_frames + 1 < 2 ? 2 : sp.num_ref_frames + 1;
-  st->sp = sp;
-  st->have_sps = true;                        // VUI (if any) is not needed for reconstruction
+  f.sp = sp;
+  f.crop_left = cl; f.crop_top = ct;          // the picture is decoded whole; the output skips 2 * crop samples at the left / top
+  f.n_slots = sp.num_ref_frames + 1 < 2 ? 2 : sp.num_ref_frames + 1;
+  f.valid = true;                             // VUI (if any) is not needed for reconstruction
+  st->sps_tab[sps_id] = f;
+  if (!st->have_sps || st->sp.sps_id == sps_id) activate_sps(st, sps_id);
   return PARSE_OK;
+}
+
+void activate_pps(ParserState* st, int id) {
+  const PpsFields& f = st->pps_tab[id];
+  st->pic_init_qp = f.pic_init_qp; st->deblocking_control = f.deblocking_control; st->num_ref_idx_default = f.num_ref_idx_default;
+  st->constrained_intra_pred = f.constrained_intra_pred;
+  st->sp.pps_id = id;
+  st->have_pps = true;
 }
 
 int parse_pps(BitReader& r, ParserState* st) {
   const int pps_id = (int)r.ue();
   const int sps_id = (int)r.ue();
-  if (!st->have_sps || sps_id != st->sp.sps_id) return PARSE_NO_PARAMETER_SETS;
+  if (pps_id < 0 || pps_id > 255 || sps_id < 0 || sps_id > 31) return PARSE_INVALID;
+  PpsFields f;
+  f.sps_id = sps_id;
   if (r.bit()) return PARSE_UNSUPPORTED;      // entropy_coding_mode_flag: CABAC
   const int bottom_field_poc = r.bit();
   if (r.ue() != 0) return PARSE_UNSUPPORTED;  // slice groups
-  st->num_ref_idx_default = (int)r.ue() + 1;
+  f.num_ref_idx_default = (int)r.ue() + 1;
   r.ue();
   if (r.bit()) return PARSE_UNSUPPORTED;      // weighted_pred_flag
   r.get(2);
-  st->pic_init_qp = 26 + r.se();
+  f.pic_init_qp = 26 + r.se();
   r.se();
   if (r.se() != 0) return PARSE_UNSUPPORTED;  // chroma_qp_index_offset
-  st->deblocking_control = r.bit() != 0;
-  st->constrained_intra_pred = r.bit() != 0;
+  f.deblocking_control = r.bit() != 0;
+  f.constrained_intra_pred = r.bit() != 0;
   if (r.bit()) return PARSE_UNSUPPORTED;      // redundant_pic_cnt_present_flag
   if (bottom_field_poc) return PARSE_UNSUPPORTED;
   if (!r.ok()) return PARSE_TRUNCATED;
-  st->sp.pps_id = pps_id;
-  st->have_pps = true;
+  f.valid = true;
+  st->pps_tab[pps_id] = f;
+  if (st->sps_tab[sps_id].valid && (!st->have_pps || st->sp.pps_id == pps_id)) { activate_sps(st, sps_id); activate_pps(st, pps_id); }
   return PARSE_OK;
 }
 
@@ -260,10 +284,8 @@ int cbp_from_code(int code, bool intra) {
 }
 
 int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pic) {
-  if (!st->have_sps || !st->have_pps) return PARSE_NO_PARAMETER_SETS;
   const bool idr = nal.type == 5;
   if (!idr && !st->have_ref) return PARSE_INVALID;            // a P picture before any IDR: nothing to predict from
-  const int mbw = st->sp.mb_w, n = st->sp.mb_w * st->sp.mb_h;
   const bool first_slice = pic->n_slices == 0;
   const int first_mb = (int)r.ue();
   if (first_mb != pic->next_mb) return PARSE_UNSUPPORTED;     // slices out of raster order / missing slices (ASO, FMO, losses)
@@ -271,7 +293,17 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
   if (slice_type != 0 && slice_type != 2) return PARSE_UNSUPPORTED;
   const bool is_p = slice_type == 0;
   if (idr && is_p) return PARSE_INVALID;
-  if ((int)r.ue() != st->sp.pps_id) return PARSE_NO_PARAMETER_SETS;
+  {                                                           // the slice names its PPS, the PPS its SPS (several of each may be around)
+    const uint32_t id = r.ue();
+    if (id > 255 || !st->pps_tab[id].valid || !st->sps_tab[st->pps_tab[id].sps_id].valid) return PARSE_NO_PARAMETER_SETS;
+    if (!first_slice && (int)id != st->sp.pps_id && st->pps_tab[id].sps_id != st->sp.sps_id) return PARSE_INVALID;
+    if (first_slice && (st->sp.sps_id != st->pps_tab[id].sps_id || !st->have_sps)) {
+      if (!idr && st->have_sps) return PARSE_UNSUPPORTED;     // a new sequence may only start at an IDR picture
+      activate_sps(st, st->pps_tab[id].sps_id);
+    }
+    activate_pps(st, (int)id);
+  }
+  const int mbw = st->sp.mb_w, n = st->sp.mb_w * st->sp.mb_h;
   SliceState ss;
   ss.idr = idr;
   ss.frame_num = (int)r.get(st->log2_max_frame_num);
@@ -287,61 +319,83 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     if (r.bit()) n_ref = (int)r.ue() + 1;
     if (n_ref < 1 || n_ref > 32) return PARSE_INVALID;
     const int max_fn = 1 << st->log2_max_frame_num;
-    struct Cand { int slot, pic_num; };
+    // key: short-term pictures by PicNum (FrameNumWrap), long-term pictures by LongTermPicNum (= LongTermFrameIdx for frames)
+    struct Cand { int slot, num; bool lt; };
     Cand cand[32];
-    int nc = 0;
+    int nc = 0, n_st = 0;
     for (const ParserState::RefPic& rp : st->refs) {
-      if (nc >= 32) break;
-      cand[nc].slot = rp.slot;
-      cand[nc].pic_num = rp.frame_num > ss.frame_num ? rp.frame_num - max_fn : rp.frame_num;      // FrameNumWrap
+      if (nc >= 32 || rp.long_term) continue;
+      cand[nc].slot = rp.slot; cand[nc].lt = false;
+      cand[nc].num = rp.frame_num > ss.frame_num ? rp.frame_num - max_fn : rp.frame_num;      // FrameNumWrap
       nc++;
     }
+    n_st = nc;
+    for (int i = 1; i < n_st; i++)                            // short-term: descending PicNum
+      for (int j = i; j > 0 && cand[j].num > cand[j - 1].num; j--) { const Cand t = cand[j]; cand[j] = cand[j - 1]; cand[j - 1] = t; }
+    for (const ParserState::RefPic& rp : st->refs) {
+      if (nc >= 32 || !rp.long_term) continue;
+      cand[nc].slot = rp.slot; cand[nc].lt = true; cand[nc].num = rp.lt_idx;
+      nc++;
+    }
+    for (int i = n_st + 1; i < nc; i++)                       // long-term: ascending LongTermPicNum
+      for (int j = i; j > n_st && cand[j].num < cand[j - 1].num; j--) { const Cand t = cand[j]; cand[j] = cand[j - 1]; cand[j - 1] = t; }
     if (nc == 0) return PARSE_INVALID;
-    for (int i = 1; i < nc; i++)                              // descending PicNum
-      for (int j = i; j > 0 && cand[j].pic_num > cand[j - 1].pic_num; j--) { const Cand t = cand[j]; cand[j] = cand[j - 1]; cand[j - 1] = t; }
-    int pn[33];
-    for (int i = 0; i < 32; i++) { list0[i] = cand[i < nc ? i : nc - 1].slot; pn[i] = i < nc ? cand[i].pic_num : -0x40000000; }   // entries past the
-                                                              // available pictures repeat the last one (a conforming stream does not use them)
-    if (r.bit()) {                                            // ref_pic_list_modification_flag_l0
+    int key[33];                                              // identity of an entry: PicNum, or LongTermPicNum + 2^20
+    for (int i = 0; i < 32; i++) {                            // entries past the available pictures repeat the last one (a conforming
+      const Cand& cd = cand[i < nc ? i : nc - 1];             // stream does not use them)
+      list0[i] = cd.slot;
+      key[i] = i < nc ? (cd.lt ? cd.num + (1 << 20) : cd.num) : -0x40000000;
+    }
+    if (r.bit()) {                                            // ref_pic_list_modification_flag_l0 (8.2.4.3)
       int pred = ss.frame_num, idx = 0;
       for (;;) {
         const uint32_t idc = r.ue();
         if (idc == 3) break;
         if (idc > 3 || !r.ok()) return PARSE_INVALID;
         const uint32_t v = r.ue();
-        if (idc == 2) return PARSE_UNSUPPORTED;               // long-term reference pictures
-        if (v >= (uint32_t)max_fn || idx >= n_ref) return PARSE_INVALID;
-        int no_wrap = idc == 0 ? pred - ((int)v + 1) : pred + ((int)v + 1);
-        if (no_wrap < 0) no_wrap += max_fn;
-        if (no_wrap >= max_fn) no_wrap -= max_fn;
-        pred = no_wrap;
-        const int pic_num = no_wrap > ss.frame_num ? no_wrap - max_fn : no_wrap;
+        if (idx >= n_ref) return PARSE_INVALID;
+        int want;
+        if (idc == 2) {
+          want = (int)v + (1 << 20);                          // long_term_pic_num
+        } else {
+          if (v >= (uint32_t)max_fn) return PARSE_INVALID;
+          int no_wrap = idc == 0 ? pred - ((int)v + 1) : pred + ((int)v + 1);
+          if (no_wrap < 0) no_wrap += max_fn;
+          if (no_wrap >= max_fn) no_wrap -= max_fn;
+          pred = no_wrap;
+          want = no_wrap > ss.frame_num ? no_wrap - max_fn : no_wrap;
+        }
         int found = -1;
-        for (int i = 0; i < nc; i++) if (cand[i].pic_num == pic_num) found = cand[i].slot;
+        for (int i = 0; i < nc; i++) if ((cand[i].lt ? cand[i].num + (1 << 20) : cand[i].num) == want) found = cand[i].slot;
         if (found < 0) return PARSE_UNSUPPORTED;              // refers to a picture that is not in the buffer (loss): needs concealment
-        // 8.2.4.3.1: insert at idx, shift the rest, drop the later duplicate
-        for (int c = n_ref; c > idx; c--) { list0[c < 32 ? c : 31] = list0[c - 1]; pn[c < 33 ? c : 32] = pn[c - 1]; }
-        list0[idx] = found; pn[idx] = pic_num;
+        // insert at idx, shift the rest, drop the later duplicate
+        for (int c = n_ref; c > idx; c--) { list0[c < 32 ? c : 31] = list0[c - 1]; key[c < 33 ? c : 32] = key[c - 1]; }
+        list0[idx] = found; key[idx] = want;
         idx++;
         int nidx = idx;
         for (int c = idx; c <= n_ref && c < 32; c++)
-          if (pn[c] != pic_num) { list0[nidx] = list0[c]; pn[nidx] = pn[c]; nidx++; }
+          if (key[c] != want) { list0[nidx] = list0[c]; key[nidx] = key[c]; nidx++; }
       }
     }
   }
   const bool is_ref = nal.ref_idc != 0;                       // a non-reference picture is output but never predicted from
-  bool adaptive = false;
-  std::vector<int> mmco1;
-  if (nal.ref_idc) {                                          // dec_ref_pic_marking
-    if (idr) { r.bit(); if (r.bit()) return PARSE_UNSUPPORTED; }          // long_term_reference_flag
-    else if (r.bit()) {                                       // adaptive marking: only "mark a short-term picture unused" (operation 1)
+  bool adaptive = false, idr_lt = false;
+  std::vector<ParsedPicture::Mmco> mmco;
+  if (nal.ref_idc) {                                          // dec_ref_pic_marking (7.3.3.3)
+    if (idr) { r.bit(); idr_lt = r.bit() != 0; }              // no_output_of_prior_pics_flag, long_term_reference_flag
+    else if (r.bit()) {
       adaptive = true;
       for (;;) {
-        const uint32_t op = r.ue();
-        if (op == 0) break;
-        if (op != 1 || !r.ok()) return PARSE_UNSUPPORTED;     // long-term operations (2..6)
-        mmco1.push_back((int)r.ue());
-        if (mmco1.size() > 64) return PARSE_INVALID;
+        ParsedPicture::Mmco m;
+        m.op = (int)r.ue(); m.a = m.b = 0;
+        if (m.op == 0) break;
+        if (m.op > 6 || !r.ok()) return PARSE_INVALID;
+        if (m.op == 1 || m.op == 3) m.a = (int)r.ue();        // difference_of_pic_nums_minus1
+        if (m.op == 2) m.a = (int)r.ue();                     // long_term_pic_num
+        if (m.op == 3 || m.op == 6) m.b = (int)r.ue();        // long_term_frame_idx
+        if (m.op == 4) m.a = (int)r.ue();                     // max_long_term_frame_idx_plus1
+        mmco.push_back(m);
+        if (mmco.size() > 64) return PARSE_INVALID;
       }
     }
   }
@@ -364,7 +418,9 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     pic->ss = ss;
     pic->is_ref = is_ref;
     pic->adaptive_marking = adaptive;
-    pic->mmco1_diff = mmco1;
+    pic->mmco = mmco;
+    pic->idr_long_term = idr_lt;
+    pic->crop_left = 2 * st->crop_left; pic->crop_top = 2 * st->crop_top;
     pic->n_slots = st->n_slots;
     {                                                         // a slot no reference picture occupies
       int slot = 0;
@@ -470,7 +526,23 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
         m.i16_mode = (uint8_t)(v & 3);
         cbp = (((v >> 2) % 3) << 4) | (v >= 12 ? 15 : 0);
         m.chroma_mode = (uint8_t)r.ue();
-      } else return PARSE_UNSUPPORTED;                        // I_PCM
+      } else if (t == 25) {                                   // I_PCM (7.3.5): byte-aligned raw samples
+        m.mb_type = MBT_IPCM;
+        while (r.pos() & 7) r.skip(1);
+        uint8_t* py = reinterpret_cast<uint8_t*>(m.luma);
+        uint8_t* pc = reinterpret_cast<uint8_t*>(m.chroma_ac);
+        for (int i = 0; i < 256; i++) py[i] = (uint8_t)r.get(8);
+        for (int i = 0; i < 128; i++) pc[i] = (uint8_t)r.get(8);
+        if (!r.ok()) return PARSE_TRUNCATED;
+        for (int i = 0; i < 24; i++) m.nnz[i] = 16;           // what the neighbours' coeff_token context sees (9.2.1)
+        m.cbp = 0x2f;
+        m.qp = 0;                                             // QP'Y of an I_PCM macroblock is 0 for the deblocking filter; like the reference
+                                                              // decoder (decode_slice.cpp:1870: iLastMbQp untouched) the QP predictor
+                                                              // of the next macroblock stays what it was
+        idx++;
+        if (!r.more_data()) break;
+        continue;
+      } else return PARSE_INVALID;
       if (m.chroma_mode > 3) return PARSE_INVALID;
       if (!st->constrained_intra_pred) {                      // prediction modes must have their neighbours (8.3.3, 8.3.4); with
         const bool L = avL, T = avT;                          // constrained intra prediction the construct stage knows which count
@@ -551,34 +623,57 @@ int parse_access_unit(const uint8_t* au, size_t len, ParserState* st, ParsedPict
   if (!got_slice) return PARSE_NO_PICTURE;
   if (pic->next_mb != st->sp.mb_w * st->sp.mb_h) return PARSE_INCOMPLETE;    // macroblocks missing: more slices to come (or lost: needs concealment)
   if (pic->is_ref) {
-    // decoded reference picture marking (8.2.5): an IDR picture empties the buffer; otherwise either the explicit "unused"
-    // commands or the sliding window make room, then the picture joins the short-term references
-    if (pic->ss.idr) st->refs.clear();
-    else if (pic->adaptive_marking) {
-      const int max_fn = 1 << st->log2_max_frame_num;
-      for (int diff : pic->mmco1_diff) {
-        const int pic_num = pic->ss.frame_num - (diff + 1);
-        for (size_t i = 0; i < st->refs.size(); i++) {
-          const int fn = st->refs[i].frame_num, wrap = fn > pic->ss.frame_num ? fn - max_fn : fn;
-          if (wrap == pic_num) { st->refs.erase(st->refs.begin() + i); break; }
+    // decoded reference picture marking (8.2.5): an IDR picture empties the buffer; otherwise the memory management commands
+    // or the sliding window make room, then the picture joins the references (short-term unless a command says otherwise)
+    const int max_fn = 1 << st->log2_max_frame_num, cur = pic->ss.frame_num;
+    auto pic_num = [&](const ParserState::RefPic& rp) { return rp.frame_num > cur ? rp.frame_num - max_fn : rp.frame_num; };
+    bool cur_long = false, reset = false;
+    int cur_lt_idx = 0;
+    if (pic->ss.idr) {
+      st->refs.clear();
+      if (pic->idr_long_term) { cur_long = true; cur_lt_idx = 0; }
+    } else if (pic->adaptive_marking) {
+      for (const ParsedPicture::Mmco& m : pic->mmco) {
+        if (m.op == 1 || m.op == 3) {                           // a short-term picture: unused, or turned into a long-term one
+          const int want = cur - (m.a + 1);
+          for (size_t i = 0; i < st->refs.size(); i++) {
+            if (st->refs[i].long_term || pic_num(st->refs[i]) != want) continue;
+            if (m.op == 1) st->refs.erase(st->refs.begin() + i);
+            else {
+              for (size_t j = 0; j < st->refs.size(); j++)      // the index is taken over
+                if (st->refs[j].long_term && st->refs[j].lt_idx == m.b && j != i) { st->refs.erase(st->refs.begin() + j); if (j < i) i--; break; }
+              st->refs[i].long_term = true; st->refs[i].lt_idx = m.b;
+            }
+            break;
+          }
+        } else if (m.op == 2) {
+          for (size_t i = 0; i < st->refs.size(); i++)
+            if (st->refs[i].long_term && st->refs[i].lt_idx == m.a) { st->refs.erase(st->refs.begin() + i); break; }
+        } else if (m.op == 4) {
+          for (size_t i = 0; i < st->refs.size();)
+            if (st->refs[i].long_term && st->refs[i].lt_idx >= m.a) st->refs.erase(st->refs.begin() + i); else i++;
+        } else if (m.op == 5) {
+          st->refs.clear(); reset = true;
+        } else if (m.op == 6) {
+          for (size_t j = 0; j < st->refs.size(); j++)
+            if (st->refs[j].long_term && st->refs[j].lt_idx == m.b) { st->refs.erase(st->refs.begin() + j); break; }
+          cur_long = true; cur_lt_idx = m.b;
         }
       }
     }
     const int cap = st->sp.num_ref_frames < 1 ? 1 : st->sp.num_ref_frames;
-    while ((int)st->refs.size() >= cap) {                      // sliding window (8.2.5.3): the smallest FrameNumWrap goes
-      const int max_fn = 1 << st->log2_max_frame_num;
-      size_t victim = 0;
+    while ((int)st->refs.size() >= cap) {                      // sliding window (8.2.5.3): the short-term picture with the smallest FrameNumWrap goes
+      size_t victim = st->refs.size();
       int best = 0x7fffffff;
-      for (size_t i = 0; i < st->refs.size(); i++) {
-        const int fn = st->refs[i].frame_num, wrap = fn > pic->ss.frame_num ? fn - max_fn : fn;
-        if (wrap < best) { best = wrap; victim = i; }
-      }
+      for (size_t i = 0; i < st->refs.size(); i++)
+        if (!st->refs[i].long_term && pic_num(st->refs[i]) < best) { best = pic_num(st->refs[i]); victim = i; }
+      if (victim == st->refs.size()) victim = 0;               // only long-term pictures left: a non-conforming stream; drop the first
       st->refs.erase(st->refs.begin() + victim);
     }
     ParserState::RefPic rp;
-    rp.slot = pic->cur_slot; rp.frame_num = pic->ss.frame_num;
+    rp.slot = pic->cur_slot; rp.frame_num = reset ? 0 : cur; rp.long_term = cur_long; rp.lt_idx = cur_lt_idx;
     st->refs.push_back(rp);
-    st->have_ref = true; st->last_frame_num = pic->ss.frame_num;
+    st->have_ref = true; st->last_frame_num = reset ? 0 : cur;
   }
   return PARSE_OK;
 }

@@ -27,8 +27,24 @@ enum ParseError {
   PARSE_INCOMPLETE = -5        // the slices seen so far do not cover the picture (more slices of the access unit to come, or lost)
 };
 
+// what an SPS / a PPS contributes; streams may carry several of each (selected per slice through pic_parameter_set_id)
+struct SpsFields {
+  bool valid = false;
+  StreamParams sp{};
+  int log2_max_frame_num = 0, poc_type = 2, log2_max_poc_lsb = 0, n_slots = 2, crop_left = 0, crop_top = 0;
+  bool delta_pic_order_always_zero = false;
+};
+struct PpsFields {
+  bool valid = false;
+  int sps_id = 0, pic_init_qp = 26, num_ref_idx_default = 1;
+  bool deblocking_control = true, constrained_intra_pred = false;
+};
+
 // parameter sets carried from access unit to access unit
 struct ParserState {
+  SpsFields sps_tab[32];
+  PpsFields pps_tab[256];
+  int crop_left = 0, crop_top = 0;   // of the active SPS, in units of 2 luma samples
   bool have_sps = false, have_pps = false;
   StreamParams sp{};             // width / height / mb_w / mb_h / crop / level / ids (num_ref_frames)
   int log2_max_frame_num = 0;
@@ -42,7 +58,7 @@ struct ParserState {
   int last_frame_num = 0;
   // decoded picture buffer bookkeeping (8.2.4, 8.2.5.3): the short-term reference pictures in decoding order, each in one
   // of n_slots picture slots of the construct stage (num_ref_frames + 1: the picture being decoded needs one too)
-  struct RefPic { int slot, frame_num; };
+  struct RefPic { int slot, frame_num; bool long_term; int lt_idx; };
   std::vector<RefPic> refs;
   int n_slots = 2;
 };
@@ -51,6 +67,7 @@ struct ParsedPicture {
   SliceState ss;                 // idr, frame_num, idr_pic_id, slice qp
   int disable_deblocking_idc = 0;
   bool is_ref = true;            // nal_ref_idc != 0
+  int crop_left = 0, crop_top = 0;   // luma samples to drop at the left / top of the decoded picture
   std::vector<MbOut> mbs;        // mb_w * mb_h records, same meaning as the encoder's hand-over records
   std::vector<DecMbAux> aux;     // one per macroblock: slice membership, sub-macroblock partitions, deblocking control
   int next_mb = 0;               // macroblocks parsed so far (slices arrive in raster order)
@@ -59,7 +76,10 @@ struct ParsedPicture {
   int n_slots = 2;               // slots the stream needs (from its SPS)
   // dec_ref_pic_marking of the picture (first slice): sliding window, or memory_management_control_operation 1 commands
   bool adaptive_marking = false;
-  std::vector<int> mmco1_diff;   // difference_of_pic_nums_minus1 of each "mark short-term picture unused" command
+  struct Mmco { int op, a, b; };  // memory_management_control_operation with its operands
+  std::vector<Mmco> mmco;
+  bool idr_long_term = false;    // long_term_reference_flag of an IDR picture
+  std::vector<int> mmco1_diff_unused;   // difference_of_pic_nums_minus1 of each "mark short-term picture unused" command
   bool any_deblock = false;      // some slice wants its macroblocks filtered
 };
 

@@ -32,6 +32,14 @@ Pool::Pool(const PoolKey& key, int capacity, int device) : key_(key), cap_(capac
     enc_ = nullptr; pinned_ = nullptr;
     return;
   }
+  cudaStream_t us = nullptr;
+  if (cudaMalloc((void**)&d_stage_, frame_bytes_ * capacity) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&us, cudaStreamNonBlocking) != cudaSuccess) {
+    b2h264_enc_destroy(enc_); cudaFreeHost(pinned_); if (d_stage_) cudaFree(d_stage_);
+    enc_ = nullptr; pinned_ = nullptr; d_stage_ = nullptr;
+    return;
+  }
+  up_stream_ = us;
   state_.assign(capacity, FREE);
   au_.resize(capacity);
   idr_.assign(capacity, 0);
@@ -40,6 +48,14 @@ Pool::Pool(const PoolKey& key, int capacity, int device) : key_(key), cap_(capac
 Pool::~Pool() {
   if (enc_) b2h264_enc_destroy(enc_);
   if (pinned_) cudaFreeHost(pinned_);
+  if (d_stage_) { cudaSetDevice(device_); cudaFree(d_stage_); }
+  if (up_stream_) cudaStreamDestroy((cudaStream_t)up_stream_);
+}
+
+int Pool::upload(int slot) {
+  if (cudaSetDevice(device_) != cudaSuccess) return -1;
+  return cudaMemcpyAsync(d_stage_ + (size_t)slot * frame_bytes_, pinned_ + (size_t)slot * frame_bytes_, frame_bytes_, cudaMemcpyHostToDevice,
+                         (cudaStream_t)up_stream_) == cudaSuccess ? 0 : -1;
 }
 
 int Pool::acquire() {
@@ -74,12 +90,14 @@ void Pool::flush_locked(std::unique_lock<std::mutex>& lk) {
   flushing_ = true;
   std::vector<const uint8_t*> src(cap_, nullptr);
   for (int s = 0; s < cap_; s++)
-    if (state_[s] == PENDING) { state_[s] = INFLIGHT; src[s] = staging(s); }
+    if (state_[s] == PENDING) { state_[s] = INFLIGHT; src[s] = d_stage_ + (size_t)s * frame_bytes_; }
   n_pending_ = 0;
   lk.unlock();
   std::vector<const uint8_t*> bs(cap_, nullptr);
   std::vector<int32_t> nb(cap_, 0), ft(cap_, 0);
-  int rc = b2h264_enc_submit(enc_, src.data(), 0);
+  // every pending stream enqueued its upload before it registered as pending: one wait covers them all
+  int rc = cudaSetDevice(device_) == cudaSuccess && cudaStreamSynchronize((cudaStream_t)up_stream_) == cudaSuccess ? 0 : -1;
+  if (rc == 0) rc = b2h264_enc_submit(enc_, src.data(), 1);
   if (rc == 0) rc = b2h264_enc_collect(enc_, bs.data(), nb.data(), ft.data());
   lk.lock();
   for (int s = 0; s < cap_; s++) {

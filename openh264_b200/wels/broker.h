@@ -45,6 +45,9 @@ class Pool {
   // synchronous: codes `planes` (tightly packed I420 already gathered into the slot's staging picture by stage())
   // as the next picture of `slot`; *au receives the access unit, *idr its type.  0 or a negative / CUDA error.
   uint8_t* staging(int slot) { return pinned_ + (size_t)slot * frame_bytes_; }
+  // starts the host -> device copy of the slot's staged picture right away (on the caller's thread): by the time the last
+  // stream of a batch arrives the pictures of the others are already in HBM
+  int upload(int slot);
   int encode(int slot, std::vector<uint8_t>* au, bool* idr);
   int force_idr(int slot);
 
@@ -56,6 +59,8 @@ class Pool {
   size_t frame_bytes_;
   b2h264_enc* enc_ = nullptr;
   uint8_t* pinned_ = nullptr;
+  uint8_t* d_stage_ = nullptr;             // device copies of the staged pictures (what the batch reads)
+  void* up_stream_ = nullptr;              // cudaStream_t of the early uploads
   std::mutex m_;
   std::condition_variable cv_;
   std::vector<State> state_;

@@ -132,6 +132,7 @@ class B2Encoder : public ISVCEncoder {
       d += (size_t)pw * ph;
     }
     bool idr = false;
+    if (pool_->upload(slot_) != 0) return cmUnknownReason;
     if (pool_->encode(slot_, &au_, &idr) != 0) return cmUnknownReason;
     fill_info(info, idr, pic->uiTimeStamp);
     return cmResultSuccess;

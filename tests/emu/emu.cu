@@ -328,7 +328,8 @@ extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, i
       if (outpos + (long)W * H * 3 / 2 > cap) return -2;
       for (int pl = 0; pl < 3; pl++) {
         const int pw = pl ? W / 2 : W, ph = pl ? H / 2 : H, stp = pl ? p.rec_stride_c : p.rec_stride_y;
-        for (int y = 0; y < ph; y++) { memcpy(out + outpos, f.rec[pl] + (size_t)y * stp, pw); outpos += pw; }
+        const int cx = pp.crop_left >> (pl ? 1 : 0), cy = pp.crop_top >> (pl ? 1 : 0);
+        for (int y = 0; y < ph; y++) { memcpy(out + outpos, f.rec[pl] + (size_t)(y + cy) * stp + cx, pw); outpos += pw; }
       }
       frames++;
       au_begin = au_end;

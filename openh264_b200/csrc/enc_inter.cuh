@@ -65,7 +65,7 @@ MBK_FN void fill_inter_cache(const MbCtx& c, MbScratch& s, bool ref_ids = false)
 }
 
 // ---- motion vector prediction (mv_pred.cpp:45-150) ----------------------------------------------------
-MBK_HD void pred_mv(const MbScratch& s, int blk /*coding idx*/, int part_w, int ref, int* px, int* py) {
+MBK_FN void pred_mv(const MbScratch& s, int blk /*coding idx*/, int part_w, int ref, int* px, int* py) {
   const int left = cache30(blk) - 1, top = cache30(blk) - 6;
   const int lr = s.refc[left], tr = s.refc[top], rtr = s.refc[top + part_w];
   int dr, dmx, dmy;
@@ -153,6 +153,7 @@ MBK_HD const uint8_t* ref_chroma(const MbCtx& c, int pl, int px, int py) {
 // chroma prediction of a (w x h luma) partition at luma offset (ox, oy) with quarter-pel luma mv
 MBK_FN void mc_chroma_part(const MbCtx& c, uint8_t* dst /*Cb, Cr at +64, stride 8*/, int ox, int oy, int w, int h, int mvx, int mvy) {
   const int cx = ox >> 1, cy = oy >> 1;
+  MBK_NO_UNROLL
   for (int pl = 0; pl < 2; pl++) {
     const uint8_t* src = ref_chroma(c, 1 + pl, cx + (mvx >> 3), cy + (mvy >> 3));
     warp_mc_chroma(src, c.p.rec_stride_c, dst + 64 * pl + cy * 8 + cx, 8, mvx, mvy, w >> 1, h >> 1);
@@ -226,6 +227,7 @@ MBK_FN SkipResult pskip_enc(const MbCtx& c, MbScratch& s, int sad_pred_skip, int
   phase_mark(s, 13);
   const int sad_y = warp_sad(s.cur_y, 16, py, 16, 4, 4);
   // NB the reference derives the chroma offset from the INTEGER luma vector: (ix >> 1, iy >> 1)
+  MBK_NO_UNROLL
   for (int pl = 0; pl < 2; pl++)
     warp_mc_chroma(ref_chroma(c, 1 + pl, ix >> 1, iy >> 1), c.p.rec_stride_c, s.skip_pred + 256 + 64 * pl, 8, mvx, mvy, 8, 8);
   warp_sync();
@@ -471,6 +473,7 @@ MBK_FN void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy,
   int hx = 0, hy = 0;                    // offsets from the integer vector
   {
     int bi = -1;
+    MBK_NO_UNROLL
     for (int i = 0; i < 4; i++) {      // up, down, left, right by half a sample
       const int cst = eval(i == 2 ? -2 : i == 3 ? 2 : 0, i == 0 ? -2 : i == 1 ? 2 : 0);
       if (cst < best) { best = cst; bi = i; }
@@ -487,6 +490,7 @@ MBK_FN void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy,
   int fx = hx, fy = hy;
   {
     int bi = -1;
+    MBK_NO_UNROLL
     for (int i = 0; i < 4; i++) {      // the same four directions by a quarter sample
       const int cst = eval(hx + (i == 2 ? -1 : i == 3 ? 1 : 0), hy + (i == 0 ? -1 : i == 1 ? 1 : 0));
       if (cst < best) { best = cst; bi = i; }
@@ -724,6 +728,7 @@ MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
     const int16_t mvc0[2] = {0, 0};
     auto md_p8x8 = [&]() {
       int cost8 = 0;
+      MBK_NO_UNROLL
       for (int i = 0; i < 4; i++) {
         int px, py;
         pred_mv(s, 4 * i, 2, 0, &px, &py);
@@ -735,6 +740,7 @@ MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
     };
     auto md_p16x8 = [&]() {
       int cst = 0;
+      MBK_NO_UNROLL
       for (int i = 0; i < 2; i++) {
         int px, py;
         pred_16x8_mv(s, 8 * i, 0, &px, &py);
@@ -746,6 +752,7 @@ MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
     };
     auto md_p8x16 = [&]() {
       int cst = 0;
+      MBK_NO_UNROLL
       for (int i = 0; i < 2; i++) {
         int px, py;
         pred_8x16_mv(s, 4 * i, 0, &px, &py);
@@ -798,6 +805,7 @@ MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
       mc_chroma_part(c, pc, 0, 0, 16, 16, me16.mv_x, me16.mv_y);
       cost_skip_mb = warp_sad(s.cur_y, 16, pl, 16, 4, 4) + warp_sad(s.cur_c, 8, pc, 8, 3, 3) + warp_sad(s.cur_c + 64, 8, pc + 64, 8, 3, 3);
     } else if (final_type == MBT_P16x8) {
+      MBK_NO_UNROLL
       for (int i = 0; i < 2; i++) {
         { int qx, qy; pred_16x8_mv(s, 8 * i, 0, &qx, &qy); if (lane_id() == 0) { me16x8[i].mvp_x = qx; me16x8[i].mvp_y = qy; } warp_sync(); }
         me_refine(c, s, &me16x8[i], 0, 8 * i, 16, 8, pl + 128 * i);
@@ -808,6 +816,7 @@ MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
         mc_chroma_part(c, pc, 0, 8 * i, 16, 8, me16x8[i].mv_x, me16x8[i].mv_y);
       }
     } else if (final_type == MBT_P8x16) {
+      MBK_NO_UNROLL
       for (int i = 0; i < 2; i++) {
         { int qx, qy; pred_8x16_mv(s, 4 * i, 0, &qx, &qy); if (lane_id() == 0) { me8x16[i].mvp_x = qx; me8x16[i].mvp_y = qy; } warp_sync(); }
         me_refine(c, s, &me8x16[i], 8 * i, 0, 8, 16, pl + 8 * i);
@@ -820,6 +829,7 @@ MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
     } else {
       if (lane_id() == 0) { s.refc[9] = s.refc[21] = REF_NOT_AVAIL; }
       warp_sync();
+      MBK_NO_UNROLL
       for (int i = 0; i < 4; i++) {
         const int ox = (i & 1) * 8, oy = (i >> 1) * 8;
         { int qx, qy; pred_mv(s, 4 * i, 2, 0, &qx, &qy); if (lane_id() == 0) { me8x8[i].mvp_x = qx; me8x8[i].mvp_y = qy; } warp_sync(); }

@@ -363,8 +363,7 @@ __device__ __forceinline__ uint2 g8(const uint8_t* p) {
 }
 __device__ __forceinline__ uint2 avg8(uint2 a, uint2 b) { return make_uint2(__vavgu4(a.x, b.x), __vavgu4(a.y, b.y)); }
 // eight prediction samples at quarter-sample phase (fx, fy); p = integer sample (x0, row) in the tile
-// out of line on purpose: the integer-vector path of the tiled kernels keeps its own (small) register allocation
-__device__ __noinline__ uint2 qpel8(const uint8_t* p, int P, int fx, int fy) {
+__device__ __forceinline__ uint2 qpel8(const uint8_t* p, int P, int fx, int fy) {
   if (fy == 0) {
     const uint2 b = h8(p);
     return fx == 2 ? b : avg8(b, g8(p + (fx == 3)));
@@ -385,7 +384,8 @@ __device__ __noinline__ uint2 qpel8(const uint8_t* p, int P, int fx, int fy) {
 // waits on the mbarrier: no per-thread address arithmetic for staging, out-of-picture parts are zero-filled by
 // the copy engine.  ncu on the cp.async form showed the SMs issue-bound (89 % issue-active, 187 warp instructions
 // per macroblock, a third of them staging arithmetic): profiles/r01_mc_sad_ncu.txt.
-__global__ void __launch_bounds__(32 * MCT_W, 8)
+// 6 CTAs per SM (40 registers): the packed interpolation needs them; the integer path loses nothing measurable against 8
+__global__ void __launch_bounds__(32 * MCT_W, 6)
 k_mc_sad_tma(const __grid_constant__ CUtensorMap tm_cur, const __grid_constant__ CUtensorMap tm_ref, int mb_w, int mb_h,
              const int16_t* __restrict__ mv, int k, int32_t* __restrict__ cost) {
   __shared__ __align__(128) uint8_t t_cur[16 * MCT_H][16 * MCT_W];

@@ -24,6 +24,13 @@
 // notes in profiles/r01_encode_stages.txt).  Externally visible functions follow the standard ABI.  Every
 // translation unit is compiled with the same register cap because nvlink keeps one copy of each function.
 #define MBK_FN inline __host__ __device__ __noinline__
+// loops around calls to the big warp routines are kept rolled: the macroblock kernel is bound by instruction fetch (the code one
+// stage walks through does not fit the instruction cache), so code size is time
+#ifdef __CUDACC__
+#define MBK_NO_UNROLL _Pragma("unroll 1")
+#else
+#define MBK_NO_UNROLL
+#endif
 #ifdef __CUDA_ARCH__
 #define MBK_WS 32
 #else

@@ -390,6 +390,10 @@ k_mc_sad_tma(const __grid_constant__ CUtensorMap tm_cur, const __grid_constant__
              const int16_t* __restrict__ mv, int k, int32_t* __restrict__ cost) {
   __shared__ __align__(128) uint8_t t_cur[16 * MCT_H][16 * MCT_W];
   __shared__ __align__(128) uint8_t t_ref[MCT_ROWS][MCT_PITCH];
+  // A bulk tensor copy lays the tile down densely: 160 bytes = 40 words per row, so rows r and r + 4 start in the same bank
+  // and the 16 rows a warp interpolates at once collide four ways.  Tiles with fractional vectors are therefore copied once
+  // into a 41-word pitch (rows spread over all 32 banks) before the packed interpolation reads them ~50 words per lane.
+  __shared__ __align__(16) uint8_t t_pad[MCT_ROWS][MCT_PITCH + 4];
   __shared__ __align__(8) unsigned long long bar;
   const int mbx0 = blockIdx.x * MCT_W, mby0 = blockIdx.y * MCT_H;
   const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
@@ -420,6 +424,23 @@ k_mc_sad_tma(const __grid_constant__ CUtensorMap tm_cur, const __grid_constant__
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
                    : "=r"(ok) : "r"(bar_a) : "memory");
   }
+  {
+    // does any candidate of this tile have a fractional vector?  (each warp scans its own column of macroblocks)
+    int frac = 0;
+    if (mbx < mb_w)
+      for (int i = l; i < MCT_H * k; i += 32) {
+        const int ty = i / k, c = i - ty * k;
+        if (mby0 + ty < mb_h) frac |= __ldg(reinterpret_cast<const int*>(mv + (size_t)(((mby0 + ty) * mb_w + mbx) * k + c) * 2)) & 0x00030003;
+      }
+    if (__syncthreads_or(frac)) {
+      constexpr int kW = MCT_PITCH / 4;
+      for (int i = threadIdx.x; i < MCT_ROWS * kW; i += blockDim.x) {
+        const int r = i / kW, w = i - r * kW;
+        reinterpret_cast<uint32_t*>(&t_pad[r][0])[w] = reinterpret_cast<const uint32_t*>(&t_ref[r][0])[w];
+      }
+      __syncthreads();
+    }
+  }
   if (mbx >= mb_w) return;
   const uint32_t cur_s = (uint32_t)__cvta_generic_to_shared(&t_cur[0][16 * tx]);
   const uint32_t ref_s = (uint32_t)__cvta_generic_to_shared(&t_ref[MCT_TOP][MCT_HALO_X + 16 * tx]);
@@ -447,8 +468,8 @@ k_mc_sad_tma(const __grid_constant__ CUtensorMap tm_cur, const __grid_constant__
         }
       } else {                                 // fractional vector: lane = (row, 8-sample half), packed interpolation, packed SAD
         const int r = l >> 1, x0 = (l & 1) * 8;
-        const uint8_t* p = &t_ref[MCT_TOP + 16 * ty + r][MCT_HALO_X + 16 * tx + x0] + (mvy >> 2) * MCT_PITCH + (mvx >> 2);
-        const uint2 pr = qpel8(p, MCT_PITCH, fx, fy);
+        const uint8_t* p = &t_pad[MCT_TOP + 16 * ty + r][MCT_HALO_X + 16 * tx + x0] + (mvy >> 2) * (MCT_PITCH + 4) + (mvx >> 2);
+        const uint2 pr = qpel8(p, MCT_PITCH + 4, fx, fy);
         const uint2 cw = *reinterpret_cast<const uint2*>(&t_cur[16 * ty + r][16 * tx + x0]);
         s = (int)(__vsadu4(cw.x, pr.x) + __vsadu4(cw.y, pr.y));
       }

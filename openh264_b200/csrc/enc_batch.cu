@@ -97,9 +97,8 @@ struct b2h264_enc {
   // pinned host memory
   uint8_t* h_src = nullptr;               // 2 slots x S x frame
   MbOut* h_out[2] = {nullptr, nullptr};      // mapped pinned: coded records, packed per stream (worst case sized)
-  int32_t* h_idx[2] = {nullptr, nullptr};    // mapped pinned: per MB rank in the packed records or -1
-  int32_t* h_cnt[2] = {nullptr, nullptr};    // mapped pinned: coded macroblocks per stream
-  int32_t* d_list = nullptr;                 // device scratch of the pack kernel
+  int32_t* h_idx[2] = {nullptr, nullptr};    // mapped pinned: per MB offset of its compact record (32-byte units) or -1
+  int32_t* h_cnt[2] = {nullptr, nullptr};    // mapped pinned: 32-byte units written per stream
   unsigned long long last_d2h = 0;
   StreamFrame* h_sf[2] = {nullptr, nullptr};
   const uint8_t** h_srcptr[2] = {nullptr, nullptr};
@@ -167,7 +166,6 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
   CK(cudaMemset(e->d_cur, 0, 2 * S * e->cur_bytes + 256));
   CK(cudaMalloc(&e->d_vaa, S * e->n_mb * 4 * sizeof(int32_t)));
   CK(cudaMemset(e->d_vaa, 0, S * e->n_mb * 4 * sizeof(int32_t)));
-  CK(cudaMalloc(&e->d_list, S * e->n_mb * sizeof(int32_t)));
   for (int i = 0; i < 2; i++) {
     e->d_pic[i] = e->d_pic_all + (size_t)i * S * e->pic_bytes;
     CK(cudaMalloc(&e->d_rinfo[i], S * e->n_mb * sizeof(RefMbInfo)));
@@ -217,7 +215,7 @@ void b2h264_enc_destroy(b2h264_enc* e) {
   cudaSetDevice(e->cfg.device);
   cudaStreamSynchronize(e->st);
   delete e->pool;
-  cudaFree(e->d_pic_all); cudaFree(e->d_cur); cudaFree(e->d_vaa); cudaFree(e->d_tmap); cudaFree(e->d_src); cudaFree(e->d_mbi); cudaFree(e->d_sad); cudaFree(e->d_prog); cudaFree(e->d_bits); cudaFree(e->d_tickets); cudaFree(e->d_stash); cudaFree(e->d_list);
+  cudaFree(e->d_pic_all); cudaFree(e->d_cur); cudaFree(e->d_vaa); cudaFree(e->d_tmap); cudaFree(e->d_src); cudaFree(e->d_mbi); cudaFree(e->d_sad); cudaFree(e->d_prog); cudaFree(e->d_bits); cudaFree(e->d_tickets); cudaFree(e->d_stash);
   cudaFreeHost(e->h_src);
   for (int i = 0; i < 2; i++) {
     cudaFree(e->d_rinfo[i]); cudaFree(e->d_out[i]); cudaFree(e->d_sf[i]); cudaFree(e->d_srcptr[i]);
@@ -309,7 +307,7 @@ int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_devic
   CK(cudaEventRecord(sl.ev2, e->st));
   // the macroblock records are final once the encode kernel is done (deblocking does not touch them)
   CK(cudaStreamWaitEvent(e->st_out, sl.ev1, 0));
-  rc = enc_launch_pack(e->d_sf[k], n, e->n_mb, e->h_out[k], e->h_idx[k], e->h_cnt[k], e->d_list, e->st_out);
+  rc = enc_launch_pack(e->d_sf[k], n, e->n_mb, e->h_out[k], e->h_idx[k], e->h_cnt[k], e->st_out);
   if (rc) return rc;
   CK(cudaEventRecord(sl.done, e->st_out));
   sl.busy = true;
@@ -335,7 +333,7 @@ int b2h264_enc_collect(b2h264_enc* e, const uint8_t** bs, int32_t* bs_bytes, int
   const auto t0 = std::chrono::steady_clock::now();
   const int n_mb = e->n_mb, n = (int)sl.act.size();
   e->last_d2h = (unsigned long long)n * (n_mb + 1) * sizeof(int32_t);
-  for (int i = 0; i < n; i++) e->last_d2h += (unsigned long long)e->h_cnt[k][i] * sizeof(MbOut);
+  for (int i = 0; i < n; i++) e->last_d2h += (unsigned long long)e->h_cnt[k][i] * 32;
   for (int s = 0; s < e->S; s++) e->bs[s].clear();
   std::function<void(int)> job = [&](int i) {
     const int s = sl.act[i];

@@ -1,6 +1,7 @@
 // enc_host.cpp — see enc_host.h.
 #include "enc_host.h"
 
+#include <stddef.h>
 #include <string.h>
 
 namespace b2h264 {
@@ -42,11 +43,32 @@ void StreamCtl::write_access_unit(bool idr, const MbOut* mbs, std::vector<uint8_
   write_au(idr, recs_.data(), au);
 }
 
+// compact records (enc_kernels.cu: k_pack_records): idx[mb] = offset in 32-byte units or -1; 128-byte head
+// (MbOut bytes [0, 112) + chroma_dc, presence mask of the 24 residual blocks in pad0) + 32 bytes per present block
 void StreamCtl::write_access_unit_packed(bool idr, const MbOut* packed, const int32_t* idx, std::vector<uint8_t>* au) {
   static const MbOut kSkip = [] { MbOut m; memset(&m, 0, sizeof(m)); m.mb_type = MBT_PSKIP; return m; }();
   const int n = sp.mb_w * sp.mb_h;
   recs_.resize(n);
-  for (int i = 0; i < n; i++) recs_[i] = idx[i] < 0 ? &kSkip : packed + idx[i];
+  int coded = 0;
+  for (int i = 0; i < n; i++) coded += idx[i] >= 0;
+  expand_.resize(coded);
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(packed);
+  int k = 0;
+  for (int i = 0; i < n; i++) {
+    if (idx[i] < 0) { recs_[i] = &kSkip; continue; }
+    const uint8_t* r = base + (size_t)idx[i] * 32;
+    MbOut& m = expand_[k++];
+    memcpy(&m, r, offsetof(MbOut, luma));
+    memcpy(m.chroma_dc, r + offsetof(MbOut, luma), sizeof(m.chroma_dc));
+    const unsigned mask = (unsigned)m.pad0[0] | ((unsigned)m.pad0[1] << 8) | ((unsigned)m.pad0[2] << 16);
+    memset(m.pad0, 0, sizeof(m.pad0));
+    memset(m.luma, 0, sizeof(m.luma));
+    memset(m.chroma_ac, 0, sizeof(m.chroma_ac));
+    const uint8_t* blk = r + 128;
+    for (int b = 0; b < 24; b++)
+      if ((mask >> b) & 1) { memcpy(b < 16 ? m.luma[b] : m.chroma_ac[b - 16], blk, 32); blk += 32; }
+    recs_[i] = &m;
+  }
   write_au(idr, recs_.data(), au);
 }
 

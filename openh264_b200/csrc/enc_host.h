@@ -37,11 +37,12 @@ struct StreamCtl {
   EncFrameParams frame_params(bool idr, bool ref_is_p) const;
   // serialises the access unit of the frame just coded (SPS+PPS+IDR slice, or P slice)
   void write_access_unit(bool idr, const MbOut* mbs, std::vector<uint8_t>* au);                 // one record per MB
-  // packed form: idx[mb] = position of the macroblock's record in `packed`, or -1 for a P_SKIP macroblock
+  // compact form (k_pack_records): idx[mb] = offset of the macroblock's record in `packed` in 32-byte units, or -1 for P_SKIP
   void write_access_unit_packed(bool idr, const MbOut* packed, const int32_t* idx, std::vector<uint8_t>* au);
  private:
   void write_au(bool idr, const MbOut* const* recs, std::vector<uint8_t>* au);
   std::vector<const MbOut*> recs_;
+  std::vector<MbOut> expand_;               // compact records of the coded macroblocks, expanded for the slice writer
  public:
 };
 

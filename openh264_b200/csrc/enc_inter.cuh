@@ -209,7 +209,7 @@ MBK_FN void dct_luma_mb(MbScratch& s, const uint8_t* pred /*stride 16*/) {
   warp_sync();
 }
 
-MBK_FN SkipResult pskip_enc(const MbCtx& c, MbScratch& s, int sad_pred_skip, int ref_mb_type) {
+MBK_STAGE SkipResult pskip_enc(const MbCtx& c, MbScratch& s, int sad_pred_skip, int ref_mb_type) {
   SkipResult r;
   r.ok = false; r.cost_luma = 0; r.cost_skip = 0;
   int mvx, mvy;
@@ -625,7 +625,7 @@ MBK_HD void st_save(MbScratch& s, int is_skip, int cost_luma, int cost_skip_mb, 
   warp_sync();
 }
 
-MBK_FN int inter_stage_a(const MbCtx& c, MbScratch& s) {
+MBK_STAGE int inter_stage_a(const MbCtx& c, MbScratch& s) {
   const int mbw = c.p.mb_w, idx = c.mby * mbw + c.mbx;
   fill_inter_cache(c, s);
   phase_mark(s, 1);
@@ -660,7 +660,7 @@ MBK_FN int inter_stage_a(const MbCtx& c, MbScratch& s) {
   return is_skip ? MBS_BSKIP : MBS_B;
 }
 
-MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
+MBK_STAGE int inter_stage_b(const MbCtx& c, MbScratch& s) {
   const int mbw = c.p.mb_w, idx = c.mby * mbw + c.mbx;
   const bool is_skip = s.st.is_skip != 0;
   int cost_luma = s.st.cost_luma, cost_skip_mb = s.st.cost_skip_mb, p16_mvx = s.st.p16_mvx, p16_mvy = s.st.p16_mvy;
@@ -870,7 +870,7 @@ MBK_FN int inter_stage_b(const MbCtx& c, MbScratch& s) {
 }
 
 // the intra branch of a P macroblock (WelsMdFirstIntraMode :1829 after the 16x16 cost won)
-MBK_FN int inter_stage_c(const MbCtx& c, MbScratch& s) {
+MBK_STAGE int inter_stage_c(const MbCtx& c, MbScratch& s) {
   const int idx = c.mby * c.p.mb_w + c.mbx;
   const int bb = s.st.bb;
   int cost = s.st.cost16;

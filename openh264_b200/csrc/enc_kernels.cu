@@ -8,6 +8,7 @@
 // predictors, intra neighbours, skip context (SURVEY.md §7 hard part 1); bit-exactness forbids breaking
 // that chain, so parallelism comes from rows (2-MB lag) x independent streams of the batch.
 #include <cuda.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -164,6 +165,13 @@ __device__ __forceinline__ void esched_push(const EncSched& q, int total, int st
 
 // optional batch statistics (debug, B2H264_ENC_STATS): per ready list [batches, tasks, batch cycles]; [NQ] = leader wait cycles
 __device__ unsigned long long g_batch_stats[NQ + 1][3];
+__device__ unsigned long long g_fill_stats[NQ][ENC_WPC + 1][2];      // per list and batch fill: [batches, cycles]
+extern "C" int b2h264_debug_fill_stats(unsigned long long* out, int* n_lists, int* wpc, int reset) {
+  *n_lists = NQ; *wpc = ENC_WPC;
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_fill_stats, sizeof(g_fill_stats));
+  if (reset) { void* a = nullptr; if (cudaGetSymbolAddress(&a, g_fill_stats) == cudaSuccess) cudaMemset(a, 0, sizeof(g_fill_stats)); }
+  return (int)e;
+}
 extern "C" int b2h264_debug_batch_stats(unsigned long long* out, int reset) {
   cudaError_t e = cudaMemcpyFromSymbol(out, g_batch_stats, sizeof(g_batch_stats));
   if (e == cudaSuccess && reset) { unsigned long long z[NQ + 1][3] = {}; e = cudaMemcpyToSymbol(g_batch_stats, z, sizeof(z)); }
@@ -226,7 +234,7 @@ __device__ __forceinline__ void run_task(const StreamFrame* sf, const EncSched& 
 #define ENC_FREE_QUOTA 4
 #endif
 template <class Body>
-__device__ __forceinline__ void run_stages(const StreamFrame* sf, int n_streams, const EncSched q, MbScratch& s, int stats, Body body) {
+__device__ __forceinline__ void run_stages(const StreamFrame* sf, int n_streams, const EncSched q, MbScratch& s, int stats, bool legacy_claim, Body body) {
   __shared__ int s_k, s_base, s_n, s_next;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int mb_w = sf[0].p.mb_w, mb_h = sf[0].p.mb_h, n_mb = mb_w * mb_h, total = n_streams * n_mb;
@@ -235,27 +243,54 @@ __device__ __forceinline__ void run_stages(const StreamFrame* sf, int n_streams,
     if (threadIdx.x == 0) {
       int k = 0, h = 0, n = 0;
       const long long t_wait = stats ? clock64() : 0;
+      unsigned long long n_poll = 0, n_fail = 0, n_idle = 0;
       for (;;) {
-        if (ld_volatile(q.ctl + 2 * NQ) >= total) { n = -1; break; }
+        n_poll++;
+        // ONE look at the control block: heads, tails and the finished count share a line, three independent 16-byte loads
+        // (five dependent pairs of scalar loads cost the leader five L2 round trips per look)
+        int c[12];
+        static_assert(2 * NQ + 1 <= 12, "control block fits three vector loads");
+#pragma unroll
+        for (int v = 0; v < 3; v++)
+          asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(c[4 * v]), "=r"(c[4 * v + 1]), "=r"(c[4 * v + 2]), "=r"(c[4 * v + 3]) : "l"(q.ctl + 4 * v) : "memory");
+        if (c[2 * NQ] >= total) { n = -1; break; }
         // later stages first (they finish macroblocks others wait for); a FULL batch beats a partial one
         int best = -1, best_avail = 0;
 #pragma unroll
         for (int kk = NQ - 1; kk >= 0; kk--) {
-          const int avail = ld_volatile(q.ctl + NQ + kk) - ld_volatile(q.ctl + kk);
-          if (avail >= ENC_WPC) { best = kk; best_avail = avail; break; }
-          if (avail > best_avail) { best = kk; best_avail = avail; }
+          const int avail = c[NQ + kk] - c[kk];
+          if (avail >= ENC_WPC && best_avail < ENC_WPC) { best = kk; best_avail = avail; }
+          else if (best_avail < ENC_WPC && avail > best_avail) { best = kk; best_avail = avail; }
         }
         if (best >= 0) {
           const int cap = ((ENC_FREE_STAGES >> (best + 1)) & 1) ? ENC_WPC * ENC_FREE_QUOTA : ENC_WPC;
-          h = ld_volatile(q.ctl + best);
-          n = min(cap, ld_volatile(q.ctl + NQ + best) - h);
-          if (n > 0 && atomicCAS(q.ctl + best, h, h + n) == h) { k = best; break; }
+          int tail = 0;
+#pragma unroll
+          for (int kk = 0; kk < NQ; kk++) if (kk == best) { h = c[kk]; tail = c[NQ + kk]; }
+          bool got = false;
+          for (;;) {                       // a lost race returns the new head: claim from there instead of looking at every list again
+            n = min(cap, tail - h);
+            if (n <= 0) break;
+            const int old = atomicCAS(q.ctl + best, h, h + n);
+            if (old == h) { got = true; break; }
+            n_fail++;
+            h = old;
+            if (legacy_claim) break;
+          }
+          if (got) { k = best; break; }
           continue;
         }
+        n_idle++;
         __nanosleep(100);
       }
       s_k = k; s_base = h; s_n = n; s_next = 0;
-      if (stats) { t_batch = clock64(); atomicAdd(&g_batch_stats[NQ][2], (unsigned long long)(t_batch - t_wait)); }
+      if (stats) {
+        t_batch = clock64();
+        atomicAdd(&g_batch_stats[NQ][2], (unsigned long long)(t_batch - t_wait));
+        atomicAdd(&g_batch_stats[NQ][0], n_poll + (n_fail << 32));        // low word: polls, high word: failed claims
+        atomicAdd(&g_batch_stats[NQ][1], n_idle);
+      }
     }
     __syncthreads();
     const int k = s_k, base = s_base, n = s_n;
@@ -284,7 +319,10 @@ __device__ __forceinline__ void run_stages(const StreamFrame* sf, int n_streams,
     __syncthreads();
     if (stats && threadIdx.x == 0) {
       atomicAdd(&g_batch_stats[k][0], 1ull);
-      atomicAdd(&g_batch_stats[k][2], (unsigned long long)(clock64() - t_batch));
+      const unsigned long long dt = (unsigned long long)(clock64() - t_batch);
+      atomicAdd(&g_batch_stats[k][2], dt);
+      atomicAdd(&g_fill_stats[k][min(n, ENC_WPC)][0], 1ull);
+      atomicAdd(&g_fill_stats[k][min(n, ENC_WPC)][1], dt);
     }
   }
 }
@@ -349,7 +387,7 @@ __global__ void __launch_bounds__(32 * ENC_WPC, ENC_MIN_CTAS) k_encode_mbs(const
   __syncthreads();
   const void* tmap = win_mode == 1 ? (const void*)&tm_ref : win_mode == 3 ? tm_global : nullptr;
   const int wmode = win_mode == 3 ? 1 : win_mode;
-  run_stages(sf, n_streams, q, s, stats & 1, [&](const StreamFrame& F, int x, int y, int stage) {
+  run_stages(sf, n_streams, q, s, stats & 1, (stats & 4) != 0, [&](const StreamFrame& F, int x, int y, int stage) {
     const long long t0 = (stats & 1) ? clock64() : 0;
     mb_ctx(s.ctx, F.p, F.f, x, y);
     if ((threadIdx.x & 31) == 0) { s.ctx.tmap_ref = tmap; s.ctx.wbar = wb; s.ctx.win_mode = wmode; }
@@ -557,7 +595,7 @@ int enc_launch_frame(const StreamFrame* d_sf, const uint8_t* const* d_src, int n
   int blocks = enc_grid_blocks();
   const int need = (total + ENC_WPC - 1) / ENC_WPC;
   if (blocks > need) blocks = need;
-  static const int stats = (getenv("B2H264_ENC_STATS") ? 1 : 0) | (getenv("B2H264_FUSE_STAGES") ? 2 : 0);
+  static const int stats = (getenv("B2H264_ENC_STATS") ? 1 : 0) | (getenv("B2H264_FUSE_STAGES") ? 2 : 0) | (getenv("B2H264_LEGACY_CLAIM") ? 4 : 0);
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
   // B2H264_ENC_WIN: 0 = search out of the plane, 1 = TMA window, descriptor passed as kernel parameter (default),
@@ -615,47 +653,70 @@ int dec_launch_frame(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h,
   return b2h264_launched();
 }
 
-// ---- record hand-over: only coded macroblocks travel ---------------------------------------------------------------
-// One CTA per stream.  idx[mb] = rank of the macroblock among the stream's coded (non P_SKIP) macroblocks or -1;
-// the coded records are written back to back into `pack` — which is MAPPED PINNED HOST memory: the SMs' 16-byte
-// stores go over PCIe as posted writes, there is no separate copy and no size round trip (a P picture hands over
-// ~14 % of the 896-byte records: 7.3 MB -> ~1 MB per 1080p picture).
+// ---- record hand-over: only coded macroblocks travel, and of those only the residual blocks that carry levels ------
+// One CTA per stream, a warp per coded macroblock.  `pack` is MAPPED PINNED HOST memory: the SMs' 16-byte stores go over
+// PCIe as posted writes, there is no separate copy and no size round trip.  The hand-over is PCIe-bound (whole 896-byte
+// records of the coded macroblocks were 326 MB per 256 x 1080p pictures, ~11 ms at the ~28 GB/s such stores reach), so a
+// record is compacted before it travels (enc_types.h: MbRecHead):
+//   128-byte head = MbOut bytes [0, 112) + chroma_dc, with the presence mask of the 24 residual blocks in pad0[3]
+//   32 bytes per PRESENT block (luma in coding order 0..15, chroma AC 16..23): inside a coded 8x8 / chroma AC set and not all zero
+// idx[mb] = offset of the macroblock's record in 32-byte units, or -1 for P_SKIP; cnt[stream] = units written.
+// Records land in whatever order the warps finish (one shared-memory atomic hands out the space); the host goes through idx.
 #define PACK_THREADS 256          // small CTAs: the kernel is PCIe-bound and must leave the SMs to the deblocking kernel
-__global__ void __launch_bounds__(PACK_THREADS) k_pack_records(const StreamFrame* __restrict__ sf, int n_mb, MbOut* __restrict__ pack,
-                                                               int32_t* __restrict__ idx, int32_t* __restrict__ cnt, int32_t* __restrict__ list) {
-  __shared__ int warp_tot[PACK_THREADS / 32];
-  __shared__ int s_total;
+__global__ void __launch_bounds__(PACK_THREADS) k_pack_records(const StreamFrame* __restrict__ sf, int n_mb, uint4* __restrict__ pack,
+                                                               int32_t* __restrict__ idx, int32_t* __restrict__ cnt) {
+  __shared__ int s_units;
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wi = tid >> 5;
   const MbOut* out = sf[s].f.out;
   int32_t* my_idx = idx + (size_t)s * n_mb;
-  int32_t* my_list = list + (size_t)s * n_mb;
-  int base = 0;
-  for (int c0 = 0; c0 < n_mb; c0 += PACK_THREADS) {
-    const int mb = c0 + tid;
+  uint4* dst0 = pack + (size_t)s * n_mb * (sizeof(MbOut) / 16);
+  if (tid == 0) s_units = 0;
+  __syncthreads();
+  for (int c0 = wi * 32; c0 < n_mb; c0 += PACK_THREADS) {
+    const int mb = c0 + lane;
     const bool coded = mb < n_mb && out[mb].mb_type != MBT_PSKIP;
-    const unsigned m = __ballot_sync(0xffffffffu, coded);
-    if (lane == 0) warp_tot[wi] = __popc(m);
-    __syncthreads();
-    int off = base + __popc(m & ((1u << lane) - 1));
-    for (int w = 0; w < wi; w++) off += warp_tot[w];
-    if (tid == PACK_THREADS - 1) s_total = off + (coded ? 1 : 0) - base;
-    if (mb < n_mb) my_idx[mb] = coded ? off : -1;
-    if (coded) my_list[off] = mb;
-    __syncthreads();
-    base += s_total;
-    __syncthreads();
+    unsigned m = __ballot_sync(0xffffffffu, coded);
+    if (mb < n_mb && !coded) my_idx[mb] = -1;
+    while (m) {
+      const int j = __ffs(m) - 1;
+      m &= m - 1;
+      const MbOut* rec = out + c0 + j;
+      const uint4* rq = reinterpret_cast<const uint4*>(rec);
+      const int type = rec->mb_type, cbp = rec->cbp;
+      uint4 a = make_uint4(0, 0, 0, 0), b = a;
+      bool want = false;
+      if (lane < 16) want = type == MBT_I16x16 ? (cbp & 15) != 0 : ((cbp >> (lane >> 2)) & 1) != 0;
+      else if (lane < 24) want = (cbp >> 4) == 2;
+      if (want) {
+        const int q = lane < 16 ? 7 + 2 * lane : 40 + 2 * (lane - 16);      // luma at byte 112, chroma_ac at byte 640
+        a = rq[q]; b = rq[q + 1];
+        want = (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) != 0;
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, want);
+      int off = 0;
+      if (lane == 0) off = atomicAdd(&s_units, 4 + __popc(mask));
+      off = __shfl_sync(0xffffffffu, off, 0);
+      uint4* dst = dst0 + (size_t)off * 2;
+      if (lane < 8) {
+        uint4 v = rq[lane < 7 ? lane : 39];                                    // chroma_dc at byte 624
+        if (lane == 0) v.y = (v.y & 0xffu) | (mask << 8);                      // pad0[3] = presence mask
+        dst[lane] = v;
+      }
+      if (want) {
+        const int pos = 8 + 2 * __popc(mask & ((1u << lane) - 1));
+        dst[pos] = a; dst[pos + 1] = b;
+      }
+      if (lane == 0) my_idx[c0 + j] = off;
+    }
   }
-  if (tid == 0) cnt[s] = base;
-  constexpr int kW = (int)(sizeof(MbOut) / 16);
-  uint4* dst = reinterpret_cast<uint4*>(pack + (size_t)s * n_mb);
-  for (int q = tid; q < base * kW; q += PACK_THREADS) {
-    const int r = q / kW, w = q - r * kW;
-    dst[q] = reinterpret_cast<const uint4*>(out + my_list[r])[w];
-  }
+  __syncthreads();
+  if (tid == 0) cnt[s] = s_units;
 }
 
-int enc_launch_pack(const StreamFrame* d_sf, int n_streams, int n_mb, MbOut* pack, int32_t* idx, int32_t* cnt, int32_t* d_list, cudaStream_t st) {
-  k_pack_records<<<n_streams, PACK_THREADS, 0, st>>>(d_sf, n_mb, pack, idx, cnt, d_list);
+int enc_launch_pack(const StreamFrame* d_sf, int n_streams, int n_mb, MbOut* pack, int32_t* idx, int32_t* cnt, cudaStream_t st) {
+  static_assert(sizeof(MbOut) == 896 && offsetof(MbOut, luma) == 112 && offsetof(MbOut, chroma_dc) == 624 && offsetof(MbOut, chroma_ac) == 640 &&
+                offsetof(MbOut, pad0) == 5, "compact record layout");
+  k_pack_records<<<n_streams, PACK_THREADS, 0, st>>>(d_sf, n_mb, reinterpret_cast<uint4*>(pack), idx, cnt);
   return b2h264_launched();
 }
 

@@ -200,7 +200,7 @@ MBK_HD void mb_load_borders(const MbCtx& c, MbScratch& s) {
 // (11 independent global loads in flight: neighbour records, SAD history, current MB, border samples) and only
 // then stores to the scratch, so the macroblock pays one memory latency here instead of five serialized ones
 // (profiles/r01_phase_cycles.txt: 12k cycles/MB before).
-MBK_FN void mb_load_all(const MbCtx& c, MbScratch& s) {
+MBK_STAGE void mb_load_all(const MbCtx& c, MbScratch& s) {
   const int mbw = c.p.mb_w, idx = c.mby * mbw + c.mbx, l = lane_id();
   const int offs[4] = {-mbw - 1, -mbw, -mbw + 1, -1};
   const int bits[4] = {NB_TOPLEFT, NB_TOP, NB_TOPRIGHT, NB_LEFT};
@@ -638,7 +638,7 @@ MBK_FN int intra_mb_md_enc(const MbCtx& c, MbScratch& s, int cost_limit_for_i16 
 }
 
 // publishes MbInfo / RefMbInfo / MbOut of a finished macroblock
-MBK_FN void mb_publish(const MbCtx& c, MbScratch& s) {
+MBK_STAGE void mb_publish(const MbCtx& c, MbScratch& s) {
   const int idx = c.mby * c.p.mb_w + c.mbx;
   if (lane_id() == 0) {
     s.info.qp = (uint8_t)c.qp; s.info.qp_c = (uint8_t)c.qp_c;

@@ -276,13 +276,20 @@ k_mc_sad_tiled(const uint8_t* __restrict__ cur, int cs, const uint8_t* __restric
 //   vertical 6-tap:   two samples per register as 16-bit halves, biased so that every intermediate stays non-negative
 //   centre:           vertical pass (unrounded, 16 columns) in the packed form, horizontal pass on the 16-bit intermediates
 // Same arithmetic as McHorVer20 / McHorVer02 / McHorVer22 (codec/common/src/mc.cpp:187-231): (x + 16) >> 5, (x + 512) >> 10, clip.
+// All tile addresses below are 32-bit SHARED-space addresses (cvta.to.shared): ld.shared with 32-bit address arithmetic.
+// (Through generic pointers the compiler emitted LD.E and 64-bit pointer arithmetic: 165 generic loads, ~170 extra integer
+// instructions in the fractional path.)
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
 template <int N>
-__device__ __forceinline__ void seg_words(const uint8_t* a, uint32_t* s) {      // N words starting at ANY byte address
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(a) & ~uintptr_t(3));
-  const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(a) & 3) * 8;
+__device__ __forceinline__ void seg_words(uint32_t a, uint32_t* s) {      // N words starting at ANY byte address
+  const uint32_t w = a & ~3u, sh = (a & 3u) * 8;
   uint32_t r[N + 1];
 #pragma unroll
-  for (int k = 0; k <= N; k++) r[k] = w[k];
+  for (int k = 0; k <= N; k++) r[k] = lds32(w + 4 * k);
 #pragma unroll
   for (int k = 0; k < N; k++) s[k] = __funnelshift_r(r[k], r[k + 1], sh);
 }
@@ -292,27 +299,28 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
   asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
 }
-__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
-  return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
+// four signed values clipped to 0..255 and packed (a lowest byte): two cvt.pack.sat (I2IP) instead of 8 min/max + 3 inserts
+__device__ __forceinline__ uint32_t pack4_sat(int a, int b, int c, int d) {
+  uint32_t hi, r;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(d), "r"(c), "r"(0));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(b), "r"(a), "r"(hi));
+  return r;
 }
-// half-sample row H(x0 .. x0+7) at row pointer `row` (sample x0 at row[0])
-__device__ __forceinline__ uint2 h8(const uint8_t* row) {
+// half-sample row H(x0 .. x0+7) at row address `row` (sample x0 at row + 0)
+__device__ __forceinline__ uint2 h8(uint32_t row) {
   uint32_t s[4];
   seg_words<4>(row - 2, s);
+  uint32_t w[12];                                   // w[i] = bytes i .. i+3 of the row from sample x0 - 2
+#pragma unroll
+  for (int i = 0; i < 12; i++) w[i] = (i & 3) ? __funnelshift_r(s[i >> 2], s[(i >> 2) + 1], 8 * (i & 3)) : s[i >> 2];
   int v[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const uint32_t w0 = (i & 3) ? __funnelshift_r(s[i >> 2], s[(i >> 2) + 1], 8 * (i & 3)) : s[i >> 2];
-    const int j = i + 4;
-    const uint32_t w1 = (j & 3) ? __funnelshift_r(s[j >> 2], s[(j >> 2) + 1], 8 * (j & 3)) : s[j >> 2];
-    v[i] = dp4a_us(w0, (int)0x1414FB01, dp4a_us(w1, (int)0x000001FB, 16));
-    v[i] = min(max(v[i] >> 5, 0), 255);
-  }
-  return make_uint2(pack4(v[0], v[1], v[2], v[3]), pack4(v[4], v[5], v[6], v[7]));
+  for (int i = 0; i < 8; i++) v[i] = dp4a_us(w[i], (int)0x1414FB01, dp4a_us(w[i + 4], (int)0x000001FB, 16)) >> 5;
+  return make_uint2(pack4_sat(v[0], v[1], v[2], v[3]), pack4_sat(v[4], v[5], v[6], v[7]));
 }
 // packed vertical 6-tap of NW words per row: t[q] = (tap(col 2q) + 2560) | (tap(col 2q + 1) + 2560) << 16, rows a..f at base + k * P
 template <int NW>
-__device__ __forceinline__ void v_taps(const uint8_t* base, int P, uint32_t* t) {
+__device__ __forceinline__ void v_taps(uint32_t base, int P, uint32_t* t) {
 #pragma unroll
   for (int q = 0; q < 2 * NW; q++) t[q] = 0x0A000A00u;
   // rows in the order c, d (x20), a, f (x1), b, e (x -5): every partial sum stays positive in both halves
@@ -330,8 +338,8 @@ __device__ __forceinline__ void v_taps(const uint8_t* base, int P, uint32_t* t) 
     }
   }
 }
-// half-sample column V(x0 .. x0+7): `p` points at sample (x0, row) of the integer plane
-__device__ __forceinline__ uint2 v8(const uint8_t* p, int P) {
+// half-sample column V(x0 .. x0+7): `p` = address of sample (x0, row) of the integer plane
+__device__ __forceinline__ uint2 v8(uint32_t p, int P) {
   uint32_t t[4];
   v_taps<2>(p - 2 * P, P, t);
 #pragma unroll
@@ -342,7 +350,7 @@ __device__ __forceinline__ uint2 v8(const uint8_t* p, int P) {
   return make_uint2(__byte_perm(t[0], t[1], 0x6420), __byte_perm(t[2], t[3], 0x6420));
 }
 // centre samples C(x0 .. x0+7) of the row of `p`
-__device__ __forceinline__ uint2 c8(const uint8_t* p, int P) {
+__device__ __forceinline__ uint2 c8(uint32_t p, int P) {
   uint32_t t[8];
   v_taps<4>(p - 2 * P - 2, P, t);                       // unrounded vertical taps (+2560) of columns x0-2 .. x0+13
   int m[13];
@@ -352,18 +360,18 @@ __device__ __forceinline__ uint2 c8(const uint8_t* p, int P) {
 #pragma unroll
   for (int i = 0; i < 8; i++) {
     const int x = (m[i] + m[i + 5]) - 5 * (m[i + 1] + m[i + 4]) + 20 * (m[i + 2] + m[i + 3]) - 32 * 2560 + 512;
-    v[i] = min(max(x >> 10, 0), 255);
+    v[i] = x >> 10;
   }
-  return make_uint2(pack4(v[0], v[1], v[2], v[3]), pack4(v[4], v[5], v[6], v[7]));
+  return make_uint2(pack4_sat(v[0], v[1], v[2], v[3]), pack4_sat(v[4], v[5], v[6], v[7]));
 }
-__device__ __forceinline__ uint2 g8(const uint8_t* p) {
+__device__ __forceinline__ uint2 g8(uint32_t p) {
   uint32_t s[2];
   seg_words<2>(p, s);
   return make_uint2(s[0], s[1]);
 }
 __device__ __forceinline__ uint2 avg8(uint2 a, uint2 b) { return make_uint2(__vavgu4(a.x, b.x), __vavgu4(a.y, b.y)); }
-// eight prediction samples at quarter-sample phase (fx, fy); p = integer sample (x0, row) in the tile
-__device__ __forceinline__ uint2 qpel8(const uint8_t* p, int P, int fx, int fy) {
+// eight prediction samples at quarter-sample phase (fx, fy); p = address of integer sample (x0, row) in the tile
+__device__ __forceinline__ uint2 qpel8(uint32_t p, int P, int fx, int fy) {
   if (fy == 0) {
     const uint2 b = h8(p);
     return fx == 2 ? b : avg8(b, g8(p + (fx == 3)));
@@ -390,10 +398,6 @@ k_mc_sad_tma(const __grid_constant__ CUtensorMap tm_cur, const __grid_constant__
              const int16_t* __restrict__ mv, int k, int32_t* __restrict__ cost) {
   __shared__ __align__(128) uint8_t t_cur[16 * MCT_H][16 * MCT_W];
   __shared__ __align__(128) uint8_t t_ref[MCT_ROWS][MCT_PITCH];
-  // A bulk tensor copy lays the tile down densely: 160 bytes = 40 words per row, so rows r and r + 4 start in the same bank
-  // and the 16 rows a warp interpolates at once collide four ways.  Tiles with fractional vectors are therefore copied once
-  // into a 41-word pitch (rows spread over all 32 banks) before the packed interpolation reads them ~50 words per lane.
-  __shared__ __align__(16) uint8_t t_pad[MCT_ROWS][MCT_PITCH + 4];
   __shared__ __align__(8) unsigned long long bar;
   const int mbx0 = blockIdx.x * MCT_W, mby0 = blockIdx.y * MCT_H;
   const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar);
@@ -424,23 +428,6 @@ k_mc_sad_tma(const __grid_constant__ CUtensorMap tm_cur, const __grid_constant__
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
                    : "=r"(ok) : "r"(bar_a) : "memory");
   }
-  {
-    // does any candidate of this tile have a fractional vector?  (each warp scans its own column of macroblocks)
-    int frac = 0;
-    if (mbx < mb_w)
-      for (int i = l; i < MCT_H * k; i += 32) {
-        const int ty = i / k, c = i - ty * k;
-        if (mby0 + ty < mb_h) frac |= __ldg(reinterpret_cast<const int*>(mv + (size_t)(((mby0 + ty) * mb_w + mbx) * k + c) * 2)) & 0x00030003;
-      }
-    if (__syncthreads_or(frac)) {
-      constexpr int kW = MCT_PITCH / 4;
-      for (int i = threadIdx.x; i < MCT_ROWS * kW; i += blockDim.x) {
-        const int r = i / kW, w = i - r * kW;
-        reinterpret_cast<uint32_t*>(&t_pad[r][0])[w] = reinterpret_cast<const uint32_t*>(&t_ref[r][0])[w];
-      }
-      __syncthreads();
-    }
-  }
   if (mbx >= mb_w) return;
   const uint32_t cur_s = (uint32_t)__cvta_generic_to_shared(&t_cur[0][16 * tx]);
   const uint32_t ref_s = (uint32_t)__cvta_generic_to_shared(&t_ref[MCT_TOP][MCT_HALO_X + 16 * tx]);
@@ -468,9 +455,10 @@ k_mc_sad_tma(const __grid_constant__ CUtensorMap tm_cur, const __grid_constant__
         }
       } else {                                 // fractional vector: lane = (row, 8-sample half), packed interpolation, packed SAD
         const int r = l >> 1, x0 = (l & 1) * 8;
-        const uint8_t* p = &t_pad[MCT_TOP + 16 * ty + r][MCT_HALO_X + 16 * tx + x0] + (mvy >> 2) * (MCT_PITCH + 4) + (mvx >> 2);
-        const uint2 pr = qpel8(p, MCT_PITCH + 4, fx, fy);
-        const uint2 cw = *reinterpret_cast<const uint2*>(&t_cur[16 * ty + r][16 * tx + x0]);
+        const uint32_t p = ref_s + (16 * ty + r + (mvy >> 2)) * MCT_PITCH + x0 + (mvx >> 2);
+        const uint2 pr = qpel8(p, MCT_PITCH, fx, fy);
+        uint2 cw;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cw.x), "=r"(cw.y) : "r"(cur_s + (16 * ty + r) * (16 * MCT_W) + x0));
         s = (int)(__vsadu4(cw.x, pr.x) + __vsadu4(cw.y, pr.y));
       }
       s = warp_sum(s);

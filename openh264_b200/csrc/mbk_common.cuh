@@ -24,6 +24,13 @@
 // notes in profiles/r01_encode_stages.txt).  Externally visible functions follow the standard ABI.  Every
 // translation unit is compiled with the same register cap because nvlink keeps one copy of each function.
 #define MBK_FN inline __host__ __device__ __noinline__
+// stage entry points have ONE call site each: inlined there, they cost no code and save the callee-saved register
+// spill / reload of a real call (17-27 STL + LDL per call: 4 % of the encode kernel's instructions, profiles/r02_encode_local.txt)
+#ifdef B2H264_STAGE_CALLS                  // profiling variant: stage entry points as real calls
+#define MBK_STAGE MBK_FN
+#else
+#define MBK_STAGE __host__ __device__ __forceinline__
+#endif
 // loops around calls to the big warp routines are kept rolled: the macroblock kernel is bound by instruction fetch (the code one
 // stage walks through does not fit the instruction cache), so code size is time
 #ifdef __CUDACC__

@@ -17,6 +17,7 @@
 #include "enc_host.h"
 #include "enc_launch.h"
 #include "h264_parse.h"
+#include "host_pool.h"
 
 using namespace b2h264;
 
@@ -27,6 +28,9 @@ struct b2h264_dec {
   int S = 0, mb_w = 0, mb_h = 0, n_mb = 0;
   StreamCtl geo;                          // picture geometry (strides, padded rows)
   std::vector<ParserState> parser;
+  std::vector<ParsedPicture> parsed;      // per stream: the access unit of the running call
+  std::vector<int> parse_rc;
+  Pool* pool = nullptr;                   // the streams are parsed side by side (the parser is the decoder's host cost)
   int slots = 2;                          // picture slots per stream (num_ref_frames + 1 of the most demanding stream so far)
   std::vector<int> out_cx, out_cy;        // per active stream: luma samples cropped at the left / top of the output
   std::vector<int> out_slot;              // per active stream: slot of the picture decoded in this call
@@ -67,6 +71,9 @@ int b2h264_dec_create(const b2h264_dec_config* cfg, b2h264_dec** out) {
   d->geo.init(cfg->width, cfg->height, 26, 30.0f, 0);
   d->mb_w = d->geo.sp.mb_w; d->mb_h = d->geo.sp.mb_h; d->n_mb = d->mb_w * d->mb_h;
   d->parser.resize(d->S);
+  d->parsed.resize(d->S);
+  d->parse_rc.assign(d->S, 0);
+  { int nt = usable_cores(); if (nt > d->S) nt = d->S; d->pool = new Pool(nt < 1 ? 1 : nt); }
   d->pic_y_bytes = (size_t)d->geo.rec_stride_y() * d->geo.rec_rows_y();
   d->pic_c_bytes = (size_t)d->geo.rec_stride_c() * d->geo.rec_rows_c();
   d->pic_bytes = d->pic_y_bytes + 2 * d->pic_c_bytes;
@@ -95,6 +102,7 @@ void b2h264_dec_destroy(b2h264_dec* d) {
   cudaFree(d->d_mbi); cudaFree(d->d_recs); cudaFree(d->d_aux); cudaFreeHost(d->h_aux); cudaFree(d->d_sf); cudaFree(d->d_ws);
   cudaFreeHost(d->h_recs); cudaFreeHost(d->h_sf);
   if (d->st) cudaStreamDestroy(d->st);
+  delete d->pool;
   delete d;
 }
 
@@ -106,14 +114,27 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
   const int S = d->S;
   int deblock = 1;
   d->act.clear(); d->act_ref.clear(); d->out_slot.clear(); d->out_cx.clear(); d->out_cy.clear();
+  // 1. parse: every stream's access unit on the pool (streams are independent; a stream's parser state is its own)
+  {
+    std::function<void(int)> job = [&](int s) {
+      ParsedPicture& pp = d->parsed[s];               // a fresh picture that keeps the record arrays' storage
+      std::vector<MbOut> m = std::move(pp.mbs);
+      std::vector<DecMbAux> a = std::move(pp.aux);
+      pp = ParsedPicture();
+      pp.mbs = std::move(m); pp.aux = std::move(a);
+      d->parse_rc[s] = (!au[s] || au_bytes[s] <= 0) ? PARSE_NO_PICTURE : parse_access_unit(au[s], (size_t)au_bytes[s], &d->parser[s], &pp);
+    };
+    d->pool->run(S, job);
+  }
+  // 2. the batch: descriptors and records of the streams that carry a picture, in stream order
   for (int s = 0; s < S; s++) {
     if (got_picture) got_picture[s] = 0;
     if (!au[s] || au_bytes[s] <= 0) {
       if (!got_picture) { d->last_error_stream = s; return -1; }
       continue;
     }
-    ParsedPicture pic;
-    const int rc = parse_access_unit(au[s], (size_t)au_bytes[s], &d->parser[s], &pic);
+    ParsedPicture& pic = d->parsed[s];
+    const int rc = d->parse_rc[s];
     if (rc == PARSE_NO_PICTURE && got_picture) continue;
     if (rc != PARSE_OK) { d->last_error_stream = s; return -100 + (rc == PARSE_NO_PICTURE ? PARSE_INVALID : rc); }   // -101 truncated, -102 unsupported, -103 invalid, -104 no parameter sets, -105 picture incomplete
     const StreamParams& sp = d->parser[s].sp;
@@ -141,8 +162,6 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
     if (pic.any_deblock) deblock = 1;               // the filter kernel runs if any slice of any stream wants it (per-MB control inside)
     const int i = (int)d->act.size();
     d->act.push_back(s); d->act_ref.push_back(pic.is_ref ? 1 : 0); d->out_slot.push_back(pic.cur_slot); d->out_cx.push_back(pic.crop_left); d->out_cy.push_back(pic.crop_top);
-    memcpy(d->h_recs + (size_t)i * d->n_mb, pic.mbs.data(), (size_t)d->n_mb * sizeof(MbOut));
-    memcpy(d->h_aux + (size_t)i * d->n_mb, pic.aux.data(), (size_t)d->n_mb * sizeof(DecMbAux));
     StreamFrame& F = d->h_sf[i];
     memset(&F, 0, sizeof(F));
     F.p.mb_w = d->mb_w; F.p.mb_h = d->mb_h;
@@ -155,6 +174,14 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
   }
   const int n = (int)d->act.size();
   if (n == 0) return 0;
+  {
+    std::function<void(int)> job = [&](int i) {          // 7.3 MB of records per 1080p picture into the pinned staging area
+      const ParsedPicture& pic = d->parsed[d->act[i]];
+      memcpy(d->h_recs + (size_t)i * d->n_mb, pic.mbs.data(), (size_t)d->n_mb * sizeof(MbOut));
+      memcpy(d->h_aux + (size_t)i * d->n_mb, pic.aux.data(), (size_t)d->n_mb * sizeof(DecMbAux));
+    };
+    d->pool->run(n, job);
+  }
   CK(cudaMemcpyAsync(d->d_recs, d->h_recs, (size_t)n * d->n_mb * sizeof(MbOut), cudaMemcpyHostToDevice, d->st));
   CK(cudaMemcpyAsync(d->d_aux, d->h_aux, (size_t)n * d->n_mb * sizeof(DecMbAux), cudaMemcpyHostToDevice, d->st));
   CK(cudaMemcpyAsync(d->d_sf, d->h_sf, (size_t)n * sizeof(StreamFrame), cudaMemcpyHostToDevice, d->st));

@@ -13,53 +13,16 @@
 #include "b2h264_internal.h"
 #include "enc_host.h"
 #include "enc_launch.h"
+#include "host_pool.h"
 
 using b2h264::StreamCtl;
+using b2h264::Pool;
+using b2h264::usable_cores;
 
 namespace {
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
 
-// minimal fork-join pool for the per-stream CAVLC jobs
-class Pool {
- public:
-  explicit Pool(int n) {
-    for (int i = 0; i < n; i++) th_.emplace_back([this] { loop(); });
-  }
-  ~Pool() {
-    { std::lock_guard<std::mutex> l(m_); stop_ = true; }
-    cv_.notify_all();
-    for (auto& t : th_) t.join();
-  }
-  void run(int n, const std::function<void(int)>& fn) {
-    { std::lock_guard<std::mutex> l(m_); fn_ = &fn; next_ = 0; total_ = n; done_ = 0; }
-    cv_.notify_all();
-    std::unique_lock<std::mutex> l(m_);
-    done_cv_.wait(l, [&] { return done_ == total_; });
-    fn_ = nullptr;
-  }
- private:
-  void loop() {
-    for (;;) {
-      int job;
-      const std::function<void(int)>* fn;
-      {
-        std::unique_lock<std::mutex> l(m_);
-        cv_.wait(l, [&] { return stop_ || (fn_ && next_ < total_); });
-        if (stop_) return;
-        job = next_++; fn = fn_;
-      }
-      (*fn)(job);
-      { std::lock_guard<std::mutex> l(m_); if (++done_ == total_) done_cv_.notify_all(); }
-    }
-  }
-  std::vector<std::thread> th_;
-  std::mutex m_;
-  std::condition_variable cv_, done_cv_;
-  const std::function<void(int)>* fn_ = nullptr;
-  int next_ = 0, total_ = 0, done_ = 0;
-  bool stop_ = false;
-};
 
 }  // namespace
 
@@ -204,7 +167,7 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
   CK(cudaMalloc(&e->d_stash, enc_stash_bytes((int)S, e->ctl[0].sp.mb_h)));
   e->bs.resize(S);
   int nt = cfg->entropy_threads;
-  if (nt <= 0) { nt = (int)std::thread::hardware_concurrency(); if (nt > (int)S) nt = (int)S; if (nt < 1) nt = 1; }
+  if (nt <= 0) { nt = usable_cores(); if (nt > (int)S) nt = (int)S; if (nt < 1) nt = 1; }
   e->pool = new Pool(nt);
   *out = e;
   return 0;

@@ -151,7 +151,7 @@ MBK_HD const uint8_t* ref_chroma(const MbCtx& c, int pl, int px, int py) {
 }
 
 // chroma prediction of a (w x h luma) partition at luma offset (ox, oy) with quarter-pel luma mv
-MBK_FN void mc_chroma_part(const MbCtx& c, uint8_t* dst /*Cb, Cr at +64, stride 8*/, int ox, int oy, int w, int h, int mvx, int mvy) {
+MBK_STAGE void mc_chroma_part(const MbCtx& c, uint8_t* dst /*Cb, Cr at +64, stride 8*/, int ox, int oy, int w, int h, int mvx, int mvy) {
   const int cx = ox >> 1, cy = oy >> 1;
   MBK_NO_UNROLL
   for (int pl = 0; pl < 2; pl++) {
@@ -167,7 +167,7 @@ struct SkipResult { bool ok; int cost_luma; int cost_skip; int mvx, mvy; };
 // The reference walks the blocks serially and returns at the first failing test; every term of its running
 // score is >= 0, so the outcome is "no block has a level > 1 AND the total score stays below the threshold" —
 // order independent.  One lane per 4x4 block, two warp reductions.
-MBK_FN bool try_py_skip(const MbCtx& c, MbScratch& s) {
+MBK_STAGE bool try_py_skip(const MbCtx& c, MbScratch& s) {
   const int16_t* ff = tbl_quant_ff(c.qp);
   const int16_t* mf = tbl_quant_mf(c.qp);
   int big = 0, ctr = 0;
@@ -181,7 +181,7 @@ MBK_FN bool try_py_skip(const MbCtx& c, MbScratch& s) {
   big = warp_sum(big); ctr = warp_sum(ctr);
   return big == 0 && ctr < 6;
 }
-MBK_FN bool try_puv_skip(const MbCtx& c, MbScratch& s, int uv) {
+MBK_STAGE bool try_puv_skip(const MbCtx& c, MbScratch& s, int uv) {
   const int16_t* res = s.coef + 256 + 64 * uv;
   const int16_t* ff = tbl_quant_ff(c.qp_c);
   const int16_t* mf = tbl_quant_mf(c.qp_c);
@@ -246,16 +246,21 @@ MBK_STAGE SkipResult pskip_enc(const MbCtx& c, MbScratch& s, int sad_pred_skip, 
         for (int i = 0; i < 16; i++) s.coef[256 + 16 * t + i] = d[i];
       }
       warp_sync();
-      if (try_puv_skip(c, s, 0)) {
-        for (int t = lane_id(); t < 4; t += MBK_WS) {
-          int16_t d[16];
-          const int ox = (t & 1) * 4, oy = (t >> 1) * 4;
-          dct4x4(d, s.cur_c + 64 + oy * 8 + ox, 8, s.skip_pred + 320 + oy * 8 + ox, 8);
-          for (int i = 0; i < 16; i++) s.coef[320 + 16 * t + i] = d[i];
+      bool uv_ok = true;                     // Cb, then Cr only if Cb passes (one call site for the chroma test)
+      MBK_NO_UNROLL
+      for (int uv = 0; uv < 2 && uv_ok; uv++) {
+        if (uv) {
+          for (int t = lane_id(); t < 4; t += MBK_WS) {
+            int16_t d[16];
+            const int ox = (t & 1) * 4, oy = (t >> 1) * 4;
+            dct4x4(d, s.cur_c + 64 + oy * 8 + ox, 8, s.skip_pred + 320 + oy * 8 + ox, 8);
+            for (int i = 0; i < 16; i++) s.coef[320 + 16 * t + i] = d[i];
+          }
+          warp_sync();
         }
-        warp_sync();
-        ok = try_puv_skip(c, s, 1);
+        uv_ok = try_puv_skip(c, s, uv);
       }
+      ok = uv_ok;
     }
   }
   phase_mark(s, 15);
@@ -330,7 +335,7 @@ MBK_HD void win_wait(const MbCtx& c, MbScratch& s) {
 }
 
 // ---- integer search of one partition ------------------------------------------------------------------------
-MBK_FN void me_partition(const MbCtx& c, MbScratch& s, int blk_size, int ox, int oy, int mvp_x, int mvp_y, uint32_t sad_pred,
+MBK_STAGE void me_partition(const MbCtx& c, MbScratch& s, int blk_size, int ox, int oy, int mvp_x, int mvp_y, uint32_t sad_pred,
                          int n_mvc, const int16_t* mvc, MeState* st) {
   MeIn in;
   in.enc = s.cur_y + oy * 16 + ox; in.enc_stride = 16;
@@ -396,7 +401,7 @@ MBK_HD void qpel_pair(const QpelPlanes& q, int dx, int dy, const uint8_t** pa, c
   else { *pa = H + y3; *pb = V + x3; }
 }
 
-MBK_FN void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy, int w, int h, uint8_t* dst) {
+MBK_STAGE void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy, int w, int h, uint8_t* dst) {
   const int lw = w == 16 ? 4 : 3, lh = h == 16 ? 4 : 3;
   const uint8_t* enc = s.cur_y + oy * 16 + ox;
   const int rs = c.p.rec_stride_y;
@@ -515,7 +520,7 @@ MBK_FN void me_refine(const MbCtx& c, MbScratch& s, MeState* st, int ox, int oy,
 }
 
 // ---- luma residual of an inter MB (WelsEncInterY, svc_encode_mb.cpp:180) -------------------------------------------
-MBK_FN void enc_inter_y(const MbCtx& c, MbScratch& s) {
+MBK_STAGE void enc_inter_y(const MbCtx& c, MbScratch& s) {
   const int16_t* ff = tbl_quant_ff(c.qp);
   const int16_t* mf = tbl_quant_mf(c.qp);
   // per-block quantisation / scan in parallel; the JVT-O079 accumulation is order dependent -> serial scalar part
@@ -672,21 +677,22 @@ MBK_STAGE int inter_stage_b(const MbCtx& c, MbScratch& s) {
   int sad_pred_mb = 0;
   if (lane_id() == 0) s.win_ok = 0;
   warp_sync();
+  // Every integer search of the macroblock goes through ONE call site (me_partition is inlined there: no callee-saved
+  // register traffic, the search state stays in registers): round t = -1 is the 16x16 search (WelsMdP16x16 :978), rounds
+  // t >= 0 are the sub-partition shapes of `plan` (WelsMdInterFinePartition :1238 / WelsMdInterFinePartitionVaa :1270).
+  int16_t (*mvc)[2] = s.mvcand;
+  int px16 = 0, py16 = 0, n16 = 1;
   if (!is_skip) {
-    int px, py;
-    pred_mv(s, 0, 4, 0, &px, &py);
+    pred_mv(s, 0, 4, 0, &px16, &py16);
     {                                      // the window copy flies while the candidate list is put together
       int sx, sy;
-      me_start_point(c, px, py, &sx, &sy);
+      me_start_point(c, px16, py16, &sx, &sy);
       win_issue(c, s, sx, sy);
     }
     sad_pred_mb = predict_sad(s);
-    // step 2: P16x16 (WelsMdP16x16 :978)
-    int16_t (*mvc)[2] = s.mvcand;
-    int n = 1;                                                            // [0] = sMvBase (0,0)
-    n += (c.nb & NB_LEFT) ? 1 : 0;
-    n += (c.nb & NB_TOP) ? 1 : 0;
-    if (c.p.ref_is_p) { n += c.mbx < mbw - 1 ? 1 : 0; n += c.mby < c.p.mb_h - 1 ? 1 : 0; }
+    n16 += (c.nb & NB_LEFT) ? 1 : 0;                                      // [0] = sMvBase (0,0)
+    n16 += (c.nb & NB_TOP) ? 1 : 0;
+    if (c.p.ref_is_p) { n16 += c.mbx < mbw - 1 ? 1 : 0; n16 += c.mby < c.p.mb_h - 1 ? 1 : 0; }
     if (lane_id() == 0) {
       int k = 0;
       mvc[k][0] = 0; mvc[k][1] = 0; k++;
@@ -699,72 +705,57 @@ MBK_STAGE int inter_stage_b(const MbCtx& c, MbScratch& s) {
     }
     warp_sync();
     win_wait(c, s);
-    me_partition(c, s, BLK_16x16, 0, 0, px, py, (uint32_t)sad_pred_mb, n, &mvc[0][0], &me16);
-    p16_mvx = me16.mv_x; p16_mvy = me16.mv_y;
-    cost_luma = (int)me16.satd_cost;
   }
-  phase_mark(s, 3);
-  {
-    // intra check (WelsMdFirstIntraMode :1829)
-    int bb;
-    const int cost16 = md_i16x16(c, s, &bb);
-    phase_mark(s, 4);
-    if (cost16 < cost_luma) {
-      st_save(s, is_skip ? 1 : 0, cost_luma, cost_skip_mb, p16_mvx, p16_mvy, final_type);
-      if (lane_id() == 0) { s.st.cost16 = cost16; s.st.bb = bb; }
-      warp_sync();
-      return MBS_C;
+  int plan[3] = {0, 0, 0}, n_plan = 0, cost = 0;       // shapes: 0 = 16x16, 1 = 16x8, 2 = 8x16, 3 = 8x8
+  MBK_NO_UNROLL
+  for (int t = -1; t < n_plan; t++) {
+    const int shape = t < 0 ? 0 : plan[t];
+    int cst = 0;
+    if (t >= 0 || !is_skip) {
+      const int np = shape == 0 ? 1 : shape == 3 ? 4 : 2;
+      MeState* arr = shape == 0 ? &me16 : shape == 1 ? me16x8 : shape == 2 ? me8x16 : me8x8;
+      MBK_NO_UNROLL
+      for (int i = 0; i < np; i++) {
+        int px = px16, py = py16, ox = 0, oy = 0, blk = BLK_16x16, ci = 0, cw = 4, ch = 4, ncand = n16;
+        uint32_t sp = (uint32_t)sad_pred_mb;
+        if (shape == 1) { pred_16x8_mv(s, 8 * i, 0, &px, &py); oy = 8 * i; blk = BLK_16x8; ci = 8 * i; ch = 2; sp = (uint32_t)(sad_pred_mb >> 1); ncand = 1; }
+        else if (shape == 2) { pred_8x16_mv(s, 4 * i, 0, &px, &py); ox = 8 * i; blk = BLK_8x16; ci = 4 * i; cw = 2; sp = (uint32_t)(sad_pred_mb >> 1); ncand = 1; }
+        else if (shape == 3) { pred_mv(s, 4 * i, 2, 0, &px, &py); ox = (i & 1) * 8; oy = (i >> 1) * 8; blk = BLK_8x8; ci = 4 * i; cw = 2; ch = 2; sp = (uint32_t)(sad_pred_mb >> 2); ncand = 1; }
+        me_partition(c, s, blk, ox, oy, px, py, sp, ncand, &mvc[0][0], &arr[i]);     // sub-partitions: candidate [0] = (0, 0) only
+        if (shape != 0) cache_set(s, ci, cw, ch, arr[i].mv_x, arr[i].mv_y);
+        cst += (int)arr[i].satd_cost;
+      }
     }
-  }
-  if (is_skip) {
-    decided_pskip(c, s);
-    st_save(s, 1, cost_luma, cost_skip_mb, p16_mvx, p16_mvy, MBT_PSKIP);
-    inter_tail(c, s);
-    return MBS_DONE;
-  }
-  {
-
-    // step 3: sub-16x16 partitions (WelsMdInterFinePartition :1238 / WelsMdInterFinePartitionVaa :1270)
-    const int16_t mvc0[2] = {0, 0};
-    auto md_p8x8 = [&]() {
-      int cost8 = 0;
-      MBK_NO_UNROLL
-      for (int i = 0; i < 4; i++) {
-        int px, py;
-        pred_mv(s, 4 * i, 2, 0, &px, &py);
-        me_partition(c, s, BLK_8x8, (i & 1) * 8, (i >> 1) * 8, px, py, (uint32_t)(sad_pred_mb >> 2), 1, mvc0, &me8x8[i]);
-        cache_set(s, 4 * i, 2, 2, me8x8[i].mv_x, me8x8[i].mv_y);
-        cost8 += (int)me8x8[i].satd_cost;
+    if (t >= 0) {
+      // the first shape of the plan has to beat 16x16, a later one only the best so far (<=: md.cpp keeps the later shape on a tie)
+      if (t == 0) { if (cst < cost_luma) { cost = cst; final_type = shape == 3 ? MBT_P8x8 : shape == 1 ? MBT_P16x8 : MBT_P8x16; } else break; }
+      else if (cst <= cost) { cost = cst; final_type = shape == 1 ? MBT_P16x8 : MBT_P8x16; }
+      continue;
+    }
+    // ---- after the 16x16 round ----
+    if (!is_skip) { p16_mvx = me16.mv_x; p16_mvy = me16.mv_y; cost_luma = cst; }
+    phase_mark(s, 3);
+    {
+      // intra check (WelsMdFirstIntraMode :1829)
+      int bb;
+      const int cost16 = md_i16x16(c, s, &bb);
+      phase_mark(s, 4);
+      if (cost16 < cost_luma) {
+        st_save(s, is_skip ? 1 : 0, cost_luma, cost_skip_mb, p16_mvx, p16_mvy, final_type);
+        if (lane_id() == 0) { s.st.cost16 = cost16; s.st.bb = bb; }
+        warp_sync();
+        return MBS_C;
       }
-      return cost8;
-    };
-    auto md_p16x8 = [&]() {
-      int cst = 0;
-      MBK_NO_UNROLL
-      for (int i = 0; i < 2; i++) {
-        int px, py;
-        pred_16x8_mv(s, 8 * i, 0, &px, &py);
-        me_partition(c, s, BLK_16x8, 0, 8 * i, px, py, (uint32_t)(sad_pred_mb >> 1), 1, mvc0, &me16x8[i]);
-        cache_set(s, 8 * i, 4, 2, me16x8[i].mv_x, me16x8[i].mv_y);
-        cst += (int)me16x8[i].satd_cost;
-      }
-      return cst;
-    };
-    auto md_p8x16 = [&]() {
-      int cst = 0;
-      MBK_NO_UNROLL
-      for (int i = 0; i < 2; i++) {
-        int px, py;
-        pred_8x16_mv(s, 4 * i, 0, &px, &py);
-        me_partition(c, s, BLK_8x16, 8 * i, 0, px, py, (uint32_t)(sad_pred_mb >> 1), 1, mvc0, &me8x16[i]);
-        cache_set(s, 4 * i, 2, 4, me8x16[i].mv_x, me8x16[i].mv_y);
-        cst += (int)me8x16[i].satd_cost;
-      }
-      return cst;
-    };
+    }
+    if (is_skip) {
+      decided_pskip(c, s);
+      st_save(s, 1, cost_luma, cost_skip_mb, p16_mvx, p16_mvy, MBT_PSKIP);
+      inter_tail(c, s);
+      return MBS_DONE;
+    }
     // LOW_COMPLEXITY: the four 8x8 SADs of the macroblock against the previous source picture say which partition shapes
     // are worth a search (MdInterAnalysisVaaInfo_c md.cpp:389): 15 = homogeneous, none; 3/12 -> 16x8; 5/10 -> 8x16;
-    // 6/9 -> 8x8; anything else -> the full sequence of the other complexity modes
+    // 6/9 -> 8x8; anything else -> the full sequence of the other complexity modes (8x8, then 16x8 and 8x16 if 8x8 won)
     int vaa_sign = 0;
     if (c.p.fast_mode) {
       const int32_t* v = c.f.vaa_sad8x8 + 4 * idx;
@@ -773,73 +764,47 @@ MBK_STAGE int inter_stage_b(const MbCtx& c, MbScratch& s) {
       if (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3 < 20) vaa_sign = 15;               // INTER_VARIANCE_SAD_THRESHOLD
       else vaa_sign = (b0 > avg ? 8 : 0) | (b1 > avg ? 4 : 0) | (b2 > avg ? 2 : 0) | (b3 > avg ? 1 : 0);
     }
-    if (c.p.fast_mode && vaa_sign == 15) {
-    } else if (c.p.fast_mode && (vaa_sign == 3 || vaa_sign == 12)) {
-      if (md_p16x8() < cost_luma) final_type = MBT_P16x8;
-    } else if (c.p.fast_mode && (vaa_sign == 5 || vaa_sign == 10)) {
-      if (md_p8x16() < cost_luma) final_type = MBT_P8x16;
-    } else if (c.p.fast_mode && (vaa_sign == 6 || vaa_sign == 9)) {
-      if (md_p8x8() < cost_luma) final_type = MBT_P8x8;
-    } else {
-      const int cost8 = md_p8x8();
-      if (cost8 < cost_luma) {
-        int cost = cost8;
-        final_type = MBT_P8x8;
-        int cst = md_p16x8();
-        if (cst <= cost) { cost = cst; final_type = MBT_P16x8; }
-        cst = md_p8x16();
-        if (cst <= cost) { cost = cst; final_type = MBT_P8x16; }
-      }
-    }
+    if (c.p.fast_mode && vaa_sign == 15) n_plan = 0;
+    else if (c.p.fast_mode && (vaa_sign == 3 || vaa_sign == 12)) { plan[0] = 1; n_plan = 1; }
+    else if (c.p.fast_mode && (vaa_sign == 5 || vaa_sign == 10)) { plan[0] = 2; n_plan = 1; }
+    else if (c.p.fast_mode && (vaa_sign == 6 || vaa_sign == 9)) { plan[0] = 3; n_plan = 1; }
+    else { plan[0] = 3; plan[1] = 1; plan[2] = 2; n_plan = 3; }
+  }
+  {
     phase_mark(s, 6);
     // refinement (WelsMdInterMbRefinement :1573)
     uint8_t* pl = s.pred_y[0];
     uint8_t* pc = s.pred_c[0];
     int best_sad = 0;
-    if (final_type == MBT_P16x16) {
-      me_refine(c, s, &me16, 0, 0, 16, 16, pl);
-      cache_set(s, 0, 4, 4, me16.mv_x, me16.mv_y);
-      mb_mv_set(s, 0, 4, 4, me16.mv_x, me16.mv_y);
-      if (lane_id() == 0) { s.out.mvd[0][0] = (int16_t)(me16.mv_x - me16.mvp_x); s.out.mvd[0][1] = (int16_t)(me16.mv_y - me16.mvp_y); }
-      best_sad = (int)me16.sad_cost;
-      mc_chroma_part(c, pc, 0, 0, 16, 16, me16.mv_x, me16.mv_y);
-      cost_skip_mb = warp_sad(s.cur_y, 16, pl, 16, 4, 4) + warp_sad(s.cur_c, 8, pc, 8, 3, 3) + warp_sad(s.cur_c + 64, 8, pc + 64, 8, 3, 3);
-    } else if (final_type == MBT_P16x8) {
-      MBK_NO_UNROLL
-      for (int i = 0; i < 2; i++) {
-        { int qx, qy; pred_16x8_mv(s, 8 * i, 0, &qx, &qy); if (lane_id() == 0) { me16x8[i].mvp_x = qx; me16x8[i].mvp_y = qy; } warp_sync(); }
-        me_refine(c, s, &me16x8[i], 0, 8 * i, 16, 8, pl + 128 * i);
-        cache_set(s, 8 * i, 4, 2, me16x8[i].mv_x, me16x8[i].mv_y);
-        mb_mv_set(s, 8 * i, 4, 2, me16x8[i].mv_x, me16x8[i].mv_y);
-        if (lane_id() == 0) { s.out.mvd[i][0] = (int16_t)(me16x8[i].mv_x - me16x8[i].mvp_x); s.out.mvd[i][1] = (int16_t)(me16x8[i].mv_y - me16x8[i].mvp_y); }
-        best_sad += (int)me16x8[i].sad_cost;
-        mc_chroma_part(c, pc, 0, 8 * i, 16, 8, me16x8[i].mv_x, me16x8[i].mv_y);
+    {
+      // one loop over the partitions of the chosen shape: me_refine and mc_chroma_part have ONE call site (inlined there)
+      const int shape = final_type == MBT_P16x16 ? 0 : final_type == MBT_P16x8 ? 1 : final_type == MBT_P8x16 ? 2 : 3;
+      const int np = shape == 0 ? 1 : shape == 3 ? 4 : 2;
+      MeState* arr = shape == 0 ? &me16 : shape == 1 ? me16x8 : shape == 2 ? me8x16 : me8x8;
+      if (shape == 3) {
+        if (lane_id() == 0) { s.refc[9] = s.refc[21] = REF_NOT_AVAIL; }
+        warp_sync();
       }
-    } else if (final_type == MBT_P8x16) {
       MBK_NO_UNROLL
-      for (int i = 0; i < 2; i++) {
-        { int qx, qy; pred_8x16_mv(s, 4 * i, 0, &qx, &qy); if (lane_id() == 0) { me8x16[i].mvp_x = qx; me8x16[i].mvp_y = qy; } warp_sync(); }
-        me_refine(c, s, &me8x16[i], 8 * i, 0, 8, 16, pl + 8 * i);
-        cache_set(s, 4 * i, 2, 4, me8x16[i].mv_x, me8x16[i].mv_y);
-        mb_mv_set(s, 4 * i, 2, 4, me8x16[i].mv_x, me8x16[i].mv_y);
-        if (lane_id() == 0) { s.out.mvd[i][0] = (int16_t)(me8x16[i].mv_x - me8x16[i].mvp_x); s.out.mvd[i][1] = (int16_t)(me8x16[i].mv_y - me8x16[i].mvp_y); }
-        best_sad += (int)me8x16[i].sad_cost;
-        mc_chroma_part(c, pc, 8 * i, 0, 8, 16, me8x16[i].mv_x, me8x16[i].mv_y);
+      for (int i = 0; i < np; i++) {
+        int ox = 0, oy = 0, w = 16, h = 16, ci = 0, cw = 4, ch = 4;
+        if (shape != 0) {                      // the predictor is taken again with the neighbours' final vectors
+          int qx, qy;
+          if (shape == 1) { pred_16x8_mv(s, 8 * i, 0, &qx, &qy); oy = 8 * i; h = 8; ci = 8 * i; ch = 2; }
+          else if (shape == 2) { pred_8x16_mv(s, 4 * i, 0, &qx, &qy); ox = 8 * i; w = 8; ci = 4 * i; cw = 2; }
+          else { pred_mv(s, 4 * i, 2, 0, &qx, &qy); ox = (i & 1) * 8; oy = (i >> 1) * 8; w = 8; h = 8; ci = 4 * i; cw = 2; ch = 2; }
+          if (lane_id() == 0) { arr[i].mvp_x = qx; arr[i].mvp_y = qy; }
+          warp_sync();
+        }
+        me_refine(c, s, &arr[i], ox, oy, w, h, pl + oy * 16 + ox);
+        cache_set(s, ci, cw, ch, arr[i].mv_x, arr[i].mv_y);
+        mb_mv_set(s, ci, cw, ch, arr[i].mv_x, arr[i].mv_y);
+        if (lane_id() == 0) { s.out.mvd[i][0] = (int16_t)(arr[i].mv_x - arr[i].mvp_x); s.out.mvd[i][1] = (int16_t)(arr[i].mv_y - arr[i].mvp_y); }
+        best_sad += (int)arr[i].sad_cost;
+        mc_chroma_part(c, pc, ox, oy, w, h, arr[i].mv_x, arr[i].mv_y);
       }
-    } else {
-      if (lane_id() == 0) { s.refc[9] = s.refc[21] = REF_NOT_AVAIL; }
-      warp_sync();
-      MBK_NO_UNROLL
-      for (int i = 0; i < 4; i++) {
-        const int ox = (i & 1) * 8, oy = (i >> 1) * 8;
-        { int qx, qy; pred_mv(s, 4 * i, 2, 0, &qx, &qy); if (lane_id() == 0) { me8x8[i].mvp_x = qx; me8x8[i].mvp_y = qy; } warp_sync(); }
-        me_refine(c, s, &me8x8[i], ox, oy, 8, 8, pl + oy * 16 + ox);
-        cache_set(s, 4 * i, 2, 2, me8x8[i].mv_x, me8x8[i].mv_y);
-        mb_mv_set(s, 4 * i, 2, 2, me8x8[i].mv_x, me8x8[i].mv_y);
-        if (lane_id() == 0) { s.out.mvd[i][0] = (int16_t)(me8x8[i].mv_x - me8x8[i].mvp_x); s.out.mvd[i][1] = (int16_t)(me8x8[i].mv_y - me8x8[i].mvp_y); }
-        best_sad += (int)me8x8[i].sad_cost;
-        mc_chroma_part(c, pc, ox, oy, 8, 8, me8x8[i].mv_x, me8x8[i].mv_y);
-      }
+      if (shape == 0)
+        cost_skip_mb = warp_sad(s.cur_y, 16, pl, 16, 4, 4) + warp_sad(s.cur_c, 8, pc, 8, 3, 3) + warp_sad(s.cur_c + 64, 8, pc + 64, 8, 3, 3);
     }
     if (lane_id() == 0) c.f.sad_cost[idx] = best_sad;          // pCurMb->pSadCost[0]
     phase_mark(s, 7);

@@ -27,8 +27,9 @@ __constant__ uint8_t c_beta[52];
 __constant__ uint8_t c_tc0[52][3];
 }  // namespace mbk
 
+#define DEC_WPC 24         // warps per CTA of the decoder's macroblock kernel (one CTA per SM at 80 registers)
 #ifndef ENC_WPC
-#define ENC_WPC 24         // warps per CTA of the macroblock kernels (one CTA per SM at 80 registers)
+#define ENC_WPC 23         // WORKER warps per CTA of the encode kernel; one more warp schedules (24 x 32 x 80 registers = one CTA per SM)
 #endif
 
 __device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
@@ -144,9 +145,15 @@ enum { NQ = MBS_COUNT - 1 };                       // ready lists, index = stage
 struct EncSched {
   int* dep;          // per (stream, mb): notifications received so far
   int* queue;        // NQ ready lists of capacity `total` each, -1 = slot not yet written
-  int* ctl;          // [0..NQ) heads, [NQ..2NQ) tails, [2NQ] macroblocks finished
+  int* ctl;          // one 128-byte line per ready list: [32 k] head, [32 k + 1] tail; line NQ: [32 NQ] macroblocks finished
   uint4* stash;      // parked scratches
 };
+// The control words are spread over NQ + 1 lines (different L2 slices): every finished macroblock, every push and every
+// scheduler look / claim of 148 CTAs used to hit ONE line, and the queueing there slowed the workers' own atomics.
+__device__ __forceinline__ int* ctl_head(const EncSched& q, int k) { return q.ctl + 32 * k; }
+__device__ __forceinline__ int* ctl_tail(const EncSched& q, int k) { return q.ctl + 32 * k + 1; }
+__device__ __forceinline__ int* ctl_done(const EncSched& q) { return q.ctl + 32 * NQ; }
+constexpr int kCtlInts = 32 * (NQ + 1);
 // Only the live part of a scratch is parked (enc_mb.cuh: kParkCore + skip_pred or pred_y): slot = kParkSlot bytes
 constexpr int kStashU4 = kParkSlot / 16, kCoreU4 = kParkCore / 16;
 static_assert(kParkSlot % 16 == 0 && kParkCore % 16 == 0, "parked ranges are copied as uint4");
@@ -159,7 +166,7 @@ __device__ __forceinline__ void park_extra(int stage, int* off, int* n) {
 
 __device__ __forceinline__ void esched_push(const EncSched& q, int total, int stage, int id) {
   const int k = stage - 1;
-  const int slot = atomicAdd(q.ctl + NQ + k, 1);
+  const int slot = atomicAdd(ctl_tail(q, k), 1);
   *reinterpret_cast<volatile int*>(q.queue + (size_t)k * total + slot) = id;
 }
 
@@ -201,16 +208,18 @@ __device__ __forceinline__ void run_task(const StreamFrame* sf, const EncSched& 
   if (next == MBS_DONE) {
     __threadfence();
     if (lane == 0) {
-      if (x + 1 < mb_w) {                                                       // right neighbour: we are its left
-        if (atomicAdd(q.dep + id + 1, 1) + 1 == 1 + (y > 0)) esched_push(q, total, sf[si].p.is_idr ? MBS_I : MBS_A, id + 1);
-      }
-      if (y + 1 < mb_h) {
-        if (x > 0 && atomicAdd(q.dep + id + mb_w - 1, 1) + 1 == 1 + (x - 1 > 0))   // bottom-left: we are its top-right
-          esched_push(q, total, sf[si].p.is_idr ? MBS_I : MBS_A, id + mb_w - 1);
-        if (x == mb_w - 1 && atomicAdd(q.dep + id + mb_w, 1) + 1 == 1 + (x > 0))   // last column: we are its top
-          esched_push(q, total, sf[si].p.is_idr ? MBS_I : MBS_A, id + mb_w);
-      }
-      atomicAdd(q.ctl + 2 * NQ, 1);
+      // the (up to three) notifications are independent: issue the atomics together, one L2 round trip instead of three
+      const int first = sf[si].p.is_idr ? MBS_I : MBS_A;
+      const bool nr = x + 1 < mb_w;                                              // right neighbour: we are its left
+      const bool nbl = y + 1 < mb_h && x > 0;                                    // bottom-left: we are its top-right
+      const bool nb = y + 1 < mb_h && x == mb_w - 1;                             // last column: we are its top
+      const int r0 = nr ? atomicAdd(q.dep + id + 1, 1) : 0;
+      const int r1 = nbl ? atomicAdd(q.dep + id + mb_w - 1, 1) : 0;
+      const int r2 = nb ? atomicAdd(q.dep + id + mb_w, 1) : 0;
+      if (nr && r0 + 1 == 1 + (y > 0)) esched_push(q, total, first, id + 1);
+      if (nbl && r1 + 1 == 1 + (x - 1 > 0)) esched_push(q, total, first, id + mb_w - 1);
+      if (nb && r2 + 1 == 1 + (x > 0)) esched_push(q, total, first, id + mb_w);
+      atomicAdd(ctl_done(q), 1);
     }
   } else {
     int xo, xn;
@@ -222,108 +231,119 @@ __device__ __forceinline__ void run_task(const StreamFrame* sf, const EncSched& 
   }
 }
 
-// Optional FREE mode for selected stages (bit mask ENC_FREE_STAGES, off by default): the CTA claims up to
-// ENC_WPC * ENC_FREE_QUOTA tasks of that list with ONE global atomic, its warps draw them from a shared-memory
-// counter and nobody waits for a slower macroblock until the claim is used up.  Measured on stages A and Bs
-// (128 streams): 42.2 ms against 38.3 ms for lock-step batches — without the common start the warps drift apart
-// and the stage's code no longer stays in the instruction cache (cycles per stage-A macroblock 42 k -> 55 k).
-#ifndef ENC_FREE_STAGES
-#define ENC_FREE_STAGES 0
-#endif
-#ifndef ENC_FREE_QUOTA
-#define ENC_FREE_QUOTA 4
-#endif
+// The batches are claimed by a SCHEDULER WARP (warp ENC_WPC of the CTA, no macroblock scratch): while the ENC_WPC workers run
+// batch i it watches the ready lists and claims batch i + 1, so the claim (a look at the control block plus a contended
+// CAS: ~18 k cycles per batch when thread 0 did it between two batches, a fifth of the kernel) is off the workers' path
+// and a batch costs ONE CTA barrier instead of two.  Claimed macroblocks wait until the running batch ends, so the scheduler
+// only claims ahead when that cannot starve anybody: a FULL batch once the first worker has finished (or at any time when
+// the list holds two batches' worth); a partial batch only when the workers are already waiting — exactly the decision
+// thread 0 used to take at that moment.  (Experiments that gave up the common start of a batch — warp-asynchronous
+// draws, 2 x 12 and 3 x 8 warp groups — lost 1.4-2.9x to instruction-cache misses: profiles/r01_encode_icache.txt,
+// profiles/r02_encode_variants.txt.)
+struct BatchSlot { int k, base, n, pad; };
+constexpr int kEncThreads = 32 * (ENC_WPC + 1);
+__device__ __forceinline__ void enc_cta_barrier() { asm volatile("barrier.sync 1, %0;" ::"n"(kEncThreads) : "memory"); }
+
 template <class Body>
 __device__ __forceinline__ void run_stages(const StreamFrame* sf, int n_streams, const EncSched q, MbScratch& s, int stats, bool legacy_claim, Body body) {
-  __shared__ int s_k, s_base, s_n, s_next;
+  __shared__ BatchSlot s_slot[2];
+  __shared__ int s_fin[2];                 // workers of the batch in slot p that have finished their macroblock
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int mb_w = sf[0].p.mb_w, mb_h = sf[0].p.mb_h, n_mb = mb_w * mb_h, total = n_streams * n_mb;
-  for (;;) {
-    long long t_batch = 0;
-    if (threadIdx.x == 0) {
-      int k = 0, h = 0, n = 0;
-      const long long t_wait = stats ? clock64() : 0;
-      unsigned long long n_poll = 0, n_fail = 0, n_idle = 0;
-      for (;;) {
-        n_poll++;
-        // ONE look at the control block: heads, tails and the finished count share a line, three independent 16-byte loads
-        // (five dependent pairs of scalar loads cost the leader five L2 round trips per look)
-        int c[12];
-        static_assert(2 * NQ + 1 <= 12, "control block fits three vector loads");
+  if (warp == ENC_WPC) {
+    // ---- scheduler warp: lane 0 claims, the warp meets the workers at the barrier ----
+    int p = 0, run_n = 0;                  // run_n: macroblocks of the batch the workers are running (slot p ^ 1)
+    for (;;) {
+      if (lane == 0) {
+        int k = 0, h = 0, n = 0;
+        long long t_exposed = 0;
+        bool exposed = false;
+        unsigned long long n_poll = 0, n_fail = 0, n_idle = 0;
+        for (;;) {
+          const int fin = run_n ? *reinterpret_cast<volatile int*>(&s_fin[p ^ 1]) : 0;
+          const bool all_done = fin >= run_n;
+          if (stats && all_done && !exposed) { exposed = true; t_exposed = clock64(); }
+          n_poll++;
+          // ONE look at the control words: NQ + 1 independent loads (a line per list), one L2 round trip
+          int c[2 * NQ + 1];
 #pragma unroll
-        for (int v = 0; v < 3; v++)
-          asm volatile("ld.volatile.global.v4.s32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(c[4 * v]), "=r"(c[4 * v + 1]), "=r"(c[4 * v + 2]), "=r"(c[4 * v + 3]) : "l"(q.ctl + 4 * v) : "memory");
-        if (c[2 * NQ] >= total) { n = -1; break; }
-        // later stages first (they finish macroblocks others wait for); a FULL batch beats a partial one
-        int best = -1, best_avail = 0;
+          for (int kk = 0; kk < NQ; kk++)
+            asm volatile("ld.volatile.global.v2.s32 {%0, %1}, [%2];" : "=r"(c[kk]), "=r"(c[NQ + kk]) : "l"(ctl_head(q, kk)) : "memory");
+          asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(c[2 * NQ]) : "l"(ctl_done(q)) : "memory");
+          if (c[2 * NQ] >= total) { n = -1; break; }
+          // later stages first (they finish macroblocks others wait for); a FULL batch beats a partial one
+          int best = -1, best_avail = 0;
 #pragma unroll
-        for (int kk = NQ - 1; kk >= 0; kk--) {
-          const int avail = c[NQ + kk] - c[kk];
-          if (avail >= ENC_WPC && best_avail < ENC_WPC) { best = kk; best_avail = avail; }
-          else if (best_avail < ENC_WPC && avail > best_avail) { best = kk; best_avail = avail; }
-        }
-        if (best >= 0) {
-          const int cap = ((ENC_FREE_STAGES >> (best + 1)) & 1) ? ENC_WPC * ENC_FREE_QUOTA : ENC_WPC;
-          int tail = 0;
-#pragma unroll
-          for (int kk = 0; kk < NQ; kk++) if (kk == best) { h = c[kk]; tail = c[NQ + kk]; }
-          bool got = false;
-          for (;;) {                       // a lost race returns the new head: claim from there instead of looking at every list again
-            n = min(cap, tail - h);
-            if (n <= 0) break;
-            const int old = atomicCAS(q.ctl + best, h, h + n);
-            if (old == h) { got = true; break; }
-            n_fail++;
-            h = old;
-            if (legacy_claim) break;
+          for (int kk = NQ - 1; kk >= 0; kk--) {
+            const int avail = c[NQ + kk] - c[kk];
+            if (avail >= ENC_WPC && best_avail < ENC_WPC) { best = kk; best_avail = avail; }
+            else if (best_avail < ENC_WPC && avail > best_avail) { best = kk; best_avail = avail; }
           }
-          if (got) { k = best; break; }
-          continue;
+          const bool full = best_avail >= ENC_WPC;
+          const bool take = best >= 0 && (all_done || (!legacy_claim && full && (fin > 0 || best_avail >= 2 * ENC_WPC)));
+          if (take) {
+            int tail = 0;
+#pragma unroll
+            for (int kk = 0; kk < NQ; kk++) if (kk == best) { h = c[kk]; tail = c[NQ + kk]; }
+            bool got = false;
+            for (;;) {                     // a lost race returns the new head: claim from there instead of looking at every list again
+              n = min(ENC_WPC, tail - h);
+              if (n <= 0 || (n < ENC_WPC && !all_done)) break;
+              const int old = atomicCAS(ctl_head(q, best), h, h + n);
+              if (old == h) { got = true; break; }
+              n_fail++;
+              h = old;
+            }
+            if (got) { k = best; break; }
+            __nanosleep(100 + 40 * (blockIdx.x & 7));        // lost the batch to another CTA: do not hammer the list's line
+            continue;
+          }
+          n_idle++;
+          __nanosleep(all_done ? 100 : fin > 0 ? 400 : 1500);
         }
-        n_idle++;
-        __nanosleep(100);
+        s_slot[p].k = k; s_slot[p].base = h; s_slot[p].n = n;
+        s_fin[p] = 0;
+        if (stats) {
+          if (exposed) atomicAdd(&g_batch_stats[NQ][2], (unsigned long long)(clock64() - t_exposed));   // what the workers waited for the claim
+          atomicAdd(&g_batch_stats[NQ][0], n_poll + (n_fail << 32));        // low word: looks, high word: failed claims
+          atomicAdd(&g_batch_stats[NQ][1], n_idle);
+        }
       }
-      s_k = k; s_base = h; s_n = n; s_next = 0;
-      if (stats) {
-        t_batch = clock64();
-        atomicAdd(&g_batch_stats[NQ][2], (unsigned long long)(t_batch - t_wait));
-        atomicAdd(&g_batch_stats[NQ][0], n_poll + (n_fail << 32));        // low word: polls, high word: failed claims
-        atomicAdd(&g_batch_stats[NQ][1], n_idle);
-      }
+      __syncwarp();
+      enc_cta_barrier();                   // slot p is published; the workers have finished the batch of slot p ^ 1
+      run_n = s_slot[p].n;
+      if (run_n < 0) break;
+      p ^= 1;
     }
-    __syncthreads();
-    const int k = s_k, base = s_base, n = s_n;
-    if (n < 0) break;
-    int done_here = 0;
-    if ((ENC_FREE_STAGES >> (k + 1)) & 1) {
-      for (;;) {
-        int id = -1;
-        if (lane == 0) {
-          const int i = atomicAdd(&s_next, 1);
-          if (i < n) while ((id = ld_volatile(q.queue + (size_t)k * total + base + i)) < 0) {}
-        }
-        id = __shfl_sync(MBK_FULL, id, 0);
-        if (id < 0) break;
-        run_task(sf, q, s, id, k + 1, mb_w, mb_h, total, body);
-        done_here++;
+    return;
+  }
+  // ---- workers ----
+  int p = 0, prev_k = -1, prev_n = 0;
+  long long t_prev = 0;
+  for (;;) {
+    enc_cta_barrier();
+    const int k = s_slot[p].k, base = s_slot[p].base, n = s_slot[p].n;
+    if (stats && threadIdx.x == 0) {
+      const long long t = clock64();
+      if (prev_k >= 0) {
+        const unsigned long long dt = (unsigned long long)(t - t_prev);     // barrier to barrier: the batch plus whatever the claim left exposed
+        atomicAdd(&g_batch_stats[prev_k][0], 1ull);
+        atomicAdd(&g_batch_stats[prev_k][1], (unsigned long long)prev_n);
+        atomicAdd(&g_batch_stats[prev_k][2], dt);
+        atomicAdd(&g_fill_stats[prev_k][min(prev_n, ENC_WPC)][0], 1ull);
+        atomicAdd(&g_fill_stats[prev_k][min(prev_n, ENC_WPC)][1], dt);
       }
-    } else if (warp < n) {
+      t_prev = t; prev_k = k; prev_n = n;
+    }
+    if (n < 0) break;
+    if (warp < n) {
       int id = 0;
       if (lane == 0) while ((id = ld_volatile(q.queue + (size_t)k * total + base + warp)) < 0) {}
       id = __shfl_sync(MBK_FULL, id, 0);
       run_task(sf, q, s, id, k + 1, mb_w, mb_h, total, body);
-      done_here = 1;
+      if (lane == 0) atomicAdd(&s_fin[p], 1);
     }
-    if (stats && lane == 0 && done_here) atomicAdd(&g_batch_stats[k][1], (unsigned long long)done_here);
-    __syncthreads();
-    if (stats && threadIdx.x == 0) {
-      atomicAdd(&g_batch_stats[k][0], 1ull);
-      const unsigned long long dt = (unsigned long long)(clock64() - t_batch);
-      atomicAdd(&g_batch_stats[k][2], dt);
-      atomicAdd(&g_fill_stats[k][min(n, ENC_WPC)][0], 1ull);
-      atomicAdd(&g_fill_stats[k][min(n, ENC_WPC)][1], dt);
-    }
+    p ^= 1;
   }
 }
 
@@ -337,9 +357,9 @@ __global__ void k_esched_init(EncSched q, const StreamFrame* __restrict__ sf, in
       if (sf[s].p.is_idr) q.queue[(size_t)(MBS_I - 1) * total + ni++] = s * n_mb;
       else q.queue[(size_t)(MBS_A - 1) * total + na++] = s * n_mb;
     }
-    for (int k = 0; k < 2 * NQ + 1; k++) q.ctl[k] = 0;
-    q.ctl[NQ + MBS_A - 1] = na;
-    q.ctl[NQ + MBS_I - 1] = ni;
+    for (int k = 0; k < kCtlInts; k++) q.ctl[k] = 0;
+    *ctl_tail(q, MBS_A - 1) = na;
+    *ctl_tail(q, MBS_I - 1) = ni;
   }
 }
 
@@ -364,22 +384,23 @@ extern "C" int b2h264_debug_phase_stats(unsigned long long* out32, int reset) {
 #define ENC_MIN_CTAS 1
 #endif
 // dynamic shared memory of the macroblock kernels: ENC_WPC scratches from a 128-byte aligned base (+128 bytes of slack)
-constexpr size_t kScratchSmem = sizeof(MbScratch) * ENC_WPC + 128;
+constexpr size_t kScratchSmem = sizeof(MbScratch) * DEC_WPC + 128;          // DEC_WPC >= ENC_WPC
+static_assert(DEC_WPC >= ENC_WPC, "one scratch area size for both kernels");
 __device__ __forceinline__ MbScratch& my_scratch(uint8_t* smem) {
   const uintptr_t a = (reinterpret_cast<uintptr_t>(smem) + 127) & ~uintptr_t(127);
-  return reinterpret_cast<MbScratch*>(a)[threadIdx.x >> 5];
+  return reinterpret_cast<MbScratch*>(a)[threadIdx.x >> 5];      // (the encode kernel's scheduler warp gets one it never touches)
 }
 
 // tm_ref: reference luma planes of all streams (x, y from the padded origin, z = stream); stage B stages its
 // search window out of it with one bulk tensor copy per macroblock (enc_inter.cuh: win_issue / win_wait)
-__global__ void __launch_bounds__(32 * ENC_WPC, ENC_MIN_CTAS) k_encode_mbs(const StreamFrame* __restrict__ sf, int n_streams, EncSched q, int stats,
+__global__ void __launch_bounds__(kEncThreads, ENC_MIN_CTAS) k_encode_mbs(const StreamFrame* __restrict__ sf, int n_streams, EncSched q, int stats,
                                                                           const __grid_constant__ CUtensorMap tm_ref, const void* tm_global,
                                                                           int win_mode /* 0 none, 1 TMA (descriptor = kernel parameter), 2 warp loads, 3 TMA (descriptor in global memory) */) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ WinBar s_wbar[ENC_WPC];
   MbScratch& s = my_scratch(smem);
-  WinBar* wb = &s_wbar[threadIdx.x >> 5];
-  if ((threadIdx.x & 31) == 0) {
+  WinBar* wb = &s_wbar[min((int)(threadIdx.x >> 5), ENC_WPC - 1)];
+  if ((threadIdx.x & 31) == 0 && threadIdx.x < 32 * ENC_WPC) {
     wb->phase = 0;
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&wb->bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -442,7 +463,7 @@ __global__ void __launch_bounds__(32 * DBK_WPC, 6) k_deblock_rows(const StreamFr
 // ---- decoder construct path (groundwork of the next SURVEY row: dec_mb.cuh) ------------------------------------------------
 // One warp reconstructs one macroblock from its parsed record (h264_parse.h); the macroblocks of all streams are
 // scheduled by the same dependency rule as the encoder (left + top-right done), with the simple per-warp ready list.
-__global__ void __launch_bounds__(32 * ENC_WPC) k_decode_mbs(const StreamFrame* __restrict__ sf, int n_streams, Sched q,
+__global__ void __launch_bounds__(32 * DEC_WPC) k_decode_mbs(const StreamFrame* __restrict__ sf, int n_streams, Sched q,
                                                             const MbOut* __restrict__ recs, const DecMbAux* __restrict__ aux) {
   extern __shared__ __align__(128) uint8_t smem[];
   MbScratch& s = my_scratch(smem);
@@ -507,7 +528,7 @@ int enc_upload_deblock_tables() {
 // device ordinal under a lock (encoders / decoders on several devices and threads of one process).
 #include <mutex>
 template <class K>
-static int grid_blocks_for(K kernel, int* cache /*[64]*/) {
+static int grid_blocks_for(K kernel, int threads, int* cache /*[64]*/) {
   static std::mutex mu;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -517,22 +538,23 @@ static int grid_blocks_for(K kernel, int* cache /*[64]*/) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScratchSmem);
   int sms = 0, per_sm = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 32 * ENC_WPC, kScratchSmem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, kScratchSmem);
   if (per_sm < 1) per_sm = 1;
   return cache[dev] = sms * per_sm;
 }
 static int enc_grid_blocks() {
   static int cache[64];
-  return grid_blocks_for(k_encode_mbs, cache);
+  return grid_blocks_for(k_encode_mbs, kEncThreads, cache);
 }
 static int dec_grid_blocks() {
   static int cache[64];
-  return grid_blocks_for(k_decode_mbs, cache);
+  return grid_blocks_for(k_decode_mbs, 32 * DEC_WPC, cache);
 }
 
-// scheduler workspace layout (ints): [0..3] head/tail of the deblock list, [8..8+2NQ] encode list heads/tails/finished;
-// then dep[2][total] (encode, deblock); then queue[1 + NQ][total] (deblock list, encode lists)
-size_t enc_sched_ints(int n_streams, int n_mb) { return 32 + (size_t)(3 + NQ) * n_streams * n_mb; }
+// scheduler workspace layout (ints): [0..3] head/tail of the deblock list; from 32: dep[2][total] (encode, deblock), then
+// queue[1 + NQ][total] (deblock list, encode lists); then, 128-byte aligned, the encode lists' control lines (kCtlInts)
+static size_t enc_ctl_offset(size_t total) { return (32 + (3 + NQ) * total + 31) / 32 * 32; }       // 128-byte aligned, behind the lists
+size_t enc_sched_ints(int n_streams, int n_mb) { return enc_ctl_offset((size_t)n_streams * n_mb) + kCtlInts; }
 size_t enc_stash_bytes(int n_streams, int mb_h) { return (size_t)n_streams * mb_h * kStashU4 * sizeof(uint4); }
 
 static Sched make_sched(int* ws, int which, int total) {
@@ -545,7 +567,7 @@ static Sched make_sched(int* ws, int which, int total) {
 }
 static EncSched make_esched(int* ws, int total, void* stash) {
   EncSched q;
-  q.ctl = ws + 8;
+  q.ctl = ws + enc_ctl_offset((size_t)total);
   q.dep = ws + 32;
   q.queue = ws + 32 + (size_t)3 * total;
   q.stash = reinterpret_cast<uint4*>(stash);
@@ -605,7 +627,7 @@ int enc_launch_frame(const StreamFrame* d_sf, const uint8_t* const* d_src, int n
   if ((win_mode == 1 || win_mode == 3) && tmap_ref == nullptr) win_mode = 2;
   if (win_mode == 3 && d_tmap == nullptr) win_mode = 2;
   if (win_mode == 1) memcpy(&tm, tmap_ref, sizeof(tm));
-  k_encode_mbs<<<blocks, 32 * ENC_WPC, kScratchSmem, st>>>(d_sf, n_streams, qe, stats, tm, d_tmap, win_mode);
+  k_encode_mbs<<<blocks, kEncThreads, kScratchSmem, st>>>(d_sf, n_streams, qe, stats, tm, d_tmap, win_mode);
   if ((rc = b2h264_launched())) return rc;
   return 0;
 }
@@ -641,8 +663,8 @@ int dec_launch_frame(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h,
   const Sched qc = make_dec_sched(d_ws, 0, total), qd = make_dec_sched(d_ws, 1, total);
   k_sched_init<<<(n_streams + 127) / 128, 128, 0, st>>>(qc, n_streams, mb_w * mb_h);
   k_sched_init<<<(n_streams + 127) / 128, 128, 0, st>>>(qd, n_streams, mb_w * mb_h);
-  const int need = (total + ENC_WPC - 1) / ENC_WPC;
-  k_decode_mbs<<<blocks_per_launch < need ? blocks_per_launch : need, 32 * ENC_WPC, kScratchSmem, st>>>(d_sf, n_streams, qc, d_recs, d_aux);
+  const int need = (total + DEC_WPC - 1) / DEC_WPC;
+  k_decode_mbs<<<blocks_per_launch < need ? blocks_per_launch : need, 32 * DEC_WPC, kScratchSmem, st>>>(d_sf, n_streams, qc, d_recs, d_aux);
   if ((rc = b2h264_launched())) return rc;
   if (deblock) {
     if ((rc = launch_deblock_rows(d_sf, n_streams, mb_h, d_ws + 8 + (size_t)total, d_ws + 2, st))) return rc;

@@ -276,7 +276,7 @@ MBK_STAGE void mb_load_all(const MbCtx& c, MbScratch& s) {
 }
 
 // reconstructed tile -> picture
-MBK_FN void mb_store_recon(const MbCtx& c, MbScratch& s) {
+MBK_STAGE void mb_store_recon(const MbCtx& c, MbScratch& s) {
   uint8_t* ry = c.f.rec[0] + (size_t)(c.mby * 16) * c.p.rec_stride_y + c.mbx * 16;
   for (int i = lane_id(); i < 64; i += MBK_WS) {
     const int r = i >> 2, c4 = (i & 3) << 2;

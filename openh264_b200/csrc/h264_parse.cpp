@@ -10,7 +10,7 @@
 
 namespace b2h264 {
 
-int g_reject_line = 0;      // source line of the last rejection (diagnostics: why a stream is outside the supported class)
+thread_local int g_reject_line = 0;      // source line of the last rejection (diagnostics: why a stream is outside the supported class)
 
 namespace {
 #define PARSE_UNSUPPORTED (g_reject_line = __LINE__, b2h264::PARSE_UNSUPPORTED)
@@ -270,15 +270,16 @@ inline int nc_of(int a, int b) {
 
 // inverse of the me(v) mapping of coded_block_pattern (Table 9-4): built from the writer's table
 int cbp_from_code(int code, bool intra) {
-  static uint8_t inv[2][48];
-  static bool built = false;
-  if (!built) {
+  struct Inv { uint8_t t[2][48]; };
+  static const Inv inv_s = [] {                      // thread-safe one-time build (streams are parsed on several threads)
+    Inv v;
     for (int t = 0; t < 2; t++) {
       const uint8_t* fwd = cbp_me_table(t != 0);
-      for (int cbp = 0; cbp < 48; cbp++) inv[t][fwd[cbp]] = (uint8_t)cbp;
+      for (int cbp = 0; cbp < 48; cbp++) v.t[t][fwd[cbp]] = (uint8_t)cbp;
     }
-    built = true;
-  }
+    return v;
+  }();
+  const uint8_t (*inv)[48] = inv_s.t;
   if (code < 0 || code > 47) return -1;
   return inv[intra ? 1 : 0][code];
 }

@@ -42,7 +42,12 @@ MBK_HD const uint8_t* me_block(const MeIn& in, int mx, int my, int w, int h, int
   return in.ref + my * in.ref_stride + mx;
 }
 
-MBK_FN void warp_me_search(const MeIn& in, MeOut& out) {
+#ifdef B2H264_ME_CALL                      // profiling variant: the search as a real call
+#define MBK_ME MBK_FN
+#else
+#define MBK_ME MBK_STAGE                // one call site per kernel (me_partition / k_me_search)
+#endif
+MBK_ME void warp_me_search(const MeIn& in, MeOut& out) {
   const int lw = blk_lw(in.blk), lh = blk_lh(in.blk), w = 1 << lw, h = 1 << lh;
   const int px = in.mvp_x, py = in.mvp_y;
   int rs;

@@ -8,7 +8,7 @@ namespace mbk {
 
 // SAD of a (1<<lw) x (1<<lh) block: the block is cut into 4-pixel groups, lane g takes groups
 // g, g+32, ...; each group is one __vsadu4 on packed bytes; warp total by REDUX.
-MBK_FN int warp_sad(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh) {
+MBK_HD int warp_sad(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh) {
   const int lg = lw - 2;                    // log2(groups per row)
   const int ngroups = 1 << (lg + lh);
   int s = 0;
@@ -20,7 +20,7 @@ MBK_FN int warp_sad(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, 
 }
 
 // SADs against b shifted up, down, left, right by one pixel (pfSample4Sad order), cur read once.
-MBK_FN void warp_sad_four(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh,
+MBK_STAGE void warp_sad_four(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh,
                                               int out[4]) {
   const int lg = lw - 2;
   const int ngroups = 1 << (lg + lh);
@@ -79,7 +79,7 @@ MBK_HD int satd4x4_avg_thread(const uint8_t* a, int sa, const uint8_t* p0, const
   }
   return (sum + 1) >> 1;
 }
-MBK_FN int warp_satd_avg(const uint8_t* a, int sa, const uint8_t* p0, const uint8_t* p1, int sp, int lw, int lh) {
+MBK_STAGE int warp_satd_avg(const uint8_t* a, int sa, const uint8_t* p0, const uint8_t* p1, int sp, int lw, int lh) {
   const int lbx = lw - 2;
   const int nblk = 1 << (lbx + lh - 2);
   int s = 0;

@@ -502,5 +502,5 @@ static int random_pictures(unsigned seed, int pictures, bool decodable, uint8_t*
   return 0;
 }
 
-namespace b2h264 { extern int g_reject_line; }
+namespace b2h264 { extern thread_local int g_reject_line; }
 extern "C" int emu_last_reject_line() { return b2h264::g_reject_line; }

@@ -30,6 +30,10 @@ MBK_HD int median3(int a, int b, int c) {
 // ---- neighbour caches (FillNeighborCacheInterWithoutBGD, md.cpp:132) ----------------------------------
 // ref_ids: the decoder keeps, per 4x4 block of an inter macroblock, the picture slot of its reference in MbInfo::i4_mode
 // (unused for inter macroblocks otherwise); the encoder has one reference picture (index 0 everywhere)
+// availability bit of neighbour slot k (0 TL, 1 T, 2 TR, 3 L) without a lane-indexed table (that would live in local memory)
+MBK_HD int nb_slot_bit(int k) {
+  return (int)((((uint32_t)NB_TOPLEFT) | ((uint32_t)NB_TOP << 8) | ((uint32_t)NB_TOPRIGHT << 16) | ((uint32_t)NB_LEFT << 24)) >> (8 * k)) & 0xff;
+}
 MBK_FN void fill_inter_cache(const MbCtx& c, MbScratch& s, bool ref_ids = false) {
   // one lane per cache cell: cells 0..5 = top-left, top x4, top-right; cells 6,12,18,24 = left column
   for (int ci = lane_id(); ci < 30; ci += MBK_WS) {
@@ -41,8 +45,7 @@ MBK_FN void fill_inter_cache(const MbCtx& c, MbScratch& s, bool ref_ids = false)
     int16_t mx = 0, my = 0;
     int8_t ref = 0;
     if (k >= 0) {
-      const int bits[4] = {NB_TOPLEFT, NB_TOP, NB_TOPRIGHT, NB_LEFT};
-      const bool avail = (c.nb & bits[k]) != 0;
+      const bool avail = (c.nb & nb_slot_bit(k)) != 0;
       const MbInfo* n = &s.nbi[k];
       if (avail && MBT_IS_INTER(n->mb_type)) { mx = n->mv[blk][0]; my = n->mv[blk][1]; if (ref_ids) ref = n->i4_mode[blk]; }
       else ref = avail ? REF_NOT_IN_LIST : REF_NOT_AVAIL;
@@ -52,8 +55,7 @@ MBK_FN void fill_inter_cache(const MbCtx& c, MbScratch& s, bool ref_ids = false)
     s.mvc[ci][0] = mx; s.mvc[ci][1] = my; s.refc[ci] = ref;
   }
   for (int k = lane_id(); k < 4; k += MBK_WS) {
-    const int bits[4] = {NB_TOPLEFT, NB_TOP, NB_TOPRIGHT, NB_LEFT};
-    const bool avail = (c.nb & bits[k]) != 0;
+    const bool avail = (c.nb & nb_slot_bit(k)) != 0;
     const MbInfo* n = &s.nbi[k];
     const bool inter = avail && MBT_IS_INTER(n->mb_type);
     const bool skip = inter && n->mb_type == MBT_PSKIP;
@@ -270,7 +272,7 @@ MBK_STAGE SkipResult pskip_enc(const MbCtx& c, MbScratch& s, int sad_pred_skip, 
       r.cost_luma = sad_y;
       if (lane_id() == 0) c.f.sad_cost[c.mby * c.p.mb_w + c.mbx] = sad_y;
     } else {
-      r.cost_luma = warp_satd(s.cur_y, 16, py, 16, 4, 4);
+      r.cost_luma = warp_satd_inl(s.cur_y, 16, py, 16, 4, 4);
     }
     phase_mark(s, 16);
     r.cost_skip = sad_mb;
@@ -738,7 +740,7 @@ MBK_STAGE int inter_stage_b(const MbCtx& c, MbScratch& s) {
     {
       // intra check (WelsMdFirstIntraMode :1829)
       int bb;
-      const int cost16 = md_i16x16(c, s, &bb);
+      const int cost16 = md_i16x16_inl(c, s, &bb);
       phase_mark(s, 4);
       if (cost16 < cost_luma) {
         st_save(s, is_skip ? 1 : 0, cost_luma, cost_skip_mb, p16_mvx, p16_mvy, final_type);

@@ -172,7 +172,13 @@ __device__ __forceinline__ void esched_push(const EncSched& q, int total, int st
 
 // optional batch statistics (debug, B2H264_ENC_STATS): per ready list [batches, tasks, batch cycles]; [NQ] = leader wait cycles
 __device__ unsigned long long g_batch_stats[NQ + 1][3];
+__device__ unsigned long long g_task_wall[NQ][2];                    // per list: cycles from the batch barrier to the end of run_task, tasks
 __device__ unsigned long long g_fill_stats[NQ][ENC_WPC + 1][2];      // per list and batch fill: [batches, cycles]
+extern "C" int b2h264_debug_task_wall(unsigned long long* out, int reset) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_task_wall, sizeof(g_task_wall));
+  if (e == cudaSuccess && reset) { unsigned long long z[NQ][2] = {}; e = cudaMemcpyToSymbol(g_task_wall, z, sizeof(z)); }
+  return (int)e;
+}
 extern "C" int b2h264_debug_fill_stats(unsigned long long* out, int* n_lists, int* wpc, int reset) {
   *n_lists = NQ; *wpc = ENC_WPC;
   cudaError_t e = cudaMemcpyFromSymbol(out, g_fill_stats, sizeof(g_fill_stats));
@@ -337,11 +343,13 @@ __device__ __forceinline__ void run_stages(const StreamFrame* sf, int n_streams,
     }
     if (n < 0) break;
     if (warp < n) {
+      const long long t_task = stats ? clock64() : 0;
       int id = 0;
       if (lane == 0) while ((id = ld_volatile(q.queue + (size_t)k * total + base + warp)) < 0) {}
       id = __shfl_sync(MBK_FULL, id, 0);
       run_task(sf, q, s, id, k + 1, mb_w, mb_h, total, body);
       if (lane == 0) atomicAdd(&s_fin[p], 1);
+      if (stats && lane == 0) { atomicAdd(&g_task_wall[k][0], (unsigned long long)(clock64() - t_task)); atomicAdd(&g_task_wall[k][1], 1ull); }
     }
     p ^= 1;
   }

@@ -202,21 +202,23 @@ MBK_HD void mb_load_borders(const MbCtx& c, MbScratch& s) {
 // (profiles/r01_phase_cycles.txt: 12k cycles/MB before).
 MBK_STAGE void mb_load_all(const MbCtx& c, MbScratch& s) {
   const int mbw = c.p.mb_w, idx = c.mby * mbw + c.mbx, l = lane_id();
-  const int offs[4] = {-mbw - 1, -mbw, -mbw + 1, -1};
-  const int bits[4] = {NB_TOPLEFT, NB_TOP, NB_TOPRIGHT, NB_LEFT};
   constexpr int kW = (int)(sizeof(MbInfo) / 4);
 #ifdef __CUDA_ARCH__
+  // neighbour k = 0..3: top-left, top, top-right, left.  Computed, not looked up: a lane-indexed local array lives in local memory
+  // (12 dependent LDL per macroblock in the round-2 profile of this routine)
+  auto nb_off = [&](int k) { return k == 3 ? -1 : -mbw - 1 + k; };
+  auto nb_bit = [](int k) { return (int)((((uint32_t)NB_TOPLEFT) | ((uint32_t)NB_TOP << 8) | ((uint32_t)NB_TOPRIGHT << 16) | ((uint32_t)NB_LEFT << 24)) >> (8 * k)) & 0xff; };
   // ---- issue ----
   uint32_t nbw[4];
 #pragma unroll
   for (int r = 0; r < 4; r++) {
     const int i = l + 32 * r, k = i / kW, w = i - k * kW;
-    nbw[r] = (i < 4 * kW && (c.nb & bits[k & 3])) ? ld_cg_u32(reinterpret_cast<const uint32_t*>(c.f.mbi + idx + offs[k & 3]) + w) : 0u;
+    nbw[r] = (i < 4 * kW && (c.nb & nb_bit(k & 3))) ? ld_cg_u32(reinterpret_cast<const uint32_t*>(c.f.mbi + idx + nb_off(k & 3)) + w) : 0u;
   }
   uint32_t hist = 0;
-  if (l < 8 && (c.nb & bits[l & 3]))
-    hist = l < 4 ? ld_cg_u32(reinterpret_cast<const uint32_t*>(c.f.sad_cost + idx + offs[l & 3]))
-                 : ld_cg_u32(reinterpret_cast<const uint32_t*>(&c.f.rec_info[idx + offs[l & 3]].skip_sad));
+  if (l < 8 && (c.nb & nb_bit(l & 3)))
+    hist = l < 4 ? ld_cg_u32(reinterpret_cast<const uint32_t*>(c.f.sad_cost + idx + nb_off(l & 3)))
+                 : ld_cg_u32(reinterpret_cast<const uint32_t*>(&c.f.rec_info[idx + nb_off(l & 3)].skip_sad));
   const uint8_t* cy = c.f.cur[0] + (size_t)(c.mby * 16) * c.p.cur_stride_y + c.mbx * 16;
   const uint32_t cy0 = *reinterpret_cast<const uint32_t*>(cy + (size_t)(l >> 2) * c.p.cur_stride_y + ((l & 3) << 2));
   const uint32_t cy1 = *reinterpret_cast<const uint32_t*>(cy + (size_t)(8 + (l >> 2)) * c.p.cur_stride_y + ((l & 3) << 2));
@@ -268,7 +270,7 @@ MBK_STAGE void mb_load_all(const MbCtx& c, MbScratch& s) {
   else *tile_c(t.v, -1, l - 24) = lb;
   warp_sync();
 #else
-  (void)offs; (void)bits; (void)idx; (void)l;
+  (void)idx; (void)l;
   mb_load_neighbors(c, s);
   mb_load_cur(c, s);
   mb_load_borders(c, s);
@@ -295,23 +297,28 @@ MBK_STAGE void mb_store_recon(const MbCtx& c, MbScratch& s) {
 
 // ---- I16x16 mode decision (WelsMdI16x16, svc_base_layer_md.cpp:365; pfMdCost = SATD) -------------
 // returns the cost; s.out.i16_mode = raw mode id; the winning prediction is in s.pred_y[*best_buf]
-MBK_FN int md_i16x16(const MbCtx& c, MbScratch& s, int* best_buf) {
-  int modes[4];
+MBK_HD int md_i16x16_inl(const MbCtx& c, MbScratch& s, int* best_buf) {
+  int modes[4] = {0, 0, 0, 0};
   const int n = i16_modes(c.nb & 7, modes);
+  const uint32_t packed = (uint32_t)modes[0] | ((uint32_t)modes[1] << 8) | ((uint32_t)modes[2] << 16) | ((uint32_t)modes[3] << 24);   // no indexed local array
   int best = 0x7fffffff, best_mode = modes[0], bb = 1;
   const uint8_t* org = tile_y(s.tile, 0, 0);
+  MBK_NO_UNROLL
   for (int i = 0; i < n; i++) {
+    const int mode = (int)((packed >> (8 * i)) & 0xffu);
     uint8_t* dst = s.pred_y[1 - bb];
-    pred_i16(dst, org, TY_PITCH, modes[i]);
+    pred_i16(dst, org, TY_PITCH, mode);
     const int cost = (c.p.fast_mode ? warp_sad(dst, 16, s.cur_y, 16, 4, 4) : warp_satd(dst, 16, s.cur_y, 16, 4, 4)) +
-                     c.lambda * ue_bits(map_i16(modes[i]));        // pfMdCost: SAD in LOW_COMPLEXITY (encoder_ext.cpp:2618)
-    if (cost < best) { best = cost; best_mode = modes[i]; bb = 1 - bb; }
+                     c.lambda * ue_bits(map_i16(mode));            // pfMdCost: SAD in LOW_COMPLEXITY (encoder_ext.cpp:2618)
+    if (cost < best) { best = cost; best_mode = mode; bb = 1 - bb; }
     warp_sync();
   }
   s.out.i16_mode = (uint8_t)map_i16(best_mode);
   *best_buf = bb;
   return best;
 }
+// the shared (real-call) copy of the intra paths; stage B / Bs of a P picture, which runs it for every non-skipped macroblock, inlines it
+MBK_FN int md_i16x16(const MbCtx& c, MbScratch& s, int* best_buf) { return md_i16x16_inl(c, s, best_buf); }
 
 // ---- intra chroma mode decision (WelsMdIntraChroma, :867) ---------------------------------------
 MBK_FN int md_chroma(const MbCtx& c, MbScratch& s, int* best_buf) {

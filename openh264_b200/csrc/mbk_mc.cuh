@@ -37,7 +37,7 @@ MBK_HD int luma_qpel_sample(const uint8_t* p, int s, int fx, int fy) {
 }
 
 // w x h luma prediction; src already offset by the integer part of the MV (as McLuma_c expects)
-MBK_FN void warp_mc_luma(const uint8_t* src, int ss, uint8_t* dst, int ds, int mvx, int mvy, int w,
+MBK_STAGE void warp_mc_luma(const uint8_t* src, int ss, uint8_t* dst, int ds, int mvx, int mvy, int w,
                                              int h) {
   const int fx = mvx & 3, fy = mvy & 3;
   const int sh = 31 - clz32((uint32_t)w);
@@ -48,7 +48,8 @@ MBK_FN void warp_mc_luma(const uint8_t* src, int ss, uint8_t* dst, int ds, int m
       const int y = g >> gsh, x = (g & ((1 << gsh) - 1)) << 2;
       const uint32_t v = ld4u(src + y * ss + x);
       uint8_t* d = dst + y * ds + x;
-      d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24);
+      if (((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)ds) & 3) == 0) *reinterpret_cast<uint32_t*>(d) = v;     // every caller's case
+      else { d[0] = (uint8_t)v; d[1] = (uint8_t)(v >> 8); d[2] = (uint8_t)(v >> 16); d[3] = (uint8_t)(v >> 24); }
     }
     return;
   }

@@ -92,7 +92,7 @@ MBK_STAGE int warp_satd_avg(const uint8_t* a, int sa, const uint8_t* p0, const u
 }
 
 // SATD of a block: one lane per 4x4 sub-block (16 lanes busy for 16x16), warp total by REDUX.
-MBK_FN int warp_satd(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh) {
+MBK_HD int warp_satd_inl(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh) {
   const int lbx = lw - 2;                    // log2(4x4 blocks per row)
   const int nblk = 1 << (lbx + lh - 2);
   int s = 0;
@@ -102,5 +102,7 @@ MBK_FN int warp_satd(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw,
   }
   return warp_sum(s);
 }
+// the shared (real-call) copy; the skip test of stage A, which every macroblock runs, uses the inlined form
+MBK_FN int warp_satd(const uint8_t* a, int sa, const uint8_t* b, int sb, int lw, int lh) { return warp_satd_inl(a, sa, b, sb, lw, lh); }
 
 }  // namespace mbk

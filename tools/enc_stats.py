@@ -26,6 +26,9 @@ for f in range(6):
         fs=fs.reshape(-1)[:nl.value*(wp.value+1)*2].reshape(nl.value,wp.value+1,2)
         for k in range(nl.value):
             if fs[k,:,0].sum(): print('   fill histogram', names[k+1], {n:(int(fs[k,n,0]), int(fs[k,n,1]//max(1,fs[k,n,0]))) for n in range(1,wp.value+1) if fs[k,n,0]})
+    if hasattr(L,'b2h264_debug_task_wall'):
+        tw=np.zeros((5,2),np.uint64); L.b2h264_debug_task_wall.argtypes=[C.c_void_p,C.c_int]; L.b2h264_debug_task_wall(tw.ctypes.data,1)
+        print('   task wall (barrier -> end of run_task) avg cycles:', {names[k+1]: int(tw[k][0]//max(1,tw[k][1])) for k in range(5) if tw[k][1]})
     busy=float(sum(st[0::2])); n=float(sum(st[1::2]))
     print('   avg cyc/MB %.0f  utilisation of 1184 warps @1.9GHz: %.2f'%(busy/n, busy/(1184*t[0]*1900.0)))
     print('frame',f,'kernel us',round(t[0]),'dbk',round(t[1]), {names[i]:(int(st[2*i+1]), int(st[2*i]//max(1,st[2*i+1]))) for i in range(7) if st[2*i+1]})

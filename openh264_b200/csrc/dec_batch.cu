@@ -40,7 +40,11 @@ struct b2h264_dec {
   uint8_t* d_pic = nullptr;               // S x slots padded pictures: picture (s, slot) at (s * slots + slot) * pic_bytes
   MbInfo* d_mbi = nullptr;
   MbOut* d_recs = nullptr;
-  MbOut* h_recs = nullptr;                // pinned
+  MbOut* h_recs = nullptr;                // pinned: COMPACT records (pack_records_compact), one worst-case slot per stream
+  uint8_t* d_pack = nullptr;              // device copy of the compact records (same slots)
+  int32_t* h_idx = nullptr;               // pinned: per macroblock offset of its compact record or -1 - qp (skipped)
+  int32_t* d_idx = nullptr;
+  std::vector<int> units;                 // 32-byte units packed per active stream
   DecMbAux* d_aux = nullptr;
   DecMbAux* h_aux = nullptr;              // pinned
   StreamFrame* d_sf = nullptr;
@@ -85,6 +89,10 @@ int b2h264_dec_create(const b2h264_dec_config* cfg, b2h264_dec** out) {
   CK(cudaMemset(d->d_mbi, 0, S * d->n_mb * sizeof(MbInfo)));
   CK(cudaMalloc(&d->d_recs, S * d->n_mb * sizeof(MbOut)));
   CK(cudaMallocHost(&d->h_recs, S * d->n_mb * sizeof(MbOut)));
+  CK(cudaMalloc(&d->d_pack, S * d->n_mb * sizeof(MbOut)));
+  CK(cudaMallocHost(&d->h_idx, S * d->n_mb * sizeof(int32_t)));
+  CK(cudaMalloc(&d->d_idx, S * d->n_mb * sizeof(int32_t)));
+  d->units.assign(d->S, 0);
   CK(cudaMalloc(&d->d_aux, S * d->n_mb * sizeof(DecMbAux)));
   CK(cudaMallocHost(&d->h_aux, S * d->n_mb * sizeof(DecMbAux)));
   CK(cudaMalloc(&d->d_sf, S * sizeof(StreamFrame)));
@@ -100,7 +108,7 @@ void b2h264_dec_destroy(b2h264_dec* d) {
   if (d->st) cudaStreamSynchronize(d->st);
   cudaFree(d->d_pic);
   cudaFree(d->d_mbi); cudaFree(d->d_recs); cudaFree(d->d_aux); cudaFreeHost(d->h_aux); cudaFree(d->d_sf); cudaFree(d->d_ws);
-  cudaFreeHost(d->h_recs); cudaFreeHost(d->h_sf);
+  cudaFreeHost(d->h_recs); cudaFreeHost(d->h_sf); cudaFree(d->d_pack); cudaFreeHost(d->h_idx); cudaFree(d->d_idx);
   if (d->st) cudaStreamDestroy(d->st);
   delete d->pool;
   delete d;
@@ -175,14 +183,18 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
   const int n = (int)d->act.size();
   if (n == 0) return 0;
   {
-    std::function<void(int)> job = [&](int i) {          // 7.3 MB of records per 1080p picture into the pinned staging area
+    std::function<void(int)> job = [&](int i) {          // compact records + index table into the stream's pinned slot
       const ParsedPicture& pic = d->parsed[d->act[i]];
-      memcpy(d->h_recs + (size_t)i * d->n_mb, pic.mbs.data(), (size_t)d->n_mb * sizeof(MbOut));
+      d->units[i] = pack_records_compact(pic.mbs.data(), d->n_mb, reinterpret_cast<uint8_t*>(d->h_recs + (size_t)i * d->n_mb), d->h_idx + (size_t)i * d->n_mb);
       memcpy(d->h_aux + (size_t)i * d->n_mb, pic.aux.data(), (size_t)d->n_mb * sizeof(DecMbAux));
     };
     d->pool->run(n, job);
   }
-  CK(cudaMemcpyAsync(d->d_recs, d->h_recs, (size_t)n * d->n_mb * sizeof(MbOut), cudaMemcpyHostToDevice, d->st));
+  for (int i = 0; i < n; i++)                            // only what was packed crosses PCIe
+    if (d->units[i] > 0)
+      CK(cudaMemcpyAsync(d->d_pack + (size_t)i * d->n_mb * sizeof(MbOut), d->h_recs + (size_t)i * d->n_mb, (size_t)d->units[i] * 32, cudaMemcpyHostToDevice, d->st));
+  CK(cudaMemcpyAsync(d->d_idx, d->h_idx, (size_t)n * d->n_mb * sizeof(int32_t), cudaMemcpyHostToDevice, d->st));
+  { const int rcu = dec_launch_unpack(d->d_pack, (size_t)d->n_mb * sizeof(MbOut), d->d_idx, d->d_recs, n, d->n_mb, d->st); if (rcu) return rcu; }
   CK(cudaMemcpyAsync(d->d_aux, d->h_aux, (size_t)n * d->n_mb * sizeof(DecMbAux), cudaMemcpyHostToDevice, d->st));
   CK(cudaMemcpyAsync(d->d_sf, d->h_sf, (size_t)n * sizeof(StreamFrame), cudaMemcpyHostToDevice, d->st));
   const int rc = dec_launch_frame(d->d_sf, n, d->mb_w, d->mb_h, d->d_ws, d->d_recs, d->d_aux, deblock, d->st);

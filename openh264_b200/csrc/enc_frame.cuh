@@ -65,7 +65,10 @@ MBK_HD int mb_run_stage(const MbCtx& c, MbScratch& s, int stage) {
   warp_sync();
   if (next == MBS_DONE) {
     phase_mark(s, 10);
-    mb_store_recon(c, s);
+    // a DECIDED skip (decided_pskip: st.is_skip) keeps its reconstruction in skip_pred; a 16x16 macroblock that turned out to be
+    // codable as P_SKIP (no residual, vector == skip vector) has it in the tile like every other coded macroblock
+    if (s.info.mb_type == MBT_PSKIP && s.st.is_skip != 0) mb_store_recon_skip(c, s);
+    else mb_store_recon(c, s);
     mb_publish(c, s);
     if (c.f.mb_bits != nullptr) {          // exact entropy-coded size of this macroblock, without emitting a bit
       const int b = mb_cavlc_bits(c, s);

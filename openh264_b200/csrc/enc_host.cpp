@@ -43,6 +43,34 @@ void StreamCtl::write_access_unit(bool idr, const MbOut* mbs, std::vector<uint8_
   write_au(idr, recs_.data(), au);
 }
 
+int pack_records_compact(const MbOut* mbs, int n, uint8_t* dst, int32_t* idx) {
+  size_t at = 0;
+  for (int i = 0; i < n; i++) {
+    const MbOut& m = mbs[i];
+    if (m.mb_type == MBT_PSKIP) { idx[i] = -1 - (int32_t)m.qp; continue; }
+    idx[i] = (int32_t)(at / 32);
+    uint8_t* head = dst + at;
+    memcpy(head, &m, offsetof(MbOut, luma));
+    memcpy(head + offsetof(MbOut, luma), m.chroma_dc, sizeof(m.chroma_dc));
+    at += 128;
+    unsigned mask = 0;
+    for (int b = 0; b < 24; b++) {
+      const bool want = m.mb_type == MBT_IPCM ? true
+                        : b < 16 ? (m.mb_type == MBT_I16x16 ? (m.cbp & 15) != 0 : ((m.cbp >> (b >> 2)) & 1) != 0) : (m.cbp >> 4) == 2;
+      if (!want) continue;
+      const int16_t* blk = b < 16 ? m.luma[b] : m.chroma_ac[b - 16];
+      bool nz = false;
+      for (int q = 0; q < 16; q++) nz |= blk[q] != 0;
+      if (!nz) continue;
+      mask |= 1u << b;
+      memcpy(dst + at, blk, 32);
+      at += 32;
+    }
+    head[5] = (uint8_t)mask; head[6] = (uint8_t)(mask >> 8); head[7] = (uint8_t)(mask >> 16);
+  }
+  return (int)(at / 32);
+}
+
 // compact records (enc_kernels.cu: k_pack_records): idx[mb] = offset in 32-byte units or -1; 128-byte head
 // (MbOut bytes [0, 112) + chroma_dc, presence mask of the 24 residual blocks in pad0) + 32 bytes per present block
 void StreamCtl::write_access_unit_packed(bool idr, const MbOut* packed, const int32_t* idx, std::vector<uint8_t>* au) {

@@ -12,6 +12,12 @@
 
 namespace b2h264 {
 
+// Host twin of k_pack_records (enc_kernels.cu): compacts n records into `dst` (worst case n * sizeof(MbOut) bytes) and fills idx[mb] =
+// offset of the macroblock's record in 32-byte units, or -1 - qp for a P_SKIP macroblock (the decoder's hand-over keeps the
+// quantiser of a skipped macroblock: deblocking needs it; the encoder's reader only tests the sign).  Returns the units written.
+// Record: 128-byte head (MbOut bytes [0, 112) + chroma_dc, presence mask of the 24 residual blocks in pad0) + 32 bytes per present block.
+int pack_records_compact(const MbOut* mbs, int n, uint8_t* dst, int32_t* idx);
+
 struct StreamCtl {
   StreamParams sp;
   float fps;

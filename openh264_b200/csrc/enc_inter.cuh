@@ -582,17 +582,14 @@ MBK_FN void rec_luma_inter(MbScratch& s, const uint8_t* pred) {
 }
 
 // ---- decided skip (WelsMdInterDecidedPskip :1954 + WelsRecPskip svc_encode_mb.cpp:315) ------------------------------
-MBK_FN void decided_pskip(const MbCtx& c, MbScratch& s) {
-  for (int i = lane_id(); i < 256; i += MBK_WS) *tile_y(s.tile, i & 15, i >> 4) = s.skip_pred[i];
-  for (int i = lane_id(); i < 64; i += MBK_WS) {
-    *tile_c(s.tile.u, i & 7, i >> 3) = s.skip_pred[256 + i];
-    *tile_c(s.tile.v, i & 7, i >> 3) = s.skip_pred[320 + i];
-  }
+// the reconstruction of a P_SKIP macroblock stays in s.skip_pred (mb_store_recon_skip writes it to the picture)
+MBK_HD void decided_pskip(const MbCtx& c, MbScratch& s) {
+  (void)c;
   if (lane_id() == 0) {
     s.info.mb_type = MBT_PSKIP;
     s.info.cbp = 0;
-    for (int i = 0; i < 24; i++) s.info.nnz[i] = 0;
   }
+  for (int i = lane_id(); i < 24; i += MBK_WS) s.info.nnz[i] = 0;
   warp_sync();
 }
 
@@ -843,14 +840,19 @@ MBK_STAGE int inter_stage_c(const MbCtx& c, MbScratch& s) {
   int cost = s.st.cost16;
   {
     {
-      s.info.mb_type = MBT_I16x16;
-      s.info.cbp = 0;
+      bool use_i4 = false;                       // warp-uniform; the staged record is written by lane 0 only
+      if (lane_id() == 0) { s.info.mb_type = MBT_I16x16; s.info.cbp = 0; }
+      warp_sync();
       fill_i4_cache(c, s);
       if (intra_try_i4x4(c, s)) {
         const int cost4 = md_enc_i4x4(c, s, cost);
-        if (cost4 < cost) { s.info.mb_type = MBT_I4x4; cost = cost4; }
+        if (cost4 < cost) { use_i4 = true; cost = cost4; if (lane_id() == 0) s.info.mb_type = MBT_I4x4; warp_sync(); }
       }
-      if (s.info.mb_type == MBT_I16x16) { s.info.cbp = 0; enc_rec_i16x16(c, s, s.pred_y[bb]); }
+      if (!use_i4) {
+    if (lane_id() == 0) s.info.cbp = 0;        // the I4x4 attempt may have set bits
+    warp_sync();
+    enc_rec_i16x16(c, s, s.pred_y[bb]);
+  }
       int cb;
       md_chroma(c, s, &cb);
       dct_chroma(s, s.pred_c[cb]);

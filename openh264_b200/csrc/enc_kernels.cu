@@ -253,6 +253,7 @@ __device__ __forceinline__ void enc_cta_barrier() { asm volatile("barrier.sync 1
 template <class Body>
 __device__ __forceinline__ void run_stages(const StreamFrame* sf, int n_streams, const EncSched q, MbScratch& s, int stats, bool legacy_claim, Body body) {
   __shared__ BatchSlot s_slot[2];
+  __shared__ int s_ids[2][ENC_WPC];        // the claimed macroblocks of slot p, read off the ready list by the scheduler warp
   __shared__ int s_fin[2];                 // workers of the batch in slot p that have finished their macroblock
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int mb_w = sf[0].p.mb_w, mb_h = sf[0].p.mb_h, n_mb = mb_w * mb_h, total = n_streams * n_mb;
@@ -316,6 +317,17 @@ __device__ __forceinline__ void run_stages(const StreamFrame* sf, int n_streams,
         }
       }
       __syncwarp();
+      {
+        // lane i fetches the i-th claimed macroblock (its producer may still be writing the entry: spin), so that the workers
+        // start from shared memory instead of each paying an L2 round trip after the barrier
+        const int kk = s_slot[p].k, nn = s_slot[p].n;
+        if (lane < nn) {
+          int id;
+          while ((id = ld_volatile(q.queue + (size_t)kk * total + s_slot[p].base + lane)) < 0) {}
+          s_ids[p][lane] = id;
+        }
+      }
+      __syncwarp();
       enc_cta_barrier();                   // slot p is published; the workers have finished the batch of slot p ^ 1
       run_n = s_slot[p].n;
       if (run_n < 0) break;
@@ -328,7 +340,7 @@ __device__ __forceinline__ void run_stages(const StreamFrame* sf, int n_streams,
   long long t_prev = 0;
   for (;;) {
     enc_cta_barrier();
-    const int k = s_slot[p].k, base = s_slot[p].base, n = s_slot[p].n;
+    const int k = s_slot[p].k, n = s_slot[p].n;
     if (stats && threadIdx.x == 0) {
       const long long t = clock64();
       if (prev_k >= 0) {
@@ -344,9 +356,7 @@ __device__ __forceinline__ void run_stages(const StreamFrame* sf, int n_streams,
     if (n < 0) break;
     if (warp < n) {
       const long long t_task = stats ? clock64() : 0;
-      int id = 0;
-      if (lane == 0) while ((id = ld_volatile(q.queue + (size_t)k * total + base + warp)) < 0) {}
-      id = __shfl_sync(MBK_FULL, id, 0);
+      const int id = s_ids[p][warp];
       run_task(sf, q, s, id, k + 1, mb_w, mb_h, total, body);
       if (lane == 0) atomicAdd(&s_fin[p], 1);
       if (stats && lane == 0) { atomicAdd(&g_task_wall[k][0], (unsigned long long)(clock64() - t_task)); atomicAdd(&g_task_wall[k][1], 1ull); }
@@ -747,6 +757,42 @@ int enc_launch_pack(const StreamFrame* d_sf, int n_streams, int n_mb, MbOut* pac
   static_assert(sizeof(MbOut) == 896 && offsetof(MbOut, luma) == 112 && offsetof(MbOut, chroma_dc) == 624 && offsetof(MbOut, chroma_ac) == 640 &&
                 offsetof(MbOut, pad0) == 5, "compact record layout");
   k_pack_records<<<n_streams, PACK_THREADS, 0, st>>>(d_sf, n_mb, reinterpret_cast<uint4*>(pack), idx, cnt);
+  return b2h264_launched();
+}
+
+// ---- decoder hand-over: compact records (host: pack_records_compact, enc_host.cpp) -> the MbOut array k_decode_mbs reads ----
+// One warp per macroblock.  idx < 0: a P_SKIP macroblock, only its header is (re)written (type, quantiser = -1 - idx); the
+// levels of such a record are never read.  Otherwise the 128-byte head goes back to its two places and each of the 24
+// residual blocks is copied or zeroed.  7.3 MB per 1080p picture used to cross PCIe; a typical P picture now sends ~0.3 MB.
+__global__ void __launch_bounds__(256) k_unpack_records(const uint4* __restrict__ pack, size_t stream_stride_u4, const int32_t* __restrict__ idx,
+                                                        MbOut* __restrict__ recs, int n_mb) {
+  const int s = blockIdx.y, lane = threadIdx.x & 31, mb = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (mb >= n_mb) return;
+  const int32_t o = idx[(size_t)s * n_mb + mb];
+  uint4* dst = reinterpret_cast<uint4*>(recs + (size_t)s * n_mb + mb);
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  if (o < 0) {
+    if (lane < 7) dst[lane] = lane == 0 ? make_uint4((uint32_t)MBT_PSKIP | ((uint32_t)(-1 - o) << 16), 0, 0, 0) : z;
+    else if (lane == 7) dst[39] = z;
+    return;
+  }
+  const uint4* src = pack + (size_t)s * stream_stride_u4 + (size_t)o * 2;
+  const uint32_t mask = src[0].y >> 8;
+  if (lane < 7) {
+    uint4 v = src[lane];
+    if (lane == 0) v.y &= 0xffu;                                   // pad0 carried the presence mask
+    dst[lane] = v;
+  } else if (lane == 7) {
+    dst[39] = src[7];                                              // chroma_dc
+  } else {
+    const int b = lane - 8, q = b < 16 ? 7 + 2 * b : 40 + 2 * (b - 16);
+    uint4 v0 = z, v1 = z;
+    if ((mask >> b) & 1) { const int pos = 8 + 2 * __popc(mask & ((1u << b) - 1)); v0 = src[pos]; v1 = src[pos + 1]; }
+    dst[q] = v0; dst[q + 1] = v1;
+  }
+}
+int dec_launch_unpack(const void* d_pack, size_t stream_stride_bytes, const int32_t* d_idx, MbOut* d_recs, int n_streams, int n_mb, cudaStream_t st) {
+  k_unpack_records<<<dim3((n_mb + 7) / 8, n_streams), 256, 0, st>>>(reinterpret_cast<const uint4*>(d_pack), stream_stride_bytes / 16, d_idx, d_recs, n_mb);
   return b2h264_launched();
 }
 

@@ -277,6 +277,23 @@ MBK_STAGE void mb_load_all(const MbCtx& c, MbScratch& s) {
 #endif
 }
 
+// P_SKIP: the reconstruction IS the skip prediction (s.skip_pred: 16x16 luma, 8x8 Cb, 8x8 Cr, dense and word aligned) — stored
+// straight from there: 3 word loads + 3 word stores per lane instead of a byte-wise copy into the tile and a byte-wise gather out of it
+// (five of six macroblocks of the bench clip end this way)
+MBK_HD void mb_store_recon_skip(const MbCtx& c, MbScratch& s) {
+  uint8_t* ry = c.f.rec[0] + (size_t)(c.mby * 16) * c.p.rec_stride_y + c.mbx * 16;
+  for (int i = lane_id(); i < 64; i += MBK_WS) {
+    const int r = i >> 2, c4 = (i & 3) << 2;
+    *reinterpret_cast<uint32_t*>(ry + (size_t)r * c.p.rec_stride_y + c4) = *reinterpret_cast<const uint32_t*>(s.skip_pred + r * 16 + c4);
+  }
+  for (int i = lane_id(); i < 32; i += MBK_WS) {
+    const int pl = i >> 4, r = (i >> 1) & 7, c4 = (i & 1) << 2;
+    uint8_t* dst = c.f.rec[1 + pl] + (size_t)(c.mby * 8 + r) * c.p.rec_stride_c + c.mbx * 8 + c4;
+    *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<const uint32_t*>(s.skip_pred + 256 + 64 * pl + r * 8 + c4);
+  }
+  warp_sync();
+}
+
 // reconstructed tile -> picture
 MBK_STAGE void mb_store_recon(const MbCtx& c, MbScratch& s) {
   uint8_t* ry = c.f.rec[0] + (size_t)(c.mby * 16) * c.p.rec_stride_y + c.mbx * 16;
@@ -624,15 +641,17 @@ MBK_FN int intra_mb_md_enc(const MbCtx& c, MbScratch& s, int cost_limit_for_i16 
   (void)cost_limit_for_i16;
   int bb;
   int cost = md_i16x16(c, s, &bb);
-  s.info.mb_type = MBT_I16x16;
-  s.info.cbp = 0;
+  bool use_i4 = false;                       // warp-uniform; the staged record is written by lane 0 only
+  if (lane_id() == 0) { s.info.mb_type = MBT_I16x16; s.info.cbp = 0; }
+  warp_sync();
   fill_i4_cache(c, s);
   if (intra_try_i4x4(c, s)) {
     const int cost4 = md_enc_i4x4(c, s, cost);         // pfIntraFineMd = WelsMdIntraFinePartition[Vaa] (:932, :942)
-    if (cost4 < cost) { s.info.mb_type = MBT_I4x4; cost = cost4; }
+    if (cost4 < cost) { use_i4 = true; cost = cost4; if (lane_id() == 0) s.info.mb_type = MBT_I4x4; warp_sync(); }
   }
-  if (s.info.mb_type == MBT_I16x16) {
-    s.info.cbp = 0;
+  if (!use_i4) {
+    if (lane_id() == 0) s.info.cbp = 0;        // the I4x4 attempt may have set bits
+    warp_sync();
     enc_rec_i16x16(c, s, s.pred_y[bb]);
   }
   int cb;

@@ -4,6 +4,7 @@
 // parse_mb_syn_cavlc.cpp (WelsResidualBlockCavlc :~700, ParseInterInfo, ParseIntra4x4Mode).
 #include "h264_parse.h"
 
+#include <stddef.h>
 #include <string.h>
 
 #include "cavlc_tables.h"
@@ -268,6 +269,13 @@ inline int nc_of(int a, int b) {
   return 0;
 }
 
+// a skipped macroblock: header bytes and chroma DC cleared (levels of such a record are never read), type P_SKIP
+static inline void reset_skip_record(MbOut* m) {
+  memset(m, 0, offsetof(MbOut, luma));
+  memset(m->chroma_dc, 0, sizeof(m->chroma_dc));
+  m->mb_type = MBT_PSKIP;
+}
+
 // inverse of the me(v) mapping of coded_block_pattern (Table 9-4): built from the writer's table
 int cbp_from_code(int code, bool intra) {
   struct Inv { uint8_t t[2][48]; };
@@ -434,8 +442,9 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
       pic->cur_slot = slot;
     }
     pic->disable_deblocking_idc = dbk_idc;
-    pic->mbs.assign(n, MbOut());
-    for (MbOut& m : pic->mbs) { memset(&m, 0, sizeof(m)); m.mb_type = MBT_PSKIP; }
+    // the records are initialised as the macroblocks are parsed (7.3 MB per 1080p picture are not filled up front: a skipped
+    // macroblock resets its 128 header bytes, a coded one its whole record); a picture is only handed out complete (next_mb == n)
+    if ((int)pic->mbs.size() != n) pic->mbs.assign(n, MbOut());
     DecMbAux za;
     memset(&za, 0, sizeof(za));
     pic->aux.assign(n, za);
@@ -455,6 +464,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
       const int run = (int)r.ue();
       if (!r.ok() || idx + run > n) return PARSE_INVALID;
       for (int k = 0; k < run; k++, idx++) {
+        reset_skip_record(&pic->mbs[idx]);
         pic->mbs[idx].qp = (uint8_t)qp;
         DecMbAux& a = pic->aux[idx];
         a.slice = (uint16_t)slice_no; a.dbk_idc = (uint8_t)dbk_idc; a.alpha_off = (int8_t)alpha_off; a.beta_off = (int8_t)beta_off;
@@ -466,6 +476,8 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
       if (idx == n || !r.more_data()) break;                  // the slice may end with a skip run
     }
     MbOut& m = pic->mbs[idx];
+    memset(&m, 0, sizeof(m));
+    m.mb_type = MBT_PSKIP;
     DecMbAux& ax = pic->aux[idx];
     const int mbx = idx % mbw, mby = idx / mbw;
     ax.slice = (uint16_t)slice_no; ax.dbk_idc = (uint8_t)dbk_idc; ax.alpha_off = (int8_t)alpha_off; ax.beta_off = (int8_t)beta_off;

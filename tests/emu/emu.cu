@@ -115,32 +115,10 @@ struct HostFrameEncoder {
     // write the access unit through that form too and insist on the same bytes
     {
       b2h264::StreamCtl twin = ctl;
-      // host mirror of k_pack_records: 128-byte head + the residual blocks that are inside a coded set and not all zero
-      std::vector<uint8_t> packed;
+      // the host twin of k_pack_records (the decoder's hand-over uses it; the encoder's device kernel follows the same rules)
+      std::vector<uint8_t> packed(out.size() * sizeof(MbOut));
       std::vector<int32_t> index(out.size());
-      for (size_t i = 0; i < out.size(); i++) {
-        const MbOut& m = out[i];
-        if (m.mb_type == MBT_PSKIP) { index[i] = -1; continue; }
-        index[i] = (int32_t)(packed.size() / 32);
-        const size_t at = packed.size();
-        packed.resize(at + 128);
-        memcpy(&packed[at], &m, offsetof(MbOut, luma));
-        memcpy(&packed[at + offsetof(MbOut, luma)], m.chroma_dc, sizeof(m.chroma_dc));
-        unsigned mask = 0;
-        for (int b = 0; b < 24; b++) {
-          const bool want = b < 16 ? (m.mb_type == MBT_I16x16 ? (m.cbp & 15) != 0 : ((m.cbp >> (b >> 2)) & 1) != 0) : (m.cbp >> 4) == 2;
-          const int16_t* blk = b < 16 ? m.luma[b] : m.chroma_ac[b - 16];
-          bool nz = false;
-          for (int q = 0; q < 16; q++) nz |= blk[q] != 0;
-          if (want && nz) {
-            mask |= 1u << b;
-            const size_t o = packed.size();
-            packed.resize(o + 32);
-            memcpy(&packed[o], blk, 32);
-          }
-        }
-        packed[at + 5] = (uint8_t)mask; packed[at + 6] = (uint8_t)(mask >> 8); packed[at + 7] = (uint8_t)(mask >> 16);
-      }
+      b2h264::pack_records_compact(out.data(), (int)out.size(), packed.data(), index.data());
       std::vector<uint8_t> a, b;
       b2h264::StreamCtl plain = ctl;
       plain.write_access_unit(idr, out.data(), &a);

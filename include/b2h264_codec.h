@@ -120,6 +120,12 @@ int  b2h264_dec_decode2 (b2h264_dec* d, const uint8_t* const* au, const int32_t*
  * size (so that a caller can create the decoder for it: ISVCDecoder learns the size from the stream) */
 int  b2h264_dec_probe (const uint8_t* au, int32_t au_bytes, int32_t* width, int32_t* height, int32_t* has_slice);
 
+/* Page-locked host memory for pictures handed to b2h264_enc_submit / received from b2h264_dec_decode: copies to and from such
+ * memory run at PCIe speed and asynchronously; ordinary (pageable) buffers work too, at roughly a third of the rate.
+ * The reference's callers own their picture buffers (SSourcePicture::pData, codec_app_def.h) - this is the allocator for them. */
+void* b2h264_host_alloc (size_t bytes);
+void  b2h264_host_free (void* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,8 @@ API = {
     "b2h264_dec_decode": [vp, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(vp)],
     "b2h264_dec_decode2": [vp, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(vp), C.POINTER(C.c_int32)],
     "b2h264_dec_probe": [vp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
+    "b2h264_host_alloc": [C.c_size_t],
+    "b2h264_host_free": [vp],
     "b2h264_enc_set_stream": [vp, vp],
     "b2h264_table_quant_ff": [C.c_int],
     "b2h264_table_quant_mf": [C.c_int],
@@ -101,7 +103,7 @@ class EncConfig(C.Structure):
                 ("device", C.c_int32), ("sps_pps_id_strategy", C.c_int32), ("complexity_low", C.c_int32)]
 
 
-_RESTYPES = {"b2h264_enc_destroy": None, "b2h264_dec_destroy": None, "b2h264_error_string": C.c_char_p, "b2h264_launch_count": C.c_ulonglong,
+_RESTYPES = {"b2h264_enc_destroy": None, "b2h264_dec_destroy": None, "b2h264_host_alloc": C.c_void_p, "b2h264_host_free": None, "b2h264_error_string": C.c_char_p, "b2h264_launch_count": C.c_ulonglong,
              "b2h264_table_quant_ff": i16p, "b2h264_table_quant_mf": i16p, "b2h264_table_dequant": u16p}
 
 _lib = None
@@ -267,18 +269,30 @@ class DecConfig(C.Structure):
 class BatchDecoder:
     """include/b2h264_codec.h b2h264_dec_*: one access unit per stream per call -> one I420 picture per stream."""
 
-    def __init__(self, width, height, n_streams=1, device=0):
+    def __init__(self, width, height, n_streams=1, device=0, pinned_output=False):
+        """pinned_output: the pictures land in ONE page-locked area owned by the decoder object (b2h264_host_alloc) and the
+        arrays decode() returns are views of it, valid until the next call — what a server that consumes each picture at once does."""
         self.L = lib(device)
         self.cfg = DecConfig(width, height, n_streams, device)
         self.h = vp()
         check(self.L.b2h264_dec_create(C.byref(self.cfg), C.byref(self.h)))
         self.n = n_streams
         self.frame_bytes = width * height * 3 // 2
+        self._pin = None
+        if pinned_output:
+            self._pin = self.L.b2h264_host_alloc(self.frame_bytes * n_streams)
+            if not self._pin:
+                raise MemoryError("b2h264_host_alloc")
+            whole = np.ctypeslib.as_array(C.cast(self._pin, C.POINTER(C.c_uint8)), shape=(self.frame_bytes * n_streams,))
+            self._outs = [whole[i * self.frame_bytes:(i + 1) * self.frame_bytes] for i in range(n_streams)]
+
+    def _out_buffers(self):
+        return self._outs if self._pin else [np.empty(self.frame_bytes, np.uint8) for _ in range(self.n)]
 
     def decode(self, access_units):
         """access_units: list of n_streams bytes objects; returns a list of numpy uint8 pictures (packed I420)."""
         bufs = [np.frombuffer(bytes(a), np.uint8) for a in access_units]
-        outs = [np.empty(self.frame_bytes, np.uint8) for _ in range(self.n)]
+        outs = self._out_buffers()
         au = (vp * self.n)(*[b.ctypes.data for b in bufs])
         nb = (C.c_int32 * self.n)(*[len(b) for b in bufs])
         yo = (vp * self.n)(*[o.ctypes.data for o in outs])
@@ -288,7 +302,7 @@ class BatchDecoder:
     def decode2(self, access_units):
         """like decode(); entries may be None (stream sits the call out).  Returns (pictures or None per stream)."""
         bufs = [None if a is None else np.frombuffer(bytes(a), np.uint8) for a in access_units]
-        outs = [np.empty(self.frame_bytes, np.uint8) for _ in range(self.n)]
+        outs = self._out_buffers()
         au = (vp * self.n)(*[None if b is None else b.ctypes.data for b in bufs])
         nb = (C.c_int32 * self.n)(*[0 if b is None else len(b) for b in bufs])
         yo = (vp * self.n)(*[o.ctypes.data for o in outs])
@@ -300,6 +314,10 @@ class BatchDecoder:
         if self.h:
             self.L.b2h264_dec_destroy(self.h)
             self.h = None
+        if self._pin:
+            self._outs = None
+            self.L.b2h264_host_free(self._pin)
+            self._pin = None
 
 
 def probe_access_unit(au):

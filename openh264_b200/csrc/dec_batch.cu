@@ -8,7 +8,11 @@
 // code; there is no CPU reconstruction path in this library.
 // Synchronous per call (parse -> H2D -> kernels -> D2H); streams without a slice in their access unit sit the call out.
 #include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <chrono>
 
 #include <vector>
 
@@ -121,6 +125,9 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
   CK(cudaSetDevice(d->cfg.device));
   const int S = d->S;
   int deblock = 1;
+  static const bool timing = getenv("B2H264_DEC_TIMING") != nullptr;          // debug: host phases of the call on stderr
+  const auto t0 = std::chrono::steady_clock::now();
+  auto ms_since = [&](std::chrono::steady_clock::time_point a) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count(); };
   d->act.clear(); d->act_ref.clear(); d->out_slot.clear(); d->out_cx.clear(); d->out_cy.clear();
   // 1. parse: every stream's access unit on the pool (streams are independent; a stream's parser state is its own)
   {
@@ -134,6 +141,7 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
     };
     d->pool->run(S, job);
   }
+  const double t_parse = ms_since(t0);
   // 2. the batch: descriptors and records of the streams that carry a picture, in stream order
   for (int s = 0; s < S; s++) {
     if (got_picture) got_picture[s] = 0;
@@ -190,6 +198,7 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
     };
     d->pool->run(n, job);
   }
+  const double t_pack = ms_since(t0);
   for (int i = 0; i < n; i++)                            // only what was packed crosses PCIe
     if (d->units[i] > 0)
       CK(cudaMemcpyAsync(d->d_pack + (size_t)i * d->n_mb * sizeof(MbOut), d->h_recs + (size_t)i * d->n_mb, (size_t)d->units[i] * 32, cudaMemcpyHostToDevice, d->st));
@@ -199,6 +208,9 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
   CK(cudaMemcpyAsync(d->d_sf, d->h_sf, (size_t)n * sizeof(StreamFrame), cudaMemcpyHostToDevice, d->st));
   const int rc = dec_launch_frame(d->d_sf, n, d->mb_w, d->mb_h, d->d_ws, d->d_recs, d->d_aux, deblock, d->st);
   if (rc) return rc;
+  const double t_launch = ms_since(t0);
+  if (timing) cudaStreamSynchronize(d->st);
+  const double t_kernels = ms_since(t0);
   const int w = d->cfg.width, h = d->cfg.height;
   for (int i = 0; i < n; i++) {
     const int s = d->act[i], rec = d->out_slot[i];
@@ -213,6 +225,12 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
     if (got_picture) got_picture[s] = 1;
   }
   CK(cudaStreamSynchronize(d->st));
+  if (timing) {
+    long long units = 0;
+    for (int i = 0; i < n; i++) units += d->units[i];
+    fprintf(stderr, "b2h264_dec_decode: %d pictures: parse %.2f ms, pack %.2f, launches issued %.2f, kernels done %.2f, pictures on the host %.2f; %.2f MB of records\n", n, t_parse,
+            t_pack - t_parse, t_launch - t_pack, t_kernels - t_launch, ms_since(t0) - t_kernels, units * 32 / 1e6);
+  }
   return 0;
 }
 
@@ -232,5 +250,11 @@ int b2h264_dec_probe(const uint8_t* au, int32_t au_bytes, int32_t* width, int32_
   if (h > 0 && height) *height = h;
   return 0;
 }
+
+void* b2h264_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) == cudaSuccess ? p : nullptr;
+}
+void b2h264_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 }  // extern "C"

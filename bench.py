@@ -286,7 +286,7 @@ def mc_sad_roofline(L, local, peak):
             "note": "64 stacked padded 1080p planes per launch (302 MB of pixels, larger than L2)"}
 
 
-def decode_bench(local, clip, seq, peak, S=64, n_pictures=10):
+def decode_bench(local, clip, seq, peak, S=256, n_pictures=8):
     """Decoder construct path (b2h264_dec_*: host parse, GPU prediction + residual + deblocking + padding): S copies of a
     1080p stream produced by this library's encoder (IDR + P, the bench clip), one access unit per stream per call.
     fps = pictures per second through b2h264_dec_decode with host bitstreams in and host pictures out (synchronous).

@@ -140,6 +140,31 @@ typedef struct {
 int b2h264_k_me_search (const uint8_t* cur, int cs, const uint8_t* ref, int rs, const b2h264_me_job* jobs, int n,
                         b2h264_me_result* out, void* stream);
 
+/* ---- WelsMotionCrossSearch (svc_motion_estimate.cpp:620-643): LineFullSearch_c (:568-618) along the vertical line through the
+ * co-located block, then — while the cost is still >= sad_cost_threshold — along the horizontal line.  The screen-content refinement
+ * after the diamond search (WelsDiamondCrossSearch :388).  mv_min / mv_max = SSlice::sMvStartMin / sMvStartMax (integer pels, the
+ * maximum is exclusive).  `io` carries SWelsME::sMv (INTEGER pels, as inside the search), uiSadCost and pRefMb in and out. */
+typedef struct {
+  int32_t blk;
+  int32_t cur_off, ref_off;            /* pEncMb; pColoRefMb */
+  int16_t mvp_x, mvp_y;                /* quarter-pel predictor */
+  int16_t mv_min_x, mv_min_y, mv_max_x, mv_max_y;
+  int32_t qp;
+  uint32_t sad_cost_threshold;
+} b2h264_cross_job;
+int b2h264_k_me_cross_search (const uint8_t* cur, int cs, const uint8_t* ref, int rs, const b2h264_cross_job* jobs, int n,
+                              b2h264_me_result* io, void* stream);
+
+/* ---- decoder inter prediction beyond plain MC (rec_mb.cpp): WeightPrediction :298 (explicit weights of one list), BiWeightPrediction :366
+ * (explicit, or implicit with w1 + w2 = 64 and log2_denom 5), BiPrediction :425 (rounded average).  n blocks of w x h samples of ONE
+ * plane, in place on dst + dst_off[i]; the second prediction at tmp + tmp_off[i] with the same stride.  mode 0 weight, 1 bi-weight, 2 average. */
+typedef struct {
+  int32_t log2_denom;
+  int32_t w1, o1, w2, o2;              /* mode 0 uses w1 / o1 only */
+} b2h264_weight_job;
+int b2h264_k_weighted_pred (int mode, uint8_t* dst, const uint8_t* tmp, int stride, const int32_t* dst_off, const int32_t* tmp_off,
+                            const b2h264_weight_job* jobs, int w, int h, int n, void* stream);
+
 /* ---- MC + SAD (the roofline-graded unit) --------------------------------------
  * For every macroblock m of an (mb_w x mb_h) frame: interpolate the 16x16 luma prediction at each of
  * the k quarter-pel motion vectors mv[m][0..k) (McLuma_c) and return SAD16x16 against the current

@@ -116,6 +116,12 @@ int  b2h264_dec_decode (b2h264_dec* d, const uint8_t* const* au, const int32_t* 
 /* as b2h264_dec_decode; streams whose au[s] is NULL or carries no slice (parameter sets only) sit the call out:
  * got_picture[s] = 1 where yuv[s] was written, else 0 (the parameter sets are kept for the stream) */
 int  b2h264_dec_decode2 (b2h264_dec* d, const uint8_t* const* au, const int32_t* au_bytes, uint8_t* const* yuv, int32_t* got_picture);
+/* for callers that batch UNRELATED streams (the ISVCDecoder broker of layer 3): status[s] = 1 picture decoded, 0 no slice in the unit (or
+ * au[s] == NULL), < 0 that stream's own error (-101 .. -105 as above, -2 size mismatch) — it sits the batch out, the other streams are
+ * decoded.  The return value only reports errors of the call as a whole (CUDA). */
+int  b2h264_dec_decode3 (b2h264_dec* d, const uint8_t* const* au, const int32_t* au_bytes, uint8_t* const* yuv, int32_t* status);
+/* stream `stream` starts over: parameter sets, frame numbering and reference pictures are forgotten (the next unit must carry SPS / PPS / IDR) */
+int  b2h264_dec_reset_stream (b2h264_dec* d, int stream);
 /* stateless look at an access unit: *has_slice, and — if it carries an SPS of the supported class — the cropped picture
  * size (so that a caller can create the decoder for it: ISVCDecoder learns the size from the stream) */
 int  b2h264_dec_probe (const uint8_t* au, int32_t au_bytes, int32_t* width, int32_t* height, int32_t* has_slice);

@@ -71,6 +71,8 @@ API = {
     "b2h264_k_downsample": [C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_size_t, vp],
     "b2h264_downsample_mode": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
     "b2h264_k_me_search": [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp],
+    "b2h264_k_me_cross_search": [vp, C.c_int, vp, C.c_int, vp, C.c_int, vp, vp],
+    "b2h264_k_weighted_pred": [C.c_int, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp],
     "b2h264_k_mc_sad": [vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, vp, vp],
     "b2h264_enc_create": [vp, C.POINTER(vp)],
     "b2h264_enc_destroy": [vp],
@@ -87,7 +89,9 @@ API = {
     "b2h264_dec_destroy": [vp],
     "b2h264_dec_decode": [vp, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(vp)],
     "b2h264_dec_decode2": [vp, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(vp), C.POINTER(C.c_int32)],
+    "b2h264_dec_decode3": [vp, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(vp), C.POINTER(C.c_int32)],
     "b2h264_dec_probe": [vp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
+    "b2h264_dec_reset_stream": [vp, C.c_int32],
     "b2h264_host_alloc": [C.c_size_t],
     "b2h264_host_free": [vp],
     "b2h264_enc_set_stream": [vp, vp],
@@ -309,6 +313,21 @@ class BatchDecoder:
         got = (C.c_int32 * self.n)()
         check(self.L.b2h264_dec_decode2(self.h, au, nb, yo, got))
         return [outs[i] if got[i] else None for i in range(self.n)]
+
+    def decode3(self, access_units):
+        """like decode2(), with the outcome of every stream: returns (pictures or None, status) — status 1 picture, 0 none,
+        < 0 that stream's error; a failing stream does not stop the others (b2h264_dec_decode3)."""
+        bufs = [None if a is None else np.frombuffer(bytes(a), np.uint8) for a in access_units]
+        outs = self._out_buffers()
+        au = (vp * self.n)(*[None if b is None else b.ctypes.data for b in bufs])
+        nb = (C.c_int32 * self.n)(*[0 if b is None else len(b) for b in bufs])
+        yo = (vp * self.n)(*[o.ctypes.data for o in outs])
+        st = (C.c_int32 * self.n)()
+        check(self.L.b2h264_dec_decode3(self.h, au, nb, yo, st))
+        return [outs[i] if st[i] == 1 else None for i in range(self.n)], list(st)
+
+    def reset_stream(self, stream):
+        check(self.L.b2h264_dec_reset_stream(self.h, stream))
 
     def close(self):
         if self.h:

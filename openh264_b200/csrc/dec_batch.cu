@@ -120,7 +120,10 @@ void b2h264_dec_destroy(b2h264_dec* d) {
 
 // got_picture (may be NULL): per stream 1 = a picture was decoded into yuv[s], 0 = the access unit carried no slice
 // (parameter sets only / au[s] == NULL).  With got_picture == NULL an access unit without a slice is an error.
-int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* au_bytes, uint8_t* const* yuv, int32_t* got_picture) {
+// status (may be NULL): per-stream outcome for callers that batch UNRELATED streams (the ISVCDecoder broker): 1 = picture, 0 = no slice in
+// the unit, < 0 = this stream's error (-101 .. -105, -2) — such a stream sits the batch out and the others are decoded; without
+// `status` the first stream error ends the call (the streams of one application stand or fall together).
+static int dec_decode_impl(b2h264_dec* d, const uint8_t* const* au, const int32_t* au_bytes, uint8_t* const* yuv, int32_t* got_picture, int32_t* status) {
   if (!d || !au || !au_bytes || !yuv) return -1;
   CK(cudaSetDevice(d->cfg.device));
   const int S = d->S;
@@ -143,22 +146,24 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
   }
   const double t_parse = ms_since(t0);
   // 2. the batch: descriptors and records of the streams that carry a picture, in stream order
+#define STREAM_FAIL(code) { d->last_error_stream = s; if (status) { status[s] = (code); continue; } return (code); }
+  if (status) for (int s = 0; s < S; s++) status[s] = 0;
   for (int s = 0; s < S; s++) {
     if (got_picture) got_picture[s] = 0;
     if (!au[s] || au_bytes[s] <= 0) {
-      if (!got_picture) { d->last_error_stream = s; return -1; }
+      if (!got_picture && !status) { d->last_error_stream = s; return -1; }
       continue;
     }
     ParsedPicture& pic = d->parsed[s];
     const int rc = d->parse_rc[s];
-    if (rc == PARSE_NO_PICTURE && got_picture) continue;
-    if (rc != PARSE_OK) { d->last_error_stream = s; return -100 + (rc == PARSE_NO_PICTURE ? PARSE_INVALID : rc); }   // -101 truncated, -102 unsupported, -103 invalid, -104 no parameter sets, -105 picture incomplete
+    if (rc == PARSE_NO_PICTURE && (got_picture || status)) continue;
+    if (rc != PARSE_OK) STREAM_FAIL(-100 + (rc == PARSE_NO_PICTURE ? PARSE_INVALID : rc))   // -101 truncated, -102 unsupported, -103 invalid, -104 no parameter sets, -105 picture incomplete
     const StreamParams& sp = d->parser[s].sp;
-    if (sp.mb_w != d->mb_w || sp.mb_h != d->mb_h || sp.width != d->cfg.width || sp.height != d->cfg.height) { d->last_error_stream = s; return -2; }
-    if ((int)pic.mbs.size() != d->n_mb) { d->last_error_stream = s; return -103; }
-    if ((int)pic.aux.size() != d->n_mb) { d->last_error_stream = s; return -103; }
+    if (sp.mb_w != d->mb_w || sp.mb_h != d->mb_h || sp.width != d->cfg.width || sp.height != d->cfg.height) STREAM_FAIL(-2)
+    if ((int)pic.mbs.size() != d->n_mb) STREAM_FAIL(-103)
+    if ((int)pic.aux.size() != d->n_mb) STREAM_FAIL(-103)
     if (pic.n_slots > d->slots) {                   // a stream with more reference frames: widen every stream's slot array, keeping the pictures
-      if (pic.n_slots > 17) { d->last_error_stream = s; return -103; }
+      if (pic.n_slots > 17) STREAM_FAIL(-103)
       uint8_t* np = nullptr;
       CK(cudaMalloc(&np, (size_t)S * pic.n_slots * d->pic_bytes + 256));
       CK(cudaMemsetAsync(np, 0, (size_t)S * pic.n_slots * d->pic_bytes + 256, d->st));
@@ -183,7 +188,7 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
     F.p.mb_w = d->mb_w; F.p.mb_h = d->mb_h;
     F.p.rec_stride_y = d->geo.rec_stride_y(); F.p.rec_stride_c = d->geo.rec_stride_c();
     F.p.qp = pic.ss.qp; F.p.is_idr = pic.ss.idr; F.p.ref_is_p = !pic.ss.idr; F.p.mv_range = 64; F.p.dec_mode = 1;
-    if (pic.cur_slot >= d->slots) { d->last_error_stream = s; return -103; }
+    if (pic.cur_slot >= d->slots) STREAM_FAIL(-103)
     for (int pl = 0; pl < 3; pl++) { F.f.rec[pl] = d->plane0(pic.cur_slot, s, pl); F.f.ref[pl] = F.f.dpb0[pl] = d->plane0(0, s, pl); }
     F.f.dpb_stride = (int64_t)d->pic_bytes;
     F.f.mbi = d->d_mbi + (size_t)s * d->n_mb;
@@ -223,6 +228,7 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
       dst += (size_t)pw * ph;
     }
     if (got_picture) got_picture[s] = 1;
+    if (status) status[s] = 1;
   }
   CK(cudaStreamSynchronize(d->st));
   if (timing) {
@@ -234,8 +240,17 @@ int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* a
   return 0;
 }
 
+#undef STREAM_FAIL
+
+int b2h264_dec_decode2(b2h264_dec* d, const uint8_t* const* au, const int32_t* au_bytes, uint8_t* const* yuv, int32_t* got_picture) {
+  return dec_decode_impl(d, au, au_bytes, yuv, got_picture, nullptr);
+}
+int b2h264_dec_decode3(b2h264_dec* d, const uint8_t* const* au, const int32_t* au_bytes, uint8_t* const* yuv, int32_t* status) {
+  if (!status) return -1;
+  return dec_decode_impl(d, au, au_bytes, yuv, nullptr, status);
+}
 int b2h264_dec_decode(b2h264_dec* d, const uint8_t* const* au, const int32_t* au_bytes, uint8_t* const* yuv) {
-  return b2h264_dec_decode2(d, au, au_bytes, yuv, nullptr);
+  return dec_decode_impl(d, au, au_bytes, yuv, nullptr, nullptr);
 }
 
 // Looks at an access unit without a decoder: *has_slice = a coded slice NAL is present; if it carries an SPS of the
@@ -248,6 +263,14 @@ int b2h264_dec_probe(const uint8_t* au, int32_t au_bytes, int32_t* width, int32_
   if (rc != PARSE_OK) return -100 + rc;
   if (w > 0 && width) *width = w;
   if (h > 0 && height) *height = h;
+  return 0;
+}
+
+// a stream slot starts over (a new ISVCDecoder object takes it): parser state, parameter sets and reference pictures are forgotten
+int b2h264_dec_reset_stream(b2h264_dec* d, int stream) {
+  if (!d || stream < 0 || stream >= d->S) return -1;
+  d->parser[stream] = ParserState();
+  d->parsed[stream] = ParsedPicture();
   return 0;
 }
 

@@ -135,6 +135,74 @@ __global__ void __launch_bounds__(256) k_me_search(const uint8_t* __restrict__ c
 }
 
 // ------------------------------------------------------------------------------------------------
+// WelsMotionCrossSearch / LineFullSearch_c (svc_motion_estimate.cpp:568-643).  One warp per job; a LANE per candidate position:
+// the positions of a line are independent (the reference walks them serially and keeps the first minimum), so every lane scores
+// whole blocks at its positions with packed SADs and the warp takes the minimum of (cost << 12 | index): the smallest index wins a
+// tie, like the reference's strict `<` in ascending order.
+__device__ __forceinline__ uint32_t lane_block_sad(const uint8_t* a, int sa, const uint8_t* b, int sb, int w, int h) {
+  uint32_t s = 0;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x += 4) s += vsadu4(ld4u(a + y * sa + x), ld4u(b + y * sb + x));
+  return s;
+}
+__device__ __forceinline__ void line_search(const uint8_t* enc, int cs, const uint8_t* colo, const uint8_t* plane, int rs, int w, int h, int lambda,
+                                            int mvp_x, int mvp_y, int min_mv, int max_mv, bool vertical, b2h264_me_result& io) {
+  const int n = max_mv - min_mv;
+  if (n <= 0) return;
+  const int fixed = (lambda * se_bits(vertical ? -mvp_x : -mvp_y)) & 0xffff;
+  const int stride = vertical ? rs : 1;
+  unsigned long long best = ~0ull;
+  for (int i = lane_id(); i < n; i += 32) {
+    const int mv = min_mv + i;
+    const uint32_t cost = lane_block_sad(enc, cs, colo + (ptrdiff_t)mv * stride, rs, w, h) +
+                          (uint32_t)(fixed + ((lambda * se_bits(mv * 4 - (vertical ? mvp_y : mvp_x))) & 0xffff));
+    const unsigned long long key = ((unsigned long long)cost << 16) | (unsigned)i;
+    best = key < best ? key : best;
+  }
+  for (int o = 16; o; o >>= 1) { const unsigned long long other = __shfl_xor_sync(MBK_FULL, best, o); best = other < best ? other : best; }
+  const uint32_t cost = (uint32_t)(best >> 16);
+  const int mv = min_mv + (int)(best & 0xffff);
+  if (cost < io.sad_cost) {                              // UpdateMeResults (:60)
+    io.mv_x = (int16_t)(vertical ? 0 : mv); io.mv_y = (int16_t)(vertical ? mv : 0);
+    io.sad_cost = cost;
+    io.ref_off = (int32_t)(colo + (ptrdiff_t)io.mv_y * rs + io.mv_x - plane);
+  }
+}
+__global__ void __launch_bounds__(256) k_me_cross_search(const uint8_t* __restrict__ cur, int cs, const uint8_t* __restrict__ ref, int rs,
+                                                         const b2h264_cross_job* __restrict__ jobs, int n, b2h264_me_result* io) {
+  const int j = warp_job();
+  if (j >= n) return;
+  const b2h264_cross_job jb = jobs[j];
+  b2h264_me_result r = io[j];
+  const int w = 1 << blk_lw(jb.blk), h = 1 << blk_lh(jb.blk), lambda = c_lambda[jb.qp];
+  const uint8_t* enc = cur + jb.cur_off;
+  const uint8_t* colo = ref + jb.ref_off;
+  line_search(enc, cs, colo, ref, rs, w, h, lambda, jb.mvp_x, jb.mvp_y, jb.mv_min_y, jb.mv_max_y, true, r);
+  if (r.sad_cost >= jb.sad_cost_threshold) line_search(enc, cs, colo, ref, rs, w, h, lambda, jb.mvp_x, jb.mvp_y, jb.mv_min_x, jb.mv_max_x, false, r);
+  if (lane_id() == 0) io[j] = r;
+}
+
+// rec_mb.cpp:298-460: explicit weighted, bi-weighted (explicit / implicit) and averaged prediction, one plane of a block per warp
+__global__ void __launch_bounds__(256) k_weighted_pred(int mode, uint8_t* __restrict__ dst, const uint8_t* __restrict__ tmp, int stride,
+                                                       const int32_t* __restrict__ dst_off, const int32_t* __restrict__ tmp_off,
+                                                       const b2h264_weight_job* __restrict__ jobs, int w, int h, int n) {
+  const int j = warp_job();
+  if (j >= n) return;
+  uint8_t* d = dst + dst_off[j];
+  const uint8_t* t = mode ? tmp + tmp_off[j] : nullptr;
+  const b2h264_weight_job jb = mode == 2 ? b2h264_weight_job{0, 0, 0, 0, 0} : jobs[j];
+  for (int i = lane_id(); i < w * h; i += 32) {
+    const int y = i / w, x = i - y * w;
+    const int p = d[y * stride + x];
+    int v;
+    if (mode == 0) v = jb.log2_denom >= 1 ? ((p * jb.w1 + (1 << (jb.log2_denom - 1))) >> jb.log2_denom) + jb.o1 : p * jb.w1 + jb.o1;
+    else if (mode == 1) v = ((p * jb.w1 + t[y * stride + x] * jb.w2 + (1 << jb.log2_denom)) >> (jb.log2_denom + 1)) + ((jb.o1 + jb.o2 + 1) >> 1);
+    else v = (p + t[y * stride + x] + 1) >> 1;
+    d[y * stride + x] = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // MC + SAD roofline unit.  One warp per macroblock.  The warp stages the reference window that all
 // of the macroblock's k candidates can touch ([-R-2, 16+R+3) in both axes, R = 8 integer pels) and
 // the current macroblock into shared memory once (coalesced 4-byte loads of 128-B-aligned rows from
@@ -562,6 +630,19 @@ int b2h264_k_me_search(const uint8_t* cur, int cs, const uint8_t* ref, int rs, c
                        b2h264_me_result* out, void* stream) {
   if (n <= 0) return 0;
   k_me_search<<<JOB_GRID(n), 0, (cudaStream_t)stream>>>(cur, cs, ref, rs, jobs, n, out);
+  return b2h264_launched();
+}
+int b2h264_k_me_cross_search(const uint8_t* cur, int cs, const uint8_t* ref, int rs, const b2h264_cross_job* jobs, int n,
+                             b2h264_me_result* io, void* stream) {
+  if (n <= 0) return 0;
+  k_me_cross_search<<<JOB_GRID(n), 0, (cudaStream_t)stream>>>(cur, cs, ref, rs, jobs, n, io);
+  return b2h264_launched();
+}
+int b2h264_k_weighted_pred(int mode, uint8_t* dst, const uint8_t* tmp, int stride, const int32_t* dst_off, const int32_t* tmp_off,
+                           const b2h264_weight_job* jobs, int w, int h, int n, void* stream) {
+  if (n <= 0) return 0;
+  if (mode < 0 || mode > 2 || w <= 0 || h <= 0 || (mode != 2 && !jobs) || (mode != 0 && (!tmp || !tmp_off))) return cudaErrorInvalidValue;
+  k_weighted_pred<<<JOB_GRID(n), 0, (cudaStream_t)stream>>>(mode, dst, tmp, stride, dst_off, tmp_off, jobs, w, h, n);
   return b2h264_launched();
 }
 int b2h264_k_mc_sad(const uint8_t* cur, int cs, const uint8_t* ref, int rs, int mb_w, int mb_h, const int16_t* mv, int k,

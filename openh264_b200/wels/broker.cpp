@@ -131,6 +131,90 @@ int Pool::encode(int slot, std::vector<uint8_t>* au, bool* idr) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+DecPool::DecPool(int width, int height, int capacity, int device) : w_(width), h_(height), cap_(capacity), device_(device) {
+  frame_bytes_ = (size_t)width * height * 3 / 2;
+  wait_us_ = env_long("B2H264_BROKER_WAIT_US", 2000);
+  b2h264_dec_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.width = width; cfg.height = height; cfg.n_streams = capacity; cfg.device = device;
+  if (b2h264_dec_create(&cfg, &dec_) != 0) { dec_ = nullptr; return; }
+  pinned_ = static_cast<uint8_t*>(b2h264_host_alloc(frame_bytes_ * capacity));
+  if (!pinned_) { b2h264_dec_destroy(dec_); dec_ = nullptr; return; }
+  state_.assign(capacity, FREE);
+  au_.assign(capacity, nullptr);
+  bytes_.assign(capacity, 0);
+  status_.assign(capacity, 0);
+}
+
+DecPool::~DecPool() {
+  if (dec_) b2h264_dec_destroy(dec_);
+  if (pinned_) b2h264_host_free(pinned_);
+}
+
+int DecPool::acquire() {
+  std::unique_lock<std::mutex> lk(m_);
+  for (int s = 0; s < cap_; s++)
+    if (state_[s] == FREE) { state_[s] = IDLE; n_registered_++; return s; }
+  return -1;
+}
+
+void DecPool::release(int slot) {
+  std::unique_lock<std::mutex> lk(m_);
+  cv_.wait(lk, [&] { return !flushing_; });
+  b2h264_dec_reset_stream(dec_, slot);
+  state_[slot] = FREE;
+  n_registered_--;
+  cv_.notify_all();
+}
+
+int DecPool::registered() {
+  std::unique_lock<std::mutex> lk(m_);
+  return n_registered_;
+}
+
+void DecPool::flush_locked(std::unique_lock<std::mutex>& lk) {
+  flushing_ = true;
+  std::vector<const uint8_t*> au(cap_, nullptr);
+  std::vector<int32_t> nb(cap_, 0), st(cap_, 0);
+  std::vector<uint8_t*> out(cap_, nullptr);
+  for (int s = 0; s < cap_; s++) {
+    out[s] = pinned_ + (size_t)s * frame_bytes_;
+    if (state_[s] == PENDING) { state_[s] = INFLIGHT; au[s] = au_[s]; nb[s] = bytes_[s]; }
+  }
+  n_pending_ = 0;
+  lk.unlock();
+  const int rc = b2h264_dec_decode3(dec_, au.data(), nb.data(), out.data(), st.data());
+  lk.lock();
+  for (int s = 0; s < cap_; s++) {
+    if (state_[s] != INFLIGHT) continue;
+    status_[s] = rc ? (rc > 0 ? -1000 - rc : rc) : st[s];        // a failure of the call as a whole fails every stream of the batch
+    state_[s] = DONE;
+  }
+  flushing_ = false;
+  cv_.notify_all();
+}
+
+int DecPool::decode(int slot, const uint8_t* au, int32_t bytes) {
+  std::unique_lock<std::mutex> lk(m_);
+  if (slot < 0 || slot >= cap_ || state_[slot] != IDLE) return -1;
+  au_[slot] = au; bytes_[slot] = bytes;
+  state_[slot] = PENDING;
+  n_pending_++;
+  const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(wait_us_);
+  while (state_[slot] != DONE) {
+    if (state_[slot] == PENDING && !flushing_) {
+      if (n_pending_ >= n_registered_ || std::chrono::steady_clock::now() >= deadline) { flush_locked(lk); continue; }
+      cv_.wait_until(lk, deadline);
+    } else {
+      cv_.wait(lk);
+    }
+  }
+  const int st = status_[slot];
+  state_[slot] = IDLE;
+  return st;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 Broker& Broker::get() {
   static Broker* b = new Broker();       // never destroyed: encoder objects may outlive static destruction order
   return *b;
@@ -158,6 +242,36 @@ std::shared_ptr<Pool> Broker::attach(const PoolKey& key, int* slot) {
   pools_.push_back(p);
   *slot = p->acquire();
   return p;
+}
+
+std::shared_ptr<DecPool> Broker::attach_decoder(int width, int height, int* slot) {
+  std::lock_guard<std::mutex> g(m_);
+  int same_class = 0;
+  for (auto& p : dec_pools_) {
+    if (p->width() != width || p->height() != height) continue;
+    same_class++;
+    const int s = p->acquire();
+    if (s >= 0) { *slot = s; return p; }
+  }
+  long cap = env_long("B2H264_BROKER_SLOTS", 0);
+  if (cap <= 0) { cap = 4L << (2 * (same_class < 3 ? same_class : 3)); if (cap > 128) cap = 128; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return nullptr;
+  const long dev_env = env_long("B2H264_DEVICE", -1);
+  const int device = dev_env >= 0 ? (int)(dev_env % ndev) : (next_device_++ % ndev);
+  auto p = std::make_shared<DecPool>(width, height, (int)cap, device);
+  if (!p->ok()) return nullptr;
+  dec_pools_.push_back(p);
+  *slot = p->acquire();
+  return p;
+}
+
+void Broker::detach_decoder(const std::shared_ptr<DecPool>& pool, int slot) {
+  pool->release(slot);
+  std::lock_guard<std::mutex> g(m_);
+  if (pool->registered() == 0)
+    for (size_t i = 0; i < dec_pools_.size(); i++)
+      if (dec_pools_[i] == pool) { dec_pools_.erase(dec_pools_.begin() + i); break; }
 }
 
 void Broker::detach(const std::shared_ptr<Pool>& pool, int slot) {

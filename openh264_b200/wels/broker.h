@@ -71,6 +71,41 @@ class Pool {
   long wait_us_;
 };
 
+// The same for ISVCDecoder objects: decoders of one picture size are streams of ONE shared b2h264_dec.  DecodeFrame2 hands in its
+// access unit (the caller's own buffer: the caller blocks until the batch is done) and gets its picture in the slot's page-locked
+// output area; every stream of a batch has its own outcome (b2h264_dec_decode3), a broken stream does not disturb the others.
+class DecPool {
+ public:
+  DecPool(int width, int height, int capacity, int device);
+  ~DecPool();
+  bool ok() const { return dec_ != nullptr; }
+  int width() const { return w_; }
+  int height() const { return h_; }
+  int acquire();
+  void release(int slot);
+  int registered();
+  uint8_t* picture(int slot) { return pinned_ + (size_t)slot * frame_bytes_; }
+  // synchronous: decodes the access unit as the next unit of `slot`.  Returns the stream's status: 1 picture (in picture(slot)),
+  // 0 no picture, < 0 the layer-2 error of this stream / the call
+  int decode(int slot, const uint8_t* au, int32_t bytes);
+
+ private:
+  enum State { FREE, IDLE, PENDING, INFLIGHT, DONE };
+  void flush_locked(std::unique_lock<std::mutex>& lk);
+  int w_, h_, cap_, device_;
+  size_t frame_bytes_;
+  b2h264_dec* dec_ = nullptr;
+  uint8_t* pinned_ = nullptr;
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::vector<State> state_;
+  std::vector<const uint8_t*> au_;
+  std::vector<int32_t> bytes_, status_;
+  int n_registered_ = 0, n_pending_ = 0;
+  bool flushing_ = false;
+  long wait_us_;
+};
+
 // the pools of the process
 class Broker {
  public:
@@ -78,10 +113,13 @@ class Broker {
   // registers a stream; returns its pool + slot (nullptr on failure)
   std::shared_ptr<Pool> attach(const PoolKey& key, int* slot);
   void detach(const std::shared_ptr<Pool>& pool, int slot);
+  std::shared_ptr<DecPool> attach_decoder(int width, int height, int* slot);
+  void detach_decoder(const std::shared_ptr<DecPool>& pool, int slot);
 
  private:
   std::mutex m_;
   std::vector<std::shared_ptr<Pool>> pools_;
+  std::vector<std::shared_ptr<DecPool>> dec_pools_;
   int next_device_ = 0;
 };
 

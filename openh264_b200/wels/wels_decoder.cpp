@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "b2h264_codec.h"
+#include "broker.h"
 #include "codec_api.h"
 
 namespace {
@@ -33,8 +34,7 @@ class B2Decoder : public ISVCDecoder {
   }
 
   long EXTAPI Uninitialize() override {
-    if (dec_) { b2h264_dec_destroy(dec_); dec_ = nullptr; }
-    if (pic_) { cudaFreeHost(pic_); pic_ = nullptr; }
+    drop_slot();
     w_ = h_ = 0;
     inited_ = false;
     return cmResultSuccess;
@@ -71,25 +71,24 @@ class B2Decoder : public ISVCDecoder {
     int rc = b2h264_dec_probe(pending_.data(), (int32_t)pending_.size(), &w, &h, &has_slice);
     if (rc) { pending_.clear(); return refuse(rc); }
     vcl_ = has_slice;
-    if (w > 0 && h > 0 && (w != w_ || h != h_)) {                 // a (new) SPS: size the GPU decoder for it
-      if (dec_) { b2h264_dec_destroy(dec_); dec_ = nullptr; }
-      if (pic_) { cudaFreeHost(pic_); pic_ = nullptr; }
-      b2h264_dec_config cfg;
-      cfg.width = w; cfg.height = h; cfg.n_streams = 1; cfg.device = 0;
-      if (b2h264_dec_create(&cfg, &dec_) != 0 || !dec_) { dec_ = nullptr; pending_.clear(); return dsOutOfMemory; }
-      if (cudaHostAlloc((void**)&pic_, (size_t)w * h * 3 / 2, cudaHostAllocDefault) != cudaSuccess) { pic_ = nullptr; pending_.clear(); return dsOutOfMemory; }
+    if (w > 0 && h > 0 && (w != w_ || h != h_)) {                 // a (new) SPS: a stream slot of the shared decoder of that size
+      drop_slot();
+      pool_ = b2wels::Broker::get().attach_decoder(w, h, &slot_);
+      if (!pool_ || slot_ < 0) { pool_.reset(); slot_ = -1; pending_.clear(); return dsOutOfMemory; }
+      pic_ = pool_->picture(slot_);
       w_ = w; h_ = h;
     }
-    if (!dec_) { pending_.clear(); return dsNoParamSets; }
-    const uint8_t* au[1] = {pending_.data()};
-    const int32_t nb[1] = {(int32_t)pending_.size()};
-    uint8_t* out[1] = {pic_};
-    int32_t got[1] = {0};
-    rc = b2h264_dec_decode2(dec_, au, nb, out, got);
+    if (!pool_) { pending_.clear(); return dsNoParamSets; }
+    // objects of one picture size are streams of one batched GPU decoder: the units of the callers that arrive together are
+    // decoded by one launch (openh264_b200/wels/broker.h); a lone decoder is served at once
+    rc = pool_->decode(slot_, pending_.data(), (int32_t)pending_.size());
+    const int got0 = rc == 1;
+    if (rc >= 0) rc = 0;
+    else if (rc <= -1000) rc = -1000 - rc;                       // CUDA error of the call
     if (rc == -105) return dsErrorFree;                           // more slices of this picture to come
     pending_.clear();
     if (rc) return refuse(rc);
-    if (got[0]) {
+    if (got0) {
       frames_++;
       info->iBufferStatus = 1;
       info->uiOutYuvTimeStamp = ts;
@@ -169,8 +168,13 @@ class B2Decoder : public ISVCDecoder {
   SDecodingParam par_;
   bool inited_ = false, eos_ = false;
   int ec_ = 0, vcl_ = 0;
-  b2h264_dec* dec_ = nullptr;
-  uint8_t* pic_ = nullptr;
+  void drop_slot() {
+    if (pool_) { b2wels::Broker::get().detach_decoder(pool_, slot_); pool_.reset(); }
+    slot_ = -1; pic_ = nullptr;
+  }
+  std::shared_ptr<b2wels::DecPool> pool_;
+  int slot_ = -1;
+  uint8_t* pic_ = nullptr;                // the slot's page-locked output picture (owned by the pool)
   int w_ = 0, h_ = 0;
   long frames_ = 0;
   std::vector<uint8_t> pending_;         // NAL units of a picture whose slices have not all arrived yet

@@ -678,3 +678,59 @@ void orc_downsample (int mode, uint8_t* dst, int ds, int dst_w, int dst_h, const
     }
   }
 }
+
+/* ---- WelsMotionCrossSearch / LineFullSearch_c (svc_motion_estimate.cpp:568-643) ------------------------------------------ */
+static void orc_line_search (const uint8_t* enc, int cs, const uint8_t* colo, const uint8_t* ref_plane, int rs, const orc_cross_job* j,
+                             const uint16_t* mvd, int min_mv, int max_mv, int vertical, orc_me_result* io) {
+  /* iFixedMvd: the cost of the component that stays at 0; pMvdCost walks the other one in integer-pel steps (:585-598) */
+  const int fixed = vertical ? mvd[-j->mvp_x] : mvd[-j->mvp_y];
+  const uint16_t* c = mvd + min_mv * 4 - (vertical ? j->mvp_y : j->mvp_x);
+  const int stride = vertical ? rs : 1;
+  const uint8_t* r = colo + min_mv * stride;
+  uint32_t best = 0xFFFFFFFFu;
+  int best_mv = 0;
+  for (int mv = min_mv; mv < max_mv; mv++) {                 /* iTargetPos < iMaxPos: the maximum is exclusive */
+    const uint32_t cost = (uint32_t) orc_sad (j->blk, enc, cs, r, rs) + (uint32_t) (fixed + *c);
+    if (cost < best) { best = cost; best_mv = mv; }
+    r += stride; c += 4;
+  }
+  if (best < io->sad_cost) {                                 /* UpdateMeResults (:60) */
+    io->mv_x = (int16_t) (vertical ? 0 : best_mv);
+    io->mv_y = (int16_t) (vertical ? best_mv : 0);
+    io->sad_cost = best;
+    io->ref_off = (int32_t) (colo + io->mv_y * rs + io->mv_x - ref_plane);
+  }
+}
+void orc_me_cross_search (const uint8_t* cur, int cs, const uint8_t* ref, int rs, const orc_cross_job* j, orc_me_result* io) {
+  static uint16_t cost_tbl[52][2 * ORC_MVD_SZ + 1];
+  static uint8_t cost_ready[52];
+  if (!cost_ready[j->qp]) { orc_mvd_cost_init (cost_tbl[j->qp] + ORC_MVD_SZ, ORC_MVD_SZ, j->qp); cost_ready[j->qp] = 1; }
+  const uint16_t* mvd = cost_tbl[j->qp] + ORC_MVD_SZ;
+  const uint8_t* enc = cur + j->cur_off;
+  const uint8_t* colo = ref + j->ref_off;
+  orc_line_search (enc, cs, colo, ref, rs, j, mvd, j->mv_min_y, j->mv_max_y, 1, io);
+  if (io->sad_cost >= j->sad_cost_threshold)
+    orc_line_search (enc, cs, colo, ref, rs, j, mvd, j->mv_min_x, j->mv_max_x, 0, io);
+}
+
+/* ---- rec_mb.cpp:298-460: weighted / bi-directional prediction of one plane ------------------------------------------------ */
+static uint8_t orc_clip255 (int v) { return (uint8_t) (v < 0 ? 0 : v > 255 ? 255 : v); }
+void orc_weight_pred (uint8_t* dst, int stride, int w, int h, int log2_denom, int weight, int offset) {
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      const int p = dst[y * stride + x];
+      const int v = log2_denom >= 1 ? ((p * weight + (1 << (log2_denom - 1))) >> log2_denom) + offset : p * weight + offset;
+      dst[y * stride + x] = orc_clip255 (v);
+    }
+}
+void orc_biweight_pred (uint8_t* dst, const uint8_t* tmp, int stride, int w, int h, int log2_denom, int w1, int o1, int w2, int o2) {
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {
+      const int v = ((dst[y * stride + x] * w1 + tmp[y * stride + x] * w2 + (1 << log2_denom)) >> (log2_denom + 1)) + ((o1 + o2 + 1) >> 1);
+      dst[y * stride + x] = orc_clip255 (v);
+    }
+}
+void orc_bi_pred (uint8_t* dst, const uint8_t* tmp, int stride, int w, int h) {
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) dst[y * stride + x] = (uint8_t) ((dst[y * stride + x] + tmp[y * stride + x] + 1) >> 1);
+}

@@ -188,6 +188,36 @@ void ref_me_search (const uint8_t* cur, int cs, const uint8_t* ref, int rs, cons
   out->ref_off = (int32_t) (me.pRefMb - ref);
 }
 
+/* WelsMotionCrossSearch (svc_motion_estimate.cpp:620) with the reference's own structs; io = SWelsME::sMv (integer pels) / uiSadCost / pRefMb */
+void ref_me_cross_search (const uint8_t* cur, int cs, const uint8_t* ref, int rs, const orc_cross_job* j, orc_me_result* io) {
+  static uint16_t* cost = NULL;
+  const int kSz = 1100, kStride = 2 * kSz + 1;
+  if (!cost) { cost = (uint16_t*) malloc (sizeof (uint16_t) * 52 * kStride); MvdCostInit (cost, kStride); }
+  SWelsFuncPtrList* f = Funcs();
+  f->pfVerticalFullSearch = LineFullSearch_c;
+  f->pfHorizontalFullSearch = LineFullSearch_c;
+  static SSlice* slice = NULL;
+  if (!slice) slice = (SSlice*) calloc (1, sizeof (SSlice));
+  slice->sMvStartMin.iMvX = j->mv_min_x; slice->sMvStartMin.iMvY = j->mv_min_y;
+  slice->sMvStartMax.iMvX = j->mv_max_x; slice->sMvStartMax.iMvY = j->mv_max_y;
+  SWelsME me;
+  memset (&me, 0, sizeof (me));
+  me.pMvdCost = cost + j->qp * kStride + kSz;
+  me.uiBlockSize = (uint8_t) j->blk;
+  me.pEncMb = (uint8_t*) cur + j->cur_off;
+  me.pColoRefMb = (uint8_t*) ref + j->ref_off;
+  me.pRefMb = (uint8_t*) ref + io->ref_off;
+  me.sMvp.iMvX = j->mvp_x; me.sMvp.iMvY = j->mvp_y;
+  me.sMv.iMvX = io->mv_x; me.sMv.iMvY = io->mv_y;
+  me.uiSadCost = io->sad_cost;
+  me.uiSadCostThreshold = j->sad_cost_threshold;
+  me.iCurMeBlockPixX = 64; me.iCurMeBlockPixY = 64;          /* only differences of positions enter the result */
+  WelsMotionCrossSearch (f, &me, slice, cs, rs);
+  io->mv_x = me.sMv.iMvX; io->mv_y = me.sMv.iMvY;
+  io->sad_cost = me.uiSadCost;
+  io->ref_off = (int32_t) (me.pRefMb - ref);
+}
+
 } // extern "C"
 
 /* ------------------------------------------------------------------------------------------------

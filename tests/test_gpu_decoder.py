@@ -119,3 +119,34 @@ def test_gpu_decoder_conformance_other_sizes():
         assert hs.hexdigest() == sha, f
         ran += 1
     assert ran >= 2
+
+
+def test_gpu_decoder_per_stream_status_and_slot_reuse():
+    """b2h264_dec_decode3 (what the ISVCDecoder broker calls): one stream of the batch is outside the supported class, one sits
+    the call out, one is truncated later on — each gets its own status and the healthy streams decode exactly as alone;
+    page-locked output (b2h264_host_alloc); a slot handed to a new stream (b2h264_dec_reset_stream) starts over."""
+    if not h264lib.have_ref():
+        pytest.skip("oracle/_ref not present")
+    from openh264_b200.binding import BatchDecoder
+    w, h, n = 176, 144, 5
+    streams = ref_streams(w, h, n, 28, (11, 12))
+    want = [ref_decode(bs, w, h, n) for bs, _ in streams]
+    fsz = w * h * 3 // 2
+    high_sps = b"\x00\x00\x00\x01\x67\x64\x00\x1f\xac\xd9\x40\x50\x05\xbb\x01\x10"
+    dec = BatchDecoder(w, h, n_streams=4, pinned_output=True)
+    for f in range(n):
+        a0 = streams[0][1][f]
+        a1 = streams[1][1][f] if f != 2 else streams[1][1][f][:len(streams[1][1][f]) // 2]      # picture 2 of stream 1 arrives truncated
+        pics, st = dec.decode3([a0, a1, high_sps if f == 0 else None, None])
+        assert st[0] == 1 and np.array_equal(pics[0], want[0][f * fsz:(f + 1) * fsz])
+        if f < 2:
+            assert st[1] == 1 and np.array_equal(pics[1], want[1][f * fsz:(f + 1) * fsz])
+        elif f == 2:
+            assert st[1] < 0 and pics[1] is None
+        assert st[2] == (-102 if f == 0 else 0) and st[3] == 0
+    # slot 1 is handed to a new stream: it starts over with that stream's parameter sets
+    dec.reset_stream(1)
+    for f in range(n):
+        pics, st = dec.decode3([None, streams[0][1][f], None, None])
+        assert st == [0, 1, 0, 0] and np.array_equal(pics[1], want[0][f * fsz:(f + 1) * fsz])
+    dec.close()

@@ -146,3 +146,44 @@ def test_decoder_drop_in_on_conformance_streams(tmp_path, name):
     assert r0.returncode == 0 and r1.returncode == 0, r0.stderr + r1.stderr
     assert len(y0) > 0 and y0 == y1
     assert l0 == l1, "call log differs:\n" + l0[:2000] + "\n---\n" + l1[:2000]
+
+
+MT_DEC_DRIVER = os.path.join(ROOT, "oracle", "_ref", "wels_mt_dec_driver")
+QCIF_STREAMS = ["BA_MW_D.264", "SVA_Base_B.264", "MR1_MW_A.264", "BANM_MW_D.264", "MIDR_MW_D.264", "NRF_MW_E.264"]
+
+
+def drive_mt_dec(lib, names, threads, outdir, tag, slots=None):
+    env = dict(os.environ)
+    if slots:
+        env["B2H264_BROKER_SLOTS"] = str(slots)
+    files = [os.path.join(ROOT, "tests", "golden", "conformance", n) for n in names]
+    prefix = os.path.join(outdir, tag + "_")
+    r = subprocess.run([MT_DEC_DRIVER, lib, str(threads), "1", prefix] + files, capture_output=True, text=True, env=env, timeout=600)
+    pics = [open(prefix + "%d.yuv" % t, "rb").read() if os.path.exists(prefix + "%d.yuv" % t) else b"" for t in range(threads)]
+    return r, pics
+
+
+@need_built
+def test_mt_decoder_driver_with_reference(tmp_path):
+    """the multi-object decoder application itself, with the compiled reference: every thread reproduces the published pictures"""
+    r, pics = drive_mt_dec(REFLIB, QCIF_STREAMS[:2], 3, str(tmp_path), "ref")
+    assert r.returncode == 0, r.stderr
+    import hashlib, json
+    gold = {os.path.basename(k): v for k, v in json.load(open(os.path.join(ROOT, "tests", "golden", "reference_decoder_hashes.json")))["pairs"]}
+    for t, p in enumerate(pics):
+        assert hashlib.sha1(p).hexdigest() == gold[QCIF_STREAMS[t % 2]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("threads,slots", [(6, None), (7, 4), (12, 16)])
+def test_broker_many_decoder_objects_one_batch(tmp_path, threads, slots):
+    """T application threads, each with its own ISVCDecoder, decode six different QCIF conformance streams NAL by NAL: the objects
+    are streams of shared batched GPU decoders (one pool per picture size, several pools when the slots run out); every thread
+    must get exactly the pictures the reference gives it — streams of different length, slice structure and reference-frame
+    count in ONE batch, objects dropping out as their files end."""
+    assert os.path.exists(MT_DEC_DRIVER) and os.path.exists(OURLIB), "prebuilt layer-3 artefacts missing on the GPU box"
+    r0, p0 = drive_mt_dec(REFLIB, QCIF_STREAMS, threads, str(tmp_path), "ref")
+    r1, p1 = drive_mt_dec(OURLIB, QCIF_STREAMS, threads, str(tmp_path), "b2", slots)
+    assert r0.returncode == 0 and r1.returncode == 0, r0.stderr + r1.stderr
+    for t in range(threads):
+        assert len(p0[t]) > 0 and p0[t] == p1[t], "thread %d (%s)" % (t, QCIF_STREAMS[t % len(QCIF_STREAMS)])

@@ -37,6 +37,7 @@ struct b2h264_enc {
   cudaStream_t st = nullptr;        // kernels (may be the caller's stream, b2h264_enc_set_stream)
   cudaStream_t st_in = nullptr;     // source uploads: overlap the previous picture's kernels
   cudaStream_t st_out = nullptr;    // record downloads: overlap deblocking and the next picture's kernels
+  cudaStream_t st_dbk = nullptr;    // the deblocking CTAs that are resident beside the encode kernel (enc_kernels.cu: k_deblock_rows<4, 16>)
   // device memory
   uint8_t* d_cur = nullptr;               // 2 x S x (Y,U,V) MB-aligned source pictures (current / previous: VAA statistics)
   int32_t* d_vaa = nullptr;               // S x n_mb x 4: 8x8 SADs against the previous source picture (LOW_COMPLEXITY)
@@ -67,7 +68,7 @@ struct b2h264_enc {
   const uint8_t** h_srcptr[2] = {nullptr, nullptr};
   // in-flight bookkeeping
   struct Slot { bool busy = false; std::vector<uint8_t> idr; std::vector<int> act;   // act: streams of this batch (compact order)
-                cudaEvent_t ev0, ev1, ev2, done, in_done, enc_done; };
+                cudaEvent_t ev0, ev1, ev2, done, in_done, enc_done, ev_ready, ev_dbk; };
   Slot slot[2];
   int submit_idx = 0, collect_idx = 0;
   std::vector<std::vector<uint8_t>> bs;   // per stream output of the last collect
@@ -117,6 +118,7 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
   const size_t S = e->S;
   CK(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&e->st_in, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&e->st_dbk, cudaStreamNonBlocking));
   {
     int lo = 0, hi = 0;                       // record hand-over runs behind the kernels of the pictures
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -147,6 +149,8 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
     CK(cudaEventCreateWithFlags(&e->slot[i].done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->slot[i].in_done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&e->slot[i].enc_done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->slot[i].ev_ready, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->slot[i].ev_dbk, cudaEventDisableTiming));
   }
   // TMA descriptors of the two picture sets: (x, y) from the padded origin of the luma plane, z = stream
   e->have_tmap = b2h264_make_tmap_planes(e->tmap_pic, e->d_pic_all, (uint64_t)c0.rec_stride_y(), (uint64_t)c0.rec_rows_y(), 2 * (uint64_t)S,
@@ -183,10 +187,10 @@ void b2h264_enc_destroy(b2h264_enc* e) {
   for (int i = 0; i < 2; i++) {
     cudaFree(e->d_rinfo[i]); cudaFree(e->d_out[i]); cudaFree(e->d_sf[i]); cudaFree(e->d_srcptr[i]);
     cudaFreeHost(e->h_out[i]); cudaFreeHost(e->h_idx[i]); cudaFreeHost(e->h_cnt[i]); cudaFreeHost(e->h_sf[i]); cudaFreeHost(e->h_srcptr[i]);
-    cudaEventDestroy(e->slot[i].ev0); cudaEventDestroy(e->slot[i].ev1); cudaEventDestroy(e->slot[i].ev2); cudaEventDestroy(e->slot[i].done); cudaEventDestroy(e->slot[i].in_done); cudaEventDestroy(e->slot[i].enc_done);
+    cudaEventDestroy(e->slot[i].ev0); cudaEventDestroy(e->slot[i].ev1); cudaEventDestroy(e->slot[i].ev2); cudaEventDestroy(e->slot[i].done); cudaEventDestroy(e->slot[i].in_done); cudaEventDestroy(e->slot[i].enc_done); cudaEventDestroy(e->slot[i].ev_ready); cudaEventDestroy(e->slot[i].ev_dbk);
   }
   if (e->own_stream) cudaStreamDestroy(e->st);
-  cudaStreamDestroy(e->st_in); cudaStreamDestroy(e->st_out);
+  cudaStreamDestroy(e->st_in); cudaStreamDestroy(e->st_out); if (e->st_dbk) cudaStreamDestroy(e->st_dbk);
   delete e;
 }
 
@@ -262,10 +266,10 @@ int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_devic
   CK(cudaMemcpyAsync(e->d_srcptr[k], e->h_srcptr[k], n * sizeof(uint8_t*), cudaMemcpyHostToDevice, e->st));
   CK(cudaEventRecord(sl.ev0, e->st));
   int rc = enc_launch_frame(e->d_sf[k], e->d_srcptr[k], n, e->cfg.width, e->cfg.height, mbw, mbh, e->d_tickets, e->d_stash,
-                            e->have_tmap ? e->tmap_pic : nullptr, e->d_tmap, e->cfg.complexity_low != 0, e->st);
+                            e->have_tmap ? e->tmap_pic : nullptr, e->d_tmap, e->cfg.complexity_low != 0, e->st, e->st_dbk, sl.ev_ready, sl.ev_dbk);
   if (rc) return rc;
   CK(cudaEventRecord(sl.ev1, e->st));
-  rc = enc_launch_deblock_expand(e->d_sf[k], n, mbw, mbh, e->d_tickets, e->st);
+  rc = enc_launch_deblock_expand(e->d_sf[k], n, mbw, mbh, e->d_tickets, e->st, sl.ev_dbk);
   if (rc) return rc;
   CK(cudaEventRecord(sl.ev2, e->st));
   // the macroblock records are final once the encode kernel is done (deblocking does not touch them)

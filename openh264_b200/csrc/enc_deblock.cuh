@@ -78,7 +78,8 @@ MBK_HD void deblock_one_mb(const EncFrameParams& p, const EncFramePtrs& f, int m
     const int nidx[3] = {idx, mbx > 0 ? idx - 1 : idx, mby > 0 ? idx - p.mb_w : idx};
     for (int i = lane_id(); i < 3 * kW; i += MBK_WS) {
       const int k = i / kW, w = i - k * kW;
-      reinterpret_cast<uint32_t*>(&t.m[k])[w] = reinterpret_cast<const uint32_t*>(f.mbi + nidx[k])[w];
+      // through L2 like the samples: the records of macroblocks that are still being coded share cache lines with these
+      reinterpret_cast<uint32_t*>(&t.m[k])[w] = dbk_ld32(reinterpret_cast<const uint8_t*>(f.mbi + nidx[k]) + 4 * w);
     }
   }
   warp_sync();

@@ -147,6 +147,8 @@ struct EncSched {
   int* queue;        // NQ ready lists of capacity `total` each, -1 = slot not yet written
   int* ctl;          // one 128-byte line per ready list: [32 k] head, [32 k + 1] tail; line NQ: [32 NQ] macroblocks finished
   uint4* stash;      // parked scratches
+  int* rowprog;      // per (stream, macroblock row): macroblocks finished (rows complete left to right) — the deblocking kernel that
+                     // runs beside this one follows it
 };
 // The control words are spread over NQ + 1 lines (different L2 slices): every finished macroblock, every push and every
 // scheduler look / claim of 148 CTAs used to hit ONE line, and the queueing there slowed the workers' own atomics.
@@ -225,6 +227,7 @@ __device__ __forceinline__ void run_task(const StreamFrame* sf, const EncSched& 
       if (nr && r0 + 1 == 1 + (y > 0)) esched_push(q, total, first, id + 1);
       if (nbl && r1 + 1 == 1 + (x - 1 > 0)) esched_push(q, total, first, id + mb_w - 1);
       if (nb && r2 + 1 == 1 + (x > 0)) esched_push(q, total, first, id + mb_w);
+      if (q.rowprog) atomicAdd(q.rowprog + si * mb_h + y, 1);
       atomicAdd(ctl_done(q), 1);
     }
   } else {
@@ -413,8 +416,10 @@ __device__ __forceinline__ MbScratch& my_scratch(uint8_t* smem) {
 // search window out of it with one bulk tensor copy per macroblock (enc_inter.cuh: win_issue / win_wait)
 __global__ void __launch_bounds__(kEncThreads, ENC_MIN_CTAS) k_encode_mbs(const StreamFrame* __restrict__ sf, int n_streams, EncSched q, int stats,
                                                                           const __grid_constant__ CUtensorMap tm_ref, const void* tm_global,
-                                                                          int win_mode /* 0 none, 1 TMA (descriptor = kernel parameter), 2 warp loads, 3 TMA (descriptor in global memory) */) {
+                                                                          int win_mode /* 0 none, 1 TMA (descriptor = kernel parameter), 2 warp loads, 3 TMA (descriptor in global memory) */,
+                                                                          int* started /* tells the resident deblocking CTAs that this kernel is running */) {
   extern __shared__ __align__(128) uint8_t smem[];
+  if (threadIdx.x == 0 && started) *reinterpret_cast<volatile int*>(started) = 1;
   __shared__ WinBar s_wbar[ENC_WPC];
   MbScratch& s = my_scratch(smem);
   WinBar* wb = &s_wbar[min((int)(threadIdx.x >> 5), ENC_WPC - 1)];
@@ -439,6 +444,7 @@ __global__ void __launch_bounds__(kEncThreads, ENC_MIN_CTAS) k_encode_mbs(const 
     }
     return next;
   });
+  if (threadIdx.x == 0 && started) reinterpret_cast<volatile int*>(started)[1] = 1;      // (every CTA leaves when all macroblocks are coded)
 }
 
 // In-loop deblocking: ONE WARP PER MACROBLOCK ROW.  The tasks are short and uniform (a few microseconds each), so the
@@ -447,9 +453,39 @@ __global__ void __launch_bounds__(kEncThreads, ENC_MIN_CTAS) k_encode_mbs(const 
 // its row left to right and only has to stay two macroblocks behind the row above (MB(x, y) needs (x - 1, y) — the warp's own
 // previous step — and (x + 1, y - 1)); progress is one int per row.  Rows are handed out row-major over the streams (all
 // rows 0 first), so a row is only ever claimed after the row it waits for: no deadlock whatever the number of resident warps.
+// Two instantiations.  <8, 6>: the full-size grid (6 CTAs of 8 warps per SM), launched behind the encode kernel.
+// <4, 16>: an EXPERIMENT (B2H264_RESIDENT_DEBLOCK=1), kept because its result is instructive: ONE 4-warp CTA per SM at <= 32
+// registers, sized to be resident BESIDE the encode kernel's CTA (768 threads x 80 registers leave 4096 registers and ~9 KB of
+// shared memory per SM).  Launched with k_encode_mbs it follows the encode wavefront through `enc_prog` (macroblock (x, y) may be
+// filtered once (x + 1, y + 1) is coded: nothing reads its unfiltered samples any more); both instantiations draw rows from
+// the same counter, so the full-size grid finishes what the resident CTAs have not claimed.  It works (bit-exact, sanitizer
+// clean, steps aside where kernels are serialised) and it does hide the filter — deblock + expand 8.0 -> 4.4 ms per 256 pictures —
+// but the encode kernel beside it takes 73.2 ms instead of 50.7: a fifth instruction stream on every SM evicts the lock-step
+// batch's code from the instruction caches, the same effect as splitting the batch (profiles/r02_encode_variants.txt).
+// Net 78.8 against 59.5 ms per step (gpurun_out/rv -> profiles/r02_bench_lines.txt): off by default.
 #define DBK_WPC 8
-__global__ void __launch_bounds__(32 * DBK_WPC, 6) k_deblock_rows(const StreamFrame* __restrict__ sf, int n_streams, int* prog, int* counter) {
-  __shared__ DbkTile tiles[DBK_WPC];
+#define DBK_CO_WPC 4
+template <int WPC, int MIN_CTAS>
+__global__ void __launch_bounds__(32 * WPC, MIN_CTAS) k_deblock_rows(const StreamFrame* __restrict__ sf, int n_streams, int* prog, int* counter,
+                                                                      const int* enc_prog /* NULL: every macroblock is coded already */,
+                                                                      const int* enc_started /* resident form only, see below */) {
+  __shared__ DbkTile tiles[WPC];
+  // The resident form waits for a kernel that runs AT THE SAME TIME.  Where kernels are serialised (compute-sanitizer, ncu replay,
+  // a debugger) that kernel cannot start while this one spins: a CTA that does not see the encode kernel running within ~0.3 ms leaves
+  // without claiming a row, and the full-size grid launched behind the encode kernel does all the work.
+  if (enc_started != nullptr) {
+    __shared__ int s_go;
+    if (threadIdx.x == 0) {
+      int go = 0;
+      for (int i = 0; i < 300 && !(go = ld_volatile(enc_started)); i++) __nanosleep(1000);
+      // ... and one that only starts when the encode kernel is already DONE (serialised after it) leaves too: the full-size grid
+      // behind it is the faster way through the rows then
+      if (go && ld_volatile(enc_started + 1)) go = 0;
+      s_go = go;
+    }
+    __syncthreads();
+    if (!s_go) return;
+  }
   DbkTile& t = tiles[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int mb_w = sf[0].p.mb_w, mb_h = sf[0].p.mb_h, units = n_streams * mb_h;
@@ -462,12 +498,17 @@ __global__ void __launch_bounds__(32 * DBK_WPC, 6) k_deblock_rows(const StreamFr
     const StreamFrame& F = sf[si];
     int* mine = prog + si * mb_h + row;
     const int* up = mine - 1;
-    int seen = row > 0 ? 0 : mb_w;
+    const int* coded = enc_prog ? enc_prog + si * mb_h + (row + 1 < mb_h ? row + 1 : row) : nullptr;
+    int seen = row > 0 ? 0 : mb_w, seen_enc = coded ? 0 : mb_w;
     for (int x = 0; x < mb_w; x++) {
       const int need = x + 2 < mb_w ? x + 2 : mb_w;
-      if (seen < need) {
-        if (lane == 0) while ((seen = ld_volatile(up)) < need) __nanosleep(40);
+      if (seen < need || seen_enc < need) {
+        if (lane == 0) {
+          while (seen < need && (seen = ld_volatile(up)) < need) __nanosleep(40);
+          while (seen_enc < need && (seen_enc = ld_volatile(coded)) < need) __nanosleep(200);
+        }
         seen = __shfl_sync(MBK_FULL, seen, 0);
+        seen_enc = __shfl_sync(MBK_FULL, seen_enc, 0);
         __threadfence();
       }
       deblock_one_mb(F.p, F.f, x, row, t);
@@ -572,7 +613,8 @@ static int dec_grid_blocks() {
 // scheduler workspace layout (ints): [0..3] head/tail of the deblock list; from 32: dep[2][total] (encode, deblock), then
 // queue[1 + NQ][total] (deblock list, encode lists); then, 128-byte aligned, the encode lists' control lines (kCtlInts)
 static size_t enc_ctl_offset(size_t total) { return (32 + (3 + NQ) * total + 31) / 32 * 32; }       // 128-byte aligned, behind the lists
-size_t enc_sched_ints(int n_streams, int n_mb) { return enc_ctl_offset((size_t)n_streams * n_mb) + kCtlInts; }
+// ... then the coded-rows counters the deblocking kernels follow (n_streams * mb_h ints; n_streams * n_mb reserved)
+size_t enc_sched_ints(int n_streams, int n_mb) { return enc_ctl_offset((size_t)n_streams * n_mb) + kCtlInts + (size_t)n_streams * n_mb; }
 size_t enc_stash_bytes(int n_streams, int mb_h) { return (size_t)n_streams * mb_h * kStashU4 * sizeof(uint4); }
 
 static Sched make_sched(int* ws, int which, int total) {
@@ -589,11 +631,12 @@ static EncSched make_esched(int* ws, int total, void* stash) {
   q.dep = ws + 32;
   q.queue = ws + 32 + (size_t)3 * total;
   q.stash = reinterpret_cast<uint4*>(stash);
+  q.rowprog = nullptr;
   return q;
 }
 
-// prog: n_streams * mb_h progress counters, zero; counter: the row hand-out counter (zeroed here)
-static int launch_deblock_rows(const StreamFrame* d_sf, int n_streams, int mb_h, int* prog, int* counter, cudaStream_t st) {
+// prog: n_streams * mb_h progress counters, zero; counter: the row hand-out counter (zeroed by the caller)
+static int launch_deblock_rows(const StreamFrame* d_sf, int n_streams, int mb_h, int* prog, int* counter, const int* enc_prog, cudaStream_t st) {
   static int per_dev[64];
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -601,19 +644,39 @@ static int launch_deblock_rows(const StreamFrame* d_sf, int n_streams, int mb_h,
   if (!per_dev[dev]) {
     int per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_deblock_rows, 32 * DBK_WPC, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_deblock_rows<DBK_WPC, 6>, 32 * DBK_WPC, 0);
     per_dev[dev] = sms * (per_sm < 1 ? 1 : per_sm);
   }
-  cudaMemsetAsync(counter, 0, sizeof(int), st);
   const int units = n_streams * mb_h;
   int blocks = per_dev[dev];
   if (blocks > (units + DBK_WPC - 1) / DBK_WPC) blocks = (units + DBK_WPC - 1) / DBK_WPC;
-  k_deblock_rows<<<blocks, 32 * DBK_WPC, 0, st>>>(d_sf, n_streams, prog, counter);
+  k_deblock_rows<DBK_WPC, 6><<<blocks, 32 * DBK_WPC, 0, st>>>(d_sf, n_streams, prog, counter, enc_prog, nullptr);
+  return b2h264_launched();
+}
+// the resident companion of the encode kernel: one small CTA per SM
+static int launch_deblock_rows_resident(const StreamFrame* d_sf, int n_streams, int mb_h, int* prog, int* counter, const int* enc_prog,
+                                        const int* enc_started, cudaStream_t st) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // An SM changes its L1 / shared-memory split only when it is empty.  Should one of these CTAs ever reach an SM before the encode
+  // kernel's CTA, it must leave the SM configured for the encoder's 186 KB — otherwise the encoder could not join it and this CTA
+  // would wait for an encoder that waits for the SM to drain (seen as a hang when this kernel was launched FIRST).
+  static bool carve_set[64];
+  if (dev >= 0 && dev < 64 && !carve_set[dev]) {
+    cudaFuncSetAttribute(k_deblock_rows<DBK_CO_WPC, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    carve_set[dev] = true;
+  }
+  const int units = n_streams * mb_h;
+  int blocks = sms;
+  if (blocks > (units + DBK_CO_WPC - 1) / DBK_CO_WPC) blocks = (units + DBK_CO_WPC - 1) / DBK_CO_WPC;
+  k_deblock_rows<DBK_CO_WPC, 16><<<blocks, 32 * DBK_CO_WPC, 0, st>>>(d_sf, n_streams, prog, counter, enc_prog, enc_started);
   return b2h264_launched();
 }
 
 int enc_launch_frame(const StreamFrame* d_sf, const uint8_t* const* d_src, int n_streams, int w, int h, int mb_w, int mb_h,
-                     int* d_ws, void* d_stash, const void* tmap_ref, const void* d_tmap, int fast_mode, cudaStream_t st) {
+                     int* d_ws, void* d_stash, const void* tmap_ref, const void* d_tmap, int fast_mode, cudaStream_t st,
+                     cudaStream_t st_dbk, cudaEvent_t ev_ready, cudaEvent_t ev_dbk) {
   int rc;
   if (d_src) {
     dim3 b(32, 8), g((mb_w * 4 + 31) / 32, (mb_h * 16 + 7) / 8, n_streams);
@@ -628,10 +691,17 @@ int enc_launch_frame(const StreamFrame* d_sf, const uint8_t* const* d_src, int n
   const int total = n_streams * mb_w * mb_h;
   cudaMemsetAsync(d_ws + 32, 0, 2 * (size_t)total * sizeof(int), st);                                     // dep counters
   cudaMemsetAsync(d_ws + 32 + 2 * (size_t)total, 0xff, (size_t)(1 + NQ) * total * sizeof(int), st);       // ready lists
-  const Sched qd = make_sched(d_ws, 1, total);
-  const EncSched qe = make_esched(d_ws, total, d_stash);
+  EncSched qe = make_esched(d_ws, total, d_stash);
+  // progress counters: rows deblocked in the deblocking list's (zeroed) counter area, rows coded behind the control lines
+  int* dbk_prog = d_ws + 32 + (size_t)total;
+  static const bool resident_dbk = getenv("B2H264_RESIDENT_DEBLOCK") != nullptr;     // experiment, off: see k_deblock_rows
+  const bool co = resident_dbk && st_dbk != nullptr;
+  if (co) {                                          // the coded-rows counters are only kept for the resident deblocking CTAs
+    qe.rowprog = d_ws + enc_ctl_offset((size_t)total) + kCtlInts;
+    cudaMemsetAsync(qe.rowprog, 0, (size_t)n_streams * mb_h * sizeof(int), st);
+  }
   k_esched_init<<<1, 32, 0, st>>>(qe, d_sf, n_streams, mb_w * mb_h);
-  k_sched_init<<<(n_streams + 127) / 128, 128, 0, st>>>(qd, n_streams, mb_w * mb_h);
+  cudaMemsetAsync(d_ws + 2, 0, 3 * sizeof(int), st);               // the deblocking row hand-out counter; [3] = "the encode kernel is running", [4] = "... has finished"
   int blocks = enc_grid_blocks();
   const int need = (total + ENC_WPC - 1) / ENC_WPC;
   if (blocks > need) blocks = need;
@@ -645,17 +715,26 @@ int enc_launch_frame(const StreamFrame* d_sf, const uint8_t* const* d_src, int n
   if ((win_mode == 1 || win_mode == 3) && tmap_ref == nullptr) win_mode = 2;
   if (win_mode == 3 && d_tmap == nullptr) win_mode = 2;
   if (win_mode == 1) memcpy(&tm, tmap_ref, sizeof(tm));
-  k_encode_mbs<<<blocks, kEncThreads, kScratchSmem, st>>>(d_sf, n_streams, qe, stats, tm, d_tmap, win_mode);
+  if (co && cudaEventRecord(ev_ready, st) != cudaSuccess) return (int)cudaGetLastError();
+  k_encode_mbs<<<blocks, kEncThreads, kScratchSmem, st>>>(d_sf, n_streams, qe, stats, tm, d_tmap, win_mode, co ? d_ws + 3 : nullptr);
   if ((rc = b2h264_launched())) return rc;
+  if (co) {
+    // the resident deblocking CTAs are launched BEHIND the encode kernel (its CTAs take their SMs first) and follow its wavefront
+    if (cudaStreamWaitEvent(st_dbk, ev_ready, 0) != cudaSuccess) return (int)cudaGetLastError();
+    if ((rc = launch_deblock_rows_resident(d_sf, n_streams, mb_h, dbk_prog, d_ws + 2, qe.rowprog, d_ws + 3, st_dbk))) return rc;
+    if (cudaEventRecord(ev_dbk, st_dbk) != cudaSuccess) return (int)cudaGetLastError();
+  }
   return 0;
 }
 
-int enc_launch_deblock_expand(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h, int* d_ws, cudaStream_t st) {
+int enc_launch_deblock_expand(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h, int* d_ws, cudaStream_t st, cudaEvent_t ev_dbk) {
   int rc;
   const int total = n_streams * mb_w * mb_h;
-  (void)total;
-  if ((rc = launch_deblock_rows(d_sf, n_streams, mb_h, d_ws + 32 + (size_t)total /* the deblocking list's counters: zeroed per picture */, d_ws + 2, st))) return rc;
-  if ((rc = b2h264_launched())) return rc;
+  int* dbk_prog = d_ws + 32 + (size_t)total;      // the deblocking list's counters: zeroed per picture (enc_launch_frame)
+  // the full-size grid takes the rows the resident CTAs have not claimed (same hand-out counter, same progress words)
+  static const bool resident_dbk = getenv("B2H264_RESIDENT_DEBLOCK") != nullptr;     // experiment, off: see k_deblock_rows
+  if ((rc = launch_deblock_rows(d_sf, n_streams, mb_h, dbk_prog, d_ws + 2, resident_dbk ? d_ws + enc_ctl_offset((size_t)total) + kCtlInts : nullptr, st))) return rc;
+  if (resident_dbk && ev_dbk && cudaStreamWaitEvent(st, ev_dbk, 0) != cudaSuccess) return (int)cudaGetLastError();
   k_expand_lr_batch<<<dim3((mb_h * 16 + 7) / 8, 1, 3 * n_streams), dim3(32, 8), 0, st>>>(d_sf);
   if ((rc = b2h264_launched())) return rc;
   k_expand_tb_batch<<<dim3((mb_w * 16 + 64 + 127) / 128, 4, 3 * n_streams), dim3(128), 0, st>>>(d_sf);
@@ -685,7 +764,8 @@ int dec_launch_frame(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h,
   k_decode_mbs<<<blocks_per_launch < need ? blocks_per_launch : need, 32 * DEC_WPC, kScratchSmem, st>>>(d_sf, n_streams, qc, d_recs, d_aux);
   if ((rc = b2h264_launched())) return rc;
   if (deblock) {
-    if ((rc = launch_deblock_rows(d_sf, n_streams, mb_h, d_ws + 8 + (size_t)total, d_ws + 2, st))) return rc;
+    cudaMemsetAsync(d_ws + 2, 0, sizeof(int), st);
+    if ((rc = launch_deblock_rows(d_sf, n_streams, mb_h, d_ws + 8 + (size_t)total, d_ws + 2, nullptr, st))) return rc;
   }
   k_expand_lr_batch<<<dim3((mb_h * 16 + 7) / 8, 1, 3 * n_streams), dim3(32, 8), 0, st>>>(d_sf);
   if ((rc = b2h264_launched())) return rc;

@@ -632,6 +632,7 @@ MBK_HD void st_save(MbScratch& s, int is_skip, int cost_luma, int cost_skip_mb, 
 MBK_STAGE int inter_stage_a(const MbCtx& c, MbScratch& s) {
   const int mbw = c.p.mb_w, idx = c.mby * mbw + c.mbx;
   fill_inter_cache(c, s);
+  mbk_batch_sync(5, c.batch_n);                        // stage A: together again behind the load phase
   phase_mark(s, 1);
   const int ref_mb_type = c.p.ref_is_p ? c.f.ref_info[idx].mb_type : 0xff;
   int p16_mvx = 0, p16_mvy = 0;                       // sP16x16Mv / sMvList (WelsMdInterInit :352-353)
@@ -653,6 +654,7 @@ MBK_STAGE int inter_stage_a(const MbCtx& c, MbScratch& s) {
       mb_mv_set(s, 0, 4, 4, r.mvx, r.mvy);
     }
   }
+  mbk_batch_sync(6, c.batch_n);                        // ... and behind the skip test
   phase_mark(s, 2);
   if (is_skip && keep_skip) {
     decided_pskip(c, s);
@@ -706,6 +708,7 @@ MBK_STAGE int inter_stage_b(const MbCtx& c, MbScratch& s) {
     win_wait(c, s);
   }
   int plan[3] = {0, 0, 0}, n_plan = 0, cost = 0;       // shapes: 0 = 16x16, 1 = 16x8, 2 = 8x16, 3 = 8x8
+  int rounds_run = 0;
   MBK_NO_UNROLL
   for (int t = -1; t < n_plan; t++) {
     const int shape = t < 0 ? 0 : plan[t];
@@ -726,6 +729,8 @@ MBK_STAGE int inter_stage_b(const MbCtx& c, MbScratch& s) {
       }
     }
     if (t >= 0) {
+      mbk_batch_sync(7 + t, c.batch_n_fine);             // finer re-alignment: behind every shape's searches (rounds not run: see below)
+      rounds_run = t + 1;
       // the first shape of the plan has to beat 16x16, a later one only the best so far (<=: md.cpp keeps the later shape on a tie)
       if (t == 0) { if (cst < cost_luma) { cost = cst; final_type = shape == 3 ? MBT_P8x8 : shape == 1 ? MBT_P16x8 : MBT_P8x16; } else break; }
       else if (cst <= cost) { cost = cst; final_type = shape == 1 ? MBT_P16x8 : MBT_P8x16; }
@@ -733,6 +738,7 @@ MBK_STAGE int inter_stage_b(const MbCtx& c, MbScratch& s) {
     }
     // ---- after the 16x16 round ----
     if (!is_skip) { p16_mvx = me16.mv_x; p16_mvy = me16.mv_y; cost_luma = cst; }
+    if (!is_skip) mbk_batch_sync(2, c.batch_n);                         // list B: together again after the 16x16 search
     phase_mark(s, 3);
     {
       // intra check (WelsMdFirstIntraMode :1829)
@@ -743,6 +749,10 @@ MBK_STAGE int inter_stage_b(const MbCtx& c, MbScratch& s) {
         st_save(s, is_skip ? 1 : 0, cost_luma, cost_skip_mb, p16_mvx, p16_mvy, final_type);
         if (lane_id() == 0) { s.st.cost16 = cost16; s.st.bb = bb; }
         warp_sync();
+        if (!is_skip) {
+          mbk_batch_leave(3, c.batch_n); mbk_batch_leave(4, c.batch_n);
+          for (int r = 0; r < 3; r++) mbk_batch_leave(7 + r, c.batch_n_fine);
+        }
         return MBS_C;
       }
     }
@@ -770,6 +780,8 @@ MBK_STAGE int inter_stage_b(const MbCtx& c, MbScratch& s) {
     else { plan[0] = 3; plan[1] = 1; plan[2] = 2; n_plan = 3; }
   }
   {
+    for (int r = rounds_run; r < 3; r++) mbk_batch_leave(7 + r, c.batch_n_fine);   // the shapes this macroblock did not search
+    mbk_batch_sync(3, c.batch_n);                                            // ... after the sub-partition searches
     phase_mark(s, 6);
     // refinement (WelsMdInterMbRefinement :1573)
     uint8_t* pl = s.pred_y[0];
@@ -806,6 +818,7 @@ MBK_STAGE int inter_stage_b(const MbCtx& c, MbScratch& s) {
         cost_skip_mb = warp_sad(s.cur_y, 16, pl, 16, 4, 4) + warp_sad(s.cur_c, 8, pc, 8, 3, 3) + warp_sad(s.cur_c + 64, 8, pc + 64, 8, 3, 3);
     }
     if (lane_id() == 0) c.f.sad_cost[idx] = best_sad;          // pCurMb->pSadCost[0]
+    mbk_batch_sync(4, c.batch_n);                                            // ... and after the refinement
     phase_mark(s, 7);
     // step 7: residual coding (WelsMdInterEncode :1964)
     if (lane_id() == 0) s.info.cbp = 0;

@@ -196,7 +196,7 @@ extern "C" int b2h264_debug_batch_stats(unsigned long long* out, int reset) {
 // one task: (continue) macroblock `id` at `stage`; notify the dependants or park it for its next stage
 template <class Body>
 __device__ __forceinline__ void run_task(const StreamFrame* sf, const EncSched& q, MbScratch& s, int id, int stage, int mb_w, int mb_h,
-                                         int total, Body& body) {
+                                         int total, int batch_n, Body& body) {
   const int lane = threadIdx.x & 31, n_mb = mb_w * mb_h;
   __threadfence();
   const int si = id / n_mb, mb = id - si * n_mb, y = mb / mb_w, x = mb - y * mb_w;
@@ -211,7 +211,7 @@ __device__ __forceinline__ void run_task(const StreamFrame* sf, const EncSched& 
     }
     __syncwarp();
   }
-  const int next = body(sf[si], x, y, stage);
+  const int next = body(sf[si], x, y, stage, batch_n);
   __syncwarp();
   if (next == MBS_DONE) {
     __threadfence();
@@ -360,7 +360,7 @@ __device__ __forceinline__ void run_stages(const StreamFrame* sf, int n_streams,
     if (warp < n) {
       const long long t_task = stats ? clock64() : 0;
       const int id = s_ids[p][warp];
-      run_task(sf, q, s, id, k + 1, mb_w, mb_h, total, body);
+      run_task(sf, q, s, id, k + 1, mb_w, mb_h, total, n, body);
       if (lane == 0) atomicAdd(&s_fin[p], 1);
       if (stats && lane == 0) { atomicAdd(&g_task_wall[k][0], (unsigned long long)(clock64() - t_task)); atomicAdd(&g_task_wall[k][1], 1ull); }
     }
@@ -431,10 +431,10 @@ __global__ void __launch_bounds__(kEncThreads, ENC_MIN_CTAS) k_encode_mbs(const 
   __syncthreads();
   const void* tmap = win_mode == 1 ? (const void*)&tm_ref : win_mode == 3 ? tm_global : nullptr;
   const int wmode = win_mode == 3 ? 1 : win_mode;
-  run_stages(sf, n_streams, q, s, stats & 1, (stats & 4) != 0, [&](const StreamFrame& F, int x, int y, int stage) {
+  run_stages(sf, n_streams, q, s, stats & 1, (stats & 4) != 0, [&](const StreamFrame& F, int x, int y, int stage, int batch_n) {
     const long long t0 = (stats & 1) ? clock64() : 0;
     mb_ctx(s.ctx, F.p, F.f, x, y);
-    if ((threadIdx.x & 31) == 0) { s.ctx.tmap_ref = tmap; s.ctx.wbar = wb; s.ctx.win_mode = wmode; }
+    if ((threadIdx.x & 31) == 0) { s.ctx.tmap_ref = tmap; s.ctx.wbar = wb; s.ctx.win_mode = wmode; s.ctx.batch_n = (stats & (stage == MBS_A ? 16 : 8)) ? batch_n : 0; s.ctx.batch_n_fine = (stats & 32) ? batch_n : 0; }
     __syncwarp();
     int next = mb_run_stage(s.ctx, s, stage);
     if (stats & 2) while (next != MBS_DONE) next = mb_run_stage(s.ctx, s, next);      // debugging: all stages in one task
@@ -674,6 +674,13 @@ static int launch_deblock_rows_resident(const StreamFrame* d_sf, int n_streams, 
   return b2h264_launched();
 }
 
+// B2H264_BATCH_SYNC: bit 0 stage B (default: measured +5.5 %), bit 1 stage A (measured: no gain, -1.5 % together with B), bit 2 finer points in stage B
+static int batch_sync_bits() {
+  const char* v = getenv("B2H264_BATCH_SYNC");
+  const int m = v ? atoi(v) : 1;
+  return ((m & 1) ? 8 : 0) | ((m & 2) ? 16 : 0) | ((m & 4) ? 32 : 0);
+}
+
 int enc_launch_frame(const StreamFrame* d_sf, const uint8_t* const* d_src, int n_streams, int w, int h, int mb_w, int mb_h,
                      int* d_ws, void* d_stash, const void* tmap_ref, const void* d_tmap, int fast_mode, cudaStream_t st,
                      cudaStream_t st_dbk, cudaEvent_t ev_ready, cudaEvent_t ev_dbk) {
@@ -705,7 +712,8 @@ int enc_launch_frame(const StreamFrame* d_sf, const uint8_t* const* d_src, int n
   int blocks = enc_grid_blocks();
   const int need = (total + ENC_WPC - 1) / ENC_WPC;
   if (blocks > need) blocks = need;
-  static const int stats = (getenv("B2H264_ENC_STATS") ? 1 : 0) | (getenv("B2H264_FUSE_STAGES") ? 2 : 0) | (getenv("B2H264_LEGACY_CLAIM") ? 4 : 0);
+  static const int stats = (getenv("B2H264_ENC_STATS") ? 1 : 0) | (getenv("B2H264_FUSE_STAGES") ? 2 : 0) | (getenv("B2H264_LEGACY_CLAIM") ? 4 : 0) |
+                           batch_sync_bits();      // 8 / 16: re-alignment points inside stages B / A (mbk_batch_sync)
   CUtensorMap tm;
   memset(&tm, 0, sizeof(tm));
   // B2H264_ENC_WIN: 0 = search out of the plane, 1 = TMA window, descriptor passed as kernel parameter (default),

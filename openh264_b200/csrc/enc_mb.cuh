@@ -21,6 +21,8 @@ struct MbCtx {
   const void* tmap_ref;
   WinBar* wbar;
   int win_mode;                 // 0: search out of the plane; 1: window staged by TMA; 2: window staged by the warp's own loads
+  int batch_n;                  // device: worker warps of the lock-step batch this macroblock runs in (0: no re-alignment points)
+  int batch_n_fine;             // the same for the finer points inside stage B (one per sub-partition shape), 0: off
 };
 
 struct MeState {            // the parts of SWelsME the later steps of a partition need

@@ -38,6 +38,17 @@
 #else
 #define MBK_NO_UNROLL
 #endif
+// Re-alignment points of a lock-step batch (device, experiment B2H264_BATCH_SYNC): the warps of a batch drift apart inside a long
+// stage (different search lengths) and stop sharing instruction-cache fills; a named barrier over the n warps of the batch pulls
+// them together again.  Every warp of the batch passes each point exactly once: mbk_batch_sync waits, a warp that leaves the
+// stage early calls mbk_batch_leave for the points it will not reach.  Barrier ids 2.. (0 = __syncthreads, 1 = the batch barrier).
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ void mbk_batch_sync(int id, int n) { if (n > 1) asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(32 * n) : "memory"); }
+__device__ __forceinline__ void mbk_batch_leave(int id, int n) { if (n > 1) asm volatile("barrier.arrive %0, %1;" ::"r"(id), "r"(32 * n) : "memory"); }
+#else
+inline void mbk_batch_sync(int, int) {}
+inline void mbk_batch_leave(int, int) {}
+#endif
 #ifdef __CUDA_ARCH__
 #define MBK_WS 32
 #else

@@ -399,7 +399,7 @@ def main():
     def timed_run(enc, on_dev, warmup, steps, keep, **kw):
         """pipelined submit/collect (two batches in flight); returns timing + per-stream access units (if keep)"""
         aus = [[] for _ in range(S)] if keep else None
-        kern, d2h = [], []
+        kern, d2h, coded_mbs = [], [], []
         nb = 0
 
         def loop(first, count, timed):
@@ -416,6 +416,7 @@ def main():
                     nb += sum(len(b) for b in bs)
                     kern.append(enc.timing_us())
                     d2h.append(enc.d2h_bytes())
+                    coded_mbs.append(enc.coded_mbs())
         loop(0, warmup, False)                                     # warm-up (includes the IDR pictures)
         torch.cuda.synchronize()
         shard.barrier()
@@ -436,7 +437,7 @@ def main():
         sampler.join(timeout=2)
         dt, pics = shard.job_totals(max(wall, dev), S * steps, device="cuda")   # MAX over ranks / SUM over ranks
         return {"dt": dt, "pictures": pics, "wall": wall, "dev": dev, "bytes": nb, "clocks": sampler.summary(), "kern": kern, "d2h": d2h,
-                "aus": aus}
+                "coded": coded_mbs, "aus": aus}
 
     results = {}
     launches0 = L.b2h264_launch_count()
@@ -505,7 +506,7 @@ def main():
         hsteps = max(4, args.steps // 2)
         r = timed_run(enc, True, 3, hsteps, False, clip_dev=hd, sq=ping_pong(HARD_FRAMES))
         enc.close()
-        coded = (float(np.mean(r["d2h"])) - S * (MBS_PER_FRAME + 1) * 4) / 896.0
+        coded = float(np.mean(r["coded"]))                       # coded (not P_SKIP) macroblocks per step, counted by the host writer
         hard = {"generator": "same synthetic generator, +-%d per-frame noise" % HARD_NOISE, "value": r["pictures"] / r["dt"], "unit": "frames/s",
                 "steps": hsteps, "skip_ratio": 1.0 - coded / (S * MBS_PER_FRAME), "bitstream_kbytes_per_frame": r["bytes"] / (S * hsteps) / 1e3,
                 "encode_kernel_ms": float(np.mean([k[0] for k in r["kern"]])) * 1e-3, "host_entropy_ms": float(np.mean([k[2] for k in r["kern"]])) * 1e-3}
@@ -520,7 +521,7 @@ def main():
         ent = float(np.mean([k[2] for k in res["kern"]])) * 1e-6
         alg = S * MBS_PER_FRAME * ALG_BYTES_PER_MB
         achieved = alg / k_enc / 1e9
-        coded = (float(np.mean(l2["d2h"])) - S * (MBS_PER_FRAME + 1) * 4) / 896.0
+        coded = float(np.mean(l2["coded"]))
         d2h = int(world * np.mean(l2["d2h"]))
         if api and "job_fps" in api:
             e2e = {"value": api["job_fps"], "unit": "frames/s", "h2d_bytes_per_step": world * S * FSZ, "d2h_bytes_per_step": d2h,

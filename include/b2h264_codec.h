@@ -88,6 +88,8 @@ int  b2h264_enc_last_timing (b2h264_enc* e, float* us3);
 /* bytes the device handed to the host for the batch collected last: the index table plus the records of the
  * coded (non P_SKIP) macroblocks, written by the GPU straight into mapped pinned memory */
 int  b2h264_enc_last_d2h_bytes (b2h264_enc* e, unsigned long long* bytes);
+/* statistics: macroblocks of the last collected batch that were coded (not P_SKIP), over all its streams */
+int  b2h264_enc_last_coded_mbs (b2h264_enc* e, unsigned long long* count);
 
 /* makes the encoder issue all its GPU work on the caller's CUDA stream (cudaStream_t as void*), e.g. so
  * that a harness can bracket it with its own events; only while nothing is in flight */

@@ -85,6 +85,7 @@ API = {
     "b2h264_enc_get_recon": [vp, C.c_int, vp],
     "b2h264_enc_last_timing": [vp, C.POINTER(C.c_float)],
     "b2h264_enc_last_d2h_bytes": [vp, C.POINTER(C.c_ulonglong)],
+    "b2h264_enc_last_coded_mbs": [vp, C.POINTER(C.c_ulonglong)],
     "b2h264_dec_create": [vp, C.POINTER(vp)],
     "b2h264_dec_destroy": [vp],
     "b2h264_dec_decode": [vp, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(vp)],
@@ -249,6 +250,12 @@ class BatchEncoder:
         """bytes the device handed over for the batch collected last (index table + coded records)"""
         v = C.c_ulonglong(0)
         check(self.L.b2h264_enc_last_d2h_bytes(self.h, C.byref(v)))
+        return int(v.value)
+
+    def coded_mbs(self):
+        """macroblocks of the batch collected last that were coded (not P_SKIP), over all streams"""
+        v = C.c_ulonglong(0)
+        check(self.L.b2h264_enc_last_coded_mbs(self.h, C.byref(v)))
         return int(v.value)
 
     def set_stream(self, cuda_stream_handle):

@@ -360,6 +360,14 @@ int b2h264_enc_get_mb_bits(b2h264_enc* e, int stream, int32_t* device_bits, int3
   return 0;
 }
 
+// macroblocks of the last collected batch that were coded (not P_SKIP), summed over its streams
+int b2h264_enc_last_coded_mbs(b2h264_enc* e, unsigned long long* count) {
+  if (!e || !count) return -1;
+  unsigned long long n = 0;
+  for (const auto& c : e->ctl) n += (unsigned long long)c.last_coded_mbs;
+  *count = n;
+  return 0;
+}
 int b2h264_enc_last_d2h_bytes(b2h264_enc* e, unsigned long long* bytes) {
   if (!e || !bytes) return -1;
   *bytes = e->last_d2h;

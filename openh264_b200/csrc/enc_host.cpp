@@ -80,6 +80,7 @@ void StreamCtl::write_access_unit_packed(bool idr, const MbOut* packed, const in
   int coded = 0;
   for (int i = 0; i < n; i++) coded += idx[i] >= 0;
   expand_.resize(coded);
+  last_coded_mbs = coded;
   const uint8_t* base = reinterpret_cast<const uint8_t*>(packed);
   int k = 0;
   for (int i = 0; i < n; i++) {

@@ -50,6 +50,7 @@ struct StreamCtl {
   std::vector<const MbOut*> recs_;
   std::vector<MbOut> expand_;               // compact records of the coded macroblocks, expanded for the slice writer
  public:
+  int last_coded_mbs = 0;                   // macroblocks of the last picture that were not P_SKIP (write_access_unit_packed)
 };
 
 // copies a w x h I420 picture into MB-aligned planes; rows/cols beyond the picture are 0 (luma) / 0x80

@@ -41,6 +41,11 @@ typedef struct {
   int32_t sps_pps_id_strategy;  /* eSpsPpsIdStrategy: 0 CONSTANT_ID, 1 INCREASING_ID (the reference's default) */
   int32_t complexity_low;       /* 1: iComplexityMode = LOW_COMPLEXITY (the reference's default: SAD mode costs, VAA-driven
                                  * partition choice, pruned I4x4 search); 0: MEDIUM / HIGH (identical bitstreams for this class) */
+  int32_t entropy_cabac;        /* SEncParamExt::iEntropyCodingModeFlag: 0 CAVLC, 1 CABAC (the host slice writer changes, the
+                                 * macroblock kernel and its records do not) */
+  int32_t profile_idc;          /* SSpatialLayerConfig::uiProfileIdc: 0 unspecified (Baseline, High with CABAC), 66, 77 or 100; resolved
+                                 * as the reference does (encoder_ext.cpp:126-141,652-664): Baseline turns CABAC off, other values
+                                 * count as unspecified.  No High-profile tool is used (no 8x8 transform): only the SPS / PPS change */
 } b2h264_enc_config;
 
 /* returns 0 or a negative b2h264 error / positive cudaError_t */

@@ -100,7 +100,7 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
   e->S = cfg->n_streams;
   e->ctl.resize(e->S);
   for (auto& c : e->ctl) {
-    c.init(cfg->width, cfg->height, cfg->qp, cfg->fps, cfg->target_bitrate);
+    c.init(cfg->width, cfg->height, cfg->qp, cfg->fps, cfg->target_bitrate, cfg->entropy_cabac, cfg->profile_idc);
     c.fast_mode = cfg->complexity_low != 0;
     c.increasing_ids = cfg->sps_pps_id_strategy != 0;
   }
@@ -325,7 +325,7 @@ int b2h264_enc_reset_stream(b2h264_enc* e, int stream) {
   if (e->slot[0].busy || e->slot[1].busy) return -3;
   CK(cudaSetDevice(e->cfg.device));
   e->ctl[stream] = StreamCtl();
-  e->ctl[stream].init(e->cfg.width, e->cfg.height, e->cfg.qp, e->cfg.fps, e->cfg.target_bitrate);
+  e->ctl[stream].init(e->cfg.width, e->cfg.height, e->cfg.qp, e->cfg.fps, e->cfg.target_bitrate, e->cfg.entropy_cabac, e->cfg.profile_idc);
   e->ctl[stream].increasing_ids = e->cfg.sps_pps_id_strategy != 0;
   e->ctl[stream].fast_mode = e->cfg.complexity_low != 0;
   e->ctl[stream].record_mb_bits = e->mb_bits_on;

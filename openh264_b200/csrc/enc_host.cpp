@@ -6,8 +6,15 @@
 
 namespace b2h264 {
 
-void StreamCtl::init(int width, int height, int qp, float fps_, int target_bitrate) {
+void StreamCtl::init(int width, int height, int qp, float fps_, int target_bitrate, int entropy_cabac, int profile_idc) {
   memset(&sp, 0, sizeof(sp));
+  // WelsEncoderApplyProfile... (encoder_ext.cpp:650-668): CAVLC -> Baseline; CABAC -> High unless the layer asks for Main
+  // the reference's resolution of (iEntropyCodingModeFlag, uiProfileIdc) for spatial layer 0: profiles other than Baseline / Main /
+  // High count as unspecified (encoder_ext.cpp:126-141), Baseline turns CABAC off, unspecified becomes High with CABAC and
+  // Baseline without (encoder_ext.cpp:652-664)
+  if (profile_idc != 66 && profile_idc != 77 && profile_idc != 100) profile_idc = 0;
+  sp.entropy_cabac = entropy_cabac != 0 && profile_idc != 66;
+  sp.profile_idc = profile_idc ? profile_idc : (sp.entropy_cabac ? 100 : 66);
   sp.width = width; sp.height = height;
   sp.mb_w = (width + 15) >> 4; sp.mb_h = (height + 15) >> 4;
   sp.num_ref_frames = 1;
@@ -113,7 +120,8 @@ void StreamCtl::write_au(bool idr, const MbOut* const* mbs, std::vector<uint8_t>
   }
   SliceState ss;
   ss.idr = idr; ss.frame_num = frame_num; ss.idr_pic_id = idr_pic_id; ss.qp = sp.qp;
-  write_slice(sp, ss, mbs, &rbsp, record_mb_bits ? &last_mb_bits : nullptr);
+  if (sp.entropy_cabac) write_slice_cabac(sp, ss, mbs, &rbsp);
+  else write_slice(sp, ss, mbs, &rbsp, record_mb_bits ? &last_mb_bits : nullptr);
   append_nal(au, 3, idr ? 5 : 1, rbsp);
   frame_num = (frame_num + 1) & 0x7fff;
   frames_coded++;

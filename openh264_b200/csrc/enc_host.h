@@ -33,7 +33,7 @@ struct StreamCtl {
   bool record_mb_bits = false;              // keep the writer's bits per macroblock of the last picture (parity of the device count)
   std::vector<int32_t> last_mb_bits;
 
-  void init(int width, int height, int qp, float fps_, int target_bitrate);
+  void init(int width, int height, int qp, float fps_, int target_bitrate, int entropy_cabac = 0, int profile_idc = 0);
   bool next_is_idr() const { return force_idr; }
   // geometry of the padded pictures (picture_handle.cpp:60-85: 32-pixel luma padding)
   int rec_stride_y() const { return sp.mb_w * 16 + 64; }

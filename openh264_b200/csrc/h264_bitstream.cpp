@@ -47,18 +47,24 @@ void select_level(StreamParams* sp, float fps, int target_bitrate) {
     break;
   }
   sp->constraint_set3 = false;
-  if (level == 9) { level = 11; sp->constraint_set3 = true; }   // level 1b signalling for Baseline
+  if (level == 9) {                     // level 1b: Baseline / Main signal it as level 1.1 + constraint_set3 (au_set.cpp:530-534), High keeps 9
+    if (sp->profile_idc == 66 || sp->profile_idc == 77) { level = 11; sp->constraint_set3 = true; }
+  }
   sp->level_idc = level;
 }
 
 // ---- parameter sets ---------------------------------------------------------------------------------
 void write_sps(const StreamParams& sp, std::vector<uint8_t>* rbsp) {
   BitWriter w(rbsp);
-  w.put(8, 66);                         // profile_idc: Baseline
-  w.bit(1); w.bit(1); w.bit(0); w.bit(sp.constraint_set3);   // constraint_set0..3
-  w.put(4, 0);
+  // au_set.cpp:269-300: constraint_set0 for Baseline, set1 up to Main; Main / High add set4 = set5 = 1 (frame macroblocks only, no B slices);
+  // High carries chroma_format_idc 1, 8-bit depths, no transform bypass, no scaling matrices
+  w.put(8, (uint32_t)sp.profile_idc);
+  w.bit(sp.profile_idc == 66); w.bit(sp.profile_idc <= 77); w.bit(0); w.bit(sp.constraint_set3);   // constraint_set0..3
+  if (sp.profile_idc == 77 || sp.profile_idc == 100) { w.bit(1); w.bit(1); w.put(2, 0); }
+  else w.put(4, 0);
   w.put(8, (uint32_t)sp.level_idc);
   w.ue((uint32_t)sp.sps_id);            // seq_parameter_set_id
+  if (sp.profile_idc == 100) { w.ue(1); w.ue(0); w.ue(0); w.bit(0); w.bit(0); }
   w.ue(15 - 4);                         // log2_max_frame_num_minus4
   w.ue(2);                              // pic_order_cnt_type
   w.ue((uint32_t)sp.num_ref_frames);
@@ -83,7 +89,7 @@ void write_sps(const StreamParams& sp, std::vector<uint8_t>* rbsp) {
 void write_pps(const StreamParams& sp, std::vector<uint8_t>* rbsp) {
   BitWriter w(rbsp);
   w.ue((uint32_t)sp.pps_id); w.ue((uint32_t)sp.sps_id);   // pps id, sps id
-  w.bit(0);                             // entropy_coding_mode_flag: CAVLC
+  w.bit(sp.entropy_cabac);              // entropy_coding_mode_flag
   w.bit(0);                             // bottom_field_pic_order_in_frame_present_flag
   w.ue(0);                              // num_slice_groups_minus1
   w.ue(0); w.ue(0);                     // num_ref_idx_l0/l1_default_active_minus1

@@ -48,6 +48,8 @@ struct StreamParams {
   bool crop;
   int crop_right, crop_bottom;  // in units of 2 luma samples
   int sps_id, pps_id;           // ids written into the parameter sets / slice headers (paraset_strategy.cpp)
+  int profile_idc = 66;         // 66 Baseline (CAVLC); with CABAC the reference picks High (100) unless the layer asks for Main (77)
+  bool entropy_cabac = false;   // entropy_coding_mode_flag
 };
 
 // level selection (WelsGetLevelIdc, au_set.cpp:51-195; limits = H.264 Table A-1)
@@ -73,5 +75,8 @@ const uint8_t* cbp_me_table(bool intra);
 // mb_bits (optional): bits of macroblock_layer() of every macroblock (0 for P_SKIP; mb_skip_run not included)
 void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* const* recs, std::vector<uint8_t>* rbsp,
                  std::vector<int32_t>* mb_bits = nullptr);
+
+// the same picture through CABAC (entropy_coding_mode_flag = 1): h264_cabac.cpp
+void write_slice_cabac(const StreamParams& sp, const SliceState& ss, const MbOut* const* recs, std::vector<uint8_t>* rbsp);
 
 }  // namespace b2h264

@@ -64,7 +64,6 @@ class B2Encoder : public ISVCEncoder {
     REQUIRE(p->iSpatialLayerNum == 1 && p->iTemporalLayerNum == 1, "more than one spatial/temporal layer");
     REQUIRE(p->iRCMode == RC_OFF_MODE, "iRCMode != RC_OFF_MODE");
     REQUIRE(l.sSliceArgument.uiSliceMode == SM_SINGLE_SLICE, "uiSliceMode != SM_SINGLE_SLICE");
-    REQUIRE(p->iEntropyCodingModeFlag == 0, "CABAC");
     REQUIRE(p->iNumRefFrame == 1 || p->iNumRefFrame == AUTO_REF_PIC_COUNT, "iNumRefFrame != 1");
     REQUIRE(p->uiIntraPeriod == 0, "uiIntraPeriod != 0");
     REQUIRE(p->iLoopFilterDisableIdc == 0 && p->iLoopFilterAlphaC0Offset == 0 && p->iLoopFilterBetaOffset == 0, "loop filter idc/offsets != 0");
@@ -76,7 +75,7 @@ class B2Encoder : public ISVCEncoder {
     REQUIRE(p->bEnableFrameCroppingFlag, "bEnableFrameCroppingFlag false");
     REQUIRE(!p->bEnableSSEI && !p->bSimulcastAVC && !p->bPrefixNalAddingCtrl, "SSEI / simulcast / prefix NAL");
     REQUIRE(p->eSpsPpsIdStrategy == CONSTANT_ID || p->eSpsPpsIdStrategy == INCREASING_ID, "eSpsPpsIdStrategy");
-    REQUIRE(l.uiProfileIdc == PRO_UNKNOWN || l.uiProfileIdc == PRO_BASELINE, "profile != baseline");
+    REQUIRE(l.uiProfileIdc != PRO_SCALABLE_BASELINE && l.uiProfileIdc != PRO_SCALABLE_HIGH, "scalable profile");
     REQUIRE(l.uiLevelIdc == LEVEL_UNKNOWN, "explicit level");
     REQUIRE(!l.bAspectRatioPresent && !l.bVideoSignalTypePresent, "VUI");
     REQUIRE(l.iVideoWidth == p->iPicWidth && l.iVideoHeight == p->iPicHeight, "layer resolution != picture resolution");
@@ -99,6 +98,10 @@ class B2Encoder : public ISVCEncoder {
     key.bitrate = l.iSpatialBitrate ? l.iSpatialBitrate : p->iTargetBitrate;
     key.strategy = p->eSpsPpsIdStrategy == INCREASING_ID ? 1 : 0;
     key.complexity_low = p->iComplexityMode == LOW_COMPLEXITY ? 1 : 0;
+    // CABAC / CAVLC and the profile: layer 2 resolves the pair as the reference does (Baseline forces CAVLC, anything but
+    // Baseline / Main / High counts as unspecified: encoder_ext.cpp:126-141,652-664)
+    key.entropy_cabac = p->iEntropyCodingModeFlag != 0 ? 1 : 0;
+    key.profile_idc = (int)l.uiProfileIdc;
     pool_ = b2wels::Broker::get().attach(key, &slot_);
     if (!pool_ || slot_ < 0) { pool_.reset(); slot_ = -1; return cmMallocMemeError; }
     par_ = *p;

@@ -237,6 +237,11 @@ extern "C" {
  * (1 = single thread, single slice; >1 = that many fixed slices + threads: a speed reference only,
  * it changes the bitstream).  Returns total bytes written to out (or <0 on error); seconds spent in
  * EncodeFrame in *enc_seconds; per-frame byte counts in frame_bytes[n]. */
+/* entropy coder / profile of the following ref_encode calls (0 / 66 = CAVLC Baseline, the default; 1 / 0 = CABAC with the profile the
+ * reference picks itself, i.e. High; 1 / 77 = CABAC Main) */
+static int g_entropy_cabac = 0, g_profile_idc = 66;
+void ref_set_entropy (int cabac, int profile_idc) { g_entropy_cabac = cabac; g_profile_idc = profile_idc; }
+
 long ref_encode (const uint8_t* yuv, int w, int h, int n, int qp, int complexity, int threads, float fps,
                  uint8_t* out, long out_cap, int32_t* frame_bytes, double* enc_seconds) {
   ISVCEncoder* enc = NULL;
@@ -253,7 +258,7 @@ long ref_encode (const uint8_t* yuv, int w, int h, int n, int qp, int complexity
   p.iComplexityMode = (ECOMPLEXITY_MODE) complexity;
   p.uiIntraPeriod = 0;
   p.iNumRefFrame = 1;
-  p.iEntropyCodingModeFlag = 0;
+  p.iEntropyCodingModeFlag = g_entropy_cabac;
   p.bEnableFrameSkip = false;
   p.bEnableLongTermReference = false;
   p.iMultipleThreadIdc = (unsigned short) threads;
@@ -268,7 +273,7 @@ long ref_encode (const uint8_t* yuv, int w, int h, int n, int qp, int complexity
   p.sSpatialLayers[0].fFrameRate = fps;
   p.sSpatialLayers[0].iSpatialBitrate = 5000000;
   p.sSpatialLayers[0].iDLayerQp = qp;
-  p.sSpatialLayers[0].uiProfileIdc = PRO_BASELINE;
+  p.sSpatialLayers[0].uiProfileIdc = (EProfileIdc) g_profile_idc;
   if (threads > 1) {
     p.sSpatialLayers[0].sSliceArgument.uiSliceMode = SM_FIXEDSLCNUM_SLICE;
     p.sSpatialLayers[0].sSliceArgument.uiSliceNum = threads;

@@ -29,6 +29,7 @@ static bool same_record(const MbOut& a, const MbOut& b);
 namespace {
 
 // host-memory twin of the product's device-side frame buffers
+static int g_emu_cabac = 0, g_emu_profile = 0;       // entropy coder of the host writer (the macroblock decisions do not depend on it)
 struct HostFrameEncoder {
   b2h264::StreamCtl ctl;
   EncFrameParams p;
@@ -45,7 +46,7 @@ struct HostFrameEncoder {
   bool idr = true, have_ref_p = false;
 
   HostFrameEncoder(int w, int h, int qp, float fps) {
-    ctl.init(w, h, qp, fps, 5000000);
+    ctl.init(w, h, qp, fps, 5000000, g_emu_cabac, g_emu_profile);
     const int n = ctl.sp.mb_w * ctl.sp.mb_h;
     cur[0].resize((size_t)n * 256 + 64); cur[1].resize((size_t)n * 64 + 64); cur[2].resize((size_t)n * 64 + 64);
     for (int b = 0; b < 2; b++) {
@@ -127,8 +128,8 @@ struct HostFrameEncoder {
     }
     ctl.write_access_unit(idr, out.data(), bs);
     // the bit count the macroblock code computed without writing must equal what the writer spent, macroblock by macroblock
-    if (ctl.last_mb_bits != mb_bits) mb_bits_ok = false;
-    if (parse_status == 0) check_parse(*bs);
+    if (!ctl.sp.entropy_cabac && ctl.last_mb_bits != mb_bits) mb_bits_ok = false;
+    if (!ctl.sp.entropy_cabac && parse_status == 0) check_parse(*bs);        // (the repository's parser is CAVLC only)
     have_ref_p = !idr;
     prev_y = cur[0];
     cur_rec = 1 - cur_rec;            // the picture just reconstructed becomes the reference
@@ -203,6 +204,7 @@ extern "C" int emu_last(MbOut* out, MbInfo* info, int n) {
   return 0;
 }
 static int g_emu_fast_mode = 0;
+extern "C" void emu_set_entropy(int cabac, int profile_idc) { g_emu_cabac = cabac; g_emu_profile = profile_idc; }
 extern "C" void emu_set_complexity_low(int on) { g_emu_fast_mode = on; }
 extern "C" long emu_encode(const uint8_t* yuv, int w, int h, int nframes, int qp, float fps, uint8_t* out, long cap,
                            int32_t* frame_bytes, uint8_t* recon_out /* nframes * w*h*3/2 or NULL */) {

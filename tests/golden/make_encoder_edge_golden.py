@@ -25,6 +25,12 @@ LOW_CASES = [  # (w, h, n, qp, seed, noise)
     (32, 18, 4, 20, 8, 3), (176, 144, 4, 51, 3, 3),
 ]
 
+CABAC_CASES = [  # (w, h, n, qp, seed, noise, profile_idc: 0 = the encoder's choice (High), 77 = Main)
+    (176, 144, 4, 26, 3, 3, 0), (176, 144, 4, 26, 3, 3, 77), (320, 192, 5, 32, 4, 3, 0), (64, 64, 3, 12, 5, 3, 77), (180, 148, 4, 26, 5, 3, 0),
+    (16, 16, 4, 26, 7, 3, 0), (32, 18, 4, 20, 8, 3, 77), (176, 144, 4, 0, 3, 3, 0), (176, 144, 4, 51, 3, 3, 0), (480, 32, 4, 28, 9, 3, 77),
+    (320, 192, 4, 24, 60, 40, 0), (640, 360, 3, 30, 2, 6, 0),
+]
+
 if __name__ == "__main__":
     assert h264lib.have_ref()
     src = os.path.join("/root/reference/res", CLIP)
@@ -49,5 +55,16 @@ if __name__ == "__main__":
         y = h264lib.synth_clip(w, h, n, seed=seed, noise=noise)
         bs, fb, _ = ref_encode(y, w, h, n, qp, 30.0, complexity=0)
         gold["low"]["%dx%d_n%d_qp%d_seed%d_noise%d" % (w, h, n, qp, seed, noise)] = {"sha1": hashlib.sha1(bs).hexdigest(), "frame_bytes": fb}
+    # iEntropyCodingModeFlag = 1 (CABAC; High profile unless the layer asks for Main)
+    gold["cabac"] = {}
+    for prof in (0, 77):
+        bs, fb, _ = ref_encode(yuv, 320, 192, 9, 26, 12.0, entropy=(1, prof))
+        gold["cabac"]["clip_qp26_profile%d" % prof] = {"sha1": hashlib.sha1(bs).hexdigest(), "frame_bytes": fb}
+    for (w, h, n, qp, seed, noise, prof) in CABAC_CASES:
+        y = h264lib.synth_clip(w, h, n, seed=seed, noise=noise)
+        bs, fb, _ = ref_encode(y, w, h, n, qp, 30.0, entropy=(1, prof))
+        gold["cabac"]["%dx%d_n%d_qp%d_seed%d_noise%d_profile%d" % (w, h, n, qp, seed, noise, prof)] = {"sha1": hashlib.sha1(bs).hexdigest(), "frame_bytes": fb}
+    bs, fb, _ = ref_encode(yuv, 320, 192, 9, 30, 12.0, complexity=0, entropy=(1, 0))
+    gold["cabac"]["clip_qp30_profile0_low"] = {"sha1": hashlib.sha1(bs).hexdigest(), "frame_bytes": fb}
     json.dump(gold, open(os.path.join(HERE, "encoder_edge.json"), "w"), indent=1, sort_keys=True)
     print(json.dumps(gold, indent=1))

@@ -16,14 +16,20 @@ CASES = [  # (w, h, frames, qp, fps)
 ]
 
 
-def ref_encode(yuv, w, h, n, qp, fps, complexity=2, threads=1):
+def ref_encode(yuv, w, h, n, qp, fps, complexity=2, threads=1, entropy=(0, 66)):
+    """entropy = (iEntropyCodingModeFlag, uiProfileIdc; 0 = leave the profile to the encoder: High with CABAC)"""
     R = C.CDLL(h264lib.REFSHIM_SO)
+    R.ref_set_entropy.argtypes = [C.c_int, C.c_int]
     R.ref_encode.restype = C.c_long
     R.ref_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
                              C.c_long, C.c_void_p, C.POINTER(C.c_double)]
     cap = 64 << 20
     out, fb, secs = np.zeros(cap, np.uint8), np.zeros(n, np.int32), C.c_double()
-    tot = R.ref_encode(yuv.ctypes.data, w, h, n, qp, complexity, threads, fps, out.ctypes.data, cap, fb.ctypes.data, C.byref(secs))
+    R.ref_set_entropy(*entropy)
+    try:
+        tot = R.ref_encode(yuv.ctypes.data, w, h, n, qp, complexity, threads, fps, out.ctypes.data, cap, fb.ctypes.data, C.byref(secs))
+    finally:
+        R.ref_set_entropy(0, 66)
     assert tot > 0
     return out[:tot].tobytes(), fb.tolist(), secs.value
 

@@ -28,8 +28,9 @@ def emu():
     return E
 
 
-def emu_encode(E, yuv, w, h, n, qp, fps, low=False):
+def emu_encode(E, yuv, w, h, n, qp, fps, low=False, entropy=(0, 66)):
     E.emu_set_complexity_low(1 if low else 0)
+    E.emu_set_entropy(*entropy)
     cap = 32 << 20
     out, fb = np.zeros(cap, np.uint8), np.zeros(n, np.int32)
     tot = E.emu_encode(yuv.ctypes.data, w, h, n, qp, fps, out.ctypes.data, cap, fb.ctypes.data, None)
@@ -132,3 +133,44 @@ def test_emu_low_complexity_matches_reference_golden(emu, key):
         fps = 30.0
     bs, fb = emu_encode(emu, yuv, w, h, n, qp, fps, low=True)
     assert fb == g["frame_bytes"] and hashlib.sha1(bs).hexdigest() == g["sha1"]
+
+
+@pytest.mark.parametrize("key", sorted(EDGE["cabac"]))
+def test_emu_cabac_matches_reference_golden(emu, key):
+    """iEntropyCodingModeFlag = 1: the host CABAC slice writer (csrc/h264_cabac.cpp; High profile by default, Main on request)
+    behind the unchanged macroblock pipeline, against goldens from the unmodified reference with the same setting"""
+    g = EDGE["cabac"][key]
+    prof = int(key.split("_profile")[1].split("_")[0])
+    if key.startswith("clip"):
+        w, h, n, qp, fps = 320, 192, 9, int(key.split("qp")[1].split("_")[0]), 12.0
+        yuv = np.fromfile(os.path.join(ROOT, "tests", "golden", "CiscoVT2people_320x192_12fps.yuv"), dtype=np.uint8)
+    else:
+        w, h = map(int, key.split("_")[0].split("x"))
+        n, qp = int(key.split("_n")[1].split("_")[0]), int(key.split("_qp")[1].split("_")[0])
+        yuv = h264lib.synth_clip(w, h, n, seed=int(key.split("_seed")[1].split("_")[0]), noise=int(key.split("_noise")[1].split("_")[0]))
+        fps = 30.0
+    bs, fb = emu_encode(emu, yuv, w, h, n, qp, fps, low=key.endswith("_low"), entropy=(1, prof))
+    assert fb == g["frame_bytes"] and hashlib.sha1(bs).hexdigest() == g["sha1"]
+
+
+def test_emu_cabac_matches_reference_side_by_side(emu):
+    """the same, against the compiled reference on its own clips, both profiles"""
+    if not h264lib.have_ref():
+        pytest.skip("reference build not on this machine")
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_encoder_golden import ref_encode
+    clips = [("/root/reference/res/CiscoVT2people_160x96_6fps.yuv", 160, 96, 5, 24), ("/root/reference/res/Static_152_100.yuv", 152, 100, 8, 28)]
+    ran = 0
+    for path, w, h, n, qp in clips:
+        fsz = w * h * 3 // 2
+        if not os.path.exists(path) or os.path.getsize(path) < n * fsz:
+            continue
+        yuv = np.fromfile(path, dtype=np.uint8, count=n * fsz)
+        for prof in (0, 77):
+            ref_bs, ref_fb, _ = ref_encode(yuv, w, h, n, qp, 30.0, entropy=(1, prof))
+            bs, fb = emu_encode(emu, yuv, w, h, n, qp, 30.0, entropy=(1, prof))
+            assert fb == ref_fb and bs == bytes(ref_bs), (path, prof)
+        ran += 1
+    if not ran:
+        pytest.skip("no reference clips on this machine")

@@ -225,3 +225,29 @@ def test_low_complexity_through_cuda(key):
     enc.close()
     assert [len(b) for b in out[0]] == g["frame_bytes"]
     assert hashlib.sha1(b"".join(out[0])).hexdigest() == g["sha1"] and out[1] == out[0]
+
+
+@pytest.mark.parametrize("key", sorted(EDGE["cabac"]))
+def test_cabac_through_cuda(key):
+    """iEntropyCodingModeFlag = 1: the same macroblock kernel, records entropy-coded by the host CABAC writer (csrc/h264_cabac.cpp);
+    golden = the unmodified reference with CABAC (High profile by default, Main on request)."""
+    from openh264_b200.binding import BatchEncoder
+    g = EDGE["cabac"][key]
+    prof = int(key.split("_profile")[1].split("_")[0])
+    if key.startswith("clip"):
+        w, h, n, qp, fps = 320, 192, 9, int(key.split("qp")[1].split("_")[0]), 12.0
+        yuv = np.fromfile(os.path.join(ROOT, "tests", "golden", "CiscoVT2people_320x192_12fps.yuv"), dtype=np.uint8)
+    else:
+        w, h = map(int, key.split("_")[0].split("x"))
+        n, qp = int(key.split("_n")[1].split("_")[0]), int(key.split("_qp")[1].split("_")[0])
+        yuv = h264lib.synth_clip(w, h, n, seed=int(key.split("_seed")[1].split("_")[0]), noise=int(key.split("_noise")[1].split("_")[0]))
+        fps = 30.0
+    enc = BatchEncoder(w, h, qp=qp, fps=fps, n_streams=2, complexity_low=key.endswith("_low"), entropy_cabac=True, profile_idc=prof)
+    fsz = w * h * 3 // 2
+    out = [[], []]
+    for f in range(n):
+        bs, _ = enc.encode([yuv[f * fsz:(f + 1) * fsz]] * 2)
+        out[0].append(bs[0]); out[1].append(bs[1])
+    enc.close()
+    assert [len(b) for b in out[0]] == g["frame_bytes"]
+    assert hashlib.sha1(b"".join(out[0])).hexdigest() == g["sha1"] and out[1] == out[0]

@@ -19,12 +19,13 @@ need_built = pytest.mark.skipif(not (os.path.exists(DRIVER) and os.path.exists(O
                                 reason="layer-3 shim / driver are built where the reference headers exist (build())")
 
 
-def drive(lib, clip, w, h, n, qp, idr_at, tmp, tag):
+def drive(lib, clip, w, h, n, qp, idr_at, tmp, tag, entropy=None):
     yuv = os.path.join(tmp, "in.yuv")
     with open(yuv, "wb") as f:
         f.write(clip.tobytes())
     out, lay = os.path.join(tmp, tag + ".264"), os.path.join(tmp, tag + ".layout")
-    r = subprocess.run([DRIVER, lib, yuv, str(w), str(h), str(n), str(qp), str(idr_at), out, lay], capture_output=True, text=True,
+    extra = [str(entropy[0]), str(entropy[1])] if entropy else []
+    r = subprocess.run([DRIVER, lib, yuv, str(w), str(h), str(n), str(qp), str(idr_at), out, lay] + extra, capture_output=True, text=True,
                        timeout=300)
     return r, (open(out, "rb").read() if os.path.exists(out) else b""), (open(lay).read() if os.path.exists(lay) else "")
 
@@ -73,6 +74,21 @@ def test_drop_in_same_driver_two_libraries(tmp_path, w, h, n, qp, idr_at):
     assert r1.returncode == 0, r1.stderr
     assert bs0 == bs1, "bitstream through ISVCEncoder differs from the reference"
     assert lay0 == lay1, "SFrameBSInfo layout / defaults differ:\n" + lay0 + "\n---\n" + lay1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cabac,profile", [(1, 0), (1, 77), (1, 66), (0, 77), (0, 100)])
+def test_drop_in_entropy_mode_and_profile(tmp_path, cabac, profile):
+    """iEntropyCodingModeFlag / uiProfileIdc through ISVCEncoder: CABAC slice data (High by default, Main on request), Baseline
+    forcing CAVLC, Main / High parameter sets over CAVLC — the same driver binary against both libraries"""
+    assert os.path.exists(DRIVER) and os.path.exists(OURLIB), "prebuilt layer-3 artefacts missing on the GPU box"
+    w, h, n, qp = 320, 192, 5, 27
+    clip = h264lib.synth_clip(w, h, n, seed=11, noise=5)
+    r0, bs0, lay0 = drive(REFLIB, clip, w, h, n, qp, 3, str(tmp_path), "ref", entropy=(cabac, profile))
+    r1, bs1, lay1 = drive(OURLIB, clip, w, h, n, qp, 3, str(tmp_path), "b2", entropy=(cabac, profile))
+    assert r0.returncode == 0, r0.stderr
+    assert r1.returncode == 0, r1.stderr
+    assert bs0 == bs1 and lay0 == lay1
 
 
 # ---- ISVCDecoder object and the batching broker behind ISVCEncoder -------------------------------------------------------

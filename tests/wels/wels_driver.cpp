@@ -49,6 +49,10 @@ int main(int argc, char** argv) {
   p.sSpatialLayers[0].iSpatialBitrate = 5000000;
   p.sSpatialLayers[0].iDLayerQp = qp;
   p.sSpatialLayers[0].uiProfileIdc = PRO_BASELINE;
+  if (argc > 11) {                       // optional: iEntropyCodingModeFlag and uiProfileIdc (0 = PRO_UNKNOWN)
+    p.iEntropyCodingModeFlag = atoi(argv[10]);
+    p.sSpatialLayers[0].uiProfileIdc = (EProfileIdc)atoi(argv[11]);
+  }
   p.sSpatialLayers[0].sSliceArgument.uiSliceMode = SM_SINGLE_SLICE;
   int rc = enc->InitializeExt(&p);
   if (rc) { fprintf(stderr, "InitializeExt -> %d\n", rc); return 5; }

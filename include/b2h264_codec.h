@@ -6,8 +6,8 @@
  * of the reference (WelsCodeOneSlice -> WelsISliceMdEnc / WelsMdInterMbLoop,
  * codec/encoder/core/src/svc_encode_slice.cpp:534,1642,1807) plus PerformDeblockingFilter
  * (deblocking.cpp:744) and ExpandReferencingPicture (expand_pic.cpp:388) run on the GPU as a wavefront
- * over macroblock rows x streams; CAVLC / NAL serialisation (svc_set_mb_syn_cavlc.cpp, nal_encap.cpp)
- * runs on host threads from the pinned copy-back of the per-macroblock records.
+ * over macroblock rows x streams; CAVLC or CABAC / NAL serialisation (svc_set_mb_syn_cavlc.cpp,
+ * svc_set_mb_syn_cabac.cpp, nal_encap.cpp) runs on host threads from the pinned copy-back of the per-macroblock records.
  *
  * Layer 3 — the reference's own public API (codec/api/wels/codec_api.h:272-339,545-586):
  * WelsCreateSVCEncoder() returns an object whose vtable layout is that of ISVCEncoder, so a caller
@@ -16,7 +16,7 @@
  *
  * Supported configuration (everything else is rejected with an error, never silently approximated):
  * CAMERA_VIDEO_REAL_TIME, 1 spatial / 1 temporal layer, RC_OFF_MODE (constant QP), SM_SINGLE_SLICE,
- * CAVLC, any iComplexityMode (LOW / MEDIUM / HIGH), 1 reference frame, deblocking idc 0, IDR at the first frame (and on
+ * CAVLC or CABAC (Baseline / Main / High parameter sets, no 8x8 transform), any iComplexityMode (LOW / MEDIUM / HIGH), 1 reference frame, deblocking idc 0, IDR at the first frame (and on
  * ForceIntraFrame), no denoise / background detection / adaptive quant / scene-change / LTR.
  * For that configuration the bitstream is bit-identical to the reference's.
  */
@@ -103,9 +103,10 @@ int  b2h264_enc_set_stream (b2h264_enc* e, void* stream);
 /* layer 3 (WelsCreateSVCEncoder / ISVCEncoder, codec_api.h:272-339,545-586) is declared in b2h264_wels_api.h */
 
 /* ---- batched decoder (first device version of the decoder construct path) -----------------
- * Replaces, for Baseline CAVLC streams (I and P slices, several slices per picture in raster order, up to 16 reference frames with
- * list modification and sliding-window / "unused" marking, all partition shapes down to 4x4, constrained intra prediction,
- * per-slice deblocking control, non-reference pictures; no FMO / ASO, long-term references, I_PCM, B slices or CABAC), ISVCDecoder::DecodeFrameNoDelay
+ * Replaces, for Baseline / Main / High streams with CAVLC or CABAC slice data (I and P slices, several slices per picture in raster
+ * order, up to 16 reference frames with list modification, sliding-window and memory-management marking incl. long-term pictures,
+ * all partition shapes down to 4x4, I_PCM, constrained intra prediction, per-slice deblocking control, non-reference pictures; no
+ * FMO / ASO, B slices, weighted prediction, interlace, 8x8 transform or scaling lists), ISVCDecoder::DecodeFrameNoDelay
  * (codec/api/wels/codec_api.h:383; codec/decoder/plus/src/welsDecoderExt.cpp:~700).  The host parses, the GPU
  * reconstructs, deblocks and pads.  Anything else is rejected: -101 truncated, -102 unsupported stream feature,
  * -103 invalid syntax, -104 slice before its parameter sets, -105 the slices given do not cover the picture; -2 picture size differs from the configuration. */

@@ -1,0 +1,194 @@
+// h264_cabac_dec.h — CABAC arithmetic DECODER and the binarisations of the macroblock layer (Rec. H.264 9.3.1.2, 9.3.2, 9.3.3.2),
+// the inverse of h264_cabac.cpp.  Used by h264_parse.cpp for streams with entropy_coding_mode_flag = 1 (I and P slices, frame
+// macroblocks, 4x4 transform).  The reference's counterpart: codec/decoder/core/src/cabac_decoder.cpp (DecodeBinCabac,
+// DecodeBypassCabac, DecodeTerminateCabac) and parse_mb_syn_cabac.cpp; this file follows the Recommendation's bit-serial
+// description (9-bit offset register), the context variables are the same tables the encoder uses (cabac_tables.h).
+// Context index increments that depend on neighbouring macroblocks are computed by the caller (h264_parse.cpp keeps the
+// per-macroblock context records) and passed in.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "cabac_tables.h"
+
+namespace b2h264 {
+
+class CabacDecoder {
+ public:
+  CabacDecoder(const uint8_t* p, size_t nbytes) : p_(p), nbits_(nbytes * 8) {}
+  bool ok() const { return !overrun_; }
+  size_t pos() const { return pos_; }
+
+  void init_contexts(int slice_qp, int table /* 0 = I slice, 1 + cabac_init_idc */) {
+    const int qp = slice_qp < 0 ? 0 : slice_qp > 51 ? 51 : slice_qp;
+    for (int i = 0; i < 460; i++) {
+      int pre = ((kCabacInit[i][table][0] * qp) >> 4) + kCabacInit[i][table][1];
+      pre = pre < 1 ? 1 : pre > 126 ? 126 : pre;
+      if (pre <= 63) { state_[i] = (uint8_t)(63 - pre); mps_[i] = 0; }
+      else { state_[i] = (uint8_t)(pre - 64); mps_[i] = 1; }
+    }
+  }
+  // 9.3.1.2: at the start of the slice data and after the samples of an I_PCM macroblock (bit_pos: byte aligned)
+  void init_engine(size_t bit_pos) {
+    pos_ = bit_pos;
+    range_ = 510;
+    offset_ = 0;
+    for (int i = 0; i < 9; i++) offset_ = (offset_ << 1) | read_bit();
+  }
+  int decision(int ctx) {
+    const uint32_t lps = kCabacRangeLps[state_[ctx]][(range_ >> 6) & 3];
+    range_ -= lps;
+    int bin;
+    if (offset_ >= range_) {
+      bin = !mps_[ctx];
+      offset_ -= range_;
+      range_ = lps;
+      if (state_[ctx] == 0) mps_[ctx] ^= 1;
+      state_[ctx] = kCabacNextLps[state_[ctx]];
+    } else {
+      bin = mps_[ctx];
+      state_[ctx] = kCabacNextMps[state_[ctx]];
+    }
+    while (range_ < 256) { range_ <<= 1; offset_ = (offset_ << 1) | read_bit(); }
+    return bin;
+  }
+  int bypass() {
+    offset_ = (offset_ << 1) | read_bit();
+    if (offset_ >= range_) { offset_ -= range_; return 1; }
+    return 0;
+  }
+  // end_of_slice_flag / the I_PCM bin of mb_type.  After a 1 the read position is just behind the encoder's flush (whose last
+  // bit is the rbsp_stop_one_bit, 9.3.4.5): nothing more is read
+  int terminate() {
+    range_ -= 2;
+    if (offset_ >= range_) return 1;
+    while (range_ < 256) { range_ <<= 1; offset_ = (offset_ << 1) | read_bit(); }
+    return 0;
+  }
+  // k-th order Exp-Golomb suffix, bypass coded (9.3.2.3); -1: not a valid code
+  int64_t exp_golomb_bypass(int k) {
+    int64_t v = 0;
+    while (bypass()) {
+      v += (int64_t)1 << k;
+      if (++k > 24) { overrun_ = true; return -1; }
+    }
+    while (k--) v += (int64_t)bypass() << k;
+    return v;
+  }
+
+  // ---- syntax elements (ctxIdx: Table 9-34; bins: 9.3.2.5 and Tables 9-36 .. 9-38) ----
+  // mb_type of an I slice (prefix_ctx = 3 + inc, rest 3 + 3..7) or the suffix inside a P slice (prefix_ctx = 17, rest 17 + 1..3);
+  // returns mb_type 0..25
+  int mb_type_intra(int prefix_ctx, bool in_p) {
+    if (!decision(prefix_ctx)) return 0;                                  // I_NxN
+    if (terminate()) return 25;                                           // I_PCM
+    const int base = in_p ? 17 : 3;
+    const int c_l = in_p ? base + 1 : base + 3, c_c0 = in_p ? base + 2 : base + 4, c_c1 = in_p ? base + 2 : base + 5;
+    const int c_m0 = in_p ? base + 3 : base + 6, c_m1 = in_p ? base + 3 : base + 7;
+    const int luma = decision(c_l);
+    int chroma = decision(c_c0);
+    if (chroma) chroma += decision(c_c1);
+    const int m0 = decision(c_m0), m1 = decision(c_m1);                   // 9.3.3.1.2: the same two contexts with or without the extra chroma bin
+    return 1 + (m0 * 2 + m1) + 4 * chroma + 12 * luma;
+  }
+  // P slice: 0 P_L0_16x16, 1 P_L0_L0_16x8, 2 P_L0_L0_8x16, 3 P_8x8, 5.. = 5 + intra type
+  int mb_type_p() {
+    if (decision(14)) return 5 + mb_type_intra(17, true);
+    if (!decision(15)) return decision(16) ? 3 : 0;
+    return decision(17) ? 1 : 2;
+  }
+  int sub_mb_type_p() {                                                    // 0 8x8, 1 8x4, 2 4x8, 3 4x4
+    if (decision(21)) return 0;
+    if (!decision(22)) return 1;
+    return decision(23) ? 2 : 3;
+  }
+  int ref_idx(int inc) {                                                   // unary, ctx 54 + inc / 58 / 59
+    if (!decision(54 + inc)) return 0;
+    int v = 1;
+    if (!decision(58)) return v;
+    for (v = 2; decision(59); v++) if (v > 32) { overrun_ = true; return 0; }
+    return v;
+  }
+  int mvd(int ctx_base, int sum) {                                         // UEG3, uCoff 9, signed
+    int inc = sum > 32 ? 2 : sum > 2 ? 1 : 0;
+    int a = 0;
+    while (a < 9 && decision(ctx_base + inc)) {
+      inc = a == 0 ? 3 : (inc < 6 ? inc + 1 : 6);
+      a++;
+    }
+    if (a == 9) {
+      const int64_t s = exp_golomb_bypass(3);
+      if (s < 0 || s > 1 << 20) { overrun_ = true; return 0; }
+      a += (int)s;
+    }
+    if (a && bypass()) a = -a;
+    return a;
+  }
+  int intra_chroma_pred_mode(int inc) {
+    if (!decision(64 + inc)) return 0;
+    if (!decision(67)) return 1;
+    return decision(67) ? 3 : 2;
+  }
+  int mb_qp_delta(int inc) {
+    if (!decision(60 + inc)) return 0;
+    int v = 1;
+    if (decision(62)) for (v = 2; decision(63); v++) if (v > 104) { overrun_ = true; return 0; }
+    return (v & 1) ? (v + 1) / 2 : -(v / 2);
+  }
+  // residual_block_cabac without the coded_block_flag (7.3.5.3.3): fills lv[0..max_coef) (scan order), returns the number of
+  // non-zero levels or -1
+  int residual_levels(int cat, int16_t* lv, int max_coef) {
+    static const int kSigOff[5] = {0, 15, 29, 44, 47}, kAbsOff[5] = {0, 10, 20, 30, 39};
+    for (int i = 0; i < max_coef; i++) lv[i] = 0;
+    int sig_pos[16], n = 0;
+    int i = 0;
+    for (; i < max_coef - 1; i++) {
+      const int inc = cat == 3 ? (i < 2 ? i : 2) : i;
+      if (decision(105 + kSigOff[cat] + inc)) {
+        sig_pos[n++] = i;
+        if (decision(166 + kSigOff[cat] + inc)) break;
+      }
+    }
+    if (i == max_coef - 1) sig_pos[n++] = max_coef - 1;                   // no "last" flag seen: the final position is significant
+    int eq1 = 0, gt1 = 0;
+    const int base = 227 + kAbsOff[cat];
+    for (int k = n - 1; k >= 0; k--) {
+      int a = 0;
+      if (decision(base + (gt1 ? 0 : (1 + eq1 < 4 ? 1 + eq1 : 4)))) {
+        const int lim = 4 - (cat == 3 ? 1 : 0);
+        const int ctx = base + 5 + (gt1 < lim ? gt1 : lim);
+        a = 1;
+        while (a < 14 && decision(ctx)) a++;
+        if (a == 14) {
+          const int64_t s = exp_golomb_bypass(0);
+          if (s < 0 || s > 1 << 16) { overrun_ = true; return -1; }
+          a += (int)s;
+        }
+        gt1++;
+      } else {
+        eq1++;
+      }
+      const int v = a + 1;
+      if (v > 32767) { overrun_ = true; return -1; }
+      lv[sig_pos[k]] = (int16_t)(bypass() ? -v : v);
+    }
+    return n;
+  }
+
+ private:
+  uint32_t read_bit() {
+    if (pos_ >= nbits_) { if (++past_end_ > 64) overrun_ = true; pos_++; return 0; }      // a few bits past the end are legal look-ahead
+    const uint32_t b = (p_[pos_ >> 3] >> (7 - (pos_ & 7))) & 1u;
+    pos_++;
+    return b;
+  }
+  const uint8_t* p_;
+  size_t nbits_, pos_ = 0;
+  uint8_t state_[460], mps_[460];
+  uint32_t range_ = 510, offset_ = 0;
+  int past_end_ = 0;
+  bool overrun_ = false;
+};
+
+}  // namespace b2h264

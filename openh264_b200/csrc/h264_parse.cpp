@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include "cavlc_tables.h"
+#include "h264_cabac_dec.h"
 
 namespace b2h264 {
 
@@ -102,8 +103,16 @@ int parse_sps(BitReader& r, ParserState* st) {
   const int level = (int)r.get(8);
   const int sps_id = (int)r.ue();
   if (sps_id < 0 || sps_id > 31) return PARSE_INVALID;
-  // Baseline, or Main / Extended streams that declare Baseline conformance (constraint_set0_flag): no chroma_format_idc / scaling lists
-  if (!(profile == 66 || ((profile == 77 || profile == 88) && (flags & 0x80)))) return PARSE_UNSUPPORTED;
+  // Baseline, Main, Extended streams that declare Baseline conformance (constraint_set0_flag), High in its 4:2:0 8-bit form
+  // without scaling lists.  Tools outside the supported class (B slices, weighted prediction, interlace, the 8x8 transform, data
+  // partitioning) are rejected where they show up: slice type, PPS flags, frame_mbs_only_flag, NAL types 2..4.
+  if (!(profile == 66 || profile == 77 || profile == 100 || (profile == 88 && (flags & 0x80)))) return PARSE_UNSUPPORTED;
+  if (profile == 100) {
+    if (r.ue() != 1) return PARSE_UNSUPPORTED;                // chroma_format_idc
+    if (r.ue() != 0 || r.ue() != 0) return PARSE_UNSUPPORTED; // bit_depth_luma_minus8, bit_depth_chroma_minus8
+    if (r.bit()) return PARSE_UNSUPPORTED;                    // qpprime_y_zero_transform_bypass_flag
+    if (r.bit()) return PARSE_UNSUPPORTED;                    // seq_scaling_matrix_present_flag
+  }
   SpsFields f;
   {
     const uint32_t v = r.ue();
@@ -159,6 +168,7 @@ void activate_pps(ParserState* st, int id) {
   const PpsFields& f = st->pps_tab[id];
   st->pic_init_qp = f.pic_init_qp; st->deblocking_control = f.deblocking_control; st->num_ref_idx_default = f.num_ref_idx_default;
   st->constrained_intra_pred = f.constrained_intra_pred;
+  st->entropy_cabac = f.entropy_cabac;
   st->sp.pps_id = id;
   st->have_pps = true;
 }
@@ -169,7 +179,7 @@ int parse_pps(BitReader& r, ParserState* st) {
   if (pps_id < 0 || pps_id > 255 || sps_id < 0 || sps_id > 31) return PARSE_INVALID;
   PpsFields f;
   f.sps_id = sps_id;
-  if (r.bit()) return PARSE_UNSUPPORTED;      // entropy_coding_mode_flag: CABAC
+  f.entropy_cabac = r.bit() != 0;             // entropy_coding_mode_flag
   const int bottom_field_poc = r.bit();
   if (r.ue() != 0) return PARSE_UNSUPPORTED;  // slice groups
   f.num_ref_idx_default = (int)r.ue() + 1;
@@ -184,6 +194,12 @@ int parse_pps(BitReader& r, ParserState* st) {
   if (r.bit()) return PARSE_UNSUPPORTED;      // redundant_pic_cnt_present_flag
   if (bottom_field_poc) return PARSE_UNSUPPORTED;
   if (!r.ok()) return PARSE_TRUNCATED;
+  if (r.more_data()) {                        // High profile tail (7.3.2.2)
+    if (r.bit()) return PARSE_UNSUPPORTED;    // transform_8x8_mode_flag
+    if (r.bit()) return PARSE_UNSUPPORTED;    // pic_scaling_matrix_present_flag
+    if (r.se() != 0) return PARSE_UNSUPPORTED;// second_chroma_qp_index_offset
+    if (!r.ok()) return PARSE_TRUNCATED;
+  }
   f.valid = true;
   st->pps_tab[pps_id] = f;
   if (st->sps_tab[sps_id].valid && (!st->have_pps || st->sp.pps_id == pps_id)) { activate_sps(st, sps_id); activate_pps(st, pps_id); }
@@ -408,6 +424,12 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
       }
     }
   }
+  int cabac_init_idc = 0;
+  if (st->entropy_cabac && is_p) {
+    const uint32_t v = r.ue();
+    if (v > 2) return PARSE_INVALID;
+    cabac_init_idc = (int)v;
+  }
   ss.qp = st->pic_init_qp + r.se();
   int dbk_idc = 0, alpha_off = 0, beta_off = 0;
   if (st->deblocking_control) {
@@ -455,8 +477,232 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
   const int slice_no = pic->n_slices++;
   if (dbk_idc != 1) pic->any_deblock = true;
 
-  // ---- slice data ----
   auto same_slice = [&](int other) { return other >= first_mb; };          // raster-ordered slices: a neighbour is in this slice iff it is not before its start
+
+  // ---- slice data, CABAC (7.3.4 with entropy_coding_mode_flag = 1; macroblock layer 7.3.5, context selection 9.3.3.1.1) ----
+  if (st->entropy_cabac) {
+    while (r.pos() & 7) if (!r.bit()) return PARSE_INVALID;   // cabac_alignment_one_bit
+    if (!r.ok()) return PARSE_TRUNCATED;
+    CabacDecoder d(nal.rbsp.data(), nal.rbsp.size());
+    d.init_contexts(ss.qp, is_p ? 1 + cabac_init_idc : 0);
+    d.init_engine(r.pos());
+    if ((int)pic->cabac_info.size() != n) pic->cabac_info.resize(n);
+    CabacMbInfo* info = pic->cabac_info.data();
+    static const int kCbfOff[5] = {0, 4, 8, 12, 16};
+    int qp = ss.qp, idx = first_mb;
+    bool prev_dqp_nonzero = false;
+    for (;;) {
+      if (idx >= n) return PARSE_INVALID;                     // the slice goes on beyond the picture
+      const int mbx = idx % mbw, mby = idx / mbw;
+      const bool avL = mbx > 0 && same_slice(idx - 1), avT = mby > 0 && same_slice(idx - mbw);
+      const CabacMbInfo* L = avL ? &info[idx - 1] : nullptr;
+      const CabacMbInfo* T = avT ? &info[idx - mbw] : nullptr;
+      CabacMbInfo& me = info[idx];
+      memset(&me, 0, sizeof(me));
+      MbOut& m = pic->mbs[idx];
+      DecMbAux& ax = pic->aux[idx];
+      ax.slice = (uint16_t)slice_no; ax.dbk_idc = (uint8_t)dbk_idc; ax.alpha_off = (int8_t)alpha_off; ax.beta_off = (int8_t)beta_off;
+      ax.flags = st->constrained_intra_pred ? DECAUX_CIP : 0;
+      ax.avail = (uint8_t)((avL ? 1 : 0) | (avT ? 2 : 0) | (mbx > 0 && mby > 0 && same_slice(idx - mbw - 1) ? 4 : 0) |
+                           (mby > 0 && mbx < mbw - 1 && same_slice(idx - mbw + 1) ? 8 : 0));
+      if (is_p && d.decision(11 + (L && !L->skip ? 1 : 0) + (T && !T->skip ? 1 : 0))) {       // mb_skip_flag
+        reset_skip_record(&m);
+        m.qp = (uint8_t)qp;
+        ax.flags = 0;
+        for (int q = 0; q < 4; q++) ax.ref_idx[q] = (int8_t)list0[0];
+        me.type = MBT_PSKIP; me.skip = 1;
+        prev_dqp_nonzero = false;
+      } else {
+        memset(&m, 0, sizeof(m));
+        int t;
+        bool intra = !is_p;
+        if (is_p) {
+          t = d.mb_type_p();
+          if (t >= 5) { intra = true; t -= 5; }
+        } else {
+          t = d.mb_type_intra(3 + (L && L->type != MBT_I4x4 ? 1 : 0) + (T && T->type != MBT_I4x4 ? 1 : 0), false);
+        }
+        me.intra = intra ? 1 : 0;
+        int cbp = -1;
+        if (intra && t == 25) {                               // I_PCM: the arithmetic decoder stopped behind its flush; raw bytes follow
+          m.mb_type = MBT_IPCM;
+          size_t bp = (d.pos() + 7) & ~(size_t)7;             // pcm_alignment_zero_bit
+          const size_t byte0 = bp >> 3;
+          if (byte0 + 384 > nal.rbsp.size()) return PARSE_TRUNCATED;
+          memcpy(reinterpret_cast<uint8_t*>(m.luma), nal.rbsp.data() + byte0, 256);
+          memcpy(reinterpret_cast<uint8_t*>(m.chroma_ac), nal.rbsp.data() + byte0 + 256, 128);
+          d.init_engine(bp + 384 * 8);                        // 9.3.1.2: the engine starts over after the samples
+          for (int i = 0; i < 24; i++) m.nnz[i] = 16;
+          m.cbp = 0x2f;
+          m.qp = 0;                                           // as in the CAVLC path: QP'Y 0 for the filter, the QP predictor stays
+          me.type = MBT_IPCM; me.cbp = 0x2f; me.cbf = 0x7ffffff;
+          prev_dqp_nonzero = false;
+        } else {
+          if (!intra) {
+            int ri[4] = {0, 0, 0, 0};
+            // partitions as (first 4x4 block, width, height in 4x4 blocks); a P_8x8 macroblock lists its sub-macroblock partitions
+            struct Part { int b, w, h, q, slot; };             // q: 8x8 quadrant; slot: where the vector goes (m.mvd / ax.mvd index)
+            Part parts[16];
+            int np = 0;
+            if (t == 0) { m.mb_type = MBT_P16x16; parts[np++] = {0, 4, 4, 0, 0}; }
+            else if (t == 1) { m.mb_type = MBT_P16x8; parts[np++] = {0, 4, 2, 0, 0}; parts[np++] = {8, 4, 2, 2, 1}; }
+            else if (t == 2) { m.mb_type = MBT_P8x16; parts[np++] = {0, 2, 4, 0, 0}; parts[np++] = {2, 2, 4, 1, 1}; }
+            else {
+              m.mb_type = MBT_P8x8;
+              bool sub = false;
+              for (int k = 0; k < 4; k++) { ax.sub_type[k] = (uint8_t)d.sub_mb_type_p(); sub = sub || ax.sub_type[k] != 0; }
+              if (sub) ax.flags |= DECAUX_SUB;
+              for (int k = 0; k < 4; k++) {
+                const int b0 = (k & 1) * 2 + (k >> 1) * 8;
+                switch (ax.sub_type[k]) {
+                  case 0: parts[np++] = {b0, 2, 2, k, 4 * k}; break;
+                  case 1: parts[np++] = {b0, 2, 1, k, 4 * k}; parts[np++] = {b0 + 4, 2, 1, k, 4 * k + 1}; break;
+                  case 2: parts[np++] = {b0, 1, 2, k, 4 * k}; parts[np++] = {b0 + 1, 1, 2, k, 4 * k + 1}; break;
+                  default:
+                    parts[np++] = {b0, 1, 1, k, 4 * k}; parts[np++] = {b0 + 1, 1, 1, k, 4 * k + 1};
+                    parts[np++] = {b0 + 4, 1, 1, k, 4 * k + 2}; parts[np++] = {b0 + 5, 1, 1, k, 4 * k + 3};
+                    break;
+                }
+              }
+            }
+            // ref_idx_l0 of every macroblock partition / sub-macroblock, then the vectors (7.3.5.1, 7.3.5.2)
+            if (n_ref > 1) {
+              auto gt0 = [&](int q) {                          // condTermFlag of the 8x8 blocks left of and above quadrant q
+                const int qx = q & 1, qy = q >> 1;
+                const int a = qx ? (me.ref_gt0 >> (q - 1)) & 1 : (L ? (L->ref_gt0 >> (qy * 2 + 1)) & 1 : 0);
+                const int b = qy ? (me.ref_gt0 >> (q - 2)) & 1 : (T ? (T->ref_gt0 >> (2 + qx)) & 1 : 0);
+                return a + 2 * b;
+              };
+              if (m.mb_type == MBT_P8x8) {
+                for (int k = 0; k < 4; k++) { ri[k] = d.ref_idx(gt0(k)); if (ri[k] > 0) me.ref_gt0 |= (uint8_t)(1 << k); }
+              } else {
+                const int nmp = m.mb_type == MBT_P16x16 ? 1 : 2;
+                for (int pi = 0; pi < nmp; pi++) {
+                  const int q0 = parts[pi].q;
+                  const int v = d.ref_idx(gt0(q0));
+                  const int mask = m.mb_type == MBT_P16x16 ? 15 : m.mb_type == MBT_P16x8 ? (3 << (2 * pi)) : (5 << pi);
+                  for (int q = 0; q < 4; q++) if (mask & (1 << q)) ri[q] = v;
+                  if (v > 0) me.ref_gt0 |= (uint8_t)mask;
+                }
+              }
+            }
+            for (int k = 0; k < 4; k++) {
+              if (ri[k] < 0 || ri[k] >= n_ref) return PARSE_INVALID;
+              ax.ref_idx[k] = (int8_t)list0[ri[k]];
+            }
+            for (int pi = 0; pi < np; pi++) {
+              const Part& pt = parts[pi];
+              const int bx = pt.b & 3, by = pt.b >> 2;
+              int v[2];
+              for (int c = 0; c < 2; c++) {
+                const int a = bx > 0 ? me.mvd[pt.b - 1][c] : (L ? L->mvd[by * 4 + 3][c] : 0);
+                const int b = by > 0 ? me.mvd[pt.b - 4][c] : (T ? T->mvd[12 + bx][c] : 0);
+                v[c] = d.mvd(c ? 47 : 40, a + b);
+              }
+              if (m.mb_type == MBT_P8x8) { ax.mvd[pt.slot][0] = (int16_t)v[0]; ax.mvd[pt.slot][1] = (int16_t)v[1]; }
+              else { m.mvd[pt.slot][0] = (int16_t)v[0]; m.mvd[pt.slot][1] = (int16_t)v[1]; }
+              const uint8_t a0 = (uint8_t)(abs(v[0]) > 255 ? 255 : abs(v[0])), a1 = (uint8_t)(abs(v[1]) > 255 ? 255 : abs(v[1]));
+              for (int y = 0; y < pt.h; y++)
+                for (int x = 0; x < pt.w; x++) { me.mvd[(by + y) * 4 + bx + x][0] = a0; me.mvd[(by + y) * 4 + bx + x][1] = a1; }
+            }
+            if (m.mb_type == MBT_P8x8 && !(ax.flags & DECAUX_SUB))
+              for (int k = 0; k < 4; k++) { m.mvd[k][0] = ax.mvd[4 * k][0]; m.mvd[k][1] = ax.mvd[4 * k][1]; }
+          } else {
+            if (t == 0) {
+              m.mb_type = MBT_I4x4;
+              for (int k = 0; k < 16; k++) {
+                m.prev_i4_flag[k] = (int8_t)d.decision(68);
+                if (!m.prev_i4_flag[k]) { int v = d.decision(69); v |= d.decision(69) << 1; v |= d.decision(69) << 2; m.rem_i4_mode[k] = (int8_t)v; }
+              }
+            } else {
+              m.mb_type = MBT_I16x16;
+              const int v = t - 1;
+              m.i16_mode = (uint8_t)(v & 3);
+              cbp = (((v >> 2) % 3) << 4) | (v >= 12 ? 15 : 0);
+            }
+            m.chroma_mode = (uint8_t)d.intra_chroma_pred_mode((L && L->chroma_mode != 0 ? 1 : 0) + (T && T->chroma_mode != 0 ? 1 : 0));
+            me.chroma_mode = m.chroma_mode;
+            if (!st->constrained_intra_pred) {
+              if ((m.chroma_mode == 1 && !avL) || (m.chroma_mode == 2 && !avT) || (m.chroma_mode == 3 && !(avL && avT))) return PARSE_INVALID;
+              if (m.mb_type == MBT_I16x16 &&
+                  ((m.i16_mode == 0 && !avT) || (m.i16_mode == 1 && !avL) || (m.i16_mode == 3 && !(avL && avT)))) return PARSE_INVALID;
+            }
+          }
+          me.type = m.mb_type;
+          if (cbp < 0) {                                      // coded_block_pattern: prefix (luma, 4 bins) + suffix (chroma)
+            const int la[2] = {L ? !((L->cbp >> 1) & 1) : 0, L ? !((L->cbp >> 3) & 1) : 0};
+            const int ta[2] = {T ? !((T->cbp >> 2) & 1) : 0, T ? !((T->cbp >> 3) & 1) : 0};
+            const int b0 = d.decision(73 + la[0] + 2 * ta[0]);
+            const int b1 = d.decision(73 + !b0 + 2 * ta[1]);
+            const int b2 = d.decision(73 + la[1] + 2 * !b0);
+            const int b3 = d.decision(73 + !b2 + 2 * !b1);
+            const int lc = L ? L->cbp >> 4 : 0, tc = T ? T->cbp >> 4 : 0;
+            int cc = d.decision(77 + (lc ? 1 : 0) + (tc ? 2 : 0));
+            if (cc) cc += d.decision(81 + (lc >> 1) + 2 * (tc >> 1));
+            cbp = b0 | (b1 << 1) | (b2 << 2) | (b3 << 3) | (cc << 4);
+          }
+          m.cbp = (uint8_t)cbp; me.cbp = (uint8_t)cbp;
+          const int cbp_l = cbp & 15, cbp_c = cbp >> 4;
+          if (cbp > 0 || m.mb_type == MBT_I16x16) {
+            const int dqp = d.mb_qp_delta(prev_dqp_nonzero ? 1 : 0);
+            if (dqp < -26 || dqp > 25) return PARSE_INVALID;
+            qp = (qp + dqp + 52) % 52;
+            prev_dqp_nonzero = dqp != 0;
+            const int un = intra ? 1 : 0;                     // coded_block_flag of a block in a macroblock that is not available
+            auto cbf_of = [&](const CabacMbInfo* nb, int bit) { return nb ? (int)((nb->cbf >> bit) & 1) : un; };
+            auto luma_inc = [&](int bx, int by) {
+              const int a = bx > 0 ? (int)((me.cbf >> (by * 4 + bx - 1)) & 1) : cbf_of(L, by * 4 + 3);
+              const int b = by > 0 ? (int)((me.cbf >> ((by - 1) * 4 + bx)) & 1) : cbf_of(T, 12 + bx);
+              return a + 2 * b;
+            };
+            if (m.mb_type == MBT_I16x16 && d.decision(85 + kCbfOff[0] + cbf_of(L, 24) + 2 * cbf_of(T, 24))) {
+              if (d.residual_levels(0, m.luma_dc, 16) < 0) return PARSE_INVALID;
+              me.cbf |= 1u << 24;
+            }
+            const int lcat = m.mb_type == MBT_I16x16 ? 1 : 2;
+            for (int k = 0; k < 16; k++) {
+              if (!(cbp_l & (1 << (k >> 2)))) continue;
+              const int bx = (k & 1) | ((k >> 1) & 2), by = ((k >> 1) & 1) | ((k >> 2) & 2);
+              if (!d.decision(85 + kCbfOff[lcat] + luma_inc(bx, by))) continue;
+              const int cnt = d.residual_levels(lcat, m.luma[k], lcat == 1 ? 15 : 16);
+              if (cnt < 0) return PARSE_INVALID;
+              m.nnz[by * 4 + bx] = (int8_t)cnt;
+              me.cbf |= 1u << (by * 4 + bx);
+            }
+            if (cbp_c) {
+              for (int uv = 0; uv < 2; uv++)
+                if (d.decision(85 + kCbfOff[3] + cbf_of(L, 25 + uv) + 2 * cbf_of(T, 25 + uv))) {
+                  if (d.residual_levels(3, m.chroma_dc[uv], 4) < 0) return PARSE_INVALID;
+                  me.cbf |= 1u << (25 + uv);
+                }
+              if (cbp_c == 2)
+                for (int uv = 0; uv < 2; uv++)
+                  for (int j = 0; j < 4; j++) {
+                    const int bx = j & 1, by = j >> 1, base = 16 + 4 * uv;
+                    const int a = bx > 0 ? (int)((me.cbf >> (base + by * 2)) & 1) : cbf_of(L, base + by * 2 + 1);
+                    const int b = by > 0 ? (int)((me.cbf >> (base + bx)) & 1) : cbf_of(T, base + 2 + bx);
+                    if (!d.decision(85 + kCbfOff[4] + a + 2 * b)) continue;
+                    const int cnt = d.residual_levels(4, m.chroma_ac[4 * uv + j], 15);
+                    if (cnt < 0) return PARSE_INVALID;
+                    m.nnz[base + j] = (int8_t)cnt;
+                    me.cbf |= 1u << (base + j);
+                  }
+            }
+          } else {
+            prev_dqp_nonzero = false;
+          }
+          m.qp = (uint8_t)qp;
+        }
+      }
+      if (!d.ok()) return PARSE_TRUNCATED;
+      idx++;
+      if (d.terminate()) break;                               // end_of_slice_flag
+    }
+    pic->next_mb = idx;
+    return PARSE_OK;
+  }
+
+  // ---- slice data, CAVLC ----
   int qp = ss.qp;
   int idx = first_mb;
   while (idx < n) {

@@ -1,5 +1,5 @@
 // h264_parse.h — host-side bitstream PARSER: the inverse of h264_bitstream.{h,cpp} for the stream class this
-// library decodes: Baseline, CAVLC, I and P slices (several per picture, in raster order: no FMO / ASO), one reference
+// library decodes: Baseline / Main / High without the 8x8 transform, CAVLC or CABAC, I and P slices (several per picture, in raster order: no FMO / ASO), one reference
 // frame, all partition shapes down to 4x4, non-reference pictures, constrained intra prediction, per-slice deblocking control.  Groundwork for the decoder construct path (SURVEY.md section 8f / DESIGN.md section 9): the
 // reference parses on the host too (codec/decoder/core/src/{au_parser,parse_mb_syn_cavlc,decode_slice}.cpp) and
 // hands macroblock arrays to the pixel stage; here the macroblock array is the same MbOut record the encoder's
@@ -21,7 +21,7 @@ enum ParseError {
   PARSE_OK = 0,
   PARSE_NO_PICTURE = 1,        // the access unit was parsed (parameter sets taken) but holds no slice
   PARSE_TRUNCATED = -1,        // ran out of bits
-  PARSE_UNSUPPORTED = -2,      // valid H.264 outside the supported class (CABAC, B slices, FMO, sub-8x8 partitions, ...)
+  PARSE_UNSUPPORTED = -2,      // valid H.264 outside the supported class (B slices, FMO, 8x8 transform, interlace, ...)
   PARSE_INVALID = -3,          // not valid H.264 syntax / values out of range
   PARSE_NO_PARAMETER_SETS = -4,// a slice before its SPS / PPS
   PARSE_INCOMPLETE = -5        // the slices seen so far do not cover the picture (more slices of the access unit to come, or lost)
@@ -37,7 +37,15 @@ struct SpsFields {
 struct PpsFields {
   bool valid = false;
   int sps_id = 0, pic_init_qp = 26, num_ref_idx_default = 1;
-  bool deblocking_control = true, constrained_intra_pred = false;
+  bool deblocking_control = true, constrained_intra_pred = false, entropy_cabac = false;
+};
+
+// CABAC only: what later macroblocks of the slice need to know about a parsed macroblock (context selection, 9.3.3.1.1)
+struct CabacMbInfo {
+  uint8_t type, skip, intra, cbp, chroma_mode, ref_gt0;   // ref_gt0: bit q = ref_idx_l0 of 8x8 block q is > 0
+  uint8_t pad[2];
+  uint32_t cbf;                     // bit 0..15 luma 4x4 (raster), 16..19 Cb AC, 20..23 Cr AC, 24 luma DC, 25 Cb DC, 26 Cr DC
+  uint8_t mvd[16][2];               // min(|mvd|, 255) per 4x4 block (raster); the context only distinguishes sums up to 33
 };
 
 // parameter sets carried from access unit to access unit
@@ -53,6 +61,7 @@ struct ParserState {
   int pic_init_qp = 26;
   bool deblocking_control = true;
   bool constrained_intra_pred = false;
+  bool entropy_cabac = false;
   int num_ref_idx_default = 1;
   bool have_ref = false;         // a picture has been decoded (a P slice has something to predict from)
   int last_frame_num = 0;
@@ -81,6 +90,7 @@ struct ParsedPicture {
   bool idr_long_term = false;    // long_term_reference_flag of an IDR picture
   std::vector<int> mmco1_diff_unused;   // difference_of_pic_nums_minus1 of each "mark short-term picture unused" command
   bool any_deblock = false;      // some slice wants its macroblocks filtered
+  std::vector<CabacMbInfo> cabac_info;   // scratch of the CABAC slice-data parser (one per macroblock)
 };
 
 // Parses one access unit: [SPS] [PPS] slice, each NAL behind a 3- or 4-byte start code.  Returns PARSE_OK or an error.

@@ -6,7 +6,7 @@
 // input flushes (nothing is ever buffered here: the supported stream class has no picture reordering, so every access
 // unit with a slice yields its picture in the same call and NUM_OF_FRAMES_REMAINING_IN_BUFFER is always 0).
 // The picture size comes from the stream: the GPU decoder is (re)created when an SPS announces a new size.
-// Stream class: what layer 2 decodes (Baseline, CAVLC, one slice per picture, one reference frame, partitions >= 8x8);
+// Stream class: what layer 2 decodes (include/b2h264_codec.h: I and P slices with CAVLC or CABAC, no 8x8 transform, progressive);
 // anything else is refused with dsBitstreamError and a reason on stderr — there is no CPU decoder in this library.
 #include <cuda_runtime_api.h>
 #include <stdio.h>
@@ -158,8 +158,8 @@ class B2Decoder : public ISVCDecoder {
 
  private:
   DECODING_STATE refuse(int rc) {
-    const char* what = rc == -101 ? "truncated access unit" : rc == -102 ? "stream feature outside the supported class (Baseline, CAVLC, "
-                       "one slice per picture, one reference frame, partitions >= 8x8)" : rc == -103 ? "invalid syntax"
+    const char* what = rc == -101 ? "truncated access unit" : rc == -102 ? "stream feature outside the supported class (I / P slices, CAVLC or "
+                       "CABAC, 4x4 transform, progressive, no FMO / ASO)" : rc == -103 ? "invalid syntax"
                        : rc == -104 ? "slice before its parameter sets" : rc == -2 ? "picture size changed without an SPS" : "CUDA / internal error";
     fprintf(stderr, "[b2h264] ISVCDecoder: %s (%d)\n", what, rc);
     return rc == -104 ? dsNoParamSets : rc > 0 ? dsOutOfMemory : dsBitstreamError;

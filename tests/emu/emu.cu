@@ -129,7 +129,7 @@ struct HostFrameEncoder {
     ctl.write_access_unit(idr, out.data(), bs);
     // the bit count the macroblock code computed without writing must equal what the writer spent, macroblock by macroblock
     if (!ctl.sp.entropy_cabac && ctl.last_mb_bits != mb_bits) mb_bits_ok = false;
-    if (!ctl.sp.entropy_cabac && parse_status == 0) check_parse(*bs);        // (the repository's parser is CAVLC only)
+    if (parse_status == 0) check_parse(*bs);                                  // CAVLC and CABAC alike
     have_ref_p = !idr;
     prev_y = cur[0];
     cur_rec = 1 - cur_rec;            // the picture just reconstructed becomes the reference

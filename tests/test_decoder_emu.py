@@ -80,8 +80,8 @@ def test_host_decoder_on_the_references_own_clip(emu):
 
 
 def test_unsupported_streams_are_rejected_not_guessed(emu):
-    """a CABAC / B-frame stream of the reference's test set must come back as a parse error, never as pictures"""
-    path = "/root/reference/res/test_cif_P_CABAC_slice.264"
+    """a B-frame stream of the reference's test set must come back as a parse error, never as pictures"""
+    path = "/root/reference/res/Cisco_Men_whisper_640x320_CABAC_Bframe_9.264"
     if not os.path.exists(path):
         pytest.skip("reference bitstreams not on this machine")
     a = np.fromfile(path, dtype=np.uint8)
@@ -110,9 +110,14 @@ def test_reference_conformance_table_exact_or_rejected(emu):
         (exact if h == sha else wrong).append(os.path.basename(path))
     assert not wrong, wrong
     assert {"BA1_Sony_D.jsv", "NL1_Sony_D.jsv", "SVA_BA1_B.264", "SVA_NL1_B.264"} <= set(exact)
+    # CABAC (I and P slices, several slices per picture, I_PCM under CABAC) and the CAVLC I_PCM / multi-reference streams
+    assert {"test_qcif_cabac.264", "test_cif_P_CABAC_slice.264", "test_cif_I_CABAC_slice.264", "test_cif_I_CABAC_PCM.264",
+            "CVPCMNL1_SVA_C.264", "MR2_TANDBERG_E.264"} <= set(exact)
+    assert len(exact) >= 40                      # of 51; rejected: B slices (8), scaling lists / 8x8 transform, SVC subset SPS
 
 
-def test_parser_survives_corrupted_streams(emu):
+@pytest.mark.parametrize("entropy", [(0, 66), (1, 0)])
+def test_parser_survives_corrupted_streams(emu, entropy):
     """bit flips, byte substitutions and deletions: the parser / host construct path must return (a picture or an
     error code), never crash; the same parser guards the GPU decoder's input (run under ASan during development)"""
     if not h264lib.have_ref():
@@ -121,7 +126,7 @@ def test_parser_survives_corrupted_streams(emu):
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
     from make_encoder_golden import ref_encode
     clip = h264lib.synth_clip(64, 48, 4, seed=3)
-    bs = bytes(ref_encode(clip, 64, 48, 4, 24, 30.0)[0])
+    bs = bytes(ref_encode(clip, 64, 48, 4, 24, 30.0, entropy=entropy)[0])
     out = np.zeros(8 << 20, np.uint8)
     rng = random.Random(7)
     seen_error = 0
@@ -172,6 +177,34 @@ def test_random_streams_host_decoder_vs_reference_decoder(emu):
         b = R.ref_decode(buf.ctypes.data, n, o2.ctypes.data, o2.size, C.byref(W2), C.byref(H2), C.byref(sec))
         assert a == n_pic and b == n_pic, (seed, a, b)
         assert np.array_equal(o1[:sz], o2[:sz]), seed
+
+
+def test_host_decoder_cabac_streams_of_our_encoder(emu):
+    """the host build of the encoder writes the same pictures with CAVLC and with CABAC (High and Main parameter sets): the CABAC
+    parser + construct path must give the encoder's own reconstruction, i.e. the same pictures as the CAVLC stream decodes to —
+    and what the reference decoder makes of the CABAC stream where it is available"""
+    emu.emu_encode.restype = C.c_long
+    emu.emu_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_long, C.c_void_p, C.c_void_p]
+    emu.emu_decode.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    for (w, h, n, qp, seed, noise) in [(176, 144, 5, 24, 3, 3), (320, 192, 4, 33, 5, 12), (64, 48, 4, 8, 6, 30), (180, 148, 4, 40, 9, 3)]:
+        yuv = h264lib.synth_clip(w, h, n, seed=seed, noise=noise)
+        pics = []
+        for entropy in ((0, 66), (1, 0), (1, 77)):
+            emu.emu_set_complexity_low(0)
+            emu.emu_set_entropy(*entropy)
+            bs, fb, rec = np.zeros(16 << 20, np.uint8), np.zeros(n, np.int32), np.zeros(yuv.size, np.uint8)
+            tot = emu.emu_encode(yuv.ctypes.data, w, h, n, qp, 30.0, bs.ctypes.data, bs.size, fb.ctypes.data, rec.ctypes.data)
+            assert tot > 0
+            out = np.zeros(yuv.size + 64, np.uint8)
+            W, H = C.c_int(), C.c_int()
+            assert emu.emu_decode(bs.ctypes.data, tot, out.ctypes.data, out.size, C.byref(W), C.byref(H)) == n
+            assert (W.value, H.value) == (w, h) and np.array_equal(out[:yuv.size], rec), entropy
+            if entropy[0] and h264lib.have_ref():
+                nr, rw, rh, want = ref_decode(bs[:tot].tobytes())
+                assert nr == n and np.array_equal(want[:yuv.size], rec)
+            pics.append(out[:yuv.size].copy())
+        emu.emu_set_entropy(0, 66)
+        assert np.array_equal(pics[0], pics[1]) and np.array_equal(pics[0], pics[2])
 
 
 CONF_DIR = os.path.join(ROOT, "tests", "golden", "conformance")

@@ -57,7 +57,7 @@ def test_gpu_decoder_rejects_unsupported_stream():
     from openh264_b200.binding import BatchDecoder, B2H264Error
     dec = BatchDecoder(176, 144)
     with pytest.raises(B2H264Error):
-        dec.decode([b"\x00\x00\x00\x01\x67\x64\x00\x1f\xac\xd9\x40\x50\x05\xbb\x01\x10"])      # a High-profile SPS
+        dec.decode([b"\x00\x00\x00\x01\x67\x6e\x00\x1f\xac\xd9\x40\x50\x05\xbb\x01\x10"])      # a High 10 profile SPS
     dec.close()
 
 
@@ -132,7 +132,7 @@ def test_gpu_decoder_per_stream_status_and_slot_reuse():
     streams = ref_streams(w, h, n, 28, (11, 12))
     want = [ref_decode(bs, w, h, n) for bs, _ in streams]
     fsz = w * h * 3 // 2
-    high_sps = b"\x00\x00\x00\x01\x67\x64\x00\x1f\xac\xd9\x40\x50\x05\xbb\x01\x10"
+    high_sps = b"\x00\x00\x00\x01\x67\x6e\x00\x1f\xac\xd9\x40\x50\x05\xbb\x01\x10"
     dec = BatchDecoder(w, h, n_streams=4, pinned_output=True)
     for f in range(n):
         a0 = streams[0][1][f]
@@ -150,3 +150,26 @@ def test_gpu_decoder_per_stream_status_and_slot_reuse():
         pics, st = dec.decode3([None, streams[0][1][f], None, None])
         assert st == [0, 1, 0, 0] and np.array_equal(pics[1], want[0][f * fsz:(f + 1) * fsz])
     dec.close()
+
+
+def test_gpu_decoder_cabac_streams_of_the_gpu_encoder():
+    """BatchEncoder writes the same pictures with CAVLC and with CABAC (High / Main parameter sets); the GPU decoder (host CABAC
+    parser, csrc/h264_cabac_dec.h, in front of the same construct kernels) must turn all three streams into the same pictures —
+    and into what the reference decoder makes of the CABAC stream where the reference is on the machine"""
+    from openh264_b200.binding import BatchDecoder, BatchEncoder
+    w, h, n, qp = 320, 192, 6, 25
+    yuv = h264lib.synth_clip(w, h, n, seed=21, noise=8)
+    fsz = w * h * 3 // 2
+    decoded = []
+    for cabac, prof in ((False, 0), (True, 0), (True, 77)):
+        enc = BatchEncoder(w, h, qp=qp, fps=30.0, n_streams=1, entropy_cabac=cabac, profile_idc=prof)
+        aus = [enc.encode([yuv[f * fsz:(f + 1) * fsz]])[0][0] for f in range(n)]
+        enc.close()
+        dec = BatchDecoder(w, h)
+        pics = np.concatenate([dec.decode([au])[0] for au in aus])
+        dec.close()
+        if cabac and h264lib.have_ref():
+            assert np.array_equal(ref_decode(b"".join(aus), w, h, n)[:pics.size], pics)
+        decoded.append(pics)
+    assert np.array_equal(decoded[0], decoded[1]) and np.array_equal(decoded[0], decoded[2])
+    assert len(decoded[0]) == n * fsz

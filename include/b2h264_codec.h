@@ -16,8 +16,8 @@
  *
  * Supported configuration (everything else is rejected with an error, never silently approximated):
  * CAMERA_VIDEO_REAL_TIME, 1 spatial / 1 temporal layer, RC_OFF_MODE (constant QP), SM_SINGLE_SLICE,
- * CAVLC or CABAC (Baseline / Main / High parameter sets, no 8x8 transform), any iComplexityMode (LOW / MEDIUM / HIGH), 1 reference frame, deblocking idc 0, IDR at the first frame (and on
- * ForceIntraFrame), no denoise / background detection / adaptive quant / scene-change / LTR.
+ * CAVLC or CABAC (Baseline / Main / High parameter sets, no 8x8 transform), any iComplexityMode (LOW / MEDIUM / HIGH), 1 reference frame, deblocking idc 0, IDR at the first frame, every uiIntraPeriod frames and on
+ * ForceIntraFrame, no denoise / background detection / adaptive quant / scene-change / LTR.
  * For that configuration the bitstream is bit-identical to the reference's.
  */
 #ifndef B2H264_CODEC_H
@@ -46,6 +46,8 @@ typedef struct {
   int32_t profile_idc;          /* SSpatialLayerConfig::uiProfileIdc: 0 unspecified (Baseline, High with CABAC), 66, 77 or 100; resolved
                                  * as the reference does (encoder_ext.cpp:126-141,652-664): Baseline turns CABAC off, other values
                                  * count as unspecified.  No High-profile tool is used (no 8x8 transform): only the SPS / PPS change */
+  int32_t intra_period;         /* SEncParamExt::uiIntraPeriod: 0 = only the first picture (and forced ones) is IDR; N: a stream codes an
+                                 * IDR picture once N - 1 P pictures followed the last one (wels_preprocess.cpp:369-371) */
 } b2h264_enc_config;
 
 /* returns 0 or a negative b2h264 error / positive cudaError_t */

@@ -31,6 +31,7 @@ struct b2h264_enc {
   int S = 0, n_mb = 0;
   std::vector<StreamCtl> ctl;
   std::vector<uint8_t> idr_next;          // per stream: code next picture as IDR
+  std::vector<int32_t> p_since_idr;       // per stream: P pictures since the last IDR (SSpatialLayerInternal::iFrameIndex)
   std::vector<uint8_t> have_ref_p;        // reference picture of the stream was a P picture
   int cur_rec = 0;                        // (unused: every stream keeps its own parity, stream_rec)
   std::vector<uint8_t> stream_rec;        // per stream: which of its two pictures is written next
@@ -105,6 +106,7 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
     c.increasing_ids = cfg->sps_pps_id_strategy != 0;
   }
   e->idr_next.assign(e->S, 1);
+  e->p_since_idr.assign(e->S, 0);
   e->have_ref_p.assign(e->S, 0);
   e->stream_rec.assign(e->S, 0);
   const StreamCtl& c0 = e->ctl[0];
@@ -235,7 +237,10 @@ int b2h264_enc_submit(b2h264_enc* e, const uint8_t* const* src, int src_on_devic
   sl.idr.assign(S, 0);
   for (int i = 0; i < n; i++) {
     const int s = sl.act[i];
-    const bool idr = e->idr_next[s] != 0;
+    // uiIntraPeriod: bIdrPeriodFlag = 1 + iFrameIndex >= uiIntraPeriod (wels_preprocess.cpp:369-371); iFrameIndex counts the P
+    // pictures since the last IDR (encoder.cpp:284,301)
+    const bool idr = e->idr_next[s] != 0 || (e->cfg.intra_period > 0 && 1 + e->p_since_idr[s] >= e->cfg.intra_period);
+    e->p_since_idr[s] = idr ? 0 : e->p_since_idr[s] + 1;
     sl.idr[s] = idr;
     StreamFrame& F = e->h_sf[k][i];
     F.p = e->ctl[s].frame_params(idr, e->have_ref_p[s] != 0);
@@ -330,6 +335,7 @@ int b2h264_enc_reset_stream(b2h264_enc* e, int stream) {
   e->ctl[stream].fast_mode = e->cfg.complexity_low != 0;
   e->ctl[stream].record_mb_bits = e->mb_bits_on;
   e->idr_next[stream] = 1;
+  e->p_since_idr[stream] = 0;
   e->have_ref_p[stream] = 0;
   // what a fresh encoder starts from: no SAD history, no reference-picture records
   CK(cudaMemsetAsync(e->d_sad + (size_t)stream * e->n_mb, 0, e->n_mb * sizeof(int32_t), e->st));

@@ -27,6 +27,7 @@ Pool::Pool(const PoolKey& key, int capacity, int device) : key_(key), cap_(capac
   cfg.complexity_low = key.complexity_low;
   cfg.entropy_cabac = key.entropy_cabac;
   cfg.profile_idc = key.profile_idc;
+  cfg.intra_period = key.intra_period;
   if (b2h264_enc_create(&cfg, &enc_) != 0) { enc_ = nullptr; return; }
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaHostAlloc((void**)&pinned_, frame_bytes_ * capacity, cudaHostAllocPortable) != cudaSuccess) {

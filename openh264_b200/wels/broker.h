@@ -25,11 +25,11 @@
 namespace b2wels {
 
 struct PoolKey {
-  int width, height, qp, bitrate, strategy, complexity_low, entropy_cabac, profile_idc;
+  int width, height, qp, bitrate, strategy, complexity_low, entropy_cabac, profile_idc, intra_period;
   float fps;
   bool operator==(const PoolKey& o) const {
     return width == o.width && height == o.height && qp == o.qp && bitrate == o.bitrate && strategy == o.strategy && complexity_low == o.complexity_low && entropy_cabac == o.entropy_cabac &&
-           profile_idc == o.profile_idc && fps == o.fps;
+           profile_idc == o.profile_idc && intra_period == o.intra_period && fps == o.fps;
   }
 };
 

@@ -65,7 +65,6 @@ class B2Encoder : public ISVCEncoder {
     REQUIRE(p->iRCMode == RC_OFF_MODE, "iRCMode != RC_OFF_MODE");
     REQUIRE(l.sSliceArgument.uiSliceMode == SM_SINGLE_SLICE, "uiSliceMode != SM_SINGLE_SLICE");
     REQUIRE(p->iNumRefFrame == 1 || p->iNumRefFrame == AUTO_REF_PIC_COUNT, "iNumRefFrame != 1");
-    REQUIRE(p->uiIntraPeriod == 0, "uiIntraPeriod != 0");
     REQUIRE(p->iLoopFilterDisableIdc == 0 && p->iLoopFilterAlphaC0Offset == 0 && p->iLoopFilterBetaOffset == 0, "loop filter idc/offsets != 0");
     REQUIRE(p->iComplexityMode == LOW_COMPLEXITY || p->iComplexityMode == MEDIUM_COMPLEXITY || p->iComplexityMode == HIGH_COMPLEXITY,
             "iComplexityMode");
@@ -102,6 +101,7 @@ class B2Encoder : public ISVCEncoder {
     // Baseline / Main / High counts as unspecified: encoder_ext.cpp:126-141,652-664)
     key.entropy_cabac = p->iEntropyCodingModeFlag != 0 ? 1 : 0;
     key.profile_idc = (int)l.uiProfileIdc;
+    key.intra_period = p->uiIntraPeriod == (unsigned int)-1 ? 0 : (int)p->uiIntraPeriod;       // param_svc.h:370-372 (GOP size 1: no rounding)
     pool_ = b2wels::Broker::get().attach(key, &slot_);
     if (!pool_ || slot_ < 0) { pool_.reset(); slot_ = -1; return cmMallocMemeError; }
     par_ = *p;

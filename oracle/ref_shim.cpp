@@ -239,8 +239,9 @@ extern "C" {
  * EncodeFrame in *enc_seconds; per-frame byte counts in frame_bytes[n]. */
 /* entropy coder / profile of the following ref_encode calls (0 / 66 = CAVLC Baseline, the default; 1 / 0 = CABAC with the profile the
  * reference picks itself, i.e. High; 1 / 77 = CABAC Main) */
-static int g_entropy_cabac = 0, g_profile_idc = 66;
+static int g_entropy_cabac = 0, g_profile_idc = 66, g_intra_period = 0;
 void ref_set_entropy (int cabac, int profile_idc) { g_entropy_cabac = cabac; g_profile_idc = profile_idc; }
+void ref_set_intra_period (int n) { g_intra_period = n; }      /* uiIntraPeriod of the following ref_encode calls (0: the default) */
 
 long ref_encode (const uint8_t* yuv, int w, int h, int n, int qp, int complexity, int threads, float fps,
                  uint8_t* out, long out_cap, int32_t* frame_bytes, double* enc_seconds) {
@@ -256,7 +257,7 @@ long ref_encode (const uint8_t* yuv, int w, int h, int n, int qp, int complexity
   p.iTemporalLayerNum = 1;
   p.iSpatialLayerNum = 1;
   p.iComplexityMode = (ECOMPLEXITY_MODE) complexity;
-  p.uiIntraPeriod = 0;
+  p.uiIntraPeriod = (unsigned int) g_intra_period;
   p.iNumRefFrame = 1;
   p.iEntropyCodingModeFlag = g_entropy_cabac;
   p.bEnableFrameSkip = false;

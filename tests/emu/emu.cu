@@ -29,6 +29,7 @@ static bool same_record(const MbOut& a, const MbOut& b);
 namespace {
 
 // host-memory twin of the product's device-side frame buffers
+static int g_emu_intra_period = 0;                    // uiIntraPeriod, the rule of csrc/enc_batch.cu (b2h264_enc_submit)
 static int g_emu_cabac = 0, g_emu_profile = 0;       // entropy coder of the host writer (the macroblock decisions do not depend on it)
 struct HostFrameEncoder {
   b2h264::StreamCtl ctl;
@@ -44,6 +45,7 @@ struct HostFrameEncoder {
   MbScratch scratch;
   int cur_rec = 0;
   bool idr = true, have_ref_p = false;
+  int p_since_idr = 0;
 
   HostFrameEncoder(int w, int h, int qp, float fps) {
     ctl.init(w, h, qp, fps, 5000000, g_emu_cabac, g_emu_profile);
@@ -64,7 +66,8 @@ struct HostFrameEncoder {
     b2h264::pad_source(yuv, ctl.sp.width, ctl.sp.height, ctl.sp.mb_w, ctl.sp.mb_h, cur[0].data(), cur[1].data(), cur[2].data());
   }
   void begin_frame() {
-    idr = ctl.next_is_idr();
+    idr = ctl.next_is_idr() || (g_emu_intra_period > 0 && 1 + p_since_idr >= g_emu_intra_period);
+    p_since_idr = idr ? 0 : p_since_idr + 1;
     p = ctl.frame_params(idr, have_ref_p);
     if (ctl.fast_mode) {
       // VAACalcSad_c (codec/processing/src/vaacalc/vaacalcfuncs.cpp:254): 8x8 SADs of the (w >> 4) x (h >> 4) whole macroblocks
@@ -205,6 +208,7 @@ extern "C" int emu_last(MbOut* out, MbInfo* info, int n) {
 }
 static int g_emu_fast_mode = 0;
 extern "C" void emu_set_entropy(int cabac, int profile_idc) { g_emu_cabac = cabac; g_emu_profile = profile_idc; }
+extern "C" void emu_set_intra_period(int n) { g_emu_intra_period = n; }
 extern "C" void emu_set_complexity_low(int on) { g_emu_fast_mode = on; }
 extern "C" long emu_encode(const uint8_t* yuv, int w, int h, int nframes, int qp, float fps, uint8_t* out, long cap,
                            int32_t* frame_bytes, uint8_t* recon_out /* nframes * w*h*3/2 or NULL */) {

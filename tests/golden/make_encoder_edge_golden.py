@@ -66,5 +66,11 @@ if __name__ == "__main__":
         gold["cabac"]["%dx%d_n%d_qp%d_seed%d_noise%d_profile%d" % (w, h, n, qp, seed, noise, prof)] = {"sha1": hashlib.sha1(bs).hexdigest(), "frame_bytes": fb}
     bs, fb, _ = ref_encode(yuv, 320, 192, 9, 30, 12.0, complexity=0, entropy=(1, 0))
     gold["cabac"]["clip_qp30_profile0_low"] = {"sha1": hashlib.sha1(bs).hexdigest(), "frame_bytes": fb}
+    # uiIntraPeriod: periodic IDR pictures (with the INCREASING_ID parameter-set strategy every IDR brings new SPS / PPS ids)
+    gold["intra_period"] = {}
+    for (w, h, n, qp, seed, period, ent) in [(176, 144, 8, 27, 3, 3, (0, 66)), (320, 192, 7, 31, 4, 2, (1, 0)), (64, 64, 4, 20, 5, 1, (0, 66))]:
+        y = h264lib.synth_clip(w, h, n, seed=seed)
+        bs, fb, _ = ref_encode(y, w, h, n, qp, 30.0, entropy=ent, intra_period=period)
+        gold["intra_period"]["%dx%d_n%d_qp%d_seed%d_period%d_cabac%d" % (w, h, n, qp, seed, period, ent[0])] = {"sha1": hashlib.sha1(bs).hexdigest(), "frame_bytes": fb}
     json.dump(gold, open(os.path.join(HERE, "encoder_edge.json"), "w"), indent=1, sort_keys=True)
     print(json.dumps(gold, indent=1))

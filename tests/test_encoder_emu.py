@@ -28,9 +28,10 @@ def emu():
     return E
 
 
-def emu_encode(E, yuv, w, h, n, qp, fps, low=False, entropy=(0, 66)):
+def emu_encode(E, yuv, w, h, n, qp, fps, low=False, entropy=(0, 66), intra_period=0):
     E.emu_set_complexity_low(1 if low else 0)
     E.emu_set_entropy(*entropy)
+    E.emu_set_intra_period(intra_period)
     cap = 32 << 20
     out, fb = np.zeros(cap, np.uint8), np.zeros(n, np.int32)
     tot = E.emu_encode(yuv.ctypes.data, w, h, n, qp, fps, out.ctypes.data, cap, fb.ctypes.data, None)
@@ -174,3 +175,14 @@ def test_emu_cabac_matches_reference_side_by_side(emu):
         ran += 1
     if not ran:
         pytest.skip("no reference clips on this machine")
+
+
+@pytest.mark.parametrize("key", sorted(EDGE["intra_period"]))
+def test_emu_intra_period_matches_reference_golden(emu, key):
+    """uiIntraPeriod: periodic IDR pictures, each with fresh parameter-set ids (INCREASING_ID), frame_num / idr_pic_id restarts"""
+    g = EDGE["intra_period"][key]
+    w, h = map(int, key.split("_")[0].split("x"))
+    f = {k: int(key.split("_" + k)[1].split("_")[0]) for k in ("n", "qp", "seed", "period", "cabac")}
+    yuv = h264lib.synth_clip(w, h, f["n"], seed=f["seed"])
+    bs, fb = emu_encode(emu, yuv, w, h, f["n"], f["qp"], 30.0, entropy=(f["cabac"], 0 if f["cabac"] else 66), intra_period=f["period"])
+    assert fb == g["frame_bytes"] and hashlib.sha1(bs).hexdigest() == g["sha1"]

@@ -251,3 +251,23 @@ def test_cabac_through_cuda(key):
     enc.close()
     assert [len(b) for b in out[0]] == g["frame_bytes"]
     assert hashlib.sha1(b"".join(out[0])).hexdigest() == g["sha1"] and out[1] == out[0]
+
+
+@pytest.mark.parametrize("key", sorted(EDGE["intra_period"]))
+def test_intra_period_through_cuda(key):
+    """uiIntraPeriod in layer 2 (b2h264_enc_config::intra_period): periodic IDR pictures per stream; golden = the unmodified reference"""
+    from openh264_b200.binding import BatchEncoder
+    g = EDGE["intra_period"][key]
+    w, h = map(int, key.split("_")[0].split("x"))
+    f = {k: int(key.split("_" + k)[1].split("_")[0]) for k in ("n", "qp", "seed", "period", "cabac")}
+    yuv = h264lib.synth_clip(w, h, f["n"], seed=f["seed"])
+    enc = BatchEncoder(w, h, qp=f["qp"], fps=30.0, n_streams=2, entropy_cabac=bool(f["cabac"]), intra_period=f["period"])
+    fsz = w * h * 3 // 2
+    out = [[], []]
+    for i in range(f["n"]):
+        frames = [yuv[i * fsz:(i + 1) * fsz], yuv[i * fsz:(i + 1) * fsz]]
+        bs, _ = enc.encode(frames)
+        out[0].append(bs[0]); out[1].append(bs[1])
+    enc.close()
+    assert [len(b) for b in out[0]] == g["frame_bytes"]
+    assert hashlib.sha1(b"".join(out[0])).hexdigest() == g["sha1"] and out[1] == out[0]

@@ -19,12 +19,14 @@ need_built = pytest.mark.skipif(not (os.path.exists(DRIVER) and os.path.exists(O
                                 reason="layer-3 shim / driver are built where the reference headers exist (build())")
 
 
-def drive(lib, clip, w, h, n, qp, idr_at, tmp, tag, entropy=None):
+def drive(lib, clip, w, h, n, qp, idr_at, tmp, tag, entropy=None, intra_period=None):
     yuv = os.path.join(tmp, "in.yuv")
     with open(yuv, "wb") as f:
         f.write(clip.tobytes())
     out, lay = os.path.join(tmp, tag + ".264"), os.path.join(tmp, tag + ".layout")
     extra = [str(entropy[0]), str(entropy[1])] if entropy else []
+    if intra_period is not None:
+        extra = (extra or ["0", "66"]) + [str(intra_period)]
     r = subprocess.run([DRIVER, lib, yuv, str(w), str(h), str(n), str(qp), str(idr_at), out, lay] + extra, capture_output=True, text=True,
                        timeout=300)
     return r, (open(out, "rb").read() if os.path.exists(out) else b""), (open(lay).read() if os.path.exists(lay) else "")
@@ -74,6 +76,19 @@ def test_drop_in_same_driver_two_libraries(tmp_path, w, h, n, qp, idr_at):
     assert r1.returncode == 0, r1.stderr
     assert bs0 == bs1, "bitstream through ISVCEncoder differs from the reference"
     assert lay0 == lay1, "SFrameBSInfo layout / defaults differ:\n" + lay0 + "\n---\n" + lay1
+
+
+@pytest.mark.gpu
+def test_drop_in_intra_period(tmp_path):
+    """uiIntraPeriod through ISVCEncoder (with a forced IDR in between, which restarts the period)"""
+    assert os.path.exists(DRIVER) and os.path.exists(OURLIB), "prebuilt layer-3 artefacts missing on the GPU box"
+    w, h, n, qp = 176, 144, 9, 29
+    clip = h264lib.synth_clip(w, h, n, seed=13)
+    r0, bs0, lay0 = drive(REFLIB, clip, w, h, n, qp, 4, str(tmp_path), "ref", intra_period=3)
+    r1, bs1, lay1 = drive(OURLIB, clip, w, h, n, qp, 4, str(tmp_path), "b2", intra_period=3)
+    assert r0.returncode == 0, r0.stderr
+    assert r1.returncode == 0, r1.stderr
+    assert bs0 == bs1 and lay0 == lay1
 
 
 @pytest.mark.gpu

@@ -53,6 +53,7 @@ int main(int argc, char** argv) {
     p.iEntropyCodingModeFlag = atoi(argv[10]);
     p.sSpatialLayers[0].uiProfileIdc = (EProfileIdc)atoi(argv[11]);
   }
+  if (argc > 12) p.uiIntraPeriod = (unsigned int)atoi(argv[12]);   // optional: uiIntraPeriod
   p.sSpatialLayers[0].sSliceArgument.uiSliceMode = SM_SINGLE_SLICE;
   int rc = enc->InitializeExt(&p);
   if (rc) { fprintf(stderr, "InitializeExt -> %d\n", rc); return 5; }

@@ -16,7 +16,7 @@
  *
  * Supported configuration (everything else is rejected with an error, never silently approximated):
  * CAMERA_VIDEO_REAL_TIME, 1 spatial / 1 temporal layer, RC_OFF_MODE (constant QP), SM_SINGLE_SLICE,
- * CAVLC or CABAC (Baseline / Main / High parameter sets, no 8x8 transform), any iComplexityMode (LOW / MEDIUM / HIGH), 1 reference frame, deblocking idc 0, IDR at the first frame, every uiIntraPeriod frames and on
+ * CAVLC or CABAC (Baseline / Main / High parameter sets, no 8x8 transform), any iComplexityMode (LOW / MEDIUM / HIGH), 1 reference frame, any loop filter idc / offsets, IDR at the first frame, every uiIntraPeriod frames and on
  * ForceIntraFrame, no denoise / background detection / adaptive quant / scene-change / LTR.
  * For that configuration the bitstream is bit-identical to the reference's.
  */
@@ -48,6 +48,8 @@ typedef struct {
                                  * count as unspecified.  No High-profile tool is used (no 8x8 transform): only the SPS / PPS change */
   int32_t intra_period;         /* SEncParamExt::uiIntraPeriod: 0 = only the first picture (and forced ones) is IDR; N: a stream codes an
                                  * IDR picture once N - 1 P pictures followed the last one (wels_preprocess.cpp:369-371) */
+  int32_t loop_filter_idc;      /* iLoopFilterDisableIdc: 0 on, 1 off, 2 = 0 (one slice per picture) */
+  int32_t loop_filter_alpha_c0_offset, loop_filter_beta_offset;   /* iLoopFilterAlphaC0Offset / iLoopFilterBetaOffset, -6..6 */
 } b2h264_enc_config;
 
 /* returns 0 or a negative b2h264 error / positive cudaError_t */

@@ -106,7 +106,8 @@ class EncConfig(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("qp", C.c_int32), ("fps", C.c_float),
                 ("target_bitrate", C.c_int32), ("n_streams", C.c_int32), ("entropy_threads", C.c_int32),
                 ("device", C.c_int32), ("sps_pps_id_strategy", C.c_int32), ("complexity_low", C.c_int32),
-                ("entropy_cabac", C.c_int32), ("profile_idc", C.c_int32), ("intra_period", C.c_int32)]
+                ("entropy_cabac", C.c_int32), ("profile_idc", C.c_int32), ("intra_period", C.c_int32),
+                ("loop_filter_idc", C.c_int32), ("loop_filter_alpha_c0_offset", C.c_int32), ("loop_filter_beta_offset", C.c_int32)]
 
 
 _RESTYPES = {"b2h264_enc_destroy": None, "b2h264_dec_destroy": None, "b2h264_host_alloc": C.c_void_p, "b2h264_host_free": None, "b2h264_error_string": C.c_char_p, "b2h264_launch_count": C.c_ulonglong,
@@ -194,10 +195,10 @@ class BatchEncoder:
     stream per call; returns the Annex-B access units.  No computation happens in Python."""
 
     def __init__(self, width, height, qp=26, fps=30.0, n_streams=1, target_bitrate=5000000, entropy_threads=0, device=0,
-                 sps_pps_id_strategy=1, complexity_low=False, entropy_cabac=False, profile_idc=0, intra_period=0):
+                 sps_pps_id_strategy=1, complexity_low=False, entropy_cabac=False, profile_idc=0, intra_period=0, loop_filter=(0, 0, 0)):
         self.L = lib(device)
         self.cfg = EncConfig(width, height, qp, fps, target_bitrate, n_streams, entropy_threads, device, sps_pps_id_strategy,
-                             1 if complexity_low else 0, 1 if entropy_cabac else 0, profile_idc, intra_period)
+                             1 if complexity_low else 0, 1 if entropy_cabac else 0, profile_idc, intra_period, *loop_filter)
         self.h = vp()
         check(self.L.b2h264_enc_create(C.byref(self.cfg), C.byref(self.h)))
         self.n = n_streams

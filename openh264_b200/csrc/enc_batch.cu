@@ -103,6 +103,7 @@ int b2h264_enc_create(const b2h264_enc_config* cfg, b2h264_enc** out) {
   for (auto& c : e->ctl) {
     c.init(cfg->width, cfg->height, cfg->qp, cfg->fps, cfg->target_bitrate, cfg->entropy_cabac, cfg->profile_idc);
     c.fast_mode = cfg->complexity_low != 0;
+    if (!c.set_loop_filter(cfg->loop_filter_idc, cfg->loop_filter_alpha_c0_offset, cfg->loop_filter_beta_offset)) { delete e; return -1; }
     c.increasing_ids = cfg->sps_pps_id_strategy != 0;
   }
   e->idr_next.assign(e->S, 1);
@@ -333,6 +334,7 @@ int b2h264_enc_reset_stream(b2h264_enc* e, int stream) {
   e->ctl[stream].init(e->cfg.width, e->cfg.height, e->cfg.qp, e->cfg.fps, e->cfg.target_bitrate, e->cfg.entropy_cabac, e->cfg.profile_idc);
   e->ctl[stream].increasing_ids = e->cfg.sps_pps_id_strategy != 0;
   e->ctl[stream].fast_mode = e->cfg.complexity_low != 0;
+  e->ctl[stream].set_loop_filter(e->cfg.loop_filter_idc, e->cfg.loop_filter_alpha_c0_offset, e->cfg.loop_filter_beta_offset);
   e->ctl[stream].record_mb_bits = e->mb_bits_on;
   e->idr_next[stream] = 1;
   e->p_since_idr[stream] = 0;

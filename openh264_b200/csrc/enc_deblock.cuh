@@ -86,8 +86,8 @@ MBK_HD void deblock_one_mb(const EncFrameParams& p, const EncFramePtrs& f, int m
   const MbInfo* cur = &t.m[0];
   uint8_t* ty = t.y + 4 * DBK_PY + 4;
   // decoder: per-slice control travels in MbInfo::p16x16_mv (dec_mb.cuh): disable_deblocking_filter_idc, FilterOffsetA / B and the
-  // slice number (idc 2: edges between slices stay unfiltered).  The encoder path always filters with offsets 0.
-  int idc = 0, off_a = 0, off_b = 0;
+  // slice number (idc 2: edges between slices stay unfiltered).  The encoder path codes one slice: its control is per picture.
+  int idc = p.dbk_idc, off_a = p.dbk_off_a, off_b = p.dbk_off_b;
   if (p.dec_mode) {
     const int v = (uint16_t)cur->p16x16_mv[1];
     idc = v & 3; off_a = ((v >> 2) & 31) - 16; off_b = ((v >> 7) & 31) - 16;

@@ -40,6 +40,7 @@ EncFrameParams StreamCtl::frame_params(bool idr, bool ref_is_p) const {
   p.mv_range = sp.level_idc <= 10 ? 63 : 64;
   p.ref_is_p = ref_is_p;
   p.fast_mode = fast_mode ? 1 : 0;
+  p.dbk_idc = sp.dbk_idc; p.dbk_off_a = 2 * sp.dbk_alpha_div2; p.dbk_off_b = 2 * sp.dbk_beta_div2;
   return p;
 }
 

@@ -35,6 +35,13 @@ struct StreamCtl {
 
   void init(int width, int height, int qp, float fps_, int target_bitrate, int entropy_cabac = 0, int profile_idc = 0);
   bool next_is_idr() const { return force_idr; }
+  // iLoopFilterDisableIdc / iLoopFilterAlphaC0Offset / iLoopFilterBetaOffset (after init): with one slice per picture idc 2 is
+  // idc 0 (encoder_ext.cpp:1109-1114); false if a value is out of range (encoder_ext.cpp:316-318)
+  bool set_loop_filter(int idc, int alpha_c0_offset, int beta_offset) {
+    if (idc < 0 || idc > 2 || alpha_c0_offset < -6 || alpha_c0_offset > 6 || beta_offset < -6 || beta_offset > 6) return false;
+    sp.dbk_idc = idc == 2 ? 0 : idc; sp.dbk_alpha_div2 = alpha_c0_offset; sp.dbk_beta_div2 = beta_offset;
+    return true;
+  }
   // geometry of the padded pictures (picture_handle.cpp:60-85: 32-pixel luma padding)
   int rec_stride_y() const { return sp.mb_w * 16 + 64; }
   int rec_stride_c() const { return sp.mb_w * 8 + 32; }

@@ -82,6 +82,7 @@ typedef struct {
   int32_t dec_mode;                       // 1: decoder construct path (MbInfo::p16x16_mv carries slice / deblocking control)
   int32_t fast_mode;                      // iComplexityMode == LOW_COMPLEXITY: SAD mode costs, VAA-driven partition choice
                                           // (SetFastCodingFunc / WelsMdInterFinePartitionVaa, encoder_ext.cpp:2616,2688)
+  int32_t dbk_idc, dbk_off_a, dbk_off_b;  // encoder: disable_deblocking_filter_idc (0 / 1), FilterOffsetA / B (2 x the slice header's div2 values)
 } EncFrameParams;
 
 typedef struct {

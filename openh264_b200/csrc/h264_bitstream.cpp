@@ -196,7 +196,8 @@ void write_slice(const StreamParams& sp, const SliceState& ss, const MbOut* cons
     w.bit(0); w.bit(0);                  // no_output_of_prior_pics_flag, long_term_reference_flag
   }
   w.se(ss.qp - 26);                      // slice_qp_delta
-  w.ue(0); w.se(0); w.se(0);             // disable_deblocking_filter_idc, alpha_c0 / beta offsets div2
+  w.ue((uint32_t)sp.dbk_idc);            // disable_deblocking_filter_idc; the offsets only with the filter on (svc_encode_slice.cpp:404-410)
+  if (sp.dbk_idc != 1) { w.se(sp.dbk_alpha_div2); w.se(sp.dbk_beta_div2); }
 
   // ---- slice data ----
   const int mbw = sp.mb_w, n = sp.mb_w * sp.mb_h;

@@ -50,6 +50,8 @@ struct StreamParams {
   int sps_id, pps_id;           // ids written into the parameter sets / slice headers (paraset_strategy.cpp)
   int profile_idc = 66;         // 66 Baseline (CAVLC); with CABAC the reference picks High (100) unless the layer asks for Main (77)
   bool entropy_cabac = false;   // entropy_coding_mode_flag
+  // slice header: disable_deblocking_filter_idc (0 / 1), slice_alpha_c0_offset_div2, slice_beta_offset_div2 (-6..6)
+  int dbk_idc = 0, dbk_alpha_div2 = 0, dbk_beta_div2 = 0;
 };
 
 // level selection (WelsGetLevelIdc, au_set.cpp:51-195; limits = H.264 Table A-1)

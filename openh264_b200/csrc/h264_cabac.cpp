@@ -175,7 +175,8 @@ void write_slice_cabac(const StreamParams& sp, const SliceState& ss, const MbOut
     w.bit(0); w.bit(0);                  // no_output_of_prior_pics_flag, long_term_reference_flag
   }
   w.se(ss.qp - 26);                      // slice_qp_delta
-  w.ue(0); w.se(0); w.se(0);             // disable_deblocking_filter_idc, alpha_c0 / beta offsets div2
+  w.ue((uint32_t)sp.dbk_idc);            // disable_deblocking_filter_idc; the offsets only with the filter on (svc_encode_slice.cpp:404-410)
+  if (sp.dbk_idc != 1) { w.se(sp.dbk_alpha_div2); w.se(sp.dbk_beta_div2); }
   while (w.bit_pos() & 7) w.bit(1);      // cabac_alignment_one_bit
 
   CabacEncoder e(&w);

@@ -28,6 +28,7 @@ Pool::Pool(const PoolKey& key, int capacity, int device) : key_(key), cap_(capac
   cfg.entropy_cabac = key.entropy_cabac;
   cfg.profile_idc = key.profile_idc;
   cfg.intra_period = key.intra_period;
+  cfg.loop_filter_idc = key.dbk_idc; cfg.loop_filter_alpha_c0_offset = key.dbk_alpha; cfg.loop_filter_beta_offset = key.dbk_beta;
   if (b2h264_enc_create(&cfg, &enc_) != 0) { enc_ = nullptr; return; }
   if (cudaSetDevice(device) != cudaSuccess ||
       cudaHostAlloc((void**)&pinned_, frame_bytes_ * capacity, cudaHostAllocPortable) != cudaSuccess) {

@@ -25,11 +25,12 @@
 namespace b2wels {
 
 struct PoolKey {
-  int width, height, qp, bitrate, strategy, complexity_low, entropy_cabac, profile_idc, intra_period;
+  int width, height, qp, bitrate, strategy, complexity_low, entropy_cabac, profile_idc, intra_period, dbk_idc, dbk_alpha, dbk_beta;
   float fps;
   bool operator==(const PoolKey& o) const {
     return width == o.width && height == o.height && qp == o.qp && bitrate == o.bitrate && strategy == o.strategy && complexity_low == o.complexity_low && entropy_cabac == o.entropy_cabac &&
-           profile_idc == o.profile_idc && intra_period == o.intra_period && fps == o.fps;
+           profile_idc == o.profile_idc && intra_period == o.intra_period && dbk_idc == o.dbk_idc &&
+           dbk_alpha == o.dbk_alpha && dbk_beta == o.dbk_beta && fps == o.fps;
   }
 };
 

@@ -65,7 +65,8 @@ class B2Encoder : public ISVCEncoder {
     REQUIRE(p->iRCMode == RC_OFF_MODE, "iRCMode != RC_OFF_MODE");
     REQUIRE(l.sSliceArgument.uiSliceMode == SM_SINGLE_SLICE, "uiSliceMode != SM_SINGLE_SLICE");
     REQUIRE(p->iNumRefFrame == 1 || p->iNumRefFrame == AUTO_REF_PIC_COUNT, "iNumRefFrame != 1");
-    REQUIRE(p->iLoopFilterDisableIdc == 0 && p->iLoopFilterAlphaC0Offset == 0 && p->iLoopFilterBetaOffset == 0, "loop filter idc/offsets != 0");
+    if (p->iLoopFilterDisableIdc < 0 || p->iLoopFilterDisableIdc > 2 || p->iLoopFilterAlphaC0Offset < -6 || p->iLoopFilterAlphaC0Offset > 6 ||
+        p->iLoopFilterBetaOffset < -6 || p->iLoopFilterBetaOffset > 6) return cmInitParaError;       // encoder_ext.cpp:316-323
     REQUIRE(p->iComplexityMode == LOW_COMPLEXITY || p->iComplexityMode == MEDIUM_COMPLEXITY || p->iComplexityMode == HIGH_COMPLEXITY,
             "iComplexityMode");
     REQUIRE(!p->bEnableDenoise && !p->bEnableBackgroundDetection && !p->bEnableAdaptiveQuant && !p->bEnableSceneChangeDetect,
@@ -101,10 +102,20 @@ class B2Encoder : public ISVCEncoder {
     // Baseline / Main / High counts as unspecified: encoder_ext.cpp:126-141,652-664)
     key.entropy_cabac = p->iEntropyCodingModeFlag != 0 ? 1 : 0;
     key.profile_idc = (int)l.uiProfileIdc;
+    key.dbk_idc = p->iLoopFilterDisableIdc; key.dbk_alpha = p->iLoopFilterAlphaC0Offset; key.dbk_beta = p->iLoopFilterBetaOffset;
     key.intra_period = p->uiIntraPeriod == (unsigned int)-1 ? 0 : (int)p->uiIntraPeriod;       // param_svc.h:370-372 (GOP size 1: no rounding)
     pool_ = b2wels::Broker::get().attach(key, &slot_);
     if (!pool_ || slot_ < 0) { pool_.reset(); slot_ = -1; return cmMallocMemeError; }
     par_ = *p;
+    // what GetOption(ENCODER_OPTION_SVC_ENCODE_PARAM_EXT) reports is the RESOLVED configuration, as with the reference
+    // (param_svc.h:370-372, encoder_ext.cpp:126-141,652-664)
+    if (par_.uiIntraPeriod == (unsigned int)-1) par_.uiIntraPeriod = 0;
+    {
+      EProfileIdc& pr = par_.sSpatialLayers[0].uiProfileIdc;
+      if (pr != PRO_BASELINE && pr != PRO_MAIN && pr != PRO_HIGH) pr = PRO_UNKNOWN;
+      if (pr == PRO_BASELINE) par_.iEntropyCodingModeFlag = 0;
+      if (pr == PRO_UNKNOWN) pr = par_.iEntropyCodingModeFlag ? PRO_HIGH : PRO_BASELINE;
+    }
     w_ = key.width; h_ = key.height;
     return cmResultSuccess;
   }
@@ -161,10 +172,14 @@ class B2Encoder : public ISVCEncoder {
         return cmResultSuccess;                                    // this library does not trace
       case ENCODER_OPTION_DATAFORMAT:
         return *(int*)v == videoFormatI420 ? cmResultSuccess : cmInitParaError;
-      case ENCODER_OPTION_IDR_INTERVAL:
-        if (*(int*)v == 0) return cmResultSuccess;
-        why("ENCODER_OPTION_IDR_INTERVAL != 0");
+      case ENCODER_OPTION_IDR_INTERVAL: {
+        // the period is part of the shared encoder's configuration: it can be set before InitializeExt (through the parameters),
+        // a change on a running stream would need the stream to move to another pool
+        const int want = *(int*)v == -1 ? 0 : *(int*)v;
+        if (want == (int)par_.uiIntraPeriod) return cmResultSuccess;
+        why("ENCODER_OPTION_IDR_INTERVAL: changing uiIntraPeriod of a running stream (set it in InitializeExt)");
         return cmUnsupportedData;
+      }
       default:
         why("SetOption: option not supported by the constant-QP single-layer pipeline");
         return cmUnsupportedData;
@@ -176,7 +191,7 @@ class B2Encoder : public ISVCEncoder {
     if (!pool_) return cmInitExpected;
     switch (id) {
       case ENCODER_OPTION_DATAFORMAT: *(int*)v = videoFormatI420; return cmResultSuccess;
-      case ENCODER_OPTION_IDR_INTERVAL: *(int*)v = 0; return cmResultSuccess;
+      case ENCODER_OPTION_IDR_INTERVAL: *(int*)v = (int)par_.uiIntraPeriod; return cmResultSuccess;
       case ENCODER_OPTION_SVC_ENCODE_PARAM_EXT: *(SEncParamExt*)v = par_; return cmResultSuccess;
       case ENCODER_OPTION_FRAME_RATE: *(float*)v = par_.fMaxFrameRate; return cmResultSuccess;
       default: return cmInitParaError;

@@ -241,6 +241,8 @@ extern "C" {
  * reference picks itself, i.e. High; 1 / 77 = CABAC Main) */
 static int g_entropy_cabac = 0, g_profile_idc = 66, g_intra_period = 0;
 void ref_set_entropy (int cabac, int profile_idc) { g_entropy_cabac = cabac; g_profile_idc = profile_idc; }
+static int g_dbk_idc = 0, g_dbk_alpha = 0, g_dbk_beta = 0;
+void ref_set_loop_filter (int idc, int alpha, int beta) { g_dbk_idc = idc; g_dbk_alpha = alpha; g_dbk_beta = beta; }   /* iLoopFilterDisableIdc / offsets */
 void ref_set_intra_period (int n) { g_intra_period = n; }      /* uiIntraPeriod of the following ref_encode calls (0: the default) */
 
 long ref_encode (const uint8_t* yuv, int w, int h, int n, int qp, int complexity, int threads, float fps,
@@ -263,7 +265,9 @@ long ref_encode (const uint8_t* yuv, int w, int h, int n, int qp, int complexity
   p.bEnableFrameSkip = false;
   p.bEnableLongTermReference = false;
   p.iMultipleThreadIdc = (unsigned short) threads;
-  p.iLoopFilterDisableIdc = 0;
+  p.iLoopFilterDisableIdc = g_dbk_idc;
+  p.iLoopFilterAlphaC0Offset = g_dbk_alpha;
+  p.iLoopFilterBetaOffset = g_dbk_beta;
   p.bEnableDenoise = false;
   p.bEnableBackgroundDetection = false;
   p.bEnableAdaptiveQuant = false;

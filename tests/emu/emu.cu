@@ -29,6 +29,7 @@ static bool same_record(const MbOut& a, const MbOut& b);
 namespace {
 
 // host-memory twin of the product's device-side frame buffers
+static int g_emu_dbk[3] = {0, 0, 0};                  // iLoopFilterDisableIdc, alpha / beta offsets
 static int g_emu_intra_period = 0;                    // uiIntraPeriod, the rule of csrc/enc_batch.cu (b2h264_enc_submit)
 static int g_emu_cabac = 0, g_emu_profile = 0;       // entropy coder of the host writer (the macroblock decisions do not depend on it)
 struct HostFrameEncoder {
@@ -49,6 +50,7 @@ struct HostFrameEncoder {
 
   HostFrameEncoder(int w, int h, int qp, float fps) {
     ctl.init(w, h, qp, fps, 5000000, g_emu_cabac, g_emu_profile);
+    ctl.set_loop_filter(g_emu_dbk[0], g_emu_dbk[1], g_emu_dbk[2]);
     const int n = ctl.sp.mb_w * ctl.sp.mb_h;
     cur[0].resize((size_t)n * 256 + 64); cur[1].resize((size_t)n * 64 + 64); cur[2].resize((size_t)n * 64 + 64);
     for (int b = 0; b < 2; b++) {
@@ -208,6 +210,7 @@ extern "C" int emu_last(MbOut* out, MbInfo* info, int n) {
 }
 static int g_emu_fast_mode = 0;
 extern "C" void emu_set_entropy(int cabac, int profile_idc) { g_emu_cabac = cabac; g_emu_profile = profile_idc; }
+extern "C" void emu_set_loop_filter(int idc, int a, int b) { g_emu_dbk[0] = idc; g_emu_dbk[1] = a; g_emu_dbk[2] = b; }
 extern "C" void emu_set_intra_period(int n) { g_emu_intra_period = n; }
 extern "C" void emu_set_complexity_low(int on) { g_emu_fast_mode = on; }
 extern "C" long emu_encode(const uint8_t* yuv, int w, int h, int nframes, int qp, float fps, uint8_t* out, long cap,

@@ -72,5 +72,12 @@ if __name__ == "__main__":
         y = h264lib.synth_clip(w, h, n, seed=seed)
         bs, fb, _ = ref_encode(y, w, h, n, qp, 30.0, entropy=ent, intra_period=period)
         gold["intra_period"]["%dx%d_n%d_qp%d_seed%d_period%d_cabac%d" % (w, h, n, qp, seed, period, ent[0])] = {"sha1": hashlib.sha1(bs).hexdigest(), "frame_bytes": fb}
+    # iLoopFilterDisableIdc / iLoopFilterAlphaC0Offset / iLoopFilterBetaOffset
+    gold["loop_filter"] = {}
+    for (w, h, n, qp, seed, lf, ent) in [(176, 144, 5, 30, 3, (1, 0, 0), (0, 66)), (176, 144, 5, 30, 3, (0, 3, -2), (0, 66)), (320, 192, 4, 36, 4, (2, -6, 6), (1, 0)),
+                                           (64, 64, 4, 24, 5, (0, 6, 6), (0, 66)), (180, 148, 4, 40, 6, (0, -4, -5), (0, 66))]:
+        y = h264lib.synth_clip(w, h, n, seed=seed, noise=6)
+        bs, fb, _ = ref_encode(y, w, h, n, qp, 30.0, entropy=ent, loop_filter=lf)
+        gold["loop_filter"]["%dx%d_n%d_qp%d_seed%d_idc%d_a%d_b%d_cabac%d" % (w, h, n, qp, seed, lf[0], lf[1], lf[2], ent[0])] = {"sha1": hashlib.sha1(bs).hexdigest(), "frame_bytes": fb}
     json.dump(gold, open(os.path.join(HERE, "encoder_edge.json"), "w"), indent=1, sort_keys=True)
     print(json.dumps(gold, indent=1))

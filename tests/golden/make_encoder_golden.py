@@ -16,7 +16,7 @@ CASES = [  # (w, h, frames, qp, fps)
 ]
 
 
-def ref_encode(yuv, w, h, n, qp, fps, complexity=2, threads=1, entropy=(0, 66), intra_period=0):
+def ref_encode(yuv, w, h, n, qp, fps, complexity=2, threads=1, entropy=(0, 66), intra_period=0, loop_filter=(0, 0, 0)):
     """entropy = (iEntropyCodingModeFlag, uiProfileIdc; 0 = leave the profile to the encoder: High with CABAC)"""
     R = C.CDLL(h264lib.REFSHIM_SO)
     R.ref_set_entropy.argtypes = [C.c_int, C.c_int]
@@ -27,11 +27,13 @@ def ref_encode(yuv, w, h, n, qp, fps, complexity=2, threads=1, entropy=(0, 66), 
     out, fb, secs = np.zeros(cap, np.uint8), np.zeros(n, np.int32), C.c_double()
     R.ref_set_entropy(*entropy)
     R.ref_set_intra_period(intra_period)
+    R.ref_set_loop_filter(*loop_filter)
     try:
         tot = R.ref_encode(yuv.ctypes.data, w, h, n, qp, complexity, threads, fps, out.ctypes.data, cap, fb.ctypes.data, C.byref(secs))
     finally:
         R.ref_set_entropy(0, 66)
         R.ref_set_intra_period(0)
+        R.ref_set_loop_filter(0, 0, 0)
     assert tot > 0
     return out[:tot].tobytes(), fb.tolist(), secs.value
 

@@ -28,10 +28,11 @@ def emu():
     return E
 
 
-def emu_encode(E, yuv, w, h, n, qp, fps, low=False, entropy=(0, 66), intra_period=0):
+def emu_encode(E, yuv, w, h, n, qp, fps, low=False, entropy=(0, 66), intra_period=0, loop_filter=(0, 0, 0)):
     E.emu_set_complexity_low(1 if low else 0)
     E.emu_set_entropy(*entropy)
     E.emu_set_intra_period(intra_period)
+    E.emu_set_loop_filter(*loop_filter)
     cap = 32 << 20
     out, fb = np.zeros(cap, np.uint8), np.zeros(n, np.int32)
     tot = E.emu_encode(yuv.ctypes.data, w, h, n, qp, fps, out.ctypes.data, cap, fb.ctypes.data, None)
@@ -185,4 +186,22 @@ def test_emu_intra_period_matches_reference_golden(emu, key):
     f = {k: int(key.split("_" + k)[1].split("_")[0]) for k in ("n", "qp", "seed", "period", "cabac")}
     yuv = h264lib.synth_clip(w, h, f["n"], seed=f["seed"])
     bs, fb = emu_encode(emu, yuv, w, h, f["n"], f["qp"], 30.0, entropy=(f["cabac"], 0 if f["cabac"] else 66), intra_period=f["period"])
+    assert fb == g["frame_bytes"] and hashlib.sha1(bs).hexdigest() == g["sha1"]
+
+
+def _loop_filter_case(key):
+    w, h = map(int, key.split("_")[0].split("x"))
+    f = {}
+    for k in ("n", "qp", "seed", "idc", "a", "b", "cabac"):
+        f[k] = int(key.split("_" + k)[1].split("_")[0])
+    return w, h, f
+
+
+@pytest.mark.parametrize("key", sorted(EDGE["loop_filter"]))
+def test_emu_loop_filter_control_matches_reference_golden(emu, key):
+    """iLoopFilterDisableIdc (1: the reference pictures stay unfiltered; 2 = 0 with one slice) and the alpha / beta offsets"""
+    g = EDGE["loop_filter"][key]
+    w, h, f = _loop_filter_case(key)
+    yuv = h264lib.synth_clip(w, h, f["n"], seed=f["seed"], noise=6)
+    bs, fb = emu_encode(emu, yuv, w, h, f["n"], f["qp"], 30.0, entropy=(f["cabac"], 0 if f["cabac"] else 66), loop_filter=(f["idc"], f["a"], f["b"]))
     assert fb == g["frame_bytes"] and hashlib.sha1(bs).hexdigest() == g["sha1"]

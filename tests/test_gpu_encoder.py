@@ -271,3 +271,23 @@ def test_intra_period_through_cuda(key):
     enc.close()
     assert [len(b) for b in out[0]] == g["frame_bytes"]
     assert hashlib.sha1(b"".join(out[0])).hexdigest() == g["sha1"] and out[1] == out[0]
+
+
+@pytest.mark.parametrize("key", sorted(EDGE["loop_filter"]))
+def test_loop_filter_control_through_cuda(key):
+    """iLoopFilterDisableIdc / alpha / beta offsets (b2h264_enc_config::loop_filter_*): slice header fields on the host, FilterOffsetA / B
+    and the on / off switch in the deblocking kernel; golden = the unmodified reference"""
+    from openh264_b200.binding import BatchEncoder
+    g = EDGE["loop_filter"][key]
+    w, h = map(int, key.split("_")[0].split("x"))
+    f = {k: int(key.split("_" + k)[1].split("_")[0]) for k in ("n", "qp", "seed", "idc", "a", "b", "cabac")}
+    yuv = h264lib.synth_clip(w, h, f["n"], seed=f["seed"], noise=6)
+    enc = BatchEncoder(w, h, qp=f["qp"], fps=30.0, n_streams=2, entropy_cabac=bool(f["cabac"]), loop_filter=(f["idc"], f["a"], f["b"]))
+    fsz = w * h * 3 // 2
+    out = [[], []]
+    for i in range(f["n"]):
+        bs, _ = enc.encode([yuv[i * fsz:(i + 1) * fsz]] * 2)
+        out[0].append(bs[0]); out[1].append(bs[1])
+    enc.close()
+    assert [len(b) for b in out[0]] == g["frame_bytes"]
+    assert hashlib.sha1(b"".join(out[0])).hexdigest() == g["sha1"] and out[1] == out[0]

@@ -19,7 +19,7 @@ need_built = pytest.mark.skipif(not (os.path.exists(DRIVER) and os.path.exists(O
                                 reason="layer-3 shim / driver are built where the reference headers exist (build())")
 
 
-def drive(lib, clip, w, h, n, qp, idr_at, tmp, tag, entropy=None, intra_period=None):
+def drive(lib, clip, w, h, n, qp, idr_at, tmp, tag, entropy=None, intra_period=None, loop_filter=None):
     yuv = os.path.join(tmp, "in.yuv")
     with open(yuv, "wb") as f:
         f.write(clip.tobytes())
@@ -27,6 +27,8 @@ def drive(lib, clip, w, h, n, qp, idr_at, tmp, tag, entropy=None, intra_period=N
     extra = [str(entropy[0]), str(entropy[1])] if entropy else []
     if intra_period is not None:
         extra = (extra or ["0", "66"]) + [str(intra_period)]
+    if loop_filter is not None:
+        extra = (extra + ["0"] if len(extra) == 2 else extra or ["0", "66", "0"]) + [str(v) for v in loop_filter]
     r = subprocess.run([DRIVER, lib, yuv, str(w), str(h), str(n), str(qp), str(idr_at), out, lay] + extra, capture_output=True, text=True,
                        timeout=300)
     return r, (open(out, "rb").read() if os.path.exists(out) else b""), (open(lay).read() if os.path.exists(lay) else "")
@@ -76,6 +78,19 @@ def test_drop_in_same_driver_two_libraries(tmp_path, w, h, n, qp, idr_at):
     assert r1.returncode == 0, r1.stderr
     assert bs0 == bs1, "bitstream through ISVCEncoder differs from the reference"
     assert lay0 == lay1, "SFrameBSInfo layout / defaults differ:\n" + lay0 + "\n---\n" + lay1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lf", [(1, 0, 0), (0, 2, -3), (2, -6, 6)])
+def test_drop_in_loop_filter_control(tmp_path, lf):
+    assert os.path.exists(DRIVER) and os.path.exists(OURLIB), "prebuilt layer-3 artefacts missing on the GPU box"
+    w, h, n, qp = 176, 144, 5, 33
+    clip = h264lib.synth_clip(w, h, n, seed=17, noise=6)
+    r0, bs0, lay0 = drive(REFLIB, clip, w, h, n, qp, -1, str(tmp_path), "ref", loop_filter=lf)
+    r1, bs1, lay1 = drive(OURLIB, clip, w, h, n, qp, -1, str(tmp_path), "b2", loop_filter=lf)
+    assert r0.returncode == 0, r0.stderr
+    assert r1.returncode == 0, r1.stderr
+    assert bs0 == bs1 and lay0 == lay1
 
 
 @pytest.mark.gpu

@@ -54,6 +54,9 @@ int main(int argc, char** argv) {
     p.sSpatialLayers[0].uiProfileIdc = (EProfileIdc)atoi(argv[11]);
   }
   if (argc > 12) p.uiIntraPeriod = (unsigned int)atoi(argv[12]);   // optional: uiIntraPeriod
+  if (argc > 15) {                       // optional: iLoopFilterDisableIdc, iLoopFilterAlphaC0Offset, iLoopFilterBetaOffset
+    p.iLoopFilterDisableIdc = atoi(argv[13]); p.iLoopFilterAlphaC0Offset = atoi(argv[14]); p.iLoopFilterBetaOffset = atoi(argv[15]);
+  }
   p.sSpatialLayers[0].sSliceArgument.uiSliceMode = SM_SINGLE_SLICE;
   int rc = enc->InitializeExt(&p);
   if (rc) { fprintf(stderr, "InitializeExt -> %d\n", rc); return 5; }

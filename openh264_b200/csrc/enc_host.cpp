@@ -110,7 +110,8 @@ void StreamCtl::write_access_unit_packed(bool idr, const MbOut* packed, const in
 }
 
 void StreamCtl::write_au(bool idr, const MbOut* const* mbs, std::vector<uint8_t>* au) {
-  std::vector<uint8_t> rbsp;
+  std::vector<uint8_t>& rbsp = rbsp_;             // kept between pictures: its capacity settles at the stream's picture size
+  rbsp.clear();
   if (idr) {
     idr_pic_id = idr_pic_id < 65535 ? idr_pic_id + 1 : 0;
     frame_num = 0;

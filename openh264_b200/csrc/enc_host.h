@@ -55,6 +55,7 @@ struct StreamCtl {
  private:
   void write_au(bool idr, const MbOut* const* recs, std::vector<uint8_t>* au);
   std::vector<const MbOut*> recs_;
+  std::vector<uint8_t> rbsp_;               // payload of the NAL being written (reused from picture to picture)
   std::vector<MbOut> expand_;               // compact records of the coded macroblocks, expanded for the slice writer
  public:
   int last_coded_mbs = 0;                   // macroblocks of the last picture that were not P_SKIP (write_access_unit_packed)

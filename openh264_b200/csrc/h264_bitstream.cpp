@@ -10,15 +10,23 @@ namespace b2h264 {
 
 // ---- NAL encapsulation (nal_encap.cpp: start code, header byte, emulation prevention) ------------
 void append_nal(std::vector<uint8_t>* dst, int nal_ref_idc, int nal_type, const std::vector<uint8_t>& rbsp) {
-  static const uint8_t kStart[4] = {0, 0, 0, 1};
-  dst->insert(dst->end(), kStart, kStart + 4);
-  dst->push_back((uint8_t)((nal_ref_idc << 5) | nal_type));
+  // start code, header, payload with emulation prevention (7.4.1: 00 00 0x -> 00 00 03 0x for x <= 3).  Written through a pointer into
+  // space sized for the worst case (every third byte an escape), cut back afterwards
+  const size_t base = dst->size(), n = rbsp.size();
+  dst->resize(base + 5 + n + n / 2 + 1);
+  uint8_t* o = dst->data() + base;
+  o[0] = 0; o[1] = 0; o[2] = 0; o[3] = 1;
+  o[4] = (uint8_t)((nal_ref_idc << 5) | nal_type);
+  o += 5;
+  const uint8_t* in = rbsp.data();
   int zeros = 0;
-  for (uint8_t b : rbsp) {
-    if (zeros >= 2 && b <= 3) { dst->push_back(3); zeros = 0; }
-    dst->push_back(b);
+  for (size_t i = 0; i < n; i++) {
+    const uint8_t b = in[i];
+    if (zeros >= 2 && b <= 3) { *o++ = 3; zeros = 0; }
+    *o++ = b;
     zeros = b == 0 ? zeros + 1 : 0;
   }
+  dst->resize((size_t)(o - dst->data()));
 }
 
 // ---- level selection -------------------------------------------------------------------------------

@@ -16,26 +16,27 @@ namespace b2h264 {
 class BitWriter {
  public:
   explicit BitWriter(std::vector<uint8_t>* out) : out_(out) {}
-  void put(int n, uint32_t v) {                 // n <= 32 bits, MSB first
-    for (int i = n - 1; i >= 0; i--) {
-      cur_ = (uint8_t)((cur_ << 1) | ((v >> i) & 1));
-      if (++nbits_ == 8) { out_->push_back(cur_); cur_ = 0; nbits_ = 0; }
-    }
+  // n <= 32 bits, MSB first.  Bits gather in a 64-bit accumulator; whole bytes go to the buffer at once (a byte is in the buffer as
+  // soon as it is complete, so bit_pos() / the buffer's size always tell the truth)
+  void put(int n, uint32_t v) {
+    if (n <= 0) return;
+    acc_ = (acc_ << n) | (n >= 32 ? (uint64_t)v : (uint64_t)(v & ((1u << n) - 1u)));
+    nbits_ += n;
+    while (nbits_ >= 8) { nbits_ -= 8; out_->push_back((uint8_t)(acc_ >> nbits_)); }
   }
   void bit(int b) { put(1, (uint32_t)(b != 0)); }
   void ue(uint32_t v) {
-    int len = 0;
-    for (uint32_t t = v + 1; t > 1; t >>= 1) len++;
-    put(len, 0);
-    put(len + 1, v + 1);
+    const int len = 31 - __builtin_clz(v + 1);     // v + 1 >= 1; v < 2^32 - 1
+    if (len > 16) { put(len, 0); put(len + 1, v + 1); }
+    else put(2 * len + 1, v + 1);
   }
   void se(int32_t v) { ue(v > 0 ? (uint32_t)(2 * v - 1) : (uint32_t)(-2 * v)); }
-  void trailing() { bit(1); while (nbits_) bit(0); }
+  void trailing() { bit(1); if (nbits_) put(8 - nbits_, 0); }
   size_t bit_pos() const { return out_->size() * 8 + nbits_; }
  private:
   std::vector<uint8_t>* out_;
-  uint8_t cur_ = 0;
-  int nbits_ = 0;
+  uint64_t acc_ = 0;             // the low nbits_ bits are pending
+  int nbits_ = 0;                // < 8 between calls
 };
 
 struct StreamParams {

@@ -19,50 +19,57 @@ namespace b2h264 {
 namespace {
 
 // ---- arithmetic encoder, Rec. H.264 9.3.4.2 ------------------------------------------------------------------------------
+// The Recommendation describes the encoder bit by bit (PutBit with outstanding bits).  This is the same arithmetic with byte-wise
+// output: `low_` keeps the 10-bit coding window in its low bits and the bits already shifted out of the window above it; once 8 of
+// them (plus the carry position) are complete a byte leaves, a carry runs back into the bytes written before (a run of 0xff bytes
+// is held back until it is known whether a carry reaches it).  The first bit PutBit would write is dropped by starting 9 shifts
+// short of a byte, as 9.3.4.2 prescribes.  The slice header before the first byte is byte aligned (cabac_alignment_one_bit).
 class CabacEncoder {
  public:
-  explicit CabacEncoder(BitWriter* w) : w_(w) {}
+  explicit CabacEncoder(std::vector<uint8_t>* out) : out_(out) {}
   void init_contexts(int slice_qp, int table /* 0 = I slice, 1 + cabac_init_idc */) {
     const int qp = slice_qp < 0 ? 0 : slice_qp > 51 ? 51 : slice_qp;
     for (int i = 0; i < 460; i++) {
       int pre = ((kCabacInit[i][table][0] * qp) >> 4) + kCabacInit[i][table][1];
       pre = pre < 1 ? 1 : pre > 126 ? 126 : pre;
-      if (pre <= 63) { state_[i] = (uint8_t)(63 - pre); mps_[i] = 0; }
-      else { state_[i] = (uint8_t)(pre - 64); mps_[i] = 1; }
+      // state in bits 1..6, valMPS in bit 0
+      ctx_[i] = pre <= 63 ? (uint8_t)((63 - pre) << 1) : (uint8_t)(((pre - 64) << 1) | 1);
     }
-    low_ = 0; range_ = 510; outstanding_ = 0; first_ = true;
+    low_ = 0; range_ = 510; queue_ = -9; outstanding_ = 0;
   }
   void decision(int ctx, int bin) {
-    const uint32_t lps = kCabacRangeLps[state_[ctx]][(range_ >> 6) & 3];
+    const uint32_t c = ctx_[ctx], st = c >> 1;
+    const uint32_t lps = kCabacRangeLps[st][(range_ >> 6) & 3];
     range_ -= lps;
-    if ((bin != 0) != (mps_[ctx] != 0)) {
+    if ((uint32_t)(bin != 0) != (c & 1)) {
       low_ += range_;
       range_ = lps;
-      if (state_[ctx] == 0) mps_[ctx] ^= 1;
-      state_[ctx] = kCabacNextLps[state_[ctx]];
+      ctx_[ctx] = (uint8_t)((kCabacNextLps[st] << 1) | ((c & 1) ^ (st == 0)));
     } else {
-      state_[ctx] = kCabacNextMps[state_[ctx]];
+      ctx_[ctx] = (uint8_t)((kCabacNextMps[st] << 1) | (c & 1));
     }
     renorm();
   }
   void bypass(int bin) {
     low_ <<= 1;
     if (bin) low_ += range_;
-    if (low_ >= 1024) { put_bit(1); low_ -= 1024; }
-    else if (low_ < 512) put_bit(0);
-    else { low_ -= 512; outstanding_++; }
+    queue_++;
+    put_byte();
   }
   void terminate(int bin) {
     range_ -= 2;
-    if (bin) {
-      low_ += range_;
-      range_ = 2;                                      // EncodeFlush (9.3.4.5)
-      renorm();
-      put_bit((low_ >> 9) & 1);
-      w_->put(2, ((low_ >> 7) & 3) | 1);               // the last bit written is the rbsp_stop_one_bit
-    } else {
-      renorm();
-    }
+    if (!bin) { renorm(); return; }
+    // EncodeFlush (9.3.4.5): the window moves 7 places (range 2 -> 256), then its top bit and two more bits leave, the last one
+    // forced to 1: the rbsp_stop_one_bit.  What is left of the last byte is rbsp_alignment_zero_bit.
+    low_ += range_;
+    range_ = 2;
+    renorm();
+    low_ |= 0x80;
+    low_ <<= 3; queue_ += 3;
+    put_byte();
+    low_ &= ~(uint64_t)0x3ff;                           // the rest of the window is not part of the stream
+    if (queue_ > -8) { low_ <<= -queue_; queue_ = 0; put_byte(); }
+    for (; outstanding_ > 0; outstanding_--) out_->push_back(0xff);
   }
   // unary-exp-Golomb suffix of order k, bypass coded (9.3.2.3)
   void exp_golomb_bypass(int k, uint32_t v) {
@@ -73,24 +80,29 @@ class CabacEncoder {
 
  private:
   void renorm() {
-    while (range_ < 256) {
-      if (low_ < 256) put_bit(0);
-      else if (low_ >= 512) { low_ -= 512; put_bit(1); }
-      else { low_ -= 256; outstanding_++; }
-      range_ <<= 1;
-      low_ <<= 1;
-    }
+    if (range_ >= 256) return;
+    const int shift = __builtin_clz(range_) - 23;       // range_ in [2, 255]: up to 7 places
+    range_ <<= shift;
+    low_ <<= shift;
+    queue_ += shift;
+    put_byte();
   }
-  void put_bit(int b) {
-    if (first_) first_ = false;
-    else w_->bit(b);
-    for (; outstanding_ > 0; outstanding_--) w_->bit(!b);
+  void put_byte() {
+    if (queue_ < 0) return;
+    const uint32_t out = (uint32_t)(low_ >> (queue_ + 10));          // 9 bits: a carry on top of the byte
+    low_ &= ((uint64_t)0x400 << queue_) - 1;
+    queue_ -= 8;
+    if ((out & 0xff) == 0xff) { outstanding_++; return; }           // cannot be written before a possible carry is known
+    const uint32_t carry = out >> 8;
+    if (carry) out_->back() = (uint8_t)(out_->back() + 1);           // the byte before a held-back run is never 0xff
+    for (; outstanding_ > 0; outstanding_--) out_->push_back((uint8_t)(carry - 1));   // 0xff without, 0x00 with a carry
+    out_->push_back((uint8_t)out);
   }
-  BitWriter* w_;
-  uint8_t state_[460], mps_[460];
-  uint32_t low_ = 0, range_ = 510;
-  int outstanding_ = 0;
-  bool first_ = true;
+  std::vector<uint8_t>* out_;
+  uint8_t ctx_[460];
+  uint64_t low_ = 0;
+  uint32_t range_ = 510;
+  int queue_ = -9, outstanding_ = 0;
 };
 
 // what later macroblocks need to know about a coded macroblock (context selection, 9.3.3.1.1)
@@ -179,7 +191,7 @@ void write_slice_cabac(const StreamParams& sp, const SliceState& ss, const MbOut
   if (sp.dbk_idc != 1) { w.se(sp.dbk_alpha_div2); w.se(sp.dbk_beta_div2); }
   while (w.bit_pos() & 7) w.bit(1);      // cabac_alignment_one_bit
 
-  CabacEncoder e(&w);
+  CabacEncoder e(rbsp);                  // the header is byte aligned: the arithmetic coder appends whole bytes
   e.init_contexts(ss.qp, ss.idr ? 0 : 1);
 
   const int mbw = sp.mb_w, n = sp.mb_w * sp.mb_h;
@@ -339,8 +351,7 @@ void write_slice_cabac(const StreamParams& sp, const SliceState& ss, const MbOut
       prev_dqp_nonzero = false;
     }
   }
-  e.terminate(1);                          // end_of_slice_flag = 1 + flush; the flush ends with the stop bit
-  while (w.bit_pos() & 7) w.bit(0);        // rbsp_alignment_zero_bit
+  e.terminate(1);                          // end_of_slice_flag = 1 + flush: stop bit and alignment included
 }
 
 }  // namespace b2h264

@@ -9,6 +9,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <chrono>
 #include <vector>
 
 #define B2H264_WITH_INTER 1
@@ -29,6 +30,8 @@ static bool same_record(const MbOut& a, const MbOut& b);
 namespace {
 
 // host-memory twin of the product's device-side frame buffers
+static int g_emu_time_writer = 0;                     // > 0: time that many extra write_access_unit calls per picture
+static double g_emu_writer_us = 0;
 static int g_emu_dbk[3] = {0, 0, 0};                  // iLoopFilterDisableIdc, alpha / beta offsets
 static int g_emu_intra_period = 0;                    // uiIntraPeriod, the rule of csrc/enc_batch.cu (b2h264_enc_submit)
 static int g_emu_cabac = 0, g_emu_profile = 0;       // entropy coder of the host writer (the macroblock decisions do not depend on it)
@@ -119,6 +122,14 @@ struct HostFrameEncoder {
   void finish_frame(std::vector<uint8_t>* bs) {
     // the product hands the host only the coded macroblocks' records plus an index table (k_pack_records):
     // write the access unit through that form too and insist on the same bytes
+    if (g_emu_time_writer > 0) {                      // microbenchmark of the host entropy coder (tools/time_writer.py)
+      b2h264::StreamCtl c2 = ctl;
+      std::vector<uint8_t> tmp;
+      c2.write_access_unit(idr, out.data(), &tmp);      // warm: buffers at their final capacity
+      const auto t0 = std::chrono::steady_clock::now();
+      for (int r = 0; r < g_emu_time_writer; r++) { tmp.clear(); c2.write_access_unit(idr, out.data(), &tmp); }
+      g_emu_writer_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / g_emu_time_writer;
+    }
     {
       b2h264::StreamCtl twin = ctl;
       // the host twin of k_pack_records (the decoder's hand-over uses it; the encoder's device kernel follows the same rules)
@@ -210,6 +221,8 @@ extern "C" int emu_last(MbOut* out, MbInfo* info, int n) {
 }
 static int g_emu_fast_mode = 0;
 extern "C" void emu_set_entropy(int cabac, int profile_idc) { g_emu_cabac = cabac; g_emu_profile = profile_idc; }
+extern "C" void emu_set_time_writer(int reps) { g_emu_time_writer = reps; }
+extern "C" double emu_last_writer_us() { return g_emu_writer_us; }
 extern "C" void emu_set_loop_filter(int idc, int a, int b) { g_emu_dbk[0] = idc; g_emu_dbk[1] = a; g_emu_dbk[2] = b; }
 extern "C" void emu_set_intra_period(int n) { g_emu_intra_period = n; }
 extern "C" void emu_set_complexity_low(int on) { g_emu_fast_mode = on; }

@@ -16,45 +16,47 @@ namespace b2h264 {
 
 class CabacDecoder {
  public:
-  CabacDecoder(const uint8_t* p, size_t nbytes) : p_(p), nbits_(nbytes * 8) {}
+  CabacDecoder(const uint8_t* p, size_t nbytes) : p_(p), nbytes_(nbytes) {}
   bool ok() const { return !overrun_; }
-  size_t pos() const { return pos_; }
+  size_t pos() const { return byte_ * 8 - (size_t)avail_; }      // bits consumed so far
 
   void init_contexts(int slice_qp, int table /* 0 = I slice, 1 + cabac_init_idc */) {
     const int qp = slice_qp < 0 ? 0 : slice_qp > 51 ? 51 : slice_qp;
     for (int i = 0; i < 460; i++) {
       int pre = ((kCabacInit[i][table][0] * qp) >> 4) + kCabacInit[i][table][1];
       pre = pre < 1 ? 1 : pre > 126 ? 126 : pre;
-      if (pre <= 63) { state_[i] = (uint8_t)(63 - pre); mps_[i] = 0; }
-      else { state_[i] = (uint8_t)(pre - 64); mps_[i] = 1; }
+      ctx_[i] = pre <= 63 ? (uint8_t)((63 - pre) << 1) : (uint8_t)(((pre - 64) << 1) | 1);      // pStateIdx << 1 | valMPS
     }
   }
   // 9.3.1.2: at the start of the slice data and after the samples of an I_PCM macroblock (bit_pos: byte aligned)
   void init_engine(size_t bit_pos) {
-    pos_ = bit_pos;
+    byte_ = (bit_pos + 7) >> 3; buf_ = 0; avail_ = 0;
     range_ = 510;
-    offset_ = 0;
-    for (int i = 0; i < 9; i++) offset_ = (offset_ << 1) | read_bit();
+    offset_ = read_bits(9);
   }
   int decision(int ctx) {
-    const uint32_t lps = kCabacRangeLps[state_[ctx]][(range_ >> 6) & 3];
+    const uint32_t c = ctx_[ctx], st = c >> 1;
+    const uint32_t lps = kCabacRangeLps[st][(range_ >> 6) & 3];
     range_ -= lps;
     int bin;
     if (offset_ >= range_) {
-      bin = !mps_[ctx];
+      bin = (int)((c & 1) ^ 1);
       offset_ -= range_;
       range_ = lps;
-      if (state_[ctx] == 0) mps_[ctx] ^= 1;
-      state_[ctx] = kCabacNextLps[state_[ctx]];
+      ctx_[ctx] = (uint8_t)((kCabacNextLps[st] << 1) | ((c & 1) ^ (st == 0)));
     } else {
-      bin = mps_[ctx];
-      state_[ctx] = kCabacNextMps[state_[ctx]];
+      bin = (int)(c & 1);
+      ctx_[ctx] = (uint8_t)((kCabacNextMps[st] << 1) | (c & 1));
     }
-    while (range_ < 256) { range_ <<= 1; offset_ = (offset_ << 1) | read_bit(); }
+    if (range_ < 256) {
+      const int shift = __builtin_clz(range_) - 23;      // RenormD: up to 7 places (range_ >= 2... an LPS range is >= 6)
+      range_ <<= shift;
+      offset_ = (offset_ << shift) | read_bits(shift);
+    }
     return bin;
   }
   int bypass() {
-    offset_ = (offset_ << 1) | read_bit();
+    offset_ = (offset_ << 1) | read_bits(1);
     if (offset_ >= range_) { offset_ -= range_; return 1; }
     return 0;
   }
@@ -63,7 +65,7 @@ class CabacDecoder {
   int terminate() {
     range_ -= 2;
     if (offset_ >= range_) return 1;
-    while (range_ < 256) { range_ <<= 1; offset_ = (offset_ << 1) | read_bit(); }
+    if (range_ < 256) { range_ <<= 1; offset_ = (offset_ << 1) | read_bits(1); }
     return 0;
   }
   // k-th order Exp-Golomb suffix, bypass coded (9.3.2.3); -1: not a valid code
@@ -177,15 +179,26 @@ class CabacDecoder {
   }
 
  private:
-  uint32_t read_bit() {
-    if (pos_ >= nbits_) { if (++past_end_ > 64) overrun_ = true; pos_++; return 0; }      // a few bits past the end are legal look-ahead
-    const uint32_t b = (p_[pos_ >> 3] >> (7 - (pos_ & 7))) & 1u;
-    pos_++;
-    return b;
+  // the next n <= 16 bits; bits beyond the end of the payload read as 0 (a few of them are legal look-ahead of the engine)
+  uint32_t read_bits(int n) {
+    if (avail_ < n) {
+      while (avail_ <= 56) {
+        uint8_t b = 0;
+        if (byte_ < nbytes_) b = p_[byte_];
+        else if (++past_end_ > 16) overrun_ = true;
+        byte_++;
+        buf_ = (buf_ << 8) | b;
+        avail_ += 8;
+      }
+    }
+    avail_ -= n;
+    return (uint32_t)(buf_ >> avail_) & ((1u << n) - 1u);
   }
   const uint8_t* p_;
-  size_t nbits_, pos_ = 0;
-  uint8_t state_[460], mps_[460];
+  size_t nbytes_, byte_ = 0;
+  uint64_t buf_ = 0;
+  int avail_ = 0;
+  uint8_t ctx_[460];
   uint32_t range_ = 510, offset_ = 0;
   int past_end_ = 0;
   bool overrun_ = false;

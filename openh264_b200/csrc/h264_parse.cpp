@@ -21,39 +21,52 @@ namespace {
 
 class BitReader {
  public:
-  BitReader(const uint8_t* p, size_t n) : p_(p), nbits_(n * 8) {}
+  BitReader(const uint8_t* p, size_t n) : p_(p), nbytes_(n), nbits_(n * 8) {}
   bool ok() const { return !err_; }
   size_t pos() const { return pos_; }
   size_t left() const { return pos_ <= nbits_ ? nbits_ - pos_ : 0; }
-  uint32_t peek(int n) const {            // n <= 24; bits beyond the end read as 0
-    uint32_t v = 0;
-    for (int i = 0; i < n; i++) {
-      const size_t b = pos_ + i;
-      v = (v << 1) | (b < nbits_ ? (p_[b >> 3] >> (7 - (b & 7))) & 1u : 0u);
-    }
-    return v;
+  uint32_t peek(int n) const {            // n <= 32; bits beyond the end read as 0
+    if (n <= 0) return 0;
+    return (uint32_t)(window() >> (64 - n));
   }
   void skip(int n) { pos_ += n; if (pos_ > nbits_) err_ = true; }
-  uint32_t get(int n) { const uint32_t v = n ? peek(n) : 0; skip(n); return v; }
+  uint32_t get(int n) { const uint32_t v = peek(n); skip(n); return v; }
   int bit() { return (int)get(1); }
+  // number of leading zero bits in the next 32 (32 if none is set)
+  int leading_zeros() const { const uint32_t v = peek(32); return v ? __builtin_clz(v) : 32; }
   uint32_t ue() {
-    int z = 0;
-    while (left() && !peek(1)) { skip(1); if (++z > 31) { err_ = true; return 0; } }
-    if (!left()) { err_ = true; return 0; }
-    skip(1);
+    const int z = leading_zeros();
+    if (z > 31 || (size_t)(2 * z + 1) > left()) { err_ = true; pos_ = nbits_ + 1; return 0; }
+    skip(z + 1);
     return z ? ((1u << z) - 1 + get(z)) : 0;
   }
   int32_t se() { const uint32_t k = ue(); return (k & 1) ? (int32_t)((k + 1) >> 1) : -(int32_t)(k >> 1); }
   // 7.2 more_rbsp_data(): anything before the final stop bit?
   bool more_data() const {
     if (left() == 0) return false;
-    size_t last = nbits_;
-    while (last > pos_ && !((p_[(last - 1) >> 3] >> (7 - ((last - 1) & 7))) & 1)) last--;   // last = index after the stop bit
-    return last > pos_ + 1;
+    if (last_one_ == 0) {                   // index after the stop bit, found once (the payload does not change)
+      size_t last = nbits_;
+      while (last > 0 && !((p_[(last - 1) >> 3] >> (7 - ((last - 1) & 7))) & 1)) last--;
+      last_one_ = last + 1;                 // + 1: 0 means "not computed"
+    }
+    return last_one_ - 1 > pos_ + 1;
   }
  private:
+  // the next 64 bits, left aligned (at least 57 of them valid), zero beyond the end
+  uint64_t window() const {
+    const size_t byte = pos_ >> 3;
+    uint64_t v = 0;
+    if (byte + 8 <= nbytes_) {
+      memcpy(&v, p_ + byte, 8);
+      v = __builtin_bswap64(v);
+    } else {
+      for (size_t i = 0; i < 8; i++) v = (v << 8) | (byte + i < nbytes_ ? p_[byte + i] : 0);
+    }
+    return v << (pos_ & 7);
+  }
   const uint8_t* p_;
-  size_t nbits_, pos_ = 0;
+  size_t nbytes_, nbits_, pos_ = 0;
+  mutable size_t last_one_ = 0;
   bool err_ = false;
 };
 
@@ -207,42 +220,89 @@ int parse_pps(BitReader& r, ParserState* st) {
 }
 
 // ---- residual block (9.2): the inverse of write_block() ------------------------------------------------------------
-// table entry = (bits << 8) | codeword; returns the index whose code matches the next bits, or -1
-template <int N>
-int match_code(BitReader& r, const uint16_t (&tbl)[N], int n_valid) {
-  const uint32_t look = r.peek(16);
-  for (int i = 0; i < n_valid; i++) {
-    const int bits = tbl[i] >> 8;
-    if (bits && (look >> (16 - bits)) == (uint32_t)(tbl[i] & 0xff)) { r.skip(bits); return i; }
+// Decoding tables built once from the writer's code tables (cavlc_tables.h; entry = (bits << 8) | codeword), so that a symbol
+// costs one look-up instead of a search:
+//  * coeff_token: codes of up to 16 bits whose codeword has at most 8 significant bits -> per table class and per count of
+//    leading zeros, 128 entries indexed by the 7 bits that follow the first 1 bit;
+//  * total_zeros / run_before: short codes (<= 9 / <= 11 bits) -> one table per context indexed by the next 9 / 11 bits.
+// entry = (bits << 8) | symbol, 0 = no code.
+struct VlcTables {
+  uint16_t coeff[3][16][128];
+  uint16_t coeff_flc[64], coeff_dc[256];                // nC >= 8 (6-bit fixed length) and chroma DC (<= 8 bits): these two have an all-zero code
+  uint16_t tz[16][512];
+  uint16_t tz_dc[4][8];
+  uint16_t run[8][2048];
+  VlcTables() {
+    memset(this, 0, sizeof(*this));
+    for (int cls = 0; cls < 3; cls++)
+      for (int t = 0; t <= 16; t++)
+        for (int o = 0; o < 4 && o <= t; o++) {
+          const int bits = kCoeffToken[cls][t][o] >> 8, code = kCoeffToken[cls][t][o] & 0xff;
+          if (!bits || !code) continue;
+          int sig = 0;
+          while ((code >> sig) != 0) sig++;               // significant bits of the codeword
+          const int z = bits - sig, r = sig - 1;          // leading zeros; bits after the first 1
+          const int first = (code & ((1 << r) - 1)) << (7 - r);
+          for (int k = 0; k < (1 << (7 - r)); k++) coeff[cls][z][first + k] = (uint16_t)((bits << 8) | (t * 4 + o));
+        }
+    for (int t = 0; t <= 16; t++)
+      for (int o = 0; o < 4 && o <= t; o++)
+        for (int cls = 3; cls < 5; cls++) {
+          const int bits = kCoeffToken[cls][t][o] >> 8, code = kCoeffToken[cls][t][o] & 0xff, width = cls == 3 ? 6 : 8;
+          if (!bits) continue;
+          uint16_t* tab = cls == 3 ? coeff_flc : coeff_dc;
+          for (int k = 0; k < (1 << (width - bits)); k++) tab[(code << (width - bits)) + k] = (uint16_t)((bits << 8) | (t * 4 + o));
+        }
+    auto fill = [](uint16_t* tab, int width, const uint16_t* codes, int n) {
+      for (int i = 0; i < n; i++) {
+        const int bits = codes[i] >> 8, code = codes[i] & 0xff;
+        if (!bits) continue;
+        const int first = code << (width - bits);
+        for (int k = 0; k < (1 << (width - bits)); k++) tab[first + k] = (uint16_t)((bits << 8) | i);
+      }
+    };
+    for (int t = 1; t < 16; t++) fill(tz[t], 9, kTotalZeros[t], 16);
+    for (int t = 1; t < 4; t++) fill(tz_dc[t], 3, kTotalZerosChromaDc[t], 4);
+    for (int t = 1; t < 8; t++) fill(run[t], 11, kRunBefore[t], 15);
   }
-  return -1;
+};
+const VlcTables& vlc_tables() {
+  static const VlcTables t;                              // thread-safe one-time build (streams are parsed on several threads)
+  return t;
 }
 
 // reads one block into lv[0..max_coef) (scan order); returns total_coeff or a negative ParseError
 int read_block(BitReader& r, int16_t* lv, int max_coef, int nc) {
+  const VlcTables& V = vlc_tables();
   for (int i = 0; i < max_coef; i++) lv[i] = 0;
   const int cls = nc < 0 ? 4 : kNcClass[nc > 16 ? 16 : nc];
-  int total = -1, t1 = 0;
+  int total, t1;
   {
-    const uint32_t look = r.peek(16);
-    const int max_total = nc < 0 ? 4 : 16;
-    for (int t = 0; t <= max_total && total < 0; t++)
-      for (int o = 0; o < 4 && o <= t; o++) {
-        const uint16_t e = kCoeffToken[cls][t][o];
-        const int bits = e >> 8;
-        if (bits && (look >> (16 - bits)) == (uint32_t)(e & 0xff)) { total = t; t1 = o; r.skip(bits); break; }
-      }
+    uint16_t e;
+    if (cls == 3) e = V.coeff_flc[r.peek(6)];
+    else if (cls == 4) e = V.coeff_dc[r.peek(8)];
+    else {
+      const uint32_t look = r.peek(32);
+      const int z = look ? __builtin_clz(look) : 32;
+      if (z > 15) return PARSE_INVALID;
+      e = V.coeff[cls][z][(uint32_t)(look << (z + 1)) >> 25];
+    }
+    if (!e) return PARSE_INVALID;
+    r.skip(e >> 8);
+    total = (e & 0xff) >> 2; t1 = e & 3;
   }
-  if (total < 0) return PARSE_INVALID;
   if (total > max_coef) return PARSE_INVALID;
   if (total == 0) return 0;
   int level[16];
-  for (int k = 0; k < t1; k++) level[k] = r.bit() ? -1 : 1;
+  if (t1) {
+    const uint32_t signs = r.get(t1);
+    for (int k = 0; k < t1; k++) level[k] = ((signs >> (t1 - 1 - k)) & 1) ? -1 : 1;
+  }
   int suffix_len = (total > 10 && t1 < 3) ? 1 : 0;
   for (int k = t1; k < total; k++) {
-    int prefix = 0;
-    while (r.left() && !r.peek(1)) { r.skip(1); if (++prefix > 32) return PARSE_INVALID; }
-    r.skip(1);
+    const int prefix = r.leading_zeros();
+    if (prefix > 31 || (size_t)prefix >= r.left()) return PARSE_INVALID;
+    r.skip(prefix + 1);
     int suffix_size = (prefix == 14 && suffix_len == 0) ? 4 : (prefix >= 15 ? prefix - 3 : suffix_len);
     int code = ((prefix < 15 ? prefix : 15) << suffix_len) + (suffix_size ? (int)r.get(suffix_size) : 0);
     if (prefix >= 15 && suffix_len == 0) code += 15;
@@ -255,15 +315,19 @@ int read_block(BitReader& r, int16_t* lv, int max_coef, int nc) {
   }
   int zeros_left = 0;
   if (total < max_coef) {
-    const int tz = nc >= 0 ? match_code(r, kTotalZeros[total], 16) : match_code(r, kTotalZerosChromaDc[total], 4);
-    if (tz < 0) return PARSE_INVALID;
-    zeros_left = tz;
+    const uint16_t e = nc >= 0 ? V.tz[total][r.peek(9)] : V.tz_dc[total][r.peek(3)];
+    if (!e) return PARSE_INVALID;
+    r.skip(e >> 8);
+    zeros_left = e & 0xff;
   }
   int run[16];
   for (int k = 0; k < total; k++) run[k] = 0;
   for (int k = 0; k + 1 < total && zeros_left > 0; k++) {
-    const int rb = match_code(r, kRunBefore[zeros_left > 7 ? 7 : zeros_left], 15);
-    if (rb < 0 || rb > zeros_left) return PARSE_INVALID;
+    const uint16_t e = V.run[zeros_left > 7 ? 7 : zeros_left][r.peek(11)];
+    if (!e) return PARSE_INVALID;
+    r.skip(e >> 8);
+    const int rb = e & 0xff;
+    if (rb > zeros_left) return PARSE_INVALID;
     run[k] = rb;
     zeros_left -= rb;
   }

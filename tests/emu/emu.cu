@@ -31,7 +31,7 @@ namespace {
 
 // host-memory twin of the product's device-side frame buffers
 static int g_emu_time_writer = 0;                     // > 0: time that many extra write_access_unit calls per picture
-static double g_emu_writer_us = 0;
+static double g_emu_writer_us = 0, g_emu_parser_us = 0;
 static int g_emu_dbk[3] = {0, 0, 0};                  // iLoopFilterDisableIdc, alpha / beta offsets
 static int g_emu_intra_period = 0;                    // uiIntraPeriod, the rule of csrc/enc_batch.cu (b2h264_enc_submit)
 static int g_emu_cabac = 0, g_emu_profile = 0;       // entropy coder of the host writer (the macroblock decisions do not depend on it)
@@ -110,6 +110,19 @@ struct HostFrameEncoder {
   int parse_status = 0;              // 0 ok, <0 ParseError, >0 = 1 + index of the first macroblock that differs
   void check_parse(const std::vector<uint8_t>& au) {
     b2h264::ParsedPicture pic;
+    if (g_emu_time_writer > 0) {                      // microbenchmark of the parser on the same access unit
+      b2h264::ParsedPicture tp;
+      { b2h264::ParserState ps = parser; b2h264::parse_access_unit(au.data(), au.size(), &ps, &tp); }
+      double us = 0;
+      for (int r = 0; r < g_emu_time_writer; r++) {
+        b2h264::ParserState ps = parser;
+        tp.next_mb = 0; tp.n_slices = 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        b2h264::parse_access_unit(au.data(), au.size(), &ps, &tp);
+        us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+      }
+      g_emu_parser_us = us / g_emu_time_writer;
+    }
     const int rc = b2h264::parse_access_unit(au.data(), au.size(), &parser, &pic);
     if (rc != 0) { parse_status = rc; return; }
     if (pic.ss.idr != idr || pic.mbs.size() != out.size() || parser.sp.mb_w != ctl.sp.mb_w || parser.sp.width != ctl.sp.width ||
@@ -223,6 +236,7 @@ static int g_emu_fast_mode = 0;
 extern "C" void emu_set_entropy(int cabac, int profile_idc) { g_emu_cabac = cabac; g_emu_profile = profile_idc; }
 extern "C" void emu_set_time_writer(int reps) { g_emu_time_writer = reps; }
 extern "C" double emu_last_writer_us() { return g_emu_writer_us; }
+extern "C" double emu_last_parser_us() { return g_emu_parser_us; }
 extern "C" void emu_set_loop_filter(int idc, int a, int b) { g_emu_dbk[0] = idc; g_emu_dbk[1] = a; g_emu_dbk[2] = b; }
 extern "C" void emu_set_intra_period(int n) { g_emu_intra_period = n; }
 extern "C" void emu_set_complexity_low(int on) { g_emu_fast_mode = on; }

@@ -22,16 +22,45 @@ MBK_HD int tbl_beta(int i) { return MBK_TBL(c_beta, h_beta)[i]; }
 MBK_HD int tbl_tc0(int i, int bs) { return bs == 0 ? -1 : MBK_TBL(c_tc0, h_tc0)[i][bs - 1]; }
 
 // boundary strength of the 4 segments of one edge; dir 0 = vertical edge (left neighbour), 1 = horizontal
+// motion of 4x4 block `blk` (raster) of a decoded macroblock for the filter: reference picture (slot, -1: list not used) and
+// vector per list.  List 0 lives in MbInfo (dec_mb.cuh), list 1 of a B macroblock in its DecMbAuxB record (vectors in coding order).
+MBK_HD void dbk_block_motion(const MbInfo* m, const DecMbAuxB* b, int blk, int r[2], int mv[2][2]) {
+  r[0] = m->i4_mode[blk];
+  mv[0][0] = r[0] < 0 ? 0 : m->mv[blk][0]; mv[0][1] = r[0] < 0 ? 0 : m->mv[blk][1];
+  r[1] = -1; mv[1][0] = mv[1][1] = 0;
+  if (b) {
+    const int bx = blk & 3, by = blk >> 2, z = ((by >> 1) * 2 + (bx >> 1)) * 4 + (by & 1) * 2 + (bx & 1);
+    r[1] = b->ref_idx[z >> 2];
+    if (r[1] >= 0) { mv[1][0] = b->mv[z][0]; mv[1][1] = b->mv[z][1]; }
+  }
+}
+MBK_HD bool dbk_mv_far(const int a[2], const int b[2]) { return iabs(a[0] - b[0]) >= 4 || iabs(a[1] - b[1]) >= 4; }
+
 MBK_HD void edge_bs(const MbInfo* cur, const MbInfo* nb /*other MB for edge 0, else == cur*/, int dir, int edge, int bs[4],
-                    bool ref_ids = false /* decoder: i4_mode holds the reference picture of every 4x4 block */) {
+                    bool ref_ids = false /* decoder: i4_mode holds the reference picture of every 4x4 block */,
+                    const DecMbAuxB* cur_b = nullptr, const DecMbAuxB* nb_b = nullptr /* list 1 of a B macroblock, else NULL */) {
   const bool mb_edge = edge == 0;
   for (int i = 0; i < 4; i++) {
     // q block in cur, p block in nb (raster 4x4 indices)
     const int q = dir == 0 ? i * 4 + edge : edge * 4 + i;
     const int p = dir == 0 ? (mb_edge ? i * 4 + 3 : q - 1) : (mb_edge ? 12 + i : q - 4);
     if (MBT_IS_INTRA(cur->mb_type) || MBT_IS_INTRA(nb->mb_type)) { bs[i] = mb_edge ? 4 : 3; continue; }
-    if (!mb_edge && cur->mb_type == MBT_PSKIP) { bs[i] = 0; continue; }
+    if (!mb_edge && (cur->mb_type == MBT_PSKIP || cur->mb_type == MBT_BSKIP)) { bs[i] = 0; continue; }
     if (cur->nnz[q] | nb->nnz[p]) { bs[i] = 2; continue; }
+    if (cur_b || nb_b) {
+      // a B macroblock on either side (DeblockingBSliceBsMarginalMBAvcbase / IN_SMB_EDGE_MV, deblocking.cpp:544, :95): strength 1
+      // unless both blocks use the same set of reference pictures and their vectors — matched by picture — are close
+      int rq[2], rp[2], mq[2][2], mp[2][2];
+      dbk_block_motion(cur, cur_b, q, rq, mq);
+      dbk_block_motion(nb, nb_b, p, rp, mp);
+      int v = 1;
+      if ((rq[0] == rp[0] && rq[1] == rp[1]) || (rq[0] == rp[1] && rq[1] == rp[0])) {
+        if (rq[0] != rq[1]) v = rq[0] == rp[0] ? (dbk_mv_far(mq[0], mp[0]) || dbk_mv_far(mq[1], mp[1])) : (dbk_mv_far(mq[0], mp[1]) || dbk_mv_far(mq[1], mp[0]));
+        else v = (dbk_mv_far(mq[0], mp[0]) || dbk_mv_far(mq[1], mp[1])) && (dbk_mv_far(mq[0], mp[1]) || dbk_mv_far(mq[1], mp[0]));
+      }
+      bs[i] = v;
+      continue;
+    }
     if (ref_ids && cur->i4_mode[q] != nb->i4_mode[p]) { bs[i] = 1; continue; }      // different reference pictures
     const int dx = cur->mv[q][0] - nb->mv[p][0], dy = cur->mv[q][1] - nb->mv[p][1];
     bs[i] = (iabs(dx) >= 4 || iabs(dy) >= 4) ? 1 : 0;
@@ -47,6 +76,7 @@ struct alignas(16) DbkTile {
   uint8_t y[20 * DBK_PY];          // rows -4..15, cols -4..15 (sample (0,0) at y[4 * DBK_PY + 4])
   uint8_t c[2][12 * DBK_PC];       // rows -4..7, cols -4..7
   MbInfo m[3];                     // cur, left, top
+  DecMbAuxB b[3];                  // decoder, pictures with B slices: list 1 of those of the three that are B macroblocks
 };
 
 MBK_HD uint32_t dbk_ld32(const uint8_t* p) {
@@ -83,6 +113,18 @@ MBK_HD void deblock_one_mb(const EncFrameParams& p, const EncFramePtrs& f, int m
     }
   }
   warp_sync();
+  const DecMbAuxB* lb[3] = {nullptr, nullptr, nullptr};
+  if (f.dec_aux_b) {                                               // a picture with B slices: list 1 of the B macroblocks among the three
+    constexpr int kWb = (int)(sizeof(DecMbAuxB) / 4);
+    const int nidx[3] = {idx, mbx > 0 ? idx - 1 : idx, mby > 0 ? idx - p.mb_w : idx};
+    for (int k = 0; k < 3; k++) {
+      if (!MBT_IS_B(t.m[k].mb_type)) continue;
+      for (int i = lane_id(); i < kWb; i += MBK_WS)
+        reinterpret_cast<uint32_t*>(&t.b[k])[i] = reinterpret_cast<const uint32_t*>(f.dec_aux_b + nidx[k])[i];
+      lb[k] = &t.b[k];
+    }
+    warp_sync();
+  }
   const MbInfo* cur = &t.m[0];
   uint8_t* ty = t.y + 4 * DBK_PY + 4;
   // decoder: per-slice control travels in MbInfo::p16x16_mv (dec_mb.cuh): disable_deblocking_filter_idc, FilterOffsetA / B and the
@@ -100,7 +142,7 @@ MBK_HD void deblock_one_mb(const EncFrameParams& p, const EncFramePtrs& f, int m
       if (edge == 0 && !have_nb) continue;
       const MbInfo* other = edge == 0 ? nbm : cur;
       int bs[4];
-      edge_bs(cur, other, dir, edge, bs, p.dec_mode != 0);
+      edge_bs(cur, other, dir, edge, bs, p.dec_mode != 0, lb[0], edge == 0 ? lb[1 + dir] : lb[0]);
       if ((bs[0] | bs[1] | bs[2] | bs[3]) == 0) continue;
       const int qp_y = edge == 0 ? (cur->qp + other->qp + 1) >> 1 : cur->qp;
       const int qp_c = edge == 0 ? (cur->qp_c + other->qp_c + 1) >> 1 : cur->qp_c;

@@ -6,10 +6,14 @@
 // macroblock types (own numbering)
 enum {
   MBT_I4x4 = 0, MBT_I16x16 = 1, MBT_P16x16 = 2, MBT_P16x8 = 3, MBT_P8x16 = 4, MBT_P8x8 = 5, MBT_PSKIP = 6,
-  MBT_IPCM = 7               // decoder only: raw samples (luma in MbOut::luma as 256 bytes, Cb / Cr in MbOut::chroma_ac as 2 x 64 bytes)
+  MBT_IPCM = 7,              // decoder only: raw samples (luma in MbOut::luma as 256 bytes, Cb / Cr in MbOut::chroma_ac as 2 x 64 bytes)
+  MBT_B = 8, MBT_BSKIP = 9   // decoder only: a macroblock of a B slice; the parser resolved its vectors and reference pictures for both
+                             // lists (DecMbAux: list 0, DecMbAuxB: list 1).  B_Skip is kept apart because the reference's filter gives its
+                             // inner edges strength 0 (deblocking.cpp:1186 IS_SKIP covers B_Skip)
 };
 #define MBT_IS_INTRA(t) ((t) <= MBT_I16x16 || (t) == MBT_IPCM)
-#define MBT_IS_INTER(t) ((t) >= MBT_P16x16 && (t) <= MBT_PSKIP)
+#define MBT_IS_B(t) ((t) == MBT_B || (t) == MBT_BSKIP)
+#define MBT_IS_INTER(t) (((t) >= MBT_P16x16 && (t) <= MBT_PSKIP) || MBT_IS_B(t))
 
 // Per-macroblock state kept in HBM for the frame being coded: read by the neighbours' mode decision,
 // by the deblocking pass and (through MbOut) by the host entropy coder.
@@ -65,6 +69,18 @@ typedef struct {
   int8_t  ref_idx[4];                     // per 8x8: PICTURE SLOT of its reference picture (the parser resolves RefPicList0)
   int16_t mvd[16][2];                     // sub-macroblock partition j of 8x8 k at [4 * k + j]
 } DecMbAux;                               // 16 + 64 = 80 bytes
+/* Decoder, B slices only: list 1 of a macroblock (one record per macroblock, uploaded only for pictures that hold B slices).
+ * For a B macroblock DecMbAux::ref_idx / mvd hold list 0 the same way: picture slot per 8x8 (-1: list not used) and the FINAL vector
+ * of 4x4 block j of 8x8 k at [4 * k + j] (coding order), not a difference. */
+typedef struct {
+  int8_t  ref_idx[4];                     // per 8x8: picture slot of the list-1 reference, -1: list 1 not used
+  uint8_t pred_lists[4];                  // per 8x8: lists that enter the SAMPLE prediction (bit 0 / bit 1).  Normally the lists in use; the
+                                          // reference's GetInterBPred (rec_mb.cpp:737-825) predicts a bi-predicted 16x8 / 8x16 partition from
+                                          // one list only (first partition: list 1, second: list 0) and its output is the oracle
+  int16_t w1[4];                          // per 8x8 with both lists: weight of the list-1 prediction out of 64 (32: plain average; implicit
+                                          // weights 8.4.2.3.1 otherwise); w0 = 64 - w1
+  int16_t mv[16][2];                      // final list-1 vector of 4x4 block j of 8x8 k at [4 * k + j]
+} DecMbAuxB;                              // 80 bytes
 #define DECAUX_SUB 1
 #define DECAUX_CIP 2
 
@@ -100,6 +116,7 @@ typedef struct {
   const uint8_t* dpb0[3];                 // decoder: planes (pixel (0,0)) of picture slot 0; slot k lies dpb_stride bytes further
   int64_t dpb_stride;
   const DecMbAux* dec_aux;                // decoder: per-macroblock side records (NULL in the encoder)
+  const DecMbAuxB* dec_aux_b;             // decoder: list-1 records of the picture's macroblocks (NULL unless the picture holds B slices)
   const uint8_t* prev_luma;               // fast mode: luma of the previous SOURCE picture (same layout as cur[0])
   int32_t* mb_bits;                       // optional (NULL = off): exact CAVLC bits of every macroblock (enc_cavlc_bits.cuh)
 } EncFramePtrs;

@@ -85,7 +85,7 @@ class CabacDecoder {
   int mb_type_intra(int prefix_ctx, bool in_p) {
     if (!decision(prefix_ctx)) return 0;                                  // I_NxN
     if (terminate()) return 25;                                           // I_PCM
-    const int base = in_p ? 17 : 3;
+    const int base = in_p ? prefix_ctx : 3;                               // P slices 17, B slices 32
     const int c_l = in_p ? base + 1 : base + 3, c_c0 = in_p ? base + 2 : base + 4, c_c1 = in_p ? base + 2 : base + 5;
     const int c_m0 = in_p ? base + 3 : base + 6, c_m1 = in_p ? base + 3 : base + 7;
     const int luma = decision(c_l);
@@ -99,6 +99,34 @@ class CabacDecoder {
     if (decision(14)) return 5 + mb_type_intra(17, true);
     if (!decision(15)) return decision(16) ? 3 : 0;
     return decision(17) ? 1 : 2;
+  }
+  // B slice (Table 9-37 b): 0 B_Direct_16x16, 1..22 as Table 7-14, 23.. = 23 + intra type; inc: neighbours that are neither
+  // B_Skip nor B_Direct_16x16
+  int mb_type_b(int inc) {
+    if (!decision(27 + inc)) return 0;
+    if (!decision(27 + 3)) return 1 + decision(27 + 5);
+    int bits = decision(27 + 4) << 3;
+    bits |= decision(27 + 5) << 2;
+    bits |= decision(27 + 5) << 1;
+    bits |= decision(27 + 5);
+    if (bits < 8) return bits + 3;
+    if (bits == 13) return 23 + mb_type_intra(32, true);
+    if (bits == 14) return 11;
+    if (bits == 15) return 22;
+    bits = (bits << 1) | decision(27 + 5);
+    return bits - 4;
+  }
+  int sub_mb_type_b() {                                                    // 0..12 as Table 7-18
+    if (!decision(36)) return 0;
+    if (!decision(37)) return 1 + decision(39);
+    int type = 3;
+    if (decision(38)) {
+      if (decision(39)) return 11 + decision(39);
+      type += 4;
+    }
+    type += 2 * decision(39);
+    type += decision(39);
+    return type;
   }
   int sub_mb_type_p() {                                                    // 0 8x8, 1 8x4, 2 4x8, 3 4x4
     if (decision(21)) return 0;

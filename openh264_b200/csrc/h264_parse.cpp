@@ -9,6 +9,7 @@
 
 #include "cavlc_tables.h"
 #include "h264_cabac_dec.h"
+#include "h264_motion.h"
 
 namespace b2h264 {
 
@@ -107,6 +108,7 @@ void activate_sps(ParserState* st, int id) {
   st->log2_max_frame_num = f.log2_max_frame_num; st->poc_type = f.poc_type; st->log2_max_poc_lsb = f.log2_max_poc_lsb;
   st->delta_pic_order_always_zero = f.delta_pic_order_always_zero;
   st->n_slots = f.n_slots; st->crop_left = f.crop_left; st->crop_top = f.crop_top;
+  st->profile = f.profile; st->direct_8x8_inference = f.direct_8x8_inference;
   st->have_sps = true;
 }
 
@@ -153,7 +155,8 @@ int parse_sps(BitReader& r, ParserState* st) {
   sp.mb_w = (int)r.ue() + 1;
   sp.mb_h = (int)r.ue() + 1;
   if (!r.bit()) return PARSE_UNSUPPORTED;     // frame_mbs_only_flag
-  r.bit();                                    // direct_8x8_inference_flag
+  f.direct_8x8_inference = r.bit() != 0;      // direct_8x8_inference_flag
+  f.profile = profile;
   sp.crop = r.bit() != 0;
   int cl = 0, ct = 0;
   if (sp.crop) {
@@ -182,6 +185,7 @@ void activate_pps(ParserState* st, int id) {
   st->pic_init_qp = f.pic_init_qp; st->deblocking_control = f.deblocking_control; st->num_ref_idx_default = f.num_ref_idx_default;
   st->constrained_intra_pred = f.constrained_intra_pred;
   st->entropy_cabac = f.entropy_cabac;
+  st->num_ref_idx_l1_default = f.num_ref_idx_l1_default; st->weighted_bipred_idc = f.weighted_bipred_idc;
   st->sp.pps_id = id;
   st->have_pps = true;
 }
@@ -196,9 +200,10 @@ int parse_pps(BitReader& r, ParserState* st) {
   const int bottom_field_poc = r.bit();
   if (r.ue() != 0) return PARSE_UNSUPPORTED;  // slice groups
   f.num_ref_idx_default = (int)r.ue() + 1;
-  r.ue();
+  f.num_ref_idx_l1_default = (int)r.ue() + 1;
   if (r.bit()) return PARSE_UNSUPPORTED;      // weighted_pred_flag
-  r.get(2);
+  f.weighted_bipred_idc = (int)r.get(2);
+  if (f.weighted_bipred_idc == 1 || f.weighted_bipred_idc == 3) return PARSE_UNSUPPORTED;   // explicit weights in B slices
   f.pic_init_qp = 26 + r.se();
   r.se();
   if (r.se() != 0) return PARSE_UNSUPPORTED;  // chroma_qp_index_offset
@@ -379,9 +384,9 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
   const int first_mb = (int)r.ue();
   if (first_mb != pic->next_mb) return PARSE_UNSUPPORTED;     // slices out of raster order / missing slices (ASO, FMO, losses)
   const int slice_type = (int)r.ue() % 5;
-  if (slice_type != 0 && slice_type != 2) return PARSE_UNSUPPORTED;
-  const bool is_p = slice_type == 0;
-  if (idr && is_p) return PARSE_INVALID;
+  if (slice_type > 2) return PARSE_UNSUPPORTED;               // SP / SI slices
+  const bool is_p = slice_type == 0, is_b = slice_type == 1, inter_slice = is_p || is_b;
+  if (idr && inter_slice) return PARSE_INVALID;
   {                                                           // the slice names its PPS, the PPS its SPS (several of each may be around)
     const uint32_t id = r.ue();
     if (id > 255 || !st->pps_tab[id].valid || !st->sps_tab[st->pps_tab[id].sps_id].valid) return PARSE_NO_PARAMETER_SETS;
@@ -392,57 +397,98 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     }
     activate_pps(st, (int)id);
   }
+  // B slices: where the profile has them, with picture order count type 0 and direct_8x8_inference (frame macroblocks: the corner
+  // blocks of the co-located macroblock stand for its 8x8 blocks)
+  if (is_b && (st->profile == 66 || st->poc_type != 0 || !st->direct_8x8_inference)) return PARSE_UNSUPPORTED;
   const int mbw = st->sp.mb_w, n = st->sp.mb_w * st->sp.mb_h;
   SliceState ss;
   ss.idr = idr;
   ss.frame_num = (int)r.get(st->log2_max_frame_num);
   ss.idr_pic_id = idr ? (int)r.ue() : 0;
-  if (st->poc_type == 0) r.get(st->log2_max_poc_lsb);
+  int poc_lsb = 0, poc_msb = 0, poc;
+  if (st->poc_type == 0) poc_lsb = (int)r.get(st->log2_max_poc_lsb);
   else if (st->poc_type == 1 && !st->delta_pic_order_always_zero) r.se();          // delta_pic_order_cnt[0]
-  // RefPicList0 of this slice as picture slots (8.2.4.2.1 + 8.2.4.3.1): short-term pictures by descending PicNum, then the
-  // slice's modification commands.  Long-term pictures are outside the supported class.
+  if (st->poc_type == 0) {                                    // 8.2.1.1
+    const int max_lsb = 1 << st->log2_max_poc_lsb;
+    const int prev_msb = idr ? 0 : st->prev_poc_msb, prev_lsb = idr ? 0 : st->prev_poc_lsb;
+    if (poc_lsb < prev_lsb && prev_lsb - poc_lsb >= max_lsb / 2) poc_msb = prev_msb + max_lsb;
+    else if (poc_lsb > prev_lsb && poc_lsb - prev_lsb > max_lsb / 2) poc_msb = prev_msb - max_lsb;
+    else poc_msb = prev_msb;
+    poc = poc_msb + poc_lsb;
+  } else {
+    poc = 2 * (idr ? 0 : st->decode_count);                   // types 1 / 2 without B slices: output order is decoding order
+  }
+  const bool direct_spatial = is_b ? r.bit() != 0 : true;     // direct_spatial_mv_pred_flag
+  // RefPicList0 / RefPicList1 of this slice (8.2.4.2): P slices order the short-term pictures by descending PicNum, B slices by
+  // picture order count around the current picture; long-term pictures follow by ascending LongTermPicNum; then the slice's
+  // modification commands (8.2.4.3).  Entries carry the picture SLOT of the construct stage.
+  RefEntry lists[2][33];
   int list0[32];
-  int n_ref = 0;
-  if (is_p) {
+  int n_ref = 0, n_ref1 = 0;
+  if (inter_slice) {
     n_ref = st->num_ref_idx_default;
-    if (r.bit()) n_ref = (int)r.ue() + 1;
-    if (n_ref < 1 || n_ref > 32) return PARSE_INVALID;
+    n_ref1 = is_b ? st->num_ref_idx_l1_default : 0;
+    if (r.bit()) { n_ref = (int)r.ue() + 1; if (is_b) n_ref1 = (int)r.ue() + 1; }
+    if (n_ref < 1 || n_ref > 32 || (is_b && (n_ref1 < 1 || n_ref1 > 32))) return PARSE_INVALID;
     const int max_fn = 1 << st->log2_max_frame_num;
     // key: short-term pictures by PicNum (FrameNumWrap), long-term pictures by LongTermPicNum (= LongTermFrameIdx for frames)
-    struct Cand { int slot, num; bool lt; };
+    struct Cand { int slot, num; bool lt; int poc, pic_id; };
     Cand cand[32];
-    int nc = 0, n_st = 0;
+    int nc = 0;
     for (const ParserState::RefPic& rp : st->refs) {
-      if (nc >= 32 || rp.long_term) continue;
-      cand[nc].slot = rp.slot; cand[nc].lt = false;
-      cand[nc].num = rp.frame_num > ss.frame_num ? rp.frame_num - max_fn : rp.frame_num;      // FrameNumWrap
+      if (nc >= 32) break;
+      cand[nc].slot = rp.slot; cand[nc].lt = rp.long_term; cand[nc].poc = rp.poc; cand[nc].pic_id = rp.pic_id;
+      cand[nc].num = rp.long_term ? rp.lt_idx : (rp.frame_num > ss.frame_num ? rp.frame_num - max_fn : rp.frame_num);      // FrameNumWrap
       nc++;
     }
-    n_st = nc;
-    for (int i = 1; i < n_st; i++)                            // short-term: descending PicNum
-      for (int j = i; j > 0 && cand[j].num > cand[j - 1].num; j--) { const Cand t = cand[j]; cand[j] = cand[j - 1]; cand[j - 1] = t; }
-    for (const ParserState::RefPic& rp : st->refs) {
-      if (nc >= 32 || !rp.long_term) continue;
-      cand[nc].slot = rp.slot; cand[nc].lt = true; cand[nc].num = rp.lt_idx;
-      nc++;
-    }
-    for (int i = n_st + 1; i < nc; i++)                       // long-term: ascending LongTermPicNum
-      for (int j = i; j > n_st && cand[j].num < cand[j - 1].num; j--) { const Cand t = cand[j]; cand[j] = cand[j - 1]; cand[j - 1] = t; }
     if (nc == 0) return PARSE_INVALID;
-    int key[33];                                              // identity of an entry: PicNum, or LongTermPicNum + 2^20
-    for (int i = 0; i < 32; i++) {                            // entries past the available pictures repeat the last one (a conforming
-      const Cand& cd = cand[i < nc ? i : nc - 1];             // stream does not use them)
-      list0[i] = cd.slot;
-      key[i] = i < nc ? (cd.lt ? cd.num + (1 << 20) : cd.num) : -0x40000000;
+    auto key_of = [](const Cand& c) { return c.lt ? c.num + (1 << 20) : c.num; };   // identity of an entry: PicNum, or LongTermPicNum + 2^20
+    auto entry_of = [&](const Cand& c) { RefEntry e; e.slot = c.slot; e.key = key_of(c); e.poc = c.poc; e.pic_id = c.pic_id; e.lt = c.lt; return e; };
+    int ord[2][32], no[2] = {0, 0};
+    auto append_sorted = [&](int l, auto pick, auto before) {   // the candidates `pick` selects, ordered by `before`
+      const int first = no[l];
+      for (int i = 0; i < nc; i++) {
+        if (!pick(cand[i])) continue;
+        int j = no[l]++;
+        ord[l][j] = i;
+        for (; j > first && before(cand[ord[l][j]], cand[ord[l][j - 1]]); j--) { const int t = ord[l][j]; ord[l][j] = ord[l][j - 1]; ord[l][j - 1] = t; }
+      }
+    };
+    auto lt_asc = [](const Cand& a, const Cand& b) { return a.num < b.num; };
+    auto is_lt = [](const Cand& c) { return c.lt; };
+    if (is_p) {
+      append_sorted(0, [](const Cand& c) { return !c.lt; }, [](const Cand& a, const Cand& b) { return a.num > b.num; });
+      append_sorted(0, is_lt, lt_asc);
+    } else {
+      auto poc_desc = [](const Cand& a, const Cand& b) { return a.poc > b.poc; };
+      auto poc_asc = [](const Cand& a, const Cand& b) { return a.poc < b.poc; };
+      auto before_cur = [&](const Cand& c) { return !c.lt && c.poc < poc; };
+      auto after_cur = [&](const Cand& c) { return !c.lt && c.poc > poc; };
+      append_sorted(0, before_cur, poc_desc); append_sorted(0, after_cur, poc_asc); append_sorted(0, is_lt, lt_asc);
+      append_sorted(1, after_cur, poc_asc); append_sorted(1, before_cur, poc_desc); append_sorted(1, is_lt, lt_asc);
+      if (no[1] > 1 && no[0] == no[1]) {                      // identical lists: the first two entries of list 1 change places
+        bool same = true;
+        for (int i = 0; i < no[0]; i++) same = same && ord[0][i] == ord[1][i];
+        if (same) { const int t = ord[1][0]; ord[1][0] = ord[1][1]; ord[1][1] = t; }
+      }
     }
-    if (r.bit()) {                                            // ref_pic_list_modification_flag_l0 (8.2.4.3)
+    for (int l = 0; l < (is_b ? 2 : 1); l++)
+      for (int i = 0; i < 33; i++) {
+        if (i < no[l]) lists[l][i] = entry_of(cand[ord[l][i]]);
+        else if (is_p && no[l] > 0) { lists[l][i] = entry_of(cand[ord[l][no[l] - 1]]); lists[l][i].key = -0x40000000; }   // entries past the available
+        else lists[l][i] = RefEntry();                                                            // pictures (a conforming stream does not use them)
+      }
+    for (int l = 0; l < (is_b ? 2 : 1); l++) {
+      const int nref_l = l ? n_ref1 : n_ref;
+      RefEntry* L = lists[l];
+      if (!r.bit()) continue;                                 // ref_pic_list_modification_flag_lX (8.2.4.3)
       int pred = ss.frame_num, idx = 0;
       for (;;) {
         const uint32_t idc = r.ue();
         if (idc == 3) break;
         if (idc > 3 || !r.ok()) return PARSE_INVALID;
         const uint32_t v = r.ue();
-        if (idx >= n_ref) return PARSE_INVALID;
+        if (idx >= nref_l) return PARSE_INVALID;
         int want;
         if (idc == 2) {
           want = (int)v + (1 << 20);                          // long_term_pic_num
@@ -455,17 +501,19 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
           want = no_wrap > ss.frame_num ? no_wrap - max_fn : no_wrap;
         }
         int found = -1;
-        for (int i = 0; i < nc; i++) if ((cand[i].lt ? cand[i].num + (1 << 20) : cand[i].num) == want) found = cand[i].slot;
+        for (int i = 0; i < nc; i++) if (key_of(cand[i]) == want) found = i;
         if (found < 0) return PARSE_UNSUPPORTED;              // refers to a picture that is not in the buffer (loss): needs concealment
         // insert at idx, shift the rest, drop the later duplicate
-        for (int c = n_ref; c > idx; c--) { list0[c < 32 ? c : 31] = list0[c - 1]; key[c < 33 ? c : 32] = key[c - 1]; }
-        list0[idx] = found; key[idx] = want;
+        for (int c = nref_l; c > idx; c--) L[c] = L[c - 1];
+        L[idx] = entry_of(cand[found]);
         idx++;
         int nidx = idx;
-        for (int c = idx; c <= n_ref && c < 32; c++)
-          if (key[c] != want) { list0[nidx] = list0[c]; key[nidx] = key[c]; nidx++; }
+        for (int c = idx; c <= nref_l; c++)
+          if (L[c].key != want) L[nidx++] = L[c];
       }
     }
+    for (int i = 0; i < 32; i++) list0[i] = lists[0][i].slot;
+    for (int i = 0; i < n_ref; i++) if (list0[i] < 0 && is_p) return PARSE_INVALID;
   }
   const bool is_ref = nal.ref_idc != 0;                       // a non-reference picture is output but never predicted from
   bool adaptive = false, idr_lt = false;
@@ -489,7 +537,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     }
   }
   int cabac_init_idc = 0;
-  if (st->entropy_cabac && is_p) {
+  if (st->entropy_cabac && inter_slice) {
     const uint32_t v = r.ue();
     if (v > 2) return PARSE_INVALID;
     cabac_init_idc = (int)v;
@@ -528,15 +576,53 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
       pic->cur_slot = slot;
     }
     pic->disable_deblocking_idc = dbk_idc;
+    pic->poc = poc; pic->poc_msb = poc_msb; pic->poc_lsb = poc_lsb;
+    pic->pic_id = st->next_pic_id++;
+    pic->max_reorder = st->profile == 66 ? 0 : st->sp.num_ref_frames;
+    pic->has_b = false;
+    if (st->profile != 66) {                                  // the stream may hold B slices: keep the motion field of every picture
+      if ((int)st->motion.size() < st->n_slots) st->motion.resize(st->n_slots);
+      MotionStore& ms = st->motion[pic->cur_slot];
+      if ((int)ms.intra.size() != n) ms.size_for(n);
+      ms.poc = poc; ms.pic_id = pic->pic_id;
+    } else {
+      st->motion.clear();
+    }
     // the records are initialised as the macroblocks are parsed (7.3 MB per 1080p picture are not filled up front: a skipped
     // macroblock resets its 128 header bytes, a coded one its whole record); a picture is only handed out complete (next_mb == n)
     if ((int)pic->mbs.size() != n) pic->mbs.assign(n, MbOut());
     DecMbAux za;
     memset(&za, 0, sizeof(za));
     pic->aux.assign(n, za);
-  } else if (ss.idr != pic->ss.idr || ss.frame_num != pic->ss.frame_num || is_ref != pic->is_ref) {
+  } else if (ss.idr != pic->ss.idr || ss.frame_num != pic->ss.frame_num || is_ref != pic->is_ref || poc != pic->poc) {
     return PARSE_INVALID;                                     // slices of one access unit must agree
   }
+  if (is_b && !pic->has_b) {
+    pic->has_b = true;
+    DecMbAuxB zb;
+    memset(&zb, 0, sizeof(zb));
+    pic->aux_b.assign(n, zb);
+  }
+  // host-side motion derivation (h264_motion.h): the field of every picture where B slices may occur, B macroblocks resolved here
+  MotionCtx M;
+  const bool track = !st->motion.empty();
+  if (track) { M.cur = &st->motion[pic->cur_slot]; M.mbw = mbw; }
+  BSliceCtx bsl;
+  if (is_b) {
+    bsl.direct_spatial = direct_spatial; bsl.cur_poc = poc; bsl.n_ref[0] = n_ref; bsl.n_ref[1] = n_ref1;
+    for (int l = 0; l < 2; l++) for (int i = 0; i < 33; i++) bsl.list[l][i] = lists[l][i];
+    bsl.implicit = st->weighted_bipred_idc == 2;
+    const int cslot = lists[1][0].slot;
+    bsl.col = (cslot >= 0 && cslot < (int)st->motion.size()) ? &st->motion[cslot] : nullptr;
+    bsl.col_long_term = lists[1][0].lt;
+  }
+  auto track_mb = [&](int i, const int* ri) {                 // a macroblock of an I / P slice is complete: its cells of the field
+    if (!track) return;
+    const MbOut& mm = pic->mbs[i];
+    if (MBT_IS_INTRA(mm.mb_type)) M.store_intra(i);
+    else if (!MBT_IS_B(mm.mb_type)) derive_p(M, i, pic->aux[i].avail, mm, pic->aux[i], ri, lists[0]);
+  };
+  static const int kRiZero[4] = {0, 0, 0, 0};
   if (pic->n_slices >= 65535) return PARSE_UNSUPPORTED;
   const int slice_no = pic->n_slices++;
   if (dbk_idc != 1) pic->any_deblock = true;
@@ -548,7 +634,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     while (r.pos() & 7) if (!r.bit()) return PARSE_INVALID;   // cabac_alignment_one_bit
     if (!r.ok()) return PARSE_TRUNCATED;
     CabacDecoder d(nal.rbsp.data(), nal.rbsp.size());
-    d.init_contexts(ss.qp, is_p ? 1 + cabac_init_idc : 0);
+    d.init_contexts(ss.qp, inter_slice ? 1 + cabac_init_idc : 0);
     d.init_engine(r.pos());
     if ((int)pic->cabac_info.size() != n) pic->cabac_info.resize(n);
     CabacMbInfo* info = pic->cabac_info.data();
@@ -569,20 +655,32 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
       ax.flags = st->constrained_intra_pred ? DECAUX_CIP : 0;
       ax.avail = (uint8_t)((avL ? 1 : 0) | (avT ? 2 : 0) | (mbx > 0 && mby > 0 && same_slice(idx - mbw - 1) ? 4 : 0) |
                            (mby > 0 && mbx < mbw - 1 && same_slice(idx - mbw + 1) ? 8 : 0));
-      if (is_p && d.decision(11 + (L && !L->skip ? 1 : 0) + (T && !T->skip ? 1 : 0))) {       // mb_skip_flag
+      int cur_ri[4] = {0, 0, 0, 0};                           // ref_idx_l0 of the 8x8 blocks of a P macroblock (host-side motion field)
+      if (inter_slice && d.decision((is_b ? 24 : 11) + (L && !L->skip ? 1 : 0) + (T && !T->skip ? 1 : 0))) {       // mb_skip_flag
         reset_skip_record(&m);
         m.qp = (uint8_t)qp;
         ax.flags = 0;
-        for (int q = 0; q < 4; q++) ax.ref_idx[q] = (int8_t)list0[0];
-        me.type = MBT_PSKIP; me.skip = 1;
+        if (is_b) {                                           // B_Skip: direct prediction, no residual
+          m.mb_type = MBT_BSKIP;
+          BMbSyntax sx;
+          sx.skip = true;
+          if (!derive_b(M, idx, ax.avail, sx, bsl, &ax, &pic->aux_b[idx])) return PARSE_INVALID;
+          me.type = MBT_BSKIP; me.skip = 1; me.direct = 1;
+        } else {
+          for (int q = 0; q < 4; q++) ax.ref_idx[q] = (int8_t)list0[0];
+          me.type = MBT_PSKIP; me.skip = 1;
+        }
         prev_dqp_nonzero = false;
       } else {
         memset(&m, 0, sizeof(m));
         int t;
-        bool intra = !is_p;
+        bool intra = !inter_slice;
         if (is_p) {
           t = d.mb_type_p();
           if (t >= 5) { intra = true; t -= 5; }
+        } else if (is_b) {
+          t = d.mb_type_b((L && !L->direct ? 1 : 0) + (T && !T->direct ? 1 : 0));
+          if (t >= 23) { intra = true; t -= 23; }
         } else {
           t = d.mb_type_intra(3 + (L && L->type != MBT_I4x4 ? 1 : 0) + (T && T->type != MBT_I4x4 ? 1 : 0), false);
         }
@@ -602,7 +700,54 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
           me.type = MBT_IPCM; me.cbp = 0x2f; me.cbf = 0x7ffffff;
           prev_dqp_nonzero = false;
         } else {
-          if (!intra) {
+          if (!intra && is_b) {
+            // B macroblock (7.3.5.1 / 7.3.5.2 for B slices): the syntax is collected, then resolved on the host (h264_motion.h)
+            m.mb_type = MBT_B;
+            BMbSyntax sx;
+            memset(sx.ref, 0, sizeof(sx.ref)); memset(sx.mvd, 0, sizeof(sx.mvd));
+            sx.type = t;
+            if (t == 0) me.direct = 1;
+            if (t == 22) for (int k = 0; k < 4; k++) sx.sub[k] = d.sub_mb_type_b();
+            BUnit ru[4], mu[16];
+            const int nru = b_ref_units(sx, ru), nmu = b_mvd_units(sx, mu);
+            for (int l = 0; l < 2; l++) {
+              const int nref_l = l ? n_ref1 : n_ref;
+              uint8_t& gt = l ? me.ref_gt0_l1 : me.ref_gt0;
+              for (int i = 0; i < nru; i++) {
+                if (!(ru[i].lists & (1 << l))) continue;
+                int v = 0;
+                if (nref_l > 1) {
+                  const int q = ru[i].q0, qx = q & 1, qy = q >> 1;
+                  auto bits_of = [&](const CabacMbInfo* nb) { return nb ? (l ? nb->ref_gt0_l1 : nb->ref_gt0) : 0; };
+                  const int a = qx ? (gt >> (q - 1)) & 1 : (bits_of(L) >> (qy * 2 + 1)) & 1;
+                  const int b = qy ? (gt >> (q - 2)) & 1 : (bits_of(T) >> (2 + qx)) & 1;
+                  v = d.ref_idx(a + 2 * b);
+                }
+                if (v >= nref_l) return PARSE_INVALID;
+                for (int q = 0; q < 4; q++) if (ru[i].qmask & (1 << q)) sx.ref[l][q] = v;
+                if (v > 0) gt |= (uint8_t)ru[i].qmask;
+              }
+            }
+            for (int l = 0; l < 2; l++) {
+              uint8_t (*mine)[2] = l ? me.mvd_l1 : me.mvd;
+              for (int i = 0; i < nmu; i++) {
+                if (!(mu[i].lists & (1 << l))) continue;
+                const int bx = mu[i].bx, by = mu[i].by;
+                int v[2];
+                for (int c = 0; c < 2; c++) {
+                  const int a = bx > 0 ? mine[by * 4 + bx - 1][c] : (L ? (l ? L->mvd_l1 : L->mvd)[by * 4 + 3][c] : 0);
+                  const int b = by > 0 ? mine[(by - 1) * 4 + bx][c] : (T ? (l ? T->mvd_l1 : T->mvd)[12 + bx][c] : 0);
+                  v[c] = d.mvd(c ? 47 : 40, a + b);
+                }
+                sx.mvd[l][mu[i].slot][0] = (int16_t)v[0]; sx.mvd[l][mu[i].slot][1] = (int16_t)v[1];
+                const uint8_t a0 = (uint8_t)(abs(v[0]) > 255 ? 255 : abs(v[0])), a1 = (uint8_t)(abs(v[1]) > 255 ? 255 : abs(v[1]));
+                for (int y = 0; y < mu[i].h4; y++)
+                  for (int x = 0; x < mu[i].w4; x++) { mine[(by + y) * 4 + bx + x][0] = a0; mine[(by + y) * 4 + bx + x][1] = a1; }
+              }
+            }
+            if (!d.ok()) return PARSE_TRUNCATED;
+            if (!derive_b(M, idx, ax.avail, sx, bsl, &ax, &pic->aux_b[idx])) return PARSE_INVALID;
+          } else if (!intra) {
             int ri[4] = {0, 0, 0, 0};
             // partitions as (first 4x4 block, width, height in 4x4 blocks); a P_8x8 macroblock lists its sub-macroblock partitions
             struct Part { int b, w, h, q, slot; };             // q: 8x8 quadrant; slot: where the vector goes (m.mvd / ax.mvd index)
@@ -653,6 +798,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
             for (int k = 0; k < 4; k++) {
               if (ri[k] < 0 || ri[k] >= n_ref) return PARSE_INVALID;
               ax.ref_idx[k] = (int8_t)list0[ri[k]];
+              cur_ri[k] = ri[k];
             }
             for (int pi = 0; pi < np; pi++) {
               const Part& pt = parts[pi];
@@ -759,6 +905,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
         }
       }
       if (!d.ok()) return PARSE_TRUNCATED;
+      track_mb(idx, cur_ri);
       idx++;
       if (d.terminate()) break;                               // end_of_slice_flag
     }
@@ -770,7 +917,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
   int qp = ss.qp;
   int idx = first_mb;
   while (idx < n) {
-    if (is_p) {
+    if (inter_slice) {
       const int run = (int)r.ue();
       if (!r.ok() || idx + run > n) return PARSE_INVALID;
       for (int k = 0; k < run; k++, idx++) {
@@ -778,10 +925,18 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
         pic->mbs[idx].qp = (uint8_t)qp;
         DecMbAux& a = pic->aux[idx];
         a.slice = (uint16_t)slice_no; a.dbk_idc = (uint8_t)dbk_idc; a.alpha_off = (int8_t)alpha_off; a.beta_off = (int8_t)beta_off;
-        for (int q = 0; q < 4; q++) a.ref_idx[q] = (int8_t)list0[0];
         const int x = idx % mbw, y = idx / mbw;
         a.avail = (uint8_t)((x > 0 && same_slice(idx - 1) ? 1 : 0) | (y > 0 && same_slice(idx - mbw) ? 2 : 0) |
                             (x > 0 && y > 0 && same_slice(idx - mbw - 1) ? 4 : 0) | (y > 0 && x < mbw - 1 && same_slice(idx - mbw + 1) ? 8 : 0));
+        if (is_b) {                                           // B_Skip
+          pic->mbs[idx].mb_type = MBT_BSKIP;
+          BMbSyntax sx;
+          sx.skip = true;
+          if (!derive_b(M, idx, a.avail, sx, bsl, &a, &pic->aux_b[idx])) return PARSE_INVALID;
+        } else {
+          for (int q = 0; q < 4; q++) a.ref_idx[q] = (int8_t)list0[0];
+          track_mb(idx, kRiZero);
+        }
       }
       if (idx == n || !r.more_data()) break;                  // the slice may end with a skip run
     }
@@ -796,12 +951,41 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     ax.avail = (uint8_t)((avL ? 1 : 0) | (avT ? 2 : 0) | (mbx > 0 && mby > 0 && same_slice(idx - mbw - 1) ? 4 : 0) |
                          (mby > 0 && mbx < mbw - 1 && same_slice(idx - mbw + 1) ? 8 : 0));
     int t = (int)r.ue();
-    bool intra = !is_p;
+    bool intra = !inter_slice;
     if (is_p) {
       if (t >= 5) { intra = true; t -= 5; }
+    } else if (is_b) {
+      if (t >= 23) { intra = true; t -= 23; }
     }
     int cbp = -1;
-    if (!intra) {
+    int cur_ri[4] = {0, 0, 0, 0};
+    if (!intra && is_b) {
+      // B macroblock: the syntax is collected (mb_pred / sub_mb_pred of B slices), then resolved on the host (h264_motion.h)
+      m.mb_type = MBT_B;
+      BMbSyntax sx;
+      memset(sx.ref, 0, sizeof(sx.ref)); memset(sx.mvd, 0, sizeof(sx.mvd));
+      sx.type = t;
+      if (t == 22)
+        for (int k = 0; k < 4; k++) { const uint32_t v = r.ue(); if (v > 12) return PARSE_INVALID; sx.sub[k] = (int)v; }
+      BUnit ru[4], mu[16];
+      const int nru = b_ref_units(sx, ru), nmu = b_mvd_units(sx, mu);
+      for (int l = 0; l < 2; l++) {
+        const int nref_l = l ? n_ref1 : n_ref;
+        for (int i = 0; i < nru; i++) {
+          if (!(ru[i].lists & (1 << l))) continue;
+          const int v = nref_l == 1 ? 0 : nref_l == 2 ? !r.bit() : (int)r.ue();       // te(v)
+          if (v < 0 || v >= nref_l) return PARSE_INVALID;
+          for (int q = 0; q < 4; q++) if (ru[i].qmask & (1 << q)) sx.ref[l][q] = v;
+        }
+      }
+      for (int l = 0; l < 2; l++)
+        for (int i = 0; i < nmu; i++) {
+          if (!(mu[i].lists & (1 << l))) continue;
+          sx.mvd[l][mu[i].slot][0] = (int16_t)r.se(); sx.mvd[l][mu[i].slot][1] = (int16_t)r.se();
+        }
+      if (!r.ok()) return PARSE_TRUNCATED;
+      if (!derive_b(M, idx, ax.avail, sx, bsl, &ax, &pic->aux_b[idx])) return PARSE_INVALID;
+    } else if (!intra) {
       // ref_idx_l0: te(v) with range num_ref_idx_active - 1 (9.1): absent for one picture, an inverted bit for two, else ue(v)
       auto read_ref = [&]() -> int {
         if (n_ref == 1) return 0;
@@ -837,6 +1021,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
       for (int k = 0; k < 4; k++) {
         if (ri[k] < 0 || ri[k] >= n_ref) return PARSE_INVALID;
         ax.ref_idx[k] = (int8_t)list0[ri[k]];
+        cur_ri[k] = ri[k];
       }
     } else {
       if (t == 0) {
@@ -862,6 +1047,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
         m.qp = 0;                                             // QP'Y of an I_PCM macroblock is 0 for the deblocking filter; like the reference
                                                               // decoder (decode_slice.cpp:1870: iLastMbQp untouched) the QP predictor
                                                               // of the next macroblock stays what it was
+        track_mb(idx, kRiZero);
         idx++;
         if (!r.more_data()) break;
         continue;
@@ -918,6 +1104,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     }
     m.qp = (uint8_t)qp;
     if (!r.ok()) return PARSE_TRUNCATED;
+    track_mb(idx, cur_ri);
     idx++;
     if (!r.more_data()) break;                                // end of this slice
   }
@@ -995,9 +1182,12 @@ int parse_access_unit(const uint8_t* au, size_t len, ParserState* st, ParsedPict
     }
     ParserState::RefPic rp;
     rp.slot = pic->cur_slot; rp.frame_num = reset ? 0 : cur; rp.long_term = cur_long; rp.lt_idx = cur_lt_idx;
+    rp.poc = pic->poc; rp.pic_id = pic->pic_id;
     st->refs.push_back(rp);
     st->have_ref = true; st->last_frame_num = reset ? 0 : cur;
+    st->prev_poc_msb = reset ? 0 : pic->poc_msb; st->prev_poc_lsb = reset ? 0 : pic->poc_lsb;
   }
+  st->decode_count = pic->ss.idr ? 1 : st->decode_count + 1;
   return PARSE_OK;
 }
 

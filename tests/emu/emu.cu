@@ -6,10 +6,13 @@
 // container without a GPU.  It is built into tests/emu/libb2h264_emu.so, which the product library
 // never links or loads; the shipped path is the CUDA one (enc_kernels.cu) and fails without a device.
 #include <stddef.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include <chrono>
+#include <array>
+#include <algorithm>
 #include <vector>
 
 #define B2H264_WITH_INTER 1
@@ -295,7 +298,8 @@ extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, i
   int n_slots = 0;
   std::vector<MbInfo> mbi;
   static MbScratch scratch;
-  int frames = 0;
+  int frames = 0, seq = 0;
+  std::vector<std::array<int, 3>> order;      // (coded video sequence, picture order count, position in `out`) of every picture
   long outpos = 0;
   bool have_buffers = false;
   auto is_start = [&](long k) { return k + 2 < len && bs[k] == 0 && bs[k + 1] == 0 && bs[k + 2] == 1; };
@@ -353,6 +357,22 @@ extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, i
       }
       f.dpb_stride = (int64_t)pic_bytes;
       f.mbi = mbi.data();
+      f.dec_aux_b = pp.has_b ? pp.aux_b.data() : nullptr;
+      if (const char* dbg = getenv("EMU_DUMP_MB")) {            // debugging aid: "frame,mbx,mby"
+        int df = 0, dx = 0, dy = 0;
+        if (sscanf(dbg, "%d,%d,%d", &df, &dx, &dy) == 3 && df == frames && dx < p.mb_w && dy < p.mb_h) {
+          const MbOut& m = pp.mbs[(size_t)dy * p.mb_w + dx];
+          const DecMbAux& a = pp.aux[(size_t)dy * p.mb_w + dx];
+          fprintf(stderr, "mb (%d,%d) frame %d: type %d cbp %d qp %d i16 %d chroma %d avail %d flags %d poc %d\n", dx, dy, df, m.mb_type, m.cbp, m.qp, m.i16_mode, m.chroma_mode, a.avail, a.flags, pp.poc);
+          fprintf(stderr, "  i4 prev/rem:");
+          for (int k = 0; k < 16; k++) fprintf(stderr, " %d/%d", m.prev_i4_flag[k], m.rem_i4_mode[k]);
+          fprintf(stderr, "\n  ref0 %d %d %d %d", a.ref_idx[0], a.ref_idx[1], a.ref_idx[2], a.ref_idx[3]);
+          if (pp.has_b) { const DecMbAuxB& b = pp.aux_b[(size_t)dy * p.mb_w + dx]; fprintf(stderr, " ref1 %d %d %d %d w1 %d", b.ref_idx[0], b.ref_idx[1], b.ref_idx[2], b.ref_idx[3], b.w1[0]);
+            fprintf(stderr, "\n  mv0:"); for (int k = 0; k < 16; k++) fprintf(stderr, " (%d,%d)", a.mvd[k][0], a.mvd[k][1]);
+            fprintf(stderr, "\n  mv1:"); for (int k = 0; k < 16; k++) fprintf(stderr, " (%d,%d)", b.mv[k][0], b.mv[k][1]); }
+          fprintf(stderr, "\n");
+        }
+      }
       for (int mby = 0; mby < p.mb_h; mby++)
         for (int mbx = 0; mbx < p.mb_w; mbx++) dec_one_mb(p, f, scratch, mbx, mby, pp.mbs[(size_t)mby * p.mb_w + mbx], pp.aux[(size_t)mby * p.mb_w + mbx]);
       if (pp.any_deblock) deblock_frame_host(p, f);
@@ -365,10 +385,23 @@ extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, i
         const int cx = pp.crop_left >> (pl ? 1 : 0), cy = pp.crop_top >> (pl ? 1 : 0);
         for (int y = 0; y < ph; y++) { memcpy(out + outpos, f.rec[pl] + (size_t)(y + cy) * stp + cx, pw); outpos += pw; }
       }
+      if (pp.ss.idr) seq++;
+      order.push_back({seq, pp.poc, frames});
       frames++;
       au_begin = au_end;
     }
     pos = next;
+  }
+  // output order: by picture order count inside every coded video sequence (an IDR picture starts a new one); decoding order for
+  // streams without B slices (their counts rise with the decoding order)
+  bool sorted = true;
+  for (size_t i = 1; i < order.size(); i++) sorted = sorted && !(order[i] < order[i - 1]);
+  if (!sorted) {
+    std::vector<std::array<int, 3>> o2 = order;
+    std::stable_sort(o2.begin(), o2.end(), [](const std::array<int, 3>& a, const std::array<int, 3>& b) { return a[0] != b[0] ? a[0] < b[0] : a[1] < b[1]; });
+    const size_t fsz = (size_t)*w * *h * 3 / 2;
+    std::vector<uint8_t> tmp(out, out + fsz * frames);
+    for (int i = 0; i < frames; i++) memcpy(out + fsz * i, tmp.data() + fsz * o2[i][2], fsz);
   }
   return frames > 0 ? frames : -3;          // nothing decodable is an error, not an empty success
 }

@@ -60,6 +60,16 @@ def dump(bs, verbose=True):
         info = {"off": off, "type": t, "ref_idc": ref, "size": len(nal)}
         if t == 7:
             info["profile"] = r.u(8); info["constraints"] = r.u(8); info["level"] = r.u(8); info["sps_id"] = r.ue()
+            if info["profile"] in (100, 110, 122, 244, 44, 83, 86, 118, 128):
+                info["chroma_format"] = r.ue(); info["bit_depth"] = (r.ue() + 8, r.ue() + 8); info["bypass"] = r.u(1)
+                info["scaling_matrix"] = r.u(1)
+                if info["scaling_matrix"]:
+                    for k in range(8):
+                        if r.u(1):
+                            last = nxt = 8
+                            for _ in range(16 if k < 6 else 64):
+                                if nxt: nxt = (last + r.se() + 256) % 256
+                                last = nxt if nxt else last
             info["log2_max_frame_num"] = r.ue() + 4; info["poc_type"] = r.ue()
             if info["poc_type"] == 0: info["log2_max_poc_lsb"] = r.ue() + 4
             info["num_ref"] = r.ue(); info["gaps"] = r.u(1); info["mbw"] = r.ue() + 1; info["mbh"] = r.ue() + 1
@@ -72,12 +82,17 @@ def dump(bs, verbose=True):
             info["slice_groups"] = r.ue() + 1; info["nref0"] = r.ue() + 1; info["nref1"] = r.ue() + 1
             info["wp"] = r.u(1); info["wbi"] = r.u(2); info["init_qp"] = r.se() + 26; info["init_qs"] = r.se() + 26
             info["cqp_off"] = r.se(); info["dbf_ctrl"] = r.u(1); info["cip"] = r.u(1); info["red"] = r.u(1)
+            if r.p + 8 < 8 * (len(nal) - 1):
+                info["t8x8"] = r.u(1); info["pps_scaling"] = r.u(1)
+            pps = info
         elif t in (1, 5):
             info["first_mb"] = r.ue(); info["slice_type"] = r.ue(); info["pps_id"] = r.ue()
             info["frame_num"] = r.u(sps.get("log2_max_frame_num", 15))
             if t == 5: info["idr_pic_id"] = r.ue()
             if sps.get("poc_type", 2) == 0: info["poc_lsb"] = r.u(sps["log2_max_poc_lsb"])
-            if info["slice_type"] % 5 == 0:
+            if info["slice_type"] % 5 == 1:
+                info["direct_spatial"] = r.u(1)
+            if info["slice_type"] % 5 in (0, 1):
                 info["num_ref_override"] = r.u(1)
                 if info["num_ref_override"]: info["nref"] = r.ue() + 1
                 info["reorder"] = r.u(1)

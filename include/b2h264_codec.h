@@ -109,8 +109,8 @@ int  b2h264_enc_set_stream (b2h264_enc* e, void* stream);
 /* ---- batched decoder (first device version of the decoder construct path) -----------------
  * Replaces, for Baseline / Main / High streams with CAVLC or CABAC slice data (I and P slices, several slices per picture in raster
  * order, up to 16 reference frames with list modification, sliding-window and memory-management marking incl. long-term pictures,
- * all partition shapes down to 4x4, I_PCM, constrained intra prediction, per-slice deblocking control, non-reference pictures; no
- * FMO / ASO, B slices, weighted prediction, interlace, 8x8 transform or scaling lists), ISVCDecoder::DecodeFrameNoDelay
+ * all partition shapes down to 4x4, I_PCM, constrained intra prediction, per-slice deblocking control, non-reference pictures, B slices with
+ * spatial / temporal direct prediction and implicit weights; no FMO / ASO, explicit weighted prediction, interlace, 8x8 transform or scaling lists), ISVCDecoder::DecodeFrameNoDelay
  * (codec/api/wels/codec_api.h:383; codec/decoder/plus/src/welsDecoderExt.cpp:~700).  The host parses, the GPU
  * reconstructs, deblocks and pads.  Anything else is rejected: -101 truncated, -102 unsupported stream feature,
  * -103 invalid syntax, -104 slice before its parameter sets, -105 the slices given do not cover the picture; -2 picture size differs from the configuration. */
@@ -132,6 +132,11 @@ int  b2h264_dec_decode2 (b2h264_dec* d, const uint8_t* const* au, const int32_t*
  * au[s] == NULL), < 0 that stream's own error (-101 .. -105 as above, -2 size mismatch) — it sits the batch out, the other streams are
  * decoded.  The return value only reports errors of the call as a whole (CUDA). */
 int  b2h264_dec_decode3 (b2h264_dec* d, const uint8_t* const* au, const int32_t* au_bytes, uint8_t* const* yuv, int32_t* status);
+/* Pictures come back in DECODING order.  Of the picture stream `stream` decoded last: its picture order count inside its coded video
+ * sequence, *flags (bit 0: an IDR picture — a new sequence starts; bit 1: the picture holds B slices), and the stream's reorder depth (num_ref_frames; 0 for Baseline streams,
+ * whose decoding order is the output order).  The reference reorders inside DecodeFrameNoDelay (welsDecoderExt.cpp: ReorderPicturesInDisplay);
+ * layer 3 does the same with these values. */
+int  b2h264_dec_last_picture_order (b2h264_dec* d, int stream, int32_t* poc, int32_t* flags, int32_t* reorder_depth);
 /* stream `stream` starts over: parameter sets, frame numbering and reference pictures are forgotten (the next unit must carry SPS / PPS / IDR) */
 int  b2h264_dec_reset_stream (b2h264_dec* d, int stream);
 /* stateless look at an access unit: *has_slice, and — if it carries an SPS of the supported class — the cropped picture

@@ -93,6 +93,7 @@ API = {
     "b2h264_dec_decode3": [vp, C.POINTER(vp), C.POINTER(C.c_int32), C.POINTER(vp), C.POINTER(C.c_int32)],
     "b2h264_dec_probe": [vp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
     "b2h264_dec_reset_stream": [vp, C.c_int32],
+    "b2h264_dec_last_picture_order": [vp, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
     "b2h264_host_alloc": [C.c_size_t],
     "b2h264_host_free": [vp],
     "b2h264_enc_set_stream": [vp, vp],
@@ -337,6 +338,13 @@ class BatchDecoder:
 
     def reset_stream(self, stream):
         check(self.L.b2h264_dec_reset_stream(self.h, stream))
+
+    def picture_order(self, stream=0):
+        """(picture order count, flags: bit 0 IDR / bit 1 holds B slices, reorder depth) of the picture `stream` decoded last (b2h264_dec_last_picture_order): pictures
+        come back in DECODING order; streams with B slices are output by ascending count inside each IDR period."""
+        poc, idr, depth = C.c_int32(), C.c_int32(), C.c_int32()
+        check(self.L.b2h264_dec_last_picture_order(self.h, stream, C.byref(poc), C.byref(idr), C.byref(depth)))
+        return poc.value, idr.value, depth.value
 
     def close(self):
         if self.h:

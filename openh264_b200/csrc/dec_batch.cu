@@ -51,6 +51,9 @@ struct b2h264_dec {
   std::vector<int> units;                 // 32-byte units packed per active stream
   DecMbAux* d_aux = nullptr;
   DecMbAux* h_aux = nullptr;              // pinned
+  DecMbAuxB* d_aux_b = nullptr;           // list 1 of B macroblocks: allocated when the first picture with B slices arrives
+  DecMbAuxB* h_aux_b = nullptr;           // pinned
+  std::vector<int> last_poc, last_idr, last_reorder;   // per stream: picture order count / IDR flag / reorder depth of the last decoded picture
   StreamFrame* d_sf = nullptr;
   StreamFrame* h_sf = nullptr;            // pinned
   int* d_ws = nullptr;
@@ -97,6 +100,7 @@ int b2h264_dec_create(const b2h264_dec_config* cfg, b2h264_dec** out) {
   CK(cudaMallocHost(&d->h_idx, S * d->n_mb * sizeof(int32_t)));
   CK(cudaMalloc(&d->d_idx, S * d->n_mb * sizeof(int32_t)));
   d->units.assign(d->S, 0);
+  d->last_poc.assign(d->S, 0); d->last_idr.assign(d->S, 0); d->last_reorder.assign(d->S, 0);
   CK(cudaMalloc(&d->d_aux, S * d->n_mb * sizeof(DecMbAux)));
   CK(cudaMallocHost(&d->h_aux, S * d->n_mb * sizeof(DecMbAux)));
   CK(cudaMalloc(&d->d_sf, S * sizeof(StreamFrame)));
@@ -112,6 +116,8 @@ void b2h264_dec_destroy(b2h264_dec* d) {
   if (d->st) cudaStreamSynchronize(d->st);
   cudaFree(d->d_pic);
   cudaFree(d->d_mbi); cudaFree(d->d_recs); cudaFree(d->d_aux); cudaFreeHost(d->h_aux); cudaFree(d->d_sf); cudaFree(d->d_ws);
+  if (d->d_aux_b) cudaFree(d->d_aux_b);
+  if (d->h_aux_b) cudaFreeHost(d->h_aux_b);
   cudaFreeHost(d->h_recs); cudaFreeHost(d->h_sf); cudaFree(d->d_pack); cudaFreeHost(d->h_idx); cudaFree(d->d_idx);
   if (d->st) cudaStreamDestroy(d->st);
   delete d->pool;
@@ -138,8 +144,10 @@ static int dec_decode_impl(b2h264_dec* d, const uint8_t* const* au, const int32_
       ParsedPicture& pp = d->parsed[s];               // a fresh picture that keeps the record arrays' storage
       std::vector<MbOut> m = std::move(pp.mbs);
       std::vector<DecMbAux> a = std::move(pp.aux);
+      std::vector<DecMbAuxB> ab = std::move(pp.aux_b);
+      std::vector<CabacMbInfo> ci = std::move(pp.cabac_info);
       pp = ParsedPicture();
-      pp.mbs = std::move(m); pp.aux = std::move(a);
+      pp.mbs = std::move(m); pp.aux = std::move(a); pp.aux_b = std::move(ab); pp.cabac_info = std::move(ci);
       d->parse_rc[s] = (!au[s] || au_bytes[s] <= 0) ? PARSE_NO_PICTURE : parse_access_unit(au[s], (size_t)au_bytes[s], &d->parser[s], &pp);
     };
     d->pool->run(S, job);
@@ -162,6 +170,7 @@ static int dec_decode_impl(b2h264_dec* d, const uint8_t* const* au, const int32_
     if (sp.mb_w != d->mb_w || sp.mb_h != d->mb_h || sp.width != d->cfg.width || sp.height != d->cfg.height) STREAM_FAIL(-2)
     if ((int)pic.mbs.size() != d->n_mb) STREAM_FAIL(-103)
     if ((int)pic.aux.size() != d->n_mb) STREAM_FAIL(-103)
+    if (pic.has_b && (int)pic.aux_b.size() != d->n_mb) STREAM_FAIL(-103)
     if (pic.n_slots > d->slots) {                   // a stream with more reference frames: widen every stream's slot array, keeping the pictures
       if (pic.n_slots > 17) STREAM_FAIL(-103)
       uint8_t* np = nullptr;
@@ -192,6 +201,14 @@ static int dec_decode_impl(b2h264_dec* d, const uint8_t* const* au, const int32_
     for (int pl = 0; pl < 3; pl++) { F.f.rec[pl] = d->plane0(pic.cur_slot, s, pl); F.f.ref[pl] = F.f.dpb0[pl] = d->plane0(0, s, pl); }
     F.f.dpb_stride = (int64_t)d->pic_bytes;
     F.f.mbi = d->d_mbi + (size_t)s * d->n_mb;
+    d->last_poc[s] = pic.poc; d->last_idr[s] = (pic.ss.idr ? 1 : 0) | (pic.has_b ? 2 : 0); d->last_reorder[s] = pic.max_reorder;
+    if (pic.has_b) {                                // list-1 records of the picture's B macroblocks travel beside the aux records
+      if (!d->d_aux_b) {
+        CK(cudaMalloc(&d->d_aux_b, (size_t)S * d->n_mb * sizeof(DecMbAuxB)));
+        CK(cudaMallocHost(&d->h_aux_b, (size_t)S * d->n_mb * sizeof(DecMbAuxB)));
+      }
+      F.f.dec_aux_b = d->d_aux_b + (size_t)i * d->n_mb;
+    }
   }
   const int n = (int)d->act.size();
   if (n == 0) return 0;
@@ -200,6 +217,7 @@ static int dec_decode_impl(b2h264_dec* d, const uint8_t* const* au, const int32_
       const ParsedPicture& pic = d->parsed[d->act[i]];
       d->units[i] = pack_records_compact(pic.mbs.data(), d->n_mb, reinterpret_cast<uint8_t*>(d->h_recs + (size_t)i * d->n_mb), d->h_idx + (size_t)i * d->n_mb);
       memcpy(d->h_aux + (size_t)i * d->n_mb, pic.aux.data(), (size_t)d->n_mb * sizeof(DecMbAux));
+      if (pic.has_b) memcpy(d->h_aux_b + (size_t)i * d->n_mb, pic.aux_b.data(), (size_t)d->n_mb * sizeof(DecMbAuxB));
     };
     d->pool->run(n, job);
   }
@@ -210,8 +228,13 @@ static int dec_decode_impl(b2h264_dec* d, const uint8_t* const* au, const int32_
   CK(cudaMemcpyAsync(d->d_idx, d->h_idx, (size_t)n * d->n_mb * sizeof(int32_t), cudaMemcpyHostToDevice, d->st));
   { const int rcu = dec_launch_unpack(d->d_pack, (size_t)d->n_mb * sizeof(MbOut), d->d_idx, d->d_recs, n, d->n_mb, d->st); if (rcu) return rcu; }
   CK(cudaMemcpyAsync(d->d_aux, d->h_aux, (size_t)n * d->n_mb * sizeof(DecMbAux), cudaMemcpyHostToDevice, d->st));
+  for (int i = 0; i < n; i++)
+    if (d->parsed[d->act[i]].has_b)
+      CK(cudaMemcpyAsync(d->d_aux_b + (size_t)i * d->n_mb, d->h_aux_b + (size_t)i * d->n_mb, (size_t)d->n_mb * sizeof(DecMbAuxB), cudaMemcpyHostToDevice, d->st));
   CK(cudaMemcpyAsync(d->d_sf, d->h_sf, (size_t)n * sizeof(StreamFrame), cudaMemcpyHostToDevice, d->st));
-  const int rc = dec_launch_frame(d->d_sf, n, d->mb_w, d->mb_h, d->d_ws, d->d_recs, d->d_aux, deblock, d->st);
+  int b_slices = 0;
+  for (int i = 0; i < n; i++) b_slices |= d->parsed[d->act[i]].has_b ? 1 : 0;
+  const int rc = dec_launch_frame(d->d_sf, n, d->mb_w, d->mb_h, d->d_ws, d->d_recs, d->d_aux, deblock, d->st, b_slices);
   if (rc) return rc;
   const double t_launch = ms_since(t0);
   if (timing) cudaStreamSynchronize(d->st);
@@ -263,6 +286,17 @@ int b2h264_dec_probe(const uint8_t* au, int32_t au_bytes, int32_t* width, int32_
   if (rc != PARSE_OK) return -100 + rc;
   if (w > 0 && width) *width = w;
   if (h > 0 && height) *height = h;
+  return 0;
+}
+
+// Output order: the decoder hands every picture back in DECODING order; *poc is its picture order count inside its coded video sequence
+// (*flags: bit 0 = IDR picture, a new sequence starts; bit 1 = the picture holds B slices), *reorder_depth how many later-decoded pictures may precede it on output (0: the stream class has no
+// reordering — Baseline — and decoding order is output order).  Layer 3 (ISVCDecoder) reorders with these.
+int b2h264_dec_last_picture_order(b2h264_dec* d, int stream, int32_t* poc, int32_t* flags, int32_t* reorder_depth) {
+  if (!d || stream < 0 || stream >= d->S) return -1;
+  if (poc) *poc = d->last_poc[stream];
+  if (flags) *flags = d->last_idr[stream];
+  if (reorder_depth) *reorder_depth = d->last_reorder[stream];
   return 0;
 }
 

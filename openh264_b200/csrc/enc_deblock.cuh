@@ -36,6 +36,7 @@ MBK_HD void dbk_block_motion(const MbInfo* m, const DecMbAuxB* b, int blk, int r
 }
 MBK_HD bool dbk_mv_far(const int a[2], const int b[2]) { return iabs(a[0] - b[0]) >= 4 || iabs(a[1] - b[1]) >= 4; }
 
+template <bool BSL = true>
 MBK_HD void edge_bs(const MbInfo* cur, const MbInfo* nb /*other MB for edge 0, else == cur*/, int dir, int edge, int bs[4],
                     bool ref_ids = false /* decoder: i4_mode holds the reference picture of every 4x4 block */,
                     const DecMbAuxB* cur_b = nullptr, const DecMbAuxB* nb_b = nullptr /* list 1 of a B macroblock, else NULL */) {
@@ -45,9 +46,9 @@ MBK_HD void edge_bs(const MbInfo* cur, const MbInfo* nb /*other MB for edge 0, e
     const int q = dir == 0 ? i * 4 + edge : edge * 4 + i;
     const int p = dir == 0 ? (mb_edge ? i * 4 + 3 : q - 1) : (mb_edge ? 12 + i : q - 4);
     if (MBT_IS_INTRA(cur->mb_type) || MBT_IS_INTRA(nb->mb_type)) { bs[i] = mb_edge ? 4 : 3; continue; }
-    if (!mb_edge && (cur->mb_type == MBT_PSKIP || cur->mb_type == MBT_BSKIP)) { bs[i] = 0; continue; }
+    if (!mb_edge && (cur->mb_type == MBT_PSKIP || (BSL && cur->mb_type == MBT_BSKIP))) { bs[i] = 0; continue; }
     if (cur->nnz[q] | nb->nnz[p]) { bs[i] = 2; continue; }
-    if (cur_b || nb_b) {
+    if (BSL && (cur_b || nb_b)) {
       // a B macroblock on either side (DeblockingBSliceBsMarginalMBAvcbase / IN_SMB_EDGE_MV, deblocking.cpp:544, :95): strength 1
       // unless both blocks use the same set of reference pictures and their vectors — matched by picture — are close
       int rq[2], rp[2], mq[2][2], mp[2][2];
@@ -76,6 +77,8 @@ struct alignas(16) DbkTile {
   uint8_t y[20 * DBK_PY];          // rows -4..15, cols -4..15 (sample (0,0) at y[4 * DBK_PY + 4])
   uint8_t c[2][12 * DBK_PC];       // rows -4..7, cols -4..7
   MbInfo m[3];                     // cur, left, top
+};
+struct alignas(16) DbkTileB : DbkTile {
   DecMbAuxB b[3];                  // decoder, pictures with B slices: list 1 of those of the three that are B macroblocks
 };
 
@@ -87,7 +90,10 @@ MBK_HD uint32_t dbk_ld32(const uint8_t* p) {
 #endif
 }
 
-MBK_HD void deblock_one_mb(const EncFrameParams& p, const EncFramePtrs& f, int mbx, int mby, DbkTile& t) {
+// BSL: the picture may hold B macroblocks (decoder only).  The encoder and B-free decoder pictures run the BSL = false instantiation,
+// whose code and shared-memory footprint are those of the single-list filter.
+template <bool BSL, typename Tile>
+MBK_HD void deblock_one_mb_t(const EncFrameParams& p, const EncFramePtrs& f, int mbx, int mby, Tile& t) {
   const int idx = mby * p.mb_w + mbx;
   uint8_t* y = f.rec[0] + (size_t)(mby * 16) * p.rec_stride_y + mbx * 16;
   uint8_t* u = f.rec[1] + (size_t)(mby * 8) * p.rec_stride_c + mbx * 8;
@@ -113,8 +119,8 @@ MBK_HD void deblock_one_mb(const EncFrameParams& p, const EncFramePtrs& f, int m
     }
   }
   warp_sync();
-  const DecMbAuxB* lb[3] = {nullptr, nullptr, nullptr};
-  if (f.dec_aux_b) {                                               // a picture with B slices: list 1 of the B macroblocks among the three
+  [[maybe_unused]] const DecMbAuxB* lb[3] = {nullptr, nullptr, nullptr};
+  if constexpr (BSL) if (f.dec_aux_b) {                                         // a picture with B slices: list 1 of the B macroblocks among the three
     constexpr int kWb = (int)(sizeof(DecMbAuxB) / 4);
     const int nidx[3] = {idx, mbx > 0 ? idx - 1 : idx, mby > 0 ? idx - p.mb_w : idx};
     for (int k = 0; k < 3; k++) {
@@ -142,7 +148,8 @@ MBK_HD void deblock_one_mb(const EncFrameParams& p, const EncFramePtrs& f, int m
       if (edge == 0 && !have_nb) continue;
       const MbInfo* other = edge == 0 ? nbm : cur;
       int bs[4];
-      edge_bs(cur, other, dir, edge, bs, p.dec_mode != 0, lb[0], edge == 0 ? lb[1 + dir] : lb[0]);
+      if constexpr (BSL) edge_bs<true>(cur, other, dir, edge, bs, p.dec_mode != 0, lb[0], edge == 0 ? lb[1 + dir] : lb[0]);
+      else edge_bs<false>(cur, other, dir, edge, bs, p.dec_mode != 0);
       if ((bs[0] | bs[1] | bs[2] | bs[3]) == 0) continue;
       const int qp_y = edge == 0 ? (cur->qp + other->qp + 1) >> 1 : cur->qp;
       const int qp_c = edge == 0 ? (cur->qp_c + other->qp_c + 1) >> 1 : cur->qp_c;
@@ -195,5 +202,7 @@ MBK_HD void deblock_one_mb(const EncFrameParams& p, const EncFramePtrs& f, int m
   }
   warp_sync();
 }
+MBK_HD void deblock_one_mb(const EncFrameParams& p, const EncFramePtrs& f, int mbx, int mby, DbkTile& t) { deblock_one_mb_t<false>(p, f, mbx, mby, t); }
+MBK_HD void deblock_one_mb_b(const EncFrameParams& p, const EncFramePtrs& f, int mbx, int mby, DbkTileB& t) { deblock_one_mb_t<true>(p, f, mbx, mby, t); }
 
 }  // namespace mbk

@@ -8,6 +8,7 @@
 // predictors, intra neighbours, skip context (SURVEY.md §7 hard part 1); bit-exactness forbids breaking
 // that chain, so parallelism comes from rows (2-MB lag) x independent streams of the batch.
 #include <cuda.h>
+#include <type_traits>
 #include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
@@ -465,11 +466,12 @@ __global__ void __launch_bounds__(kEncThreads, ENC_MIN_CTAS) k_encode_mbs(const 
 // Net 78.8 against 59.5 ms per step (gpurun_out/rv -> profiles/r02_bench_lines.txt): off by default.
 #define DBK_WPC 8
 #define DBK_CO_WPC 4
-template <int WPC, int MIN_CTAS>
+template <int WPC, int MIN_CTAS, bool BSL = false /* decoder: the pictures may hold B macroblocks (two reference lists in the strength rule) */>
 __global__ void __launch_bounds__(32 * WPC, MIN_CTAS) k_deblock_rows(const StreamFrame* __restrict__ sf, int n_streams, int* prog, int* counter,
                                                                       const int* enc_prog /* NULL: every macroblock is coded already */,
                                                                       const int* enc_started /* resident form only, see below */) {
-  __shared__ DbkTile tiles[WPC];
+  using Tile = typename std::conditional<BSL, DbkTileB, DbkTile>::type;
+  __shared__ Tile tiles[WPC];
   // The resident form waits for a kernel that runs AT THE SAME TIME.  Where kernels are serialised (compute-sanitizer, ncu replay,
   // a debugger) that kernel cannot start while this one spins: a CTA that does not see the encode kernel running within ~0.3 ms leaves
   // without claiming a row, and the full-size grid launched behind the encode kernel does all the work.
@@ -486,7 +488,7 @@ __global__ void __launch_bounds__(32 * WPC, MIN_CTAS) k_deblock_rows(const Strea
     __syncthreads();
     if (!s_go) return;
   }
-  DbkTile& t = tiles[threadIdx.x >> 5];
+  Tile& t = tiles[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int mb_w = sf[0].p.mb_w, mb_h = sf[0].p.mb_h, units = n_streams * mb_h;
   for (;;) {
@@ -511,7 +513,7 @@ __global__ void __launch_bounds__(32 * WPC, MIN_CTAS) k_deblock_rows(const Strea
         seen_enc = __shfl_sync(MBK_FULL, seen_enc, 0);
         __threadfence();
       }
-      deblock_one_mb(F.p, F.f, x, row, t);
+      deblock_one_mb_t<BSL>(F.p, F.f, x, row, t);
       __threadfence();
       __syncwarp();
       if (lane == 0) *reinterpret_cast<volatile int*>(mine) = x + 1;
@@ -636,7 +638,8 @@ static EncSched make_esched(int* ws, int total, void* stash) {
 }
 
 // prog: n_streams * mb_h progress counters, zero; counter: the row hand-out counter (zeroed by the caller)
-static int launch_deblock_rows(const StreamFrame* d_sf, int n_streams, int mb_h, int* prog, int* counter, const int* enc_prog, cudaStream_t st) {
+static int launch_deblock_rows(const StreamFrame* d_sf, int n_streams, int mb_h, int* prog, int* counter, const int* enc_prog, cudaStream_t st,
+                               bool b_slices = false) {
   static int per_dev[64];
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -650,7 +653,8 @@ static int launch_deblock_rows(const StreamFrame* d_sf, int n_streams, int mb_h,
   const int units = n_streams * mb_h;
   int blocks = per_dev[dev];
   if (blocks > (units + DBK_WPC - 1) / DBK_WPC) blocks = (units + DBK_WPC - 1) / DBK_WPC;
-  k_deblock_rows<DBK_WPC, 6><<<blocks, 32 * DBK_WPC, 0, st>>>(d_sf, n_streams, prog, counter, enc_prog, nullptr);
+  if (b_slices) k_deblock_rows<DBK_WPC, 6, true><<<blocks, 32 * DBK_WPC, 0, st>>>(d_sf, n_streams, prog, counter, enc_prog, nullptr);
+  else k_deblock_rows<DBK_WPC, 6><<<blocks, 32 * DBK_WPC, 0, st>>>(d_sf, n_streams, prog, counter, enc_prog, nullptr);
   return b2h264_launched();
 }
 // the resident companion of the encode kernel: one small CTA per SM
@@ -759,7 +763,7 @@ static Sched make_dec_sched(int* ws, int which, int total) {
   return q;
 }
 int dec_launch_frame(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h, int* d_ws, const MbOut* d_recs, const DecMbAux* d_aux, int deblock,
-                     cudaStream_t st) {
+                     cudaStream_t st, int b_slices) {
   const int blocks_per_launch = dec_grid_blocks();
   int rc;
   const int total = n_streams * mb_w * mb_h;
@@ -773,7 +777,7 @@ int dec_launch_frame(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h,
   if ((rc = b2h264_launched())) return rc;
   if (deblock) {
     cudaMemsetAsync(d_ws + 2, 0, sizeof(int), st);
-    if ((rc = launch_deblock_rows(d_sf, n_streams, mb_h, d_ws + 8 + (size_t)total, d_ws + 2, nullptr, st))) return rc;
+    if ((rc = launch_deblock_rows(d_sf, n_streams, mb_h, d_ws + 8 + (size_t)total, d_ws + 2, nullptr, st, b_slices != 0))) return rc;
   }
   k_expand_lr_batch<<<dim3((mb_h * 16 + 7) / 8, 1, 3 * n_streams), dim3(32, 8), 0, st>>>(d_sf);
   if ((rc = b2h264_launched())) return rc;

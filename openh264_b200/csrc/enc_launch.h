@@ -28,7 +28,7 @@ size_t enc_scratch_bytes();
 // decoder construct path: reconstruct + deblock (if `deblock`) + expand one picture per stream from parsed records
 size_t dec_sched_ints(int n_streams, int n_mb);
 int dec_launch_frame(const StreamFrame* d_sf, int n_streams, int mb_w, int mb_h, int* d_ws, const MbOut* d_recs, const DecMbAux* d_aux, int deblock,
-                     cudaStream_t st);
+                     cudaStream_t st, int b_slices /* some picture of the batch holds B slices */);
 // compacts the records of the picture just coded into (mapped pinned) `pack`; idx / cnt likewise host-visible
 int dec_launch_unpack(const void* d_pack, size_t stream_stride_bytes, const int32_t* d_idx, MbOut* d_recs, int n_streams, int n_mb, cudaStream_t st);
 int enc_launch_pack(const StreamFrame* d_sf, int n_streams, int n_mb, MbOut* pack, int32_t* idx, int32_t* cnt, cudaStream_t st);

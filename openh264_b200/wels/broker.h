@@ -90,6 +90,8 @@ class DecPool {
   // synchronous: decodes the access unit as the next unit of `slot`.  Returns the stream's status: 1 picture (in picture(slot)),
   // 0 no picture, < 0 the layer-2 error of this stream / the call
   int decode(int slot, const uint8_t* au, int32_t bytes);
+  // of the picture `slot` decoded last (b2h264_dec_last_picture_order); only the slot's owner calls this, between its decode calls
+  void picture_order(int slot, int32_t* poc, int32_t* flags, int32_t* depth) { b2h264_dec_last_picture_order(dec_, slot, poc, flags, depth); }
 
  private:
   enum State { FREE, IDLE, PENDING, INFLIGHT, DONE };

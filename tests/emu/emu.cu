@@ -191,7 +191,11 @@ void expand_frame_host(const EncFrameParams& p, const EncFramePtrs& f) {
 }
 void deblock_frame_host(const EncFrameParams& p, const EncFramePtrs& f) {
   for (int mby = 0; mby < p.mb_h; mby++)
-    for (int mbx = 0; mbx < p.mb_w; mbx++) { static DbkTile tile; deblock_one_mb(p, f, mbx, mby, tile); }
+    for (int mbx = 0; mbx < p.mb_w; mbx++) {
+      static DbkTileB tile;
+      if (f.dec_aux_b) deblock_one_mb_b(p, f, mbx, mby, tile);     // a decoded picture with B slices
+      else deblock_one_mb(p, f, mbx, mby, tile);
+    }
 }
 
 }  // namespace

@@ -232,3 +232,27 @@ def test_host_decoder_on_committed_conformance_streams(emu, name, sha):
     n = emu.emu_decode(a.ctypes.data, len(a), out.ctypes.data, out.size, C.byref(W), C.byref(H))
     assert n > 0, n
     assert hashlib.sha1(out[:n * W.value * H.value * 3 // 2].tobytes()).hexdigest() == sha
+
+
+CONF_B_DIR = os.path.join(ROOT, "tests", "golden", "conformance_b")
+
+
+def conformance_b_fixtures():
+    import json
+    tab = dict((p.split("/")[-1], s) for p, s in json.load(open(os.path.join(ROOT, "tests", "golden", "reference_decoder_hashes.json")))["pairs"])
+    return sorted((f, tab[f]) for f in os.listdir(CONF_B_DIR) if f in tab)
+
+
+@pytest.mark.parametrize("name,sha", conformance_b_fixtures())
+def test_host_decoder_on_committed_b_slice_streams(emu, name, sha):
+    """the reference's B-frame vectors (test/api/decoder_test.cpp; committed under tests/golden/conformance_b): Main profile, CAVLC and
+    CABAC, B slices with spatial direct prediction, one- and two-list partitions, B_8x8, B_Skip; the pictures leave in POC order
+    (the B pictures of these streams PRECEDE the IDR picture they follow in the stream) — the PUBLISHED SHA-1 of the output"""
+    import hashlib
+    a = np.fromfile(os.path.join(CONF_B_DIR, name), dtype=np.uint8)
+    out = np.zeros(64 << 20, np.uint8)
+    W, H = C.c_int(), C.c_int()
+    emu.emu_decode.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    n = emu.emu_decode(a.ctypes.data, len(a), out.ctypes.data, out.size, C.byref(W), C.byref(H))
+    assert n == 9, n
+    assert hashlib.sha1(out[:n * W.value * H.value * 3 // 2].tobytes()).hexdigest() == sha

@@ -1,6 +1,6 @@
 // h264_parse.h — host-side bitstream PARSER: the inverse of h264_bitstream.{h,cpp} for the stream class this
-// library decodes: Baseline / Main / High without the 8x8 transform, CAVLC or CABAC, I and P slices (several per picture, in raster order: no FMO / ASO), one reference
-// frame, all partition shapes down to 4x4, non-reference pictures, constrained intra prediction, per-slice deblocking control.  Groundwork for the decoder construct path (SURVEY.md section 8f / DESIGN.md section 9): the
+// library decodes: Baseline / Main / High without the 8x8 transform, CAVLC or CABAC, I, P and B slices (several per picture, in raster order: no FMO / ASO),
+// up to 16 reference frames, all partition shapes down to 4x4, direct prediction and implicit weights in B slices (h264_motion.h), non-reference pictures, constrained intra prediction, per-slice deblocking control.  Groundwork for the decoder construct path (SURVEY.md section 8f / DESIGN.md section 9): the
 // reference parses on the host too (codec/decoder/core/src/{au_parser,parse_mb_syn_cavlc,decode_slice}.cpp) and
 // hands macroblock arrays to the pixel stage; here the macroblock array is the same MbOut record the encoder's
 // entropy coder consumes, so "parse(write(x)) == x" is checked for every picture the host build encodes
@@ -21,7 +21,7 @@ enum ParseError {
   PARSE_OK = 0,
   PARSE_NO_PICTURE = 1,        // the access unit was parsed (parameter sets taken) but holds no slice
   PARSE_TRUNCATED = -1,        // ran out of bits
-  PARSE_UNSUPPORTED = -2,      // valid H.264 outside the supported class (B slices, FMO, 8x8 transform, interlace, ...)
+  PARSE_UNSUPPORTED = -2,      // valid H.264 outside the supported class (FMO, 8x8 transform, explicit weights, interlace, ...)
   PARSE_INVALID = -3,          // not valid H.264 syntax / values out of range
   PARSE_NO_PARAMETER_SETS = -4,// a slice before its SPS / PPS
   PARSE_INCOMPLETE = -5        // the slices seen so far do not cover the picture (more slices of the access unit to come, or lost)

@@ -196,6 +196,7 @@ static int dec_decode_impl(b2h264_dec* d, const uint8_t* const* au, const int32_
     memset(&F, 0, sizeof(F));
     F.p.mb_w = d->mb_w; F.p.mb_h = d->mb_h;
     F.p.rec_stride_y = d->geo.rec_stride_y(); F.p.rec_stride_c = d->geo.rec_stride_c();
+    F.p.dec_cqp_off = pic.chroma_qp_offset;
     F.p.qp = pic.ss.qp; F.p.is_idr = pic.ss.idr; F.p.ref_is_p = !pic.ss.idr; F.p.mv_range = 64; F.p.dec_mode = 1;
     if (pic.cur_slot >= d->slots) STREAM_FAIL(-103)
     for (int pl = 0; pl < 3; pl++) { F.f.rec[pl] = d->plane0(pic.cur_slot, s, pl); F.f.ref[pl] = F.f.dpb0[pl] = d->plane0(0, s, pl); }
@@ -233,7 +234,7 @@ static int dec_decode_impl(b2h264_dec* d, const uint8_t* const* au, const int32_
       CK(cudaMemcpyAsync(d->d_aux_b + (size_t)i * d->n_mb, d->h_aux_b + (size_t)i * d->n_mb, (size_t)d->n_mb * sizeof(DecMbAuxB), cudaMemcpyHostToDevice, d->st));
   CK(cudaMemcpyAsync(d->d_sf, d->h_sf, (size_t)n * sizeof(StreamFrame), cudaMemcpyHostToDevice, d->st));
   int b_slices = 0;
-  for (int i = 0; i < n; i++) b_slices |= d->parsed[d->act[i]].has_b ? 1 : 0;
+  for (int i = 0; i < n; i++) b_slices |= (d->parsed[d->act[i]].has_b || d->parsed[d->act[i]].has_t8) ? 1 : 0;   // Main / High tools: the wider filter kernel
   const int rc = dec_launch_frame(d->d_sf, n, d->mb_w, d->mb_h, d->d_ws, d->d_recs, d->d_aux, deblock, d->st, b_slices);
   if (rc) return rc;
   const double t_launch = ms_since(t0);

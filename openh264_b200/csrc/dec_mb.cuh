@@ -10,6 +10,7 @@
 // Runs on the device as k_decode_mbs (enc_kernels.cu) and, compiled for the host, as the debugging build of tests/emu.
 #pragma once
 #include "enc_inter.cuh"
+#include "dec_t8x8.cuh"
 
 namespace mbk {
 
@@ -87,12 +88,28 @@ MBK_HD void dec_mc_part(const MbCtx& c, uint8_t* pl, uint8_t* pc, int slot, int 
 // reference slot of the 8x8 quadrant that holds 4x4 block `blk` (coding order)
 MBK_HD int dec_ref_of(const DecMbAux& aux, int blk) { return aux.ref_idx[blk >> 2]; }
 
+// luma of an inter macroblock with the 8x8 transform: lane k reconstructs 8x8 block k (prediction + inverse transform of its 64 levels)
+MBK_HD void rec_luma_inter8(MbScratch& s, const MbOut& m, int qp, const uint8_t* pl) {
+  for (int k = lane_id(); k < 4; k += MBK_WS) {
+    const int ox = (k & 1) * 8, oy = (k >> 1) * 8;
+    uint8_t* org = tile_y(s.tile, ox, oy);
+    if (m.cbp & (1 << k)) {
+      int16_t d[64];
+      unscan_dequant8x8(d, &m.luma[4 * k][0], qp);
+      idct8x8_rec(org, TY_PITCH, pl + oy * 16 + ox, 16, d);
+    } else {
+      for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) org[y * TY_PITCH + x] = pl[(oy + y) * 16 + ox + x];
+    }
+  }
+  warp_sync();
+}
+
 // One macroblock.  f.rec = picture being reconstructed, f.ref = reference picture (padded), f.mbi = MbInfo array of
 // the picture (neighbour lookups + what deblocking reads).  Raster / wavefront order like the encoder.
 MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch& s, int mbx, int mby, const MbOut& m, const DecMbAux& aux) {
   mb_ctx(s.ctx, p, f, mbx, mby);
   // neighbour availability comes from the parser: macroblocks of other slices do not count (6.4.x)
-  if (lane_id() == 0) { s.ctx.qp = m.qp; s.ctx.qp_c = tbl_chroma_qp(m.qp); s.ctx.nb = aux.avail; }
+  if (lane_id() == 0) { s.ctx.qp = m.qp; s.ctx.qp_c = tbl_chroma_qp(clip3(m.qp + p.dec_cqp_off, 0, 51)); s.ctx.nb = aux.avail; }
   warp_sync();
   const MbCtx& c = s.ctx;
   {
@@ -131,7 +148,7 @@ MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch
     warp_sync();
     mb_store_recon(c, s);
     if (lane_id() == 0) {
-      s.info.qp = 0; s.info.qp_c = (uint8_t)tbl_chroma_qp(0);
+      s.info.qp = 0; s.info.qp_c = (uint8_t)tbl_chroma_qp(clip3(p.dec_cqp_off, 0, 51));
       s.info.p16x16_mv[0] = (int16_t)aux.slice;
       s.info.p16x16_mv[1] = (int16_t)(aux.dbk_idc | ((aux.alpha_off + 16) << 2) | ((aux.beta_off + 16) << 7));
     }
@@ -191,8 +208,8 @@ MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch
         s.info.mv[b][0] = used ? aux.mvd[z][0] : 0; s.info.mv[b][1] = used ? aux.mvd[z][1] : 0;
       }
     warp_sync();
-    dec_luma_coef(s, m, qp, false, nullptr);
-    rec_luma_inter(s, pl);
+    if (aux.flags & DECAUX_T8) rec_luma_inter8(s, m, qp, pl);
+    else { dec_luma_coef(s, m, qp, false, nullptr); rec_luma_inter(s, pl); }
   } else if (type == MBT_P8x8 && (aux.flags & DECAUX_SUB)) {
     // sub-macroblock partitions (8x4, 4x8, 4x4): every partition predicts its vector from the cells decoded so far —
     // the in-macroblock cells start as "not available" and are filled in decoding order (8.4.1.3.2: a partition that
@@ -238,8 +255,8 @@ MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch
       dec_mc_part(c, pl, pc, ref, blk, w4, h4, mvx, mvy);
     }
     warp_sync();
-    dec_luma_coef(s, m, qp, false, nullptr);
-    rec_luma_inter(s, pl);
+    if (aux.flags & DECAUX_T8) rec_luma_inter8(s, m, qp, pl);
+    else { dec_luma_coef(s, m, qp, false, nullptr); rec_luma_inter(s, pl); }
   } else if (type == MBT_I16x16) {
     const int mode = m.i16_mode == 2 ? (L && T ? I16_DC : L ? I16_DC_L : T ? I16_DC_T : I16_DC_128) : m.i16_mode;
     pred_i16(pl, tile_y(s.tile, 0, 0), TY_PITCH, mode);
@@ -254,6 +271,43 @@ MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch
     }
     dec_luma_coef(s, m, qp, true, dcq);
     rec_luma_inter(s, pl);                       // inverse transform + prediction for all 16 blocks
+  } else if (aux.flags & DECAUX_T8) {            // Intra_8x8: four blocks, each predicts from what was just reconstructed
+    fill_i4_cache(c, s);                         // mode cache at 4x4 granularity: an Intra_8x8 block's mode stands in its four cells
+    if (aux.flags & DECAUX_CIP) {
+      if (lane_id() == 0) {
+        if ((c.nb & NB_LEFT) && MBT_IS_INTER(s.nbi[3].mb_type)) for (int y = 0; y < 4; y++) s.i4m[(y + 1) * 5] = -1;
+        if ((c.nb & NB_TOP) && MBT_IS_INTER(s.nbi[1].mb_type)) for (int x = 0; x < 4; x++) s.i4m[x + 1] = -1;
+      }
+      warp_sync();
+    }
+    if (lane_id() == 0) {
+      for (int k = 0; k < 4; k++) {
+        const int bx = (k & 1) * 2, by = (k >> 1) * 2;
+        uint8_t* org = tile_y(s.tile, bx * 4, by * 4);
+        const int lm = s.i4m[(by + 1) * 5 + bx], tm = s.i4m[by * 5 + bx + 1];
+        const int pm = (lm == -1 || tm == -1) ? 2 : (lm < tm ? lm : tm);
+        const int coded = m.prev_i4_flag[k] ? pm : (m.rem_i4_mode[k] < pm ? m.rem_i4_mode[k] : m.rem_i4_mode[k] + 1);
+        // neighbouring samples of the 8x8 block (6.4.11): left / top from the neighbouring macroblock or from inside, top-right of
+        // block 1 from the top-right macroblock, of block 2 from block 1, of block 3 never
+        const bool aL = (k & 1) ? true : (nb_i & NB_LEFT) != 0, aT = (k >> 1) ? true : (nb_i & NB_TOP) != 0;
+        const bool aTL = k == 0 ? (nb_i & NB_TOPLEFT) != 0 : k == 1 ? (nb_i & NB_TOP) != 0 : k == 2 ? (nb_i & NB_LEFT) != 0 : true;
+        const bool aTR = k == 0 ? (nb_i & NB_TOP) != 0 : k == 1 ? (nb_i & NB_TOPRIGHT) != 0 : k == 2;
+        for (int y = 0; y < 2; y++) for (int x = 0; x < 2; x++) {
+          s.i4m[(by + y + 1) * 5 + bx + x + 1] = (int8_t)coded;
+          s.info.i4_mode[(by + y) * 4 + bx + x] = (int8_t)coded;
+        }
+        uint8_t pr[64];
+        pred_i8x8(pr, org, TY_PITCH, coded, (aL ? 1 : 0) | (aT ? 2 : 0) | (aTL ? 4 : 0) | (aTR ? 8 : 0));
+        if (m.cbp & (1 << k)) {
+          int16_t d[64];
+          unscan_dequant8x8(d, &m.luma[4 * k][0], qp);
+          idct8x8_rec(org, TY_PITCH, pr, 8, d);
+        } else {
+          for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) org[y * TY_PITCH + x] = pr[8 * y + x];
+        }
+      }
+    }
+    warp_sync();
   } else {                                       // I4x4: block by block, each predicts from what was just reconstructed
     fill_i4_cache(c, s);
     if (aux.flags & DECAUX_CIP) {              // 8.3.1.1: an Inter neighbour under constrained_intra_pred forces the DC prediction of the
@@ -301,6 +355,14 @@ MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch
   // what the neighbours and the deblocking filter read
   if (lane_id() == 0) {
     s.info.qp = (uint8_t)qp; s.info.qp_c = (uint8_t)qp_c;
+    if (aux.flags & DECAUX_T8) {                // the filter asks whether the 8x8 TRANSFORM block holds coefficients (8.7.2.1)
+      s.info.t8x8 = 1;
+      for (int k = 0; k < 4; k++) {
+        const int b0 = (k >> 1) * 8 + (k & 1) * 2;
+        const int tot = s.info.nnz[b0] + s.info.nnz[b0 + 1] + s.info.nnz[b0 + 4] + s.info.nnz[b0 + 5];
+        s.info.nnz[b0] = s.info.nnz[b0 + 1] = s.info.nnz[b0 + 4] = s.info.nnz[b0 + 5] = (int8_t)(tot > 64 ? 64 : tot);
+      }
+    }
     if (MBT_IS_INTER(type))                     // reference picture slot of every 4x4 block (raster): MV prediction of the neighbours, bS
       for (int b = 0; b < 16; b++) s.info.i4_mode[b] = aux.ref_idx[(b >> 3) * 2 + ((b >> 1) & 1)];
     // the decoder has no use for sP16x16Mv: the field carries what the deblocking pass needs to know about the slice

@@ -90,7 +90,7 @@ MBK_HD uint32_t dbk_ld32(const uint8_t* p) {
 #endif
 }
 
-// BSL: the picture may hold B macroblocks (decoder only).  The encoder and B-free decoder pictures run the BSL = false instantiation,
+// BSL: the picture may hold B macroblocks or macroblocks with the 8x8 transform (decoder only: Main / High tools).  The encoder and B-free decoder pictures run the BSL = false instantiation,
 // whose code and shared-memory footprint are those of the single-list filter.
 template <bool BSL, typename Tile>
 MBK_HD void deblock_one_mb_t(const EncFrameParams& p, const EncFramePtrs& f, int mbx, int mby, Tile& t) {
@@ -146,6 +146,7 @@ MBK_HD void deblock_one_mb_t(const EncFrameParams& p, const EncFramePtrs& f, int
     const MbInfo* nbm = dir == 0 ? &t.m[1] : &t.m[2];
     for (int edge = 0; edge < 4; edge++) {
       if (edge == 0 && !have_nb) continue;
+      if constexpr (BSL) if (cur->t8x8 && (edge & 1)) continue;      // 8x8 transform: the inner 4x4 edges are no transform edges (chroma has none there)
       const MbInfo* other = edge == 0 ? nbm : cur;
       int bs[4];
       if constexpr (BSL) edge_bs<true>(cur, other, dir, edge, bs, p.dec_mode != 0, lb[0], edge == 0 ? lb[1 + dir] : lb[0]);

@@ -29,7 +29,8 @@ typedef struct {
   uint8_t cbp;
   uint8_t qp, qp_c;
   int8_t  ref_idx;          // 0 for inter, -2 for intra (REF_NOT_IN_LIST)
-  uint8_t pad[3];
+  uint8_t t8x8;             // decoder: transform_size_8x8_flag (the filter leaves the inner 4x4 edges of such a macroblock alone)
+  uint8_t pad[2];
 } MbInfo;                   // 64+24+16+4+4+8 = 120 bytes
 
 // Per-macroblock info a coded picture carries for the NEXT frame's decisions
@@ -83,6 +84,8 @@ typedef struct {
 } DecMbAuxB;                              // 80 bytes
 #define DECAUX_SUB 1
 #define DECAUX_CIP 2
+#define DECAUX_T8 4                       /* transform_size_8x8_flag: the luma levels are four 8x8 blocks (MbOut::luma[4k .. 4k+3] = 64 levels in
+                                             8x8 zig-zag order); an MBT_I4x4 record with this flag is an Intra_8x8 macroblock (prev / rem flags [0..3]) */
 
 #define MBOUT_HEADER_WORDS 20             /* mb_type .. nnz: all a P_SKIP macroblock needs to hand over */
 
@@ -99,6 +102,7 @@ typedef struct {
   int32_t fast_mode;                      // iComplexityMode == LOW_COMPLEXITY: SAD mode costs, VAA-driven partition choice
                                           // (SetFastCodingFunc / WelsMdInterFinePartitionVaa, encoder_ext.cpp:2616,2688)
   int32_t dbk_idc, dbk_off_a, dbk_off_b;  // encoder: disable_deblocking_filter_idc (0 / 1), FilterOffsetA / B (2 x the slice header's div2 values)
+  int32_t dec_cqp_off;                    // decoder: chroma_qp_index_offset of the picture's PPS (both chroma planes)
 } EncFrameParams;
 
 typedef struct {

@@ -166,6 +166,45 @@ class CabacDecoder {
     if (decision(62)) for (v = 2; decision(63); v++) if (v > 104) { overrun_ = true; return 0; }
     return (v & 1) ? (v + 1) / 2 : -(v / 2);
   }
+  // residual_block_cabac of an 8x8 luma block (ctxBlockCat 5: no coded_block_flag in 4:2:0; frame-coded context maps of Table 9-43):
+  // fills lv[0..64) in 8x8 zig-zag order, returns the number of non-zero levels or -1
+  int residual_levels8x8(int16_t* lv) {
+    static const uint8_t kSig[63] = {0, 1, 2, 3, 4, 5, 5, 4, 4, 3, 3, 4, 4, 4, 5, 5, 4, 4, 4, 4, 3, 3, 6, 7, 7, 7, 8, 9, 10, 9, 8, 7,
+                                     7, 6, 11, 12, 13, 11, 6, 7, 8, 9, 14, 10, 9, 8, 6, 11, 12, 13, 11, 6, 9, 14, 10, 9, 11, 12, 13, 11, 14, 10, 12};
+    static const uint8_t kLast[63] = {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2,
+                                      3, 3, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 6, 6, 6, 6, 7, 7, 7, 7, 8, 8, 8};
+    for (int i = 0; i < 64; i++) lv[i] = 0;
+    int sig_pos[64], n = 0, i = 0;
+    for (; i < 63; i++) {
+      if (decision(402 + kSig[i])) {
+        sig_pos[n++] = i;
+        if (decision(417 + kLast[i])) break;
+      }
+    }
+    if (i == 63) sig_pos[n++] = 63;
+    int eq1 = 0, gt1 = 0;
+    const int base = 426;
+    for (int k = n - 1; k >= 0; k--) {
+      int a = 0;
+      if (decision(base + (gt1 ? 0 : (1 + eq1 < 4 ? 1 + eq1 : 4)))) {
+        const int ctx = base + 5 + (gt1 < 4 ? gt1 : 4);
+        a = 1;
+        while (a < 14 && decision(ctx)) a++;
+        if (a == 14) {
+          const int64_t s = exp_golomb_bypass(0);
+          if (s < 0 || s > 1 << 16) { overrun_ = true; return -1; }
+          a += (int)s;
+        }
+        gt1++;
+      } else {
+        eq1++;
+      }
+      const int v = a + 1;
+      if (v > 32767) { overrun_ = true; return -1; }
+      lv[sig_pos[k]] = (int16_t)(bypass() ? -v : v);
+    }
+    return n;
+  }
   // residual_block_cabac without the coded_block_flag (7.3.5.3.3): fills lv[0..max_coef) (scan order), returns the number of
   // non-zero levels or -1
   int residual_levels(int cat, int16_t* lv, int max_coef) {

@@ -21,6 +21,13 @@ enum { MREF_NA = -2, MREF_NONE = -1 };           // cell outside the slice / not
 // one entry of a slice's reference picture list
 struct RefEntry { int slot = -1, key = -0x40000000, poc = 0, pic_id = -1; bool lt = false; };
 
+// explicit weights of a slice (pred_weight_table): [list][ref_idx][plane Y / Cb / Cr][weight, offset]
+struct WpTable {
+  bool on = false;
+  int log2[2] = {0, 0};                          // luma, chroma denominators
+  int16_t w[2][32][3][2];
+};
+
 // what a B slice adds to the slice state
 struct BSliceCtx {
   bool direct_spatial = true;

@@ -186,6 +186,7 @@ void activate_pps(ParserState* st, int id) {
   st->constrained_intra_pred = f.constrained_intra_pred;
   st->entropy_cabac = f.entropy_cabac;
   st->num_ref_idx_l1_default = f.num_ref_idx_l1_default; st->weighted_bipred_idc = f.weighted_bipred_idc;
+  st->chroma_qp_offset = f.chroma_qp_offset; st->transform_8x8 = f.transform_8x8; st->weighted_pred = f.weighted_pred;
   st->sp.pps_id = id;
   st->have_pps = true;
 }
@@ -201,21 +202,22 @@ int parse_pps(BitReader& r, ParserState* st) {
   if (r.ue() != 0) return PARSE_UNSUPPORTED;  // slice groups
   f.num_ref_idx_default = (int)r.ue() + 1;
   f.num_ref_idx_l1_default = (int)r.ue() + 1;
-  if (r.bit()) return PARSE_UNSUPPORTED;      // weighted_pred_flag
-  f.weighted_bipred_idc = (int)r.get(2);
-  if (f.weighted_bipred_idc == 1 || f.weighted_bipred_idc == 3) return PARSE_UNSUPPORTED;   // explicit weights in B slices
+  f.weighted_pred = r.bit() != 0;             // weighted_pred_flag: explicit weights in P slices
+  f.weighted_bipred_idc = (int)r.get(2);      // 1: explicit weights in B slices, 2: implicit
+  if (f.weighted_bipred_idc == 3) return PARSE_INVALID;
   f.pic_init_qp = 26 + r.se();
   r.se();
-  if (r.se() != 0) return PARSE_UNSUPPORTED;  // chroma_qp_index_offset
+  f.chroma_qp_offset = r.se();                // chroma_qp_index_offset
+  if (f.chroma_qp_offset < -12 || f.chroma_qp_offset > 12) return PARSE_INVALID;
   f.deblocking_control = r.bit() != 0;
   f.constrained_intra_pred = r.bit() != 0;
   if (r.bit()) return PARSE_UNSUPPORTED;      // redundant_pic_cnt_present_flag
   if (bottom_field_poc) return PARSE_UNSUPPORTED;
   if (!r.ok()) return PARSE_TRUNCATED;
   if (r.more_data()) {                        // High profile tail (7.3.2.2)
-    if (r.bit()) return PARSE_UNSUPPORTED;    // transform_8x8_mode_flag
+    f.transform_8x8 = r.bit() != 0;           // transform_8x8_mode_flag
     if (r.bit()) return PARSE_UNSUPPORTED;    // pic_scaling_matrix_present_flag
-    if (r.se() != 0) return PARSE_UNSUPPORTED;// second_chroma_qp_index_offset
+    if (r.se() != f.chroma_qp_offset) return PARSE_UNSUPPORTED;   // second_chroma_qp_index_offset: one offset for both chroma planes
     if (!r.ok()) return PARSE_TRUNCATED;
   }
   f.valid = true;
@@ -515,6 +517,31 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     for (int i = 0; i < 32; i++) list0[i] = lists[0][i].slot;
     for (int i = 0; i < n_ref; i++) if (list0[i] < 0 && is_p) return PARSE_INVALID;
   }
+  // pred_weight_table (7.3.3.2): explicit weights of a P slice (weighted_pred_flag) or a B slice (weighted_bipred_idc 1)
+  WpTable wp;
+  if ((is_p && st->weighted_pred) || (is_b && st->weighted_bipred_idc == 1)) {
+    wp.on = true;
+    const uint32_t dl = r.ue(), dc = r.ue();
+    if (dl > 7 || dc > 7) return PARSE_INVALID;
+    wp.log2[0] = (int)dl; wp.log2[1] = (int)dc;
+    for (int l = 0; l < (is_b ? 2 : 1); l++)
+      for (int i = 0; i < (l ? n_ref1 : n_ref); i++) {
+        for (int pl = 0; pl < 3; pl++) { wp.w[l][i][pl][0] = (int16_t)(1 << wp.log2[pl ? 1 : 0]); wp.w[l][i][pl][1] = 0; }
+        if (r.bit()) {
+          const int w = r.se(), o = r.se();
+          if (w < -128 || w > 127 || o < -128 || o > 127) return PARSE_INVALID;
+          wp.w[l][i][0][0] = (int16_t)w; wp.w[l][i][0][1] = (int16_t)o;
+        }
+        if (r.bit())
+          for (int pl = 1; pl < 3; pl++) {
+            const int w = r.se(), o = r.se();
+            if (w < -128 || w > 127 || o < -128 || o > 127) return PARSE_INVALID;
+            wp.w[l][i][pl][0] = (int16_t)w; wp.w[l][i][pl][1] = (int16_t)o;
+          }
+      }
+    if (!r.ok()) return PARSE_TRUNCATED;
+    return PARSE_UNSUPPORTED;                                 // WP_TODO: explicit weights are parsed but not yet applied
+  }
   const bool is_ref = nal.ref_idc != 0;                       // a non-reference picture is output but never predicted from
   bool adaptive = false, idr_lt = false;
   std::vector<ParsedPicture::Mmco> mmco;
@@ -580,6 +607,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     pic->pic_id = st->next_pic_id++;
     pic->max_reorder = st->profile == 66 ? 0 : st->sp.num_ref_frames;
     pic->has_b = false;
+    pic->has_t8 = st->transform_8x8; pic->chroma_qp_offset = st->chroma_qp_offset;
     if (st->profile != 66) {                                  // the stream may hold B slices: keep the motion field of every picture
       if ((int)st->motion.size() < st->n_slots) st->motion.resize(st->n_slots);
       MotionStore& ms = st->motion[pic->cur_slot];
@@ -686,6 +714,8 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
         }
         me.intra = intra ? 1 : 0;
         int cbp = -1;
+        bool no_sub8 = true;                                  // no sub-macroblock partition smaller than 8x8 (7.3.5: gate of transform_size_8x8_flag)
+        auto read_t8 = [&]() { return d.decision(399 + (L && L->t8 ? 1 : 0) + (T && T->t8 ? 1 : 0)) != 0; };
         if (intra && t == 25) {                               // I_PCM: the arithmetic decoder stopped behind its flush; raw bytes follow
           m.mb_type = MBT_IPCM;
           size_t bp = (d.pos() + 7) & ~(size_t)7;             // pcm_alignment_zero_bit
@@ -707,7 +737,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
             memset(sx.ref, 0, sizeof(sx.ref)); memset(sx.mvd, 0, sizeof(sx.mvd));
             sx.type = t;
             if (t == 0) me.direct = 1;
-            if (t == 22) for (int k = 0; k < 4; k++) sx.sub[k] = d.sub_mb_type_b();
+            if (t == 22) for (int k = 0; k < 4; k++) { sx.sub[k] = d.sub_mb_type_b(); if (sx.sub[k] != 0 && b_sub_shape(sx.sub[k]) != 0) no_sub8 = false; }
             BUnit ru[4], mu[16];
             const int nru = b_ref_units(sx, ru), nmu = b_mvd_units(sx, mu);
             for (int l = 0; l < 2; l++) {
@@ -760,7 +790,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
               m.mb_type = MBT_P8x8;
               bool sub = false;
               for (int k = 0; k < 4; k++) { ax.sub_type[k] = (uint8_t)d.sub_mb_type_p(); sub = sub || ax.sub_type[k] != 0; }
-              if (sub) ax.flags |= DECAUX_SUB;
+              if (sub) { ax.flags |= DECAUX_SUB; no_sub8 = false; }
               for (int k = 0; k < 4; k++) {
                 const int b0 = (k & 1) * 2 + (k >> 1) * 8;
                 switch (ax.sub_type[k]) {
@@ -820,7 +850,9 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
           } else {
             if (t == 0) {
               m.mb_type = MBT_I4x4;
-              for (int k = 0; k < 16; k++) {
+              const bool t8i = st->transform_8x8 && read_t8();          // Intra_8x8: four prediction modes instead of sixteen
+              if (t8i) { ax.flags |= DECAUX_T8; me.t8 = 1; }
+              for (int k = 0; k < (t8i ? 4 : 16); k++) {
                 m.prev_i4_flag[k] = (int8_t)d.decision(68);
                 if (!m.prev_i4_flag[k]) { int v = d.decision(69); v |= d.decision(69) << 1; v |= d.decision(69) << 2; m.rem_i4_mode[k] = (int8_t)v; }
               }
@@ -853,6 +885,8 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
           }
           m.cbp = (uint8_t)cbp; me.cbp = (uint8_t)cbp;
           const int cbp_l = cbp & 15, cbp_c = cbp >> 4;
+          if (!intra && cbp_l > 0 && st->transform_8x8 && no_sub8 && read_t8()) { ax.flags |= DECAUX_T8; me.t8 = 1; }
+          const bool t8 = (ax.flags & DECAUX_T8) != 0;
           if (cbp > 0 || m.mb_type == MBT_I16x16) {
             const int dqp = d.mb_qp_delta(prev_dqp_nonzero ? 1 : 0);
             if (dqp < -26 || dqp > 25) return PARSE_INVALID;
@@ -870,7 +904,17 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
               me.cbf |= 1u << 24;
             }
             const int lcat = m.mb_type == MBT_I16x16 ? 1 : 2;
-            for (int k = 0; k < 16; k++) {
+            if (t8) {                                         // four 8x8 blocks (ctxBlockCat 5: no coded_block_flag, the pattern bit decides)
+              for (int q = 0; q < 4; q++) {
+                if (!(cbp_l & (1 << q))) continue;
+                const int cnt = d.residual_levels8x8(&m.luma[4 * q][0]);
+                if (cnt < 0) return PARSE_INVALID;
+                const int b0 = (q >> 1) * 8 + (q & 1) * 2;
+                m.nnz[b0] = m.nnz[b0 + 1] = m.nnz[b0 + 4] = m.nnz[b0 + 5] = (int8_t)(cnt > 16 ? 16 : cnt);
+                me.cbf |= (1u << b0) | (1u << (b0 + 1)) | (1u << (b0 + 4)) | (1u << (b0 + 5));
+              }
+            }
+            for (int k = 0; k < 16 && !t8; k++) {
               if (!(cbp_l & (1 << (k >> 2)))) continue;
               const int bx = (k & 1) | ((k >> 1) & 2), by = ((k >> 1) & 1) | ((k >> 2) & 2);
               if (!d.decision(85 + kCbfOff[lcat] + luma_inc(bx, by))) continue;
@@ -959,6 +1003,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     }
     int cbp = -1;
     int cur_ri[4] = {0, 0, 0, 0};
+    bool no_sub8 = true;
     if (!intra && is_b) {
       // B macroblock: the syntax is collected (mb_pred / sub_mb_pred of B slices), then resolved on the host (h264_motion.h)
       m.mb_type = MBT_B;
@@ -966,7 +1011,12 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
       memset(sx.ref, 0, sizeof(sx.ref)); memset(sx.mvd, 0, sizeof(sx.mvd));
       sx.type = t;
       if (t == 22)
-        for (int k = 0; k < 4; k++) { const uint32_t v = r.ue(); if (v > 12) return PARSE_INVALID; sx.sub[k] = (int)v; }
+        for (int k = 0; k < 4; k++) {
+          const uint32_t v = r.ue();
+          if (v > 12) return PARSE_INVALID;
+          sx.sub[k] = (int)v;
+          if (v != 0 && b_sub_shape((int)v) != 0) no_sub8 = false;
+        }
       BUnit ru[4], mu[16];
       const int nru = b_ref_units(sx, ru), nmu = b_mvd_units(sx, mu);
       for (int l = 0; l < 2; l++) {
@@ -1015,7 +1065,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
         static const int kParts[4] = {1, 2, 2, 4};
         for (int k = 0; k < 4; k++)
           for (int j = 0; j < kParts[ax.sub_type[k]]; j++) { ax.mvd[4 * k + j][0] = (int16_t)r.se(); ax.mvd[4 * k + j][1] = (int16_t)r.se(); }
-        if (sub) ax.flags |= DECAUX_SUB;
+        if (sub) { ax.flags |= DECAUX_SUB; no_sub8 = false; }
         else for (int k = 0; k < 4; k++) { m.mvd[k][0] = ax.mvd[4 * k][0]; m.mvd[k][1] = ax.mvd[4 * k][1]; }
       } else return PARSE_INVALID;
       for (int k = 0; k < 4; k++) {
@@ -1026,7 +1076,9 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     } else {
       if (t == 0) {
         m.mb_type = MBT_I4x4;
-        for (int k = 0; k < 16; k++) { m.prev_i4_flag[k] = (int8_t)r.bit(); m.rem_i4_mode[k] = m.prev_i4_flag[k] ? 0 : (int8_t)r.get(3); }
+        const bool t8i = st->transform_8x8 && r.bit();        // transform_size_8x8_flag: Intra_8x8, four prediction modes
+        if (t8i) ax.flags |= DECAUX_T8;
+        for (int k = 0; k < (t8i ? 4 : 16); k++) { m.prev_i4_flag[k] = (int8_t)r.bit(); m.rem_i4_mode[k] = m.prev_i4_flag[k] ? 0 : (int8_t)r.get(3); }
         m.chroma_mode = (uint8_t)r.ue();
       } else if (t <= 24) {
         m.mb_type = MBT_I16x16;
@@ -1066,6 +1118,8 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     }
     m.cbp = (uint8_t)cbp;
     const int cbp_l = cbp & 15, cbp_c = cbp >> 4;
+    if (!intra && cbp_l > 0 && st->transform_8x8 && no_sub8 && r.bit()) ax.flags |= DECAUX_T8;   // transform_size_8x8_flag
+    const bool t8 = (ax.flags & DECAUX_T8) != 0;
     if (cbp > 0 || m.mb_type == MBT_I16x16) {
       const int dqp = r.se();
       if (dqp < -26 || dqp > 25) return PARSE_INVALID;
@@ -1082,8 +1136,16 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
       for (int k = 0; k < 16; k++) {
         if (!(cbp_l & (1 << (k >> 2)))) continue;
         const int bx = (k & 1) | ((k >> 1) & 2), by = ((k >> 1) & 1) | ((k >> 2) & 2);
-        rc = read_block(r, m.luma[k], m.mb_type == MBT_I16x16 ? 15 : 16, luma_nc(bx, by));
-        if (rc < 0) return rc;
+        if (t8) {                                             // 8x8 block as four interleaved 4x4 blocks (7.3.5.3.2: level 4 * j + i of the 8x8)
+          int16_t tmp[16];
+          rc = read_block(r, tmp, 16, luma_nc(bx, by));
+          if (rc < 0) return rc;
+          int16_t* lv64 = &m.luma[k & ~3][0];
+          for (int j = 0; j < 16; j++) lv64[4 * j + (k & 3)] = tmp[j];
+        } else {
+          rc = read_block(r, m.luma[k], m.mb_type == MBT_I16x16 ? 15 : 16, luma_nc(bx, by));
+          if (rc < 0) return rc;
+        }
         m.nnz[by * 4 + bx] = (int8_t)rc;
       }
       if (cbp_c) {

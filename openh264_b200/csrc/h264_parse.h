@@ -40,6 +40,8 @@ struct PpsFields {
   bool valid = false;
   int sps_id = 0, pic_init_qp = 26, num_ref_idx_default = 1, num_ref_idx_l1_default = 1, weighted_bipred_idc = 0;
   bool deblocking_control = true, constrained_intra_pred = false, entropy_cabac = false;
+  int chroma_qp_offset = 0;            // chroma_qp_index_offset (= second_chroma_qp_index_offset, else the PPS is rejected)
+  bool transform_8x8 = false, weighted_pred = false;
 };
 
 // CABAC only: what later macroblocks of the slice need to know about a parsed macroblock (context selection, 9.3.3.1.1)
@@ -47,6 +49,8 @@ struct CabacMbInfo {
   uint8_t type, skip, intra, cbp, chroma_mode, ref_gt0;   // ref_gt0: bit q = ref_idx_l0 of 8x8 block q is > 0
   uint8_t ref_gt0_l1;               // the same for list 1 (B slices); direct-predicted blocks count as 0 in both (9.3.3.1.1.6)
   uint8_t direct;                   // B_Skip or B_Direct_16x16 (ctxIdxInc of mb_type in B slices)
+  uint8_t t8;                       // transform_size_8x8_flag (ctxIdxInc of the neighbours' flag)
+  uint8_t pad1[3];
   uint32_t cbf;                     // bit 0..15 luma 4x4 (raster), 16..19 Cb AC, 20..23 Cr AC, 24 luma DC, 25 Cb DC, 26 Cr DC
   uint8_t mvd[16][2];               // min(|mvd|, 255) per 4x4 block (raster); the context only distinguishes sums up to 33
   uint8_t mvd_l1[16][2];            // list 1 (B slices)
@@ -91,6 +95,8 @@ struct ParserState {
   int n_slots = 2;
   // B slices: picture order count (type 0, 8.2.1.1), motion fields by picture slot
   int profile = 66, weighted_bipred_idc = 0, num_ref_idx_l1_default = 1;
+  int chroma_qp_offset = 0;
+  bool transform_8x8 = false, weighted_pred = false;
   bool direct_8x8_inference = true;
   int prev_poc_msb = 0, prev_poc_lsb = 0;      // of the previous reference picture
   int next_pic_id = 0;
@@ -112,6 +118,8 @@ struct ParsedPicture {
   int pic_id = 0;                // decoding counter: identity of the picture in other pictures' motion fields
   int max_reorder = 0;           // pictures that may have to wait for an earlier-output picture (0: output order = decoding order)
   bool has_b = false;            // some slice is a B slice: aux_b is filled
+  bool has_t8 = false;           // the picture's PPS allows the 8x8 transform (the filter must look at MbInfo::t8x8)
+  int chroma_qp_offset = 0;      // chroma_qp_index_offset of the picture's PPS
   std::vector<DecMbAuxB> aux_b;  // list 1 of the B macroblocks (sized like aux when has_b)
   int cur_slot = 0;              // picture slot this picture is reconstructed into
   int n_slots = 2;               // slots the stream needs (from its SPS)

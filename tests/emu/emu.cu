@@ -193,7 +193,7 @@ void deblock_frame_host(const EncFrameParams& p, const EncFramePtrs& f) {
   for (int mby = 0; mby < p.mb_h; mby++)
     for (int mbx = 0; mbx < p.mb_w; mbx++) {
       static DbkTileB tile;
-      if (f.dec_aux_b) deblock_one_mb_b(p, f, mbx, mby, tile);     // a decoded picture with B slices
+      if (p.dec_mode) deblock_one_mb_b(p, f, mbx, mby, tile);      // decoded pictures: B slices / the 8x8 transform may occur
       else deblock_one_mb(p, f, mbx, mby, tile);
     }
 }
@@ -332,6 +332,7 @@ extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, i
       if (au_end < len && au_end > 0 && bs[au_end - 1] == 0) au_end--;        // zero_byte of the next 4-byte start code
       b2h264::ParsedPicture pp;
       const int rc = b2h264::parse_access_unit(bs + au_begin, (size_t)(au_end - au_begin), &st, &pp);
+      if (rc != 0 && getenv("EMU_MAX_FRAMES")) { fprintf(stderr, "parse error %d at picture %d\n", rc, frames); break; }
       if (rc != 0) return -1000 + rc;
       b2h264::StreamCtl geo;                                                    // picture geometry helpers
       geo.sp = st.sp;
@@ -351,6 +352,7 @@ extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, i
       p.mb_w = st.sp.mb_w; p.mb_h = st.sp.mb_h;
       p.rec_stride_y = geo.rec_stride_y(); p.rec_stride_c = geo.rec_stride_c();
       p.qp = pp.ss.qp; p.is_idr = pp.ss.idr; p.ref_is_p = !pp.ss.idr; p.mv_range = 64; p.dec_mode = 1;
+      p.dec_cqp_off = pp.chroma_qp_offset;
       EncFramePtrs f;
       memset(&f, 0, sizeof(f));
       for (int pl = 0; pl < 3; pl++) {
@@ -392,6 +394,7 @@ extern "C" int emu_decode(const uint8_t* bs, long len, uint8_t* out, long cap, i
       if (pp.ss.idr) seq++;
       order.push_back({seq, pp.poc, frames});
       frames++;
+      if (const char* mf = getenv("EMU_MAX_FRAMES")) if (frames >= atoi(mf)) break;   // debugging aid: stop after N pictures
       au_begin = au_end;
     }
     pos = next;

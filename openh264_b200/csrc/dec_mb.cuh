@@ -189,6 +189,19 @@ MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch
           }
         }
       }
+      if (ab.wp_on && (r0 >= 0) != (r1 >= 0)) {
+        // explicit weights of the 8x8's single reference (WeightPrediction, rec_mb.cpp:298; 8.4.2.3.2): luma, then Cb / Cr
+        const int qx = (k & 1) * 8, qy = (k >> 1) * 8;
+        for (int i = lane_id(); i < 64 + 32; i += MBK_WS) {
+          int pos, plane;
+          uint8_t* a;
+          if (i < 64) { pos = (qy + (i >> 3)) * 16 + qx + (i & 7); a = pl; plane = 0; }
+          else { const int t = i - 64, cpl = t >> 4, e = t & 15; pos = 64 * cpl + ((qy >> 1) + (e >> 2)) * 8 + (qx >> 1) + (e & 3); a = pc; plane = 1 + cpl; }
+          const int ld = ab.wp_log2[plane ? 1 : 0], w = ab.wp[k][plane][0], o = ab.wp[k][plane][1];
+          a[pos] = (uint8_t)clip255(ld >= 1 ? ((a[pos] * w + (1 << (ld - 1))) >> ld) + o : a[pos] * w + o);
+        }
+        warp_sync();
+      }
       if (r0 >= 0 && r1 >= 0) {
         const int w1 = ab.w1[k], w0 = 64 - w1, qx = (k & 1) * 8, qy = (k >> 1) * 8;
         for (int i = lane_id(); i < 64 + 32; i += MBK_WS) {

@@ -81,7 +81,11 @@ typedef struct {
   int16_t w1[4];                          // per 8x8 with both lists: weight of the list-1 prediction out of 64 (32: plain average; implicit
                                           // weights 8.4.2.3.1 otherwise); w0 = 64 - w1
   int16_t mv[16][2];                      // final list-1 vector of 4x4 block j of 8x8 k at [4 * k + j]
-} DecMbAuxB;                              // 80 bytes
+  uint8_t wp_on;                          // explicit weights (pred_weight_table of the slice) apply to this macroblock's single-list predictions
+  uint8_t wp_log2[2];                     // luma_log2_weight_denom, chroma_log2_weight_denom
+  uint8_t pad;
+  int16_t wp[4][3][2];                    // per 8x8, plane Y / Cb / Cr: weight, offset of its (single) reference
+} DecMbAuxB;                              // 132 bytes
 #define DECAUX_SUB 1
 #define DECAUX_CIP 2
 #define DECAUX_T8 4                       /* transform_size_8x8_flag: the luma levels are four 8x8 blocks (MbOut::luma[4k .. 4k+3] = 64 levels in

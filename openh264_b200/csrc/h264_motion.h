@@ -217,6 +217,8 @@ inline bool dist_scale(int cur_poc, int poc0, int poc1, bool lt, int* dsf) {
   return true;
 }
 
+inline bool emit_resolved(const MotionCtx& M, const BMbSyntax& sx, const BSliceCtx& S, const WpTable* wp, DecMbAux* ax, DecMbAuxB* axb);
+
 // Resolves a B macroblock: final vectors and reference pictures of both lists into ax (list 0) / axb (list 1), the field, and
 // returns false if the stream refers to a picture that is not there.
 inline bool derive_b(MotionCtx& M, int idx, int avail, const BMbSyntax& sx, const BSliceCtx& S, DecMbAux* ax, DecMbAuxB* axb) {
@@ -302,7 +304,13 @@ inline bool derive_b(MotionCtx& M, int idx, int avail, const BMbSyntax& sx, cons
     for (int l = 0; l < 2; l++)
       for (int k = 0; k < 4; k++) {
         const int bx = (k & 1) * 2, by = (k >> 1) * 2;
-        if (sx.sub[k] == 0) { M.set(l, bx, by, 2, 2, dref[l][k], dmv[l][k][0], dmv[l][k][1]); continue; }
+        if (sx.sub[k] == 0) {
+          // the reference leaves the reference-index CACHE of a temporal-direct 8x8 at "not in list" while the other 8x8s of the
+          // macroblock predict their vectors (ParseInterBInfo, parse_mb_syn_cavlc.cpp:1618-1624: ref_idx_list is only filled for
+          // spatial direct); the picture's arrays get the real index.  Its output is the oracle: the cells are corrected below
+          M.set(l, bx, by, 2, 2, S.direct_spatial ? dref[l][k] : MREF_NONE, dmv[l][k][0], dmv[l][k][1]);
+          continue;
+        }
         if (!(b_sub_lists(sx.sub[k]) & (1 << l))) { M.set(l, bx, by, 2, 2, MREF_NONE, 0, 0); continue; }
         const int st = b_sub_shape(sx.sub[k]), ref = sx.ref[l][k];
         const int w4 = (st == 0 || st == 1) ? 2 : 1, h4 = (st == 0 || st == 2) ? 2 : 1, np = st == 0 ? 1 : st == 3 ? 4 : 2;
@@ -315,7 +323,18 @@ inline bool derive_b(MotionCtx& M, int idx, int avail, const BMbSyntax& sx, cons
         }
       }
   }
-  // hand-over records: picture slots per 8x8, final vectors in coding order
+  if (sx.type == 22 && !sx.skip && !S.direct_spatial)
+    for (int l = 0; l < 2; l++)
+      for (int k = 0; k < 4; k++)
+        if (sx.sub[k] == 0) M.set(l, (k & 1) * 2, (k >> 1) * 2, 2, 2, dref[l][k], dmv[l][k][0], dmv[l][k][1]);
+  if (!emit_resolved(M, sx, S, nullptr, ax, axb)) return false;
+  M.store(idx, S.list[0], S.list[1]);
+  return true;
+}
+
+// the macroblock's cells -> hand-over records: picture slots per 8x8, final vectors in coding order, weights
+inline bool emit_resolved(const MotionCtx& M, const BMbSyntax& sx, const BSliceCtx& S, const WpTable* wp, DecMbAux* ax, DecMbAuxB* axb) {
+  axb->wp_on = 0;
   for (int k = 0; k < 4; k++) {
     const int c0 = MotionCtx::cell((k & 1) * 2, (k >> 1) * 2);
     int r[2];
@@ -349,9 +368,24 @@ inline bool derive_b(MotionCtx& M, int idx, int avail, const BMbSyntax& sx, cons
       if (b_part_lists(sx.type, part) == 3) use = part == 0 ? 2 : 1;
     }
     axb->pred_lists[k] = (uint8_t)use;
+    if (wp && wp->on && (use == 1 || use == 2)) {                  // explicit weights of the 8x8's reference (8.4.2.3.2, one list)
+      const int l = use - 1;
+      axb->wp_on = 1; axb->wp_log2[0] = (uint8_t)wp->log2[0]; axb->wp_log2[1] = (uint8_t)wp->log2[1];
+      for (int pl = 0; pl < 3; pl++) { axb->wp[k][pl][0] = wp->w[l][r[l]][pl][0]; axb->wp[k][pl][1] = wp->w[l][r[l]][pl][1]; }
+    }
   }
-  M.store(idx, S.list[0], S.list[1]);
   return true;
+}
+
+// a P macroblock of a slice with explicit weights travels RESOLVED like a B macroblock (list 0 only): its prediction is weighted per
+// reference index, which the device — it knows picture slots, not indices — cannot look up.  Call after derive_p().
+inline bool emit_resolved_p(const MotionCtx& M, const RefEntry* l0, int n_ref, const WpTable& wp, DecMbAux* ax, DecMbAuxB* axb) {
+  BSliceCtx S;
+  S.n_ref[0] = n_ref; S.n_ref[1] = 0;
+  for (int i = 0; i < 33; i++) S.list[0][i] = l0[i];
+  BMbSyntax sx;
+  sx.skip = true;                                                  // no partition quirk applies (one list)
+  return emit_resolved(M, sx, S, &wp, ax, axb);
 }
 
 }  // namespace b2h264

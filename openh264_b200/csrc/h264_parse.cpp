@@ -540,7 +540,8 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
           }
       }
     if (!r.ok()) return PARSE_TRUNCATED;
-    return PARSE_UNSUPPORTED;                                 // WP_TODO: explicit weights are parsed but not yet applied
+    if (is_b) return PARSE_UNSUPPORTED;                       // explicit weights in B slices (weighted_bipred_idc 1) are not built
+    if (st->profile == 66) return PARSE_INVALID;
   }
   const bool is_ref = nal.ref_idc != 0;                       // a non-reference picture is output but never predicted from
   bool adaptive = false, idr_lt = false;
@@ -625,7 +626,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
   } else if (ss.idr != pic->ss.idr || ss.frame_num != pic->ss.frame_num || is_ref != pic->is_ref || poc != pic->poc) {
     return PARSE_INVALID;                                     // slices of one access unit must agree
   }
-  if (is_b && !pic->has_b) {
+  if ((is_b || wp.on) && !pic->has_b) {                       // B macroblocks, and P macroblocks with explicit weights, travel resolved
     pic->has_b = true;
     DecMbAuxB zb;
     memset(&zb, 0, sizeof(zb));
@@ -644,11 +645,18 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     bsl.col = (cslot >= 0 && cslot < (int)st->motion.size()) ? &st->motion[cslot] : nullptr;
     bsl.col_long_term = lists[1][0].lt;
   }
+  bool track_fail = false;
   auto track_mb = [&](int i, const int* ri) {                 // a macroblock of an I / P slice is complete: its cells of the field
     if (!track) return;
-    const MbOut& mm = pic->mbs[i];
+    MbOut& mm = pic->mbs[i];
     if (MBT_IS_INTRA(mm.mb_type)) M.store_intra(i);
-    else if (!MBT_IS_B(mm.mb_type)) derive_p(M, i, pic->aux[i].avail, mm, pic->aux[i], ri, lists[0]);
+    else if (!MBT_IS_B(mm.mb_type)) {
+      derive_p(M, i, pic->aux[i].avail, mm, pic->aux[i], ri, lists[0]);
+      if (wp.on) {                                            // explicit weights: the macroblock travels resolved, like a B macroblock
+        if (!emit_resolved_p(M, lists[0], n_ref, wp, &pic->aux[i], &pic->aux_b[i])) track_fail = true;
+        mm.mb_type = mm.mb_type == MBT_PSKIP ? MBT_BSKIP : MBT_B;
+      }
+    }
   };
   static const int kRiZero[4] = {0, 0, 0, 0};
   if (pic->n_slices >= 65535) return PARSE_UNSUPPORTED;
@@ -954,7 +962,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
       if (d.terminate()) break;                               // end_of_slice_flag
     }
     pic->next_mb = idx;
-    return PARSE_OK;
+    return track_fail ? PARSE_INVALID : PARSE_OK;
   }
 
   // ---- slice data, CAVLC ----
@@ -1171,7 +1179,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     if (!r.more_data()) break;                                // end of this slice
   }
   pic->next_mb = idx;
-  return PARSE_OK;
+  return track_fail ? PARSE_INVALID : PARSE_OK;
 }
 
 }  // namespace

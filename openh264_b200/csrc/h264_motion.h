@@ -37,6 +37,7 @@ struct BSliceCtx {
   int implicit = 0;                              // weighted_bipred_idc == 2
   const MotionStore* col = nullptr;              // motion field of RefPicList1[0]
   bool col_long_term = false;
+  bool cabac = false;                            // entropy coder of the slice: the reference's two parsers treat temporal-direct 8x8s differently
 };
 
 // syntax of one B macroblock as read from the stream (both entropy coders fill this, then derive_b() resolves it)
@@ -301,9 +302,20 @@ inline bool derive_b(MotionCtx& M, int idx, int avail, const BMbSyntax& sx, cons
         M.set(l, bx, by, w4, h4, ref, px + sx.mvd[l][p][0], py + sx.mvd[l][p][1]);
       }
   } else {
+    // temporal-direct 8x8s inside B_8x8, as the reference's two parsers have them while the OTHER 8x8s predict their vectors (its
+    // output is the oracle): the CABAC parser (ParseInterBMotionInfoCabac, parse_mb_syn_cabac.cpp:943-970) enters their reference
+    // indices into the cache BEFORE any vector is predicted — so even an earlier 8x8 sees them as neighbour C — whereas the CAVLC
+    // parser (ParseInterBInfo, parse_mb_syn_cavlc.cpp:1618-1624) leaves their cache cells at "not in list".  Spatial direct follows
+    // the decoding order in both.  The picture's arrays get the real indices either way (corrected below).
+    const bool early = !S.direct_spatial && S.cabac;
+    if (early)
+      for (int l = 0; l < 2; l++)
+        for (int k = 0; k < 4; k++)
+          if (sx.sub[k] == 0) M.set(l, (k & 1) * 2, (k >> 1) * 2, 2, 2, dref[l][k], dmv[l][k][0], dmv[l][k][1]);
     for (int l = 0; l < 2; l++)
       for (int k = 0; k < 4; k++) {
         const int bx = (k & 1) * 2, by = (k >> 1) * 2;
+        if (sx.sub[k] == 0 && early) continue;
         if (sx.sub[k] == 0) {
           // the reference leaves the reference-index CACHE of a temporal-direct 8x8 at "not in list" while the other 8x8s of the
           // macroblock predict their vectors (ParseInterBInfo, parse_mb_syn_cavlc.cpp:1618-1624: ref_idx_list is only filled for

@@ -641,6 +641,7 @@ int parse_slice(BitReader& r, const Nal& nal, ParserState* st, ParsedPicture* pi
     bsl.direct_spatial = direct_spatial; bsl.cur_poc = poc; bsl.n_ref[0] = n_ref; bsl.n_ref[1] = n_ref1;
     for (int l = 0; l < 2; l++) for (int i = 0; i < 33; i++) bsl.list[l][i] = lists[l][i];
     bsl.implicit = st->weighted_bipred_idc == 2;
+    bsl.cabac = st->entropy_cabac;
     const int cslot = lists[1][0].slot;
     bsl.col = (cslot >= 0 && cslot < (int)st->motion.size()) ? &st->motion[cslot] : nullptr;
     bsl.col_long_term = lists[1][0].lt;

@@ -89,7 +89,8 @@ MBK_HD void dec_mc_part(const MbCtx& c, uint8_t* pl, uint8_t* pc, int slot, int 
 MBK_HD int dec_ref_of(const DecMbAux& aux, int blk) { return aux.ref_idx[blk >> 2]; }
 
 // luma of an inter macroblock with the 8x8 transform: lane k reconstructs 8x8 block k (prediction + inverse transform of its 64 levels)
-MBK_HD void rec_luma_inter8(MbScratch& s, const MbOut& m, int qp, const uint8_t* pl) {
+// (real functions, not inlined: their 64-entry arrays live on the stack, and only High-profile macroblocks pay for that frame)
+MBK_FN void rec_luma_inter8(MbScratch& s, const MbOut& m, int qp, const uint8_t* pl) {
   for (int k = lane_id(); k < 4; k += MBK_WS) {
     const int ox = (k & 1) * 8, oy = (k >> 1) * 8;
     uint8_t* org = tile_y(s.tile, ox, oy);
@@ -102,6 +103,37 @@ MBK_HD void rec_luma_inter8(MbScratch& s, const MbOut& m, int qp, const uint8_t*
     }
   }
   warp_sync();
+}
+
+// the four Intra_8x8 blocks of a macroblock on lane 0, each predicting from what was just reconstructed (mode cache s.i4m prepared)
+MBK_FN void dec_i8x8_blocks(MbScratch& s, const MbOut& m, int nb_i, int qp) {
+  if (lane_id() == 0) {
+    for (int k = 0; k < 4; k++) {
+      const int bx = (k & 1) * 2, by = (k >> 1) * 2;
+      uint8_t* org = tile_y(s.tile, bx * 4, by * 4);
+      const int lm = s.i4m[(by + 1) * 5 + bx], tm = s.i4m[by * 5 + bx + 1];
+      const int pm = (lm == -1 || tm == -1) ? 2 : (lm < tm ? lm : tm);
+      const int coded = m.prev_i4_flag[k] ? pm : (m.rem_i4_mode[k] < pm ? m.rem_i4_mode[k] : m.rem_i4_mode[k] + 1);
+      // neighbouring samples of the 8x8 block (6.4.11): left / top from the neighbouring macroblock or from inside, top-right of
+      // block 1 from the top-right macroblock, of block 2 from block 1, of block 3 never
+      const bool aL = (k & 1) ? true : (nb_i & NB_LEFT) != 0, aT = (k >> 1) ? true : (nb_i & NB_TOP) != 0;
+      const bool aTL = k == 0 ? (nb_i & NB_TOPLEFT) != 0 : k == 1 ? (nb_i & NB_TOP) != 0 : k == 2 ? (nb_i & NB_LEFT) != 0 : true;
+      const bool aTR = k == 0 ? (nb_i & NB_TOP) != 0 : k == 1 ? (nb_i & NB_TOPRIGHT) != 0 : k == 2;
+      for (int y = 0; y < 2; y++) for (int x = 0; x < 2; x++) {
+        s.i4m[(by + y + 1) * 5 + bx + x + 1] = (int8_t)coded;
+        s.info.i4_mode[(by + y) * 4 + bx + x] = (int8_t)coded;
+      }
+      uint8_t pr[64];
+      pred_i8x8(pr, org, TY_PITCH, coded, (aL ? 1 : 0) | (aT ? 2 : 0) | (aTL ? 4 : 0) | (aTR ? 8 : 0));
+      if (m.cbp & (1 << k)) {
+        int16_t d[64];
+        unscan_dequant8x8(d, &m.luma[4 * k][0], qp);
+        idct8x8_rec(org, TY_PITCH, pr, 8, d);
+      } else {
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) org[y * TY_PITCH + x] = pr[8 * y + x];
+      }
+    }
+  }
 }
 
 // One macroblock.  f.rec = picture being reconstructed, f.ref = reference picture (padded), f.mbi = MbInfo array of
@@ -293,33 +325,7 @@ MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch
       }
       warp_sync();
     }
-    if (lane_id() == 0) {
-      for (int k = 0; k < 4; k++) {
-        const int bx = (k & 1) * 2, by = (k >> 1) * 2;
-        uint8_t* org = tile_y(s.tile, bx * 4, by * 4);
-        const int lm = s.i4m[(by + 1) * 5 + bx], tm = s.i4m[by * 5 + bx + 1];
-        const int pm = (lm == -1 || tm == -1) ? 2 : (lm < tm ? lm : tm);
-        const int coded = m.prev_i4_flag[k] ? pm : (m.rem_i4_mode[k] < pm ? m.rem_i4_mode[k] : m.rem_i4_mode[k] + 1);
-        // neighbouring samples of the 8x8 block (6.4.11): left / top from the neighbouring macroblock or from inside, top-right of
-        // block 1 from the top-right macroblock, of block 2 from block 1, of block 3 never
-        const bool aL = (k & 1) ? true : (nb_i & NB_LEFT) != 0, aT = (k >> 1) ? true : (nb_i & NB_TOP) != 0;
-        const bool aTL = k == 0 ? (nb_i & NB_TOPLEFT) != 0 : k == 1 ? (nb_i & NB_TOP) != 0 : k == 2 ? (nb_i & NB_LEFT) != 0 : true;
-        const bool aTR = k == 0 ? (nb_i & NB_TOP) != 0 : k == 1 ? (nb_i & NB_TOPRIGHT) != 0 : k == 2;
-        for (int y = 0; y < 2; y++) for (int x = 0; x < 2; x++) {
-          s.i4m[(by + y + 1) * 5 + bx + x + 1] = (int8_t)coded;
-          s.info.i4_mode[(by + y) * 4 + bx + x] = (int8_t)coded;
-        }
-        uint8_t pr[64];
-        pred_i8x8(pr, org, TY_PITCH, coded, (aL ? 1 : 0) | (aT ? 2 : 0) | (aTL ? 4 : 0) | (aTR ? 8 : 0));
-        if (m.cbp & (1 << k)) {
-          int16_t d[64];
-          unscan_dequant8x8(d, &m.luma[4 * k][0], qp);
-          idct8x8_rec(org, TY_PITCH, pr, 8, d);
-        } else {
-          for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x++) org[y * TY_PITCH + x] = pr[8 * y + x];
-        }
-      }
-    }
+    dec_i8x8_blocks(s, m, nb_i, qp);
     warp_sync();
   } else {                                       // I4x4: block by block, each predicts from what was just reconstructed
     fill_i4_cache(c, s);

@@ -116,7 +116,11 @@ def test_reference_conformance_table_exact_or_rejected(emu):
     # B slices (spatial direct, one or two lists per partition, B_8x8, B_Skip; pictures that leave in POC order), CAVLC and CABAC
     assert {"Cisco_Men_whisper_640x320_CABAC_Bframe_9.264", "Cisco_Men_whisper_640x320_CAVLC_Bframe_9.264",
             "Cisco_Adobe_PDF_sample_a_1024x768_CAVLC_Bframe_9.264"} <= set(exact)
-    assert len(exact) >= 43                      # of 51; rejected: High-profile B streams with the 8x8 transform and explicit weights (6), scaling lists, SVC subset SPS
+    # High profile as x264 writes it: 8x8 transform + Intra_8x8, explicit weighted P prediction, chroma QP offset, B pyramids, temporal
+    # direct prediction, implicit weights — BASELINE.json configs[3]'s 1080p CABAC stream among them
+    assert {"VID_1920x1080_cabac_temporal_direct.264", "VID_1920x1080_cavlc_temporal_direct.264", "VID_1280x720_cabac_temporal_direct.264",
+            "VID_1280x720_cavlc_temporal_direct.264", "VID_1280x544_cabac_temporal_direct.264", "VID_1280x544_cavlc_temporal_direct.264"} <= set(exact)
+    assert len(exact) >= 49                      # of 51; rejected: scaling lists, SVC subset SPS
 
 
 @pytest.mark.parametrize("entropy", [(0, 66), (1, 0)])
@@ -256,3 +260,23 @@ def test_host_decoder_on_committed_b_slice_streams(emu, name, sha):
     n = emu.emu_decode(a.ctypes.data, len(a), out.ctypes.data, out.size, C.byref(W), C.byref(H))
     assert n == 9, n
     assert hashlib.sha1(out[:n * W.value * H.value * 3 // 2].tobytes()).hexdigest() == sha
+
+
+def high_profile_prefixes():
+    import json
+    return sorted(json.load(open(os.path.join(ROOT, "tests", "golden", "high_profile_prefix.json"))).items())
+
+
+@pytest.mark.parametrize("name,gold", high_profile_prefixes())
+def test_host_decoder_on_committed_high_profile_prefixes(emu, name, gold):
+    """the first 14 access units of two of the reference's High-profile vectors (tests/golden/make_high_profile_fixture.py: 8x8 transform,
+    Intra_8x8, weighted P prediction, B pyramid, temporal direct, implicit weights; CABAC and CAVLC) against what the unmodified
+    reference decoder makes of the same prefix"""
+    import hashlib
+    a = np.fromfile(os.path.join(CONF_B_DIR, name), dtype=np.uint8)
+    out = np.zeros(64 << 20, np.uint8)
+    W, H = C.c_int(), C.c_int()
+    emu.emu_decode.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    n = emu.emu_decode(a.ctypes.data, len(a), out.ctypes.data, out.size, C.byref(W), C.byref(H))
+    assert n == gold["pictures"] and (W.value, H.value) == (gold["width"], gold["height"])
+    assert hashlib.sha1(out[:n * W.value * H.value * 3 // 2].tobytes()).hexdigest() == gold["sha1"]

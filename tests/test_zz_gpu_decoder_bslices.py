@@ -85,3 +85,25 @@ def test_gpu_decoder_b_and_p_streams_in_one_batch():
     for t in got_b:
         hs.update(t[3].tobytes())
     assert hs.hexdigest() == sha
+
+
+def _prefixes():
+    return sorted(json.load(open(os.path.join(ROOT, "tests", "golden", "high_profile_prefix.json"))).items())
+
+
+@pytest.mark.parametrize("name,gold", _prefixes())
+def test_gpu_decoder_high_profile_prefixes(name, gold):
+    """High profile as x264 writes it (the tool set of BASELINE.json configs[3]: 8x8 transform with Intra_8x8, explicit weighted P
+    prediction, chroma QP offset, B pyramid, temporal direct prediction, implicit weights; CABAC and CAVLC): the first 14 access units
+    of two of the reference's vectors against the unmodified reference decoder's output for the same prefix
+    (tests/golden/make_high_profile_fixture.py)"""
+    from openh264_b200.binding import BatchDecoder
+    aus = h264lib.split_access_units(open(os.path.join(CONF_B_DIR, name), "rb").read())
+    assert len(aus) == gold["pictures"]
+    dec = BatchDecoder(gold["width"], gold["height"])
+    pics, depth = _decode_in_output_order(dec, aus)
+    dec.close()
+    hs = hashlib.sha1()
+    for p in pics:
+        hs.update(p.tobytes())
+    assert hs.hexdigest() == gold["sha1"]

@@ -1,5 +1,5 @@
 // h264_parse.h — host-side bitstream PARSER: the inverse of h264_bitstream.{h,cpp} for the stream class this
-// library decodes: Baseline / Main / High without the 8x8 transform, CAVLC or CABAC, I, P and B slices (several per picture, in raster order: no FMO / ASO),
+// library decodes: Baseline / Main / High (8x8 transform, flat scaling lists), CAVLC or CABAC, I, P and B slices (several per picture, in raster order: no FMO / ASO),
 // up to 16 reference frames, all partition shapes down to 4x4, direct prediction and implicit weights in B slices (h264_motion.h), non-reference pictures, constrained intra prediction, per-slice deblocking control.  Groundwork for the decoder construct path (SURVEY.md section 8f / DESIGN.md section 9): the
 // reference parses on the host too (codec/decoder/core/src/{au_parser,parse_mb_syn_cavlc,decode_slice}.cpp) and
 // hands macroblock arrays to the pixel stage; here the macroblock array is the same MbOut record the encoder's

@@ -7,7 +7,7 @@
 // (B slices reorder the output): pictures are held and released by the reference's own rule (ReorderPicturesInDisplay), copies of
 // the held pictures live in this object, NUM_OF_FRAMES_REMAINING_IN_BUFFER counts them, FlushFrame hands them out at the end.
 // The picture size comes from the stream: the GPU decoder is (re)created when an SPS announces a new size.
-// Stream class: what layer 2 decodes (include/b2h264_codec.h: I, P and B slices with CAVLC or CABAC, no 8x8 transform, progressive);
+// Stream class: what layer 2 decodes (include/b2h264_codec.h: I, P and B slices with CAVLC or CABAC, 4x4 / 8x8 transform, progressive);
 // anything else is refused with dsBitstreamError and a reason on stderr — there is no CPU decoder in this library.
 #include <cuda_runtime_api.h>
 #include <stdio.h>
@@ -181,7 +181,7 @@ class B2Decoder : public ISVCDecoder {
  private:
   DECODING_STATE refuse(int rc) {
     const char* what = rc == -101 ? "truncated access unit" : rc == -102 ? "stream feature outside the supported class (I / P / B slices, CAVLC or "
-                       "CABAC, 4x4 transform, no explicit weights, progressive, no FMO / ASO)" : rc == -103 ? "invalid syntax"
+                       "CABAC, 4x4 / 8x8 transform, no scaling lists, progressive, no FMO / ASO)" : rc == -103 ? "invalid syntax"
                        : rc == -104 ? "slice before its parameter sets" : rc == -2 ? "picture size changed without an SPS" : "CUDA / internal error";
     fprintf(stderr, "[b2h264] ISVCDecoder: %s (%d)\n", what, rc);
     return rc == -104 ? dsNoParamSets : rc > 0 ? dsOutOfMemory : dsBitstreamError;

@@ -136,6 +136,75 @@ MBK_FN void dec_i8x8_blocks(MbScratch& s, const MbOut& m, int nb_i, int qp) {
   }
 }
 
+// A B macroblock (or a P macroblock that travels resolved: explicit weights).  A real function: the Baseline path of dec_one_mb keeps
+// its registers and stack frame.
+MBK_FN void dec_b_mb(const MbCtx& c, const EncFrameParams& p, MbScratch& s, const MbOut& m, const DecMbAux& aux, int mbx, int mby,
+                     uint8_t* pl, uint8_t* pc, int qp) {
+  // B macroblock (GetInterBPred, rec_mb.cpp:462 ff.): the parser resolved both lists (h264_motion.h) — per 8x8 a picture slot and
+  // FINAL vectors per 4x4 block for list 0 (aux) and list 1 (dec_aux_b).  Each list is motion compensated like a P partition (one
+  // 8x8 where the four blocks move together, else 4x4 by 4x4); where both lists predict, the two predictions are combined with the
+  // 8x8's weights (32 / 32: the plain average (a + b + 1) >> 1; implicit weights otherwise, 8.4.2.3 with logWD 5 and no offsets).
+  const DecMbAuxB& ab = c.f.dec_aux_b[mby * p.mb_w + mbx];
+  uint8_t* pl1 = s.pred_y[1];
+  uint8_t* pc1 = s.pred_c[1];
+  for (int k = 0; k < 4; k++) {
+    const int use = ab.pred_lists[k];                            // lists that enter the sample prediction (see DecMbAuxB)
+    const int r0 = (use & 1) ? aux.ref_idx[k] : -1, r1 = (use & 2) ? ab.ref_idx[k] : -1;
+    bool whole = true;
+    for (int j = 1; j < 4; j++)
+      whole = whole && aux.mvd[4 * k + j][0] == aux.mvd[4 * k][0] && aux.mvd[4 * k + j][1] == aux.mvd[4 * k][1] &&
+              ab.mv[4 * k + j][0] == ab.mv[4 * k][0] && ab.mv[4 * k + j][1] == ab.mv[4 * k][1];
+    for (int l = 0; l < 2; l++) {
+      const int slot = l ? r1 : r0;
+      if (slot < 0) continue;
+      uint8_t* dl = (l && r0 >= 0) ? pl1 : pl;                   // list 1 alone predicts straight into the first buffer
+      uint8_t* dc = (l && r0 >= 0) ? pc1 : pc;
+      if (whole) {
+        const int mvx = l ? ab.mv[4 * k][0] : aux.mvd[4 * k][0], mvy = l ? ab.mv[4 * k][1] : aux.mvd[4 * k][1];
+        dec_mc_part(c, dl, dc, slot, 4 * k, 2, 2, mvx, mvy);
+      } else {
+        for (int j = 0; j < 4; j++) {
+          const int mvx = l ? ab.mv[4 * k + j][0] : aux.mvd[4 * k + j][0], mvy = l ? ab.mv[4 * k + j][1] : aux.mvd[4 * k + j][1];
+          dec_mc_part(c, dl, dc, slot, 4 * k + j, 1, 1, mvx, mvy);
+        }
+      }
+    }
+    if (ab.wp_on && (r0 >= 0) != (r1 >= 0)) {
+      // explicit weights of the 8x8's single reference (WeightPrediction, rec_mb.cpp:298; 8.4.2.3.2): luma, then Cb / Cr
+      const int qx = (k & 1) * 8, qy = (k >> 1) * 8;
+      for (int i = lane_id(); i < 64 + 32; i += MBK_WS) {
+        int pos, plane;
+        uint8_t* a;
+        if (i < 64) { pos = (qy + (i >> 3)) * 16 + qx + (i & 7); a = pl; plane = 0; }
+        else { const int t = i - 64, cpl = t >> 4, e = t & 15; pos = 64 * cpl + ((qy >> 1) + (e >> 2)) * 8 + (qx >> 1) + (e & 3); a = pc; plane = 1 + cpl; }
+        const int ld = ab.wp_log2[plane ? 1 : 0], w = ab.wp[k][plane][0], o = ab.wp[k][plane][1];
+        a[pos] = (uint8_t)clip255(ld >= 1 ? ((a[pos] * w + (1 << (ld - 1))) >> ld) + o : a[pos] * w + o);
+      }
+      warp_sync();
+    }
+    if (r0 >= 0 && r1 >= 0) {
+      const int w1 = ab.w1[k], w0 = 64 - w1, qx = (k & 1) * 8, qy = (k >> 1) * 8;
+      for (int i = lane_id(); i < 64 + 32; i += MBK_WS) {
+        int pos;
+        uint8_t *a, *b;
+        if (i < 64) { pos = (qy + (i >> 3)) * 16 + qx + (i & 7); a = pl; b = pl1; }
+        else { const int t = i - 64, cpl = t >> 4, e = t & 15; pos = 64 * cpl + ((qy >> 1) + (e >> 2)) * 8 + (qx >> 1) + (e & 3); a = pc; b = pc1; }
+        a[pos] = (uint8_t)clip255((a[pos] * w0 + b[pos] * w1 + 32) >> 6);
+      }
+      warp_sync();
+    }
+  }
+  if (lane_id() == 0)
+    for (int b = 0; b < 16; b++) {
+      const int bx = b & 3, by = b >> 2, z = ((by >> 1) * 2 + (bx >> 1)) * 4 + (by & 1) * 2 + (bx & 1);
+      const bool used = aux.ref_idx[z >> 2] >= 0;
+      s.info.mv[b][0] = used ? aux.mvd[z][0] : 0; s.info.mv[b][1] = used ? aux.mvd[z][1] : 0;
+    }
+  warp_sync();
+  if (aux.flags & DECAUX_T8) rec_luma_inter8(s, m, qp, pl);
+  else { dec_luma_coef(s, m, qp, false, nullptr); rec_luma_inter(s, pl); }
+}
+
 // One macroblock.  f.rec = picture being reconstructed, f.ref = reference picture (padded), f.mbi = MbInfo array of
 // the picture (neighbour lookups + what deblocking reads).  Raster / wavefront order like the encoder.
 MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch& s, int mbx, int mby, const MbOut& m, const DecMbAux& aux) {
@@ -192,69 +261,7 @@ MBK_HD void dec_one_mb(const EncFrameParams& p, const EncFramePtrs& f, MbScratch
     return;
   }
   if (MBT_IS_B(type)) {
-    // B macroblock (GetInterBPred, rec_mb.cpp:462 ff.): the parser resolved both lists (h264_motion.h) — per 8x8 a picture slot and
-    // FINAL vectors per 4x4 block for list 0 (aux) and list 1 (dec_aux_b).  Each list is motion compensated like a P partition (one
-    // 8x8 where the four blocks move together, else 4x4 by 4x4); where both lists predict, the two predictions are combined with the
-    // 8x8's weights (32 / 32: the plain average (a + b + 1) >> 1; implicit weights otherwise, 8.4.2.3 with logWD 5 and no offsets).
-    const DecMbAuxB& ab = c.f.dec_aux_b[mby * p.mb_w + mbx];
-    uint8_t* pl1 = s.pred_y[1];
-    uint8_t* pc1 = s.pred_c[1];
-    for (int k = 0; k < 4; k++) {
-      const int use = ab.pred_lists[k];                            // lists that enter the sample prediction (see DecMbAuxB)
-      const int r0 = (use & 1) ? aux.ref_idx[k] : -1, r1 = (use & 2) ? ab.ref_idx[k] : -1;
-      bool whole = true;
-      for (int j = 1; j < 4; j++)
-        whole = whole && aux.mvd[4 * k + j][0] == aux.mvd[4 * k][0] && aux.mvd[4 * k + j][1] == aux.mvd[4 * k][1] &&
-                ab.mv[4 * k + j][0] == ab.mv[4 * k][0] && ab.mv[4 * k + j][1] == ab.mv[4 * k][1];
-      for (int l = 0; l < 2; l++) {
-        const int slot = l ? r1 : r0;
-        if (slot < 0) continue;
-        uint8_t* dl = (l && r0 >= 0) ? pl1 : pl;                   // list 1 alone predicts straight into the first buffer
-        uint8_t* dc = (l && r0 >= 0) ? pc1 : pc;
-        if (whole) {
-          const int mvx = l ? ab.mv[4 * k][0] : aux.mvd[4 * k][0], mvy = l ? ab.mv[4 * k][1] : aux.mvd[4 * k][1];
-          dec_mc_part(c, dl, dc, slot, 4 * k, 2, 2, mvx, mvy);
-        } else {
-          for (int j = 0; j < 4; j++) {
-            const int mvx = l ? ab.mv[4 * k + j][0] : aux.mvd[4 * k + j][0], mvy = l ? ab.mv[4 * k + j][1] : aux.mvd[4 * k + j][1];
-            dec_mc_part(c, dl, dc, slot, 4 * k + j, 1, 1, mvx, mvy);
-          }
-        }
-      }
-      if (ab.wp_on && (r0 >= 0) != (r1 >= 0)) {
-        // explicit weights of the 8x8's single reference (WeightPrediction, rec_mb.cpp:298; 8.4.2.3.2): luma, then Cb / Cr
-        const int qx = (k & 1) * 8, qy = (k >> 1) * 8;
-        for (int i = lane_id(); i < 64 + 32; i += MBK_WS) {
-          int pos, plane;
-          uint8_t* a;
-          if (i < 64) { pos = (qy + (i >> 3)) * 16 + qx + (i & 7); a = pl; plane = 0; }
-          else { const int t = i - 64, cpl = t >> 4, e = t & 15; pos = 64 * cpl + ((qy >> 1) + (e >> 2)) * 8 + (qx >> 1) + (e & 3); a = pc; plane = 1 + cpl; }
-          const int ld = ab.wp_log2[plane ? 1 : 0], w = ab.wp[k][plane][0], o = ab.wp[k][plane][1];
-          a[pos] = (uint8_t)clip255(ld >= 1 ? ((a[pos] * w + (1 << (ld - 1))) >> ld) + o : a[pos] * w + o);
-        }
-        warp_sync();
-      }
-      if (r0 >= 0 && r1 >= 0) {
-        const int w1 = ab.w1[k], w0 = 64 - w1, qx = (k & 1) * 8, qy = (k >> 1) * 8;
-        for (int i = lane_id(); i < 64 + 32; i += MBK_WS) {
-          int pos;
-          uint8_t *a, *b;
-          if (i < 64) { pos = (qy + (i >> 3)) * 16 + qx + (i & 7); a = pl; b = pl1; }
-          else { const int t = i - 64, cpl = t >> 4, e = t & 15; pos = 64 * cpl + ((qy >> 1) + (e >> 2)) * 8 + (qx >> 1) + (e & 3); a = pc; b = pc1; }
-          a[pos] = (uint8_t)clip255((a[pos] * w0 + b[pos] * w1 + 32) >> 6);
-        }
-        warp_sync();
-      }
-    }
-    if (lane_id() == 0)
-      for (int b = 0; b < 16; b++) {
-        const int bx = b & 3, by = b >> 2, z = ((by >> 1) * 2 + (bx >> 1)) * 4 + (by & 1) * 2 + (bx & 1);
-        const bool used = aux.ref_idx[z >> 2] >= 0;
-        s.info.mv[b][0] = used ? aux.mvd[z][0] : 0; s.info.mv[b][1] = used ? aux.mvd[z][1] : 0;
-      }
-    warp_sync();
-    if (aux.flags & DECAUX_T8) rec_luma_inter8(s, m, qp, pl);
-    else { dec_luma_coef(s, m, qp, false, nullptr); rec_luma_inter(s, pl); }
+    dec_b_mb(c, p, s, m, aux, mbx, mby, pl, pc, qp);
   } else if (type == MBT_P8x8 && (aux.flags & DECAUX_SUB)) {
     // sub-macroblock partitions (8x4, 4x8, 4x4): every partition predicts its vector from the cells decoded so far —
     // the in-macroblock cells start as "not available" and are filled in decoding order (8.4.1.3.2: a partition that
